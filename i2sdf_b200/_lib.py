@@ -1,0 +1,70 @@
+"""ctypes binding of libi2sdf_b200.so (C ABI in include/i2sdf_b200.h).  No torch types cross this boundary."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libi2sdf_b200.so")
+ABI_VERSION = 1
+
+
+class Desc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "abi_version", "hidden", "feature_size", "n_sdf_layers", "sdf_skip_layer", "multires_x", "n_color_layers",
+        "multires_d", "n_light_layers", "light_hidden", "n_samples", "n_samples_eval", "n_samples_extra",
+        "beta_iters", "max_total_iters")] + [(n, C.c_float) for n in (
+        "near_", "far_", "eps", "add_tiny", "beta_min", "lemma2_coeff")] + [
+        ("u_up", C.POINTER(C.c_float)), ("u_final", C.POINTER(C.c_float)), ("t_init", C.POINTER(C.c_float)),
+        ("extra_idx", C.POINTER(C.c_int32))]
+
+
+# every symbol include/i2sdf_b200.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "i2sdf_abi_version": (C.c_int, []),
+    "i2sdf_last_error": (C.c_char_p, []),
+    "i2sdf_create": (C.c_int, [C.POINTER(Desc), C.c_int, C.POINTER(_P)]),
+    "i2sdf_destroy": (C.c_int, [_P]),
+    "i2sdf_num_layers": (C.c_int, [_P]),
+    "i2sdf_pack_weights": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), _P]),
+    "i2sdf_workspace_bytes": (C.c_size_t, [_P, C.c_int64, C.c_int]),
+    "i2sdf_rays": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "i2sdf_sdf_forward": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "i2sdf_sampler_rounds": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P, C.c_size_t, _P]),
+    "i2sdf_sampler_finalize": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "i2sdf_sampler_info": (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_size_t, _P]),
+    "i2sdf_sampler_round_debug": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, _P, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "i2sdf_render_forward": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int, _P] + [_P] * 10 + [_P, C.c_size_t, _P, C.c_size_t, _P]),
+    "i2sdf_saved_bytes": (C.c_size_t, [_P, C.c_int64, C.c_int]),
+}
+
+_lib = None
+
+
+class I2SDFError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the CUDA library.  Fails loudly: there is no CPU fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise I2SDFError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or i2sdf_b200/csrc/build.sh).  i2sdf_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.i2sdf_abi_version() != ABI_VERSION:
+        raise I2SDFError(f"ABI mismatch: library {lib.i2sdf_abi_version()} vs binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().i2sdf_last_error().decode(errors="replace")
+        raise I2SDFError(f"{what} failed (code {rc}): {msg}")

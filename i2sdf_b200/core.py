@@ -1,0 +1,208 @@
+"""RenderCore: owns one i2sdf_handle (C ABI) on one GPU and the workspace tensors the calls need.
+
+torch is used here for device memory and streams only; every tensor is handed to the library as a raw pointer.
+"""
+import ctypes as C
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib
+from ._lib import Desc, check
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _f32(t: torch.Tensor, device) -> torch.Tensor:
+    if t.dtype != torch.float32 or t.device != device or not t.is_contiguous():
+        t = t.to(device=device, dtype=torch.float32).contiguous()
+    return t
+
+
+class RenderCore:
+    def __init__(self, model_conf: dict, device: torch.device):
+        if device.type != "cuda":
+            raise _lib.I2SDFError("i2sdf_b200 runs on CUDA devices only (no CPU fallback); move the module to a B200")
+        self.lib = _lib.load()
+        self.device = device
+        imp, ren, smp = model_conf["implicit_network"], model_conf["rendering_network"], model_conf["ray_sampler"]
+        if ren.get("mode", "nerf") != "nerf":
+            raise _lib.I2SDFError("rendering_network.mode must be 'nerf' (the only mode the shipped configs use)")
+        if imp.get("embed_type") != "positional" or ren.get("embed_type") != "positional":
+            raise _lib.I2SDFError("only embed_type 'positional' is supported")
+        dims = list(imp["dims"])
+        skip = list(imp.get("skip_in", ()))
+        if len(skip) > 1:
+            raise _lib.I2SDFError("at most one skip connection is supported")
+        light = model_conf.get("light_network")
+        fvs = model_conf["feature_vector_size"]
+        if any(d != 256 for d in dims + list(ren["dims"])) or fvs != 256:
+            raise _lib.I2SDFError("hidden width / feature_vector_size must be 256")
+        d = Desc()
+        d.abi_version = _lib.ABI_VERSION
+        d.hidden, d.feature_size = 256, fvs
+        d.n_sdf_layers, d.sdf_skip_layer, d.multires_x = len(dims) + 1, (skip[0] if skip else -1), imp["multires"]
+        d.n_color_layers, d.multires_d = len(ren["dims"]) + 1, ren["multires"]
+        d.n_light_layers = 2 if light else 0
+        d.light_hidden = light["dims"][0] if light else 128
+        d.n_samples, d.n_samples_eval, d.n_samples_extra = smp["N_samples"], smp["N_samples_eval"], smp["N_samples_extra"]
+        d.beta_iters, d.max_total_iters = smp["beta_iters"], smp["max_total_iters"]
+        d.near_ = float(smp["near"])
+        d.far_ = 2.0 * float(model_conf.get("scene_bounding_sphere", 1.0))
+        d.eps, d.add_tiny = float(smp["eps"]), float(smp.get("add_tiny", 0.0))
+        d.beta_min = float(model_conf["density"].get("beta_min", 1e-4))
+        # host tables with the reference's own torch ops so index arithmetic is bit-identical
+        # (ray_sampler.py:30, :76, :188, :225)
+        d.lemma2_coeff = float(1.0 / (4.0 * torch.log(torch.tensor(d.eps + 1.0))))
+        u_up = torch.linspace(0.0, 1.0, steps=d.n_samples_eval)
+        u_fin = torch.linspace(0.0, 1.0, steps=d.n_samples)
+        t_in = torch.linspace(0.0, 1.0, steps=d.n_samples_eval)
+        eidx = torch.stack([torch.linspace(0, d.n_samples_eval * (k + 1) - 1, d.n_samples_extra).long()
+                            for k in range(d.max_total_iters)]).to(torch.int32).contiguous()
+        self._tables = (u_up, u_fin, t_in, eidx)
+        d.u_up = C.cast(u_up.data_ptr(), C.POINTER(C.c_float))
+        d.u_final = C.cast(u_fin.data_ptr(), C.POINTER(C.c_float))
+        d.t_init = C.cast(t_in.data_ptr(), C.POINTER(C.c_float))
+        d.extra_idx = C.cast(eidx.data_ptr(), C.POINTER(C.c_int32))
+        self.desc = d
+        self.n_out = d.n_samples + 2 + d.n_samples_extra
+        h = C.c_void_p()
+        with torch.cuda.device(device):
+            check(self.lib.i2sdf_create(C.byref(d), device.index or 0, C.byref(h)), "i2sdf_create")
+        self.h = h
+        self.n_layers = self.lib.i2sdf_num_layers(h)
+        self._ws = None
+        self._ws_rays = -1
+        self._packed_refs = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.i2sdf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def workspace(self, R: int) -> torch.Tensor:
+        if self._ws is None or R > self._ws_rays:
+            nbytes = self.lib.i2sdf_workspace_bytes(self.h, R, 0)
+            self._ws = None
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._ws_rays = R
+            self._ws_bytes = nbytes
+        return self._ws
+
+    # ---- weights
+    def pack(self, weights: List[torch.Tensor], biases: List[torch.Tensor]):
+        """weights[i]: effective [out,in] fp32 weight of layer i (SDF layers, colour layers, light layers)."""
+        if len(weights) != self.n_layers or len(biases) != self.n_layers:
+            raise _lib.I2SDFError(f"expected {self.n_layers} layers, got {len(weights)}")
+        ws = [_f32(w.detach(), self.device) for w in weights]
+        bs = [_f32(b.detach(), self.device) for b in biases]
+        Wp = (C.c_void_p * self.n_layers)(*[w.data_ptr() for w in ws])
+        Bp = (C.c_void_p * self.n_layers)(*[b.data_ptr() for b in bs])
+        check(self.lib.i2sdf_pack_weights(self.h, Wp, Bp, self._stream()), "i2sdf_pack_weights")
+        self._packed_refs = (ws, bs)     # keep alive until the async pack kernels ran
+
+    # ---- entry points
+    def rays(self, uv, pose, intr):
+        uv, pose, intr = _f32(uv, self.device), _f32(pose, self.device), _f32(intr, self.device)
+        B, P, _ = uv.shape
+        o = torch.empty(B * P, 3, device=self.device)
+        d = torch.empty(B * P, 3, device=self.device)
+        dn = torch.empty(B * P, device=self.device)
+        check(self.lib.i2sdf_rays(self.h, _ptr(uv), _ptr(pose), _ptr(intr), B, P, _ptr(o), _ptr(d), _ptr(dn), self._stream()), "i2sdf_rays")
+        return o, d, dn
+
+    def sdf_forward(self, pts, want_feat=False, want_grad=False, save_act=None):
+        pts = _f32(pts, self.device)
+        M = pts.shape[0]
+        sdf = torch.empty(M, device=self.device)
+        feat = torch.empty(M, 256, device=self.device) if want_feat else None
+        grad = torch.empty(M, 3, device=self.device) if want_grad else None
+        ws = self.workspace(1)
+        check(self.lib.i2sdf_sdf_forward(self.h, _ptr(pts), M, _ptr(sdf), _ptr(feat), _ptr(grad), _ptr(save_act),
+                                         _ptr(ws), self._ws_bytes, self._stream()), "i2sdf_sdf_forward")
+        return sdf, feat, grad
+
+    def sample(self, o, d, beta_param, tape: Optional[Dict[str, torch.Tensor]] = None, want_info=False):
+        """ErrorBoundSampler.get_z_vals.  tape (training): jitter [R,128], u_final [R,64] fp32;
+        extra_perm: callable n -> LongTensor[32] (drawn after one 8-byte D2H of n) or int tensor; eik_idx [R]."""
+        R = o.shape[0]
+        tape = tape or {}
+        ws = self.workspace(R)
+        jit = _f32(tape["jitter"], self.device) if "jitter" in tape else None
+        ufin = _f32(tape["u_final"], self.device) if "u_final" in tape else None
+        st = self._stream()
+        check(self.lib.i2sdf_sampler_rounds(self.h, _ptr(o), _ptr(d), R, _ptr(beta_param), _ptr(jit), _ptr(ufin),
+                                            _ptr(ws), self._ws_bytes, st), "i2sdf_sampler_rounds")
+        info = torch.zeros(2, dtype=torch.int32, device=self.device)
+        extra = None
+        if "extra_perm" in tape:
+            ep = tape["extra_perm"]
+            if callable(ep):
+                check(self.lib.i2sdf_sampler_info(self.h, R, _ptr(beta_param), _ptr(info), _ptr(ws), self._ws_bytes, st), "i2sdf_sampler_info")
+                ep = ep(int(info[1].item()))
+            extra = ep.to(device=self.device, dtype=torch.int32).contiguous()
+        eik = tape["eik_idx"].to(device=self.device, dtype=torch.int32).contiguous() if "eik_idx" in tape else None
+        if callable(tape.get("eik_idx_fn")):
+            eik = tape["eik_idx_fn"]().to(device=self.device, dtype=torch.int32).contiguous()
+        z = torch.empty(R, self.n_out, device=self.device)
+        z_eik = torch.empty(R, device=self.device) if eik is not None else None
+        check(self.lib.i2sdf_sampler_finalize(self.h, R, _ptr(beta_param), _ptr(extra), _ptr(eik), _ptr(z), _ptr(z_eik),
+                                              _ptr(info), _ptr(ws), self._ws_bytes, st), "i2sdf_sampler_finalize")
+        if want_info:
+            return z, z_eik, info
+        return z, z_eik
+
+    def sampler_round_debug(self, z, sdf, beta_param, beta_in, upsample: bool, u_tape=None):
+        R, n = z.shape
+        ns = self.desc.n_samples_eval if upsample else self.desc.n_samples
+        dev = self.device
+        out = dict(beta=torch.empty(R, device=dev), cdf=torch.empty(R, n, device=dev),
+                   inds=torch.empty(R, ns, dtype=torch.int32, device=dev), samples=torch.empty(R, ns, device=dev))
+        if upsample:
+            out["z_merged"] = torch.empty(R, n + ns, device=dev)
+            out["src"] = torch.empty(R, n + ns, dtype=torch.int32, device=dev)
+        check(self.lib.i2sdf_sampler_round_debug(
+            self.h, _ptr(_f32(z, dev)), _ptr(_f32(sdf, dev)), R, n, _ptr(beta_param), _ptr(_f32(beta_in, dev)), int(upsample),
+            _ptr(None if u_tape is None else _f32(u_tape, dev)), _ptr(out["beta"]), _ptr(out["cdf"]), _ptr(out["inds"]),
+            _ptr(out["samples"]), _ptr(out.get("z_merged")), _ptr(out.get("src")), self._stream()), "i2sdf_sampler_round_debug")
+        return out
+
+    def render(self, o, d, dnorm, z, beta_param, want_normal=True, want_light=False, per_sample=False, save=None):
+        """Main pass + compositing.  z [R,N+1].  Returns dict of per-ray tensors (+ per-sample ones if asked)."""
+        R, N1 = z.shape
+        N = N1 - 1
+        dev = self.device
+        ws = self.workspace(R)
+        out = dict(rgb=torch.empty(R, 3, device=dev), depth=torch.empty(R, device=dev), weight_sum=torch.empty(R, device=dev))
+        if want_normal:
+            out["normal"] = torch.empty(R, 3, device=dev)
+        if want_light:
+            out["light"] = torch.empty(R, device=dev)
+        ps = {}
+        if per_sample:
+            ps = dict(s_sdf=torch.empty(R * N, device=dev), s_rgb=torch.empty(R * N, 3, device=dev), s_w=torch.empty(R * N, device=dev))
+            if want_normal:
+                ps["s_grad"] = torch.empty(R * N, 3, device=dev)
+            if want_light:
+                ps["s_light"] = torch.empty(R * N, device=dev)
+        save_bytes = 0 if save is None else save.numel() * save.element_size()
+        check(self.lib.i2sdf_render_forward(
+            self.h, _ptr(o), _ptr(d), _ptr(dnorm), _ptr(_f32(z, dev)), R, N, _ptr(beta_param),
+            _ptr(out["rgb"]), _ptr(out["depth"]), _ptr(out["weight_sum"]), _ptr(out.get("normal")), _ptr(out.get("light")),
+            _ptr(ps.get("s_sdf")), _ptr(ps.get("s_grad")), _ptr(ps.get("s_rgb")), _ptr(ps.get("s_w")), _ptr(ps.get("s_light")),
+            _ptr(save), save_bytes, _ptr(ws), self._ws_bytes, self._stream()), "i2sdf_render_forward")
+        out.update(ps)
+        return out

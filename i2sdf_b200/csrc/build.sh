@@ -1,0 +1,15 @@
+#!/bin/bash
+# Build libi2sdf_b200.so in-tree for sm_100a.  Usage: build.sh [outdir]
+set -e
+HERE="$(cd "$(dirname "$0")" && pwd)"
+OUT="${1:-$HERE/..}"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+ARCH="-gencode arch=compute_100a,code=sm_100a"
+COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC $ARCH"
+mkdir -p "$HERE/build"
+$NVCC $COMMON -Xptxas -v -c "$HERE/mlp_simt.cu" -o "$HERE/build/mlp_simt.o" 2> "$HERE/build/mlp_simt.ptxas.txt"
+$NVCC $COMMON -Xptxas -v -c "$HERE/mlp_tc.cu" -o "$HERE/build/mlp_tc.o" 2> "$HERE/build/mlp_tc.ptxas.txt"
+$NVCC $COMMON -fmad=false -Xptxas -v -c "$HERE/sampler.cu" -o "$HERE/build/sampler.o" 2> "$HERE/build/sampler.ptxas.txt"
+$NVCC $COMMON -c "$HERE/c_abi.cu" -o "$HERE/build/c_abi.o"
+$NVCC -shared $ARCH -o "$OUT/libi2sdf_b200.so" "$HERE/build/mlp_simt.o" "$HERE/build/mlp_tc.o" "$HERE/build/sampler.o" "$HERE/build/c_abi.o" -lcudart
+echo "built $OUT/libi2sdf_b200.so"

@@ -1,0 +1,370 @@
+// C-ABI of the i2sdf_b200 core (include/i2sdf_b200.h): handle life-cycle, weight packing, entry points.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace i2sdf {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// declared in sampler.cu
+int launch_rays(const float*, const float*, const float*, int, int, float*, float*, float*, cudaStream_t);
+size_t sampler_ws_floats(const i2sdf_handle*, long long);
+SamplerWs carve_sampler_ws(const i2sdf_handle*, long long, float*);
+int launch_sampler_init(const i2sdf_handle*, const SamplerWs&, long long, const float*, float, cudaStream_t);
+int launch_sampler_round(const i2sdf_handle*, const SamplerWs&, long long, int, int, const float*, const float*, cudaStream_t);
+int launch_sampler_finalize(const i2sdf_handle*, const SamplerWs&, long long, const float*, const int*, const int*, float*,
+                            float*, int*, cudaStream_t);
+int launch_sampler_round_debug(const i2sdf_handle*, const float*, const float*, long long, int, const float*, const float*, int,
+                               const float*, float*, float*, int*, float*, float*, int*, cudaStream_t);
+int launch_composite(const i2sdf_handle*, const float*, const float*, const float*, const float*, const float*, const float*,
+                     const float*, long long, int, float*, float*, float*, float*, float*, float*, cudaStream_t);
+// declared in mlp_tc.cu
+int tc_create(i2sdf_handle* h);
+void tc_destroy(i2sdf_handle* h);
+int tc_pack(i2sdf_handle* h, const float* const* W, const float* const* b, cudaStream_t st);
+int tc_launch_sdf(const i2sdf_handle* h, const MlpParams& p, cudaStream_t st);
+
+// ---- packing ------------------------------------------------------------------------------------
+enum { PACK_T = 0, PACK_R = 1, PACK_V = 2 };
+struct PackJob {
+    int mode;
+    float* dst;
+    int rows, ld;          // dst is [rows][ld]
+    const float* src;
+    int out, in;           // src is [out][in] (or a vector of `out`)
+    int row_off;           // PACK_T: feature f reads src row f+row_off ; PACK_V: element offset
+    int nvalid;            // number of valid features / elements
+    int feat_first;        // PACK_T colour layer 0: k<feat_first -> col ed+k ; k-feat_first<ed -> col k-feat_first
+    int ed;
+};
+
+__global__ void pack_kernel(PackJob J) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long n = (long long)J.rows * J.ld;
+    if (i >= n) return;
+    int k = (int)(i / J.ld), f = (int)(i % J.ld);
+    float v = 0.f;
+    if (J.mode == PACK_T) {
+        int col = -1;
+        if (J.feat_first > 0) {
+            if (k < J.feat_first) col = J.ed + k;
+            else if (k - J.feat_first < J.ed) col = k - J.feat_first;
+        } else if (k < J.in) col = k;
+        if (col >= 0 && col < J.in && f < J.nvalid) v = J.src[(size_t)(f + J.row_off) * J.in + col];
+    } else if (J.mode == PACK_R) {
+        if (k < J.out && f < J.in) v = J.src[(size_t)k * J.in + f];
+    } else {
+        if (f < J.nvalid) v = J.src[J.row_off + f];
+    }
+    J.dst[i] = v;
+}
+
+static int run_pack(const PackJob& J, cudaStream_t st) {
+    long long n = (long long)J.rows * J.ld;
+    pack_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(J);
+    I2SDF_CUDA_CHECK(cudaGetLastError());
+    return I2SDF_OK;
+}
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace i2sdf
+
+using namespace i2sdf;
+
+extern "C" {
+
+int i2sdf_abi_version(void) { return I2SDF_ABI_VERSION; }
+const char* i2sdf_last_error(void) { return g_err; }
+
+int i2sdf_create(const i2sdf_desc* d, int device, i2sdf_handle** out) {
+    if (!d || !out) { set_error("null argument"); return I2SDF_E_INVALID; }
+    if (d->abi_version != I2SDF_ABI_VERSION) { set_error("ABI version mismatch (%d vs %d)", d->abi_version, I2SDF_ABI_VERSION); return I2SDF_E_INVALID; }
+    if (d->hidden != 256 || d->feature_size != 256) { set_error("only hidden=256 / feature_vector_size=256 networks are supported (got %d/%d)", d->hidden, d->feature_size); return I2SDF_E_INVALID; }
+    const int ex = 3 + 6 * d->multires_x, ed = 3 + 6 * d->multires_d;
+    if (d->n_sdf_layers < 3 || d->n_sdf_layers > kMaxLayers || d->n_color_layers < 2 || d->n_color_layers > kMaxLayers) { set_error("layer counts out of range"); return I2SDF_E_INVALID; }
+    if (ex > 39 || ed > 39) { set_error("multires > 6 unsupported"); return I2SDF_E_INVALID; }
+    if (d->sdf_skip_layer != -1 && (d->sdf_skip_layer < 1 || d->sdf_skip_layer > d->n_sdf_layers - 2)) { set_error("skip layer %d unsupported", d->sdf_skip_layer); return I2SDF_E_INVALID; }
+    if (d->n_light_layers != 0 && (d->n_light_layers != 2 || d->light_hidden != 128)) { set_error("light head must be [256,128,1]"); return I2SDF_E_INVALID; }
+    if (d->n_samples_eval != 128 || d->n_samples + 2 + d->n_samples_extra > 128 || d->max_total_iters > 5 || d->max_total_iters < 1) { set_error("sampler sizes unsupported (N_samples_eval must be 128, N_samples+2+N_extra <= 128, max_total_iters <= 5)"); return I2SDF_E_INVALID; }
+    if (!d->u_up || !d->u_final || !d->t_init || !d->extra_idx) { set_error("sampler tables missing"); return I2SDF_E_INVALID; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device"); return I2SDF_E_NOGPU; }
+    cudaDeviceProp prop;
+    I2SDF_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) { set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return I2SDF_E_NOGPU; }
+    I2SDF_CUDA_CHECK(cudaSetDevice(device));
+
+    i2sdf_handle* h = (i2sdf_handle*)calloc(1, sizeof(i2sdf_handle));
+    h->desc = *d;
+    h->desc.u_up = h->desc.u_final = h->desc.t_init = nullptr; h->desc.extra_idx = nullptr;
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    NetDev& n = h->net;
+    n.L = d->n_sdf_layers; n.skip = d->sdf_skip_layer; n.mx = d->multires_x; n.ex = ex; n.exp_ = round_up(ex, 8);
+    n.Lc = d->n_color_layers; n.md = d->multires_d; n.ed = ed; n.Ll = d->n_light_layers; n.lh = d->light_hidden;
+    // layer shapes in API order
+    int li = 0;
+    for (int l = 0; l < n.L; ++l, ++li) {
+        int in = (l == 0) ? ex : 256;
+        int outd = (l == n.L - 1) ? 257 : ((l + 1 == n.skip) ? 256 - ex : 256);
+        h->lay_out[li] = outd; h->lay_in[li] = in;
+    }
+    for (int l = 0; l < n.Lc; ++l, ++li) { h->lay_out[li] = (l == n.Lc - 1) ? 3 : 256; h->lay_in[li] = (l == 0) ? 256 + ed : 256; }
+    for (int l = 0; l < n.Ll; ++l, ++li) { h->lay_out[li] = (l == 0) ? n.lh : 1; h->lay_in[li] = (l == 0) ? 256 : n.lh; }
+    h->n_layers = li;
+
+    // pool layout
+    size_t off = 0;
+    auto take = [&](size_t nfloats) { size_t o = off; off += (nfloats + 63) / 64 * 64; return o; };
+    size_t o_wt[kMaxLayers], o_wr[kMaxLayers], o_b[kMaxLayers], o_cwt[kMaxLayers], o_cb[kMaxLayers];
+    for (int l = 0; l < n.L; ++l) {
+        n.sdf_kpad[l] = (l == 0) ? n.exp_ : 256;
+        o_wt[l] = take((size_t)n.sdf_kpad[l] * 256);
+        o_wr[l] = take((size_t)256 * (l == 0 ? 64 : 256));
+        o_b[l] = take(256);
+    }
+    size_t o_head = take(320);
+    for (int l = 0; l < n.Lc - 1; ++l) {
+        n.col_kpad[l] = (l == 0) ? round_up(256 + ed, 4) : 256;
+        o_cwt[l] = take((size_t)n.col_kpad[l] * 256);
+        o_cb[l] = take(256);
+    }
+    size_t o_chead = take(3 * 256 + 64);
+    size_t o_lwt = take(256 * 128), o_lb = take(128), o_lhead = take(192);
+    const int ne = d->n_samples_extra, mi = d->max_total_iters;
+    size_t o_uup = take(d->n_samples_eval), o_ufin = take(d->n_samples), o_tin = take(d->n_samples_eval), o_eidx = take((size_t)mi * ne);
+    h->pool_floats = off;
+    if (cudaMalloc(&h->pool, off * sizeof(float)) != cudaSuccess) { free(h); set_error("cudaMalloc of %zu bytes failed", off * sizeof(float)); return I2SDF_E_CUDA; }
+    cudaMemset(h->pool, 0, off * sizeof(float));
+    for (int l = 0; l < n.L; ++l) { n.sdf_wt[l] = h->pool + o_wt[l]; n.sdf_wr[l] = h->pool + o_wr[l]; n.sdf_b[l] = h->pool + o_b[l]; }
+    n.sdf_head = h->pool + o_head;
+    for (int l = 0; l < n.Lc - 1; ++l) { n.col_wt[l] = h->pool + o_cwt[l]; n.col_b[l] = h->pool + o_cb[l]; }
+    n.col_head = h->pool + o_chead;
+    n.light_wt0 = h->pool + o_lwt; n.light_b0 = h->pool + o_lb; n.light_head = h->pool + o_lhead;
+    SamplerDev& s = h->smp;
+    s.n_samples = d->n_samples; s.n_eval = d->n_samples_eval; s.n_extra = ne; s.beta_iters = d->beta_iters; s.max_iters = mi;
+    s.near_ = d->near_; s.far_ = d->far_; s.eps = d->eps; s.add_tiny = d->add_tiny; s.beta_min = d->beta_min;
+    s.u_up = h->pool + o_uup; s.u_final = h->pool + o_ufin; s.t_init = h->pool + o_tin; s.extra_idx = reinterpret_cast<int*>(h->pool + o_eidx);
+    cudaMemcpy(h->pool + o_uup, d->u_up, sizeof(float) * d->n_samples_eval, cudaMemcpyHostToDevice);
+    cudaMemcpy(h->pool + o_ufin, d->u_final, sizeof(float) * d->n_samples, cudaMemcpyHostToDevice);
+    cudaMemcpy(h->pool + o_tin, d->t_init, sizeof(float) * d->n_samples_eval, cudaMemcpyHostToDevice);
+    cudaMemcpy(h->pool + o_eidx, d->extra_idx, sizeof(int) * mi * ne, cudaMemcpyHostToDevice);
+    const char* env = getenv("I2SDF_SIMT");
+    h->use_tc = !(env && env[0] == '1');
+    h->tc = nullptr;
+    if (h->use_tc) {
+        int rc = tc_create(h);
+        if (rc != I2SDF_OK) { cudaFree(h->pool); free(h); return rc; }
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { set_error("create: %s", cudaGetErrorString(e)); cudaFree(h->pool); free(h); return I2SDF_E_CUDA; }
+    *out = h;
+    return I2SDF_OK;
+}
+
+int i2sdf_destroy(i2sdf_handle* h) {
+    if (!h) return I2SDF_OK;
+    if (h->tc) tc_destroy(h);
+    cudaFree(h->pool);
+    free(h);
+    return I2SDF_OK;
+}
+
+int i2sdf_num_layers(const i2sdf_handle* h) { return h ? h->n_layers : 0; }
+
+int i2sdf_pack_weights(i2sdf_handle* h, const float* const* W, const float* const* b, void* stream) {
+    if (!h || !W || !b) { set_error("null argument"); return I2SDF_E_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const NetDev& n = h->net;
+    int li = 0, rc;
+    for (int l = 0; l < n.L; ++l, ++li) {
+        const int outd = h->lay_out[li], in = h->lay_in[li];
+        const bool last = (l == n.L - 1);
+        PackJob J{};
+        J.mode = PACK_T; J.dst = (float*)n.sdf_wt[l]; J.rows = n.sdf_kpad[l]; J.ld = 256; J.src = W[li]; J.out = outd; J.in = in;
+        J.row_off = last ? 1 : 0; J.nvalid = last ? 256 : outd;
+        if ((rc = run_pack(J, st))) return rc;
+        PackJob R{};
+        R.mode = PACK_R; R.dst = (float*)n.sdf_wr[l]; R.rows = 256; R.ld = (l == 0) ? 64 : 256; R.src = W[li]; R.out = last ? 1 : outd; R.in = in;
+        if ((rc = run_pack(R, st))) return rc;
+        PackJob V{};
+        V.mode = PACK_V; V.dst = (float*)n.sdf_b[l]; V.rows = 1; V.ld = 256; V.src = b[li]; V.row_off = last ? 1 : 0; V.nvalid = last ? 256 : outd;
+        if ((rc = run_pack(V, st))) return rc;
+        if (last) {
+            PackJob H{}; H.mode = PACK_V; H.dst = (float*)n.sdf_head; H.rows = 1; H.ld = 256; H.src = W[li]; H.row_off = 0; H.nvalid = 256;
+            if ((rc = run_pack(H, st))) return rc;
+            PackJob HB{}; HB.mode = PACK_V; HB.dst = (float*)n.sdf_head + 256; HB.rows = 1; HB.ld = 1; HB.src = b[li]; HB.row_off = 0; HB.nvalid = 1;
+            if ((rc = run_pack(HB, st))) return rc;
+        }
+    }
+    for (int l = 0; l < n.Lc; ++l, ++li) {
+        const int outd = h->lay_out[li], in = h->lay_in[li];
+        if (l < n.Lc - 1) {
+            PackJob J{};
+            J.mode = PACK_T; J.dst = (float*)n.col_wt[l]; J.rows = n.col_kpad[l]; J.ld = 256; J.src = W[li]; J.out = outd; J.in = in; J.nvalid = outd;
+            if (l == 0) { J.feat_first = 256; J.ed = n.ed; }
+            if ((rc = run_pack(J, st))) return rc;
+            PackJob V{}; V.mode = PACK_V; V.dst = (float*)n.col_b[l]; V.rows = 1; V.ld = 256; V.src = b[li]; V.nvalid = outd;
+            if ((rc = run_pack(V, st))) return rc;
+        } else {
+            PackJob H{}; H.mode = PACK_V; H.dst = (float*)n.col_head; H.rows = 1; H.ld = 768; H.src = W[li]; H.nvalid = 768;
+            if ((rc = run_pack(H, st))) return rc;
+            PackJob HB{}; HB.mode = PACK_V; HB.dst = (float*)n.col_head + 768; HB.rows = 1; HB.ld = 3; HB.src = b[li]; HB.nvalid = 3;
+            if ((rc = run_pack(HB, st))) return rc;
+        }
+    }
+    if (n.Ll == 2) {
+        PackJob J{};
+        J.mode = PACK_T; J.dst = (float*)n.light_wt0; J.rows = 256; J.ld = 128; J.src = W[li]; J.out = n.lh; J.in = 256; J.nvalid = n.lh;
+        if ((rc = run_pack(J, st))) return rc;
+        PackJob V{}; V.mode = PACK_V; V.dst = (float*)n.light_b0; V.rows = 1; V.ld = 128; V.src = b[li]; V.nvalid = n.lh;
+        if ((rc = run_pack(V, st))) return rc;
+        ++li;
+        PackJob H{}; H.mode = PACK_V; H.dst = (float*)n.light_head; H.rows = 1; H.ld = 128; H.src = W[li]; H.nvalid = n.lh;
+        if ((rc = run_pack(H, st))) return rc;
+        PackJob HB{}; HB.mode = PACK_V; HB.dst = (float*)n.light_head + n.lh; HB.rows = 1; HB.ld = 1; HB.src = b[li]; HB.nvalid = 1;
+        if ((rc = run_pack(HB, st))) return rc;
+        ++li;
+    }
+    if (h->use_tc && (rc = tc_pack(h, W, b, st))) return rc;
+    return I2SDF_OK;
+}
+
+// workspace = [ sampler state | mlp scratch | per-sample temporaries (8 floats x R x 128) ]
+static size_t ws_sampler_floats(const i2sdf_handle* h, int64_t R) { return (sampler_ws_floats(h, R) + 63) / 64 * 64; }
+static size_t ws_scratch_floats(const i2sdf_handle* h) { return (mlp_simt_scratch_floats(h) + 63) / 64 * 64; }
+
+size_t i2sdf_workspace_bytes(const i2sdf_handle* h, int64_t R, int training) {
+    (void)training;
+    if (!h || R < 0) return 0;
+    return (ws_sampler_floats(h, R) + ws_scratch_floats(h) + (size_t)R * 128 * 8 + 64) * sizeof(float);
+}
+
+int i2sdf_rays(i2sdf_handle* h, const float* uv, const float* pose, const float* intr, int B, int P, float* o, float* d,
+               float* dnorm, void* stream) {
+    if (!h || !uv || !pose || !intr || !o || !d || !dnorm) { set_error("null argument"); return I2SDF_E_INVALID; }
+    return launch_rays(uv, pose, intr, B, P, o, d, dnorm, (cudaStream_t)stream);
+}
+
+static int run_mlp(const i2sdf_handle* h, const MlpParams& p, cudaStream_t st) {
+    const bool sdf_only = !p.out_feat && !p.out_grad && !p.want_color && !p.want_light && !p.save_act;
+    if (h->use_tc && sdf_only) return tc_launch_sdf(h, p, st);
+    return launch_mlp_simt(h, p, st);
+}
+
+int i2sdf_sdf_forward(i2sdf_handle* h, const float* pts, int64_t M, float* out_sdf, float* out_feat, float* out_grad,
+                      float* save_act, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h || !pts || !out_sdf) { set_error("null argument"); return I2SDF_E_INVALID; }
+    MlpParams p{};
+    p.pts = pts; p.M = M; p.ns = 1; p.round_idx = -1; p.beta_min = h->smp.beta_min;
+    p.out_sdf = out_sdf; p.out_feat = out_feat; p.out_grad = out_grad; p.save_act = save_act;
+    if (out_grad && !save_act) {
+        if (!workspace || workspace_bytes < ws_scratch_floats(h) * sizeof(float)) { set_error("sdf_forward: workspace too small"); return I2SDF_E_WORKSPACE; }
+        p.scratch = (float*)workspace;
+    }
+    p.net = h->net;
+    return run_mlp(h, p, (cudaStream_t)stream);
+}
+
+int i2sdf_sampler_rounds(i2sdf_handle* h, const float* o, const float* d, int64_t R, const float* beta_param,
+                         const float* jitter, const float* u_final, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h || !o || !d || !beta_param || !workspace) { set_error("null argument"); return I2SDF_E_INVALID; }
+    if (workspace_bytes < i2sdf_workspace_bytes(h, R, 0)) { set_error("sampler: workspace too small"); return I2SDF_E_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    SamplerWs W = carve_sampler_ws(h, R, (float*)workspace);
+    int rc;
+    if ((rc = launch_sampler_init(h, W, R, jitter, h->desc.lemma2_coeff, st))) return rc;
+    for (int k = 0; k < h->smp.max_iters; ++k) {
+        MlpParams p{};
+        p.ray_o = o; p.ray_d = d; p.zarr = W.samples; p.zstride = h->smp.n_eval; p.ns = h->smp.n_eval;
+        p.M = (long long)R * h->smp.n_eval; p.out_sdf = W.sdf_new;
+        p.beta_max = W.beta_max; p.beta_param = beta_param; p.beta_min = h->smp.beta_min; p.round_idx = k;
+        p.net = h->net;
+        if ((rc = run_mlp(h, p, st))) return rc;
+        if ((rc = launch_sampler_round(h, W, R, k, 0, beta_param, nullptr, st))) return rc;
+        if ((rc = launch_sampler_round(h, W, R, k, 1, beta_param, u_final, st))) return rc;
+    }
+    return I2SDF_OK;
+}
+
+int i2sdf_sampler_finalize(i2sdf_handle* h, int64_t R, const float* beta_param, const int32_t* extra_idx, const int32_t* eik_idx,
+                           float* out_z, float* out_z_eik, int32_t* out_info, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h || !beta_param || !out_z || !workspace) { set_error("null argument"); return I2SDF_E_INVALID; }
+    if (workspace_bytes < i2sdf_workspace_bytes(h, R, 0)) { set_error("sampler: workspace too small"); return I2SDF_E_WORKSPACE; }
+    SamplerWs W = carve_sampler_ws(h, R, (float*)workspace);
+    return launch_sampler_finalize(h, W, R, beta_param, extra_idx, eik_idx, out_z, out_z_eik, out_info, (cudaStream_t)stream);
+}
+
+__global__ void sampler_info_kernel(SamplerDev S, const float* beta_max, const float* beta_param, int* info) {
+    float b0 = fabsf(*beta_param) + S.beta_min;
+    int klast = 0;
+    while (klast + 1 < S.max_iters && (beta_max[klast] > b0)) ++klast;
+    info[0] = klast + 1;
+    info[1] = S.n_eval * (klast + 1);
+}
+
+int i2sdf_sampler_info(i2sdf_handle* h, int64_t R, const float* beta_param, int32_t* out_info, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+    if (!h || !beta_param || !out_info || !workspace) { set_error("null argument"); return I2SDF_E_INVALID; }
+    if (workspace_bytes < i2sdf_workspace_bytes(h, R, 0)) { set_error("sampler: workspace too small"); return I2SDF_E_WORKSPACE; }
+    SamplerWs W = carve_sampler_ws(h, R, (float*)workspace);
+    sampler_info_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(h->smp, W.beta_max, beta_param, out_info);
+    I2SDF_CUDA_CHECK(cudaGetLastError());
+    return I2SDF_OK;
+}
+
+int i2sdf_sampler_round_debug(i2sdf_handle* h, const float* z, const float* sdf, int64_t R, int n, const float* beta_param,
+                              const float* beta_in, int force_upsample, const float* u_tape, float* out_beta, float* out_cdf,
+                              int32_t* out_inds, float* out_samples, float* out_z_merged, int32_t* out_src, void* stream) {
+    if (!h || !z || !sdf || !beta_param || !beta_in || !out_samples) { set_error("null argument"); return I2SDF_E_INVALID; }
+    if (n < 2 || n > h->smp.n_eval * h->smp.max_iters) { set_error("round_debug: n=%d out of range", n); return I2SDF_E_INVALID; }
+    return launch_sampler_round_debug(h, z, sdf, R, n, beta_param, beta_in, force_upsample, u_tape, out_beta, out_cdf, out_inds,
+                                      out_samples, out_z_merged, out_src, (cudaStream_t)stream);
+}
+
+size_t i2sdf_saved_bytes(const i2sdf_handle* h, int64_t R, int N) {
+    if (!h) return 0;
+    return (size_t)(h->net.L - 1) * (size_t)R * N * 256 * sizeof(float);
+}
+
+int i2sdf_render_forward(i2sdf_handle* h, const float* o, const float* d, const float* dnorm, const float* z, int64_t R, int N,
+                         const float* beta_param, float* rgb, float* depth, float* weight_sum, float* normal, float* light,
+                         float* s_sdf, float* s_grad, float* s_rgb, float* s_w, float* s_light, void* save, size_t save_bytes,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h || !o || !d || !dnorm || !z || !beta_param || !workspace) { set_error("null argument"); return I2SDF_E_INVALID; }
+    if (N < 1 || N > 128) { set_error("render_forward: N=%d samples per ray unsupported (1..128)", N); return I2SDF_E_INVALID; }
+    if (workspace_bytes < i2sdf_workspace_bytes(h, R, 0)) { set_error("render_forward: workspace too small"); return I2SDF_E_WORKSPACE; }
+    if (light && h->net.Ll == 0) { set_error("render_forward: light output requested but the network has no light head"); return I2SDF_E_INVALID; }
+    if (save && save_bytes < i2sdf_saved_bytes(h, R, N)) { set_error("render_forward: save buffer too small"); return I2SDF_E_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    float* base = (float*)workspace;
+    float* scratch = base + ws_sampler_floats(h, R);
+    float* tmp = scratch + ws_scratch_floats(h);
+    const size_t RN = (size_t)R * N;
+    if (!s_sdf) s_sdf = tmp;
+    if (!s_grad && normal) s_grad = tmp + (size_t)R * 128;
+    if (!s_rgb && rgb) s_rgb = tmp + (size_t)R * 128 * 4;
+    if (!s_light && light) s_light = tmp + (size_t)R * 128 * 7;
+    (void)RN;
+    MlpParams p{};
+    p.ray_o = o; p.ray_d = d; p.zarr = z; p.zstride = N + 1; p.ns = N; p.M = (long long)R * N; p.round_idx = -1;
+    p.beta_min = h->smp.beta_min;
+    p.out_sdf = s_sdf; p.out_grad = s_grad; p.out_rgb = s_rgb; p.out_light = s_light;
+    p.want_color = s_rgb != nullptr; p.want_light = s_light != nullptr;
+    p.save_act = (float*)save; p.scratch = scratch;
+    p.net = h->net;
+    int rc = run_mlp(h, p, st);
+    if (rc) return rc;
+    return launch_composite(h, z, dnorm, s_sdf, s_rgb, s_grad, s_light, beta_param, R, N, rgb, depth, weight_sum, normal, light, s_w, st);
+}
+
+}  // extern "C"

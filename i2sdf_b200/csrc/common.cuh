@@ -1,0 +1,123 @@
+// Shared declarations of the i2sdf_b200 CUDA core (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/i2sdf_b200.h"
+
+namespace i2sdf {
+
+constexpr int kMaxLayers = 12;
+constexpr int kHidden = 256;
+
+// Packed device-side network (fp32 SIMT layouts).  All pointers are device memory owned by the handle.
+struct NetDev {
+    int L;            // SDF linear layers
+    int skip;         // skip layer index or -1
+    int mx, ex;       // multires of points, embedding width (3+6*mx)
+    int exp_;         // ex padded to a multiple of 8
+    int Lc;           // colour linear layers
+    int md, ed;       // multires of dirs, embedding width
+    int Ll;           // light layers (0 or 2)
+    int lh;           // light hidden (128)
+    // SDF net
+    const float* sdf_wt[kMaxLayers];   // forward, k-major [kpad][256]; last layer: feature rows (W[1:])
+    int sdf_kpad[kMaxLayers];
+    const float* sdf_wr[kMaxLayers];   // reverse sweep, row-major [256][ldr] (ldr = 256, layer 0: 64)
+    const float* sdf_b[kMaxLayers];    // [256] (last layer: b[1:])
+    const float* sdf_head;             // [257]: W_last[0,:], then b_last[0]
+    // colour net (input rows reordered: [feat(256) | PE(d)(ed) | 0-pad])
+    const float* col_wt[kMaxLayers];
+    int col_kpad[kMaxLayers];
+    const float* col_b[kMaxLayers];
+    const float* col_head;             // [3][256] then [3] bias
+    // light head
+    const float* light_wt0;            // [256][128] k-major
+    const float* light_b0;             // [128]
+    const float* light_head;           // [128] then bias
+};
+
+struct SamplerDev {
+    int n_samples, n_eval, n_extra, beta_iters, max_iters;
+    float near_, far_, eps, add_tiny, beta_min;
+    const float* u_up;       // [n_eval]
+    const float* u_final;    // [n_samples]
+    const float* t_init;     // [n_eval]
+    const int* extra_idx;    // [max_iters][n_extra]
+};
+
+}  // namespace i2sdf
+
+struct i2sdf_handle {
+    i2sdf_desc desc;
+    int device;
+    int num_sms;
+    i2sdf::NetDev net;
+    i2sdf::SamplerDev smp;
+    float* pool;             // one allocation for all packed weights / tables
+    size_t pool_floats;
+    // layer bookkeeping for pack_weights: (out,in) of every layer in API order
+    int n_layers;
+    int lay_out[2 * i2sdf::kMaxLayers + 4];
+    int lay_in[2 * i2sdf::kMaxLayers + 4];
+    bool use_tc;             // tcgen05 path available (set by env I2SDF_SIMT=1 -> false)
+    void* tc;                // opaque tcgen05 packed state (see mlp_tc.cu)
+};
+
+namespace i2sdf {
+
+void set_error(const char* fmt, ...);
+
+#define I2SDF_CUDA_CHECK(expr)                                                                 \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            i2sdf::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return I2SDF_E_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+// ---- SIMT fused MLP (mlp_simt.cu) ----------------------------------------------------------------
+struct MlpParams {
+    // point source: explicit pts, or rays: point m = (ray m / ns, sample m % ns) -> o + z * d
+    const float* pts;
+    const float* ray_o;
+    const float* ray_d;
+    const float* zarr;
+    int zstride;
+    int ns;
+    long long M;
+    // predication for sampler rounds: run only if round_idx < 0 or all beta_max[j] > beta0 for j < round_idx
+    const float* beta_max;    // device [max_iters]
+    const float* beta_param;  // device scalar (raw density.beta)
+    float beta_min;
+    int round_idx;
+    // outputs (null = skip)
+    float* out_sdf;
+    float* out_feat;
+    float* out_grad;
+    float* out_rgb;
+    float* out_light;
+    float* save_act;          // [L-1][M][256] pre-activations (training) or null
+    float* scratch;           // per-CTA [(L-1)][TM][256] when grad wanted without save_act
+    int want_color;
+    int want_light;
+    NetDev net;
+};
+
+int launch_mlp_simt(const i2sdf_handle* h, const MlpParams& p, cudaStream_t stream);
+size_t mlp_simt_scratch_floats(const i2sdf_handle* h);
+
+// ---- sampler / compositing (sampler.cu) -----------------------------------------------------------
+struct SamplerWs {            // carved from the caller's workspace
+    float* z[2];              // [R][zmax] ping-pong sorted z
+    float* sdf[2];            // [R][zmax]
+    float* samples;           // [R][n_eval] new samples of the round (unsorted order = inverse-CDF order)
+    float* sdf_new;           // [R][n_eval]
+    int* src;                 // [R][zmax] merge source index
+    float* beta;              // [R]
+    float* beta_max;          // [max_iters]  (atomicMax as int)
+    int zmax;
+};
+
+}  // namespace i2sdf

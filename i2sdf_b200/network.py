@@ -1,0 +1,412 @@
+"""Drop-in mirror of the reference's `model.network` surface, backed by the sm_100a kernels.
+
+    from i2sdf_b200.network import I2SDFNetwork, I2SDFLoss        # instead of `from model.network import ...`
+
+Same constructor node (`conf.model`), same sub-module / parameter names and shapes (so reference checkpoints load
+with strict=True), same `forward(input, predict_only=False) -> dict` keys and shapes
+(reference: model/network/__init__.py:19-221, mlp.py:10-229, density.py:5-30, ray_sampler.py:46-65).
+The modules below only HOLD parameters and describe the network; all arithmetic of the per-ray path runs in
+libi2sdf_b200.so through i2sdf_b200.core.RenderCore.  There is no PyTorch/CPU fallback: on a non-CUDA device
+forward raises.
+"""
+import math
+import weakref
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ._lib import I2SDFError
+from .core import RenderCore
+
+
+def _get(conf, key, default=None):
+    if isinstance(conf, dict):
+        return conf.get(key, default)
+    return getattr(conf, key, default)
+
+
+def _plain(conf):
+    """CfgNode / dict / namespace -> plain nested dict."""
+    if isinstance(conf, dict):
+        return {k: _plain(v) for k, v in conf.items()}
+    if isinstance(conf, (list, tuple)):
+        return [_plain(v) for v in conf]
+    if hasattr(conf, "__dict__") and not isinstance(conf, (int, float, str, bool)):
+        return {k: _plain(v) for k, v in vars(conf).items() if not k.startswith("_")}
+    return conf
+
+
+def _embed_width(multires, d_in=3):
+    return d_in + 2 * multires * d_in
+
+
+def _make_linear(n_in, n_out, init=None, *, geo_bias=0.0, n_embed=0, use_weight_norm=True):
+    """nn.Linear + the reference's geometric initialisation variants (mlp.py:52-72), drawn in the same order
+    from the global RNG so that a seed reproduces the reference's weights."""
+    lin = nn.Linear(n_in, n_out)
+    if init == "sdf_out":
+        nn.init.normal_(lin.weight, mean=np.sqrt(np.pi) / np.sqrt(n_in), std=0.0001)
+        nn.init.constant_(lin.bias, -geo_bias)
+    elif init == "first":
+        nn.init.constant_(lin.bias, 0.0)
+        nn.init.constant_(lin.weight[:, 3:], 0.0)
+        nn.init.normal_(lin.weight[:, :3], 0.0, np.sqrt(2) / np.sqrt(n_out))
+    elif init == "skip":
+        nn.init.constant_(lin.bias, 0.0)
+        nn.init.normal_(lin.weight, 0.0, np.sqrt(2) / np.sqrt(n_out))
+        nn.init.constant_(lin.weight[:, -(n_embed - 3):], 0.0)
+    elif init == "hidden":
+        nn.init.constant_(lin.bias, 0.0)
+        nn.init.normal_(lin.weight, 0.0, np.sqrt(2) / np.sqrt(n_out))
+    if use_weight_norm:
+        lin = nn.utils.weight_norm(lin)       # old-style API on purpose: checkpoint keys weight_g / weight_v
+    return lin
+
+
+def _effective_weight(lin):
+    if hasattr(lin, "weight_g"):
+        return torch._weight_norm(lin.weight_v, lin.weight_g, 0)
+    return lin.weight
+
+
+class _Stack(nn.Module):
+    """Parameter holder for a chain of lin{l} layers."""
+
+    def layers(self):
+        return [getattr(self, f"lin{l}") for l in range(self.num_layers - 1)]
+
+    def effective(self):
+        ls = self.layers()
+        return [_effective_weight(l) for l in ls], [l.bias for l in ls]
+
+    def get_param_groups(self, lr):
+        return [{"params": self.parameters(), "lr": lr}]
+
+
+class ImplicitNetwork(_Stack):
+    """SDF network (reference: mlp.py:10-151).  Holds lin0..lin{L-1}; arithmetic runs in the CUDA core."""
+
+    def __init__(self, feature_vector_size, sdf_bounding_sphere, d_in, d_out, dims, geometric_init=True, bias=1.0,
+                 skip_in=(), weight_norm=True, embed_type=None, sphere_scale=1.0, output_activation=None, **kwargs):
+        super().__init__()
+        if sdf_bounding_sphere and sdf_bounding_sphere > 0.0:
+            raise I2SDFError("sdf_bounding_sphere > 0 (sphere clamp) is not used by I2SDFNetwork and not supported")
+        self.sdf_bounding_sphere = sdf_bounding_sphere
+        self.sphere_scale = sphere_scale
+        dims = [d_in] + list(dims) + [d_out + feature_vector_size]
+        self.embed_type = embed_type
+        self.multires = kwargs.get("multires", 0)
+        if embed_type:
+            if embed_type != "positional":
+                raise I2SDFError(f"embed_type {embed_type!r} is not supported (shipped configs use 'positional')")
+            dims[0] = _embed_width(self.multires, d_in)
+        print(f"[INFO] Implicit network dims: {dims}")
+        self.dims = dims
+        self.num_layers = len(dims)
+        self.skip_in = tuple(skip_in)
+        self.weight_norm = weight_norm
+        self.output_activation_name = output_activation
+        last = self.num_layers - 2
+        for l in range(self.num_layers - 1):
+            n_out = dims[l + 1] - dims[0] if (l + 1) in self.skip_in else dims[l + 1]
+            kind = None
+            if geometric_init:
+                if l == last:
+                    kind = "sdf_out"
+                elif embed_type and l == 0:
+                    kind = "first"
+                elif embed_type and l in self.skip_in:
+                    kind = "skip"
+                else:
+                    kind = "hidden"
+            setattr(self, f"lin{l}", _make_linear(dims[l], n_out, kind, geo_bias=bias, n_embed=dims[0],
+                                                  use_weight_norm=weight_norm))
+        self._owner = None
+
+    # --- standalone callable surface used by the reference's eval / plotting code
+    def _core(self):
+        owner = self._owner() if self._owner is not None else None
+        if owner is None or owner.implicit_network is not self:
+            raise I2SDFError("this ImplicitNetwork is a parameter holder; call it through I2SDFNetwork.implicit_network")
+        return owner._ready_core()
+
+    def forward(self, input):
+        """x [M,3] -> [M, 1+F]  (mlp.py:84-105); used by mesh extraction as implicit_network(pts)[:,0]."""
+        sdf, feat, _ = self._core().sdf_forward(input, want_feat=True)
+        return torch.cat([sdf[:, None], feat], 1)
+
+    def get_sdf_vals(self, x):
+        return self._core().sdf_forward(x)[0][:, None]
+
+    def gradient(self, x):
+        owner = self._owner()
+        if owner is not None and torch.is_grad_enabled() and owner.training:
+            from .autograd import sdf_with_grad
+            return sdf_with_grad(owner, x)[2]
+        return self._core().sdf_forward(x, want_grad=True)[2]
+
+    def feature(self, x):
+        return self._core().sdf_forward(x, want_feat=True)[1]
+
+    def get_outputs(self, x, returns_grad=True):
+        sdf, feat, grad = self._core().sdf_forward(x, want_feat=True, want_grad=returns_grad)
+        return sdf[:, None], feat, grad
+
+
+class RenderingNetwork(_Stack):
+    """Radiance network (reference: mlp.py:159-229), mode 'nerf'."""
+
+    def __init__(self, feature_vector_size, mode, d_in, d_out, dims, weight_norm=True, embed_type=None,
+                 embed_point=None, output_activation="sigmoid", **kwargs):
+        super().__init__()
+        if mode != "nerf":
+            raise I2SDFError("rendering_network.mode 'idr' is not configured by any shipped yaml and not supported")
+        if output_activation != "sigmoid":
+            raise I2SDFError("rendering_network output_activation must be 'sigmoid'")
+        self.mode = mode
+        self.d_out = d_out
+        dims = [d_in + feature_vector_size] + list(dims) + [d_out]
+        self.multires = kwargs.get("multires", 0)
+        if embed_type:
+            if embed_type != "positional":
+                raise I2SDFError(f"embed_type {embed_type!r} is not supported")
+            dims[0] += _embed_width(self.multires, 3) - 3
+        print(f"[INFO] Rendering network dims: {dims}")
+        self.dims = dims
+        self.num_layers = len(dims)
+        self.weight_norm = weight_norm
+        for l in range(self.num_layers - 1):
+            setattr(self, f"lin{l}", _make_linear(dims[l], dims[l + 1], None, use_weight_norm=weight_norm))
+
+    def forward(self, points, normals, view_dirs, feature_vectors):
+        raise I2SDFError("RenderingNetwork is evaluated inside the fused render kernel; call I2SDFNetwork.forward")
+
+
+class LaplaceDensity(nn.Module):
+    """alpha * Laplace(0, beta).cdf(-sdf)  (reference: density.py:5-30).  `beta` stays an nn.Parameter."""
+
+    def __init__(self, params_init={}, beta_min=0.0001):
+        super().__init__()
+        for p in params_init:
+            setattr(self, p, nn.Parameter(torch.tensor(params_init[p])))
+        self.beta_min = torch.tensor(beta_min)
+
+    def get_beta(self):
+        return self.beta.abs() + self.beta_min.to(self.beta.device)
+
+    def density_func(self, sdf, beta=None):
+        # API-compat only (not on the hot path, which evaluates the density inside the kernels)
+        if beta is None:
+            beta = self.get_beta()
+        return (1 / beta) * (0.5 + 0.5 * sdf.sign() * torch.expm1(-sdf.abs() / beta))
+
+    def forward(self, sdf, beta=None):
+        return self.density_func(sdf, beta=beta)
+
+
+class ErrorBoundSampler:
+    """Configuration holder for the error-bounded sampler (reference: ray_sampler.py:46-65)."""
+
+    def __init__(self, scene_bounding_sphere, near, N_samples, N_samples_eval, N_samples_extra, eps, beta_iters,
+                 max_total_iters, inverse_sphere_bg=False, N_samples_inverse_sphere=0, add_tiny=0.0):
+        if inverse_sphere_bg:
+            raise I2SDFError("inverse-sphere background is not enabled by any shipped config and not supported")
+        self.near, self.far = near, 2.0 * scene_bounding_sphere
+        self.N_samples, self.N_samples_eval, self.N_samples_extra = N_samples, N_samples_eval, N_samples_extra
+        self.eps, self.beta_iters, self.max_total_iters = eps, beta_iters, max_total_iters
+        self.scene_bounding_sphere = scene_bounding_sphere
+        self.add_tiny = add_tiny
+        self.inverse_sphere_bg = False
+
+    def get_z_vals(self, ray_dirs, cam_loc, model):
+        """-> (z_vals [R,98], z_samples_eik [R,1])   (ray_sampler.py:67-241)."""
+        core = model._ready_core()
+        tape = model._draw_sampler_tape(ray_dirs.shape[0], ray_dirs.device) if model.training else None
+        if tape is None:
+            tape = {"eik_idx": torch.randint(core.n_out, (ray_dirs.shape[0],), device=ray_dirs.device)}
+        z, z_eik = core.sample(cam_loc.contiguous().float(), ray_dirs.contiguous().float(),
+                               model.density.beta.detach(), tape)
+        return z, z_eik[:, None]
+
+
+class I2SDFNetwork(nn.Module):
+    """Reference: model/network/__init__.py:19-221."""
+
+    def __init__(self, conf):
+        super().__init__()
+        self._model_conf = _plain(conf)
+        mc = self._model_conf
+        self.feature_vector_size = mc["feature_vector_size"]
+        self.scene_bounding_sphere = mc.get("scene_bounding_sphere", 1.0)
+        self.implicit_network = ImplicitNetwork(self.feature_vector_size, 0.0, **mc["implicit_network"])
+        self.rendering_network = RenderingNetwork(self.feature_vector_size, **mc["rendering_network"])
+        self.use_light = "light_network" in mc
+        if self.use_light:
+            self.light_network = ImplicitNetwork(0, 0, d_in=self.feature_vector_size, d_out=1, geometric_init=False,
+                                                 embed_type=None, output_activation="sigmoid", **mc["light_network"])
+        self.density = LaplaceDensity(**mc["density"])
+        self.use_bg = "bg_network" in mc
+        if self.use_bg:
+            raise I2SDFError("model.bg_network (inverse-sphere background) is out of scope: no shipped config enables it")
+        print("[INFO] BG Network Disabled")
+        self.ray_sampler = ErrorBoundSampler(self.scene_bounding_sphere, inverse_sphere_bg=False, **mc["ray_sampler"])
+        self.use_normal = mc.get("use_normal", False)
+        self.detach_light_feature = mc.get("detach_light_feature", True)
+        if not self.detach_light_feature:
+            raise I2SDFError("detach_light_feature=False is not supported (the reference default is True)")
+        self.implicit_network._owner = weakref.ref(self)
+        self._core_obj = None
+        self._packed_key = None
+
+    def get_param_groups(self, lr):
+        return [{"params": self.parameters(), "lr": lr}]
+
+    # ------------------------------------------------------------------ device state
+    def _stacks(self):
+        s = [self.implicit_network, self.rendering_network]
+        if self.use_light:
+            s.append(self.light_network)
+        return s
+
+    def _ready_core(self) -> RenderCore:
+        """The RenderCore on the parameters' device with up-to-date packed weights."""
+        dev = self.density.beta.device
+        if dev.type != "cuda":
+            raise I2SDFError("I2SDFNetwork (i2sdf_b200) needs its parameters on a CUDA device; there is no CPU path")
+        if self._core_obj is None or self._core_obj.device != dev:
+            self._core_obj = RenderCore(self._model_conf, dev)
+            self._packed_key = None
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if key != self._packed_key:
+            self.pack_weights()
+            self._packed_key = key
+        return self._core_obj
+
+    def effective_weights(self):
+        Ws, bs = [], []
+        for st in self._stacks():
+            w, b = st.effective()
+            Ws += w
+            bs += b
+        return Ws, bs
+
+    @torch.no_grad()
+    def pack_weights(self):
+        Ws, bs = self.effective_weights()
+        self._core_obj.pack(Ws, bs)
+
+    # ------------------------------------------------------------------ RNG tapes (training)
+    def _draw_sampler_tape(self, R, device):
+        """Same draws, same order, same devices as the reference (ray_sampler.py:39,190,223,233)."""
+        rs = self.ray_sampler
+        tape = {
+            "jitter": torch.rand(R, rs.N_samples_eval, device=device),
+            "u_final": torch.rand(R, rs.N_samples, device=device),
+            "extra_perm": lambda n: torch.randperm(n)[:rs.N_samples_extra],          # CPU generator, as the reference
+        }
+        n_out = rs.N_samples + 2 + rs.N_samples_extra
+        tape["eik_idx_fn"] = lambda: torch.randint(n_out, (R,), device=device)
+        return tape
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, input, predict_only=False):
+        core = self._ready_core()
+        if self.training and torch.is_grad_enabled():
+            from .autograd import forward_train
+            return forward_train(self, core, input, predict_only)
+        return self._forward_nograd(core, input, predict_only)
+
+    @torch.no_grad()
+    def _forward_nograd(self, core, input, predict_only):
+        o, d, dnorm = core.rays(input["uv"], input["pose"], input["intrinsics"])
+        R = o.shape[0]
+        beta = self.density.beta.detach()
+        tape = self._draw_sampler_tape(R, o.device) if self.training else None
+        z, z_eik = core.sample(o, d, beta, tape)
+        want_normal = (not predict_only) and (self.use_normal or not self.training)
+        out = core.render(o, d, dnorm, z, beta, want_normal=want_normal, want_light=self.use_light)
+        res = {"rgb_values": out["rgb"], "depth_values": out["depth"], "weight_sum": out["weight_sum"][:, None]}
+        if self.use_light:
+            res["light_mask"] = out["light"][:, None]
+        if predict_only:
+            return res
+        if self.training:
+            # no-grad training-mode call (e.g. bubble pdf refresh): the reference still emits the eikonal terms
+            from .autograd import train_extras_nograd
+            res.update(train_extras_nograd(self, core, input, o, d, z_eik))
+            if self.use_normal:
+                res["normal_values"] = out["normal"]
+        else:
+            res["normal_map"] = out["normal"]
+        return res
+
+
+class I2SDFLoss(nn.Module):
+    """Loss of the reconstruction stage; consumes I2SDFNetwork outputs (reference: model/network/__init__.py:289-406).
+    Kept in PyTorch (SURVEY §8(f) ranks fusing it as the next tier)."""
+
+    def __init__(self, eikonal_weight=0.1, smooth_weight=0.0, mask_weight=0.0, depth_weight=0.1, normal_weight=0.05,
+                 angular_weight=0.05, bubble_weight=0.0, min_bubble_iter=0, max_bubble_iter=None, smooth_iter=None,
+                 light_mask_weight=0.0, eikonal_weight_bubble=0.0):
+        super().__init__()
+        self.eikonal_weight, self.smooth_weight, self.mask_weight = eikonal_weight, smooth_weight, mask_weight
+        self.depth_weight, self.normal_weight, self.angular_weight = depth_weight, normal_weight, angular_weight
+        self.bubble_weight, self.light_mask_weight = bubble_weight, light_mask_weight
+        self.min_bubble_iter, self.max_bubble_iter, self.smooth_iter = min_bubble_iter, max_bubble_iter, smooth_iter
+        self.rgb_loss = F.l1_loss
+        if self.bubble_weight > 0 and self.max_bubble_iter is not None and self.smooth_iter < self.max_bubble_iter:
+            self.smooth_iter = self.max_bubble_iter
+
+    @staticmethod
+    def _masked_normal_l1(normal, normal_gt, mask):
+        m = mask.flatten()
+        return torch.abs(1 - torch.sum(normal[m] * normal_gt.reshape(-1, 3)[m], dim=-1)).mean()
+
+    def get_rgb_loss(self, rgb_values, rgb_gt):
+        return self.rgb_loss(rgb_values, rgb_gt.reshape(-1, 3))
+
+    def get_eikonal_loss(self, grad_theta):
+        return ((grad_theta.norm(2, dim=1) - 1) ** 2).mean()
+
+    def get_mask_loss(self, mask_pred, mask_gt):
+        return F.binary_cross_entropy(mask_pred.clip(1e-3, 1.0 - 1e-3), mask_gt)
+
+    def get_depth_loss(self, depth, depth_gt, depth_mask):
+        m = depth_mask.flatten()
+        return F.mse_loss(depth[m], depth_gt.flatten()[m])
+
+    def get_normal_l1_loss(self, normal, normal_gt, normal_mask):
+        return self._masked_normal_l1(normal, normal_gt, normal_mask)
+
+    def get_normal_angular_loss(self, normal, normal_gt, normal_mask):
+        m = normal_mask.flatten()
+        dot = torch.sum(normal[m] * normal_gt.reshape(-1, 3)[m], dim=-1)
+        return (torch.acos(torch.clamp(dot, -1.0 + 1e-6, 1.0 - 1e-6)) / math.tau).clamp_max(0.5).abs().mean()
+
+    def forward(self, model_outputs, ground_truth, current_step):
+        dev = model_outputs["rgb_values"].device
+        zero = lambda: torch.tensor(0.0, device=dev).float()      # noqa: E731
+        terms = {"rgb_loss": self.get_rgb_loss(model_outputs["rgb_values"], ground_truth["rgb"])}
+        terms["eikonal_loss"] = self.get_eikonal_loss(model_outputs["grad_theta"]) if "grad_theta" in model_outputs else zero()
+        smooth_on = self.smooth_iter is None or current_step > self.smooth_iter
+        terms["smooth_loss"] = model_outputs["diff_norm"].mean() if (smooth_on and self.smooth_weight > 0 and "diff_norm" in model_outputs) else zero()
+        terms["mask_loss"] = self.get_mask_loss(model_outputs["weight_sum"], ground_truth["mask"]) if ("mask" in ground_truth and self.mask_weight > 0) else zero()
+        terms["depth_loss"] = self.get_depth_loss(model_outputs["depth_values"], ground_truth["depth"], ground_truth["depth_mask"]) if ("depth" in ground_truth and self.depth_weight > 0) else zero()
+        has_n = "normal" in ground_truth
+        terms["normal_loss"] = self.get_normal_l1_loss(model_outputs["normal_values"], ground_truth["normal"], ground_truth["normal_mask"]) if (has_n and self.normal_weight > 0) else zero()
+        # the reference's "angular" term re-uses the L1 normal loss (model/network/__init__.py:368-371)
+        terms["angular_loss"] = self.get_normal_l1_loss(model_outputs["normal_values"], ground_truth["normal"], ground_truth["normal_mask"]) if (has_n and self.angular_weight > 0) else zero()
+        terms["bubble_loss"] = model_outputs["surface_sdf"].abs().mean() if ("surface_sdf" in model_outputs and self.bubble_weight > 0) else zero()
+        terms["light_mask_loss"] = self.get_mask_loss(model_outputs["light_mask"].reshape(-1, 1), ground_truth["light_mask"].reshape(-1, 1)) if ("light_mask" in model_outputs and self.light_mask_weight > 0) else zero()
+        weights = {"rgb_loss": 1.0, "eikonal_loss": self.eikonal_weight, "smooth_loss": self.smooth_weight,
+                   "mask_loss": self.mask_weight, "depth_loss": self.depth_weight, "normal_loss": self.normal_weight,
+                   "angular_loss": self.angular_weight, "bubble_loss": self.bubble_weight,
+                   "light_mask_loss": self.light_mask_weight}
+        loss = terms["rgb_loss"]
+        for k in ("eikonal_loss", "smooth_loss", "mask_loss", "depth_loss", "normal_loss", "angular_loss", "bubble_loss", "light_mask_loss"):
+            loss = loss + weights[k] * terms[k]
+        out = {"loss": loss}
+        out.update(terms)
+        return out

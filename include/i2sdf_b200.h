@@ -1,0 +1,158 @@
+/*
+ * i2sdf_b200 — C ABI of the B200-native I2-SDF volume-rendering core.
+ *
+ * The reference (jingsenzhu/i2-sdf) is pure Python/PyTorch and has no FFI of its own; the entry points
+ * below are what a binding for its per-ray hot path would call.  Each one names the reference
+ * function(s) it replaces (file:line relative to the reference tree).
+ *
+ * Conventions
+ *   - plain C, `extern "C"`, no C++/torch types: raw DEVICE pointers (unless marked host), sizes, a stream.
+ *   - every function returns 0 on success, a negative I2SDF_E_* code otherwise; i2sdf_last_error() gives text.
+ *     No exception crosses this boundary.  Nothing here falls back to the CPU.
+ *   - the caller owns every buffer, including the workspace (size from i2sdf_workspace_bytes()).
+ *     The library's only state is the opaque handle: packed weights, tables, device properties.
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*); no call synchronises the host.
+ *   - all floating point tensors are fp32, row-major, densely packed; index tensors are int32 unless noted.
+ */
+#ifndef I2SDF_B200_H
+#define I2SDF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define I2SDF_ABI_VERSION 1
+
+enum {
+    I2SDF_OK = 0,
+    I2SDF_E_INVALID = -1,     /* bad argument / unsupported network shape */
+    I2SDF_E_CUDA = -2,        /* a CUDA runtime call or launch failed */
+    I2SDF_E_NOGPU = -3,       /* no sm_100 device */
+    I2SDF_E_WORKSPACE = -4    /* workspace too small */
+};
+
+/* Network + sampler description: the `model:` node of a reference yaml
+ * (config/synthetic.yml:30-74; read by I2SDFNetwork.__init__, model/network/__init__.py:20-47). */
+typedef struct i2sdf_desc {
+    int32_t abi_version;       /* I2SDF_ABI_VERSION */
+    int32_t hidden;            /* width of every hidden layer; must be 256 */
+    int32_t feature_size;      /* feature_vector_size; must be 256 */
+    int32_t n_sdf_layers;      /* number of Linear layers of ImplicitNetwork (9 or 7) */
+    int32_t sdf_skip_layer;    /* skip_in[0] (4 or 3), -1 for none */
+    int32_t multires_x;        /* 6 -> 39-wide embedding of points */
+    int32_t n_color_layers;    /* Linear layers of RenderingNetwork (5 or 4), mode 'nerf' */
+    int32_t multires_d;        /* 4 -> 27-wide embedding of view dirs */
+    int32_t n_light_layers;    /* 0, or 2 for the light-mask head [256,128,1] */
+    int32_t light_hidden;      /* 128 */
+    /* ErrorBoundSampler (ray_sampler.py:46-65) */
+    int32_t n_samples;         /* 64 */
+    int32_t n_samples_eval;    /* 128 */
+    int32_t n_samples_extra;   /* 32 */
+    int32_t beta_iters;        /* 10 */
+    int32_t max_total_iters;   /* 5 */
+    float near_;               /* 0 */
+    float far_;                /* 2 * scene_bounding_sphere */
+    float eps;                 /* 0.1 */
+    float add_tiny;            /* 1e-6 */
+    float beta_min;            /* LaplaceDensity.beta_min, 1e-4 (density.py:19) */
+    float lemma2_coeff;        /* 1/(4*log(1+eps)) evaluated in fp32 by the caller (ray_sampler.py:76) */
+    /* host tables computed by the caller with torch.linspace so that index arithmetic is bit-identical
+     * to the reference: u_up[n_samples_eval], u_final[n_samples] (ray_sampler.py:188), t_init[n_samples_eval]
+     * (ray_sampler.py:30), extra_idx[max_total_iters][n_samples_extra] = linspace(0, n-1, 32).long() for
+     * n = 128,256,... (ray_sampler.py:225).  HOST pointers, copied at create time. */
+    const float* u_up;
+    const float* u_final;
+    const float* t_init;
+    const int32_t* extra_idx;
+} i2sdf_desc;
+
+typedef struct i2sdf_handle i2sdf_handle;
+
+int i2sdf_abi_version(void);
+const char* i2sdf_last_error(void);
+
+/* Replaces: I2SDFNetwork.__init__ (model/network/__init__.py:20-47) for the device-side state. */
+int i2sdf_create(const i2sdf_desc* desc, int device, i2sdf_handle** out);
+int i2sdf_destroy(i2sdf_handle* h);
+
+/* Number of Linear layers the weight arrays below must hold: n_sdf + n_color + n_light, in that order. */
+int i2sdf_num_layers(const i2sdf_handle* h);
+
+/* Replaces: the weight-norm forward pre-hook + nn.Linear parameter reads (mlp.py:71-72,97,200-201,222).
+ * W[i] : device pointer to the EFFECTIVE weight of layer i, row-major [out,in] (W = g*v/||v||, computed by
+ * the caller so autograd sees it); b[i] : device pointer to bias [out].  `W`/`b` are HOST arrays of device
+ * pointers.  Re-packs (transposes / pads / splits) into the handle's kernel layouts.  Call after every
+ * optimizer step. */
+int i2sdf_pack_weights(i2sdf_handle* h, const float* const* W, const float* const* b, void* stream);
+
+/* Workspace size in bytes for a call over R rays (sampler + render) or M points (sdf_forward: pass R=M, 1 sample). */
+size_t i2sdf_workspace_bytes(const i2sdf_handle* h, int64_t R, int training);
+
+/* Replaces: utils.get_camera_params + lift (utils/rend_util.py:92-147) and the ray flattening /
+ * normalisation at model/network/__init__.py:86-93.
+ * uv [B,P,2], pose [B,4,4], intr [B,4,4]  ->  o [B*P,3], d [B*P,3] (unit), dnorm [B*P]. */
+int i2sdf_rays(i2sdf_handle* h, const float* uv, const float* pose, const float* intr, int B, int P,
+               float* o, float* d, float* dnorm, void* stream);
+
+/* Replaces: ImplicitNetwork.forward / get_sdf_vals / get_outputs / gradient (mlp.py:84-151).
+ * pts [M,3] -> out_sdf [M] (required), out_feat [M,256] or NULL, out_grad [M,3] (= d sdf/d x) or NULL.
+ * save_act: NULL, or [n_sdf_layers-1, M, 256] to keep the pre-activations for i2sdf_sdf_backward. */
+int i2sdf_sdf_forward(i2sdf_handle* h, const float* pts, int64_t M, float* out_sdf, float* out_feat,
+                      float* out_grad, float* save_act, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces: ErrorBoundSampler.get_z_vals rounds (ray_sampler.py:67-212): uniform init (+ stratified jitter),
+ * up to max_total_iters rounds of {SDF of new samples, d*, beta line search, opacity-bound pdf, inverse CDF,
+ * merge}.  No host synchronisation: the batch-global convergence test (ray_sampler.py:151) is evaluated on
+ * the device and later rounds predicate themselves off.
+ * beta_param : device pointer to density.beta (raw parameter; beta0 = |beta| + beta_min on device).
+ * jitter [R,n_samples_eval] / u_final [R,n_samples] : training RNG tapes (ray_sampler.py:39,190) or NULL (eval).
+ * State is left in the workspace for i2sdf_sampler_finalize. */
+int i2sdf_sampler_rounds(i2sdf_handle* h, const float* o, const float* d, int64_t R, const float* beta_param,
+                         const float* jitter, const float* u_final,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces: ray_sampler.py:215-234 — extra samples, near/far, final sort, eikonal pick.
+ * extra_idx : device int32[n_samples_extra] (training: randperm(n)[:32], ray_sampler.py:223) or NULL (eval table).
+ * eik_idx   : device int32[R] (ray_sampler.py:233) or NULL.
+ * out_z [R, n_samples+2+n_samples_extra] sorted; out_z_eik [R] or NULL.
+ * out_info (device int32[2] or NULL): [0] = rounds executed, [1] = z's per ray when sampling stopped (128*rounds). */
+int i2sdf_sampler_finalize(i2sdf_handle* h, int64_t R, const float* beta_param, const int32_t* extra_idx,
+                           const int32_t* eik_idx, float* out_z, float* out_z_eik, int32_t* out_info,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* Device int32[2] as above WITHOUT finalising: lets a training caller read n (one 8-byte D2H, the only host
+ * sync of the path; the reference syncs once per round at ray_sampler.py:151) to draw randperm(n)[:32]. */
+int i2sdf_sampler_info(i2sdf_handle* h, int64_t R, const float* beta_param, int32_t* out_info,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Debug/parity entry: one sampler round on caller-supplied sorted z [R,n] and sdf [R,n] (identical inputs to
+ * the oracle's round): outputs beta [R], cdf [R,n], inds [R,ns] (searchsorted right=True, ray_sampler.py:193),
+ * samples [R,ns], and if upsample: z_merged [R,n+ns], src [R,n+ns] (merge source index, ray_sampler.py:212).
+ * beta_in [R]: upper bound entering the round.  force_upsample: 1 = opacity-bound pdf (:153-171), 0 = final (:173-183). */
+int i2sdf_sampler_round_debug(i2sdf_handle* h, const float* z, const float* sdf, int64_t R, int n,
+                              const float* beta_param, const float* beta_in, int force_upsample,
+                              const float* u_tape, float* out_beta, float* out_cdf, int32_t* out_inds,
+                              float* out_samples, float* out_z_merged, int32_t* out_src, void* stream);
+
+/* Replaces: the main pass of I2SDFNetwork.forward (model/network/__init__.py:99-125,162-170,204-219) +
+ * volume_rendering (:223-240): points o+z*d -> SDF(+grad_x) -> radiance MLP -> Laplace density -> alpha
+ * compositing (+ light-mask head).
+ * z [R,N+1] (last column = z_max).  Per-ray outputs (any may be NULL): rgb [R,3], depth [R], weight_sum [R],
+ * normal [R,3] (normalize(sum w * normalize(grad))), light [R].
+ * Per-sample outputs kept for backward / parity (any may be NULL): s_sdf [R*N], s_grad [R*N,3], s_rgb [R*N,3],
+ * s_w [R*N], s_light [R*N].   save: NULL or an i2sdf_saved-sized buffer (see i2sdf_saved_bytes). */
+int i2sdf_render_forward(i2sdf_handle* h, const float* o, const float* d, const float* dnorm, const float* z,
+                         int64_t R, int N, const float* beta_param,
+                         float* rgb, float* depth, float* weight_sum, float* normal, float* light,
+                         float* s_sdf, float* s_grad, float* s_rgb, float* s_w, float* s_light,
+                         void* save, size_t save_bytes, void* workspace, size_t workspace_bytes, void* stream);
+
+size_t i2sdf_saved_bytes(const i2sdf_handle* h, int64_t R, int N);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* I2SDF_B200_H */

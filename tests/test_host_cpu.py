@@ -1,0 +1,80 @@
+"""CPU: host-side logic and the C-ABI library surface (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from i2sdf_b200 import _lib, configs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "i2sdf_b200.h")).read()
+    declared = set(re.findall(r"\b(i2sdf_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.i2sdf_abi_version() == 1
+
+
+def test_desc_struct_layout_matches_header():
+    # 15 int32 + 6 float + 4 pointers, natural alignment
+    assert ctypes.sizeof(_lib.Desc) == 15 * 4 + 6 * 4 + 4 + 4 * 8
+
+
+def test_module_surface_matches_reference_state_dict():
+    from i2sdf_b200.network import I2SDFNetwork
+    torch.manual_seed(0)
+    m = I2SDFNetwork(configs.model_conf("synthetic_light_mask"))
+    keys = set(m.state_dict().keys())
+    want = {f"implicit_network.lin{l}.{s}" for l in range(7) for s in ("bias", "weight_g", "weight_v")}
+    want |= {f"rendering_network.lin{l}.{s}" for l in range(4) for s in ("bias", "weight_g", "weight_v")}
+    want |= {f"light_network.lin{l}.{s}" for l in range(2) for s in ("bias", "weight_g", "weight_v")}
+    want |= {"density.beta"}
+    assert keys == want
+    assert m.implicit_network.lin2.weight_v.shape == (217, 256)       # layer feeding the skip concat
+    assert m.implicit_network.lin6.weight_v.shape == (257, 256)
+    assert m.rendering_network.lin0.weight_v.shape == (256, 283)
+    assert sum(p.numel() for p in m.parameters()) == 635965
+    m2 = I2SDFNetwork(configs.model_conf("synthetic"))
+    assert sum(p.numel() for p in m2.parameters()) == 800955
+
+
+def test_geometric_init_reproduces_reference_weights():
+    """Same seed -> same weights as the reference constructor (fixture weights were made by the reference ctor,
+    then perturbed only in the embedding columns / colour heads; untouched tensors must match bit for bit)."""
+    import numpy as np
+    from i2sdf_b200.network import I2SDFNetwork
+    w = np.load(os.path.join(ROOT, "tests", "golden", "weights_synthetic.npz"))
+    torch.manual_seed(0)
+    m = I2SDFNetwork(configs.model_conf("synthetic"))
+    sd = m.state_dict()
+    for k in ("implicit_network.lin1.weight_v", "implicit_network.lin5.weight_g", "implicit_network.lin8.weight_v",
+              "implicit_network.lin8.bias", "implicit_network.lin3.weight_v"):
+        assert torch.equal(sd[k], torch.from_numpy(w[k])), k
+    assert torch.equal(sd["implicit_network.lin0.weight_v"][:, :3], torch.from_numpy(w["implicit_network.lin0.weight_v"][:, :3]))
+    # colour stack was scaled by 1.5 after construction
+    assert torch.allclose(sd["rendering_network.lin2.weight_v"] * 1.5, torch.from_numpy(w["rendering_network.lin2.weight_v"]))
+
+
+def test_forward_on_cpu_fails_loudly():
+    from i2sdf_b200.network import I2SDFNetwork
+    m = I2SDFNetwork(configs.model_conf("synthetic")).eval()
+    with pytest.raises(_lib.I2SDFError):
+        m({"uv": torch.zeros(1, 4, 2), "pose": torch.eye(4)[None], "intrinsics": torch.eye(4)[None]})
+
+
+def test_unsupported_configs_are_rejected():
+    from i2sdf_b200.network import I2SDFNetwork
+    conf = configs.model_conf("synthetic")
+    conf["bg_network"] = {}
+    with pytest.raises(_lib.I2SDFError):
+        I2SDFNetwork(conf)
+    conf = configs.model_conf("synthetic")
+    conf["rendering_network"]["mode"] = "idr"
+    with pytest.raises(_lib.I2SDFError):
+        I2SDFNetwork(conf)
