@@ -25,6 +25,7 @@ SYMBOLS = {
     "i2sdf_create": (C.c_int, [C.POINTER(Desc), C.c_int, C.POINTER(_P)]),
     "i2sdf_destroy": (C.c_int, [_P]),
     "i2sdf_num_layers": (C.c_int, [_P]),
+    "i2sdf_uses_tensor_cores": (C.c_int, [_P]),
     "i2sdf_pack_weights": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), _P]),
     "i2sdf_workspace_bytes": (C.c_size_t, [_P, C.c_int64, C.c_int]),
     "i2sdf_rays": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P]),

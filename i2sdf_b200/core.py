@@ -74,6 +74,7 @@ class RenderCore:
             check(self.lib.i2sdf_create(C.byref(d), device.index or 0, C.byref(h)), "i2sdf_create")
         self.h = h
         self.n_layers = self.lib.i2sdf_num_layers(h)
+        self.uses_tensor_cores = bool(self.lib.i2sdf_uses_tensor_cores(h))
         self._ws = None
         self._ws_rays = -1
         self._packed_refs = None
@@ -130,6 +131,8 @@ class RenderCore:
         sdf = torch.empty(M, device=self.device)
         feat = torch.empty(M, 256, device=self.device) if want_feat else None
         grad = torch.empty(M, 3, device=self.device) if want_grad else None
+        if M == 0:
+            return sdf, feat, grad
         ws = self.workspace(1)
         check(self.lib.i2sdf_sdf_forward(self.h, _ptr(pts), M, _ptr(sdf), _ptr(feat), _ptr(grad), _ptr(save_act),
                                          _ptr(ws), self._ws_bytes, self._stream()), "i2sdf_sdf_forward")

@@ -180,6 +180,7 @@ int i2sdf_destroy(i2sdf_handle* h) {
 }
 
 int i2sdf_num_layers(const i2sdf_handle* h) { return h ? h->n_layers : 0; }
+int i2sdf_uses_tensor_cores(const i2sdf_handle* h) { return (h && h->use_tc) ? 1 : 0; }
 
 int i2sdf_pack_weights(i2sdf_handle* h, const float* const* W, const float* const* b, void* stream) {
     if (!h || !W || !b) { set_error("null argument"); return I2SDF_E_INVALID; }
@@ -263,7 +264,9 @@ static int run_mlp(const i2sdf_handle* h, const MlpParams& p, cudaStream_t st) {
 
 int i2sdf_sdf_forward(i2sdf_handle* h, const float* pts, int64_t M, float* out_sdf, float* out_feat, float* out_grad,
                       float* save_act, void* workspace, size_t workspace_bytes, void* stream) {
-    if (!h || !pts || !out_sdf) { set_error("null argument"); return I2SDF_E_INVALID; }
+    if (!h) { set_error("null handle"); return I2SDF_E_INVALID; }
+    if (M == 0) return I2SDF_OK;
+    if (M < 0 || !pts || !out_sdf) { set_error("null argument"); return I2SDF_E_INVALID; }
     MlpParams p{};
     p.pts = pts; p.M = M; p.ns = 1; p.round_idx = -1; p.beta_min = h->smp.beta_min;
     p.out_sdf = out_sdf; p.out_feat = out_feat; p.out_grad = out_grad; p.save_act = save_act;

@@ -161,3 +161,38 @@ def test_forward_eval_end_to_end(cases, name):
     assert relerr(out["depth_values"], c.ref["depth_values"]) < 5e-3
     out2 = m({k: v.cuda() for k, v in c.inputs.items()}, predict_only=True)
     assert "normal_map" not in out2 and torch.equal(out2["rgb_values"], out["rgb_values"])   # idempotent / deterministic
+
+
+# ---------------------------------------------------------------------------------------------------
+# tcgen05 path (sampler SDF evaluations): bf16 hi/lo split, 3 products, fp32 accumulate in TMEM
+# ---------------------------------------------------------------------------------------------------
+def _simt_model(case):
+    import os
+    os.environ["I2SDF_SIMT"] = "1"
+    try:
+        m = _model(case)
+        m._ready_core()
+    finally:
+        os.environ.pop("I2SDF_SIMT", None)
+    return m
+
+
+@pytest.mark.parametrize("name", ["eval_synthetic_sharp", "eval_light_sharp"])
+def test_tensor_core_sdf_matches_oracle_and_fp32_kernel(cases, name):
+    c = cases[name]
+    m = _model(c)
+    core = m._ready_core()
+    assert core.uses_tensor_cores, "tcgen05 path not active"
+    ms = _simt_model(c)
+    assert not ms._core_obj.uses_tensor_cores
+    g = torch.Generator().manual_seed(11)
+    for M in (128, 1000, 128 * 148 * 2 + 77):
+        pts = (torch.rand(M, 3, generator=g) - 0.5) * 3.0
+        layers = orc.layer_params(c.params, "implicit_network", c.spec.n_sdf_layers)
+        with torch.no_grad():
+            ref = orc.sdf_mlp(c.spec, layers, pts)[0][:, 0]
+        tc = core.sdf_forward(pts.cuda())[0]
+        fp = ms._core_obj.sdf_forward(pts.cuda())[0]
+        assert relerr(fp, ref) < 1e-5
+        assert relerr(tc, ref) < TOL, (M, relerr(tc, ref))
+        assert relerr(tc, fp) < TOL
