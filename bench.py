@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py — ray-samples/s through the fused SDF+render path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rays R]
+
+A step = one pass of the hot path (I2SDFNetwork.forward: rays -> error-bounded sampler (5 x 128 sdf-evals/ray) ->
+SDF + grad_x + radiance on the 97 composited samples/ray -> alpha compositing) over one 1024-ray batch of synthetic
+rays with the config/synthetic.yml networks (W-sharp weights, density.beta = 0.01 so all five
+sampler rounds run).  value = full-path ray-samples/s = rays * 97 / step time, whole job (all ranks).
+
+N > 1 (torchrun, one rank per GPU): rays shard across ranks, every rank renders its own 1024-ray batch (weak
+scaling), inference has no collective; time = max over ranks of the device time of the K steps.
+
+--impl reference: the reference's CPU implementation of the same path.  The reference is Python/PyTorch and cannot
+travel to the GPU box, so this arm times the oracle port (oracle/i2sdf_oracle.py, pinned bit-for-bit against the
+reference on the golden fixtures) on the host cores, one bounded sample of the workload per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "full-path ray-samples/sec through SDF+render MLPs"
+UNIT = "ray-samples/s"
+N_COMPOSITED = 97               # N_samples + 2 + N_samples_extra - 1  (model/network/__init__.py:99-100)
+FLOP_PER_SDF_EVAL = 918016      # algorithmic FLOP of one sampler sdf evaluation
+FLOP_PER_RAY_SAMPLE = 2506752   # SDF fwd + grad_x sweep + radiance, per composited sample
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rays", type=int, default=1024)
+    ap.add_argument("--cpu-rays", type=int, default=256, help="rays per step of the CPU arms (bounded sample)")
+    return ap.parse_args()
+
+
+def build_params(beta=0.01):
+    """W-sharp: reference geometric init (seed 0) with density.beta = 0.01."""
+    from i2sdf_b200 import configs
+    from i2sdf_b200.network import I2SDFNetwork
+    conf = configs.model_conf("synthetic")
+    torch.manual_seed(0)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = I2SDFNetwork(conf)
+    with torch.no_grad():
+        m.density.beta.fill_(beta)
+    return conf, m
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference path)
+# ----------------------------------------------------------------------------------------------------
+def cpu_arm(conf, model, rays, steps, warmup):
+    from oracle import i2sdf_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec = orc.spec_from_model_conf(conf, use_normal=False)
+    P = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    inp = orc.synthetic_rays(rays, seed=1)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            orc.render(spec, P, inp, training=False)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    total = sum(times)
+    return dict(value=rays * N_COMPOSITED * len(times) / total, ms_per_step=1e3 * total / len(times),
+                cores=torch.get_num_threads(),
+                sample=f"{rays} of the 1024 rays per step (same weights, same ray distribution), eval forward, "
+                       f"{len(times)} steps after {warmup} warm-up, torch CPU fp32, all host threads")
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16_tflops=d.get("bf16_tflops", 1590.0), bf16_tflops_sustained=d.get("bf16_tflops_sustained", 1400.0),
+                    hbm_gbs=d.get("hbm_gbs", 6650.0), source="MEASURED_PEAKS.json (of measured)")
+    return dict(bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, hbm_gbs=6650.0, source="B200_PROFILING.md fallback (of fallback)")
+
+
+def gpu_arm(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from oracle import i2sdf_oracle as orc
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    conf, model = build_params()
+    cpu_state = None
+    if rank == 0:
+        cpu_state = (conf, model)
+    model_gpu = model.to(dev).eval()
+    R = args.rays
+    # rank-specific rays: the global batch is world * R rays sharded across ranks
+    inp_host = {k: v.pin_memory() for k, v in orc.synthetic_rays(R, seed=1 + rank).items()}
+    inp_dev = {k: v.to(dev) for k, v in inp_host.items()}
+    core = model_gpu._ready_core()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+    out_host = {}
+
+    def step_resident():
+        return model_gpu(inp_dev)
+
+    def step_e2e():
+        d = {k: v.to(dev, non_blocking=True) for k, v in inp_host.items()}
+        out = model_gpu(d)
+        for k, v in out.items():
+            if k not in out_host:
+                out_host[k] = torch.empty(v.shape, dtype=v.dtype).pin_memory()
+            out_host[k].copy_(v, non_blocking=True)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile=False):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        if profile:
+            core.profile(True)
+        for a, b in ev:
+            flush.zero_()                      # L2 flush between timed iterations (outside the event pair)
+            a.record()
+            fn()
+            b.record()
+        barrier()
+        prof = core.profile_read() if profile else None
+        if profile:
+            core.profile(False)
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        return ms, prof
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+        step_e2e()
+    clk = ClockSampler(local_rank)
+    clk.start()
+    ms_res, prof = timed(step_resident, args.steps, profile=True)
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    clocks = clk.stop()
+    t = torch.tensor([ms_res, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_res, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        return None
+    K = args.steps
+    value = world * R * N_COMPOSITED * K / (ms_res * 1e-3)
+    e2e_value = world * R * N_COMPOSITED * K / (ms_e2e * 1e-3)
+    pk = peaks()
+    # dominant kernel: sampler SDF evaluations (73 % of the path's FLOPs)
+    sdf = prof["sampler_sdf"]
+    sdf_launches = max(sdf["launches"], 1)
+    pts_per_launch = R * 128
+    per_launch_ms = sdf["ms"] / sdf_launches
+    achieved = pts_per_launch * FLOP_PER_SDF_EVAL / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
+    peak = pk["bf16_tflops_sustained"] if core.uses_tensor_cores else 72.0
+    launches = sum(v["launches"] for v in prof.values())
+    h2d = sum(v.numel() * v.element_size() for v in inp_host.values())
+    d2h = sum(v.numel() * v.element_size() for v in out_host.values())
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_res / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (bf16x3 split products on tcgen05, fp32 accumulate)" if core.uses_tensor_cores else "f32",
+        "data": "synthetic",
+        "config": {"workload": "C2/C3 batch shape: 1024-ray forward render, config/synthetic.yml networks "
+                               "(8x256 SDF + 4x256 radiance), W-sharp weights (geometric init seed 0, density.beta=0.01 -> 5 "
+                               "sampler rounds = 640 sdf-evals/ray + 97 composited samples/ray), eval layout",
+                   "rays_per_gpu": R, "global_rays": world * R, "samples_per_ray_composited": N_COMPOSITED,
+                   "sdf_evals_per_ray": 5 * 128 + N_COMPOSITED, "parallelism": f"ray-sharded x{world}, no collective (inference)",
+                   "l2": "flushed between timed iterations (256 MB write)", "timing": "CUDA events per step, max over ranks"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "kernel_ms_per_step": {k: v["ms"] / K for k, v in prof.items()},
+        "kernel_launches_per_step": {k: v["launches"] / K for k, v in prof.items()},
+        "roofline": {"bound": "tensor", "kernel": "sdf_tc_kernel (sampler SDF evaluations)" if core.uses_tensor_cores else "mlp_tile_kernel",
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                     "traffic": None, "flop_per_launch": pts_per_launch * FLOP_PER_SDF_EVAL, "ms_per_launch": per_launch_ms,
+                     "peak_source": pk["source"] + (", sustained bf16 (kernel timed inside a step)" if core.uses_tensor_cores else "; fp32 FMA peak 148 SM x 128 FMA x 2 x 1.9 GHz"),
+                     "note": "achieved counts ALGORITHMIC flops (1 MAC = 2 flop); the kernel issues 3 bf16 MMAs per MAC"},
+        "clocks": clocks,
+    }
+    conf_c, model_c = cpu_state
+    cb = cpu_arm(conf_c, model_c.cpu(), args.cpu_rays, steps=2, warmup=1)
+    line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port", "sample": cb["sample"]}
+    return line
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        conf, model = build_params()
+        cb = cpu_arm(conf, model, args.cpu_rays, steps=args.steps, warmup=args.warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "same as --impl ours (1024-ray forward render, synthetic.yml, W-sharp); each step is a bounded "
+                                       f"sample of {args.cpu_rays} rays on the host CPU"},
+                "cpu_baseline": {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port", "sample": cb["sample"]},
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (i2sdf_b200 has no CPU path)")
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    line = gpu_arm(args, rank, world, local_rank)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

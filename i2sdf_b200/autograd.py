@@ -1,0 +1,187 @@
+"""Training-mode forward/backward of I2SDFNetwork on the CUDA core.
+
+torch.autograd is used only as the tape between the loss (I2SDFLoss, PyTorch) and three custom Functions whose
+forward AND backward are library calls (C ABI): the main-pass MLP chain, the compositing, and stand-alone SDF
+(+grad_x) evaluations for the eikonal / smoothness / bubble terms.  Weight-norm (W = g v/||v||) stays a PyTorch op
+so the Functions see the effective weights as differentiable inputs and return dL/dW for them.
+
+Reference behaviour reproduced (file:line in jingsenzhu/i2-sdf): model/network/__init__.py:99-125 (main pass),
+:162-170 (light mask, detached), :175-209 (training extras), mlp.py:107-143 (create_graph gradient).
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch.autograd import Function
+
+
+def _split_params(params, n_sdf, n_col, n_light):
+    i = 0
+    out = []
+    for n in (n_sdf, n_sdf, n_col, n_col, n_light, n_light):
+        out.append(list(params[i:i + n]))
+        i += n
+    return out      # W_sdf, b_sdf, W_col, b_col, W_light, b_light
+
+
+class _PointsFn(Function):
+    """(o, d, z) -> per-sample sdf, grad_x sdf, rgb, light-mask.  Differentiable w.r.t. the effective weights."""
+
+    @staticmethod
+    def forward(ctx, core, o, d, z, want_grad, n_sdf, n_col, n_light, *params):
+        out = core.points_forward(o, d, z, want_grad, n_light > 0, save=True)
+        ctx.core, ctx.cfg = core, (want_grad, n_sdf, n_col, n_light)
+        ctx.set_materialize_grads(False)
+        keep = [o, d, z, out["act"], out["feat"], out["s_rgb"]]
+        keep.append(out["s_light"] if out["s_light"] is not None else o.new_empty(0))
+        ctx.save_for_backward(*keep, *params)
+        s_grad = out["s_grad"] if want_grad else o.new_empty(0)
+        s_light = out["s_light"] if n_light > 0 else o.new_empty(0)
+        if not want_grad:
+            ctx.mark_non_differentiable(s_grad)
+        if n_light == 0:
+            ctx.mark_non_differentiable(s_light)
+        return out["s_sdf"], s_grad, out["s_rgb"], s_light
+
+    @staticmethod
+    def backward(ctx, g_sdf, g_grad, g_rgb, g_light):
+        core = ctx.core
+        want_grad, n_sdf, n_col, n_light = ctx.cfg
+        saved = ctx.saved_tensors
+        o, d, z, act, feat, s_rgb, s_light = saved[:7]
+        W_sdf, b_sdf, W_col, b_col, W_l, b_l = _split_params(saved[7:], n_sdf, n_col, n_light)
+        R, N = z.shape[0], z.shape[1] - 1
+        M = R * N
+        zeros = lambda ts: [torch.zeros_like(t) for t in ts]      # noqa: E731
+        dW_sdf, db_sdf, dW_col, db_col, dW_l, db_l = zeros(W_sdf), zeros(b_sdf), zeros(W_col), zeros(b_col), zeros(W_l), zeros(b_l)
+        g_feat_ptr, ld = None, 256
+        if g_rgb is not None:
+            g_x = core.color_backward(W_col, b_col, d, N, feat, s_rgb, g_rgb, dW_col, db_col)
+            ed = 3 + 6 * core.desc.multires_d
+            g_feat_ptr, ld = g_x.data_ptr() + 4 * ed, 288
+        if n_light > 0 and g_light is not None:
+            core.light_backward(W_l, b_l, feat, s_light, g_light, dW_l, db_l)
+        if g_sdf is not None or g_feat_ptr is not None or (want_grad and g_grad is not None):
+            core.sdf_backward(W_sdf, M, act, dW_sdf, db_sdf, rays=(o, d, z, N), g_sdf=g_sdf, g_feat=g_feat_ptr, g_feat_ld=ld,
+                              g_grad=g_grad if want_grad else None)
+        if g_rgb is not None:
+            del g_x
+        return (None,) * 8 + tuple(dW_sdf + db_sdf + dW_col + db_col + dW_l + db_l)
+
+
+class _CompositeFn(Function):
+    """Laplace density + alpha compositing + per-ray reductions; differentiable w.r.t. per-sample inputs and beta."""
+
+    @staticmethod
+    def forward(ctx, core, z, dnorm, beta_param, s_sdf, s_rgb, s_grad, s_light, want_normal, want_light):
+        sg = s_grad if want_normal else None
+        sl = s_light if want_light else None
+        rgb, depth, wsum, normal, light = core.composite_forward(z, dnorm, beta_param, s_sdf, s_rgb, sg, sl)
+        ctx.core, ctx.cfg = core, (want_normal, want_light)
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(z, dnorm, beta_param, s_sdf, s_rgb, s_grad, s_light)
+        normal = normal if want_normal else z.new_empty(0)
+        light = light if want_light else z.new_empty(0)
+        return rgb, depth, wsum, normal, light
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth, g_wsum, g_normal, g_light):
+        want_normal, want_light = ctx.cfg
+        z, dnorm, beta_param, s_sdf, s_rgb, s_grad, s_light = ctx.saved_tensors
+        o_sdf, o_rgb, o_grad, o_light, o_beta = ctx.core.composite_backward(
+            z, dnorm, beta_param, s_sdf, s_rgb, s_grad if want_normal else None, s_light if want_light else None,
+            g_rgb, g_depth, g_wsum, g_normal if want_normal else None, g_light if want_light else None)
+        return (None, None, None, o_beta.reshape(beta_param.shape), o_sdf, o_rgb,
+                o_grad if want_normal else None, o_light if want_light else None, None, None)
+
+
+class _SdfPointsFn(Function):
+    """x [M,3] -> (sdf [M], grad_x sdf [M,3]); differentiable (incl. second order) w.r.t. the SDF stack's weights."""
+
+    @staticmethod
+    def forward(ctx, core, pts, want_grad, n_sdf, *params):
+        pts = pts.detach().contiguous().float()
+        M = pts.shape[0]
+        act = torch.empty(n_sdf - 1, M, 256, device=pts.device)
+        sdf, _, grad = core.sdf_forward(pts, want_grad=want_grad, save_act=act)
+        ctx.core, ctx.cfg = core, (want_grad, n_sdf)
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(pts, act, *params)
+        if not want_grad:
+            grad = pts.new_empty(0)
+            ctx.mark_non_differentiable(grad)
+        return sdf, grad
+
+    @staticmethod
+    def backward(ctx, g_sdf, g_grad):
+        want_grad, n_sdf = ctx.cfg
+        saved = ctx.saved_tensors
+        pts, act = saved[:2]
+        W, b = list(saved[2:2 + n_sdf]), list(saved[2 + n_sdf:2 + 2 * n_sdf])
+        dW, db = [torch.zeros_like(t) for t in W], [torch.zeros_like(t) for t in b]
+        if g_sdf is not None or (want_grad and g_grad is not None):
+            ctx.core.sdf_backward(W, pts.shape[0], act, dW, db, pts=pts, g_sdf=g_sdf, g_grad=g_grad if want_grad else None)
+        return (None,) * 4 + tuple(dW + db)
+
+
+def _sdf_params(model):
+    W, b = model.implicit_network.effective()
+    return [w.contiguous() for w in W], list(b)
+
+
+def sdf_with_grad(model, x):
+    """(sdf [M], None, grad [M,3]) with autograd support — ImplicitNetwork.gradient in training (mlp.py:107-118)."""
+    core = model._ready_core()
+    W, b = _sdf_params(model)
+    sdf, grad = _SdfPointsFn.apply(core, x, True, len(W), *W, *b)
+    return sdf, None, grad
+
+
+def forward_train(model, core, input, predict_only=False):
+    """I2SDFNetwork.forward with self.training == True (model/network/__init__.py:80-209)."""
+    ov = getattr(model, "_tape_override", None) or {}
+    o, d, dnorm = core.rays(input["uv"], input["pose"], input["intrinsics"])
+    R, dev = o.shape[0], o.device
+    beta = model.density.beta
+    if "z_all" in ov:                                   # test hook: reference z's
+        z, z_eik = ov["z_all"].to(dev).contiguous(), ov["z_eik"].to(dev).reshape(-1).contiguous()
+    else:
+        tape = {k: ov[k] for k in ("jitter", "u_final", "extra_perm", "eik_idx") if k in ov} or model._draw_sampler_tape(R, dev)
+        z, z_eik = core.sample(o, d, beta.detach(), tape)
+    Ws, bs = model.effective_weights()
+    n_sdf = model.implicit_network.num_layers - 1
+    n_col = model.rendering_network.num_layers - 1
+    n_light = (model.light_network.num_layers - 1) if model.use_light else 0
+    W_sdf, b_sdf = Ws[:n_sdf], bs[:n_sdf]
+    W_col, b_col = Ws[n_sdf:n_sdf + n_col], bs[n_sdf:n_sdf + n_col]
+    W_l, b_l = Ws[n_sdf + n_col:], bs[n_sdf + n_col:]
+    want_grad = bool(model.use_normal)                  # returns_grad (network/__init__.py:109) in training
+    params = [w.contiguous() for w in W_sdf] + list(b_sdf) + [w.contiguous() for w in W_col] + list(b_col) + \
+             [w.contiguous() for w in W_l] + list(b_l)
+    s_sdf, s_grad, s_rgb, s_light = _PointsFn.apply(core, o, d, z, want_grad, n_sdf, n_col, n_light, *params)
+    rgb, depth, wsum, normal, light = _CompositeFn.apply(core, z, dnorm, beta, s_sdf, s_rgb, s_grad, s_light,
+                                                         want_grad and not predict_only, n_light > 0)
+    res = {"rgb_values": rgb, "depth_values": depth, "weight_sum": wsum[:, None]}
+    if n_light > 0:
+        res["light_mask"] = light[:, None]
+    if predict_only:
+        return res
+    # ---- eikonal / smoothness points (network/__init__.py:175-193)
+    bsph = model.scene_bounding_sphere
+    eik_u = ov["eik_uniform"].to(dev) if "eik_uniform" in ov else torch.empty(R, 3, device=dev).uniform_(-bsph, bsph)
+    near = o + z_eik[:, None] * d
+    nbr_u = ov["nbr_uniform"].to(dev) if "nbr_uniform" in ov else torch.empty_like(near).uniform_(-0.005, 0.005)
+    pts = torch.cat([eik_u, near, near + nbr_u], 0)
+    sdf_params = [w.contiguous() for w in W_sdf] + list(b_sdf)
+    _, g = _SdfPointsFn.apply(core, pts, True, n_sdf, *sdf_params)
+    res["grad_theta"] = g[:2 * R]
+    nrm = F.normalize(g[R:], dim=1, eps=1e-6)
+    res["diff_norm"] = torch.norm(nrm[:R] - nrm[R:], dim=1)
+    # ---- bubble loss points (:196-201)
+    if "pointcloud" in input:
+        idx = int(ov["bubble_cam_idx"]) if "bubble_cam_idx" in ov else np.random.randint(0, R)
+        sp = torch.cat([input["pointcloud"].to(dev).float(), o[idx][None]], 0)
+        ssdf, _ = _SdfPointsFn.apply(core, sp, False, n_sdf, *sdf_params)
+        res["surface_sdf"] = ssdf[:-1, None]
+    if model.use_normal:
+        res["normal_values"] = normal
+    return res

@@ -103,6 +103,17 @@ class RenderCore:
             self._ws_bytes = nbytes
         return self._ws
 
+    # ---- measurement hook
+    def profile(self, enable: bool):
+        check(self.lib.i2sdf_profile_enable(self.h, int(enable)), "i2sdf_profile_enable")
+
+    def profile_read(self):
+        ms = (C.c_float * 4)()
+        n = (C.c_int64 * 4)()
+        check(self.lib.i2sdf_profile_read(self.h, ms, n), "i2sdf_profile_read")
+        kinds = ("sampler_sdf", "main_mlp", "sampler_rays", "misc")
+        return {k: dict(ms=float(ms[i]), launches=int(n[i])) for i, k in enumerate(kinds)}
+
     # ---- weights
     def pack(self, weights: List[torch.Tensor], biases: List[torch.Tensor]):
         """weights[i]: effective [out,in] fp32 weight of layer i (SDF layers, colour layers, light layers)."""
@@ -126,7 +137,7 @@ class RenderCore:
         return o, d, dn
 
     def sdf_forward(self, pts, want_feat=False, want_grad=False, save_act=None):
-        pts = _f32(pts, self.device)
+        pts = _f32(pts.detach(), self.device)
         M = pts.shape[0]
         sdf = torch.empty(M, device=self.device)
         feat = torch.empty(M, 256, device=self.device) if want_feat else None
@@ -141,6 +152,7 @@ class RenderCore:
     def sample(self, o, d, beta_param, tape: Optional[Dict[str, torch.Tensor]] = None, want_info=False):
         """ErrorBoundSampler.get_z_vals.  tape (training): jitter [R,128], u_final [R,64] fp32;
         extra_perm: callable n -> LongTensor[32] (drawn after one 8-byte D2H of n) or int tensor; eik_idx [R]."""
+        o, d = _f32(o, self.device), _f32(d, self.device)
         R = o.shape[0]
         tape = tape or {}
         ws = self.workspace(R)
@@ -169,25 +181,123 @@ class RenderCore:
         return z, z_eik
 
     def sampler_round_debug(self, z, sdf, beta_param, beta_in, upsample: bool, u_tape=None):
+        dev = self.device
+        z, sdf, beta_in = _f32(z, dev), _f32(sdf, dev), _f32(beta_in, dev)
+        u_tape = None if u_tape is None else _f32(u_tape, dev)
         R, n = z.shape
         ns = self.desc.n_samples_eval if upsample else self.desc.n_samples
-        dev = self.device
         out = dict(beta=torch.empty(R, device=dev), cdf=torch.empty(R, n, device=dev),
                    inds=torch.empty(R, ns, dtype=torch.int32, device=dev), samples=torch.empty(R, ns, device=dev))
         if upsample:
             out["z_merged"] = torch.empty(R, n + ns, device=dev)
             out["src"] = torch.empty(R, n + ns, dtype=torch.int32, device=dev)
         check(self.lib.i2sdf_sampler_round_debug(
-            self.h, _ptr(_f32(z, dev)), _ptr(_f32(sdf, dev)), R, n, _ptr(beta_param), _ptr(_f32(beta_in, dev)), int(upsample),
-            _ptr(None if u_tape is None else _f32(u_tape, dev)), _ptr(out["beta"]), _ptr(out["cdf"]), _ptr(out["inds"]),
+            self.h, _ptr(z), _ptr(sdf), R, n, _ptr(beta_param), _ptr(beta_in), int(upsample),
+            _ptr(u_tape), _ptr(out["beta"]), _ptr(out["cdf"]), _ptr(out["inds"]),
             _ptr(out["samples"]), _ptr(out.get("z_merged")), _ptr(out.get("src")), self._stream()), "i2sdf_sampler_round_debug")
         return out
 
+    # ---- training split: forward pieces + backward
+    def backward_workspace(self, M: int) -> torch.Tensor:
+        nbytes = self.lib.i2sdf_backward_workspace_bytes(self.h, M)
+        if getattr(self, "_bws", None) is None or self._bws.numel() < nbytes:
+            self._bws = None
+            self._bws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._bws
+
+    @staticmethod
+    def _ptr_array(tensors):
+        return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+    def points_forward(self, o, d, z, want_grad, want_light, save=True):
+        dev = self.device
+        o, d, z = _f32(o, dev), _f32(d, dev), _f32(z, dev)
+        R, N = z.shape[0], z.shape[1] - 1
+        M = R * N
+        L = self.desc.n_sdf_layers
+        out = dict(s_sdf=torch.empty(M, device=dev), s_rgb=torch.empty(M, 3, device=dev), feat=torch.empty(M, 256, device=dev))
+        out["s_grad"] = torch.empty(M, 3, device=dev) if want_grad else None
+        out["s_light"] = torch.empty(M, device=dev) if want_light else None
+        out["act"] = torch.empty(L - 1, M, 256, device=dev) if save else None
+        ws = self.workspace(R)
+        check(self.lib.i2sdf_points_forward(self.h, _ptr(o), _ptr(d), _ptr(z), R, N, _ptr(out["s_sdf"]), _ptr(out["s_grad"]),
+                                            _ptr(out["s_rgb"]), _ptr(out["s_light"]), _ptr(out["feat"]), _ptr(out["act"]),
+                                            _ptr(ws), self._ws_bytes, self._stream()), "i2sdf_points_forward")
+        return out
+
+    def composite_forward(self, z, dnorm, beta_param, s_sdf, s_rgb, s_grad, s_light):
+        dev = self.device
+        R, N = z.shape[0], z.shape[1] - 1
+        rgb, depth, wsum = torch.empty(R, 3, device=dev), torch.empty(R, device=dev), torch.empty(R, device=dev)
+        normal = torch.empty(R, 3, device=dev) if s_grad is not None else None
+        light = torch.empty(R, device=dev) if s_light is not None else None
+        check(self.lib.i2sdf_composite_forward(self.h, _ptr(z), _ptr(dnorm), _ptr(s_sdf), _ptr(s_rgb), _ptr(s_grad), _ptr(s_light),
+                                               _ptr(beta_param), R, N, _ptr(rgb), _ptr(depth), _ptr(wsum), _ptr(normal), _ptr(light),
+                                               _ptr(None), self._stream()), "i2sdf_composite_forward")
+        return rgb, depth, wsum, normal, light
+
+    def composite_backward(self, z, dnorm, beta_param, s_sdf, s_rgb, s_grad, s_light, g_rgb, g_depth, g_wsum, g_normal, g_light):
+        dev = self.device
+        R, N = z.shape[0], z.shape[1] - 1
+        M = R * N
+        f = lambda t: None if t is None else _f32(t, dev)        # noqa: E731
+        g_rgb, g_depth, g_wsum, g_normal, g_light = f(g_rgb), f(g_depth), f(g_wsum), f(g_normal), f(g_light)
+        o_sdf, o_rgb = torch.empty(M, device=dev), torch.empty(M, 3, device=dev)
+        o_grad = torch.empty(M, 3, device=dev) if s_grad is not None else None
+        o_light = torch.empty(M, device=dev) if s_light is not None else None
+        o_beta = torch.zeros(1, device=dev)
+        check(self.lib.i2sdf_composite_backward(self.h, _ptr(z), _ptr(dnorm), _ptr(s_sdf), _ptr(s_rgb), _ptr(s_grad), _ptr(s_light),
+                                                _ptr(beta_param), R, N, _ptr(g_rgb), _ptr(g_depth), _ptr(g_wsum),
+                                                _ptr(g_normal if s_grad is not None else None), _ptr(g_light if s_light is not None else None),
+                                                _ptr(o_sdf), _ptr(o_rgb), _ptr(o_grad), _ptr(o_light), _ptr(o_beta), self._stream()),
+              "i2sdf_composite_backward")
+        return o_sdf, o_rgb, o_grad, o_light, o_beta
+
+    def color_backward(self, Ws, bs, dirs, ns, feat, s_rgb, g_rgb, dWs, dbs):
+        dev = self.device
+        M = feat.shape[0]
+        g_x = torch.empty(M, 288, device=dev)
+        bws = self.backward_workspace(M)
+        g_rgb = _f32(g_rgb, dev)
+        check(self.lib.i2sdf_color_backward(self.h, self._ptr_array(Ws), self._ptr_array(bs), _ptr(dirs), ns, _ptr(feat), _ptr(s_rgb),
+                                            _ptr(g_rgb), M, self._ptr_array(dWs), self._ptr_array(dbs), _ptr(g_x), _ptr(bws),
+                                            bws.numel(), self._stream()), "i2sdf_color_backward")
+        return g_x
+
+    def light_backward(self, Ws, bs, feat, s_light, g_light, dWs, dbs):
+        M = feat.shape[0]
+        bws = self.backward_workspace(M)
+        g_light = _f32(g_light, self.device)
+        check(self.lib.i2sdf_light_backward(self.h, self._ptr_array(Ws), self._ptr_array(bs), _ptr(feat), _ptr(s_light), _ptr(g_light), M,
+                                            self._ptr_array(dWs), self._ptr_array(dbs), _ptr(bws), bws.numel(), self._stream()),
+              "i2sdf_light_backward")
+
+    def sdf_backward(self, Ws, M, act, dWs, dbs, pts=None, rays=None, g_sdf=None, g_feat=None, g_feat_ld=256, g_grad=None):
+        """rays = (o, d, z [R,zstride], ns).  g_feat may be a (data_ptr, ld) view into a wider buffer."""
+        dev = self.device
+        bws = self.backward_workspace(M)
+        g_sdf = None if g_sdf is None else _f32(g_sdf, dev)
+        g_grad = None if g_grad is None else _f32(g_grad, dev)
+        if rays is not None:
+            o, d, z, ns = rays
+            po, pd, pz, zs, pp = _ptr(o), _ptr(d), _ptr(z), z.shape[1], _ptr(None)
+        else:
+            po = pd = pz = _ptr(None)
+            zs, ns, pp = 0, 1, _ptr(pts)
+        gf = C.c_void_p(0)
+        if g_feat is not None:
+            gf = C.c_void_p(g_feat if isinstance(g_feat, int) else g_feat.data_ptr())
+        check(self.lib.i2sdf_sdf_backward(self.h, self._ptr_array(Ws), pp, po, pd, pz, zs, ns, M, _ptr(act), _ptr(g_sdf), gf, g_feat_ld,
+                                          _ptr(g_grad), self._ptr_array(dWs), self._ptr_array(dbs), _ptr(bws), bws.numel(), self._stream()),
+              "i2sdf_sdf_backward")
+        self._keep = (g_sdf, g_grad)
+
     def render(self, o, d, dnorm, z, beta_param, want_normal=True, want_light=False, per_sample=False, save=None):
         """Main pass + compositing.  z [R,N+1].  Returns dict of per-ray tensors (+ per-sample ones if asked)."""
+        dev = self.device
+        o, d, dnorm, z = _f32(o, dev), _f32(d, dev), _f32(dnorm, dev), _f32(z, dev)
         R, N1 = z.shape
         N = N1 - 1
-        dev = self.device
         ws = self.workspace(R)
         out = dict(rgb=torch.empty(R, 3, device=dev), depth=torch.empty(R, device=dev), weight_sum=torch.empty(R, device=dev))
         if want_normal:
@@ -203,7 +313,7 @@ class RenderCore:
                 ps["s_light"] = torch.empty(R * N, device=dev)
         save_bytes = 0 if save is None else save.numel() * save.element_size()
         check(self.lib.i2sdf_render_forward(
-            self.h, _ptr(o), _ptr(d), _ptr(dnorm), _ptr(_f32(z, dev)), R, N, _ptr(beta_param),
+            self.h, _ptr(o), _ptr(d), _ptr(dnorm), _ptr(z), R, N, _ptr(beta_param),
             _ptr(out["rgb"]), _ptr(out["depth"]), _ptr(out["weight_sum"]), _ptr(out.get("normal")), _ptr(out.get("light")),
             _ptr(ps.get("s_sdf")), _ptr(ps.get("s_grad")), _ptr(ps.get("s_rgb")), _ptr(ps.get("s_w")), _ptr(ps.get("s_light")),
             _ptr(save), save_bytes, _ptr(ws), self._ws_bytes, self._stream()), "i2sdf_render_forward")

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <vector>
 #include "common.cuh"
 
 namespace i2sdf {
@@ -26,6 +27,20 @@ int launch_sampler_round_debug(const i2sdf_handle*, const float*, const float*, 
                                const float*, float*, float*, int*, float*, float*, int*, cudaStream_t);
 int launch_composite(const i2sdf_handle*, const float*, const float*, const float*, const float*, const float*, const float*,
                      const float*, long long, int, float*, float*, float*, float*, float*, float*, cudaStream_t);
+// declared in backward.cu
+namespace bwd { struct PointSrc { const float* pts; const float* o; const float* d; const float* z; int zstride; int ns; }; }
+size_t sdf_backward_ws_floats(const i2sdf_handle*, long long);
+size_t color_backward_ws_floats(const i2sdf_handle*, long long);
+size_t light_backward_ws_floats(const i2sdf_handle*, long long);
+int sdf_backward(const i2sdf_handle*, const bwd::PointSrc&, long long, const float* const*, const float*, const float*, const float*, int,
+                 const float*, float* const*, float* const*, float*, cudaStream_t);
+int color_backward(const i2sdf_handle*, long long, int, const float*, const float* const*, const float* const*, const float*, const float*,
+                   const float*, float* const*, float* const*, float*, float**, int*, cudaStream_t);
+int light_backward(const i2sdf_handle*, long long, const float* const*, const float* const*, const float*, const float*, const float*,
+                   float* const*, float* const*, float*, cudaStream_t);
+int launch_composite_backward(const i2sdf_handle*, const float*, const float*, const float*, const float*, const float*, const float*,
+                              const float*, long long, int, const float*, const float*, const float*, const float*, const float*, float*,
+                              float*, float*, float*, float*, cudaStream_t);
 // declared in mlp_tc.cu
 int tc_create(i2sdf_handle* h);
 void tc_destroy(i2sdf_handle* h);
@@ -75,6 +90,31 @@ static int run_pack(const PackJob& J, cudaStream_t st) {
 }
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---- measurement hook ---------------------------------------------------------------------------
+struct Prof {
+    bool on = false;
+    std::vector<cudaEvent_t> ev[4];     // start/stop pairs
+    size_t used[4] = {0, 0, 0, 0};
+    long long launches[4] = {0, 0, 0, 0};
+};
+struct ProfScope {
+    Prof* p; int kind; cudaStream_t st; int nlaunch;
+    ProfScope(const i2sdf_handle* h, int kind_, cudaStream_t st_, int nlaunch_ = 1) : p((Prof*)h->prof), kind(kind_), st(st_), nlaunch(nlaunch_) {
+        if (!p || !p->on) { p = nullptr; return; }
+        if (p->used[kind] + 2 > p->ev[kind].size()) {
+            cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+            p->ev[kind].push_back(a); p->ev[kind].push_back(b);
+        }
+        cudaEventRecord(p->ev[kind][p->used[kind]], st);
+    }
+    ~ProfScope() {
+        if (!p) return;
+        cudaEventRecord(p->ev[kind][p->used[kind] + 1], st);
+        p->used[kind] += 2;
+        p->launches[kind] += nlaunch;
+    }
+};
 
 }  // namespace i2sdf
 
@@ -161,6 +201,7 @@ int i2sdf_create(const i2sdf_desc* d, int device, i2sdf_handle** out) {
     const char* env = getenv("I2SDF_SIMT");
     h->use_tc = !(env && env[0] == '1');
     h->tc = nullptr;
+    h->prof = new Prof();
     if (h->use_tc) {
         int rc = tc_create(h);
         if (rc != I2SDF_OK) { cudaFree(h->pool); free(h); return rc; }
@@ -174,6 +215,7 @@ int i2sdf_create(const i2sdf_desc* d, int device, i2sdf_handle** out) {
 int i2sdf_destroy(i2sdf_handle* h) {
     if (!h) return I2SDF_OK;
     if (h->tc) tc_destroy(h);
+    if (h->prof) { Prof* p = (Prof*)h->prof; for (auto& v : p->ev) for (auto e : v) cudaEventDestroy(e); delete p; }
     cudaFree(h->pool);
     free(h);
     return I2SDF_OK;
@@ -187,6 +229,7 @@ int i2sdf_pack_weights(i2sdf_handle* h, const float* const* W, const float* cons
     cudaStream_t st = (cudaStream_t)stream;
     const NetDev& n = h->net;
     int li = 0, rc;
+    ProfScope ps(h, 3, st, 3 * h->n_layers);
     for (int l = 0; l < n.L; ++l, ++li) {
         const int outd = h->lay_out[li], in = h->lay_in[li];
         const bool last = (l == n.L - 1);
@@ -253,11 +296,13 @@ size_t i2sdf_workspace_bytes(const i2sdf_handle* h, int64_t R, int training) {
 int i2sdf_rays(i2sdf_handle* h, const float* uv, const float* pose, const float* intr, int B, int P, float* o, float* d,
                float* dnorm, void* stream) {
     if (!h || !uv || !pose || !intr || !o || !d || !dnorm) { set_error("null argument"); return I2SDF_E_INVALID; }
+    ProfScope ps(h, 3, (cudaStream_t)stream);
     return launch_rays(uv, pose, intr, B, P, o, d, dnorm, (cudaStream_t)stream);
 }
 
 static int run_mlp(const i2sdf_handle* h, const MlpParams& p, cudaStream_t st) {
     const bool sdf_only = !p.out_feat && !p.out_grad && !p.want_color && !p.want_light && !p.save_act;
+    ProfScope ps(h, sdf_only ? 0 : 1, st);
     if (h->use_tc && sdf_only) return tc_launch_sdf(h, p, st);
     return launch_mlp_simt(h, p, st);
 }
@@ -285,7 +330,7 @@ int i2sdf_sampler_rounds(i2sdf_handle* h, const float* o, const float* d, int64_
     cudaStream_t st = (cudaStream_t)stream;
     SamplerWs W = carve_sampler_ws(h, R, (float*)workspace);
     int rc;
-    if ((rc = launch_sampler_init(h, W, R, jitter, h->desc.lemma2_coeff, st))) return rc;
+    { ProfScope ps(h, 2, st); if ((rc = launch_sampler_init(h, W, R, jitter, h->desc.lemma2_coeff, st))) return rc; }
     for (int k = 0; k < h->smp.max_iters; ++k) {
         MlpParams p{};
         p.ray_o = o; p.ray_d = d; p.zarr = W.samples; p.zstride = h->smp.n_eval; p.ns = h->smp.n_eval;
@@ -293,6 +338,7 @@ int i2sdf_sampler_rounds(i2sdf_handle* h, const float* o, const float* d, int64_
         p.beta_max = W.beta_max; p.beta_param = beta_param; p.beta_min = h->smp.beta_min; p.round_idx = k;
         p.net = h->net;
         if ((rc = run_mlp(h, p, st))) return rc;
+        ProfScope ps(h, 2, st, 2);
         if ((rc = launch_sampler_round(h, W, R, k, 0, beta_param, nullptr, st))) return rc;
         if ((rc = launch_sampler_round(h, W, R, k, 1, beta_param, u_final, st))) return rc;
     }
@@ -304,6 +350,7 @@ int i2sdf_sampler_finalize(i2sdf_handle* h, int64_t R, const float* beta_param, 
     if (!h || !beta_param || !out_z || !workspace) { set_error("null argument"); return I2SDF_E_INVALID; }
     if (workspace_bytes < i2sdf_workspace_bytes(h, R, 0)) { set_error("sampler: workspace too small"); return I2SDF_E_WORKSPACE; }
     SamplerWs W = carve_sampler_ws(h, R, (float*)workspace);
+    ProfScope ps(h, 2, (cudaStream_t)stream);
     return launch_sampler_finalize(h, W, R, beta_param, extra_idx, eik_idx, out_z, out_z_eik, out_info, (cudaStream_t)stream);
 }
 
@@ -332,6 +379,105 @@ int i2sdf_sampler_round_debug(i2sdf_handle* h, const float* z, const float* sdf,
     if (n < 2 || n > h->smp.n_eval * h->smp.max_iters) { set_error("round_debug: n=%d out of range", n); return I2SDF_E_INVALID; }
     return launch_sampler_round_debug(h, z, sdf, R, n, beta_param, beta_in, force_upsample, u_tape, out_beta, out_cdf, out_inds,
                                       out_samples, out_z_merged, out_src, (cudaStream_t)stream);
+}
+
+size_t i2sdf_backward_workspace_bytes(const i2sdf_handle* h, int64_t M) {
+    if (!h || M < 0) return 0;
+    size_t a = sdf_backward_ws_floats(h, M), b = color_backward_ws_floats(h, M), c = light_backward_ws_floats(h, M);
+    size_t m = a > b ? a : b;
+    m = m > c ? m : c;
+    return (m + 64) * sizeof(float);
+}
+
+int i2sdf_points_forward(i2sdf_handle* h, const float* o, const float* d, const float* z, int64_t R, int N, float* s_sdf, float* s_grad,
+                         float* s_rgb, float* s_light, float* s_feat, float* save_act, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h || !o || !d || !z || !s_sdf) { set_error("null argument"); return I2SDF_E_INVALID; }
+    if (N < 1 || N > 128) { set_error("points_forward: N=%d unsupported", N); return I2SDF_E_INVALID; }
+    if (s_light && h->net.Ll == 0) { set_error("points_forward: no light head"); return I2SDF_E_INVALID; }
+    MlpParams p{};
+    p.ray_o = o; p.ray_d = d; p.zarr = z; p.zstride = N + 1; p.ns = N; p.M = (long long)R * N; p.round_idx = -1; p.beta_min = h->smp.beta_min;
+    p.out_sdf = s_sdf; p.out_grad = s_grad; p.out_rgb = s_rgb; p.out_light = s_light; p.out_feat = s_feat;
+    p.want_color = s_rgb != nullptr; p.want_light = s_light != nullptr; p.save_act = save_act;
+    if (s_grad && !save_act) {
+        if (!workspace || workspace_bytes < ws_scratch_floats(h) * sizeof(float)) { set_error("points_forward: workspace too small"); return I2SDF_E_WORKSPACE; }
+        p.scratch = (float*)workspace;
+    }
+    p.net = h->net;
+    return run_mlp(h, p, (cudaStream_t)stream);
+}
+
+int i2sdf_composite_forward(i2sdf_handle* h, const float* z, const float* dnorm, const float* s_sdf, const float* s_rgb, const float* s_grad,
+                            const float* s_light, const float* beta_param, int64_t R, int N, float* rgb, float* depth, float* weight_sum,
+                            float* normal, float* light, float* s_w, void* stream) {
+    if (!h || !z || !dnorm || !s_sdf || !beta_param) { set_error("null argument"); return I2SDF_E_INVALID; }
+    ProfScope ps(h, 3, (cudaStream_t)stream);
+    return launch_composite(h, z, dnorm, s_sdf, s_rgb, s_grad, s_light, beta_param, R, N, rgb, depth, weight_sum, normal, light, s_w, (cudaStream_t)stream);
+}
+
+int i2sdf_composite_backward(i2sdf_handle* h, const float* z, const float* dnorm, const float* s_sdf, const float* s_rgb, const float* s_grad,
+                             const float* s_light, const float* beta_param, int64_t R, int N, const float* g_rgb, const float* g_depth,
+                             const float* g_wsum, const float* g_normal, const float* g_light, float* o_sdf, float* o_rgb, float* o_grad,
+                             float* o_light, float* o_beta, void* stream) {
+    if (!h || !z || !dnorm || !s_sdf || !beta_param || !o_sdf) { set_error("null argument"); return I2SDF_E_INVALID; }
+    if ((g_rgb && !s_rgb) || (g_normal && !s_grad)) { set_error("composite_backward: missing forward tensors"); return I2SDF_E_INVALID; }
+    ProfScope ps(h, 3, (cudaStream_t)stream);
+    return launch_composite_backward(h, z, dnorm, s_sdf, s_rgb, s_grad, s_light, beta_param, R, N, g_rgb, g_depth, g_wsum, g_normal, g_light,
+                                     o_sdf, o_rgb, o_grad, o_light, o_beta, (cudaStream_t)stream);
+}
+
+int i2sdf_color_backward(i2sdf_handle* h, const float* const* W, const float* const* b, const float* dirs, int ns, const float* feat,
+                         const float* s_rgb, const float* g_rgb, int64_t M, float* const* dW, float* const* db, float* g_x, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+    if (!h || !W || !b || !dirs || !feat || !s_rgb || !g_rgb || !dW || !db || !g_x || !workspace) { set_error("null argument"); return I2SDF_E_INVALID; }
+    if (workspace_bytes < i2sdf_backward_workspace_bytes(h, M)) { set_error("color_backward: workspace too small"); return I2SDF_E_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope ps(h, 1, st, 4 * h->net.Lc);
+    float* gf = nullptr; int ld = 0;
+    int rc = color_backward(h, M, ns, dirs, W, b, feat, s_rgb, g_rgb, dW, db, (float*)workspace, &gf, &ld, st);
+    if (rc) return rc;
+    // the adjoint of the stack input lives at the head of the workspace's second [M][288] block: copy it out
+    I2SDF_CUDA_CHECK(cudaMemcpyAsync(g_x, gf - h->net.ed, (size_t)M * 288 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return I2SDF_OK;
+}
+
+int i2sdf_light_backward(i2sdf_handle* h, const float* const* W, const float* const* b, const float* feat, const float* s_light,
+                         const float* g_light, int64_t M, float* const* dW, float* const* db, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h || !W || !b || !feat || !s_light || !g_light || !dW || !db || !workspace) { set_error("null argument"); return I2SDF_E_INVALID; }
+    if (h->net.Ll != 2) { set_error("light_backward: network has no light head"); return I2SDF_E_INVALID; }
+    if (workspace_bytes < i2sdf_backward_workspace_bytes(h, M)) { set_error("light_backward: workspace too small"); return I2SDF_E_WORKSPACE; }
+    ProfScope ps(h, 1, (cudaStream_t)stream, 8);
+    return light_backward(h, M, W, b, feat, s_light, g_light, dW, db, (float*)workspace, (cudaStream_t)stream);
+}
+
+int i2sdf_sdf_backward(i2sdf_handle* h, const float* const* W, const float* pts, const float* o, const float* d, const float* z, int zstride,
+                       int ns, int64_t M, const float* act, const float* g_sdf, const float* g_feat, int g_feat_ld, const float* g_grad,
+                       float* const* dW, float* const* db, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h || !W || !act || !dW || !db || !workspace || (!pts && (!o || !d || !z))) { set_error("null argument"); return I2SDF_E_INVALID; }
+    if (workspace_bytes < i2sdf_backward_workspace_bytes(h, M)) { set_error("sdf_backward: workspace too small"); return I2SDF_E_WORKSPACE; }
+    bwd::PointSrc S{pts, o, d, z, zstride, ns > 0 ? ns : 1};
+    ProfScope ps(h, 1, (cudaStream_t)stream, 10 * h->net.L);
+    return sdf_backward(h, S, M, W, act, g_sdf, g_feat, g_feat_ld, g_grad, dW, db, (float*)workspace, (cudaStream_t)stream);
+}
+
+int i2sdf_profile_enable(i2sdf_handle* h, int enable) {
+    if (!h) { set_error("null handle"); return I2SDF_E_INVALID; }
+    Prof* p = (Prof*)h->prof;
+    p->on = enable != 0;
+    if (enable) for (int k = 0; k < 4; ++k) { p->used[k] = 0; p->launches[k] = 0; }
+    return I2SDF_OK;
+}
+
+int i2sdf_profile_read(i2sdf_handle* h, float ms[4], int64_t launches[4]) {
+    if (!h || !ms || !launches) { set_error("null argument"); return I2SDF_E_INVALID; }
+    Prof* p = (Prof*)h->prof;
+    I2SDF_CUDA_CHECK(cudaDeviceSynchronize());
+    for (int k = 0; k < 4; ++k) {
+        float tot = 0.f;
+        for (size_t i = 0; i + 1 < p->used[k]; i += 2) { float t = 0.f; cudaEventElapsedTime(&t, p->ev[k][i], p->ev[k][i + 1]); tot += t; }
+        ms[k] = tot;
+        launches[k] = p->launches[k];
+    }
+    return I2SDF_OK;
 }
 
 size_t i2sdf_saved_bytes(const i2sdf_handle* h, int64_t R, int N) {
@@ -367,6 +513,7 @@ int i2sdf_render_forward(i2sdf_handle* h, const float* o, const float* d, const 
     p.net = h->net;
     int rc = run_mlp(h, p, st);
     if (rc) return rc;
+    ProfScope ps(h, 3, st);
     return launch_composite(h, z, dnorm, s_sdf, s_rgb, s_grad, s_light, beta_param, R, N, rgb, depth, weight_sum, normal, light, s_w, st);
 }
 

@@ -62,6 +62,7 @@ struct i2sdf_handle {
     int lay_in[2 * i2sdf::kMaxLayers + 4];
     bool use_tc;             // tcgen05 path available (set by env I2SDF_SIMT=1 -> false)
     void* tc;                // opaque tcgen05 packed state (see mlp_tc.cu)
+    void* prof;              // measurement hook state (c_abi.cu)
 };
 
 namespace i2sdf {

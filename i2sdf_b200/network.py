@@ -259,6 +259,7 @@ class I2SDFNetwork(nn.Module):
         self.implicit_network._owner = weakref.ref(self)
         self._core_obj = None
         self._packed_key = None
+        self._tape_override = None       # test hook: dict of RNG tapes / reference z's (see autograd.forward_train)
 
     def get_param_groups(self, lr):
         return [{"params": self.parameters(), "lr": lr}]
@@ -301,19 +302,18 @@ class I2SDFNetwork(nn.Module):
     def _draw_sampler_tape(self, R, device):
         """Same draws, same order, same devices as the reference (ray_sampler.py:39,190,223,233)."""
         rs = self.ray_sampler
-        tape = {
+        n_out = rs.N_samples + 2 + rs.N_samples_extra
+        return {
             "jitter": torch.rand(R, rs.N_samples_eval, device=device),
             "u_final": torch.rand(R, rs.N_samples, device=device),
             "extra_perm": lambda n: torch.randperm(n)[:rs.N_samples_extra],          # CPU generator, as the reference
+            "eik_idx_fn": lambda: torch.randint(n_out, (R,), device=device),
         }
-        n_out = rs.N_samples + 2 + rs.N_samples_extra
-        tape["eik_idx_fn"] = lambda: torch.randint(n_out, (R,), device=device)
-        return tape
 
     # ------------------------------------------------------------------ forward
     def forward(self, input, predict_only=False):
         core = self._ready_core()
-        if self.training and torch.is_grad_enabled():
+        if self.training:
             from .autograd import forward_train
             return forward_train(self, core, input, predict_only)
         return self._forward_nograd(core, input, predict_only)
@@ -323,22 +323,13 @@ class I2SDFNetwork(nn.Module):
         o, d, dnorm = core.rays(input["uv"], input["pose"], input["intrinsics"])
         R = o.shape[0]
         beta = self.density.beta.detach()
-        tape = self._draw_sampler_tape(R, o.device) if self.training else None
-        z, z_eik = core.sample(o, d, beta, tape)
-        want_normal = (not predict_only) and (self.use_normal or not self.training)
+        z, z_eik = core.sample(o, d, beta, None)
+        want_normal = not predict_only
         out = core.render(o, d, dnorm, z, beta, want_normal=want_normal, want_light=self.use_light)
         res = {"rgb_values": out["rgb"], "depth_values": out["depth"], "weight_sum": out["weight_sum"][:, None]}
         if self.use_light:
             res["light_mask"] = out["light"][:, None]
-        if predict_only:
-            return res
-        if self.training:
-            # no-grad training-mode call (e.g. bubble pdf refresh): the reference still emits the eikonal terms
-            from .autograd import train_extras_nograd
-            res.update(train_extras_nograd(self, core, input, o, d, z_eik))
-            if self.use_normal:
-                res["normal_values"] = out["normal"]
-        else:
+        if not predict_only:
             res["normal_map"] = out["normal"]
         return res
 

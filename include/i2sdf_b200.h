@@ -156,6 +156,61 @@ int i2sdf_render_forward(i2sdf_handle* h, const float* o, const float* d, const 
 
 size_t i2sdf_saved_bytes(const i2sdf_handle* h, int64_t R, int N);
 
+/* ---- training: split forward + backward ------------------------------------------------------------------
+ * The reference obtains these through torch.autograd (loss.backward(), model/trainer/recon.py:254-287), including
+ * the double-backward through autograd.grad(create_graph=True) at mlp.py:107-143.  W / b arguments are HOST arrays
+ * of DEVICE pointers to the effective weights [out,in] / biases of the addressed stack, in layer order; dW / db are
+ * accumulated INTO (caller zero-initialises).  All need workspace >= i2sdf_backward_workspace_bytes(h, M). */
+size_t i2sdf_backward_workspace_bytes(const i2sdf_handle* h, int64_t M);
+
+/* Main-pass MLP chain only (no compositing): per-sample s_sdf [R*N], s_grad [R*N,3] (or NULL), s_rgb [R*N,3],
+ * s_light [R*N] (or NULL), s_feat [R*N,256] (or NULL), save_act [n_sdf_layers-1, R*N, 256] (or NULL).
+ * Replaces model/network/__init__.py:103-116,162-168. */
+int i2sdf_points_forward(i2sdf_handle* h, const float* o, const float* d, const float* z, int64_t R, int N,
+                         float* s_sdf, float* s_grad, float* s_rgb, float* s_light, float* s_feat, float* save_act,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Compositing only (model/network/__init__.py:118-125,169,204-219,223-240) on per-sample inputs. */
+int i2sdf_composite_forward(i2sdf_handle* h, const float* z, const float* dnorm, const float* s_sdf, const float* s_rgb,
+                            const float* s_grad, const float* s_light, const float* beta_param, int64_t R, int N,
+                            float* rgb, float* depth, float* weight_sum, float* normal, float* light, float* s_w, void* stream);
+
+/* Backward of i2sdf_composite_forward.  Upstream g_* may be NULL (= 0).  Outputs: o_sdf [R*N], o_rgb [R*N,3],
+ * o_grad [R*N,3] (normal path; weights are detached there as in the reference, :207), o_light [R*N] (weights
+ * detached, :169), o_beta [1] (accumulated; d/d density.beta). */
+int i2sdf_composite_backward(i2sdf_handle* h, const float* z, const float* dnorm, const float* s_sdf, const float* s_rgb,
+                             const float* s_grad, const float* s_light, const float* beta_param, int64_t R, int N,
+                             const float* g_rgb, const float* g_depth, const float* g_wsum, const float* g_normal,
+                             const float* g_light, float* o_sdf, float* o_rgb, float* o_grad, float* o_light, float* o_beta,
+                             void* stream);
+
+/* Radiance stack backward (mlp.py:208-229).  dirs [M/ns, 3]; feat [M,256]; s_rgb [M,3] (forward output);
+ * g_rgb [M,3].  g_x [M,288] receives the adjoint of the stack's input [PE(dir) | feat | pad]: the feature adjoint
+ * is g_x + (3 + 6*multires_d) with leading dimension 288. */
+int i2sdf_color_backward(i2sdf_handle* h, const float* const* W, const float* const* b, const float* dirs, int ns,
+                         const float* feat, const float* s_rgb, const float* g_rgb, int64_t M, float* const* dW,
+                         float* const* db, float* g_x, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Light-mask head backward (model/network/__init__.py:162-168; features detached -> head parameters only). */
+int i2sdf_light_backward(i2sdf_handle* h, const float* const* W, const float* const* b, const float* feat,
+                         const float* s_light, const float* g_light, int64_t M, float* const* dW, float* const* db,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* SDF stack backward incl. second order.  Points: pts [M,3], or (pts NULL) rays o,d [M/ns,3] with z [.., zstride].
+ * act: pre-activations saved by the forward.  g_sdf [M] / g_feat [M, ld g_feat_ld] / g_grad [M,3] upstream (NULL = 0);
+ * g_grad is the upstream of grad_x sdf (eikonal / normal terms). */
+int i2sdf_sdf_backward(i2sdf_handle* h, const float* const* W, const float* pts, const float* o, const float* d,
+                       const float* z, int zstride, int ns, int64_t M, const float* act, const float* g_sdf,
+                       const float* g_feat, int g_feat_ld, const float* g_grad, float* const* dW, float* const* db,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Measurement hook (bench.py): when enabled, every kernel launch is bracketed by CUDA events recorded on the
+ * launching stream and counted, per class: 0 = sampler SDF evaluations (the dominant kernel), 1 = main-pass MLP
+ * chain, 2 = per-ray sampler kernels, 3 = rays / compositing / weight packing.  enable=1 also resets the counters.
+ * i2sdf_profile_read synchronises the device and returns summed event durations (ms) and launch counts. */
+int i2sdf_profile_enable(i2sdf_handle* h, int enable);
+int i2sdf_profile_read(i2sdf_handle* h, float ms[4], int64_t launches[4]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -196,3 +196,87 @@ def test_tensor_core_sdf_matches_oracle_and_fp32_kernel(cases, name):
         assert relerr(fp, ref) < 1e-5
         assert relerr(tc, ref) < TOL, (M, relerr(tc, ref))
         assert relerr(tc, fp) < TOL
+
+
+# ---------------------------------------------------------------------------------------------------
+# training: forward outputs, loss and parameter gradients (incl. second-order terms) vs the reference
+# ---------------------------------------------------------------------------------------------------
+from golden_util import TRAIN_CASES  # noqa: E402
+
+
+def _train_setup(name, use_ref_z):
+    from i2sdf_b200.network import I2SDFLoss
+    c = Case(name)
+    m = _model(c, training=True)
+    assert m.use_normal
+    ov = {"eik_uniform": c.tape["eik_uniform"], "nbr_uniform": c.tape["nbr_uniform"], "bubble_cam_idx": c.tape["bubble_cam_idx"]}
+    if use_ref_z:
+        ov.update(z_all=c.mid["z_all"], z_eik=c.mid["z_eik"])
+    else:
+        ov.update(jitter=c.tape["jitter"], u_final=c.tape["u_final"], extra_perm=c.tape["extra_perm"], eik_idx=c.tape["eik_idx"])
+    m._tape_override = ov
+    inp = {k: v.cuda() for k, v in c.inputs.items()}
+    gt = {k: v.cuda() for k, v in c.gt.items()}
+    loss_fn = I2SDFLoss(**c.loss_conf)
+    return c, m, inp, gt, loss_fn
+
+
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_training_step_on_reference_z(name):
+    """Identical z's: every output within 1e-4, loss equal, parameter gradients (first + second order) within 2e-3."""
+    c, m, inp, gt, loss_fn = _train_setup(name, use_ref_z=True)
+    out = m(inp)
+    assert set(out) == set(c.ref)
+    for k, v in c.ref.items():
+        assert out[k].shape == v.shape, k
+        tol = 2e-3 if k == "diff_norm" else 2e-4
+        assert relerr(out[k], v) < tol, (k, relerr(out[k], v))
+    res = loss_fn(out, gt, int(c.raw["meta_step"]))
+    assert abs(res["loss"].item() - c.ref_loss) < 2e-4 * abs(c.ref_loss)
+    res["loss"].backward()
+    sd = dict(m.named_parameters())
+    worst = 0.0
+    for k, g in c.refgrads().items():
+        mine = sd[k].grad
+        assert mine is not None, k
+        if "full" in g:
+            e = relerr(mine, g["full"])
+        else:
+            sub = mine.detach().cpu().flatten()[::97]
+            e = float((sub - g["sub"]).abs().max() / g["sub"].abs().max().clamp(min=1e-30))
+            assert abs(mine.norm().item() - g["norm"].item()) < 2e-3 * g["norm"].item() + 1e-9, k
+        worst = max(worst, e)
+        assert e < 2e-3, (k, e)
+    print(f"{name}: worst param-grad rel err {worst:.2e}")
+
+
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_training_step_full_pipeline(name):
+    """Sampler driven by the recorded RNG tape (jitter, u, randperm, randint): same round count, close outputs."""
+    c, m, inp, gt, loss_fn = _train_setup(name, use_ref_z=False)
+    out = m(inp)
+    for k in ("rgb_values", "depth_values", "weight_sum", "normal_values", "grad_theta"):
+        assert relerr(out[k], c.ref[k]) < 2e-2, (k, relerr(out[k], c.ref[k]))
+    loss = loss_fn(out, gt, int(c.raw["meta_step"]))["loss"]
+    assert abs(loss.item() - c.ref_loss) < 1e-2 * abs(c.ref_loss)
+    loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+
+
+def test_training_rng_draw_order_matches_reference():
+    """Without overrides the module draws its randomness with the same calls, in the same order, as the reference."""
+    c = Case("train_synthetic")
+    m = _model(c, training=True)
+    R = c.inputs["uv"].shape[0]
+    torch.manual_seed(123)
+    tape = m._draw_sampler_tape(R, torch.device("cuda"))
+    torch.manual_seed(123)
+    j = torch.rand(R, 128, device="cuda")
+    u = torch.rand(R, 64, device="cuda")
+    assert torch.equal(tape["jitter"], j) and torch.equal(tape["u_final"], u)
+    p1 = tape["extra_perm"](384)
+    e1 = tape["eik_idx_fn"]()
+    torch.manual_seed(123)
+    torch.rand(R, 128, device="cuda"); torch.rand(R, 64, device="cuda")
+    assert torch.equal(p1, torch.randperm(384)[:32])
+    assert torch.equal(e1, torch.randint(98, (R,), device="cuda"))
