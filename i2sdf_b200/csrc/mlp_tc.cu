@@ -6,12 +6,13 @@
 //   * weights (pre-split hi/lo, pre-tiled per 16-wide k step) stream from L2 through a ring of cp.async.bulk stages;
 //   * each layer is 3 tcgen05.mma products per k step -- A_hi*W_hi + A_lo*W_hi + A_hi*W_lo -- accumulated in fp32 in
 //     TMEM (128 lanes x 256 columns; two accumulators ping-pong across layers);
-//   * four epilogue warps read the accumulator with tcgen05.ld, add bias, apply softplus_100 (and the skip concat),
-//     re-split to bf16 hi/lo and write the next layer's A operand chunk by chunk; the MMA warp trails the epilogue
-//     one 32-column chunk behind, so layer l+1's tensor work overlaps layer l's epilogue on a single tile;
+//   * sixteen epilogue warps (4 per scheduler; warp (q, sub) owns TMEM lane quarter q and 32-column chunks sub, sub+4)
+//     read the accumulator with tcgen05.ld, add bias, apply softplus_100 (and the skip concat), re-split to bf16
+//     hi/lo and write the next layer's A operand chunk by chunk; the MMA warp trails the epilogue by chunks, so layer
+//     l+1's tensor work overlaps layer l's epilogue on a single tile;
 //   * the sdf head (one 256-wide dot) is folded into the last epilogue in fp32; only sdf[M] goes back to HBM.
 //
-// Warp roles: warp 0 = weight producer (one lane), warp 1 = MMA issuer (one lane), warps 2..5 = epilogue.
+// Warp roles: warp 0 = weight producer (one lane), warp 1 = MMA issuer (one lane), warps 2..17 = epilogue.
 // Replaces (reference): ImplicitNetwork.get_sdf_vals mlp.py:145-151 (-> forward :84-105, Embedder embedder.py:28-38),
 // as called by the sampler at ray_sampler.py:84-89.
 #include "common.cuh"
@@ -24,13 +25,15 @@ using namespace tc;
 
 constexpr int TM = 128;                 // points per tile = MMA M
 constexpr int NCOL = 256;               // MMA N = layer width
-constexpr int NSTAGE = 5;
+constexpr int NSTAGE = 4;
 constexpr int STAGE_BYTES = 16384;      // one k step: W_hi [2 chunks][256][8] bf16 (8 KB) + W_lo (8 KB)
 constexpr int A_PART_BYTES = TM * 256 * 2;      // 64 KB per bf16 part
-constexpr int NTHREADS = 192;
+constexpr int N_EPI_WARPS = 16;         // 4 per TMEM lane quarter; warp (q, sub) owns 32-column chunks sub and sub+4
+constexpr int NTHREADS = (2 + N_EPI_WARPS) * 32;
 constexpr int K0_STEPS = 3;             // layer 0: 39 -> 48 columns
+constexpr int STASH_LD = 40;            // embedding / sqrt2 per row, for the skip concat
 constexpr uint32_t LBO_A = TM * 16, LBO_B = NCOL * 16, SBO = 128;
-constexpr size_t kSmemBytes = 1024 + 2 * A_PART_BYTES + NSTAGE * STAGE_BYTES + 256;
+constexpr size_t kSmemBytes = 1024 + 2 * A_PART_BYTES + NSTAGE * STAGE_BYTES + TM * STASH_LD * 4 + 4 * TM * 4 + 256;
 
 struct TcNet {
     const uint8_t* wpack;       // [layer][kstep][16 KB]
@@ -39,11 +42,38 @@ struct TcNet {
     int NL;                     // MMA layers = L-1
 };
 
+// softplus_100 in the overflow-free form max(a,0) + log1p(exp(-|100 a|))/100; equals nn.Softplus(beta=100,
+// threshold=20) to < 3e-11 absolute (the thresholded branch differs from the exact value by log1p(e^-20)/100).
 __device__ __forceinline__ float softplus100_fast(float a) {
-    float t = a * 100.0f;
-    float e = __expf(t);
-    float sp = __logf(1.0f + e) * 0.01f;
-    return t > 20.0f ? a : sp;
+    float e = exp2f(-fabsf(a) * 144.26950408889634f);            // exp(-|100 a|)   (MUFU.EX2)
+    return fmaf(__log2f(1.0f + e), 0.0069314718055994531f, fmaxf(a, 0.0f));   // + ln2/100 * log2(1+e)   (MUFU.LG2)
+}
+
+// sin & cos for |a| < ~1e4: 3-constant Cody-Waite reduction to [-pi/4, pi/4] + minimax polynomials (~1 ulp)
+__device__ __forceinline__ void sincos_cw(float a, float& s, float& c) {
+    float q = rintf(a * 0.63661977236758134f);
+    int n = (int)q;
+    float r = fmaf(q, -1.5707962512969971f, a);
+    r = fmaf(q, -7.5497894158615964e-08f, r);
+    r = fmaf(q, -5.3903029534742384e-15f, r);
+    float r2 = r * r;
+    float sp = fmaf(fmaf(fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f), r2, -1.6666654611e-1f), r2 * r, r);
+    float cp = fmaf(fmaf(fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f), r2, 4.166664568298827e-2f), r2 * r2,
+                    fmaf(-0.5f, r2, 1.0f));
+    float ss = (n & 1) ? cp : sp;
+    float cc = (n & 1) ? sp : cp;
+    s = (n & 2) ? -ss : ss;
+    c = ((n + 1) & 2) ? -cc : cc;
+}
+
+// value of embedding column i (0..38) of point x:  [x, sin(2^k x), cos(2^k x)]   (embedder.py:28-38)
+__device__ __forceinline__ float embed_col(const float (&x)[3], int i, int mx) {
+    if (i < 3) return x[i];
+    const int qq = i - 3, k = qq / 6, cc = qq % 3;
+    if (k >= mx) return 0.f;
+    float s, c;
+    sincos_cw(__fmul_rn(x[cc], (float)(1 << k)), s, c);
+    return ((qq % 6) < 3) ? s : c;
 }
 
 __device__ __forceinline__ bool round_active(const MlpParams& P) {
@@ -54,17 +84,33 @@ __device__ __forceinline__ bool round_active(const MlpParams& P) {
     return true;
 }
 
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32) : "memory"); }
+
+// write 32 consecutive columns (k chunks kc0..kc0+3) of one row of the next layer's A operand, split hi / lo
+__device__ __forceinline__ void store_a_chunk(uint8_t* A_hi, uint8_t* A_lo, int row, int kc0, const float (&hv)[32]) {
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4) {
+        uint32_t h[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_bf16x2(hv[s4 * 8 + 2 * i], hv[s4 * 8 + 2 * i + 1], h[i], lo[i]);
+        const uint32_t off = seg_off<TM>(row, kc0 + s4);
+        *reinterpret_cast<uint4*>(A_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(A_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1) sdf_tc_kernel(const MlpParams P, const TcNet T) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // manual 1024-byte alignment of the operand area
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* A_hi = smem;
     uint8_t* A_lo = smem + A_PART_BYTES;
     uint8_t* ring = smem + 2 * A_PART_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + NSTAGE * STAGE_BYTES);
+    float* stash = reinterpret_cast<float*>(ring + NSTAGE * STAGE_BYTES);    // [TM][STASH_LD] embedding / sqrt2
+    float* hpart = stash + TM * STASH_LD;                                      // [4][TM] partial sdf heads
+    uint64_t* bars = reinterpret_cast<uint64_t*>(hpart + 4 * TM);
     uint64_t* full = bars;                 // [NSTAGE]
     uint64_t* empty = bars + NSTAGE;       // [NSTAGE]
-    uint64_t* a_ready = bars + 2 * NSTAGE; // [8]
+    uint64_t* a_ready = bars + 2 * NSTAGE; // [8]  (4 arrivals: one per contributing warp)
     uint64_t* d_full = a_ready + 8;        // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 2);
 
@@ -77,7 +123,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdf_tc_kernel(const MlpParams P, 
 
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 8; ++i) mbar_init(&a_ready[i], 128);
+        for (int i = 0; i < 8; ++i) mbar_init(&a_ready[i], 4);
         mbar_init(&d_full[0], 1);
         mbar_init(&d_full[1], 1);
         fence_mbar_init();
@@ -139,57 +185,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdf_tc_kernel(const MlpParams P, 
             }
         }
     } else {
-        // ================= epilogue warps (2..5) =================
+        // ================= epilogue warps =================
         const int q = warp & 3;                              // TMEM lane quarter this warp may access
+        const int sub = (warp - 2) >> 2;                     // 0..3: owns 32-column chunks sub and sub + 4
         const int row = q * 32 + lane;                       // point within the tile
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const int nsplit = 256 - net.ex;
-        const float SQRT2 = 1.41421356237309504880f;
         uint32_t dphase = 0;                                 // bit b: parity to wait on d_full[b]
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const long long m = tile * TM + row;
-            // ---- prologue: point + positional encoding -> A_0 (48 columns, hi/lo)
-            float x[3] = {0.f, 0.f, 0.f};
-            if (m < P.M) {
-                if (P.pts) { x[0] = P.pts[m * 3]; x[1] = P.pts[m * 3 + 1]; x[2] = P.pts[m * 3 + 2]; }
-                else {
-                    long long r = m / P.ns;
-                    int j = (int)(m - r * P.ns);
-                    float t = P.zarr[r * P.zstride + j];
+            // ---- prologue: positional encoding -> A_0 (48 columns) + stash of embed/sqrt2.  sub 0: columns 0..31,
+            //      sub 1: columns 32..47; subs 2,3 idle.
+            if (sub < 2) {
+                float x[3] = {0.f, 0.f, 0.f};
+                if (m < P.M) {
+                    if (P.pts) { x[0] = P.pts[m * 3]; x[1] = P.pts[m * 3 + 1]; x[2] = P.pts[m * 3 + 2]; }
+                    else {
+                        long long r = m / P.ns;
+                        int j = (int)(m - r * P.ns);
+                        float t = P.zarr[r * P.zstride + j];
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(P.ray_o[r * 3 + c], __fmul_rn(t, P.ray_d[r * 3 + c]));
-                }
-            }
-            {
-                float e[48];
-                e[0] = x[0]; e[1] = x[1]; e[2] = x[2];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        float s, co;
-                        sincosf(__fmul_rn(x[c], (float)(1 << k)), &s, &co);
-                        const bool on = k < net.mx;
-                        e[3 + 6 * k + c] = on ? s : 0.f;
-                        e[6 + 6 * k + c] = on ? co : 0.f;
+                        for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(P.ray_o[r * 3 + c], __fmul_rn(t, P.ray_d[r * 3 + c]));
                     }
                 }
+                float hv[32];
 #pragma unroll
-                for (int i = 39; i < 48; ++i) e[i] = 0.f;
-#pragma unroll
-                for (int kc = 0; kc < 6; ++kc) {
-                    uint32_t h[4], lo[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) split_bf16x2(e[kc * 8 + 2 * i], e[kc * 8 + 2 * i + 1], h[i], lo[i]);
-                    const uint32_t off = seg_off<TM>(row, kc);
-                    *reinterpret_cast<uint4*>(A_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-                    *reinterpret_cast<uint4*>(A_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                for (int j = 0; j < 32; ++j) {
+                    const int i = sub * 32 + j;
+                    hv[j] = (i < net.ex) ? embed_col(x, i, net.mx) : 0.f;
+                    if (i < STASH_LD) stash[row * STASH_LD + i] = hv[j] * 0.70710678118654752f;
                 }
+                if (sub == 0) store_a_chunk(A_hi, A_lo, row, 0, hv);
+                else {
+#pragma unroll
+                    for (int s4 = 0; s4 < 2; ++s4) {
+                        uint32_t h[4], lo[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) split_bf16x2(hv[s4 * 8 + 2 * i], hv[s4 * 8 + 2 * i + 1], h[i], lo[i]);
+                        const uint32_t off = seg_off<TM>(row, 4 + s4);
+                        *reinterpret_cast<uint4*>(A_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<uint4*>(A_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_ready[sub]);
             }
-            fence_proxy_async();
-            tc_fence_before();
-            mbar_arrive(&a_ready[0]);
-            mbar_arrive(&a_ready[1]);
+            epi_bar_sync();                                  // stash visible to the warps that fill the skip columns
 
             float head = 0.f;
             for (int l = 0; l < NL; ++l) {
@@ -201,7 +244,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdf_tc_kernel(const MlpParams P, 
                 const bool feeds_skip = (l + 1 == net.skip);
                 const float* __restrict__ bias = net.sdf_b[l];
 #pragma unroll 1
-                for (int c = 0; c < 8; ++c) {
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int c = sub + 4 * cc;
                     uint32_t v[32];
                     tmem_ld32(tmem_base + lane_base + (uint32_t)b * 256u + (uint32_t)c * 32u, v);
                     tmem_ld_wait();
@@ -229,34 +273,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) sdf_tc_kernel(const MlpParams P, 
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int f = c * 32 + j;
-                            float val = hv[j];
-                            if (f >= nsplit) {
-                                const int r = f - nsplit;
-                                if (r < 3) val = x[r];
-                                else {
-                                    const int qq = r - 3, k = qq / 6, s = (qq % 6) / 3, cc = qq % 3;
-                                    const float arg = __fmul_rn(x[cc], (float)(1 << k));
-                                    val = s ? cosf(arg) : sinf(arg);
-                                }
-                            }
-                            hv[j] = __fdiv_rn(val, SQRT2);
+                            hv[j] = (f >= nsplit) ? stash[row * STASH_LD + (f - nsplit)] : hv[j] * 0.70710678118654752f;
                         }
                     }
-#pragma unroll
-                    for (int s4 = 0; s4 < 4; ++s4) {
-                        uint32_t h[4], lo[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) split_bf16x2(hv[s4 * 8 + 2 * i], hv[s4 * 8 + 2 * i + 1], h[i], lo[i]);
-                        const uint32_t off = seg_off<TM>(row, c * 4 + s4);
-                        *reinterpret_cast<uint4*>(A_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-                        *reinterpret_cast<uint4*>(A_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    }
+                    store_a_chunk(A_hi, A_lo, row, c * 4, hv);
                     fence_proxy_async();
                     tc_fence_before();
-                    mbar_arrive(&a_ready[c]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&a_ready[c]);
                 }
             }
-            if (m < P.M) P.out_sdf[m] = head + __ldg(net.sdf_head + 256);
+            // ---- sdf head: combine the 4 column-partials of every row
+            hpart[sub * TM + row] = head;
+            epi_bar_sync();
+            if (sub == 0 && m < P.M)
+                P.out_sdf[m] = ((hpart[row] + hpart[TM + row]) + (hpart[2 * TM + row] + hpart[3 * TM + row])) + __ldg(net.sdf_head + 256);
         }
     }
     tc_fence_before();
