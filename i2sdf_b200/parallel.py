@@ -1,0 +1,63 @@
+"""Multi-GPU plumbing for the per-ray path: one process per GPU, rays sharded, weights replicated.
+
+The reference has no distributed code (`strategy=None` at main_recon.py:112); rays are independent
+units, so the B200 design is plain data parallelism:
+  * inference: shard rays / pixel chunks, no collective;
+  * training: every rank renders its shard, then ONE all-reduce of the flat gradient (800 955 fp32 = 3.2 MB for
+    config/synthetic.yml) over NCCL/NVLink per step.
+These helpers only touch torch tensors and torch.distributed, so they run under gloo on CPU for the tests.
+(A torch DistributedDataParallel wrapper around I2SDFNetwork also works: the custom autograd Functions return
+ordinary parameter gradients, so DDP's bucket hooks fire as usual.)
+
+Parity caveats of sharding, all inherited from the reference's batch-global semantics: the
+sampler's convergence test is global over the rays of ONE forward call (ray_sampler.py:151), so a shard may stop
+up-sampling one round earlier than the full batch would; masked-mean losses average per shard.
+"""
+from typing import Dict, Iterable, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, rank: int, world: int):
+    """Contiguous, balanced partition of n items: the first n % world ranks get one extra."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_rays(batch: Dict[str, torch.Tensor], rank: int, world: int) -> Dict[str, torch.Tensor]:
+    """Split a reference-style input dict across ranks along the ray axis.
+
+    Training layout (dataset/train_dataset.py:169-192): uv [R,1,2], pose [R,4,4], intrinsics [R,4,4] -> split dim 0.
+    Eval layout (dataset/eval_dataset.py:150-168): uv [1,P,2], pose [1,4,4], intrinsics [1,4,4] -> split uv dim 1."""
+    uv = batch["uv"]
+    out = dict(batch)
+    if uv.shape[0] == 1 and uv.shape[1] > 1:
+        lo, hi = shard_bounds(uv.shape[1], rank, world)
+        out["uv"] = uv[:, lo:hi].contiguous()
+        return out
+    lo, hi = shard_bounds(uv.shape[0], rank, world)
+    for k, v in batch.items():
+        if torch.is_tensor(v) and v.dim() >= 1 and v.shape[0] == uv.shape[0] and k != "pointcloud":
+            out[k] = v[lo:hi].contiguous()
+    return out
+
+
+def allreduce_gradients(params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None,
+                        average: bool = True) -> int:
+    """One all-reduce of all gradients as a single flat bucket; returns the number of elements reduced."""
+    ps = [p for p in params if p.grad is not None]
+    if not ps:
+        return 0
+    flat = torch.cat([p.grad.reshape(-1) for p in ps])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            flat /= dist.get_world_size(group)
+    off = 0
+    for p in ps:
+        n = p.grad.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        off += n
+    return flat.numel()
