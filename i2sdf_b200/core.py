@@ -74,7 +74,9 @@ class RenderCore:
             check(self.lib.i2sdf_create(C.byref(d), device.index or 0, C.byref(h)), "i2sdf_create")
         self.h = h
         self.n_layers = self.lib.i2sdf_num_layers(h)
-        self.uses_tensor_cores = bool(self.lib.i2sdf_uses_tensor_cores(h))
+        tcbits = self.lib.i2sdf_uses_tensor_cores(h)
+        self.uses_tensor_cores = bool(tcbits & 1)
+        self.uses_tensor_cores_main = bool(tcbits & 2)
         self._ws = None
         self._ws_rays = -1
         self._packed_refs = None

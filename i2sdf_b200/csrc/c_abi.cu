@@ -46,6 +46,11 @@ int tc_create(i2sdf_handle* h);
 void tc_destroy(i2sdf_handle* h);
 int tc_pack(i2sdf_handle* h, const float* const* W, const float* const* b, cudaStream_t st);
 int tc_launch_sdf(const i2sdf_handle* h, const MlpParams& p, cudaStream_t st);
+// declared in mlp_tc_main.cu
+int tcmain_create(i2sdf_handle* h, void** out_state);
+void tcmain_destroy(void* state);
+int tcmain_pack(i2sdf_handle* h, void* state, const float* const* W, cudaStream_t st);
+int tcmain_launch(const i2sdf_handle* h, void* state, const MlpParams& p, cudaStream_t st);
 
 // ---- packing ------------------------------------------------------------------------------------
 enum { PACK_T = 0, PACK_R = 1, PACK_V = 2 };
@@ -202,9 +207,15 @@ int i2sdf_create(const i2sdf_desc* d, int device, i2sdf_handle** out) {
     h->use_tc = !(env && env[0] == '1');
     h->tc = nullptr;
     h->prof = new Prof();
+    h->tcmain = nullptr;
     if (h->use_tc) {
         int rc = tc_create(h);
         if (rc != I2SDF_OK) { cudaFree(h->pool); free(h); return rc; }
+        const char* env2 = getenv("I2SDF_SIMT_MAIN");
+        if (!(env2 && env2[0] == '1')) {
+            rc = tcmain_create(h, &h->tcmain);
+            if (rc != I2SDF_OK) { tc_destroy(h); cudaFree(h->pool); free(h); return rc; }
+        }
     }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { set_error("create: %s", cudaGetErrorString(e)); cudaFree(h->pool); free(h); return I2SDF_E_CUDA; }
@@ -215,6 +226,7 @@ int i2sdf_create(const i2sdf_desc* d, int device, i2sdf_handle** out) {
 int i2sdf_destroy(i2sdf_handle* h) {
     if (!h) return I2SDF_OK;
     if (h->tc) tc_destroy(h);
+    if (h->tcmain) tcmain_destroy(h->tcmain);
     if (h->prof) { Prof* p = (Prof*)h->prof; for (auto& v : p->ev) for (auto e : v) cudaEventDestroy(e); delete p; }
     cudaFree(h->pool);
     free(h);
@@ -222,7 +234,7 @@ int i2sdf_destroy(i2sdf_handle* h) {
 }
 
 int i2sdf_num_layers(const i2sdf_handle* h) { return h ? h->n_layers : 0; }
-int i2sdf_uses_tensor_cores(const i2sdf_handle* h) { return (h && h->use_tc) ? 1 : 0; }
+int i2sdf_uses_tensor_cores(const i2sdf_handle* h) { return h ? ((h->use_tc ? 1 : 0) | (h->tcmain ? 2 : 0)) : 0; }
 
 int i2sdf_pack_weights(i2sdf_handle* h, const float* const* W, const float* const* b, void* stream) {
     if (!h || !W || !b) { set_error("null argument"); return I2SDF_E_INVALID; }
@@ -280,6 +292,7 @@ int i2sdf_pack_weights(i2sdf_handle* h, const float* const* W, const float* cons
         ++li;
     }
     if (h->use_tc && (rc = tc_pack(h, W, b, st))) return rc;
+    if (h->tcmain && (rc = tcmain_pack(h, h->tcmain, W, st))) return rc;
     return I2SDF_OK;
 }
 
@@ -304,6 +317,10 @@ static int run_mlp(const i2sdf_handle* h, const MlpParams& p, cudaStream_t st) {
     const bool sdf_only = !p.out_feat && !p.out_grad && !p.want_color && !p.want_light && !p.save_act;
     ProfScope ps(h, sdf_only ? 0 : 1, st);
     if (h->use_tc && sdf_only) return tc_launch_sdf(h, p, st);
+    // eval main pass (sdf + grad_x + rgb per sample, nothing saved) -> tensor-core kernel
+    if (h->tcmain && p.out_sdf && p.out_grad && p.out_rgb && p.want_color && !p.want_light && !p.out_feat && !p.save_act && p.scratch &&
+        (p.ray_d || p.pts))
+        return tcmain_launch(h, h->tcmain, p, st);
     return launch_mlp_simt(h, p, st);
 }
 

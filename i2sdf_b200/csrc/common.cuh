@@ -63,6 +63,7 @@ struct i2sdf_handle {
     bool use_tc;             // tcgen05 path available (set by env I2SDF_SIMT=1 -> false)
     void* tc;                // opaque tcgen05 packed state (see mlp_tc.cu)
     void* prof;              // measurement hook state (c_abi.cu)
+    void* tcmain;            // tcgen05 main-pass state (mlp_tc_main.cu), null if unavailable for this network
 };
 
 namespace i2sdf {

@@ -1,0 +1,488 @@
+// Main pass on the tensor cores (tcgen05 / TMEM), sm_100a: for a resident tile of 128 ray samples
+//   SDF stack forward -> sdf head -> feature layer -> radiance stack -> rgb head -> reverse sweep for grad_x sdf
+// as ONE persistent kernel.  Same scheme as mlp_tc.cu (bf16 hi/lo split activations as the SMEM A operand, weights
+// streamed by cp.async.bulk, fp32 accumulators ping-ponged in TMEM, 16 epilogue warps trailing chunk by chunk), driven
+// by a small table of "ops" (one op = one dense layer = ksteps x 3 tcgen05.mma):
+//   F_0..F_{NL-1}   SDF hidden layers           epilogue: +b, softplus_100 (+skip concat), sigma' -> scratch
+//   G               feature rows of last layer  epilogue: +b ; appends PE(view dir) as k chunk 8
+//   C_0..C_{Lc-2}   radiance hidden layers      epilogue: +b, ReLU ; last one: rgb head (fp32 dots) and the
+//                                               reverse prologue  ra = w_sdf * sigma'_{NL-1}
+//   R_{NL-1}..R_1   reverse sweep (W^T)         epilogue: (skip split) * sigma'_{l-1}
+//   R_0             adjoint of the embedding    epilogue: J(x)^T r  -> grad_x sdf
+// sigma' (softplus derivative, fp32) round-trips through a per-CTA scratch in global memory (L2-resident: 1 MB per CTA).
+// Only sdf / rgb / grad per sample go to HBM; compositing is the per-ray kernel in sampler.cu.
+//
+// Replaces (reference): model/network/__init__.py:103-116 = ImplicitNetwork.get_outputs mlp.py:123-143 (forward :84-105
+// + autograd.grad :134-140) and RenderingNetwork.forward mlp.py:208-229.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace i2sdf {
+namespace tcmain {
+
+using namespace tc;
+
+constexpr int TM = 128;
+constexpr int NSTAGE = 4;
+constexpr int STAGE_MAX = 16384;
+constexpr int A_CHUNKS = 36;                         // 288 columns
+constexpr int A_PART_BYTES = A_CHUNKS * TM * 16;     // 73728
+constexpr int N_EPI_WARPS = 16;
+constexpr int NTHREADS = (2 + N_EPI_WARPS) * 32;
+constexpr int MAX_OPS = 40;
+constexpr int N_READY = 9;
+constexpr uint32_t LBO_A = TM * 16, SBO = 128;
+constexpr int PART_FLOATS = 4 * 7 * TM;              // [sub][sdf, rgb x3, grad x3][row]
+constexpr size_t kSmemBytes = 1024 + 2 * (size_t)A_PART_BYTES + NSTAGE * STAGE_MAX + PART_FLOATS * 4 + 256;
+
+enum { EK_SDF_HIDDEN = 0, EK_SDF_LAST, EK_FEAT, EK_COL_HIDDEN, EK_COL_LAST, EK_REV, EK_GRAD };
+
+struct Op {
+    int w_off;          // byte offset into wpack
+    short ksteps;
+    short n;            // MMA N (256 or 48)
+    short kind;         // epilogue kind applied to this op's accumulator
+    short layer;        // layer index within its stack
+};
+struct MainNet {
+    const uint8_t* wpack;
+    int nops;
+    Op ops[MAX_OPS];
+};
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32) : "memory"); }
+
+__device__ __forceinline__ void store_a_chunk(uint8_t* A_hi, uint8_t* A_lo, int row, int kc0, const float (&hv)[32]) {
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4) {
+        uint32_t h[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_bf16x2(hv[s4 * 8 + 2 * i], hv[s4 * 8 + 2 * i + 1], h[i], lo[i]);
+        const uint32_t off = seg_off<TM>(row, kc0 + s4);
+        *reinterpret_cast<uint4*>(A_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(A_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// d embed_i / d x_c(i) and the coordinate c(i) it belongs to
+__device__ __forceinline__ float embed_jac(const float (&x)[3], int i, int mx, int& coord) {
+    if (i < 3) { coord = i; return 1.f; }
+    const int qq = i - 3, k = qq / 6, cc = qq % 3;
+    coord = cc;
+    if (k >= mx) return 0.f;
+    const float f = (float)(1 << k);
+    float s, c;
+    sincos_cw(__fmul_rn(x[cc], f), s, c);
+    return ((qq % 6) < 3) ? f * c : -f * s;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) main_tc_kernel(const MlpParams P, const MainNet T) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* A_hi = smem;
+    uint8_t* A_lo = smem + A_PART_BYTES;
+    uint8_t* ring = smem + 2 * A_PART_BYTES;
+    float* part = reinterpret_cast<float*>(ring + NSTAGE * STAGE_MAX);      // [4][7][TM]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(part + PART_FLOATS);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + NSTAGE;
+    uint64_t* a_ready = bars + 2 * NSTAGE;       // [N_READY]
+    uint64_t* d_full = a_ready + N_READY;        // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const NetDev& net = P.net;
+    const int NL = net.L - 1;
+    const long long ntiles = (P.M + TM - 1) / TM;
+
+    if (tid == 0) {
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < N_READY; ++i) mbar_init(&a_ready[i], 4);
+        mbar_init(&d_full[0], 1);
+        mbar_init(&d_full[1], 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= weight producer =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int op = 0; op < T.nops; ++op) {
+                    const uint32_t sb = (uint32_t)T.ops[op].n * 64u;
+                    const uint8_t* src = T.wpack + T.ops[op].w_off;
+                    for (int ks = 0; ks < T.ops[op].ksteps; ++ks) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&full[stage], sb);
+                        bulk_g2s(ring + stage * STAGE_MAX, src + (size_t)ks * sb, sb, &full[stage]);
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t a_hi_s = smem_u32(A_hi), a_lo_s = smem_u32(A_lo), ring_s = smem_u32(ring);
+            uint32_t stage = 0, phase = 0, aphase = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int op = 0; op < T.nops; ++op) {
+                    const int n = T.ops[op].n;
+                    const uint32_t idesc = instr_desc_bf16(TM, n);
+                    const uint32_t lbo_b = (uint32_t)n * 16u, lo_off = (uint32_t)n * 32u;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(op & 1) * 256u;
+                    const int nks = T.ops[op].ksteps;
+                    for (int ks = 0; ks < nks; ++ks) {
+                        if ((ks & 1) == 0) {
+                            const int c = ks >> 1;
+                            mbar_wait(&a_ready[c], (aphase >> c) & 1u);
+                            aphase ^= (1u << c);
+                        }
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_off = (uint32_t)ks * 2u * LBO_A;
+                        const uint32_t b_s = ring_s + stage * STAGE_MAX;
+                        const uint64_t da_hi = smem_desc(a_hi_s + a_off, LBO_A, SBO);
+                        const uint64_t da_lo = smem_desc(a_lo_s + a_off, LBO_A, SBO);
+                        const uint64_t db_hi = smem_desc(b_s, lbo_b, SBO);
+                        const uint64_t db_lo = smem_desc(b_s + lo_off, lbo_b, SBO);
+                        mma_bf16_ss(d_tmem, da_hi, db_hi, idesc, ks > 0 ? 1u : 0u);
+                        mma_bf16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
+                        mma_bf16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
+                        mma_commit(&empty[stage]);
+                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                    }
+                    mma_commit(&d_full[op & 1]);
+                }
+            }
+        }
+    } else {
+        // ================= epilogue warps =================
+        const int q = warp & 3;
+        const int sub = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const int nsplit = 256 - net.ex;
+        const float RS2 = 0.70710678118654752f;
+        float* sig_base = P.scratch + (size_t)blockIdx.x * (size_t)NL * TM * 256 + (size_t)row * 256;
+        uint32_t dphase = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const long long m = tile * TM + row;
+            float x[3] = {0.f, 0.f, 0.f}, dv[3] = {0.f, 0.f, 1.f};
+            if (m < P.M) {
+                const long long r = m / P.ns;
+                if (P.ray_d) { dv[0] = P.ray_d[r * 3]; dv[1] = P.ray_d[r * 3 + 1]; dv[2] = P.ray_d[r * 3 + 2]; }
+                if (P.pts) { x[0] = P.pts[m * 3]; x[1] = P.pts[m * 3 + 1]; x[2] = P.pts[m * 3 + 2]; }
+                else {
+                    const int j = (int)(m - r * P.ns);
+                    const float t = P.zarr[r * P.zstride + j];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(P.ray_o[r * 3 + c], __fmul_rn(t, dv[c]));
+                }
+            }
+            // ---- prologue: A_0 = embedding (48 columns): sub 0 -> columns 0..31, sub 1 -> 32..47
+            if (sub < 2) {
+                float hv[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int i = sub * 32 + j;
+                    hv[j] = (i < net.ex) ? embed_col(x, i, net.mx) : 0.f;
+                }
+                if (sub == 0) store_a_chunk(A_hi, A_lo, row, 0, hv);
+                else {
+#pragma unroll
+                    for (int s4 = 0; s4 < 2; ++s4) {
+                        uint32_t h[4], lo[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) split_bf16x2(hv[s4 * 8 + 2 * i], hv[s4 * 8 + 2 * i + 1], h[i], lo[i]);
+                        const uint32_t off = seg_off<TM>(row, 4 + s4);
+                        *reinterpret_cast<uint4*>(A_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<uint4*>(A_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_ready[sub]);
+            }
+
+            float head = 0.f, rgbp[3] = {0.f, 0.f, 0.f}, gacc[3] = {0.f, 0.f, 0.f};
+            for (int op = 0; op < T.nops; ++op) {
+                const int b = op & 1;
+                const int kind = T.ops[op].kind, l = T.ops[op].layer;
+                mbar_wait(&d_full[b], (dphase >> b) & 1u);
+                dphase ^= (1u << b);
+                tc_fence_after();
+#pragma unroll 1
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int c = sub + 4 * cc;
+                    if (kind == EK_GRAD && c >= 2) break;
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + lane_base + (uint32_t)b * 256u + (uint32_t)c * 32u, v);
+                    tmem_ld_wait();
+                    float hv[32];
+                    if (kind == EK_SDF_HIDDEN || kind == EK_SDF_LAST) {
+                        const float* __restrict__ bias = net.sdf_b[l] + c * 32;
+                        float* sg = sig_base + (size_t)l * TM * 256 + c * 32;
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + j4);
+                            const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+                            float so[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float a = __uint_as_float(v[j4 * 4 + u]) + bv[u];
+                                const float e = exp2f(-fabsf(a) * 144.26950408889634f);
+                                const float rr = __fdividef(1.0f, 1.0f + e);
+                                hv[j4 * 4 + u] = fmaf(__log2f(1.0f + e), 0.0069314718055994531f, fmaxf(a, 0.0f));
+                                so[u] = (a >= 0.f) ? rr : e * rr;                       // softplus'(a) = sigmoid(100 a)
+                            }
+                            *reinterpret_cast<float4*>(sg + j4 * 4) = make_float4(so[0], so[1], so[2], so[3]);
+                        }
+                        if (kind == EK_SDF_LAST) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) {
+                                const float4 w = __ldg(reinterpret_cast<const float4*>(net.sdf_head + c * 32) + j4);
+                                head = fmaf(hv[j4 * 4 + 0], w.x, head);
+                                head = fmaf(hv[j4 * 4 + 1], w.y, head);
+                                head = fmaf(hv[j4 * 4 + 2], w.z, head);
+                                head = fmaf(hv[j4 * 4 + 3], w.w, head);
+                            }
+                        } else if (l + 1 == net.skip) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const int f = c * 32 + j;
+                                hv[j] = ((f >= nsplit) ? embed_col(x, f - nsplit, net.mx) : hv[j]) * RS2;
+                            }
+                        }
+                    } else if (kind == EK_FEAT || kind == EK_COL_HIDDEN || kind == EK_COL_LAST) {
+                        const float* __restrict__ bias = (kind == EK_FEAT ? net.sdf_b[net.L - 1] : net.col_b[l]) + c * 32;
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + j4);
+                            hv[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + bb.x;
+                            hv[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + bb.y;
+                            hv[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + bb.z;
+                            hv[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + bb.w;
+                        }
+                        if (kind != EK_FEAT) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) hv[j] = fmaxf(hv[j], 0.f);
+                        }
+                        if (kind == EK_COL_LAST) {
+                            const float* __restrict__ wh = net.col_head + c * 32;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                rgbp[0] = fmaf(hv[j], __ldg(wh + j), rgbp[0]);
+                                rgbp[1] = fmaf(hv[j], __ldg(wh + 256 + j), rgbp[1]);
+                                rgbp[2] = fmaf(hv[j], __ldg(wh + 512 + j), rgbp[2]);
+                            }
+                            // reverse prologue: adjoint of a_{NL-1} = w_sdf * softplus'(a_{NL-1})
+                            const float* sg = sig_base + (size_t)(NL - 1) * TM * 256 + c * 32;
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) {
+                                const float4 w = __ldg(reinterpret_cast<const float4*>(net.sdf_head + c * 32) + j4);
+                                const float4 s = *reinterpret_cast<const float4*>(sg + j4 * 4);
+                                hv[j4 * 4 + 0] = w.x * s.x; hv[j4 * 4 + 1] = w.y * s.y; hv[j4 * 4 + 2] = w.z * s.z; hv[j4 * 4 + 3] = w.w * s.w;
+                            }
+                        }
+                    } else if (kind == EK_REV) {
+                        // accumulator = adjoint of the input of SDF layer l ; next A = (that) * softplus'(a_{l-1})
+                        const float* sg = sig_base + (size_t)(l - 1) * TM * 256 + c * 32;
+                        const bool is_skip = (l == net.skip);
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 s = *reinterpret_cast<const float4*>(sg + j4 * 4);
+                            const float sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                float rv = __uint_as_float(v[j4 * 4 + u]);
+                                if (is_skip) {
+                                    rv *= RS2;
+                                    const int f = c * 32 + j4 * 4 + u;
+                                    if (f >= nsplit) {
+                                        int coord;
+                                        const float jac = embed_jac(x, f - nsplit, net.mx, coord);
+                                        gacc[0] += (coord == 0) ? jac * rv : 0.f;
+                                        gacc[1] += (coord == 1) ? jac * rv : 0.f;
+                                        gacc[2] += (coord == 2) ? jac * rv : 0.f;
+                                        rv = 0.f;
+                                    }
+                                }
+                                hv[j4 * 4 + u] = rv * sv[u];
+                            }
+                        }
+                    } else {   // EK_GRAD: accumulator columns 0..47 = adjoint of the embedding
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int i = c * 32 + j;
+                            if (i < net.ex) {
+                                int coord;
+                                const float jac = embed_jac(x, i, net.mx, coord);
+                                const float rv = __uint_as_float(v[j]);
+                                gacc[0] += (coord == 0) ? jac * rv : 0.f;
+                                gacc[1] += (coord == 1) ? jac * rv : 0.f;
+                                gacc[2] += (coord == 2) ? jac * rv : 0.f;
+                            }
+                        }
+                        continue;
+                    }
+                    store_a_chunk(A_hi, A_lo, row, c * 4, hv);
+                    fence_proxy_async();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&a_ready[c]);
+                }
+                if (kind == EK_FEAT && sub == 0) {
+                    // k chunk 8 (columns 256..287) = positional encoding of the view direction, zero padded
+                    float hv[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) hv[j] = (j < net.ed) ? embed_col(dv, j, net.md) : 0.f;
+                    store_a_chunk(A_hi, A_lo, row, 32, hv);
+                    fence_proxy_async();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&a_ready[8]);
+                }
+            }
+            // ---- combine the 4 column-partials of every row and write the per-sample results
+            float* pp = part + (size_t)sub * 7 * TM;
+            pp[row] = head;
+            pp[TM + row] = rgbp[0]; pp[2 * TM + row] = rgbp[1]; pp[3 * TM + row] = rgbp[2];
+            pp[4 * TM + row] = gacc[0]; pp[5 * TM + row] = gacc[1]; pp[6 * TM + row] = gacc[2];
+            epi_bar_sync();
+            if (sub == 0 && m < P.M) {
+                float acc[7];
+#pragma unroll
+                for (int k = 0; k < 7; ++k)
+                    acc[k] = (part[k * TM + row] + part[(7 + k) * TM + row]) + (part[(14 + k) * TM + row] + part[(21 + k) * TM + row]);
+                P.out_sdf[m] = acc[0] + __ldg(net.sdf_head + 256);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float s = acc[1 + c] + __ldg(net.col_head + 768 + c);
+                    P.out_rgb[m * 3 + c] = __fdiv_rn(1.0f, 1.0f + expf(-s));
+                    P.out_grad[m * 3 + c] = acc[4 + c];
+                }
+            }
+            epi_bar_sync();     // part[] free for the next tile
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ---- weight packing -------------------------------------------------------------------------------------
+// dst block per k step: [part hi|lo][chunk 0|1][n rows][8 bf16].  Element (n, k):
+//   mode 0 (forward):  W[(n + row_off) * in + col(k)]   col(k) = k, or for the radiance input layer
+//                      k < feat ? ed + k : k - feat  (our A operand is [feat | PE(dir)], the reference's [PE(dir) | feat])
+//   mode 1 (reverse):  W[k * in + n]                     (B = W^T: n = input index, k = output index)
+__global__ void pack_main_kernel(uint8_t* __restrict__ dst, const float* __restrict__ W, int outd, int in, int ksteps, int n_rows, int mode,
+                                 int row_off, int feat_first, int ed) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int total = ksteps * 2 * n_rows;
+    if (i >= total) return;
+    int n = i % n_rows, chunk = (i / n_rows) % 2, ks = i / (2 * n_rows);
+    uint16_t hi[8], lo[8];
+    for (int e = 0; e < 8; ++e) {
+        int k = ks * 16 + chunk * 8 + e;
+        float w = 0.f;
+        if (mode == 0) {
+            int col = k;
+            if (feat_first > 0) col = (k < feat_first) ? ed + k : ((k - feat_first < ed) ? k - feat_first : -1);
+            if (col >= 0 && col < in && n + row_off < outd) w = W[(size_t)(n + row_off) * in + col];
+        } else {
+            if (k < outd && n < in) w = W[(size_t)k * in + n];
+        }
+        __nv_bfloat16 h = __float2bfloat16_rn(w);
+        __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+        hi[e] = *reinterpret_cast<uint16_t*>(&h);
+        lo[e] = *reinterpret_cast<uint16_t*>(&l);
+    }
+    const size_t sb = (size_t)n_rows * 64;
+    uint8_t* base = dst + (size_t)ks * sb + (size_t)chunk * n_rows * 16 + (size_t)n * 16;
+    *reinterpret_cast<uint4*>(base) = *reinterpret_cast<uint4*>(hi);
+    *reinterpret_cast<uint4*>(base + sb / 2) = *reinterpret_cast<uint4*>(lo);
+}
+
+struct MainState {
+    uint8_t* wpack;
+    MainNet net;
+    // packing recipe per op
+    int src_layer[MAX_OPS];   // index into the API weight array
+    int mode[MAX_OPS], row_off[MAX_OPS], feat_first[MAX_OPS];
+};
+
+}  // namespace tcmain
+
+int tcmain_create(i2sdf_handle* h, void** out_state) {
+    using namespace tcmain;
+    *out_state = nullptr;
+    const NetDev& n = h->net;
+    if (n.Ll != 0) return I2SDF_OK;            // light-mask configs keep the fp32 main pass for now
+    MainState* s = new MainState();
+    int nops = 0;
+    size_t off = 0;
+    auto add = [&](int ksteps, int nn, int kind, int layer, int src, int mode, int row_off, int feat_first) {
+        Op& o = s->net.ops[nops];
+        o.w_off = (int)off; o.ksteps = (short)ksteps; o.n = (short)nn; o.kind = (short)kind; o.layer = (short)layer;
+        s->src_layer[nops] = src; s->mode[nops] = mode; s->row_off[nops] = row_off; s->feat_first[nops] = feat_first;
+        off += (size_t)ksteps * nn * 64;
+        ++nops;
+    };
+    const int L = n.L, NL = L - 1, Lc = n.Lc;
+    for (int l = 0; l < NL; ++l) add(l == 0 ? 3 : 16, 256, l == NL - 1 ? EK_SDF_LAST : EK_SDF_HIDDEN, l, l, 0, 0, 0);
+    add(16, 256, EK_FEAT, L - 1, L - 1, 0, 1, 0);
+    for (int l = 0; l < Lc - 1; ++l) add(l == 0 ? 18 : 16, 256, l == Lc - 2 ? EK_COL_LAST : EK_COL_HIDDEN, l, L + l, 0, 0, l == 0 ? 256 : 0);
+    for (int l = NL - 1; l >= 1; --l) add(16, 256, EK_REV, l, l, 1, 0, 0);
+    add(16, 48, EK_GRAD, 0, 0, 1, 0, 0);
+    s->net.nops = nops;
+    if (cudaMalloc(&s->wpack, off) != cudaSuccess) { delete s; set_error("tcmain_create: cudaMalloc failed"); return I2SDF_E_CUDA; }
+    s->net.wpack = s->wpack;
+    cudaError_t e = cudaFuncSetAttribute(main_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) { cudaFree(s->wpack); delete s; set_error("tcmain_create: smem attribute: %s", cudaGetErrorString(e)); return I2SDF_E_CUDA; }
+    *out_state = s;
+    return I2SDF_OK;
+}
+
+void tcmain_destroy(void* state) {
+    tcmain::MainState* s = (tcmain::MainState*)state;
+    if (!s) return;
+    cudaFree(s->wpack);
+    delete s;
+}
+
+int tcmain_pack(i2sdf_handle* h, void* state, const float* const* W, cudaStream_t st) {
+    using namespace tcmain;
+    MainState* s = (MainState*)state;
+    if (!s) return I2SDF_OK;
+    for (int op = 0; op < s->net.nops; ++op) {
+        const Op& o = s->net.ops[op];
+        const int li = s->src_layer[op];
+        const int total = o.ksteps * 2 * o.n;
+        pack_main_kernel<<<(total + 255) / 256, 256, 0, st>>>(s->wpack + o.w_off, W[li], h->lay_out[li], h->lay_in[li], o.ksteps, o.n, s->mode[op],
+                                                              s->row_off[op], s->feat_first[op], h->net.ed);
+    }
+    I2SDF_CUDA_CHECK(cudaGetLastError());
+    return I2SDF_OK;
+}
+
+size_t tcmain_scratch_floats(const i2sdf_handle* h) { return (size_t)h->num_sms * (size_t)(h->net.L - 1) * tcmain::TM * 256; }
+
+int tcmain_launch(const i2sdf_handle* h, void* state, const MlpParams& p, cudaStream_t st) {
+    using namespace tcmain;
+    if (p.M <= 0) return I2SDF_OK;
+    const MainState* s = (const MainState*)state;
+    long long ntiles = (p.M + TM - 1) / TM;
+    int grid = (int)(ntiles < (long long)h->num_sms ? ntiles : (long long)h->num_sms);
+    main_tc_kernel<<<grid, NTHREADS, kSmemBytes, st>>>(p, s->net);
+    I2SDF_CUDA_CHECK(cudaGetLastError());
+    return I2SDF_OK;
+}
+
+}  // namespace i2sdf

@@ -124,5 +124,40 @@ __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, u
     lo = *reinterpret_cast<uint32_t*>(&l);
 }
 
+// softplus_100 in the overflow-free form max(a,0) + log1p(exp(-|100 a|))/100; equals nn.Softplus(beta=100,
+// threshold=20) to < 3e-11 absolute (the thresholded branch differs from the exact value by log1p(e^-20)/100).
+__device__ __forceinline__ float softplus100_fast(float a) {
+    float e = exp2f(-fabsf(a) * 144.26950408889634f);            // exp(-|100 a|)   (MUFU.EX2)
+    return fmaf(__log2f(1.0f + e), 0.0069314718055994531f, fmaxf(a, 0.0f));   // + ln2/100 * log2(1+e)   (MUFU.LG2)
+}
+
+// sin & cos for |a| < ~1e4: 3-constant Cody-Waite reduction to [-pi/4, pi/4] + minimax polynomials (~1 ulp)
+__device__ __forceinline__ void sincos_cw(float a, float& s, float& c) {
+    float q = rintf(a * 0.63661977236758134f);
+    int n = (int)q;
+    float r = fmaf(q, -1.5707962512969971f, a);
+    r = fmaf(q, -7.5497894158615964e-08f, r);
+    r = fmaf(q, -5.3903029534742384e-15f, r);
+    float r2 = r * r;
+    float sp = fmaf(fmaf(fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f), r2, -1.6666654611e-1f), r2 * r, r);
+    float cp = fmaf(fmaf(fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f), r2, 4.166664568298827e-2f), r2 * r2,
+                    fmaf(-0.5f, r2, 1.0f));
+    float ss = (n & 1) ? cp : sp;
+    float cc = (n & 1) ? sp : cp;
+    s = (n & 2) ? -ss : ss;
+    c = ((n + 1) & 2) ? -cc : cc;
+}
+
+// value of embedding column i (0..38) of point x:  [x, sin(2^k x), cos(2^k x)]   (embedder.py:28-38)
+__device__ __forceinline__ float embed_col(const float (&x)[3], int i, int mx) {
+    if (i < 3) return x[i];
+    const int qq = i - 3, k = qq / 6, cc = qq % 3;
+    if (k >= mx) return 0.f;
+    float s, c;
+    sincos_cw(__fmul_rn(x[cc], (float)(1 << k)), s, c);
+    return ((qq % 6) < 3) ? s : c;
+}
+
+
 }  // namespace tc
 }  // namespace i2sdf

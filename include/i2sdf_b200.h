@@ -78,8 +78,9 @@ const char* i2sdf_last_error(void);
 int i2sdf_create(const i2sdf_desc* desc, int device, i2sdf_handle** out);
 int i2sdf_destroy(i2sdf_handle* h);
 
-/* 1 if the sampler's SDF evaluations run on the tcgen05 tensor-core kernel, 0 if on the fp32 FMA-pipe kernel
- * (environment I2SDF_SIMT=1 at create time forces the latter; both are CUDA — there is no CPU path). */
+/* Bit 0: the sampler's SDF evaluations run on the tcgen05 tensor-core kernel; bit 1: the eval main pass
+ * (SDF + grad_x + radiance) does.  0 = everything on the fp32 FMA-pipe kernels (environment I2SDF_SIMT=1 at create
+ * time forces that, I2SDF_SIMT_MAIN=1 only the main pass; all of it is CUDA — there is no CPU path). */
 int i2sdf_uses_tensor_cores(const i2sdf_handle* h);
 
 /* Number of Linear layers the weight arrays below must hold: n_sdf + n_color + n_light, in that order. */
