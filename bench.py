@@ -167,29 +167,117 @@ def peaks():
     return dict(bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, hbm_gbs=6650.0, source="B200_PROFILING.md fallback (of fallback)")
 
 
+def make_train_gt(R, seed):
+    g = torch.Generator().manual_seed(seed)
+    return {
+        "rgb": torch.rand(R, 3, generator=g),
+        "depth": torch.rand(R, generator=g) * 2 + 0.5,
+        "depth_mask": torch.ones(R, dtype=torch.bool),
+        "normal": torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1),
+        "normal_mask": torch.ones(R, dtype=torch.bool),
+    }
+
+
+def cpu_train_arm(conf, model, rays, steps, warmup):
+    """Reference training step (forward + I2SDFLoss + backward incl. double backward) on the CPU: oracle port."""
+    from i2sdf_b200 import configs
+    from oracle import i2sdf_oracle as orc
+    spec = orc.spec_from_model_conf(conf, use_normal=True)
+    P0 = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    inp = orc.synthetic_rays(rays, seed=1, train_layout=True)
+    gt = make_train_gt(rays, 7)
+    lw = {k: v for k, v in configs.LOSS_SYNTHETIC.items() if k in ("eikonal_weight", "smooth_weight", "depth_weight", "normal_weight", "bubble_weight")}
+
+    def tape(n_final_guess=None):
+        R = rays
+        return {"jitter": torch.rand(R, spec.n_samples_eval), "u_final": torch.rand(R, spec.n_samples),
+                "extra_perm": lambda n: torch.randperm(n)[:spec.n_samples_extra], "eik_idx": torch.randint(98, (R,)),
+                "eik_uniform": torch.empty(R, 3).uniform_(-spec.bounding_sphere, spec.bounding_sphere),
+                "nbr_uniform": torch.empty(R, 3).uniform_(-0.005, 0.005)}
+
+    def one():
+        P = {k: v.clone().requires_grad_(True) for k, v in P0.items()}
+        out = orc.render(spec, P, inp, training=True, tape=tape())
+        loss = orc.recon_loss(out, gt, smooth_active=False, **lw)
+        loss.backward()
+
+    probe_inp = orc.synthetic_rays(8, seed=2, train_layout=True)
+
+    def probe():
+        P = {k: v.clone().requires_grad_(True) for k, v in P0.items()}
+        R = 8
+        tp = {"jitter": torch.rand(R, spec.n_samples_eval), "u_final": torch.rand(R, spec.n_samples),
+              "extra_perm": lambda n: torch.randperm(n)[:spec.n_samples_extra], "eik_idx": torch.randint(98, (R,)),
+              "eik_uniform": torch.empty(R, 3).uniform_(-3, 3), "nbr_uniform": torch.empty(R, 3).uniform_(-0.005, 0.005)}
+        out = orc.render(spec, P, probe_inp, training=True, tape=tp)
+        orc.recon_loss(out, make_train_gt(R, 3), smooth_active=False, **lw).backward()
+
+    pick_cpu_threads(probe)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        one()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return dict(value=rays * N_COMPOSITED * len(times) / total, ms_per_step=1e3 * total / len(times), cores=torch.get_num_threads(),
+                sample=f"{rays} of the 1024 rays per step, full training step (forward + loss + backward; no optimizer), "
+                       f"{len(times)} steps after {warmup} warm-up, torch CPU fp32, best of 8/16/32/64/all host threads "
+                       f"(picked {torch.get_num_threads()} of {os.cpu_count()})")
+
+
 def gpu_arm(args, rank, world, local_rank):
     import torch.distributed as dist
     from oracle import i2sdf_oracle as orc
+    from i2sdf_b200 import configs
+    from i2sdf_b200.network import I2SDFLoss
+    from i2sdf_b200.parallel import allreduce_gradients
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
+    train = args.mode == "train"
     conf, model = build_params()
-    cpu_state = None
-    if rank == 0:
-        cpu_state = (conf, model)
-    model_gpu = model.to(dev).eval()
+    if train:
+        model.use_normal = True          # trainer sets it from loss.normal_weight (model/trainer/recon.py:34-35)
+    cpu_snapshot = {k: v.detach().clone() for k, v in model.state_dict().items()} if rank == 0 else None
+    model_gpu = model.to(dev)
+    model_gpu.train(train)
     R = args.rays
     # rank-specific rays: the global batch is world * R rays sharded across ranks
-    inp_host = {k: v.pin_memory() for k, v in orc.synthetic_rays(R, seed=1 + rank).items()}
+    inp_host = {k: v.pin_memory() for k, v in orc.synthetic_rays(R, seed=1 + rank, train_layout=train).items()}
+    gt_host = {k: v.pin_memory() for k, v in make_train_gt(R, 7 + rank).items()} if train else {}
     inp_dev = {k: v.to(dev) for k, v in inp_host.items()}
+    gt_dev = {k: v.to(dev) for k, v in gt_host.items()}
     core = model_gpu._ready_core()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
     out_host = {}
+    if train:
+        loss_fn = I2SDFLoss(**configs.LOSS_SYNTHETIC)
+        opt = torch.optim.Adam(model_gpu.parameters(), lr=5.0e-4, eps=1e-15)      # model/trainer/recon.py:201-207
+        loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def train_step(inp, gt):
+        out = model_gpu(inp)
+        loss = loss_fn(out, gt, 0)["loss"]
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if world > 1:
+            allreduce_gradients(model_gpu.parameters())
+        opt.step()
+        return loss
 
     def step_resident():
+        if train:
+            return train_step(inp_dev, gt_dev)
         return model_gpu(inp_dev)
 
     def step_e2e():
         d = {k: v.to(dev, non_blocking=True) for k, v in inp_host.items()}
+        if train:
+            g = {k: v.to(dev, non_blocking=True) for k, v in gt_host.items()}
+            loss = train_step(d, g)
+            loss_host.copy_(loss.detach(), non_blocking=True)
+            return loss
         out = model_gpu(d)
         for k, v in out.items():
             if k not in out_host:
@@ -237,7 +325,7 @@ def gpu_arm(args, rank, world, local_rank):
     value = world * R * N_COMPOSITED * K / (ms_res * 1e-3)
     e2e_value = world * R * N_COMPOSITED * K / (ms_e2e * 1e-3)
     pk = peaks()
-    # dominant kernel: sampler SDF evaluations (73 % of the path's FLOPs)
+    # dominant kernel: sampler SDF evaluations (73 % of the forward path's FLOPs)
     sdf = prof["sampler_sdf"]
     sdf_launches = max(sdf["launches"], 1)
     pts_per_launch = R * 128
@@ -245,18 +333,28 @@ def gpu_arm(args, rank, world, local_rank):
     achieved = pts_per_launch * FLOP_PER_SDF_EVAL / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
     peak = pk["bf16_tflops_sustained"] if core.uses_tensor_cores else 72.0
     launches = sum(v["launches"] for v in prof.values())
-    h2d = sum(v.numel() * v.element_size() for v in inp_host.values())
-    d2h = sum(v.numel() * v.element_size() for v in out_host.values())
+    h2d = sum(v.numel() * v.element_size() for v in list(inp_host.values()) + list(gt_host.values()))
+    d2h = 4 if train else sum(v.numel() * v.element_size() for v in out_host.values())
+    if train:
+        workload = ("C2: training step on a 1024-ray batch, config/synthetic.yml networks and loss weights "
+                    "(rgb L1 + eikonal + depth + normal/angular; steps < 50k: no bubble/smooth terms): forward "
+                    "(error-bounded sampler 5x128 sdf-evals/ray, main pass on 97 samples/ray with saved activations, 3R eikonal "
+                    "points) + I2SDFLoss + backward incl. second-order terms + Adam(eps=1e-15) step + weight re-pack"
+                    + (" + one flat NCCL gradient all-reduce" if world > 1 else ""))
+    else:
+        workload = ("C2/C3 batch shape: 1024-ray forward render, config/synthetic.yml networks (8x256 SDF + 4x256 radiance), "
+                    "eval layout: sampler 5 rounds = 640 sdf-evals/ray + 97 composited samples/ray")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_res / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 (bf16x3 split products on tcgen05, fp32 accumulate)" if core.uses_tensor_cores else "f32",
+        "dtype": "f32 (bf16 hi/lo split products on tcgen05, fp32 accumulate)" if core.uses_tensor_cores else "f32",
         "data": "synthetic",
-        "config": {"workload": "C2/C3 batch shape: 1024-ray forward render, config/synthetic.yml networks "
-                               "(8x256 SDF + 4x256 radiance), W-sharp weights (geometric init seed 0, density.beta=0.01 -> 5 "
-                               "sampler rounds = 640 sdf-evals/ray + 97 composited samples/ray), eval layout",
+        "config": {"workload": workload, "mode": args.mode,
+                   "weights": "W-sharp: reference geometric init (seed 0), density.beta=0.01 so all 5 sampler rounds run",
                    "rays_per_gpu": R, "global_rays": world * R, "samples_per_ray_composited": N_COMPOSITED,
-                   "sdf_evals_per_ray": 5 * 128 + N_COMPOSITED, "parallelism": f"ray-sharded x{world}, no collective (inference)",
+                   "sdf_evals_per_ray": 5 * 128 + N_COMPOSITED,
+                   "parallelism": f"ray-sharded x{world}, " + ("one flat gradient all-reduce per step" if train else "no collective (inference)"),
+                   "tensor_cores": {"sampler_sdf": core.uses_tensor_cores, "main_pass": core.uses_tensor_cores_main and not train},
                    "l2": "flushed between timed iterations (256 MB write)", "timing": "CUDA events per step, max over ranks"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
@@ -266,11 +364,14 @@ def gpu_arm(args, rank, world, local_rank):
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                      "traffic": None, "flop_per_launch": pts_per_launch * FLOP_PER_SDF_EVAL, "ms_per_launch": per_launch_ms,
                      "peak_source": pk["source"] + (", sustained bf16 (kernel timed inside a step)" if core.uses_tensor_cores else "; fp32 FMA peak 148 SM x 128 FMA x 2 x 1.9 GHz"),
-                     "note": "achieved counts ALGORITHMIC flops (1 MAC = 2 flop); the kernel issues 3 bf16 MMAs per MAC"},
+                     "note": "achieved counts ALGORITHMIC flops (1 MAC = 2 flop); the kernel issues 3 bf16 MMAs per MAC, so 1/3 of the bf16 peak is this precision scheme's ceiling"},
         "clocks": clocks,
     }
-    conf_c, model_c = cpu_state
-    cb = cpu_arm(conf_c, model_c, args.cpu_rays, steps=2, warmup=1)
+    model_c = type("S", (), {"state_dict": lambda self: cpu_snapshot})()
+    if train:
+        cb = cpu_train_arm(conf, model_c, max(args.cpu_rays // 4, 16), steps=1, warmup=1)
+    else:
+        cb = cpu_arm(conf, model_c, args.cpu_rays, steps=2, warmup=1)
     line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port", "sample": cb["sample"]}
     return line
 
@@ -284,12 +385,15 @@ def main():
         if rank != 0:
             return
         conf, model = build_params()
-        cb = cpu_arm(conf, model, args.cpu_rays, steps=args.steps, warmup=args.warmup)
+        if args.mode == "train":
+            cb = cpu_train_arm(conf, model, max(args.cpu_rays // 4, 16), steps=args.steps, warmup=args.warmup)
+        else:
+            cb = cpu_arm(conf, model, args.cpu_rays, steps=args.steps, warmup=args.warmup)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "same as --impl ours (1024-ray forward render, synthetic.yml, W-sharp); each step is a bounded "
-                                       f"sample of {args.cpu_rays} rays on the host CPU"},
+                "config": {"workload": f"same as --impl ours --mode {args.mode} (1024-ray batch, synthetic.yml, W-sharp); each step is a "
+                                       "bounded sample of the batch on the host CPU (see cpu_baseline.sample)", "mode": args.mode},
                 "cpu_baseline": {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port", "sample": cb["sample"]},
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))

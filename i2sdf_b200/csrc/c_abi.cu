@@ -211,11 +211,7 @@ int i2sdf_create(const i2sdf_desc* d, int device, i2sdf_handle** out) {
     if (h->use_tc) {
         int rc = tc_create(h);
         if (rc != I2SDF_OK) { cudaFree(h->pool); free(h); return rc; }
-        const char* env2 = getenv("I2SDF_SIMT_MAIN");
-        if (!(env2 && env2[0] == '1')) {
-            rc = tcmain_create(h, &h->tcmain);
-            if (rc != I2SDF_OK) { tc_destroy(h); cudaFree(h->pool); free(h); return rc; }
-        }
+        // tc_create also sets h->tcmain when the full main pass is available (I2SDF_SIMT_MAIN=1 disables it)
     }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { set_error("create: %s", cudaGetErrorString(e)); cudaFree(h->pool); free(h); return I2SDF_E_CUDA; }
@@ -226,7 +222,6 @@ int i2sdf_create(const i2sdf_desc* d, int device, i2sdf_handle** out) {
 int i2sdf_destroy(i2sdf_handle* h) {
     if (!h) return I2SDF_OK;
     if (h->tc) tc_destroy(h);
-    if (h->tcmain) tcmain_destroy(h->tcmain);
     if (h->prof) { Prof* p = (Prof*)h->prof; for (auto& v : p->ev) for (auto e : v) cudaEventDestroy(e); delete p; }
     cudaFree(h->pool);
     free(h);

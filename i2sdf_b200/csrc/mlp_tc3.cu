@@ -1,24 +1,30 @@
-// Main pass on the tensor cores (tcgen05 / TMEM), sm_100a: for a resident tile of 128 ray samples
-//   SDF stack forward -> sdf head -> feature layer -> radiance stack -> rgb head -> reverse sweep for grad_x sdf
-// as ONE persistent kernel.  Same scheme as mlp_tc.cu (bf16 hi/lo split activations as the SMEM A operand, weights
-// streamed by cp.async.bulk, fp32 accumulators ping-ponged in TMEM, 16 epilogue warps trailing chunk by chunk), driven
-// by a small table of "ops" (one op = one dense layer = ksteps x 3 tcgen05.mma):
-//   F_0..F_{NL-1}   SDF hidden layers           epilogue: +b, softplus_100 (+skip concat), sigma' -> scratch
-//   G               feature rows of last layer  epilogue: +b ; appends PE(view dir) as k chunk 8
-//   C_0..C_{Lc-2}   radiance hidden layers      epilogue: +b, ReLU ; last one: rgb head (fp32 dots) and the
-//                                               reverse prologue  ra = w_sdf * sigma'_{NL-1}
-//   R_{NL-1}..R_1   reverse sweep (W^T)         epilogue: (skip split) * sigma'_{l-1}
-//   R_0             adjoint of the embedding    epilogue: J(x)^T r  -> grad_x sdf
-// sigma' (softplus derivative, fp32) round-trips through a per-CTA scratch in global memory (L2-resident: 1 MB per CTA).
-// Only sdf / rgb / grad per sample go to HBM; compositing is the per-ray kernel in sampler.cu.
+// Tensor-core MLP chain (tcgen05 / TMEM), sm_100a — unified kernel, version 3.
 //
-// Replaces (reference): model/network/__init__.py:103-116 = ImplicitNetwork.get_outputs mlp.py:123-143 (forward :84-105
-// + autograd.grad :134-140) and RenderingNetwork.forward mlp.py:208-229.
+// One persistent CTA per SM walks a resident tile of 128 ray points through a table of dense "ops" (one op = one
+// layer = ksteps x 3 tcgen05.mma):
+//     sdf-only (sampler):   F_0 .. F_{NL-1}                                   -> sdf
+//     full main pass:       F_0 .. F_{NL-1}, G, C_0 .. C_{Lc-2}, R_{NL-1} .. R_1, R_0   -> sdf, rgb, grad_x sdf
+//   F  SDF hidden layers        epilogue: +b, softplus_100 (+skip concat) [full: softplus' -> scratch]
+//   G  feature rows of last layer           +b ; appends PE(view dir) as k chunk 8
+//   C  radiance hidden layers               +b, ReLU ; last: rgb head (fp32 dots) + reverse prologue w_sdf * softplus'
+//   R  reverse sweep with W^T               (skip split) * softplus'_{l-1} ;  R_0: J(x)^T r -> grad_x sdf
+// Activations never leave the SM: they are the SMEM A operand (bf16 hi + bf16 lo, canonical K-major layout); weights
+// stream from L2 by cp.async.bulk into a 4-stage ring; accumulators are fp32 in TMEM, two buffers ping-ponged by op;
+// every MAC is 3 bf16 products  A_hi W_hi + A_lo W_hi + A_hi W_lo  (error ~2^-16, measured 3e-5 on the outputs).
+//
+// Warp roles: warp 0 = weight producer, warp 1 = MMA issuer, warps 2..17 = epilogue.  An epilogue warp (q, sub) owns TMEM
+// lane quarter q and, in iteration it = 0..3, the 16 columns  (2 it + sub/2) * 32 + (sub%2) * 16 .. +16 : the eight
+// warps working on a 32-column chunk finish it together and chunks complete IN ORDER, so the MMA warp (which waits per
+// chunk) trails the epilogue by one chunk pair and layer l+1's tensor work overlaps layer l's epilogue on one tile.
+//
+// Replaces (reference): ImplicitNetwork.get_sdf_vals mlp.py:145-151 as called by the sampler (ray_sampler.py:84-89);
+// model/network/__init__.py:103-116 = ImplicitNetwork.get_outputs mlp.py:123-143 (forward :84-105 + autograd.grad
+// :134-140) and RenderingNetwork.forward mlp.py:208-229; Embedder embedder.py:28-38.
 #include "common.cuh"
 #include "tc_common.cuh"
 
 namespace i2sdf {
-namespace tcmain {
+namespace tc3 {
 
 using namespace tc;
 
@@ -44,7 +50,7 @@ struct Op {
     short kind;         // epilogue kind applied to this op's accumulator
     short layer;        // layer index within its stack
 };
-struct MainNet {
+struct OpTable {
     const uint8_t* wpack;
     int nops;
     Op ops[MAX_OPS];
@@ -52,16 +58,23 @@ struct MainNet {
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32) : "memory"); }
 
-__device__ __forceinline__ void store_a_chunk(uint8_t* A_hi, uint8_t* A_lo, int row, int kc0, const float (&hv)[32]) {
+// 16 consecutive columns (k chunks kc0, kc0+1) of one row of the next A operand, split hi / lo
+__device__ __forceinline__ void store_a16(uint8_t* A_hi, uint8_t* A_lo, int row, int kc0, const float (&hv)[16]) {
 #pragma unroll
-    for (int s4 = 0; s4 < 4; ++s4) {
+    for (int s = 0; s < 2; ++s) {
         uint32_t h[4], lo[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) split_bf16x2(hv[s4 * 8 + 2 * i], hv[s4 * 8 + 2 * i + 1], h[i], lo[i]);
-        const uint32_t off = seg_off<TM>(row, kc0 + s4);
+        for (int i = 0; i < 4; ++i) split_bf16x2(hv[s * 8 + 2 * i], hv[s * 8 + 2 * i + 1], h[i], lo[i]);
+        const uint32_t off = seg_off<TM>(row, kc0 + s);
         *reinterpret_cast<uint4*>(A_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<uint4*>(A_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
+}
+__device__ __forceinline__ void publish_chunk(uint64_t* bar, int lane) {
+    fence_proxy_async();          // generic-proxy smem writes -> async proxy (tensor core operand reads)
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
 }
 
 // d embed_i / d x_c(i) and the coordinate c(i) it belongs to
@@ -76,7 +89,16 @@ __device__ __forceinline__ float embed_jac(const float (&x)[3], int i, int mx, i
     return ((qq % 6) < 3) ? f * c : -f * s;
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) main_tc_kernel(const MlpParams P, const MainNet T) {
+__device__ __forceinline__ bool round_active(const MlpParams& P) {
+    if (P.round_idx <= 0) return true;
+    float b0 = fabsf(*P.beta_param) + P.beta_min;
+    for (int j = 0; j < P.round_idx; ++j)
+        if (!(P.beta_max[j] > b0)) return false;
+    return true;
+}
+
+template <bool FULL>
+__global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, const OpTable T) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* A_hi = smem;
@@ -86,9 +108,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) main_tc_kernel(const MlpParams P,
     uint64_t* bars = reinterpret_cast<uint64_t*>(part + PART_FLOATS);
     uint64_t* full = bars;
     uint64_t* empty = bars + NSTAGE;
-    uint64_t* a_ready = bars + 2 * NSTAGE;       // [N_READY]
+    uint64_t* a_ready = bars + 2 * NSTAGE;       // [N_READY], 8 arrivals each
     uint64_t* d_full = a_ready + N_READY;        // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 2);
+
+    if (!FULL && !round_active(P)) return;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const NetDev& net = P.net;
@@ -97,7 +121,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) main_tc_kernel(const MlpParams P,
 
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < N_READY; ++i) mbar_init(&a_ready[i], 4);
+        for (int i = 0; i < N_READY; ++i) mbar_init(&a_ready[i], 8);
         mbar_init(&d_full[0], 1);
         mbar_init(&d_full[1], 1);
         fence_mbar_init();
@@ -169,7 +193,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) main_tc_kernel(const MlpParams P,
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const int nsplit = 256 - net.ex;
         const float RS2 = 0.70710678118654752f;
-        float* sig_base = P.scratch + (size_t)blockIdx.x * (size_t)NL * TM * 256 + (size_t)row * 256;
+        float* sig_base = FULL ? (P.scratch + (size_t)blockIdx.x * (size_t)NL * TM * 256 + (size_t)row * 256) : nullptr;
         uint32_t dphase = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const long long m = tile * TM + row;
@@ -185,30 +209,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) main_tc_kernel(const MlpParams P,
                     for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(P.ray_o[r * 3 + c], __fmul_rn(t, dv[c]));
                 }
             }
-            // ---- prologue: A_0 = embedding (48 columns): sub 0 -> columns 0..31, sub 1 -> 32..47
-            if (sub < 2) {
-                float hv[32];
+            // ---- prologue: A_0 = embedding, 48 columns: sub s writes columns 16 s .. 16 s + 15 (sub 3: nothing)
+            {
+                if (sub < 3) {
+                    float hv[16];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int i = sub * 32 + j;
-                    hv[j] = (i < net.ex) ? embed_col(x, i, net.mx) : 0.f;
-                }
-                if (sub == 0) store_a_chunk(A_hi, A_lo, row, 0, hv);
-                else {
-#pragma unroll
-                    for (int s4 = 0; s4 < 2; ++s4) {
-                        uint32_t h[4], lo[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) split_bf16x2(hv[s4 * 8 + 2 * i], hv[s4 * 8 + 2 * i + 1], h[i], lo[i]);
-                        const uint32_t off = seg_off<TM>(row, 4 + s4);
-                        *reinterpret_cast<uint4*>(A_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-                        *reinterpret_cast<uint4*>(A_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    for (int j = 0; j < 16; ++j) {
+                        const int i = sub * 16 + j;
+                        hv[j] = (i < net.ex) ? embed_col(x, i, net.mx) : 0.f;
                     }
+                    store_a16(A_hi, A_lo, row, sub * 2, hv);
                 }
-                fence_proxy_async();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&a_ready[sub]);
+                publish_chunk(&a_ready[sub >> 1], lane);
             }
 
             float head = 0.f, rgbp[3] = {0.f, 0.f, 0.f}, gacc[3] = {0.f, 0.f, 0.f};
@@ -219,51 +231,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) main_tc_kernel(const MlpParams P,
                 dphase ^= (1u << b);
                 tc_fence_after();
 #pragma unroll 1
-                for (int cc = 0; cc < 2; ++cc) {
-                    const int c = sub + 4 * cc;
-                    if (kind == EK_GRAD && c >= 2) break;
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + lane_base + (uint32_t)b * 256u + (uint32_t)c * 32u, v);
+                for (int it = 0; it < 4; ++it) {
+                    const int c = 2 * it + (sub >> 1);                 // 32-column chunk
+                    const int col0 = c * 32 + (sub & 1) * 16;          // first of this warp's 16 columns
+                    if (FULL && kind == EK_GRAD && col0 >= 48) break;
+                    uint32_t v[16];
+                    tmem_ld16(tmem_base + lane_base + (uint32_t)b * 256u + (uint32_t)col0, v);
                     tmem_ld_wait();
-                    float hv[32];
+                    float hv[16];
                     if (kind == EK_SDF_HIDDEN || kind == EK_SDF_LAST) {
-                        const float* __restrict__ bias = net.sdf_b[l] + c * 32;
-                        float* sg = sig_base + (size_t)l * TM * 256 + c * 32;
+                        const float* __restrict__ bias = net.sdf_b[l] + col0;
 #pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4) {
+                        for (int j4 = 0; j4 < 4; ++j4) {
                             const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + j4);
                             const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
                             float so[4];
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 const float a = __uint_as_float(v[j4 * 4 + u]) + bv[u];
-                                const float e = exp2f(-fabsf(a) * 144.26950408889634f);
-                                const float rr = __fdividef(1.0f, 1.0f + e);
-                                hv[j4 * 4 + u] = fmaf(__log2f(1.0f + e), 0.0069314718055994531f, fmaxf(a, 0.0f));
-                                so[u] = (a >= 0.f) ? rr : e * rr;                       // softplus'(a) = sigmoid(100 a)
+                                const float e = ex2_approx(-fabsf(a) * 144.26950408889634f);          // exp(-|100 a|)
+                                hv[j4 * 4 + u] = fmaf(lg2_approx(1.0f + e), 0.0069314718055994531f, fmaxf(a, 0.0f));
+                                if (FULL) {
+                                    const float rr = rcp_approx(1.0f + e);
+                                    so[u] = (a >= 0.f) ? rr : e * rr;                               // softplus'(a) = sigmoid(100 a)
+                                }
                             }
-                            *reinterpret_cast<float4*>(sg + j4 * 4) = make_float4(so[0], so[1], so[2], so[3]);
+                            if (FULL) *reinterpret_cast<float4*>(sig_base + (size_t)l * TM * 256 + col0 + j4 * 4) = make_float4(so[0], so[1], so[2], so[3]);
                         }
                         if (kind == EK_SDF_LAST) {
 #pragma unroll
-                            for (int j4 = 0; j4 < 8; ++j4) {
-                                const float4 w = __ldg(reinterpret_cast<const float4*>(net.sdf_head + c * 32) + j4);
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const float4 w = __ldg(reinterpret_cast<const float4*>(net.sdf_head + col0) + j4);
                                 head = fmaf(hv[j4 * 4 + 0], w.x, head);
                                 head = fmaf(hv[j4 * 4 + 1], w.y, head);
                                 head = fmaf(hv[j4 * 4 + 2], w.z, head);
                                 head = fmaf(hv[j4 * 4 + 3], w.w, head);
                             }
-                        } else if (l + 1 == net.skip) {
+                            if (!FULL) continue;                       // sdf-only: nothing follows the last hidden layer
+                        } else if (l + 1 == net.skip) {                // cat([h, embed]) / sqrt(2)   (mlp.py:94-95)
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const int f = c * 32 + j;
+                            for (int j = 0; j < 16; ++j) {
+                                const int f = col0 + j;
                                 hv[j] = ((f >= nsplit) ? embed_col(x, f - nsplit, net.mx) : hv[j]) * RS2;
                             }
                         }
-                    } else if (kind == EK_FEAT || kind == EK_COL_HIDDEN || kind == EK_COL_LAST) {
-                        const float* __restrict__ bias = (kind == EK_FEAT ? net.sdf_b[net.L - 1] : net.col_b[l]) + c * 32;
+                    } else if (FULL && (kind == EK_FEAT || kind == EK_COL_HIDDEN || kind == EK_COL_LAST)) {
+                        const float* __restrict__ bias = (kind == EK_FEAT ? net.sdf_b[net.L - 1] : net.col_b[l]) + col0;
 #pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4) {
+                        for (int j4 = 0; j4 < 4; ++j4) {
                             const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + j4);
                             hv[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + bb.x;
                             hv[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + bb.y;
@@ -272,31 +287,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) main_tc_kernel(const MlpParams P,
                         }
                         if (kind != EK_FEAT) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) hv[j] = fmaxf(hv[j], 0.f);
+                            for (int j = 0; j < 16; ++j) hv[j] = fmaxf(hv[j], 0.f);
                         }
                         if (kind == EK_COL_LAST) {
-                            const float* __restrict__ wh = net.col_head + c * 32;
+                            const float* __restrict__ wh = net.col_head + col0;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                rgbp[0] = fmaf(hv[j], __ldg(wh + j), rgbp[0]);
-                                rgbp[1] = fmaf(hv[j], __ldg(wh + 256 + j), rgbp[1]);
-                                rgbp[2] = fmaf(hv[j], __ldg(wh + 512 + j), rgbp[2]);
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const float4 w0 = __ldg(reinterpret_cast<const float4*>(wh) + j4);
+                                const float4 w1 = __ldg(reinterpret_cast<const float4*>(wh + 256) + j4);
+                                const float4 w2 = __ldg(reinterpret_cast<const float4*>(wh + 512) + j4);
+                                const float* hh = hv + j4 * 4;
+                                rgbp[0] = fmaf(hh[0], w0.x, fmaf(hh[1], w0.y, fmaf(hh[2], w0.z, fmaf(hh[3], w0.w, rgbp[0]))));
+                                rgbp[1] = fmaf(hh[0], w1.x, fmaf(hh[1], w1.y, fmaf(hh[2], w1.z, fmaf(hh[3], w1.w, rgbp[1]))));
+                                rgbp[2] = fmaf(hh[0], w2.x, fmaf(hh[1], w2.y, fmaf(hh[2], w2.z, fmaf(hh[3], w2.w, rgbp[2]))));
                             }
                             // reverse prologue: adjoint of a_{NL-1} = w_sdf * softplus'(a_{NL-1})
-                            const float* sg = sig_base + (size_t)(NL - 1) * TM * 256 + c * 32;
+                            const float* sg = sig_base + (size_t)(NL - 1) * TM * 256 + col0;
 #pragma unroll
-                            for (int j4 = 0; j4 < 8; ++j4) {
-                                const float4 w = __ldg(reinterpret_cast<const float4*>(net.sdf_head + c * 32) + j4);
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const float4 w = __ldg(reinterpret_cast<const float4*>(net.sdf_head + col0) + j4);
                                 const float4 s = *reinterpret_cast<const float4*>(sg + j4 * 4);
                                 hv[j4 * 4 + 0] = w.x * s.x; hv[j4 * 4 + 1] = w.y * s.y; hv[j4 * 4 + 2] = w.z * s.z; hv[j4 * 4 + 3] = w.w * s.w;
                             }
                         }
-                    } else if (kind == EK_REV) {
+                    } else if (FULL && kind == EK_REV) {
                         // accumulator = adjoint of the input of SDF layer l ; next A = (that) * softplus'(a_{l-1})
-                        const float* sg = sig_base + (size_t)(l - 1) * TM * 256 + c * 32;
+                        const float* sg = sig_base + (size_t)(l - 1) * TM * 256 + col0;
                         const bool is_skip = (l == net.skip);
 #pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4) {
+                        for (int j4 = 0; j4 < 4; ++j4) {
                             const float4 s = *reinterpret_cast<const float4*>(sg + j4 * 4);
                             const float sv[4] = {s.x, s.y, s.z, s.w};
 #pragma unroll
@@ -304,7 +323,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) main_tc_kernel(const MlpParams P,
                                 float rv = __uint_as_float(v[j4 * 4 + u]);
                                 if (is_skip) {
                                     rv *= RS2;
-                                    const int f = c * 32 + j4 * 4 + u;
+                                    const int f = col0 + j4 * 4 + u;
                                     if (f >= nsplit) {
                                         int coord;
                                         const float jac = embed_jac(x, f - nsplit, net.mx, coord);
@@ -317,10 +336,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) main_tc_kernel(const MlpParams P,
                                 hv[j4 * 4 + u] = rv * sv[u];
                             }
                         }
-                    } else {   // EK_GRAD: accumulator columns 0..47 = adjoint of the embedding
+                    } else if (FULL) {   // EK_GRAD: accumulator columns 0..47 = adjoint of the embedding
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int i = c * 32 + j;
+                        for (int j = 0; j < 16; ++j) {
+                            const int i = col0 + j;
                             if (i < net.ex) {
                                 int coord;
                                 const float jac = embed_jac(x, i, net.mx, coord);
@@ -330,43 +349,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) main_tc_kernel(const MlpParams P,
                                 gacc[2] += (coord == 2) ? jac * rv : 0.f;
                             }
                         }
-                        continue;
+                        break;
                     }
-                    store_a_chunk(A_hi, A_lo, row, c * 4, hv);
-                    fence_proxy_async();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&a_ready[c]);
+                    store_a16(A_hi, A_lo, row, col0 >> 3, hv);
+                    publish_chunk(&a_ready[c], lane);
                 }
-                if (kind == EK_FEAT && sub == 0) {
+                if (FULL && kind == EK_FEAT && sub < 2) {
                     // k chunk 8 (columns 256..287) = positional encoding of the view direction, zero padded
-                    float hv[32];
+                    float hv[16];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) hv[j] = (j < net.ed) ? embed_col(dv, j, net.md) : 0.f;
-                    store_a_chunk(A_hi, A_lo, row, 32, hv);
-                    fence_proxy_async();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&a_ready[8]);
+                    for (int j = 0; j < 16; ++j) {
+                        const int i = sub * 16 + j;
+                        hv[j] = (i < net.ed) ? embed_col(dv, i, net.md) : 0.f;
+                    }
+                    store_a16(A_hi, A_lo, row, 32 + sub * 2, hv);
+                    publish_chunk(&a_ready[8], lane);
                 }
             }
             // ---- combine the 4 column-partials of every row and write the per-sample results
             float* pp = part + (size_t)sub * 7 * TM;
             pp[row] = head;
-            pp[TM + row] = rgbp[0]; pp[2 * TM + row] = rgbp[1]; pp[3 * TM + row] = rgbp[2];
-            pp[4 * TM + row] = gacc[0]; pp[5 * TM + row] = gacc[1]; pp[6 * TM + row] = gacc[2];
+            if (FULL) {
+                pp[TM + row] = rgbp[0]; pp[2 * TM + row] = rgbp[1]; pp[3 * TM + row] = rgbp[2];
+                pp[4 * TM + row] = gacc[0]; pp[5 * TM + row] = gacc[1]; pp[6 * TM + row] = gacc[2];
+            }
             epi_bar_sync();
             if (sub == 0 && m < P.M) {
                 float acc[7];
 #pragma unroll
-                for (int k = 0; k < 7; ++k)
+                for (int k = 0; k < (FULL ? 7 : 1); ++k)
                     acc[k] = (part[k * TM + row] + part[(7 + k) * TM + row]) + (part[(14 + k) * TM + row] + part[(21 + k) * TM + row]);
                 P.out_sdf[m] = acc[0] + __ldg(net.sdf_head + 256);
+                if (FULL) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float s = acc[1 + c] + __ldg(net.col_head + 768 + c);
-                    P.out_rgb[m * 3 + c] = __fdiv_rn(1.0f, 1.0f + expf(-s));
-                    P.out_grad[m * 3 + c] = acc[4 + c];
+                    for (int c = 0; c < 3; ++c) {
+                        const float s = acc[1 + c] + __ldg(net.col_head + 768 + c);
+                        P.out_rgb[m * 3 + c] = __fdiv_rn(1.0f, 1.0f + expf(-s));
+                        P.out_grad[m * 3 + c] = acc[4 + c];
+                    }
                 }
             }
             epi_bar_sync();     // part[] free for the next tile
@@ -382,8 +402,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) main_tc_kernel(const MlpParams P,
 //   mode 0 (forward):  W[(n + row_off) * in + col(k)]   col(k) = k, or for the radiance input layer
 //                      k < feat ? ed + k : k - feat  (our A operand is [feat | PE(dir)], the reference's [PE(dir) | feat])
 //   mode 1 (reverse):  W[k * in + n]                     (B = W^T: n = input index, k = output index)
-__global__ void pack_main_kernel(uint8_t* __restrict__ dst, const float* __restrict__ W, int outd, int in, int ksteps, int n_rows, int mode,
-                                 int row_off, int feat_first, int ed) {
+__global__ void pack_kernel(uint8_t* __restrict__ dst, const float* __restrict__ W, int outd, int in, int ksteps, int n_rows, int mode,
+                            int row_off, int feat_first, int ed) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int total = ksteps * 2 * n_rows;
     if (i >= total) return;
@@ -410,77 +430,101 @@ __global__ void pack_main_kernel(uint8_t* __restrict__ dst, const float* __restr
     *reinterpret_cast<uint4*>(base + sb / 2) = *reinterpret_cast<uint4*>(lo);
 }
 
-struct MainState {
+struct State {
     uint8_t* wpack;
-    MainNet net;
-    // packing recipe per op
-    int src_layer[MAX_OPS];   // index into the API weight array
+    OpTable sdf;              // ops of the sdf-only chain (a prefix of the full table)
+    OpTable full;             // nops == 0 if the full main pass is unavailable for this network
+    int src_layer[MAX_OPS];   // packing recipe per op of the full table
     int mode[MAX_OPS], row_off[MAX_OPS], feat_first[MAX_OPS];
+    int n_pack;               // number of ops to pack
 };
 
-}  // namespace tcmain
+}  // namespace tc3
 
-int tcmain_create(i2sdf_handle* h, void** out_state) {
-    using namespace tcmain;
-    *out_state = nullptr;
+int tc_create(i2sdf_handle* h) {
+    using namespace tc3;
+    State* s = new State();
     const NetDev& n = h->net;
-    if (n.Ll != 0) return I2SDF_OK;            // light-mask configs keep the fp32 main pass for now
-    MainState* s = new MainState();
+    const int L = n.L, NL = L - 1, Lc = n.Lc;
+    const bool want_full = (n.Ll == 0) && !(getenv("I2SDF_SIMT_MAIN") && getenv("I2SDF_SIMT_MAIN")[0] == '1');
+    OpTable& T = s->full;
     int nops = 0;
     size_t off = 0;
     auto add = [&](int ksteps, int nn, int kind, int layer, int src, int mode, int row_off, int feat_first) {
-        Op& o = s->net.ops[nops];
+        Op& o = T.ops[nops];
         o.w_off = (int)off; o.ksteps = (short)ksteps; o.n = (short)nn; o.kind = (short)kind; o.layer = (short)layer;
         s->src_layer[nops] = src; s->mode[nops] = mode; s->row_off[nops] = row_off; s->feat_first[nops] = feat_first;
         off += (size_t)ksteps * nn * 64;
         ++nops;
     };
-    const int L = n.L, NL = L - 1, Lc = n.Lc;
     for (int l = 0; l < NL; ++l) add(l == 0 ? 3 : 16, 256, l == NL - 1 ? EK_SDF_LAST : EK_SDF_HIDDEN, l, l, 0, 0, 0);
-    add(16, 256, EK_FEAT, L - 1, L - 1, 0, 1, 0);
-    for (int l = 0; l < Lc - 1; ++l) add(l == 0 ? 18 : 16, 256, l == Lc - 2 ? EK_COL_LAST : EK_COL_HIDDEN, l, L + l, 0, 0, l == 0 ? 256 : 0);
-    for (int l = NL - 1; l >= 1; --l) add(16, 256, EK_REV, l, l, 1, 0, 0);
-    add(16, 48, EK_GRAD, 0, 0, 1, 0, 0);
-    s->net.nops = nops;
-    if (cudaMalloc(&s->wpack, off) != cudaSuccess) { delete s; set_error("tcmain_create: cudaMalloc failed"); return I2SDF_E_CUDA; }
-    s->net.wpack = s->wpack;
-    cudaError_t e = cudaFuncSetAttribute(main_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    if (e != cudaSuccess) { cudaFree(s->wpack); delete s; set_error("tcmain_create: smem attribute: %s", cudaGetErrorString(e)); return I2SDF_E_CUDA; }
-    *out_state = s;
+    if (want_full) {
+        add(16, 256, EK_FEAT, L - 1, L - 1, 0, 1, 0);
+        for (int l = 0; l < Lc - 1; ++l) add(l == 0 ? 18 : 16, 256, l == Lc - 2 ? EK_COL_LAST : EK_COL_HIDDEN, l, L + l, 0, 0, l == 0 ? 256 : 0);
+        for (int l = NL - 1; l >= 1; --l) add(16, 256, EK_REV, l, l, 1, 0, 0);
+        add(16, 48, EK_GRAD, 0, 0, 1, 0, 0);
+    }
+    s->n_pack = nops;
+    T.nops = want_full ? nops : 0;
+    if (cudaMalloc(&s->wpack, off) != cudaSuccess) { delete s; set_error("tc_create: cudaMalloc failed"); return I2SDF_E_CUDA; }
+    T.wpack = s->wpack;
+    s->sdf = T;
+    s->sdf.nops = NL;
+    cudaError_t e = cudaFuncSetAttribute(tc_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) { cudaFree(s->wpack); delete s; set_error("tc_create: smem attribute: %s", cudaGetErrorString(e)); return I2SDF_E_CUDA; }
+    h->tc = s;
+    h->tcmain = want_full ? (void*)s : nullptr;
     return I2SDF_OK;
 }
 
-void tcmain_destroy(void* state) {
-    tcmain::MainState* s = (tcmain::MainState*)state;
+void tc_destroy(i2sdf_handle* h) {
+    tc3::State* s = (tc3::State*)h->tc;
     if (!s) return;
     cudaFree(s->wpack);
     delete s;
+    h->tc = nullptr;
+    h->tcmain = nullptr;
 }
 
-int tcmain_pack(i2sdf_handle* h, void* state, const float* const* W, cudaStream_t st) {
-    using namespace tcmain;
-    MainState* s = (MainState*)state;
-    if (!s) return I2SDF_OK;
-    for (int op = 0; op < s->net.nops; ++op) {
-        const Op& o = s->net.ops[op];
+int tc_pack(i2sdf_handle* h, const float* const* W, const float* const* b, cudaStream_t st) {
+    using namespace tc3;
+    (void)b;   // biases / heads reuse the fp32 arrays packed for the fp32 path
+    State* s = (State*)h->tc;
+    for (int op = 0; op < s->n_pack; ++op) {
+        const Op& o = s->full.ops[op];
         const int li = s->src_layer[op];
         const int total = o.ksteps * 2 * o.n;
-        pack_main_kernel<<<(total + 255) / 256, 256, 0, st>>>(s->wpack + o.w_off, W[li], h->lay_out[li], h->lay_in[li], o.ksteps, o.n, s->mode[op],
-                                                              s->row_off[op], s->feat_first[op], h->net.ed);
+        pack_kernel<<<(total + 255) / 256, 256, 0, st>>>(s->wpack + o.w_off, W[li], h->lay_out[li], h->lay_in[li], o.ksteps, o.n, s->mode[op],
+                                                         s->row_off[op], s->feat_first[op], h->net.ed);
     }
     I2SDF_CUDA_CHECK(cudaGetLastError());
     return I2SDF_OK;
 }
 
-size_t tcmain_scratch_floats(const i2sdf_handle* h) { return (size_t)h->num_sms * (size_t)(h->net.L - 1) * tcmain::TM * 256; }
+static inline int tc_grid(const i2sdf_handle* h, long long M) {
+    long long ntiles = (M + tc3::TM - 1) / tc3::TM;
+    return (int)(ntiles < (long long)h->num_sms ? ntiles : (long long)h->num_sms);
+}
 
-int tcmain_launch(const i2sdf_handle* h, void* state, const MlpParams& p, cudaStream_t st) {
-    using namespace tcmain;
+int tc_launch_sdf(const i2sdf_handle* h, const MlpParams& p, cudaStream_t st) {
+    using namespace tc3;
     if (p.M <= 0) return I2SDF_OK;
-    const MainState* s = (const MainState*)state;
-    long long ntiles = (p.M + TM - 1) / TM;
-    int grid = (int)(ntiles < (long long)h->num_sms ? ntiles : (long long)h->num_sms);
-    main_tc_kernel<<<grid, NTHREADS, kSmemBytes, st>>>(p, s->net);
+    const State* s = (const State*)h->tc;
+    tc_mlp_kernel<false><<<tc_grid(h, p.M), NTHREADS, kSmemBytes, st>>>(p, s->sdf);
+    I2SDF_CUDA_CHECK(cudaGetLastError());
+    return I2SDF_OK;
+}
+
+// full main pass (kept under the tcmain_* names used by c_abi.cu)
+int tcmain_create(i2sdf_handle*, void** out_state) { *out_state = nullptr; return I2SDF_OK; }
+void tcmain_destroy(void*) {}
+int tcmain_pack(i2sdf_handle*, void*, const float* const*, cudaStream_t) { return I2SDF_OK; }
+int tcmain_launch(const i2sdf_handle* h, void* state, const MlpParams& p, cudaStream_t st) {
+    using namespace tc3;
+    if (p.M <= 0) return I2SDF_OK;
+    const State* s = (const State*)state;
+    tc_mlp_kernel<true><<<tc_grid(h, p.M), NTHREADS, kSmemBytes, st>>>(p, s->full);
     I2SDF_CUDA_CHECK(cudaGetLastError());
     return I2SDF_OK;
 }

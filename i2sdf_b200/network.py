@@ -324,8 +324,9 @@ class I2SDFNetwork(nn.Module):
         R = o.shape[0]
         beta = self.density.beta.detach()
         z, z_eik = core.sample(o, d, beta, None)
-        want_normal = not predict_only
-        out = core.render(o, d, dnorm, z, beta, want_normal=want_normal, want_light=self.use_light)
+        # grad_x is always evaluated (the reference's returns_grad is True in eval, network/__init__.py:109); this also
+        # keeps predict_only calls on the same kernels, hence bit-identical to the full call
+        out = core.render(o, d, dnorm, z, beta, want_normal=True, want_light=self.use_light)
         res = {"rgb_values": out["rgb"], "depth_values": out["depth"], "weight_sum": out["weight_sum"][:, None]}
         if self.use_light:
             res["light_mask"] = out["light"][:, None]

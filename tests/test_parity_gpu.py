@@ -196,7 +196,9 @@ def test_forward_eval_end_to_end(cases, name):
     assert psnr > 60.0, psnr
     assert relerr(out["depth_values"], c.ref["depth_values"]) < 5e-3
     out2 = m({k: v.cuda() for k, v in c.inputs.items()}, predict_only=True)
-    assert "normal_map" not in out2 and torch.equal(out2["rgb_values"], out["rgb_values"])   # idempotent / deterministic
+    assert "normal_map" not in out2 and torch.equal(out2["rgb_values"], out["rgb_values"])   # same kernels, deterministic
+    out3 = m({k: v.cuda() for k, v in c.inputs.items()})
+    assert all(torch.equal(out3[k], out[k]) for k in out)                                     # idempotent
 
 
 # ---------------------------------------------------------------------------------------------------
