@@ -313,8 +313,9 @@ static int run_mlp(const i2sdf_handle* h, const MlpParams& p, cudaStream_t st) {
     ProfScope ps(h, sdf_only ? 0 : 1, st);
     if (h->use_tc && sdf_only) return tc_launch_sdf(h, p, st);
     // eval main pass (sdf + grad_x + rgb per sample, nothing saved) -> tensor-core kernel
-    if (h->tcmain && p.out_sdf && p.out_grad && p.out_rgb && p.want_color && !p.want_light && !p.out_feat && !p.save_act && p.scratch &&
-        (p.ray_d || p.pts))
+    // (training: pre-activations + features are saved for the backward instead of the per-CTA scratch)
+    if (h->tcmain && p.out_sdf && p.out_grad && p.out_rgb && p.want_color && !p.want_light && (p.scratch || p.save_act) &&
+        ((p.save_act != nullptr) == (p.out_feat != nullptr)) && (p.ray_d || p.pts))
         return tcmain_launch(h, h->tcmain, p, st);
     return launch_mlp_simt(h, p, st);
 }

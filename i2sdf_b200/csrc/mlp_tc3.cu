@@ -89,6 +89,13 @@ __device__ __forceinline__ float embed_jac(const float (&x)[3], int i, int mx, i
     return ((qq % 6) < 3) ? f * c : -f * s;
 }
 
+// softplus_100'(a) = sigmoid(100 a), from a stored pre-activation
+__device__ __forceinline__ float dsoftplus_fast(float a) {
+    const float e = ex2_approx(-fabsf(a) * 144.26950408889634f);
+    const float rr = rcp_approx(1.0f + e);
+    return (a >= 0.f) ? rr : e * rr;
+}
+
 __device__ __forceinline__ bool round_active(const MlpParams& P) {
     if (P.round_idx <= 0) return true;
     float b0 = fabsf(*P.beta_param) + P.beta_min;
@@ -193,12 +200,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const int nsplit = 256 - net.ex;
         const float RS2 = 0.70710678118654752f;
-        float* sig_base = FULL ? (P.scratch + (size_t)blockIdx.x * (size_t)NL * TM * 256 + (size_t)row * 256) : nullptr;
+        // FULL: softplus'(a_l) per layer round-trips through a per-CTA scratch [l][row][256]; in training (save_act) the
+        // PRE-ACTIVATIONS a_l are written per point [l][m][256] for the backward and softplus' is recomputed from them
+        const bool save = FULL && (P.save_act != nullptr);
         uint32_t dphase = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const long long m = tile * TM + row;
+            const bool valid = m < P.M;
+            float* sig_base = nullptr;
+            size_t sig_lstride = 0;
+            if (FULL) {
+                if (save) { sig_base = P.save_act + (size_t)(valid ? m : 0) * 256; sig_lstride = (size_t)P.M * 256; }
+                else { sig_base = P.scratch + (size_t)blockIdx.x * (size_t)NL * TM * 256 + (size_t)row * 256; sig_lstride = (size_t)TM * 256; }
+            }
             float x[3] = {0.f, 0.f, 0.f}, dv[3] = {0.f, 0.f, 1.f};
-            if (m < P.M) {
+            if (valid) {
                 const long long r = m / P.ns;
                 if (P.ray_d) { dv[0] = P.ray_d[r * 3]; dv[1] = P.ray_d[r * 3 + 1]; dv[2] = P.ray_d[r * 3 + 2]; }
                 if (P.pts) { x[0] = P.pts[m * 3]; x[1] = P.pts[m * 3 + 1]; x[2] = P.pts[m * 3 + 2]; }
@@ -253,10 +269,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                                 hv[j4 * 4 + u] = fmaf(lg2_approx(1.0f + e), 0.0069314718055994531f, fmaxf(a, 0.0f));
                                 if (FULL) {
                                     const float rr = rcp_approx(1.0f + e);
-                                    so[u] = (a >= 0.f) ? rr : e * rr;                               // softplus'(a) = sigmoid(100 a)
+                                    so[u] = save ? a : ((a >= 0.f) ? rr : e * rr);                  // softplus'(a) = sigmoid(100 a)
                                 }
                             }
-                            if (FULL) *reinterpret_cast<float4*>(sig_base + (size_t)l * TM * 256 + col0 + j4 * 4) = make_float4(so[0], so[1], so[2], so[3]);
+                            if (FULL && (!save || valid))
+                                *reinterpret_cast<float4*>(sig_base + (size_t)l * sig_lstride + col0 + j4 * 4) = make_float4(so[0], so[1], so[2], so[3]);
                         }
                         if (kind == EK_SDF_LAST) {
 #pragma unroll
@@ -288,6 +305,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                         if (kind != EK_FEAT) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) hv[j] = fmaxf(hv[j], 0.f);
+                        } else if (P.out_feat && valid) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4)
+                                *reinterpret_cast<float4*>(P.out_feat + (size_t)m * 256 + col0 + j4 * 4) =
+                                    make_float4(hv[j4 * 4], hv[j4 * 4 + 1], hv[j4 * 4 + 2], hv[j4 * 4 + 3]);
                         }
                         if (kind == EK_COL_LAST) {
                             const float* __restrict__ wh = net.col_head + col0;
@@ -302,21 +324,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                                 rgbp[2] = fmaf(hh[0], w2.x, fmaf(hh[1], w2.y, fmaf(hh[2], w2.z, fmaf(hh[3], w2.w, rgbp[2]))));
                             }
                             // reverse prologue: adjoint of a_{NL-1} = w_sdf * softplus'(a_{NL-1})
-                            const float* sg = sig_base + (size_t)(NL - 1) * TM * 256 + col0;
+                            const float* sg = sig_base + (size_t)(NL - 1) * sig_lstride + col0;
 #pragma unroll
                             for (int j4 = 0; j4 < 4; ++j4) {
                                 const float4 w = __ldg(reinterpret_cast<const float4*>(net.sdf_head + col0) + j4);
-                                const float4 s = *reinterpret_cast<const float4*>(sg + j4 * 4);
+                                float4 s = *reinterpret_cast<const float4*>(sg + j4 * 4);
+                                if (save) { s.x = dsoftplus_fast(s.x); s.y = dsoftplus_fast(s.y); s.z = dsoftplus_fast(s.z); s.w = dsoftplus_fast(s.w); }
                                 hv[j4 * 4 + 0] = w.x * s.x; hv[j4 * 4 + 1] = w.y * s.y; hv[j4 * 4 + 2] = w.z * s.z; hv[j4 * 4 + 3] = w.w * s.w;
                             }
                         }
                     } else if (FULL && kind == EK_REV) {
                         // accumulator = adjoint of the input of SDF layer l ; next A = (that) * softplus'(a_{l-1})
-                        const float* sg = sig_base + (size_t)(l - 1) * TM * 256 + col0;
+                        const float* sg = sig_base + (size_t)(l - 1) * sig_lstride + col0;
                         const bool is_skip = (l == net.skip);
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
-                            const float4 s = *reinterpret_cast<const float4*>(sg + j4 * 4);
+                            float4 s = *reinterpret_cast<const float4*>(sg + j4 * 4);
+                            if (save) { s.x = dsoftplus_fast(s.x); s.y = dsoftplus_fast(s.y); s.z = dsoftplus_fast(s.z); s.w = dsoftplus_fast(s.w); }
                             const float sv[4] = {s.x, s.y, s.z, s.w};
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {

@@ -126,19 +126,62 @@ __global__ void sampler_init_kernel(SamplerDev S, SamplerWs W, long long R, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// shared helpers on the per-warp arrays
+// sampler rounds: one CTA (128 threads) per ray.  z / sdf / d* / cdf live in shared memory (<= 640 entries), every
+// thread owns <= 5 contiguous sections in registers; prefix sums are lane-local + warp shuffle + 4 warp totals,
+// accumulated in double and rounded once (torch's CPU cumsum semantics).
 // ------------------------------------------------------------------------------------------------
-struct WarpArrays {
-    float* z;     // [n]
-    float* s;     // [n] sdf
-    float* ds;    // [n-1] d*
-    float* a;     // scratch
-    float* b;     // scratch
+constexpr int kRayThreads = 128;
+constexpr int kPer = 5;                     // ceil(640 / 128)
+
+struct RayArrays {
+    float* z;       // [n]
+    float* s;       // [n] sdf
+    float* ds;      // [n-1] d*
+    float* cdf;     // [n]
+    double* scan;   // [8] warp totals of the two running sums
+    float* red;     // [4] warp maxima
 };
 
+__device__ __forceinline__ RayArrays carve_ray(float* smem) {
+    RayArrays A;
+    A.z = smem; A.s = smem + kZMax; A.ds = smem + 2 * kZMax; A.cdf = smem + 3 * kZMax;
+    A.scan = reinterpret_cast<double*>(smem + 4 * kZMax + 4);   // 8-byte aligned: 4*641+4 = 2568 floats
+    A.red = smem + 4 * kZMax + 4 + 16;
+    return A;
+}
+constexpr size_t kSamplerSmem = (size_t)(4 * kZMax + 4 + 16 + 8) * sizeof(float);
+
+// exclusive prefix (over threads, in thread order) of two per-thread sums
+__device__ __forceinline__ void block_scan2(double& a, double& b, double* sh, int warp, int lane) {
+    double ia = a, ib = b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double ya = __shfl_up_sync(0xffffffffu, ia, o), yb = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o) { ia += ya; ib += yb; }
+    }
+    if (lane == 31) { sh[warp] = ia; sh[4 + warp] = ib; }
+    __syncthreads();
+    double pa = 0.0, pb = 0.0;
+    for (int w = 0; w < warp; ++w) { pa += sh[w]; pb += sh[4 + w]; }
+    a = ia - a + pa;
+    b = ib - b + pb;
+}
+__device__ __forceinline__ float block_max(float v, float* sh, int warp, int lane) {
+    v = warp_max(v);
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    return fmaxf(fmaxf(sh[0], sh[1]), fmaxf(sh[2], sh[3]));
+}
+__device__ __forceinline__ double block_sum(double v, double* sh, int warp, int lane) {
+    v = warp_sumd(v);
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    return (sh[0] + sh[1]) + (sh[2] + sh[3]);
+}
+
 // Theorem-1 bound per section   (ray_sampler.py:98-114)
-__device__ __forceinline__ void compute_dstar(const WarpArrays& A, int n, int lane) {
-    for (int i = lane; i < n - 1; i += 32) {
+__device__ __forceinline__ void compute_dstar(const RayArrays& A, int n) {
+    for (int i = threadIdx.x; i < n - 1; i += kRayThreads) {
         float a = A.z[i + 1] - A.z[i];
         float s0 = A.s[i], s1 = A.s[i + 1];
         float b = fabsf(s0), c = fabsf(s1);
@@ -157,50 +200,56 @@ __device__ __forceinline__ void compute_dstar(const WarpArrays& A, int n, int la
         float sg1 = (s1 > 0.f) ? 1.f : ((s1 < 0.f) ? -1.f : 0.f);
         A.ds[i] = (sg1 * sg0 == 1.f) ? dstar : 0.f * dstar;
     }
-    __syncwarp();
+    __syncthreads();
 }
 
-// get_error_bound (ray_sampler.py:243-251) for one ray; all lanes return the max.
-__device__ float error_bound(const WarpArrays& A, int n, float beta, int lane) {
+// get_error_bound (ray_sampler.py:243-251) for one ray; all threads return the max.
+__device__ float error_bound(const RayArrays& A, int n, float beta) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cnt = n - 1;
-    const int per = (cnt + 31) / 32;
-    const int i0 = lane * per, i1 = min(i0 + per, cnt);
+    const int per = (cnt + kRayThreads - 1) / kRayThreads;
+    const int i0 = threadIdx.x * per, i1 = min(i0 + per, cnt);
     const float alpha = 1.0f / beta;
     const float four_b2 = 4.0f * (beta * beta);
+    float fe[kPer], ee[kPer];
     double sumI = 0.0, sumE = 0.0;
-    for (int i = i0; i < i1; ++i) {
-        float dist = A.z[i + 1] - A.z[i];
-        float fe = dist * laplace_density(A.s[i], beta, alpha);
-        float e = expf(-A.ds[i] / beta) * (dist * dist) / four_b2;
-        A.a[i] = fe;
-        A.b[i] = e;
-        sumI += (double)fe;
-        sumE += (double)e;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+        const int i = i0 + q;
+        fe[q] = 0.f; ee[q] = 0.f;
+        if (i < i1) {
+            float dist = A.z[i + 1] - A.z[i];
+            fe[q] = dist * laplace_density(A.s[i], beta, alpha);
+            ee[q] = expf(-A.ds[i] / beta) * (dist * dist) / four_b2;
+            sumI += (double)fe[q];
+            sumE += (double)ee[q];
+        }
     }
-    double totI, totE;
-    double accI = warp_excl_scan(sumI, lane, &totI);
-    double accE = warp_excl_scan(sumE, lane, &totE);
+    double accI = sumI, accE = sumE;
+    block_scan2(accI, accE, A.scan, warp, lane);
     float best = -FLT_MAX;
-    for (int i = i0; i < i1; ++i) {
-        float I = (float)accI;                       // exclusive: integral_estimation[:, :-1]
-        accE += (double)A.b[i];
-        float E = (float)accE;                       // inclusive
-        float bo = (fminf(expf(E), 1.0e6f) - 1.0f) * expf(-I);
-        best = fmaxf(best, bo);
-        accI += (double)A.a[i];
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+        if (i0 + q < i1) {
+            float I = (float)accI;                       // exclusive: integral_estimation[:, :-1]
+            accE += (double)ee[q];
+            float E = (float)accE;                       // inclusive
+            float bo = (fminf(expf(E), 1.0e6f) - 1.0f) * expf(-I);
+            best = fmaxf(best, bo);
+            accI += (double)fe[q];
+        }
     }
-    __syncwarp();
-    return warp_max(best);
+    return block_max(best, A.red, warp, lane);
 }
 
 // beta line search (ray_sampler.py:118-132)
-__device__ float beta_search(const WarpArrays& A, int n, float beta0, float beta_in, const SamplerDev& S, int lane) {
-    float err = error_bound(A, n, beta0, lane);
+__device__ float beta_search(const RayArrays& A, int n, float beta0, float beta_in, const SamplerDev& S) {
+    float err = error_bound(A, n, beta0);
     float hi = (err <= S.eps) ? beta0 : beta_in;
     float lo = beta0;
     for (int it = 0; it < S.beta_iters; ++it) {
         float mid = (lo + hi) / 2.0f;
-        err = error_bound(A, n, mid, lane);
+        err = error_bound(A, n, mid);
         bool ok = err <= S.eps;
         hi = ok ? mid : hi;
         lo = ok ? lo : mid;
@@ -208,69 +257,73 @@ __device__ float beta_search(const WarpArrays& A, int n, float beta0, float beta
     return hi;
 }
 
-// pdf -> cdf -> inverse CDF (ray_sampler.py:139-207).  Leaves cdf in A.b[0..n-1]; writes ns samples + inds.
-__device__ void resample(const WarpArrays& A, int n, float beta, bool upsample, const SamplerDev& S,
-                         const float* __restrict__ u, int ns, float* __restrict__ out_samples,
-                         int* __restrict__ out_inds, int lane) {
+// pdf -> cdf -> inverse CDF (ray_sampler.py:139-207).  Leaves cdf in A.cdf[0..n-1]; writes ns samples (+ inds).
+__device__ void resample(const RayArrays& A, int n, float beta, bool upsample, const SamplerDev& S, const float* __restrict__ u,
+                         int ns, float* __restrict__ out_samples, int* __restrict__ out_inds) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cnt = n - 1;
-    const int per = (n + 31) / 32;
-    const int i0 = lane * per, i1 = min(i0 + per, n);
+    const int per = (n + kRayThreads - 1) / kRayThreads;          // covers i = 0..n-1 (last: dist = 1e10)
+    const int i0 = threadIdx.x * per, i1 = min(i0 + per, n);
     const float alpha = 1.0f / beta;
     const float four_b2 = 4.0f * (beta * beta);
+    float fe[kPer + 1], ee[kPer + 1];
     double sumF = 0.0, sumE = 0.0;
-    for (int i = i0; i < i1; ++i) {
-        float dist = (i < cnt) ? (A.z[i + 1] - A.z[i]) : 1.0e10f;
-        float fe = dist * laplace_density(A.s[i], beta, alpha);
-        A.a[i] = fe;
-        sumF += (double)fe;
-        if (upsample && i < cnt) {
-            float e = expf(-A.ds[i] / beta) * (dist * dist) / four_b2;
-            A.b[i] = e;
-            sumE += (double)e;
-        }
-    }
-    double totF, totE;
-    double accF = warp_excl_scan(sumF, lane, &totF);
-    double accE = warp_excl_scan(sumE, lane, &totE);
-    double psum = 0.0;
-    for (int i = i0; i < i1; ++i) {
-        float T = expf(-(float)accF);                         // transmittance (exclusive cumsum)
-        float fe = A.a[i];
-        accF += (double)fe;
-        float pdf = 0.f;
-        if (i < cnt) {
-            if (upsample) {
-                accE += (double)A.b[i];
-                pdf = (fminf(expf((float)accE), 1.0e6f) - 1.0f) * T + S.add_tiny;
-            } else {
-                float w = (1.0f - expf(-fe)) * T;
-                pdf = w + 1e-5f;
+#pragma unroll
+    for (int q = 0; q < kPer + 1; ++q) {
+        const int i = i0 + q;
+        fe[q] = 0.f; ee[q] = 0.f;
+        if (i < i1) {
+            float dist = (i < cnt) ? (A.z[i + 1] - A.z[i]) : 1.0e10f;
+            fe[q] = dist * laplace_density(A.s[i], beta, alpha);
+            sumF += (double)fe[q];
+            if (upsample && i < cnt) {
+                ee[q] = expf(-A.ds[i] / beta) * (dist * dist) / four_b2;
+                sumE += (double)ee[q];
             }
-            psum += (double)pdf;
         }
-        A.a[i] = pdf;
     }
-    __syncwarp();
-    const float total = (float)warp_sumd(psum);
-    // cdf = [0, cumsum(pdf / total)]
-    double csum = 0.0;
-    const int perc = (cnt + 31) / 32;
-    const int c0 = lane * perc, c1 = min(c0 + perc, cnt);
-    for (int i = c0; i < c1; ++i) {
-        float pn = A.a[i] / total;
-        A.a[i] = pn;
-        csum += (double)pn;
+    double accF = sumF, accE = sumE;
+    block_scan2(accF, accE, A.scan, warp, lane);
+    float pdf[kPer + 1];
+    double psum = 0.0;
+#pragma unroll
+    for (int q = 0; q < kPer + 1; ++q) {
+        const int i = i0 + q;
+        pdf[q] = 0.f;
+        if (i < i1) {
+            float T = expf(-(float)accF);                         // transmittance (exclusive cumsum)
+            accF += (double)fe[q];
+            if (i < cnt) {
+                if (upsample) {
+                    accE += (double)ee[q];
+                    pdf[q] = (fminf(expf((float)accE), 1.0e6f) - 1.0f) * T + S.add_tiny;
+                } else {
+                    pdf[q] = (1.0f - expf(-fe[q])) * T + 1e-5f;
+                }
+                psum += (double)pdf[q];
+            }
+        }
     }
-    double tot;
-    double acc = warp_excl_scan(csum, lane, &tot);
-    for (int i = c0; i < c1; ++i) {
-        acc += (double)A.a[i];
-        A.b[i + 1] = (float)acc;
+    __syncthreads();                                              // A.scan reuse
+    const float total = (float)block_sum(psum, A.scan, warp, lane);
+    double csum = 0.0, dummy = 0.0;
+#pragma unroll
+    for (int q = 0; q < kPer + 1; ++q) {
+        const int i = i0 + q;
+        if (i < i1 && i < cnt) { pdf[q] = pdf[q] / total; csum += (double)pdf[q]; }
     }
-    if (lane == 0) A.b[0] = 0.f;
-    __syncwarp();
-    const float* cdf = A.b;
-    for (int j = lane; j < ns; j += 32) {
+    __syncthreads();
+    double acc = csum;
+    block_scan2(acc, dummy, A.scan, warp, lane);
+#pragma unroll
+    for (int q = 0; q < kPer + 1; ++q) {
+        const int i = i0 + q;
+        if (i < i1 && i < cnt) { acc += (double)pdf[q]; A.cdf[i + 1] = (float)acc; }
+    }
+    if (threadIdx.x == 0) A.cdf[0] = 0.f;
+    __syncthreads();
+    const float* cdf = A.cdf;
+    for (int j = threadIdx.x; j < ns; j += kRayThreads) {
         float uj = u[j];
         int lo = 0, hi = n;                                    // searchsorted(right=True): first idx with cdf > u
         while (lo < hi) {
@@ -287,20 +340,20 @@ __device__ void resample(const WarpArrays& A, int n, float beta, bool upsample, 
         out_samples[j] = zb + t * (za - zb);
         if (out_inds) out_inds[j] = inds;
     }
-    __syncwarp();
+    __syncthreads();
 }
 
 // stable merge of sorted z[0..n) (first on ties) with sorted smp[0..ns): values + source index (:211-212)
 __device__ void merge_sorted(const float* __restrict__ z, int n, const float* __restrict__ smp, int ns,
-                             float* __restrict__ out_z, int* __restrict__ out_src, int lane) {
-    for (int i = lane; i < n; i += 32) {
+                             float* __restrict__ out_z, int* __restrict__ out_src) {
+    for (int i = threadIdx.x; i < n; i += kRayThreads) {
         float v = z[i];
         int lo = 0, hi = ns;                                   // #samples strictly less than v
         while (lo < hi) { int mid = (lo + hi) >> 1; if (smp[mid] < v) lo = mid + 1; else hi = mid; }
         out_z[i + lo] = v;
         out_src[i + lo] = i;
     }
-    for (int j = lane; j < ns; j += 32) {
+    for (int j = threadIdx.x; j < ns; j += kRayThreads) {
         float v = smp[j];
         int lo = 0, hi = n;                                    // #z less than or equal to v
         while (lo < hi) { int mid = (lo + hi) >> 1; if (z[mid] <= v) lo = mid + 1; else hi = mid; }
@@ -309,32 +362,22 @@ __device__ void merge_sorted(const float* __restrict__ z, int n, const float* __
     }
 }
 
-__device__ __forceinline__ WarpArrays carve(float* smem, int warp) {
-    float* base = smem + (size_t)warp * 5 * kZMax;
-    WarpArrays A;
-    A.z = base; A.s = base + kZMax; A.ds = base + 2 * kZMax; A.a = base + 3 * kZMax; A.b = base + 4 * kZMax;
-    return A;
-}
-constexpr size_t kSamplerSmem = (size_t)kWarpsPerCta * 5 * kZMax * sizeof(float);
-
 // ------------------------------------------------------------------------------------------------
 // round k, phase 1: merge sdf, d*, beta search, batch-global max(beta)
 // ------------------------------------------------------------------------------------------------
-__global__ void sampler_beta_kernel(SamplerDev S, SamplerWs W, long long R, int k, const float* __restrict__ beta_param) {
-    extern __shared__ float smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long r = (long long)blockIdx.x * kWarpsPerCta + warp;
+__global__ void __launch_bounds__(kRayThreads) sampler_beta_kernel(SamplerDev S, SamplerWs W, long long R, int k, const float* __restrict__ beta_param) {
+    extern __shared__ __align__(16) float smem[];
+    const long long r = blockIdx.x;
     const float b0 = beta0_of(beta_param, S.beta_min);
     if (!sampler_round_active(W.beta_max, k, b0)) return;
-    if (r >= R) return;
     const int n = S.n_eval * (k + 1), n_old = S.n_eval * k, cur = k & 1;
-    WarpArrays A = carve(smem, warp);
+    RayArrays A = carve_ray(smem);
     const float* zg = W.z[cur] + r * W.zmax;
     float* sg = W.sdf[cur] + r * W.zmax;
     const float* sold = W.sdf[cur ^ 1] + r * W.zmax;
     const float* snew = W.sdf_new + r * S.n_eval;
     const int* src = W.src + r * W.zmax;
-    for (int i = lane; i < n; i += 32) {
+    for (int i = threadIdx.x; i < n; i += kRayThreads) {
         float v;
         if (k == 0) v = snew[i];
         else { int s = src[i]; v = (s < n_old) ? sold[s] : snew[s - n_old]; }       // :90-93
@@ -342,10 +385,10 @@ __global__ void sampler_beta_kernel(SamplerDev S, SamplerWs W, long long R, int 
         A.s[i] = v;
         sg[i] = v;
     }
-    __syncwarp();
-    compute_dstar(A, n, lane);
-    float beta = beta_search(A, n, b0, W.beta[r], S, lane);
-    if (lane == 0) {
+    __syncthreads();
+    compute_dstar(A, n);
+    float beta = beta_search(A, n, b0, W.beta[r], S);
+    if (threadIdx.x == 0) {
         W.beta[r] = beta;
         atomicMax(reinterpret_cast<int*>(W.beta_max + k), __float_as_int(beta));    // beta > 0
     }
@@ -354,27 +397,27 @@ __global__ void sampler_beta_kernel(SamplerDev S, SamplerWs W, long long R, int 
 // ------------------------------------------------------------------------------------------------
 // round k, phase 2: pdf / inverse-CDF / merge
 // ------------------------------------------------------------------------------------------------
-__global__ void sampler_resample_kernel(SamplerDev S, SamplerWs W, long long R, int k,
-                                        const float* __restrict__ beta_param, const float* __restrict__ u_final_tape) {
-    extern __shared__ float smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long r = (long long)blockIdx.x * kWarpsPerCta + warp;
+__global__ void __launch_bounds__(kRayThreads) sampler_resample_kernel(SamplerDev S, SamplerWs W, long long R, int k,
+                                                                       const float* __restrict__ beta_param, const float* __restrict__ u_final_tape) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ float s_smp[128];
+    const long long r = blockIdx.x;
     const float b0 = beta0_of(beta_param, S.beta_min);
     if (!sampler_round_active(W.beta_max, k, b0)) return;
-    if (r >= R) return;
     const bool upsample = (W.beta_max[k] > b0) && (k + 1 < S.max_iters);            // :151-153
     const int n = S.n_eval * (k + 1), cur = k & 1;
-    WarpArrays A = carve(smem, warp);
+    RayArrays A = carve_ray(smem);
     const float* zg = W.z[cur] + r * W.zmax;
     const float* sg = W.sdf[cur] + r * W.zmax;
-    for (int i = lane; i < n; i += 32) { A.z[i] = zg[i]; A.s[i] = sg[i]; }
-    __syncwarp();
-    if (upsample) compute_dstar(A, n, lane);
+    for (int i = threadIdx.x; i < n; i += kRayThreads) { A.z[i] = zg[i]; A.s[i] = sg[i]; }
+    __syncthreads();
+    if (upsample) compute_dstar(A, n);
     const int ns = upsample ? S.n_eval : S.n_samples;
     const float* u = upsample ? S.u_up : (u_final_tape ? u_final_tape + r * S.n_samples : S.u_final);
+    resample(A, n, W.beta[r], upsample, S, u, ns, s_smp, nullptr);
     float* smp = W.samples + r * S.n_eval;
-    resample(A, n, W.beta[r], upsample, S, u, ns, smp, nullptr, lane);
-    if (upsample) merge_sorted(A.z, n, smp, ns, W.z[cur ^ 1] + r * W.zmax, W.src + r * W.zmax, lane);
+    for (int j = threadIdx.x; j < ns; j += kRayThreads) smp[j] = s_smp[j];
+    if (upsample) merge_sorted(A.z, n, s_smp, ns, W.z[cur ^ 1] + r * W.zmax, W.src + r * W.zmax);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -493,27 +536,27 @@ __global__ void composite_kernel(CompositeArgs C) {
 // ------------------------------------------------------------------------------------------------
 // parity entry: one full round on caller-supplied (z, sdf)
 // ------------------------------------------------------------------------------------------------
-__global__ void sampler_round_debug_kernel(SamplerDev S, const float* __restrict__ z, const float* __restrict__ sdf,
+__global__ void __launch_bounds__(kRayThreads) sampler_round_debug_kernel(SamplerDev S, const float* __restrict__ z, const float* __restrict__ sdf,
                                            long long R, int n, const float* __restrict__ beta_param,
                                            const float* __restrict__ beta_in, int upsample,
                                            const float* __restrict__ u_tape, float* out_beta, float* out_cdf,
                                            int* out_inds, float* out_samples, float* out_zm, int* out_src) {
-    extern __shared__ float smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long r = (long long)blockIdx.x * kWarpsPerCta + warp;
-    if (r >= R) return;
+    extern __shared__ __align__(16) float smem[];
+    __shared__ float s_smp[128];
+    const long long r = blockIdx.x;
     const float b0 = beta0_of(beta_param, S.beta_min);
-    WarpArrays A = carve(smem, warp);
-    for (int i = lane; i < n; i += 32) { A.z[i] = z[r * n + i]; A.s[i] = sdf[r * n + i]; }
-    __syncwarp();
-    compute_dstar(A, n, lane);
-    float beta = beta_search(A, n, b0, beta_in[r], S, lane);
-    if (lane == 0 && out_beta) out_beta[r] = beta;
+    RayArrays A = carve_ray(smem);
+    for (int i = threadIdx.x; i < n; i += kRayThreads) { A.z[i] = z[r * n + i]; A.s[i] = sdf[r * n + i]; }
+    __syncthreads();
+    compute_dstar(A, n);
+    float beta = beta_search(A, n, b0, beta_in[r], S);
+    if (threadIdx.x == 0 && out_beta) out_beta[r] = beta;
     const int ns = upsample ? S.n_eval : S.n_samples;
     const float* u = u_tape ? (u_tape + r * ns) : (upsample ? S.u_up : S.u_final);
-    resample(A, n, beta, upsample != 0, S, u, ns, out_samples + r * ns, out_inds ? out_inds + r * ns : nullptr, lane);
-    if (out_cdf) for (int i = lane; i < n; i += 32) out_cdf[r * n + i] = A.b[i];
-    if (upsample && out_zm) merge_sorted(A.z, n, out_samples + r * ns, ns, out_zm + r * (n + ns), out_src + r * (n + ns), lane);
+    resample(A, n, beta, upsample != 0, S, u, ns, s_smp, out_inds ? out_inds + r * ns : nullptr);
+    for (int j = threadIdx.x; j < ns; j += kRayThreads) out_samples[r * ns + j] = s_smp[j];
+    if (out_cdf) for (int i = threadIdx.x; i < n; i += kRayThreads) out_cdf[r * n + i] = A.cdf[i];
+    if (upsample && out_zm) merge_sorted(A.z, n, s_smp, ns, out_zm + r * (n + ns), out_src + r * (n + ns));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -569,8 +612,9 @@ int launch_sampler_round(const i2sdf_handle* h, const SamplerWs& W, long long R,
                          const float* u_final_tape, cudaStream_t st) {
     int rc = ensure_smem_attrs();
     if (rc) return rc;
-    if (phase == 0) sampler_beta_kernel<<<ray_grid(R), kWarpsPerCta * 32, kSamplerSmem, st>>>(h->smp, W, R, k, beta_param);
-    else sampler_resample_kernel<<<ray_grid(R), kWarpsPerCta * 32, kSamplerSmem, st>>>(h->smp, W, R, k, beta_param, u_final_tape);
+    if (R <= 0) return I2SDF_OK;
+    if (phase == 0) sampler_beta_kernel<<<(int)R, kRayThreads, kSamplerSmem, st>>>(h->smp, W, R, k, beta_param);
+    else sampler_resample_kernel<<<(int)R, kRayThreads, kSamplerSmem, st>>>(h->smp, W, R, k, beta_param, u_final_tape);
     I2SDF_CUDA_CHECK(cudaGetLastError());
     return I2SDF_OK;
 }
@@ -587,7 +631,8 @@ int launch_sampler_round_debug(const i2sdf_handle* h, const float* z, const floa
                                int* out_inds, float* out_samples, float* out_zm, int* out_src, cudaStream_t st) {
     int rc = ensure_smem_attrs();
     if (rc) return rc;
-    sampler_round_debug_kernel<<<ray_grid(R), kWarpsPerCta * 32, kSamplerSmem, st>>>(h->smp, z, sdf, R, n, beta_param, beta_in,
+    if (R <= 0) return I2SDF_OK;
+    sampler_round_debug_kernel<<<(int)R, kRayThreads, kSamplerSmem, st>>>(h->smp, z, sdf, R, n, beta_param, beta_in,
         upsample, u_tape, out_beta, out_cdf, out_inds, out_samples, out_zm, out_src);
     I2SDF_CUDA_CHECK(cudaGetLastError());
     return I2SDF_OK;
