@@ -333,6 +333,10 @@ def gpu_arm(args, rank, world, local_rank):
     achieved = pts_per_launch * FLOP_PER_SDF_EVAL / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
     peak = pk["bf16_tflops_sustained"] if core.uses_tensor_cores else 72.0
     launches = sum(v["launches"] for v in prof.values())
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_tc_sdf_traffic.json")
+    if core.uses_tensor_cores and os.path.exists(tpath) and R == 1024:
+        traffic = json.load(open(tpath))["dram_bytes_per_launch"]      # from the committed ncu --set full capture
     h2d = sum(v.numel() * v.element_size() for v in list(inp_host.values()) + list(gt_host.values()))
     d2h = 4 if train else sum(v.numel() * v.element_size() for v in out_host.values())
     if train:
@@ -362,7 +366,8 @@ def gpu_arm(args, rank, world, local_rank):
         "kernel_launches_per_step": {k: v["launches"] / K for k, v in prof.items()},
         "roofline": {"bound": "tensor", "kernel": "sdf_tc_kernel (sampler SDF evaluations)" if core.uses_tensor_cores else "mlp_tile_kernel",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                     "traffic": None, "flop_per_launch": pts_per_launch * FLOP_PER_SDF_EVAL, "ms_per_launch": per_launch_ms,
+                     "traffic": traffic, "traffic_unit": "bytes of DRAM traffic per launch (ncu --set full, profiles/r01_tc_sdf_traffic.json)",
+                     "flop_per_launch": pts_per_launch * FLOP_PER_SDF_EVAL, "ms_per_launch": per_launch_ms,
                      "peak_source": pk["source"] + (", sustained bf16 (kernel timed inside a step)" if core.uses_tensor_cores else "; fp32 FMA peak 148 SM x 128 FMA x 2 x 1.9 GHz"),
                      "note": "achieved counts ALGORITHMIC flops (1 MAC = 2 flop); the kernel issues 3 bf16 MMAs per MAC, so 1/3 of the bf16 peak is this precision scheme's ceiling"},
         "clocks": clocks,

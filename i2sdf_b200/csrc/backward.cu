@@ -20,6 +20,14 @@
 #include "common.cuh"
 
 namespace i2sdf {
+
+// tensor-core GEMMs (tc_gemm.cu)
+size_t tc_wgrad_ws_floats(const i2sdf_handle* h);
+int tc_gemm_pw(const i2sdf_handle* h, cudaStream_t st, long long M, const float* A, int lda, int kvalid, const TcBlock& blk, float* C, int ldc,
+               int ncols, const float* bias, int relu);
+int tc_gemm_wgrad(const i2sdf_handle* h, cudaStream_t st, long long M, const float* P0, int ldp0, const float* X0, int ldx0, const float* P1,
+                  int ldp1, const float* X1, int ldx1, int n1, int n2, float* dW, int ldw, float* ws);
+
 namespace bwd {
 
 constexpr int LD = 256;
@@ -246,7 +254,7 @@ static inline int blocks(long long n, int t = 256) { return (int)((n + t - 1) / 
 // ================================================================================================
 size_t sdf_backward_ws_floats(const i2sdf_handle* h, long long M) {
     // Adot[L-1] + U,V,P,Q,X0,X1 (each M*256) + E,Ed (M*40 each)
-    return (size_t)(h->net.L - 1 + 6) * M * 256 + (size_t)2 * M * 40 + 64;
+    return (size_t)(h->net.L - 1 + 6) * M * 256 + (size_t)2 * M * 40 + 64 + (h->use_tc ? tc_wgrad_ws_floats(h) : 0);
 }
 
 int sdf_backward(const i2sdf_handle* h, const bwd::PointSrc& src, long long M, const float* const* W, const float* act,
@@ -266,6 +274,8 @@ int sdf_backward(const i2sdf_handle* h, const bwd::PointSrc& src, long long M, c
     float* X1 = X0 + MB;
     float* E = X1 + MB;                     // [M][40]
     float* Ed = E + (size_t)M * 40;
+    float* WGP = Ed + (size_t)M * 40 + 16;  // per-CTA weight-gradient partials (tensor-core path)
+    const bool tc = h->use_tc;
     const bool second = gbar != nullptr;
     auto wo = [&](int l) { return h->lay_out[l]; };     // 256, 217 (feeds skip) or 257 (last)
     auto wi = [&](int l) { return h->lay_in[l]; };      // 39 or 256
@@ -274,11 +284,15 @@ int sdf_backward(const i2sdf_handle* h, const bwd::PointSrc& src, long long M, c
     I2SDF_CUDA_CHECK(cudaGetLastError());
     // ---- tangent forward: Adot_l = Hdot~_l W_l^T
     if (second) {
-        if ((rc = gemm_nt(st, (int)M, wo(0), ex, Ed, 40, W[0], wi(0), Adot, 256))) return rc;
+        if (tc) rc = tc_gemm_pw(h, st, M, Ed, 40, ex, tc_block(h, TCB_FWD_SDF, 0), Adot, 256, 256, nullptr, 0);
+        else rc = gemm_nt(st, (int)M, wo(0), ex, Ed, 40, W[0], wi(0), Adot, 256);
+        if (rc) return rc;
         for (int l = 1; l < L - 1; ++l) {
             layer_input_kernel<<<blocks(MB), 256, 0, st>>>(M, act + (size_t)(l - 1) * MB, Adot + (size_t)(l - 1) * MB, l == n.skip, nsplit, E, Ed, nullptr, X1);
             I2SDF_CUDA_CHECK(cudaGetLastError());
-            if ((rc = gemm_nt(st, (int)M, wo(l), 256, X1, 256, W[l], wi(l), Adot + (size_t)l * MB, 256))) return rc;
+            if (tc) rc = tc_gemm_pw(h, st, M, X1, 256, 256, tc_block(h, TCB_FWD_SDF, l), Adot + (size_t)l * MB, 256, 256, nullptr, 0);
+            else rc = gemm_nt(st, (int)M, wo(l), 256, X1, 256, W[l], wi(l), Adot + (size_t)l * MB, 256);
+            if (rc) return rc;
         }
     }
     // ---- last layer (index L-1): p = [sbar; fbar], q = e_sdf
@@ -294,9 +308,13 @@ int sdf_backward(const i2sdf_handle* h, const bwd::PointSrc& src, long long M, c
         }
         if (second && (rc = colsum(st, M, 256, X1, 256, nullptr, dW[l]))) return rc;             // q = e_sdf: dW[0,:] += sum hdot~
         if (fbar) {
-            if ((rc = gemm_tn_acc(st, 256, 256, M, fbar, ldf, X0, 256, dW[l] + 256, 256, h->num_sms))) return rc;   // rows 1..256
+            if (tc) rc = tc_gemm_wgrad(h, st, M, fbar, ldf, X0, 256, nullptr, 0, nullptr, 0, 256, 256, dW[l] + 256, 256, WGP);
+            else rc = gemm_tn_acc(st, 256, 256, M, fbar, ldf, X0, 256, dW[l] + 256, 256, h->num_sms);              // rows 1..256
+            if (rc) return rc;
             if ((rc = colsum(st, M, 256, fbar, ldf, nullptr, db[l] + 1))) return rc;
-            if ((rc = gemm_nn(st, (int)M, 256, 256, fbar, ldf, W[l] + 256, 256, U, 256))) return rc;               // U = fbar W_feat
+            if (tc) rc = tc_gemm_pw(h, st, M, fbar, ldf, 256, tc_block(h, TCB_REV_FEAT, 0), U, 256, 256, nullptr, 0);
+            else rc = gemm_nn(st, (int)M, 256, 256, fbar, ldf, W[l] + 256, 256, U, 256);                           // U = fbar W_feat
+            if (rc) return rc;
         }
     }
     // ---- hidden layers, top down
@@ -322,12 +340,21 @@ int sdf_backward(const i2sdf_handle* h, const bwd::PointSrc& src, long long M, c
             I2SDF_CUDA_CHECK(cudaGetLastError());
             in0 = X0; in1 = X1; ldin = 256;
         }
-        if ((rc = gemm_tn_acc(st, wo(l), wi(l), M, P, 256, in0, ldin, dW[l], wi(l), h->num_sms))) return rc;
-        if (second && (rc = gemm_tn_acc(st, wo(l), wi(l), M, Q, 256, in1, ldin, dW[l], wi(l), h->num_sms))) return rc;
+        if (tc) {
+            if ((rc = tc_gemm_wgrad(h, st, M, P, 256, in0, ldin, second ? Q : nullptr, 256, second ? in1 : nullptr, ldin, wo(l), wi(l), dW[l], wi(l), WGP))) return rc;
+        } else {
+            if ((rc = gemm_tn_acc(st, wo(l), wi(l), M, P, 256, in0, ldin, dW[l], wi(l), h->num_sms))) return rc;
+            if (second && (rc = gemm_tn_acc(st, wo(l), wi(l), M, Q, 256, in1, ldin, dW[l], wi(l), h->num_sms))) return rc;
+        }
         if ((rc = colsum(st, M, wo(l), P, 256, nullptr, db[l]))) return rc;
         if (l > 0) {
-            if ((rc = gemm_nn(st, (int)M, 256, wo(l), P, 256, W[l], wi(l), U, 256))) return rc;
-            if (second && (rc = gemm_nn(st, (int)M, 256, wo(l), Q, 256, W[l], wi(l), V, 256))) return rc;
+            if (tc) {
+                if ((rc = tc_gemm_pw(h, st, M, P, 256, 256, tc_block(h, TCB_REV_SDF, l), U, 256, 256, nullptr, 0))) return rc;
+                if (second && (rc = tc_gemm_pw(h, st, M, Q, 256, 256, tc_block(h, TCB_REV_SDF, l), V, 256, 256, nullptr, 0))) return rc;
+            } else {
+                if ((rc = gemm_nn(st, (int)M, 256, wo(l), P, 256, W[l], wi(l), U, 256))) return rc;
+                if (second && (rc = gemm_nn(st, (int)M, 256, wo(l), Q, 256, W[l], wi(l), V, 256))) return rc;
+            }
         }
     }
     return I2SDF_OK;
@@ -337,17 +364,21 @@ int sdf_backward(const i2sdf_handle* h, const bwd::PointSrc& src, long long M, c
 // radiance stack backward (recomputes the hidden activations from feat; mlp.py:208-229)
 // ================================================================================================
 namespace bwd {
-// X [M][288] = [PE(dir) (ed) | feat (256) | 0]
-__global__ void color_input_kernel(long long M, int ns, int md, int ed, const float* __restrict__ dirs, const float* __restrict__ feat, float* __restrict__ X) {
+// X [M][288] = [PE(dir) (ed) | feat (256) | 0]   (reference column order), or with feat_first: [feat (256) | PE(dir) | 0]
+// (the column order of the packed tensor-core weight blocks)
+__global__ void color_input_kernel(long long M, int ns, int md, int ed, const float* __restrict__ dirs, const float* __restrict__ feat, float* __restrict__ X,
+                                   int feat_first) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M * 288) return;
     long long m = i / 288; int c = (int)(i % 288);
+    const int pe0 = feat_first ? 256 : 0, f0 = feat_first ? 0 : ed;
     float v = 0.f;
-    if (c < ed) {
+    if (c >= pe0 && c < pe0 + ed) {
+        const int cp = c - pe0;
         const float* d = dirs + (m / ns) * 3;
-        if (c < 3) v = d[c];
-        else { int q = c - 3, k = q / 6, s = (q % 6) / 3, cc = q % 3; float arg = __fmul_rn(d[cc], (float)(1 << k)); v = s ? cosf(arg) : sinf(arg); }
-    } else if (c < ed + 256) v = feat[m * 256 + (c - ed)];
+        if (cp < 3) v = d[cp];
+        else { int q = cp - 3, k = q / 6, s = (q % 6) / 3, cc = q % 3; float arg = __fmul_rn(d[cc], (float)(1 << k)); v = s ? cosf(arg) : sinf(arg); }
+    } else if (c >= f0 && c < f0 + 256) v = feat[m * 256 + (c - f0)];
     X[i] = v;
 }
 __global__ void bias_relu_kernel(long long M, const float* __restrict__ b, float* __restrict__ H) {
@@ -370,7 +401,7 @@ __global__ void sigmoid_adjoint3_kernel(long long M, const float* __restrict__ r
 }  // namespace bwd
 
 size_t color_backward_ws_floats(const i2sdf_handle* h, long long M) {
-    return (size_t)M * 288 * 2 + (size_t)(h->net.Lc - 1) * M * 256 + (size_t)M * 256 + (size_t)M * 4 + 64;
+    return (size_t)M * 288 * 2 + (size_t)(h->net.Lc - 1) * M * 256 + (size_t)M * 256 + (size_t)M * 4 + 64 + (h->use_tc ? tc_wgrad_ws_floats(h) : 0);
 }
 
 // gfeat_out: [M][288] buffer; the feature adjoint is columns ed..ed+255 (ld 288)
@@ -387,14 +418,20 @@ int color_backward(const i2sdf_handle* h, long long M, int ns, const float* dirs
     float* H = GX + (size_t)M * 288;            // [Lc-1][M][256]
     float* G = H + (size_t)(Lc - 1) * MB;       // [M][256] running adjoint
     float* D = G + MB;                          // [M][4]
+    float* WGP = D + (size_t)M * 4 + 16;
+    const bool tc = h->use_tc;
     int rc;
-    color_input_kernel<<<blocks((long long)M * 288), 256, 0, st>>>(M, ns, n.md, ed, dirs, feat, X);
+    color_input_kernel<<<blocks((long long)M * 288), 256, 0, st>>>(M, ns, n.md, ed, dirs, feat, X, tc ? 1 : 0);
     I2SDF_CUDA_CHECK(cudaGetLastError());
     for (int l = 0; l < Lc - 1; ++l) {          // recompute hidden activations
         const float* in = l == 0 ? X : H + (size_t)(l - 1) * MB;
-        if ((rc = gemm_nt(st, (int)M, 256, l == 0 ? kin : 256, in, l == 0 ? 288 : 256, W[l], l == 0 ? kin : 256, H + (size_t)l * MB, 256))) return rc;
-        bias_relu_kernel<<<blocks(MB), 256, 0, st>>>(M, b[l], H + (size_t)l * MB);
-        I2SDF_CUDA_CHECK(cudaGetLastError());
+        if (tc) {
+            if ((rc = tc_gemm_pw(h, st, M, in, l == 0 ? 288 : 256, l == 0 ? 288 : 256, tc_block(h, TCB_FWD_COL, l), H + (size_t)l * MB, 256, 256, b[l], 1))) return rc;
+        } else {
+            if ((rc = gemm_nt(st, (int)M, 256, l == 0 ? kin : 256, in, l == 0 ? 288 : 256, W[l], l == 0 ? kin : 256, H + (size_t)l * MB, 256))) return rc;
+            bias_relu_kernel<<<blocks(MB), 256, 0, st>>>(M, b[l], H + (size_t)l * MB);
+            I2SDF_CUDA_CHECK(cudaGetLastError());
+        }
     }
     sigmoid_adjoint3_kernel<<<blocks(M), 256, 0, st>>>(M, rgb, grgb, D);
     I2SDF_CUDA_CHECK(cudaGetLastError());
@@ -407,14 +444,28 @@ int color_backward(const i2sdf_handle* h, long long M, int ns, const float* dirs
         I2SDF_CUDA_CHECK(cudaGetLastError());
         const float* in = l == 0 ? X : H + (size_t)(l - 1) * MB;
         const int K = l == 0 ? kin : 256, ldin = l == 0 ? 288 : 256;
-        if ((rc = gemm_tn_acc(st, 256, K, M, G, 256, in, ldin, dW[l], K, h->num_sms))) return rc;
+        if (tc) {
+            if (l == 0) {   // X is [feat | PE(dir)]: feature columns -> dW[:, ed:], embedding columns -> dW[:, :ed]
+                if ((rc = tc_gemm_wgrad(h, st, M, G, 256, X, 288, nullptr, 0, nullptr, 0, 256, 256, dW[0] + ed, kin, WGP))) return rc;
+                if ((rc = tc_gemm_wgrad(h, st, M, G, 256, X + 256, 288, nullptr, 0, nullptr, 0, 256, ed, dW[0], kin, WGP))) return rc;
+            } else {
+                if ((rc = tc_gemm_wgrad(h, st, M, G, 256, in, 256, nullptr, 0, nullptr, 0, 256, 256, dW[l], 256, WGP))) return rc;
+            }
+        } else {
+            if ((rc = gemm_tn_acc(st, 256, K, M, G, 256, in, ldin, dW[l], K, h->num_sms))) return rc;
+        }
         if ((rc = colsum(st, M, 256, G, 256, nullptr, db[l]))) return rc;
         if (l > 0) {
-            // adjoint of H_{l-1}: G <- G W_l   (into X's storage as scratch, then swap roles)
-            if ((rc = gemm_nn(st, (int)M, 256, 256, G, 256, W[l], 256, GX, 256))) return rc;
+            // adjoint of H_{l-1}: G <- G W_l
+            if (tc) rc = tc_gemm_pw(h, st, M, G, 256, 256, tc_block(h, TCB_REV_COL, l), GX, 256, 256, nullptr, 0);
+            else rc = gemm_nn(st, (int)M, 256, 256, G, 256, W[l], 256, GX, 256);
+            if (rc) return rc;
             I2SDF_CUDA_CHECK(cudaMemcpyAsync(G, GX, MB * sizeof(float), cudaMemcpyDeviceToDevice, st));
         } else {
-            if ((rc = gemm_nn(st, (int)M, kin, 256, G, 256, W[0], kin, GX, 288))) return rc;
+            // adjoint of the stack input; only the feature columns are consumed downstream -> GX[:, ed:ed+256]
+            if (tc) rc = tc_gemm_pw(h, st, M, G, 256, 256, tc_block(h, TCB_REV_COL, 0), GX + ed, 288, 256, nullptr, 0);
+            else rc = gemm_nn(st, (int)M, kin, 256, G, 256, W[0], kin, GX, 288);
+            if (rc) return rc;
         }
     }
     *gfeat = GX + ed;

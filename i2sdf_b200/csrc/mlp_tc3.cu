@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
 // dst block per k step: [part hi|lo][chunk 0|1][n rows][8 bf16].  Element (n, k):
 //   mode 0 (forward):  W[(n + row_off) * in + col(k)]   col(k) = k, or for the radiance input layer
 //                      k < feat ? ed + k : k - feat  (our A operand is [feat | PE(dir)], the reference's [PE(dir) | feat])
-//   mode 1 (reverse):  W[k * in + n]                     (B = W^T: n = input index, k = output index)
+//   mode 1 (reverse):  W[(k + row_off) * in + n + col_off]   (B = W^T: n = input index, k = output index)
 __global__ void pack_kernel(uint8_t* __restrict__ dst, const float* __restrict__ W, int outd, int in, int ksteps, int n_rows, int mode,
                             int row_off, int feat_first, int ed) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -441,7 +441,8 @@ __global__ void pack_kernel(uint8_t* __restrict__ dst, const float* __restrict__
             if (feat_first > 0) col = (k < feat_first) ? ed + k : ((k - feat_first < ed) ? k - feat_first : -1);
             if (col >= 0 && col < in && n + row_off < outd) w = W[(size_t)(n + row_off) * in + col];
         } else {
-            if (k < outd && n < in) w = W[(size_t)k * in + n];
+            // reverse: feat_first doubles as a column offset (radiance layer 0: only the feature columns are needed)
+            if (k + row_off < outd && n + feat_first < in) w = W[(size_t)(k + row_off) * in + n + feat_first];
         }
         __nv_bfloat16 h = __float2bfloat16_rn(w);
         __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
@@ -461,6 +462,8 @@ struct State {
     int src_layer[MAX_OPS];   // packing recipe per op of the full table
     int mode[MAX_OPS], row_off[MAX_OPS], feat_first[MAX_OPS];
     int n_pack;               // number of ops to pack
+    // weight blocks by role, for the backward GEMMs (tc_gemm.cu): index into full.ops, -1 = absent
+    int blk_fwd_sdf[kMaxLayers], blk_fwd_feat, blk_fwd_col[kMaxLayers], blk_rev_sdf[kMaxLayers], blk_rev_feat, blk_rev_col[kMaxLayers];
 };
 
 }  // namespace tc3
@@ -481,15 +484,23 @@ int tc_create(i2sdf_handle* h) {
         off += (size_t)ksteps * nn * 64;
         ++nops;
     };
-    for (int l = 0; l < NL; ++l) add(l == 0 ? 3 : 16, 256, l == NL - 1 ? EK_SDF_LAST : EK_SDF_HIDDEN, l, l, 0, 0, 0);
-    if (want_full) {
-        add(16, 256, EK_FEAT, L - 1, L - 1, 0, 1, 0);
-        for (int l = 0; l < Lc - 1; ++l) add(l == 0 ? 18 : 16, 256, l == Lc - 2 ? EK_COL_LAST : EK_COL_HIDDEN, l, L + l, 0, 0, l == 0 ? 256 : 0);
-        for (int l = NL - 1; l >= 1; --l) add(16, 256, EK_REV, l, l, 1, 0, 0);
-        add(16, 48, EK_GRAD, 0, 0, 1, 0, 0);
-    }
+    for (int i = 0; i < kMaxLayers; ++i) s->blk_fwd_sdf[i] = s->blk_fwd_col[i] = s->blk_rev_sdf[i] = s->blk_rev_col[i] = -1;
+    s->blk_fwd_feat = s->blk_rev_feat = -1;
+    for (int l = 0; l < NL; ++l) { s->blk_fwd_sdf[l] = nops; add(l == 0 ? 3 : 16, 256, l == NL - 1 ? EK_SDF_LAST : EK_SDF_HIDDEN, l, l, 0, 0, 0); }
+    s->blk_fwd_feat = nops;
+    add(16, 256, EK_FEAT, L - 1, L - 1, 0, 1, 0);
+    for (int l = 0; l < Lc - 1; ++l) { s->blk_fwd_col[l] = nops; add(l == 0 ? 18 : 16, 256, l == Lc - 2 ? EK_COL_LAST : EK_COL_HIDDEN, l, L + l, 0, 0, l == 0 ? 256 : 0); }
+    for (int l = NL - 1; l >= 1; --l) { s->blk_rev_sdf[l] = nops; add(16, 256, EK_REV, l, l, 1, 0, 0); }
+    add(16, 48, EK_GRAD, 0, 0, 1, 0, 0);
+    const int n_kernel_ops = nops;
+    // pack-only blocks used by the training backward
+    s->blk_rev_feat = nops;
+    add(16, 256, -1, L - 1, L - 1, 1, 1, 0);                                   // B[j][i] = W_last[1 + i][j]
+    for (int l = Lc - 2; l >= 1; --l) { s->blk_rev_col[l] = nops; add(16, 256, -1, l, L + l, 1, 0, 0); }
+    s->blk_rev_col[0] = nops;
+    add(16, 256, -1, 0, L, 1, 0, n.ed);                                          // feature columns of radiance layer 0
     s->n_pack = nops;
-    T.nops = want_full ? nops : 0;
+    T.nops = want_full ? n_kernel_ops : 0;
     if (cudaMalloc(&s->wpack, off) != cudaSuccess) { delete s; set_error("tc_create: cudaMalloc failed"); return I2SDF_E_CUDA; }
     T.wpack = s->wpack;
     s->sdf = T;
@@ -529,6 +540,26 @@ int tc_pack(i2sdf_handle* h, const float* const* W, const float* const* b, cudaS
 static inline int tc_grid(const i2sdf_handle* h, long long M) {
     long long ntiles = (M + tc3::TM - 1) / tc3::TM;
     return (int)(ntiles < (long long)h->num_sms ? ntiles : (long long)h->num_sms);
+}
+
+TcBlock tc_block(const i2sdf_handle* h, int role, int layer) {
+    using namespace tc3;
+    TcBlock b{nullptr, 0, 0};
+    const State* s = (const State*)h->tc;
+    if (!s) return b;
+    int idx = -1;
+    switch (role) {
+        case TCB_FWD_SDF: idx = s->blk_fwd_sdf[layer]; break;
+        case TCB_FWD_FEAT: idx = s->blk_fwd_feat; break;
+        case TCB_FWD_COL: idx = s->blk_fwd_col[layer]; break;
+        case TCB_REV_SDF: idx = s->blk_rev_sdf[layer]; break;
+        case TCB_REV_FEAT: idx = s->blk_rev_feat; break;
+        case TCB_REV_COL: idx = s->blk_rev_col[layer]; break;
+    }
+    if (idx < 0) return b;
+    const Op& o = s->full.ops[idx];
+    b.ptr = s->wpack + o.w_off; b.ksteps = o.ksteps; b.n = o.n;
+    return b;
 }
 
 int tc_launch_sdf(const i2sdf_handle* h, const MlpParams& p, cudaStream_t st) {

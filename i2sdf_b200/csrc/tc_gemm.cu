@@ -1,0 +1,411 @@
+// Tensor-core GEMMs for the training backward (tcgen05 / TMEM, sm_100a), fp32 in / fp32 out with the same bf16 hi/lo
+// 3-product scheme as the forward kernels (mlp_tc3.cu).
+//
+//  tc_gemm_pw     C[M, n] = act(A[M, K] . B + bias)     "points x weights": A is an fp32 activation array in global
+//                 memory, staged per 128-row tile into the SMEM A operand (split hi/lo on the fly); B is a PRE-PACKED weight
+//                 block (forward or transposed, see tc_block()) streamed by cp.async.bulk; D in TMEM, two buffers
+//                 ping-ponged across tiles so the store of tile t overlaps the MMAs of tile t+1.
+//  tc_gemm_wgrad  dW[n1, n2] += P[M, n1]^T . X[M, n2]    reduction over the points: both operands are fp32 activation
+//                 arrays; 16 points per k step are transposed into the K-major operand layout by the loader warps
+//                 (coalesced reads along the feature axis), every CTA accumulates its slice of the points in TMEM
+//                 (2 x 128 feature rows x 256 columns) and writes one partial; a small kernel reduces the partials.
+// Both are HBM-bound at these shapes (an [M,256] fp32 array is read or written once per pass), which is what replaces
+// the FMA-pipe SGEMM of backward.cu when the tensor-core path is enabled.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace i2sdf {
+namespace tcg {
+
+using namespace tc;
+
+constexpr int TM = 128;
+constexpr int NSTAGE = 4;
+constexpr int STAGE_MAX = 16384;
+constexpr int A_CHUNKS = 36;
+constexpr int A_PART_BYTES = A_CHUNKS * TM * 16;
+constexpr int N_EPI_WARPS = 16;
+constexpr int NTHREADS = (2 + N_EPI_WARPS) * 32;
+constexpr int N_READY = 9;
+constexpr uint32_t LBO_A = TM * 16, SBO = 128;
+constexpr size_t kSmemPW = 1024 + 2 * (size_t)A_PART_BYTES + NSTAGE * STAGE_MAX + 256;
+
+struct PWArgs {
+    const float* A; int lda; int kvalid;       // A[m][k] valid for k < kvalid (zero beyond)
+    long long M;
+    const uint8_t* B; int ksteps; int n;       // packed weight block: ksteps x (n*64) bytes
+    float* C; int ldc; int ncols;              // write columns < ncols
+    const float* bias;                         // optional [n]
+    int relu;
+};
+
+__device__ __forceinline__ void store_a16(uint8_t* A_hi, uint8_t* A_lo, int row, int kc0, const float (&hv)[16]) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        uint32_t h[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_bf16x2(hv[s * 8 + 2 * i], hv[s * 8 + 2 * i + 1], h[i], lo[i]);
+        const uint32_t off = seg_off<TM>(row, kc0 + s);
+        *reinterpret_cast<uint4*>(A_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(A_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+__device__ __forceinline__ void publish(uint64_t* bar, int lane) {
+    fence_proxy_async();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_pw_kernel(const PWArgs G) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* A_hi = smem;
+    uint8_t* A_lo = smem + A_PART_BYTES;
+    uint8_t* ring = smem + 2 * A_PART_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + NSTAGE * STAGE_MAX);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + NSTAGE;
+    uint64_t* a_ready = bars + 2 * NSTAGE;       // [N_READY], 8 arrivals
+    uint64_t* d_full = a_ready + N_READY;        // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long ntiles = (G.M + TM - 1) / TM;
+    const int nchunks = (G.ksteps + 1) >> 1;     // 32-column A chunks the MMA waits on
+    const uint32_t sb = (uint32_t)G.n * 64u;
+
+    if (tid == 0) {
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < N_READY; ++i) mbar_init(&a_ready[i], 8);
+        mbar_init(&d_full[0], 1);
+        mbar_init(&d_full[1], 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int ks = 0; ks < G.ksteps; ++ks) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full[stage], sb);
+                    bulk_g2s(ring + stage * STAGE_MAX, G.B + (size_t)ks * sb, sb, &full[stage]);
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t a_hi_s = smem_u32(A_hi), a_lo_s = smem_u32(A_lo), ring_s = smem_u32(ring);
+            const uint32_t idesc = instr_desc_bf16(TM, G.n);
+            const uint32_t lbo_b = (uint32_t)G.n * 16u, lo_off = (uint32_t)G.n * 32u;
+            uint32_t stage = 0, phase = 0, aphase = 0, t = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+                const uint32_t d_tmem = tmem_base + (t & 1u) * 256u;
+                for (int ks = 0; ks < G.ksteps; ++ks) {
+                    if ((ks & 1) == 0) {
+                        const int c = ks >> 1;
+                        mbar_wait(&a_ready[c], (aphase >> c) & 1u);
+                        aphase ^= (1u << c);
+                    }
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_off = (uint32_t)ks * 2u * LBO_A;
+                    const uint32_t b_s = ring_s + stage * STAGE_MAX;
+                    const uint64_t da_hi = smem_desc(a_hi_s + a_off, LBO_A, SBO);
+                    const uint64_t da_lo = smem_desc(a_lo_s + a_off, LBO_A, SBO);
+                    const uint64_t db_hi = smem_desc(b_s, lbo_b, SBO);
+                    const uint64_t db_lo = smem_desc(b_s + lo_off, lbo_b, SBO);
+                    mma_bf16_ss(d_tmem, da_hi, db_hi, idesc, ks > 0 ? 1u : 0u);
+                    mma_bf16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
+                    mma_bf16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
+                    mma_commit(&empty[stage]);
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                mma_commit(&d_full[t & 1u]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int sub = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const int kpad = G.ksteps * 16;
+        const bool vec_ok = ((G.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(G.A) & 15) == 0);
+        const bool cvec_ok = ((G.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(G.C) & 15) == 0);
+
+        auto load_tile = [&](long long tile) {
+            const long long m = tile * TM + row;
+            const float* arow = G.A + (size_t)(m < G.M ? m : 0) * G.lda;
+            const int nit = (nchunks + 1) >> 1;
+            for (int it = 0; it < nit; ++it) {
+                const int c = 2 * it + (sub >> 1);
+                if (c >= nchunks) break;
+                const int col0 = c * 32 + (sub & 1) * 16;
+                if (col0 < kpad) {
+                    float hv[16];
+                    if (m < G.M && vec_ok && col0 + 16 <= G.kvalid) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const float4 v = *reinterpret_cast<const float4*>(arow + col0 + j4 * 4);
+                            hv[j4 * 4] = v.x; hv[j4 * 4 + 1] = v.y; hv[j4 * 4 + 2] = v.z; hv[j4 * 4 + 3] = v.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) hv[j] = (m < G.M && col0 + j < G.kvalid) ? arow[col0 + j] : 0.f;
+                    }
+                    store_a16(A_hi, A_lo, row, col0 >> 3, hv);
+                }
+                publish(&a_ready[c], lane);
+            }
+        };
+        auto store_tile = [&](long long tile, uint32_t buf) {
+            const long long m = tile * TM + row;
+            for (int it = 0; it < 8; ++it) {
+                const int col0 = (2 * it + (sub >> 1)) * 32 + (sub & 1) * 16;
+                if (col0 >= G.n) break;
+                uint32_t v[16];
+                tmem_ld16(tmem_base + lane_base + buf * 256u + (uint32_t)col0, v);
+                tmem_ld_wait();
+                if (m < G.M && col0 < G.ncols) {
+                    float o[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float x = __uint_as_float(v[j]);
+                        if (G.bias) x += __ldg(G.bias + col0 + j);
+                        if (G.relu) x = fmaxf(x, 0.f);
+                        o[j] = x;
+                    }
+                    float* crow = G.C + (size_t)m * G.ldc + col0;
+                    if (cvec_ok && col0 + 16 <= G.ncols) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) *reinterpret_cast<float4*>(crow + j4 * 4) = make_float4(o[j4 * 4], o[j4 * 4 + 1], o[j4 * 4 + 2], o[j4 * 4 + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) if (col0 + j < G.ncols) crow[j] = o[j];
+                    }
+                }
+            }
+            tc_fence_before();
+        };
+
+        uint32_t dphase = 0, t = 0;
+        long long tile = blockIdx.x;
+        if (tile < ntiles) load_tile(tile);
+        for (; tile < ntiles; tile += gridDim.x, ++t) {
+            const uint32_t b = t & 1u;
+            mbar_wait(&d_full[b], (dphase >> b) & 1u);      // MMAs of this tile done: A operand free, D[b] complete
+            dphase ^= (1u << b);
+            tc_fence_after();
+            const long long next = tile + gridDim.x;
+            if (next < ntiles) load_tile(next);             // next tile's MMAs (into D[b^1]) overlap this tile's store
+            store_tile(tile, b);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// =================================================================================================
+// weight gradient:  partial[cta][n1pad][256] = sum over the CTA's points of  P[m][i] * X[m][j]
+// =================================================================================================
+constexpr int WG_STAGES = 4;
+constexpr int WG_STAGE_BYTES = 32768;     // A_hi 8K | A_lo 8K | B_hi 8K | B_lo 8K   (256 rows x 2 k-chunks x 16 B each)
+constexpr size_t kSmemWG = 1024 + (size_t)WG_STAGES * WG_STAGE_BYTES + 256;
+
+struct WGArgs {
+    const float* P0; int ldp0; const float* X0; int ldx0;     // first source pair
+    const float* P1; int ldp1; const float* X1; int ldx1;     // optional second pair (null = none), same shapes
+    int n1, n2;                                               // valid feature counts (<= 256 each)
+    long long M;
+    float* partial;                                           // [grid][256][256]
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_wgrad_kernel(const WGArgs G) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* ring = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + WG_STAGES * WG_STAGE_BYTES);
+    uint64_t* full = bars;                   // [WG_STAGES] 16 arrivals (loader warps)
+    uint64_t* empty = bars + WG_STAGES;      // [WG_STAGES] 1 arrival (tcgen05.commit)
+    uint64_t* d_full = empty + WG_STAGES;    // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // this CTA's slice of the points, in units of 16
+    const long long nk16 = (G.M + 15) / 16;
+    const long long per = (nk16 + gridDim.x - 1) / gridDim.x;
+    const long long k_lo = (long long)blockIdx.x * per, k_hi = (k_lo + per < nk16) ? k_lo + per : nk16;
+    const int npairs = G.P1 ? 2 : 1;
+    const long long nsteps = (k_hi > k_lo ? (k_hi - k_lo) : 0) * npairs;
+    const int n2pad = (G.n2 + 15) & ~15;
+    const int mt_count = G.n1 > 128 ? 2 : 1;
+
+    if (tid == 0) {
+        for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full[i], N_EPI_WARPS); mbar_init(&empty[i], 1); }
+        mbar_init(d_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t ring_s = smem_u32(ring);
+            const uint32_t idesc = instr_desc_bf16(TM, n2pad);
+            const uint32_t lbo = 256u * 16u;
+            uint32_t stage = 0, phase = 0;
+            for (long long st = 0; st < nsteps; ++st) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t base = ring_s + stage * WG_STAGE_BYTES;
+                const uint64_t db_hi = smem_desc(base + 16384, lbo, SBO);
+                const uint64_t db_lo = smem_desc(base + 24576, lbo, SBO);
+                for (int mt = 0; mt < mt_count; ++mt) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)mt * 256u;
+                    const uint64_t da_hi = smem_desc(base + (uint32_t)mt * 2048u, lbo, SBO);
+                    const uint64_t da_lo = smem_desc(base + 8192 + (uint32_t)mt * 2048u, lbo, SBO);
+                    mma_bf16_ss(d_tmem, da_hi, db_hi, idesc, st > 0 ? 1u : 0u);
+                    mma_bf16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
+                    mma_bf16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
+                }
+                mma_commit(&empty[stage]);
+                if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+            }
+            mma_commit(d_full);
+        }
+    } else if (warp >= 2) {
+        // ---- loaders: thread e = (kc, r): feature row r (0..255), k chunk kc (8 points) of the A (P) and B (X) operands
+        const int e = tid - 64;                  // 0..511
+        const int kc = e >> 8, r = e & 255;
+        uint32_t stage = 0, phase = 0;
+        for (long long st = 0; st < nsteps; ++st) {
+            const int pair = (npairs == 2) ? (int)(st & 1) : 0;
+            const long long k16 = k_lo + (npairs == 2 ? (st >> 1) : st);
+            const float* Pp = pair ? G.P1 : G.P0;
+            const float* Xp = pair ? G.X1 : G.X0;
+            const int ldp = pair ? G.ldp1 : G.ldp0, ldx = pair ? G.ldx1 : G.ldx0;
+            const long long p0 = k16 * 16 + kc * 8;
+            float a[8], b[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const long long p = p0 + i;
+                const bool ok = p < G.M;
+                a[i] = (ok && r < G.n1) ? __ldg(Pp + (size_t)p * ldp + r) : 0.f;
+                b[i] = (ok && r < G.n2) ? __ldg(Xp + (size_t)p * ldx + r) : 0.f;
+            }
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* base = ring + stage * WG_STAGE_BYTES;
+            const uint32_t off = (uint32_t)kc * 4096u + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+            uint32_t h[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_bf16x2(a[2 * i], a[2 * i + 1], h[i], lo[i]);
+            *reinterpret_cast<uint4*>(base + off) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(base + 8192 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_bf16x2(b[2 * i], b[2 * i + 1], h[i], lo[i]);
+            *reinterpret_cast<uint4*>(base + 16384 + off) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(base + 24576 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[stage]);
+            if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+        }
+        // ---- epilogue: TMEM -> partial
+        mbar_wait(d_full, 0);
+        tc_fence_after();
+        const int q = warp & 3, sub = (warp - 2) >> 2;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        float* part = G.partial + (size_t)blockIdx.x * 256 * 256;
+        for (int mt = 0; mt < mt_count; ++mt) {
+            const int i = mt * 128 + q * 32 + lane;            // output row (feature of P)
+            for (int it = 0; it < 4; ++it) {
+                const int col0 = (sub * 4 + it) * 16;
+                if (col0 >= n2pad) break;
+                uint32_t v[16];
+                tmem_ld16(tmem_base + lane_base + (uint32_t)mt * 256u + (uint32_t)col0, v);
+                tmem_ld_wait();
+                float* dst = part + (size_t)i * 256 + col0;
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4)
+                    *reinterpret_cast<float4*>(dst + j4 * 4) = make_float4(nsteps > 0 ? __uint_as_float(v[j4 * 4]) : 0.f, nsteps > 0 ? __uint_as_float(v[j4 * 4 + 1]) : 0.f,
+                                                                           nsteps > 0 ? __uint_as_float(v[j4 * 4 + 2]) : 0.f, nsteps > 0 ? __uint_as_float(v[j4 * 4 + 3]) : 0.f);
+            }
+        }
+        tc_fence_before();
+    }
+    if (warp == 0 || nsteps == 0) { /* idle */ }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// dW[i][j] += sum_c partial[c][i][j]
+__global__ void reduce_partials_kernel(float* __restrict__ dW, int ldw, int n1, int n2, const float* __restrict__ partial, int nparts) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n1 * n2) return;
+    int i = idx / n2, j = idx % n2;
+    float s = 0.f;
+    for (int c = 0; c < nparts; ++c) s += partial[((size_t)c * 256 + i) * 256 + j];
+    dW[(size_t)i * ldw + j] += s;
+}
+
+}  // namespace tcg
+
+size_t tc_wgrad_ws_floats(const i2sdf_handle* h) { return (size_t)h->num_sms * 256 * 256; }
+
+int tc_gemm_pw(const i2sdf_handle* h, cudaStream_t st, long long M, const float* A, int lda, int kvalid, const TcBlock& blk, float* C, int ldc,
+               int ncols, const float* bias, int relu) {
+    using namespace tcg;
+    static bool attr = false;
+    if (!attr) {
+        I2SDF_CUDA_CHECK(cudaFuncSetAttribute(gemm_pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPW));
+        I2SDF_CUDA_CHECK(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemWG));
+        attr = true;
+    }
+    if (M <= 0) return I2SDF_OK;
+    if (!blk.ptr || blk.ksteps * 16 > A_CHUNKS * 8 || blk.n > 256) { set_error("tc_gemm_pw: bad weight block"); return I2SDF_E_INVALID; }
+    PWArgs G;
+    G.A = A; G.lda = lda; G.kvalid = kvalid; G.M = M; G.B = blk.ptr; G.ksteps = blk.ksteps; G.n = blk.n; G.C = C; G.ldc = ldc; G.ncols = ncols;
+    G.bias = bias; G.relu = relu;
+    long long ntiles = (M + TM - 1) / TM;
+    int grid = (int)(ntiles < (long long)h->num_sms ? ntiles : (long long)h->num_sms);
+    gemm_pw_kernel<<<grid, NTHREADS, kSmemPW, st>>>(G);
+    I2SDF_CUDA_CHECK(cudaGetLastError());
+    return I2SDF_OK;
+}
+
+// dW[n1][ldw] (+=) P0^T X0 (+ P1^T X1).  ws: tc_wgrad_ws_floats(h) floats.
+int tc_gemm_wgrad(const i2sdf_handle* h, cudaStream_t st, long long M, const float* P0, int ldp0, const float* X0, int ldx0, const float* P1,
+                  int ldp1, const float* X1, int ldx1, int n1, int n2, float* dW, int ldw, float* ws) {
+    using namespace tcg;
+    static bool attr = false;
+    if (!attr) {
+        I2SDF_CUDA_CHECK(cudaFuncSetAttribute(gemm_pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPW));
+        I2SDF_CUDA_CHECK(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemWG));
+        attr = true;
+    }
+    if (M <= 0) return I2SDF_OK;
+    if (n1 > 256 || n2 > 256 || n1 < 1 || n2 < 1) { set_error("tc_gemm_wgrad: n1/n2 out of range"); return I2SDF_E_INVALID; }
+    WGArgs G;
+    G.P0 = P0; G.ldp0 = ldp0; G.X0 = X0; G.ldx0 = ldx0; G.P1 = P1; G.ldp1 = ldp1; G.X1 = X1; G.ldx1 = ldx1; G.n1 = n1; G.n2 = n2; G.M = M; G.partial = ws;
+    long long nk16 = (M + 15) / 16;
+    int grid = (int)(nk16 < (long long)h->num_sms ? nk16 : (long long)h->num_sms);
+    gemm_wgrad_kernel<<<grid, NTHREADS, kSmemWG, st>>>(G);
+    I2SDF_CUDA_CHECK(cudaGetLastError());
+    reduce_partials_kernel<<<(n1 * n2 + 255) / 256, 256, 0, st>>>(dW, ldw, n1, n2, ws, grid);
+    I2SDF_CUDA_CHECK(cudaGetLastError());
+    return I2SDF_OK;
+}
+
+}  // namespace i2sdf
