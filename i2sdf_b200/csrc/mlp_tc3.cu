@@ -160,13 +160,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
         // ================= MMA issuer =================
         if (lane == 0) {
             const uint32_t a_hi_s = smem_u32(A_hi), a_lo_s = smem_u32(A_lo), ring_s = smem_u32(ring);
-            uint32_t stage = 0, phase = 0, aphase = 0;
+            uint32_t stage = 0, phase = 0, aphase = 0, g = 0;      // g: global op counter -> TMEM buffer g & 1
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int op = 0; op < T.nops; ++op) {
+                for (int op = 0; op < T.nops; ++op, ++g) {
                     const int n = T.ops[op].n;
                     const uint32_t idesc = instr_desc_bf16(TM, n);
                     const uint32_t lbo_b = (uint32_t)n * 16u, lo_off = (uint32_t)n * 32u;
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(op & 1) * 256u;
+                    const uint32_t d_tmem = tmem_base + (g & 1u) * 256u;
                     const int nks = T.ops[op].ksteps;
                     for (int ks = 0; ks < nks; ++ks) {
                         if ((ks & 1) == 0) {
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                         mma_commit(&empty[stage]);
                         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                     }
-                    mma_commit(&d_full[op & 1]);
+                    mma_commit(&d_full[g & 1u]);
                 }
             }
         }
@@ -203,18 +203,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
         // FULL: softplus'(a_l) per layer round-trips through a per-CTA scratch [l][row][256]; in training (save_act) the
         // PRE-ACTIVATIONS a_l are written per point [l][m][256] for the backward and softplus' is recomputed from them
         const bool save = FULL && (P.save_act != nullptr);
-        uint32_t dphase = 0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        uint32_t dphase = 0, g = 0;
+        // point (and view direction) of this thread's row in a tile
+        auto load_point = [&](long long tile, float (&x)[3], float (&dv)[3]) {
             const long long m = tile * TM + row;
-            const bool valid = m < P.M;
-            float* sig_base = nullptr;
-            size_t sig_lstride = 0;
-            if (FULL) {
-                if (save) { sig_base = P.save_act + (size_t)(valid ? m : 0) * 256; sig_lstride = (size_t)P.M * 256; }
-                else { sig_base = P.scratch + (size_t)blockIdx.x * (size_t)NL * TM * 256 + (size_t)row * 256; sig_lstride = (size_t)TM * 256; }
-            }
-            float x[3] = {0.f, 0.f, 0.f}, dv[3] = {0.f, 0.f, 1.f};
-            if (valid) {
+            x[0] = x[1] = x[2] = 0.f; dv[0] = 0.f; dv[1] = 0.f; dv[2] = 1.f;
+            if (m < P.M) {
                 const long long r = m / P.ns;
                 if (P.ray_d) { dv[0] = P.ray_d[r * 3]; dv[1] = P.ray_d[r * 3 + 1]; dv[2] = P.ray_d[r * 3 + 2]; }
                 if (P.pts) { x[0] = P.pts[m * 3]; x[1] = P.pts[m * 3 + 1]; x[2] = P.pts[m * 3 + 2]; }
@@ -225,34 +219,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                     for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(P.ray_o[r * 3 + c], __fmul_rn(t, dv[c]));
                 }
             }
-            // ---- prologue: A_0 = embedding, 48 columns: sub s writes columns 16 s .. 16 s + 15 (sub 3: nothing)
-            {
-                if (sub < 3) {
-                    float hv[16];
+        };
+        // prologue: A_0 = embedding, 48 columns: sub s writes columns 16 s .. 16 s + 15 (sub 3: nothing)
+        auto prologue = [&](const float (&x)[3]) {
+            if (sub < 3) {
+                float hv[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int i = sub * 16 + j;
-                        hv[j] = (i < net.ex) ? embed_col(x, i, net.mx) : 0.f;
-                    }
-                    store_a16(A_hi, A_lo, row, sub * 2, hv);
+                for (int j = 0; j < 16; ++j) {
+                    const int i = sub * 16 + j;
+                    hv[j] = (i < net.ex) ? embed_col(x, i, net.mx) : 0.f;
                 }
-                publish_chunk(&a_ready[sub >> 1], lane);
+                store_a16(A_hi, A_lo, row, sub * 2, hv);
+            }
+            publish_chunk(&a_ready[sub >> 1], lane);
+        };
+        float x[3], dv[3];
+        if ((long long)blockIdx.x < ntiles) { load_point(blockIdx.x, x, dv); prologue(x); }
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const long long m = tile * TM + row;
+            const bool valid = m < P.M;
+            const long long next_tile = tile + gridDim.x;
+            float xn[3] = {0.f, 0.f, 0.f}, dvn[3] = {0.f, 0.f, 1.f};
+            float* sig_base = nullptr;
+            size_t sig_lstride = 0;
+            if (FULL) {
+                if (save) { sig_base = P.save_act + (size_t)(valid ? m : 0) * 256; sig_lstride = (size_t)P.M * 256; }
+                else { sig_base = P.scratch + (size_t)blockIdx.x * (size_t)NL * TM * 256 + (size_t)row * 256; sig_lstride = (size_t)TM * 256; }
             }
 
             float head = 0.f, rgbp[3] = {0.f, 0.f, 0.f}, gacc[3] = {0.f, 0.f, 0.f};
-            for (int op = 0; op < T.nops; ++op) {
-                const int b = op & 1;
+            for (int op = 0; op < T.nops; ++op, ++g) {
+                const uint32_t b = g & 1u;
                 const int kind = T.ops[op].kind, l = T.ops[op].layer;
                 mbar_wait(&d_full[b], (dphase >> b) & 1u);
                 dphase ^= (1u << b);
                 tc_fence_after();
+                if (op == T.nops - 1 && next_tile < ntiles) {
+                    // the A operand is free (this tile's last MMAs are done): start the NEXT tile's first layer now, so its
+                    // tensor work overlaps this tile's last epilogue
+                    load_point(next_tile, xn, dvn);
+                    prologue(xn);
+                }
 #pragma unroll 1
                 for (int it = 0; it < 4; ++it) {
                     const int c = 2 * it + (sub >> 1);                 // 32-column chunk
                     const int col0 = c * 32 + (sub & 1) * 16;          // first of this warp's 16 columns
                     if (FULL && kind == EK_GRAD && col0 >= 48) break;
                     uint32_t v[16];
-                    tmem_ld16(tmem_base + lane_base + (uint32_t)b * 256u + (uint32_t)col0, v);
+                    tmem_ld16(tmem_base + lane_base + b * 256u + (uint32_t)col0, v);
                     tmem_ld_wait();
                     float hv[16];
                     if (kind == EK_SDF_HIDDEN || kind == EK_SDF_LAST) {
@@ -414,6 +428,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                 }
             }
             epi_bar_sync();     // part[] free for the next tile
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { x[c] = xn[c]; dv[c] = dvn[c]; }
         }
     }
     tc_fence_before();
