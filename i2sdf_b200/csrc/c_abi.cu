@@ -51,6 +51,7 @@ int tcmain_create(i2sdf_handle* h, void** out_state);
 void tcmain_destroy(void* state);
 int tcmain_pack(i2sdf_handle* h, void* state, const float* const* W, cudaStream_t st);
 int tcmain_launch(const i2sdf_handle* h, void* state, const MlpParams& p, cudaStream_t st);
+int tcmain_has_full(const void* state);
 
 // ---- packing ------------------------------------------------------------------------------------
 enum { PACK_T = 0, PACK_R = 1, PACK_V = 2 };
@@ -229,7 +230,7 @@ int i2sdf_destroy(i2sdf_handle* h) {
 }
 
 int i2sdf_num_layers(const i2sdf_handle* h) { return h ? h->n_layers : 0; }
-int i2sdf_uses_tensor_cores(const i2sdf_handle* h) { return h ? ((h->use_tc ? 1 : 0) | (h->tcmain ? 2 : 0)) : 0; }
+int i2sdf_uses_tensor_cores(const i2sdf_handle* h) { return h ? ((h->use_tc ? 1 : 0) | ((h->tcmain && tcmain_has_full(h->tcmain)) ? 2 : 0)) : 0; }
 
 int i2sdf_pack_weights(i2sdf_handle* h, const float* const* W, const float* const* b, void* stream) {
     if (!h || !W || !b) { set_error("null argument"); return I2SDF_E_INVALID; }
@@ -314,8 +315,11 @@ static int run_mlp(const i2sdf_handle* h, const MlpParams& p, cudaStream_t st) {
     if (h->use_tc && sdf_only) return tc_launch_sdf(h, p, st);
     // eval main pass (sdf + grad_x + rgb per sample, nothing saved) -> tensor-core kernel
     // (training: pre-activations + features are saved for the backward instead of the per-CTA scratch)
-    if (h->tcmain && p.out_sdf && p.out_grad && p.out_rgb && p.want_color && !p.want_light && (p.scratch || p.save_act) &&
-        ((p.save_act != nullptr) == (p.out_feat != nullptr)) && (p.ray_d || p.pts))
+    if (h->tcmain && tcmain_has_full(h->tcmain) && p.out_sdf && p.out_grad && p.out_rgb && p.want_color && !p.want_light &&
+        (p.scratch || p.save_act) && ((p.save_act != nullptr) == (p.out_feat != nullptr)) && (p.ray_d || p.pts))
+        return tcmain_launch(h, h->tcmain, p, st);
+    // sdf + grad_x only (eikonal points / ImplicitNetwork.gradient): F layers then the reverse sweep, no radiance stack
+    if (h->tcmain && p.out_sdf && p.out_grad && !p.want_color && !p.want_light && !p.out_feat && (p.scratch || p.save_act) && (p.ray_d || p.pts))
         return tcmain_launch(h, h->tcmain, p, st);
     return launch_mlp_simt(h, p, st);
 }

@@ -41,7 +41,7 @@ constexpr uint32_t LBO_A = TM * 16, SBO = 128;
 constexpr int PART_FLOATS = 4 * 7 * TM;              // [sub][sdf, rgb x3, grad x3][row]
 constexpr size_t kSmemBytes = 1024 + 2 * (size_t)A_PART_BYTES + NSTAGE * STAGE_MAX + PART_FLOATS * 4 + 256;
 
-enum { EK_SDF_HIDDEN = 0, EK_SDF_LAST, EK_FEAT, EK_COL_HIDDEN, EK_COL_LAST, EK_REV, EK_GRAD };
+enum { EK_SDF_HIDDEN = 0, EK_SDF_LAST, EK_FEAT, EK_COL_HIDDEN, EK_COL_LAST, EK_REV, EK_GRAD, EK_SDF_LAST_REV };
 
 struct Op {
     int w_off;          // byte offset into wpack
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                     tmem_ld16(tmem_base + lane_base + b * 256u + (uint32_t)col0, v);
                     tmem_ld_wait();
                     float hv[16];
-                    if (kind == EK_SDF_HIDDEN || kind == EK_SDF_LAST) {
+                    if (kind == EK_SDF_HIDDEN || kind == EK_SDF_LAST || kind == EK_SDF_LAST_REV) {
                         const float* __restrict__ bias = net.sdf_b[l] + col0;
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
@@ -283,7 +283,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                                 hv[j4 * 4 + u] = fmaf(lg2_approx(1.0f + e), 0.0069314718055994531f, fmaxf(a, 0.0f));
                                 if (FULL) {
                                     const float rr = rcp_approx(1.0f + e);
-                                    so[u] = save ? a : ((a >= 0.f) ? rr : e * rr);                  // softplus'(a) = sigmoid(100 a)
+                                    const float sgm = (a >= 0.f) ? rr : e * rr;                     // softplus'(a) = sigmoid(100 a)
+                                    so[u] = save ? a : sgm;
+                                    if (kind == EK_SDF_LAST_REV) {                                  // sdf + grad only: head, then straight
+                                        head = fmaf(hv[j4 * 4 + u], __ldg(net.sdf_head + col0 + j4 * 4 + u), head);   // into the reverse sweep
+                                        hv[j4 * 4 + u] = __ldg(net.sdf_head + col0 + j4 * 4 + u) * sgm;
+                                    }
                                 }
                             }
                             if (FULL && (!save || valid))
@@ -421,8 +426,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                 if (FULL) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        const float s = acc[1 + c] + __ldg(net.col_head + 768 + c);
-                        P.out_rgb[m * 3 + c] = __fdiv_rn(1.0f, 1.0f + expf(-s));
+                        if (P.out_rgb) {
+                            const float s = acc[1 + c] + __ldg(net.col_head + 768 + c);
+                            P.out_rgb[m * 3 + c] = __fdiv_rn(1.0f, 1.0f + expf(-s));
+                        }
                         P.out_grad[m * 3 + c] = acc[4 + c];
                     }
                 }
@@ -475,6 +482,7 @@ struct State {
     uint8_t* wpack;
     OpTable sdf;              // ops of the sdf-only chain (a prefix of the full table)
     OpTable full;             // nops == 0 if the full main pass is unavailable for this network
+    OpTable sg;               // SDF + grad_x only (eikonal points): F_0..F_{NL-1}, R_{NL-1}..R_0
     int src_layer[MAX_OPS];   // packing recipe per op of the full table
     int mode[MAX_OPS], row_off[MAX_OPS], feat_first[MAX_OPS];
     int n_pack;               // number of ops to pack
@@ -521,11 +529,16 @@ int tc_create(i2sdf_handle* h) {
     T.wpack = s->wpack;
     s->sdf = T;
     s->sdf.nops = NL;
+    s->sg.wpack = s->wpack;
+    s->sg.nops = 0;
+    for (int l = 0; l < NL; ++l) { s->sg.ops[s->sg.nops] = T.ops[s->blk_fwd_sdf[l]]; if (l == NL - 1) s->sg.ops[s->sg.nops].kind = EK_SDF_LAST_REV; ++s->sg.nops; }
+    for (int l = NL - 1; l >= 1; --l) s->sg.ops[s->sg.nops++] = T.ops[s->blk_rev_sdf[l]];
+    s->sg.ops[s->sg.nops++] = T.ops[n_kernel_ops - 1];          // R_0 (EK_GRAD)
     cudaError_t e = cudaFuncSetAttribute(tc_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) { cudaFree(s->wpack); delete s; set_error("tc_create: smem attribute: %s", cudaGetErrorString(e)); return I2SDF_E_CUDA; }
     h->tc = s;
-    h->tcmain = want_full ? (void*)s : nullptr;
+    h->tcmain = (void*)s;     // full main pass only if s->full.nops > 0 (tcmain_has_full)
     return I2SDF_OK;
 }
 
@@ -591,11 +604,12 @@ int tc_launch_sdf(const i2sdf_handle* h, const MlpParams& p, cudaStream_t st) {
 int tcmain_create(i2sdf_handle*, void** out_state) { *out_state = nullptr; return I2SDF_OK; }
 void tcmain_destroy(void*) {}
 int tcmain_pack(i2sdf_handle*, void*, const float* const*, cudaStream_t) { return I2SDF_OK; }
+int tcmain_has_full(const void* state) { return state && ((const tc3::State*)state)->full.nops > 0; }
 int tcmain_launch(const i2sdf_handle* h, void* state, const MlpParams& p, cudaStream_t st) {
     using namespace tc3;
     if (p.M <= 0) return I2SDF_OK;
     const State* s = (const State*)state;
-    tc_mlp_kernel<true><<<tc_grid(h, p.M), NTHREADS, kSmemBytes, st>>>(p, s->full);
+    tc_mlp_kernel<true><<<tc_grid(h, p.M), NTHREADS, kSmemBytes, st>>>(p, p.want_color ? s->full : s->sg);
     I2SDF_CUDA_CHECK(cudaGetLastError());
     return I2SDF_OK;
 }

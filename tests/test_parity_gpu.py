@@ -49,8 +49,8 @@ def test_sdf_forward_matches_oracle(cases, name):
     assert out.shape == (1000, 257)
     assert relerr(out[:, 0], ref[:, 0]) < 1e-5
     assert relerr(out[:, 1:], ref[:, 1:]) < 1e-5
-    g2 = m.implicit_network.gradient(pts.cuda())
-    assert relerr(g2, gref) < 2e-5
+    g2 = m.implicit_network.gradient(pts.cuda())              # sdf + grad_x: tensor-core chain F.., R.. when enabled
+    assert relerr(g2, gref) < (2 * TOL if m._core_obj.uses_tensor_cores else 2e-5), relerr(g2, gref)
     s2 = m.implicit_network.get_sdf_vals(pts.cuda())        # sdf-only evaluations run on the tcgen05 kernel
     assert s2.shape == (1000, 1) and relerr(s2[:, 0], ref[:, 0]) < (TOL if m._core_obj.uses_tensor_cores else 1e-5)
 
@@ -193,6 +193,7 @@ def test_forward_eval_end_to_end(cases, name):
     # end to end the sampler's z may differ in a few bins (see above) -> compare as images: PSNR(new, reference)
     mse = ((out["rgb_values"].cpu() - c.ref["rgb_values"]) ** 2).mean()
     psnr = -10.0 * torch.log10(mse.clamp(min=1e-20))
+    print(f"{name}: PSNR(new render, reference render) = {psnr:.1f} dB; rgb rel err {relerr(out['rgb_values'], c.ref['rgb_values']):.2e}")
     assert psnr > 60.0, psnr
     assert relerr(out["depth_values"], c.ref["depth_values"]) < 5e-3
     out2 = m({k: v.cuda() for k, v in c.inputs.items()}, predict_only=True)
