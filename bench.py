@@ -1,15 +1,18 @@
 #!/usr/bin/env python
 """bench.py — ray-samples/s through the fused SDF+render path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rays R]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode train|render] [--rays R]
 
-A step = one pass of the hot path (I2SDFNetwork.forward: rays -> error-bounded sampler (5 x 128 sdf-evals/ray) ->
-SDF + grad_x + radiance on the 97 composited samples/ray -> alpha compositing) over one 1024-ray batch of synthetic
-rays with the config/synthetic.yml networks (W-sharp weights, density.beta = 0.01 so all five
-sampler rounds run).  value = full-path ray-samples/s = rays * 97 / step time, whole job (all ranks).
+Default workload = BASELINE.json configs[1]: one TRAINING step on a 1024-ray batch with the config/synthetic.yml networks
+and loss: forward (rays -> error-bounded sampler, 5 x 128 sdf-evals/ray -> SDF + grad_x + radiance on the 97 composited
+samples/ray -> compositing -> 3R eikonal points) + I2SDFLoss + backward incl. the second-order terms + Adam(eps=1e-15)
++ weight re-pack.  Synthetic rays / targets: W-sharp weights (geometric init seed 0, density.beta =
+0.01 so all five sampler rounds run).  value = full-path ray-samples/s = rays * 97 / step time, whole job (all ranks).
+`--mode render` times the eval forward render of the same batch instead (also reported as `render` in train mode).
 
-N > 1 (torchrun, one rank per GPU): rays shard across ranks, every rank renders its own 1024-ray batch (weak
-scaling), inference has no collective; time = max over ranks of the device time of the K steps.
+N > 1 (torchrun, one rank per GPU): rays shard across ranks, every rank processes its own 1024-ray batch (weak
+scaling); training all-reduces the flat 3.2 MB gradient once per step over NCCL, inference has no collective;
+time = max over ranks of the device time of the K steps.
 
 --impl reference: the reference's CPU implementation of the same path.  The reference is Python/PyTorch and cannot
 travel to the GPU box, so this arm times the oracle port (oracle/i2sdf_oracle.py, pinned bit-for-bit against the
@@ -43,9 +46,10 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=1024)
     ap.add_argument("--cpu-rays", type=int, default=128, help="rays per step of the CPU arms (bounded sample)")
-    ap.add_argument("--mode", default="render", choices=["render", "train"],
-                    help="render: eval forward of a 1024-ray batch (default); train: full training step "
-                         "(forward + I2SDFLoss + backward incl. second order + gradient all-reduce + Adam + weight re-pack)")
+    ap.add_argument("--mode", default="train", choices=["render", "train"],
+                    help="train (default, BASELINE.json configs[1]): full training step on a 1024-ray batch (forward + I2SDFLoss + "
+                         "backward incl. second order + gradient all-reduce + Adam + weight re-pack); "
+                         "render: eval forward render of a 1024-ray batch (configs[2] batch shape)")
     return ap.parse_args()
 
 
@@ -315,10 +319,19 @@ def gpu_arm(args, rank, world, local_rank):
     ms_res, prof = timed(step_resident, args.steps, profile=True)
     ms_e2e, _ = timed(step_e2e, args.steps)
     clocks = clk.stop()
-    t = torch.tensor([ms_res, ms_e2e], dtype=torch.float64, device=dev)
+    ms_render = 0.0
+    if train:       # also report the forward-render throughput of the same networks (inference: no collective)
+        model_gpu.eval()
+        inp_eval = {k: v.to(dev) for k, v in orc.synthetic_rays(R, seed=1 + rank).items()}
+        with torch.no_grad():
+            for _ in range(3):
+                model_gpu(inp_eval)
+            ms_render, _ = timed(lambda: model_gpu(inp_eval), args.steps)
+        model_gpu.train(True)
+    t = torch.tensor([ms_res, ms_e2e, ms_render], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_res, ms_e2e = float(t[0]), float(t[1])
+    ms_res, ms_e2e, ms_render = float(t[0]), float(t[1]), float(t[2])
     if rank != 0:
         return None
     K = args.steps
@@ -372,6 +385,9 @@ def gpu_arm(args, rank, world, local_rank):
                      "note": "achieved counts ALGORITHMIC flops (1 MAC = 2 flop); the kernel issues 3 bf16 MMAs per MAC, so 1/3 of the bf16 peak is this precision scheme's ceiling"},
         "clocks": clocks,
     }
+    if train and ms_render > 0:
+        line["render"] = {"value": world * R * N_COMPOSITED * K / (ms_render * 1e-3), "unit": UNIT, "ms_per_step": ms_render / K,
+                          "workload": "eval forward render of the same 1024-ray batch (no backward, no collective), device-resident inputs"}
     model_c = type("S", (), {"state_dict": lambda self: cpu_snapshot})()
     if train:
         cb = cpu_train_arm(conf, model_c, max(args.cpu_rays // 4, 16), steps=1, warmup=1)
