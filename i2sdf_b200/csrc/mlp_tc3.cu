@@ -254,6 +254,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                 mbar_wait(&d_full[b], (dphase >> b) & 1u);
                 dphase ^= (1u << b);
                 tc_fence_after();
+                if (FULL && op + 1 < T.nops) {
+                    // the NEXT op's epilogue may read softplus' rows written ~10 ops ago (they can have left L2: 148 CTAs x
+                    // 1 MB): pull this thread's four 64-byte segments back into L2 one op ahead of their use
+                    const int nk = T.ops[op + 1].kind, nl = T.ops[op + 1].layer;
+                    const int src_l = (nk == EK_REV) ? nl - 1 : ((nk == EK_COL_LAST) ? NL - 1 : -1);
+                    if (src_l >= 0) {
+                        const float* pb = sig_base + (size_t)src_l * sig_lstride + (sub >> 1) * 32 + (sub & 1) * 16;
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + it * 64));
+                    }
+                }
                 if (op == T.nops - 1 && next_tile < ntiles) {
                     // the A operand is free (this tile's last MMAs are done): start the NEXT tile's first layer now, so its
                     // tensor work overlaps this tile's last epilogue
