@@ -246,6 +246,7 @@ def gpu_arm(args, rank, world, local_rank):
     cpu_snapshot = {k: v.detach().clone() for k, v in model.state_dict().items()} if rank == 0 else None
     model_gpu = model.to(dev)
     model_gpu.train(train)
+    init_state = {k: v.detach().clone() for k, v in model_gpu.state_dict().items()}
     R = args.rays
     # rank-specific rays: the global batch is world * R rays sharded across ranks
     inp_host = {k: v.pin_memory() for k, v in orc.synthetic_rays(R, seed=1 + rank, train_layout=train).items()}
@@ -257,7 +258,8 @@ def gpu_arm(args, rank, world, local_rank):
     out_host = {}
     if train:
         loss_fn = I2SDFLoss(**configs.LOSS_SYNTHETIC)
-        opt = torch.optim.Adam(model_gpu.parameters(), lr=5.0e-4, eps=1e-15)      # model/trainer/recon.py:201-207
+        # Adam(lr, eps=1e-15) as model/trainer/recon.py:201-207; fused=True is the same update as one multi-tensor kernel
+        opt = torch.optim.Adam(model_gpu.parameters(), lr=5.0e-4, eps=1e-15, fused=True)
         loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
 
     def train_step(inp, gt):
@@ -321,6 +323,7 @@ def gpu_arm(args, rank, world, local_rank):
     clocks = clk.stop()
     ms_render = 0.0
     if train:       # also report the forward-render throughput of the same networks (inference: no collective)
+        model_gpu.load_state_dict(init_state)          # back to the W-sharp weights (Adam steps changed beta / the surface)
         model_gpu.eval()
         inp_eval = {k: v.to(dev) for k, v in orc.synthetic_rays(R, seed=1 + rank).items()}
         with torch.no_grad():

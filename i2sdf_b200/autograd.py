@@ -14,6 +14,24 @@ import torch.nn.functional as F
 from torch.autograd import Function
 
 
+def _zeros_like_all(groups):
+    """Zero-initialised gradient buffers for several lists of tensors, carved from ONE flat allocation (one fill kernel)."""
+    flat_n = sum(t.numel() for g in groups for t in g)
+    if flat_n == 0:
+        return [[] for _ in groups]
+    ref = next(t for g in groups for t in g)
+    flat = torch.zeros(flat_n + 4 * sum(len(g) for g in groups), dtype=ref.dtype, device=ref.device)
+    out, off = [], 0
+    for g in groups:
+        cur = []
+        for t in g:
+            n = t.numel()
+            cur.append(flat[off:off + n].view(t.shape))
+            off += (n + 3) // 4 * 4                      # keep every buffer 16-byte aligned
+        out.append(cur)
+    return out
+
+
 def _split_params(params, n_sdf, n_col, n_light):
     i = 0
     out = []
@@ -51,8 +69,7 @@ class _PointsFn(Function):
         W_sdf, b_sdf, W_col, b_col, W_l, b_l = _split_params(saved[7:], n_sdf, n_col, n_light)
         R, N = z.shape[0], z.shape[1] - 1
         M = R * N
-        zeros = lambda ts: [torch.zeros_like(t) for t in ts]      # noqa: E731
-        dW_sdf, db_sdf, dW_col, db_col, dW_l, db_l = zeros(W_sdf), zeros(b_sdf), zeros(W_col), zeros(b_col), zeros(W_l), zeros(b_l)
+        dW_sdf, db_sdf, dW_col, db_col, dW_l, db_l = _zeros_like_all([W_sdf, b_sdf, W_col, b_col, W_l, b_l])
         g_feat_ptr, ld = None, 256
         if g_rgb is not None:
             g_x = core.color_backward(W_col, b_col, d, N, feat, s_rgb, g_rgb, dW_col, db_col)
@@ -117,7 +134,7 @@ class _SdfPointsFn(Function):
         saved = ctx.saved_tensors
         pts, act = saved[:2]
         W, b = list(saved[2:2 + n_sdf]), list(saved[2 + n_sdf:2 + 2 * n_sdf])
-        dW, db = [torch.zeros_like(t) for t in W], [torch.zeros_like(t) for t in b]
+        dW, db = _zeros_like_all([W, b])
         if g_sdf is not None or (want_grad and g_grad is not None):
             ctx.core.sdf_backward(W, pts.shape[0], act, dW, db, pts=pts, g_sdf=g_sdf, g_grad=g_grad if want_grad else None)
         return (None,) * 4 + tuple(dW + db)

@@ -182,6 +182,25 @@ def test_render_on_reference_z(cases, name):
         assert relerr(out["light"], c.ref["light_mask"][:, 0]) < TOL
 
 
+def test_uniform_sampler_config_c1(cases):
+    """BASELINE config 1: 64 uniform samples on [0, far] (UniformSampler(3.0, 0.0, 64), ray_sampler.py:22-31) ->
+    63 composited samples/ray through the same main pass + compositing; ragged ray counts included."""
+    c = cases["eval_synthetic_soft"]
+    m = _model(c)
+    core = m._ready_core()
+    for R in (1, 37, 1024):
+        inp = orc.synthetic_rays(R, seed=11)
+        z = (torch.linspace(0.0, 1.0, 64)[None].repeat(R, 1) * c.spec.far).contiguous()
+        with torch.no_grad():
+            ref = orc.render(c.spec, c.params, inp, training=False, z_override=z)
+        o, d, dn = core.rays(inp["uv"].cuda(), inp["pose"].cuda(), inp["intrinsics"].cuda())
+        out = core.render(o, d, dn, z.cuda(), m.density.beta.detach(), want_normal=True)
+        assert out["rgb"].shape == (R, 3)
+        assert relerr(out["rgb"], ref["rgb_values"]) < TOL
+        assert relerr(out["depth"], ref["depth_values"]) < TOL
+        assert relerr(out["weight_sum"], ref["weight_sum"][:, 0]) < TOL
+
+
 @pytest.mark.parametrize("name", EVAL_CASES)
 def test_forward_eval_end_to_end(cases, name):
     c = cases[name]
