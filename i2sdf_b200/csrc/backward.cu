@@ -17,6 +17,7 @@
 // All dense contractions go through one generic tiled SGEMM (NT / NN / TN split-K with atomics); activations are
 // [M][256] fp32 arrays in the caller's workspace.  (The forward kernels are fused; this backward is the first
 // correct version and is deliberately un-fused — DESIGN.md lists fusing it onto tcgen05 as the next step.)
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace i2sdf {
@@ -27,6 +28,11 @@ int tc_gemm_pw(const i2sdf_handle* h, cudaStream_t st, long long M, const float*
                int ncols, const float* bias, int relu);
 int tc_gemm_wgrad(const i2sdf_handle* h, cudaStream_t st, long long M, const float* P0, int ldp0, const float* X0, int ldx0, const float* P1,
                   int ldp1, const float* X1, int ldx1, int n1, int n2, float* dW, int ldw, float* ws);
+int tc_gemm_pw_ex(const i2sdf_handle* h, cudaStream_t st, long long M, const float* A, int lda, int kvalid, const TcBlock& blk, float* C, int ldc,
+                  int ncols, const float* bias, int relu, const float* A2, int lda2, int is_skip, int nsplit, const float* E2);
+int tc_gemm_wgrad_ex(const i2sdf_handle* h, cudaStream_t st, long long M, const float* P0, int ldp0, const float* X0, int ldx0, const float* P1,
+                     int ldp1, const float* X1, int ldx1, int n1, int n2, float* dW, int ldw, float* ws, const float* Aprev, const float* Adprev,
+                     int is_skip, int nsplit, const float* E0, const float* E1);
 
 namespace bwd {
 
@@ -276,6 +282,7 @@ int sdf_backward(const i2sdf_handle* h, const bwd::PointSrc& src, long long M, c
     float* Ed = E + (size_t)M * 40;
     float* WGP = Ed + (size_t)M * 40 + 16;  // per-CTA weight-gradient partials (tensor-core path)
     const bool tc = h->use_tc;
+    static const bool fuse = !(getenv("I2SDF_BWD_FUSE") && getenv("I2SDF_BWD_FUSE")[0] == '0');
     const bool second = gbar != nullptr;
     auto wo = [&](int l) { return h->lay_out[l]; };     // 256, 217 (feeds skip) or 257 (last)
     auto wi = [&](int l) { return h->lay_in[l]; };      // 39 or 256
@@ -288,6 +295,12 @@ int sdf_backward(const i2sdf_handle* h, const bwd::PointSrc& src, long long M, c
         else rc = gemm_nt(st, (int)M, wo(0), ex, Ed, 40, W[0], wi(0), Adot, 256);
         if (rc) return rc;
         for (int l = 1; l < L - 1; ++l) {
+            if (tc && fuse) {     // hdot~_l = softplus'(a_{l-1}) * adot_{l-1} (+ skip) is formed while staging the A operand
+                rc = tc_gemm_pw_ex(h, st, M, act + (size_t)(l - 1) * MB, 256, 256, tc_block(h, TCB_FWD_SDF, l), Adot + (size_t)l * MB, 256, 256, nullptr, 0,
+                                   Adot + (size_t)(l - 1) * MB, 256, l == n.skip, nsplit, Ed);
+                if (rc) return rc;
+                continue;
+            }
             layer_input_kernel<<<blocks(MB), 256, 0, st>>>(M, act + (size_t)(l - 1) * MB, Adot + (size_t)(l - 1) * MB, l == n.skip, nsplit, E, Ed, nullptr, X1);
             I2SDF_CUDA_CHECK(cudaGetLastError());
             if (tc) rc = tc_gemm_pw(h, st, M, X1, 256, 256, tc_block(h, TCB_FWD_SDF, l), Adot + (size_t)l * MB, 256, 256, nullptr, 0);
@@ -333,14 +346,20 @@ int sdf_backward(const i2sdf_handle* h, const bwd::PointSrc& src, long long M, c
         I2SDF_CUDA_CHECK(cudaGetLastError());
         // inputs of layer l
         const float* in0; const float* in1; int ldin;
+        const bool fused_in = tc && fuse && l > 0;       // layer inputs are recomputed inside the weight-gradient loaders
         if (l == 0) { in0 = E; in1 = Ed; ldin = 40; }
         else {
-            layer_input_kernel<<<blocks(MB), 256, 0, st>>>(M, act + (size_t)(l - 1) * MB, second ? Adot + (size_t)(l - 1) * MB : nullptr, l == n.skip, nsplit,
-                                                            E, Ed, X0, second ? X1 : nullptr);
-            I2SDF_CUDA_CHECK(cudaGetLastError());
+            if (!fused_in) {
+                layer_input_kernel<<<blocks(MB), 256, 0, st>>>(M, act + (size_t)(l - 1) * MB, second ? Adot + (size_t)(l - 1) * MB : nullptr, l == n.skip, nsplit,
+                                                                E, Ed, X0, second ? X1 : nullptr);
+                I2SDF_CUDA_CHECK(cudaGetLastError());
+            }
             in0 = X0; in1 = X1; ldin = 256;
         }
-        if (tc) {
+        if (fused_in) {
+            if ((rc = tc_gemm_wgrad_ex(h, st, M, P, 256, nullptr, 256, second ? Q : nullptr, 256, nullptr, 256, wo(l), wi(l), dW[l], wi(l), WGP,
+                                       act + (size_t)(l - 1) * MB, second ? Adot + (size_t)(l - 1) * MB : nullptr, l == n.skip, nsplit, E, Ed))) return rc;
+        } else if (tc) {
             if ((rc = tc_gemm_wgrad(h, st, M, P, 256, in0, ldin, second ? Q : nullptr, 256, second ? in1 : nullptr, ldin, wo(l), wi(l), dW[l], wi(l), WGP))) return rc;
         } else {
             if ((rc = gemm_tn_acc(st, wo(l), wi(l), M, P, 256, in0, ldin, dW[l], wi(l), h->num_sms))) return rc;

@@ -276,15 +276,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                     const int c = 2 * it + (sub >> 1);                 // 32-column chunk
                     const int col0 = c * 32 + (sub & 1) * 16;          // first of this warp's 16 columns
                     if (FULL && kind == EK_GRAD && col0 >= 48) break;
+                    // global operands of this item (bias, or the softplus' row of the reverse sweep) are requested BEFORE the
+                    // TMEM load so their latency overlaps it (the tcgen05.wait::ld below is a compiler barrier)
+                    float4 pre[4];
+                    {
+                        const float* psrc;
+                        if (kind == EK_SDF_HIDDEN || kind == EK_SDF_LAST || kind == EK_SDF_LAST_REV) psrc = net.sdf_b[l] + col0;
+                        else if (FULL && kind == EK_FEAT) psrc = net.sdf_b[net.L - 1] + col0;
+                        else if (FULL && kind == EK_COL_HIDDEN) psrc = net.col_b[l] + col0;
+                        else if (FULL && kind == EK_COL_LAST) psrc = sig_base + (size_t)(NL - 1) * sig_lstride + col0;
+                        else if (FULL && kind == EK_REV) psrc = sig_base + (size_t)(l - 1) * sig_lstride + col0;
+                        else psrc = net.sdf_head;
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) pre[j4] = *reinterpret_cast<const float4*>(psrc + j4 * 4);
+                    }
                     uint32_t v[16];
                     tmem_ld16(tmem_base + lane_base + b * 256u + (uint32_t)col0, v);
                     tmem_ld_wait();
                     float hv[16];
                     if (kind == EK_SDF_HIDDEN || kind == EK_SDF_LAST || kind == EK_SDF_LAST_REV) {
-                        const float* __restrict__ bias = net.sdf_b[l] + col0;
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
-                            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + j4);
+                            const float4 bb = pre[j4];
                             const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
                             float so[4];
 #pragma unroll
@@ -326,7 +339,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                         const float* __restrict__ bias = (kind == EK_FEAT ? net.sdf_b[net.L - 1] : net.col_b[l]) + col0;
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
-                            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + j4);
+                            const float4 bb = (kind == EK_COL_LAST) ? __ldg(reinterpret_cast<const float4*>(bias) + j4) : pre[j4];
                             hv[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + bb.x;
                             hv[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + bb.y;
                             hv[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + bb.z;
@@ -354,22 +367,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                                 rgbp[2] = fmaf(hh[0], w2.x, fmaf(hh[1], w2.y, fmaf(hh[2], w2.z, fmaf(hh[3], w2.w, rgbp[2]))));
                             }
                             // reverse prologue: adjoint of a_{NL-1} = w_sdf * softplus'(a_{NL-1})
-                            const float* sg = sig_base + (size_t)(NL - 1) * sig_lstride + col0;
 #pragma unroll
                             for (int j4 = 0; j4 < 4; ++j4) {
                                 const float4 w = __ldg(reinterpret_cast<const float4*>(net.sdf_head + col0) + j4);
-                                float4 s = *reinterpret_cast<const float4*>(sg + j4 * 4);
+                                float4 s = pre[j4];
                                 if (save) { s.x = dsoftplus_fast(s.x); s.y = dsoftplus_fast(s.y); s.z = dsoftplus_fast(s.z); s.w = dsoftplus_fast(s.w); }
                                 hv[j4 * 4 + 0] = w.x * s.x; hv[j4 * 4 + 1] = w.y * s.y; hv[j4 * 4 + 2] = w.z * s.z; hv[j4 * 4 + 3] = w.w * s.w;
                             }
                         }
                     } else if (FULL && kind == EK_REV) {
                         // accumulator = adjoint of the input of SDF layer l ; next A = (that) * softplus'(a_{l-1})
-                        const float* sg = sig_base + (size_t)(l - 1) * sig_lstride + col0;
                         const bool is_skip = (l == net.skip);
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
-                            float4 s = *reinterpret_cast<const float4*>(sg + j4 * 4);
+                            float4 s = pre[j4];
                             if (save) { s.x = dsoftplus_fast(s.x); s.y = dsoftplus_fast(s.y); s.z = dsoftplus_fast(s.z); s.w = dsoftplus_fast(s.w); }
                             const float sv[4] = {s.x, s.y, s.z, s.w};
 #pragma unroll

@@ -37,7 +37,21 @@ struct PWArgs {
     float* C; int ldc; int ncols;              // write columns < ncols
     const float* bias;                         // optional [n]
     int relu;
+    // optional fused input transform (tangent forward):  A'[m][k] = softplus'(A[m][k]) * A2[m][k]
+    //   (+ skip concat: k >= nsplit -> E2[m][k - nsplit]; everything / sqrt2)
+    const float* A2; int lda2; int is_skip; int nsplit; const float* E2;
 };
+
+// fast softplus_100 and its derivative (same approximations as the forward tensor-core kernels)
+__device__ __forceinline__ float sp_fast(float a) {
+    const float e = ex2_approx(-fabsf(a) * 144.26950408889634f);
+    return fmaf(lg2_approx(1.0f + e), 0.0069314718055994531f, fmaxf(a, 0.0f));
+}
+__device__ __forceinline__ float dsp_fast(float a) {
+    const float e = ex2_approx(-fabsf(a) * 144.26950408889634f);
+    const float rr = rcp_approx(1.0f + e);
+    return (a >= 0.f) ? rr : e * rr;
+}
 
 __device__ __forceinline__ void store_a16(uint8_t* A_hi, uint8_t* A_lo, int row, int kc0, const float (&hv)[16]) {
 #pragma unroll
@@ -140,29 +154,61 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_pw_kernel(const PWArgs G) {
         const bool vec_ok = ((G.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(G.A) & 15) == 0);
         const bool cvec_ok = ((G.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(G.C) & 15) == 0);
 
+        // one 16-column item of this thread's row, fp32 from global (zero beyond kvalid / M)
+        auto fetch_item = [&](const float* arow, bool rowok, int col0, float (&hv)[16]) {
+            if (rowok && vec_ok && col0 + 16 <= G.kvalid) {
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 v = *reinterpret_cast<const float4*>(arow + col0 + j4 * 4);
+                    hv[j4 * 4] = v.x; hv[j4 * 4 + 1] = v.y; hv[j4 * 4 + 2] = v.z; hv[j4 * 4 + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) hv[j] = (rowok && col0 + j < G.kvalid) ? arow[col0 + j] : 0.f;
+            }
+            if (G.A2) {          // fused: softplus'(a) * adot  (+ skip concat)
+                const long long mrow = (arow - G.A) / G.lda;
+                const float* a2 = G.A2 + (size_t)mrow * G.lda2 + col0;
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 t = rowok ? *reinterpret_cast<const float4*>(a2 + j4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    hv[j4 * 4] = dsp_fast(hv[j4 * 4]) * t.x; hv[j4 * 4 + 1] = dsp_fast(hv[j4 * 4 + 1]) * t.y;
+                    hv[j4 * 4 + 2] = dsp_fast(hv[j4 * 4 + 2]) * t.z; hv[j4 * 4 + 3] = dsp_fast(hv[j4 * 4 + 3]) * t.w;
+                }
+                if (G.is_skip) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int k = col0 + j;
+                        if (k >= G.nsplit) hv[j] = rowok ? G.E2[(size_t)mrow * 40 + (k - G.nsplit)] : 0.f;
+                        hv[j] *= 0.70710678118654752f;
+                    }
+                }
+            }
+        };
+        // stage a 128-row tile of A into the SMEM operand; the global loads run one item ahead of the convert/store
         auto load_tile = [&](long long tile) {
             const long long m = tile * TM + row;
-            const float* arow = G.A + (size_t)(m < G.M ? m : 0) * G.lda;
+            const bool rowok = m < G.M;
+            const float* arow = G.A + (size_t)(rowok ? m : 0) * G.lda;
             const int nit = (nchunks + 1) >> 1;
+            float cur[16], nxt[16];
+            {
+                const int c0 = (sub >> 1), col00 = c0 * 32 + (sub & 1) * 16;
+                if (c0 < nchunks && col00 < kpad) fetch_item(arow, rowok, col00, cur);
+            }
             for (int it = 0; it < nit; ++it) {
                 const int c = 2 * it + (sub >> 1);
                 if (c >= nchunks) break;
                 const int col0 = c * 32 + (sub & 1) * 16;
-                if (col0 < kpad) {
-                    float hv[16];
-                    if (m < G.M && vec_ok && col0 + 16 <= G.kvalid) {
-#pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            const float4 v = *reinterpret_cast<const float4*>(arow + col0 + j4 * 4);
-                            hv[j4 * 4] = v.x; hv[j4 * 4 + 1] = v.y; hv[j4 * 4 + 2] = v.z; hv[j4 * 4 + 3] = v.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) hv[j] = (m < G.M && col0 + j < G.kvalid) ? arow[col0 + j] : 0.f;
-                    }
-                    store_a16(A_hi, A_lo, row, col0 >> 3, hv);
-                }
+                const int cn = c + 2, coln = cn * 32 + (sub & 1) * 16;
+                const bool have_next = (it + 1 < nit) && (cn < nchunks) && (coln < kpad);
+                if (have_next) fetch_item(arow, rowok, coln, nxt);
+                if (col0 < kpad) store_a16(A_hi, A_lo, row, col0 >> 3, cur);
                 publish(&a_ready[c], lane);
+                if (have_next) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
+                }
             }
         };
         auto store_tile = [&](long long tile, uint32_t buf) {
@@ -226,6 +272,9 @@ struct WGArgs {
     int n1, n2;                                               // valid feature counts (<= 256 each)
     long long M;
     float* partial;                                           // [grid][256][256]
+    // optional fused X transform: X0 := softplus(Aprev) and X1 := softplus'(Aprev) * Adprev  (ld 256), with the skip concat
+    // (columns >= nsplit come from E0 / E1 [M][40]; everything / sqrt2).  When Aprev is set X0 / X1 pointers are ignored.
+    const float* Aprev; const float* Adprev; int is_skip; int nsplit; const float* E0; const float* E1;
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_wgrad_kernel(const WGArgs G) {
@@ -302,7 +351,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_wgrad_kernel(const WGArgs G)
                 const long long p = p0 + i;
                 const bool ok = p < G.M;
                 a[i] = (ok && r < G.n1) ? __ldg(Pp + (size_t)p * ldp + r) : 0.f;
-                b[i] = (ok && r < G.n2) ? __ldg(Xp + (size_t)p * ldx + r) : 0.f;
+                if (!G.Aprev) {
+                    b[i] = (ok && r < G.n2) ? __ldg(Xp + (size_t)p * ldx + r) : 0.f;
+                } else if (!(ok && r < G.n2)) {
+                    b[i] = 0.f;
+                } else if (G.is_skip && r >= G.nsplit) {
+                    b[i] = __ldg((pair ? G.E1 : G.E0) + (size_t)p * 40 + (r - G.nsplit)) * 0.70710678118654752f;
+                } else {
+                    const float av = __ldg(G.Aprev + (size_t)p * 256 + r);
+                    float x = pair ? dsp_fast(av) * __ldg(G.Adprev + (size_t)p * 256 + r) : sp_fast(av);
+                    b[i] = G.is_skip ? x * 0.70710678118654752f : x;
+                }
             }
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* base = ring + stage * WG_STAGE_BYTES;
@@ -364,8 +423,14 @@ __global__ void reduce_partials_kernel(float* __restrict__ dW, int ldw, int n1, 
 
 size_t tc_wgrad_ws_floats(const i2sdf_handle* h) { return (size_t)h->num_sms * 256 * 256; }
 
+int tc_gemm_pw_ex(const i2sdf_handle* h, cudaStream_t st, long long M, const float* A, int lda, int kvalid, const TcBlock& blk, float* C, int ldc,
+                  int ncols, const float* bias, int relu, const float* A2, int lda2, int is_skip, int nsplit, const float* E2);
 int tc_gemm_pw(const i2sdf_handle* h, cudaStream_t st, long long M, const float* A, int lda, int kvalid, const TcBlock& blk, float* C, int ldc,
                int ncols, const float* bias, int relu) {
+    return tc_gemm_pw_ex(h, st, M, A, lda, kvalid, blk, C, ldc, ncols, bias, relu, nullptr, 0, 0, 0, nullptr);
+}
+int tc_gemm_pw_ex(const i2sdf_handle* h, cudaStream_t st, long long M, const float* A, int lda, int kvalid, const TcBlock& blk, float* C, int ldc,
+                  int ncols, const float* bias, int relu, const float* A2, int lda2, int is_skip, int nsplit, const float* E2) {
     using namespace tcg;
     static bool attr = false;
     if (!attr) {
@@ -378,6 +443,7 @@ int tc_gemm_pw(const i2sdf_handle* h, cudaStream_t st, long long M, const float*
     PWArgs G;
     G.A = A; G.lda = lda; G.kvalid = kvalid; G.M = M; G.B = blk.ptr; G.ksteps = blk.ksteps; G.n = blk.n; G.C = C; G.ldc = ldc; G.ncols = ncols;
     G.bias = bias; G.relu = relu;
+    G.A2 = A2; G.lda2 = lda2; G.is_skip = is_skip; G.nsplit = nsplit; G.E2 = E2;
     long long ntiles = (M + TM - 1) / TM;
     int grid = (int)(ntiles < (long long)h->num_sms ? ntiles : (long long)h->num_sms);
     gemm_pw_kernel<<<grid, NTHREADS, kSmemPW, st>>>(G);
@@ -386,8 +452,17 @@ int tc_gemm_pw(const i2sdf_handle* h, cudaStream_t st, long long M, const float*
 }
 
 // dW[n1][ldw] (+=) P0^T X0 (+ P1^T X1).  ws: tc_wgrad_ws_floats(h) floats.
+int tc_gemm_wgrad_ex(const i2sdf_handle* h, cudaStream_t st, long long M, const float* P0, int ldp0, const float* X0, int ldx0, const float* P1,
+                     int ldp1, const float* X1, int ldx1, int n1, int n2, float* dW, int ldw, float* ws, const float* Aprev, const float* Adprev,
+                     int is_skip, int nsplit, const float* E0, const float* E1);
 int tc_gemm_wgrad(const i2sdf_handle* h, cudaStream_t st, long long M, const float* P0, int ldp0, const float* X0, int ldx0, const float* P1,
                   int ldp1, const float* X1, int ldx1, int n1, int n2, float* dW, int ldw, float* ws) {
+    return tc_gemm_wgrad_ex(h, st, M, P0, ldp0, X0, ldx0, P1, ldp1, X1, ldx1, n1, n2, dW, ldw, ws, nullptr, nullptr, 0, 0, nullptr, nullptr);
+}
+// Aprev != null: X0 / X1 are computed on the fly from the saved pre-activations / tangents of the previous layer
+int tc_gemm_wgrad_ex(const i2sdf_handle* h, cudaStream_t st, long long M, const float* P0, int ldp0, const float* X0, int ldx0, const float* P1,
+                     int ldp1, const float* X1, int ldx1, int n1, int n2, float* dW, int ldw, float* ws, const float* Aprev, const float* Adprev,
+                     int is_skip, int nsplit, const float* E0, const float* E1) {
     using namespace tcg;
     static bool attr = false;
     if (!attr) {
@@ -399,6 +474,7 @@ int tc_gemm_wgrad(const i2sdf_handle* h, cudaStream_t st, long long M, const flo
     if (n1 > 256 || n2 > 256 || n1 < 1 || n2 < 1) { set_error("tc_gemm_wgrad: n1/n2 out of range"); return I2SDF_E_INVALID; }
     WGArgs G;
     G.P0 = P0; G.ldp0 = ldp0; G.X0 = X0; G.ldx0 = ldx0; G.P1 = P1; G.ldp1 = ldp1; G.X1 = X1; G.ldx1 = ldx1; G.n1 = n1; G.n2 = n2; G.M = M; G.partial = ws;
+    G.Aprev = Aprev; G.Adprev = Adprev; G.is_skip = is_skip; G.nsplit = nsplit; G.E0 = E0; G.E1 = E1;
     long long nk16 = (M + 15) / 16;
     int grid = (int)(nk16 < (long long)h->num_sms ? nk16 : (long long)h->num_sms);
     gemm_wgrad_kernel<<<grid, NTHREADS, kSmemWG, st>>>(G);
