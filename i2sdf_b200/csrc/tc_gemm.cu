@@ -80,9 +80,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_pw_kernel(const PWArgs G) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + NSTAGE * STAGE_MAX);
     uint64_t* full = bars;
     uint64_t* empty = bars + NSTAGE;
-    uint64_t* a_ready = bars + 2 * NSTAGE;       // [N_READY], 8 arrivals
-    uint64_t* d_full = a_ready + N_READY;        // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 2);
+    uint64_t* a_ready = bars + 2 * NSTAGE;       // [N_READY], 4 arrivals (one loader warp per lane quarter)
+    uint64_t* d_full = a_ready + N_READY;        // [2]  MMAs of a tile done (A operand free, accumulator complete)
+    uint64_t* d_empty = d_full + 2;              // [2]  accumulator stored (8 storer warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long ntiles = (G.M + TM - 1) / TM;
@@ -91,9 +92,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_pw_kernel(const PWArgs G) {
 
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < N_READY; ++i) mbar_init(&a_ready[i], 8);
+        for (int i = 0; i < N_READY; ++i) mbar_init(&a_ready[i], 4);
         mbar_init(&d_full[0], 1);
         mbar_init(&d_full[1], 1);
+        mbar_init(&d_empty[0], 8);
+        mbar_init(&d_empty[1], 8);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -122,6 +125,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_pw_kernel(const PWArgs G) {
             uint32_t stage = 0, phase = 0, aphase = 0, t = 0;
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
                 const uint32_t d_tmem = tmem_base + (t & 1u) * 256u;
+                if (t >= 2) {                                   // accumulator of tile t-2 must have been stored
+                    mbar_wait(&d_empty[t & 1u], ((t >> 1) - 1) & 1u);
+                    tc_fence_after();
+                }
                 for (int ks = 0; ks < G.ksteps; ++ks) {
                     if ((ks & 1) == 0) {
                         const int c = ks >> 1;
@@ -147,111 +154,104 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_pw_kernel(const PWArgs G) {
         }
     } else {
         const int q = warp & 3;
-        const int sub = (warp - 2) >> 2;
+        const int sub = (warp - 2) >> 2;              // 0,1: storers (TMEM -> global)   2,3: loaders (global -> SMEM operand)
         const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const int kpad = G.ksteps * 16;
         const bool vec_ok = ((G.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(G.A) & 15) == 0);
         const bool cvec_ok = ((G.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(G.C) & 15) == 0);
 
-        // one 16-column item of this thread's row, fp32 from global (zero beyond kvalid / M)
-        auto fetch_item = [&](const float* arow, bool rowok, int col0, float (&hv)[16]) {
-            if (rowok && vec_ok && col0 + 16 <= G.kvalid) {
+        if (sub >= 2) {
+            // ================= loaders: stage tile t's A operand as soon as the MMAs of tile t-1 released it =================
+            const int s2 = sub - 2;
+            auto fetch_item = [&](const float* arow, long long m, bool rowok, int col0, float (&hv)[16]) {
+                if (rowok && vec_ok && col0 + 16 <= G.kvalid) {
 #pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                    const float4 v = *reinterpret_cast<const float4*>(arow + col0 + j4 * 4);
-                    hv[j4 * 4] = v.x; hv[j4 * 4 + 1] = v.y; hv[j4 * 4 + 2] = v.z; hv[j4 * 4 + 3] = v.w;
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 v = *reinterpret_cast<const float4*>(arow + col0 + j4 * 4);
+                        hv[j4 * 4] = v.x; hv[j4 * 4 + 1] = v.y; hv[j4 * 4 + 2] = v.z; hv[j4 * 4 + 3] = v.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) hv[j] = (rowok && col0 + j < G.kvalid) ? arow[col0 + j] : 0.f;
                 }
-            } else {
+                if (G.A2) {          // fused: softplus'(a) * adot  (+ skip concat)
+                    const float* a2 = G.A2 + (size_t)(rowok ? m : 0) * G.lda2 + col0;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) hv[j] = (rowok && col0 + j < G.kvalid) ? arow[col0 + j] : 0.f;
-            }
-            if (G.A2) {          // fused: softplus'(a) * adot  (+ skip concat)
-                const long long mrow = (arow - G.A) / G.lda;
-                const float* a2 = G.A2 + (size_t)mrow * G.lda2 + col0;
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const float4 t = rowok ? *reinterpret_cast<const float4*>(a2 + j4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        hv[j4 * 4] = dsp_fast(hv[j4 * 4]) * t.x; hv[j4 * 4 + 1] = dsp_fast(hv[j4 * 4 + 1]) * t.y;
+                        hv[j4 * 4 + 2] = dsp_fast(hv[j4 * 4 + 2]) * t.z; hv[j4 * 4 + 3] = dsp_fast(hv[j4 * 4 + 3]) * t.w;
+                    }
+                    if (G.is_skip) {
 #pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                    const float4 t = rowok ? *reinterpret_cast<const float4*>(a2 + j4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    hv[j4 * 4] = dsp_fast(hv[j4 * 4]) * t.x; hv[j4 * 4 + 1] = dsp_fast(hv[j4 * 4 + 1]) * t.y;
-                    hv[j4 * 4 + 2] = dsp_fast(hv[j4 * 4 + 2]) * t.z; hv[j4 * 4 + 3] = dsp_fast(hv[j4 * 4 + 3]) * t.w;
-                }
-                if (G.is_skip) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int k = col0 + j;
-                        if (k >= G.nsplit) hv[j] = rowok ? G.E2[(size_t)mrow * 40 + (k - G.nsplit)] : 0.f;
-                        hv[j] *= 0.70710678118654752f;
+                        for (int j = 0; j < 16; ++j) {
+                            const int k = col0 + j;
+                            if (k >= G.nsplit) hv[j] = rowok ? G.E2[(size_t)m * 40 + (k - G.nsplit)] : 0.f;
+                            hv[j] *= 0.70710678118654752f;
+                        }
                     }
                 }
-            }
-        };
-        // stage a 128-row tile of A into the SMEM operand; the global loads run one item ahead of the convert/store
-        auto load_tile = [&](long long tile) {
-            const long long m = tile * TM + row;
-            const bool rowok = m < G.M;
-            const float* arow = G.A + (size_t)(rowok ? m : 0) * G.lda;
-            const int nit = (nchunks + 1) >> 1;
-            float cur[16], nxt[16];
-            {
-                const int c0 = (sub >> 1), col00 = c0 * 32 + (sub & 1) * 16;
-                if (c0 < nchunks && col00 < kpad) fetch_item(arow, rowok, col00, cur);
-            }
-            for (int it = 0; it < nit; ++it) {
-                const int c = 2 * it + (sub >> 1);
-                if (c >= nchunks) break;
-                const int col0 = c * 32 + (sub & 1) * 16;
-                const int cn = c + 2, coln = cn * 32 + (sub & 1) * 16;
-                const bool have_next = (it + 1 < nit) && (cn < nchunks) && (coln < kpad);
-                if (have_next) fetch_item(arow, rowok, coln, nxt);
-                if (col0 < kpad) store_a16(A_hi, A_lo, row, col0 >> 3, cur);
-                publish(&a_ready[c], lane);
-                if (have_next) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
+            };
+            uint32_t t = 0, fphase = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+                if (t >= 1) {                                   // MMAs of the previous tile finished reading the A operand
+                    const uint32_t b = (t - 1) & 1u;
+                    mbar_wait(&d_full[b], (fphase >> b) & 1u);
+                    fphase ^= (1u << b);
+                }
+                const long long m = tile * TM + row;
+                const bool rowok = m < G.M;
+                const float* arow = G.A + (size_t)(rowok ? m : 0) * G.lda;
+                for (int c = s2; c < nchunks; c += 2) {         // this warp: every other 32-column chunk, two 16-column items each
+                    float h0[16], h1[16];
+                    const int col0 = c * 32;
+                    const bool v0 = col0 < kpad, v1 = col0 + 16 < kpad;
+                    if (v0) fetch_item(arow, m, rowok, col0, h0);
+                    if (v1) fetch_item(arow, m, rowok, col0 + 16, h1);
+                    if (v0) store_a16(A_hi, A_lo, row, col0 >> 3, h0);
+                    if (v1) store_a16(A_hi, A_lo, row, (col0 + 16) >> 3, h1);
+                    publish(&a_ready[c], lane);
                 }
             }
-        };
-        auto store_tile = [&](long long tile, uint32_t buf) {
-            const long long m = tile * TM + row;
-            for (int it = 0; it < 8; ++it) {
-                const int col0 = (2 * it + (sub >> 1)) * 32 + (sub & 1) * 16;
-                if (col0 >= G.n) break;
-                uint32_t v[16];
-                tmem_ld16(tmem_base + lane_base + buf * 256u + (uint32_t)col0, v);
-                tmem_ld_wait();
-                if (m < G.M && col0 < G.ncols) {
-                    float o[16];
+        } else {
+            // ================= storers: accumulator of tile t -> global, overlapping the staging / MMAs of tile t+1 =================
+            uint32_t t = 0, dphase = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
+                const uint32_t b = t & 1u;
+                mbar_wait(&d_full[b], (dphase >> b) & 1u);
+                dphase ^= (1u << b);
+                tc_fence_after();
+                const long long m = tile * TM + row;
+                for (int it = 0; it < 8; ++it) {
+                    const int col0 = it * 32 + sub * 16;
+                    if (col0 >= G.n) break;
+                    uint32_t v[16];
+                    tmem_ld16(tmem_base + lane_base + b * 256u + (uint32_t)col0, v);
+                    tmem_ld_wait();
+                    if (m < G.M && col0 < G.ncols) {
+                        float o[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float x = __uint_as_float(v[j]);
-                        if (G.bias) x += __ldg(G.bias + col0 + j);
-                        if (G.relu) x = fmaxf(x, 0.f);
-                        o[j] = x;
-                    }
-                    float* crow = G.C + (size_t)m * G.ldc + col0;
-                    if (cvec_ok && col0 + 16 <= G.ncols) {
+                        for (int j = 0; j < 16; ++j) {
+                            float x = __uint_as_float(v[j]);
+                            if (G.bias) x += __ldg(G.bias + col0 + j);
+                            if (G.relu) x = fmaxf(x, 0.f);
+                            o[j] = x;
+                        }
+                        float* crow = G.C + (size_t)m * G.ldc + col0;
+                        if (cvec_ok && col0 + 16 <= G.ncols) {
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) *reinterpret_cast<float4*>(crow + j4 * 4) = make_float4(o[j4 * 4], o[j4 * 4 + 1], o[j4 * 4 + 2], o[j4 * 4 + 3]);
-                    } else {
+                            for (int j4 = 0; j4 < 4; ++j4) *reinterpret_cast<float4*>(crow + j4 * 4) = make_float4(o[j4 * 4], o[j4 * 4 + 1], o[j4 * 4 + 2], o[j4 * 4 + 3]);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) if (col0 + j < G.ncols) crow[j] = o[j];
+                            for (int j = 0; j < 16; ++j) if (col0 + j < G.ncols) crow[j] = o[j];
+                        }
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d_empty[b]);
             }
-            tc_fence_before();
-        };
-
-        uint32_t dphase = 0, t = 0;
-        long long tile = blockIdx.x;
-        if (tile < ntiles) load_tile(tile);
-        for (; tile < ntiles; tile += gridDim.x, ++t) {
-            const uint32_t b = t & 1u;
-            mbar_wait(&d_full[b], (dphase >> b) & 1u);      // MMAs of this tile done: A operand free, D[b] complete
-            dphase ^= (1u << b);
-            tc_fence_after();
-            const long long next = tile + gridDim.x;
-            if (next < ntiles) load_tile(next);             // next tile's MMAs (into D[b^1]) overlap this tile's store
-            store_tile(tile, b);
         }
     }
     tc_fence_before();
@@ -338,31 +338,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_wgrad_kernel(const WGArgs G)
         const int e = tid - 64;                  // 0..511
         const int kc = e >> 8, r = e & 255;
         uint32_t stage = 0, phase = 0;
-        for (long long st = 0; st < nsteps; ++st) {
+        // fp32 operands of one k step (8 points of feature row r) -> registers
+        auto fetch = [&](long long st, float (&a)[8], float (&bv)[8]) {
             const int pair = (npairs == 2) ? (int)(st & 1) : 0;
             const long long k16 = k_lo + (npairs == 2 ? (st >> 1) : st);
             const float* Pp = pair ? G.P1 : G.P0;
             const float* Xp = pair ? G.X1 : G.X0;
             const int ldp = pair ? G.ldp1 : G.ldp0, ldx = pair ? G.ldx1 : G.ldx0;
             const long long p0 = k16 * 16 + kc * 8;
-            float a[8], b[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const long long p = p0 + i;
                 const bool ok = p < G.M;
                 a[i] = (ok && r < G.n1) ? __ldg(Pp + (size_t)p * ldp + r) : 0.f;
                 if (!G.Aprev) {
-                    b[i] = (ok && r < G.n2) ? __ldg(Xp + (size_t)p * ldx + r) : 0.f;
+                    bv[i] = (ok && r < G.n2) ? __ldg(Xp + (size_t)p * ldx + r) : 0.f;
                 } else if (!(ok && r < G.n2)) {
-                    b[i] = 0.f;
+                    bv[i] = 0.f;
                 } else if (G.is_skip && r >= G.nsplit) {
-                    b[i] = __ldg((pair ? G.E1 : G.E0) + (size_t)p * 40 + (r - G.nsplit)) * 0.70710678118654752f;
+                    bv[i] = __ldg((pair ? G.E1 : G.E0) + (size_t)p * 40 + (r - G.nsplit)) * 0.70710678118654752f;
                 } else {
                     const float av = __ldg(G.Aprev + (size_t)p * 256 + r);
                     float x = pair ? dsp_fast(av) * __ldg(G.Adprev + (size_t)p * 256 + r) : sp_fast(av);
-                    b[i] = G.is_skip ? x * 0.70710678118654752f : x;
+                    bv[i] = G.is_skip ? x * 0.70710678118654752f : x;
                 }
             }
+        };
+        auto commit = [&](const float (&a)[8], const float (&bv)[8]) {
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* base = ring + stage * WG_STAGE_BYTES;
             const uint32_t off = (uint32_t)kc * 4096u + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
@@ -372,13 +374,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_wgrad_kernel(const WGArgs G)
             *reinterpret_cast<uint4*>(base + off) = make_uint4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<uint4*>(base + 8192 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) split_bf16x2(b[2 * i], b[2 * i + 1], h[i], lo[i]);
+            for (int i = 0; i < 4; ++i) split_bf16x2(bv[2 * i], bv[2 * i + 1], h[i], lo[i]);
             *reinterpret_cast<uint4*>(base + 16384 + off) = make_uint4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<uint4*>(base + 24576 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[stage]);
             if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+        };
+        for (long long st = 0; st < nsteps; st += 2) {       // two k steps of loads in flight per thread
+            float a0[8], b0[8], a1[8], b1[8];
+            fetch(st, a0, b0);
+            const bool two = st + 1 < nsteps;
+            if (two) fetch(st + 1, a1, b1);
+            commit(a0, b0);
+            if (two) commit(a1, b1);
         }
         // ---- epilogue: TMEM -> partial
         mbar_wait(d_full, 0);
