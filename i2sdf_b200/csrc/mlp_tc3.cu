@@ -105,7 +105,8 @@ __device__ __forceinline__ bool round_active(const MlpParams& P) {
 }
 
 template <bool FULL>
-__global__ void __maxnreg__(112) tc_mlp_kernel(const MlpParams P, const OpTable T) {   // 576 threads x 112 regs = 63 K of the 64 K registers
+// 18 warps -> one scheduler hosts 5 of them: 16 K regs / 5 warps caps the kernel at 96 registers per thread
+__global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, const OpTable T) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* A_hi = smem;
@@ -271,12 +272,6 @@ __global__ void __maxnreg__(112) tc_mlp_kernel(const MlpParams P, const OpTable 
                     load_point(next_tile, xn, dvn);
                     prologue(xn);
                 }
-                // TMEM loads run one item ahead of the arithmetic: item it+1 is requested right after item it has landed
-                uint32_t vnext[16];
-                {
-                    const int col00 = (sub >> 1) * 32 + (sub & 1) * 16;
-                    if (!(FULL && kind == EK_GRAD && col00 >= 48)) tmem_ld16(tmem_base + lane_base + b * 256u + (uint32_t)col00, vnext);
-                }
 #pragma unroll 1
                 for (int it = 0; it < 4; ++it) {
                     const int c = 2 * it + (sub >> 1);                 // 32-column chunk
@@ -297,11 +292,8 @@ __global__ void __maxnreg__(112) tc_mlp_kernel(const MlpParams P, const OpTable 
                         for (int j4 = 0; j4 < 4; ++j4) pre[j4] = *reinterpret_cast<const float4*>(psrc + j4 * 4);
                     }
                     uint32_t v[16];
+                    tmem_ld16(tmem_base + lane_base + b * 256u + (uint32_t)col0, v);
                     tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = vnext[j];
-                    if (it < 3 && !(FULL && kind == EK_GRAD))
-                        tmem_ld16(tmem_base + lane_base + b * 256u + (uint32_t)(col0 + 64), vnext);
                     float hv[16];
                     if (kind == EK_SDF_HIDDEN || kind == EK_SDF_LAST || kind == EK_SDF_LAST_REV) {
 #pragma unroll
