@@ -318,6 +318,9 @@ static int run_mlp(const i2sdf_handle* h, const MlpParams& p, cudaStream_t st) {
     if (h->tcmain && tcmain_has_full(h->tcmain) && p.out_sdf && p.out_grad && p.out_rgb && p.want_color && !p.want_light &&
         (p.scratch || p.save_act) && ((p.save_act != nullptr) == (p.out_feat != nullptr)) && (p.ray_d || p.pts))
         return tcmain_launch(h, h->tcmain, p, st);
+    // sdf + features only (ImplicitNetwork.forward: mesh extraction, plots): F layers + feature layer; needs no scratch
+    if (h->tcmain && p.out_sdf && p.out_feat && !p.out_grad && !p.want_color && !p.want_light && !p.save_act && (p.ray_d || p.pts))
+        return tcmain_launch(h, h->tcmain, p, st);
     // sdf + grad_x only (eikonal points / ImplicitNetwork.gradient): F layers then the reverse sweep, no radiance stack
     if (h->tcmain && p.out_sdf && p.out_grad && !p.want_color && !p.want_light && !p.out_feat && (p.scratch || p.save_act) && (p.ray_d || p.pts))
         return tcmain_launch(h, h->tcmain, p, st);

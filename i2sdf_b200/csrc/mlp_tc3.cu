@@ -245,8 +245,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
             size_t sig_lstride = 0;
             if (FULL) {
                 if (save) { sig_base = P.save_act + (size_t)(valid ? m : 0) * 256; sig_lstride = (size_t)P.M * 256; }
-                else { sig_base = P.scratch + (size_t)blockIdx.x * (size_t)NL * TM * 256 + (size_t)row * 256; sig_lstride = (size_t)TM * 256; }
-            }
+                else if (P.scratch) { sig_base = P.scratch + (size_t)blockIdx.x * (size_t)NL * TM * 256 + (size_t)row * 256; sig_lstride = (size_t)TM * 256; }
+            }   // sig_base stays null for the sdf + features table (no reverse sweep, nothing to keep)
 
             float head = 0.f, rgbp[3] = {0.f, 0.f, 0.f}, gacc[3] = {0.f, 0.f, 0.f};
             for (int op = 0; op < T.nops; ++op, ++g) {
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                                     }
                                 }
                             }
-                            if (FULL && (!save || valid))
+                            if (FULL && sig_base && (!save || valid))
                                 *reinterpret_cast<float4*>(sig_base + (size_t)l * sig_lstride + col0 + j4 * 4) = make_float4(so[0], so[1], so[2], so[3]);
                         }
                         if (kind == EK_SDF_LAST) {
@@ -355,6 +355,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                                 *reinterpret_cast<float4*>(P.out_feat + (size_t)m * 256 + col0 + j4 * 4) =
                                     make_float4(hv[j4 * 4], hv[j4 * 4 + 1], hv[j4 * 4 + 2], hv[j4 * 4 + 3]);
                         }
+                        if (kind == EK_FEAT && op == T.nops - 1) continue;     // sdf + features only: nothing follows
                         if (kind == EK_COL_LAST) {
                             const float* __restrict__ wh = net.col_head + col0;
 #pragma unroll
@@ -420,7 +421,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                     store_a16(A_hi, A_lo, row, col0 >> 3, hv);
                     publish_chunk(&a_ready[c], lane);
                 }
-                if (FULL && kind == EK_FEAT && sub < 2) {
+                if (FULL && kind == EK_FEAT && sub < 2 && op < T.nops - 1) {
                     // k chunk 8 (columns 256..287) = positional encoding of the view direction, zero padded
                     float hv[16];
 #pragma unroll
@@ -453,7 +454,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                             const float s = acc[1 + c] + __ldg(net.col_head + 768 + c);
                             P.out_rgb[m * 3 + c] = __fdiv_rn(1.0f, 1.0f + expf(-s));
                         }
-                        P.out_grad[m * 3 + c] = acc[4 + c];
+                        if (P.out_grad) P.out_grad[m * 3 + c] = acc[4 + c];
                     }
                 }
             }
@@ -506,6 +507,7 @@ struct State {
     OpTable sdf;              // ops of the sdf-only chain (a prefix of the full table)
     OpTable full;             // nops == 0 if the full main pass is unavailable for this network
     OpTable sg;               // SDF + grad_x only (eikonal points): F_0..F_{NL-1}, R_{NL-1}..R_0
+    OpTable sf;               // SDF + features (ImplicitNetwork.forward: meshing / plots): F_0..F_{NL-1}, G
     int src_layer[MAX_OPS];   // packing recipe per op of the full table
     int mode[MAX_OPS], row_off[MAX_OPS], feat_first[MAX_OPS];
     int n_pack;               // number of ops to pack
@@ -557,6 +559,10 @@ int tc_create(i2sdf_handle* h) {
     for (int l = 0; l < NL; ++l) { s->sg.ops[s->sg.nops] = T.ops[s->blk_fwd_sdf[l]]; if (l == NL - 1) s->sg.ops[s->sg.nops].kind = EK_SDF_LAST_REV; ++s->sg.nops; }
     for (int l = NL - 1; l >= 1; --l) s->sg.ops[s->sg.nops++] = T.ops[s->blk_rev_sdf[l]];
     s->sg.ops[s->sg.nops++] = T.ops[n_kernel_ops - 1];          // R_0 (EK_GRAD)
+    s->sf.wpack = s->wpack;
+    s->sf.nops = 0;
+    for (int l = 0; l < NL; ++l) s->sf.ops[s->sf.nops++] = T.ops[s->blk_fwd_sdf[l]];
+    s->sf.ops[s->sf.nops++] = T.ops[s->blk_fwd_feat];
     cudaError_t e = cudaFuncSetAttribute(tc_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) { cudaFree(s->wpack); delete s; set_error("tc_create: smem attribute: %s", cudaGetErrorString(e)); return I2SDF_E_CUDA; }
@@ -632,7 +638,8 @@ int tcmain_launch(const i2sdf_handle* h, void* state, const MlpParams& p, cudaSt
     using namespace tc3;
     if (p.M <= 0) return I2SDF_OK;
     const State* s = (const State*)state;
-    tc_mlp_kernel<true><<<tc_grid(h, p.M), NTHREADS, kSmemBytes, st>>>(p, p.want_color ? s->full : s->sg);
+    const OpTable& tab = p.want_color ? s->full : (p.out_grad ? s->sg : s->sf);
+    tc_mlp_kernel<true><<<tc_grid(h, p.M), NTHREADS, kSmemBytes, st>>>(p, tab);
     I2SDF_CUDA_CHECK(cudaGetLastError());
     return I2SDF_OK;
 }

@@ -78,3 +78,13 @@ def test_unsupported_configs_are_rejected():
     conf["rendering_network"]["mode"] = "idr"
     with pytest.raises(_lib.I2SDFError):
         I2SDFNetwork(conf)
+
+
+def test_pixel_grid_matches_reference_get_uv():
+    """dataset/eval_dataset.py:144-148: np.mgrid -> flip -> reshape(2,-1).T"""
+    import numpy as np
+    from i2sdf_b200.render import pixel_grid
+    H, W = 5, 7
+    uv = np.mgrid[0:H, 0:W].astype(np.int32)
+    ref = torch.from_numpy(np.flip(uv, axis=0).copy()).float().reshape(2, -1).transpose(1, 0)
+    assert torch.equal(pixel_grid((H, W)), ref)

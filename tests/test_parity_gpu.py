@@ -45,10 +45,11 @@ def test_sdf_forward_matches_oracle(cases, name):
     layers = orc.layer_params(c.params, "implicit_network", c.spec.n_sdf_layers)
     with torch.no_grad():
         ref, gref = orc.sdf_mlp(c.spec, layers, pts, want_grad=True)
-    out = m.implicit_network(pts.cuda())
+    out = m.implicit_network(pts.cuda())                       # sdf + features: tensor-core chain F.., G when enabled
     assert out.shape == (1000, 257)
-    assert relerr(out[:, 0], ref[:, 0]) < 1e-5
-    assert relerr(out[:, 1:], ref[:, 1:]) < 1e-5
+    tol = TOL if m._core_obj.uses_tensor_cores else 1e-5
+    assert relerr(out[:, 0], ref[:, 0]) < tol
+    assert relerr(out[:, 1:], ref[:, 1:]) < tol
     g2 = m.implicit_network.gradient(pts.cuda())              # sdf + grad_x: tensor-core chain F.., R.. when enabled
     assert relerr(g2, gref) < (2 * TOL if m._core_obj.uses_tensor_cores else 2e-5), relerr(g2, gref)
     s2 = m.implicit_network.get_sdf_vals(pts.cuda())        # sdf-only evaluations run on the tcgen05 kernel
@@ -64,7 +65,7 @@ def test_sdf_forward_ragged_and_empty(cases):
         with torch.no_grad():
             ref = orc.sdf_mlp(c.spec, layers, pts)[0]
         out = m.implicit_network(pts.cuda())
-        assert relerr(out, ref) < 1e-5
+        assert relerr(out, ref) < (TOL if m._core_obj.uses_tensor_cores else 1e-5)
     out = m.implicit_network(torch.zeros(0, 3).cuda())
     assert out.shape == (0, 257)
 
@@ -355,3 +356,22 @@ def test_training_rng_draw_order_matches_reference():
     torch.rand(R, 128, device="cuda"); torch.rand(R, 64, device="cuda")
     assert torch.equal(p1, torch.randperm(384)[:32])
     assert torch.equal(e1, torch.randint(98, (R,), device="cuda"))
+
+
+def test_whole_image_driver_equals_chunked_forward(cases):
+    """i2sdf_b200.render.render_image == concatenation of model.forward over the same chunks (C3 call pattern)."""
+    from i2sdf_b200.render import pixel_grid, render_image
+    c = cases["eval_synthetic_soft"]
+    m = _model(c)
+    H, W, chunk = 24, 40, 300
+    pose, K = c.inputs["pose"][0], c.inputs["intrinsics"][0].clone()
+    K[0, 2], K[1, 2] = W / 2, H / 2
+    K[0, 0] = K[1, 1] = 40.0
+    img = render_image(m, pose, K, (H, W), split_n_pixels=chunk)
+    uv = pixel_grid((H, W), torch.device("cuda"))
+    parts = []
+    for lo in range(0, H * W, chunk):
+        parts.append(m({"uv": uv[None, lo:lo + chunk], "pose": pose[None].cuda(), "intrinsics": K[None].cuda()})["rgb_values"])
+    assert img["rgb_values"].shape == (H * W, 3)
+    assert torch.equal(img["rgb_values"], torch.cat(parts, 0))
+    assert set(img) == {"rgb_values", "depth_values", "weight_sum", "normal_map"}
