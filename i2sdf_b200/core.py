@@ -116,6 +116,30 @@ class RenderCore:
         kinds = ("sampler_sdf", "main_mlp", "sampler_rays", "misc")
         return {k: dict(ms=float(ms[i]), launches=int(n[i])) for i, k in enumerate(kinds)}
 
+    # ---- plane slots (HBM format of the fused training path; see csrc/planes.cuh)
+    def planes_pack(self, X: torch.Tensor, columns: int = 256) -> torch.Tensor:
+        X = _f32(X, self.device)
+        M, width = X.shape
+        slot = torch.empty(self.lib.i2sdf_planes_slot_bytes(M, columns), dtype=torch.uint8, device=self.device)
+        check(self.lib.i2sdf_planes_pack(self.h, _ptr(X), width, width, M, columns, _ptr(slot), self._stream()), "i2sdf_planes_pack")
+        return slot
+
+    def planes_unpack(self, slot: torch.Tensor, M: int, width: int = 256, columns: int = 256) -> torch.Tensor:
+        X = torch.empty(M, width, device=self.device)
+        check(self.lib.i2sdf_planes_unpack(self.h, _ptr(slot), columns, M, _ptr(X), width, width, self._stream()), "i2sdf_planes_unpack")
+        return X
+
+    def planes_wgrad(self, P_slots, X_slots, M: int, rows: int, cols: int, x_columns: int = 256, colsum: bool = False):
+        """dW [rows, cols] = sum_t P_t^T X_t on the tensor cores (+ column sums of P_0)."""
+        n = len(P_slots)
+        dW = torch.zeros(rows, cols, device=self.device)
+        cs = torch.zeros(256, device=self.device) if colsum else None
+        Pp = (C.c_void_p * n)(*[t.data_ptr() for t in P_slots])
+        Xp = (C.c_void_p * n)(*[t.data_ptr() for t in X_slots])
+        check(self.lib.i2sdf_planes_wgrad(self.h, n, Pp, Xp, x_columns, M, _ptr(dW), cols, rows, cols, _ptr(cs), self._stream()),
+              "i2sdf_planes_wgrad")
+        return (dW, cs[:rows]) if colsum else dW
+
     # ---- weights
     def pack(self, weights: List[torch.Tensor], biases: List[torch.Tensor]):
         """weights[i]: effective [out,in] fp32 weight of layer i (SDF layers, colour layers, light layers)."""

@@ -4,6 +4,8 @@
 #include <string.h>
 #include <vector>
 #include "common.cuh"
+#include "planes.cuh"
+#include "wgrad_planes.cuh"
 
 namespace i2sdf {
 
@@ -535,6 +537,34 @@ int i2sdf_render_forward(i2sdf_handle* h, const float* o, const float* d, const 
     if (rc) return rc;
     ProfScope ps(h, 3, st);
     return launch_composite(h, z, dnorm, s_sdf, s_rgb, s_grad, s_light, beta_param, R, N, rgb, depth, weight_sum, normal, light, s_w, st);
+}
+
+// ---- plane slots (diagnostics / tests) --------------------------------------------------------------------------
+size_t i2sdf_planes_slot_bytes(int64_t M, int columns) {
+    if (M < 0) return 0;
+    return columns == 256 ? planes::big_slot_bytes(M) : (columns == 48 ? planes::small_slot_bytes(M) : 0);
+}
+static int planes_chunks(int columns) { return columns == 256 ? planes::BIG_CHUNKS : (columns == 48 ? planes::SMALL_CHUNKS : 0); }
+
+int i2sdf_planes_pack(i2sdf_handle* h, const float* X, int ld, int width, int64_t M, int columns, void* slot, void* stream) {
+    if (!h || !X || !slot || !planes_chunks(columns) || width > columns) { set_error("planes_pack: bad argument"); return I2SDF_E_INVALID; }
+    return planes_pack_launch(X, ld, width, M, (uint8_t*)slot, planes_chunks(columns), (cudaStream_t)stream);
+}
+int i2sdf_planes_unpack(i2sdf_handle* h, const void* slot, int columns, int64_t M, float* X, int ld, int width, void* stream) {
+    if (!h || !X || !slot || !planes_chunks(columns) || width > columns) { set_error("planes_unpack: bad argument"); return I2SDF_E_INVALID; }
+    return planes_unpack_launch((const uint8_t*)slot, planes_chunks(columns), M, X, ld, width, (cudaStream_t)stream);
+}
+int i2sdf_planes_wgrad(i2sdf_handle* h, int nterms, const void* const* P, const void* const* X, int x_columns, int64_t M,
+                       float* dW, int ld, int rows, int cols, float* colsum, void* stream) {
+    if (!h || !P || !X || !dW || nterms < 1 || nterms > 2 || !planes_chunks(x_columns) || rows > 256 || cols > x_columns) {
+        set_error("planes_wgrad: bad argument"); return I2SDF_E_INVALID;
+    }
+    if (!h->use_tc) { set_error("planes_wgrad: tensor-core path disabled"); return I2SDF_E_INVALID; }
+    WgArgs a{};
+    a.ntiles = planes::ntiles(M); a.nterms = nterms; a.njobs = 1;
+    a.jobs[0] = WgJob{dW, ld, rows, cols};
+    for (int t = 0; t < nterms; ++t) a.terms[t] = WgTerm{(const uint8_t*)P[t], (const uint8_t*)X[t], 0, planes_chunks(x_columns), t == 0 ? colsum : nullptr, rows};
+    return wgrad_planes_launch(h, a, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -212,6 +212,18 @@ int i2sdf_sdf_backward(i2sdf_handle* h, const float* const* W, const float* pts,
 int i2sdf_profile_enable(i2sdf_handle* h, int enable);
 int i2sdf_profile_read(i2sdf_handle* h, float ms[4], int64_t launches[4]);
 
+/* Plane slots: the HBM format of the fused training path (bf16 hi + lo planes per 128-point tile in the tensor
+ * cores' SMEM layout, i2sdf_b200/csrc/planes.cuh).  pack / unpack convert from / to plain fp32 [M][ld] arrays
+ * (columns = 256 or 48); planes_wgrad is the weight-gradient kernel on its own:
+ *   dW[rows][ld] += sum_t P_t^T X_t   (P_t: 256-column slots, X_t: x_columns-column slots, t < nterms <= 2),
+ *   colsum[j] += sum_m P_0[m][j] when colsum != NULL.
+ * These three are what the parity tests drive; the training path calls the same kernels internally. */
+size_t i2sdf_planes_slot_bytes(int64_t M, int columns);
+int i2sdf_planes_pack(i2sdf_handle* h, const float* X, int ld, int width, int64_t M, int columns, void* slot, void* stream);
+int i2sdf_planes_unpack(i2sdf_handle* h, const void* slot, int columns, int64_t M, float* X, int ld, int width, void* stream);
+int i2sdf_planes_wgrad(i2sdf_handle* h, int nterms, const void* const* P, const void* const* X, int x_columns, int64_t M,
+                       float* dW, int ld, int rows, int cols, float* colsum, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -375,3 +375,41 @@ def test_whole_image_driver_equals_chunked_forward(cases):
     assert img["rgb_values"].shape == (H * W, 3)
     assert torch.equal(img["rgb_values"], torch.cat(parts, 0))
     assert set(img) == {"rgb_values", "depth_values", "weight_sum", "normal_map"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# plane slots + tensor-core weight gradients (csrc/planes.cuh, wgrad_planes.cu)
+# ---------------------------------------------------------------------------------------------------------------
+def test_planes_roundtrip_and_wgrad(cases):
+    """fp32 -> bf16 hi/lo plane slot -> fp32 (16-bit mantissa round trip), and dW = P^T X (+ second term, + column sums)
+    on MN-major tcgen05 operands against a float64 product of the same values."""
+    m = _model(cases["eval_synthetic_soft"])
+    core = m._ready_core()
+    if not core.uses_tensor_cores:
+        pytest.skip("tensor-core path disabled")
+    g = torch.Generator().manual_seed(5)
+    for M in (128, 1000, 20000):
+        P0 = torch.randn(M, 256, generator=g).cuda() * torch.logspace(-3, 1, 256).cuda()
+        X0 = torch.randn(M, 256, generator=g).cuda()
+        P1 = torch.randn(M, 256, generator=g).cuda()
+        X1 = torch.randn(M, 256, generator=g).cuda() + 0.5
+        E = torch.randn(M, 39, generator=g).cuda()
+        sP0, sX0, sP1, sX1 = (core.planes_pack(t) for t in (P0, X0, P1, X1))
+        sE = core.planes_pack(E, columns=48)
+        back = core.planes_unpack(sP0, M)
+        assert (back - P0).abs().max() <= 2.0 ** -16 * P0.abs().max()
+        assert torch.equal(core.planes_unpack(sE, M, 39, 48), core.planes_unpack(core.planes_pack(E, 48), M, 39, 48))
+        r = lambda t: core.planes_unpack(core.planes_pack(t), M).double()     # the values the kernel actually multiplies
+        ref1 = r(P0).T @ r(X0)
+        dW, cs = core.planes_wgrad([sP0], [sX0], M, 256, 256, colsum=True)
+        scale = (r(P0).abs().T @ r(X0).abs())
+        assert ((dW.double() - ref1).abs() / scale).max() < 3e-5, ((dW.double() - ref1).abs() / scale).max()
+        assert ((cs.double() - r(P0).sum(0)).abs() / r(P0).abs().sum(0)).max() < 1e-5
+        ref2 = ref1 + r(P1).T @ r(X1)
+        dW2 = core.planes_wgrad([sP0, sP1], [sX0, sX1], M, 217, 256)
+        scale2 = scale + r(P1).abs().T @ r(X1).abs()
+        assert ((dW2.double() - ref2[:217]).abs() / scale2[:217]).max() < 3e-5
+        refE = r(P0).T @ core.planes_unpack(sE, M, 39, 48).double()
+        dWE = core.planes_wgrad([sP0], [sE], M, 256, 39, x_columns=48)
+        scaleE = r(P0).abs().T @ E.double().abs()
+        assert ((dWE.double() - refE).abs() / scaleE).max() < 3e-5
