@@ -48,8 +48,9 @@ class _PointsFn(Function):
     def forward(ctx, core, o, d, z, want_grad, n_sdf, n_col, n_light, *params):
         out = core.points_forward(o, d, z, want_grad, n_light > 0, save=True)
         ctx.core, ctx.cfg = core, (want_grad, n_sdf, n_col, n_light)
+        ctx.fused = out["fused"]
         ctx.set_materialize_grads(False)
-        keep = [o, d, z, out["act"], out["feat"], out["s_rgb"]]
+        keep = [o, d, z, out["act"], out["feat"] if out["feat"] is not None else o.new_empty(0), out["s_rgb"]]
         keep.append(out["s_light"] if out["s_light"] is not None else o.new_empty(0))
         ctx.save_for_backward(*keep, *params)
         s_grad = out["s_grad"] if want_grad else o.new_empty(0)
@@ -70,6 +71,12 @@ class _PointsFn(Function):
         R, N = z.shape[0], z.shape[1] - 1
         M = R * N
         dW_sdf, db_sdf, dW_col, db_col, dW_l, db_l = _zeros_like_all([W_sdf, b_sdf, W_col, b_col, W_l, b_l])
+        if ctx.fused:
+            # plane slots: one chain kernel + one weight-gradient launch cover both stacks, first and second order
+            if g_sdf is not None or g_rgb is not None or (want_grad and g_grad is not None):
+                core.fused_backward(M, act, dW_sdf, db_sdf, rays=(o, d, z, N), s_rgb=s_rgb, g_sdf=g_sdf,
+                                    g_grad=g_grad if want_grad else None, g_rgb=g_rgb, dW_col=dW_col, db_col=db_col)
+            return (None,) * 8 + tuple(dW_sdf + db_sdf + dW_col + db_col + dW_l + db_l)
         g_feat_ptr, ld = None, 256
         if g_rgb is not None:
             g_x = core.color_backward(W_col, b_col, d, N, feat, s_rgb, g_rgb, dW_col, db_col)
@@ -118,9 +125,10 @@ class _SdfPointsFn(Function):
     def forward(ctx, core, pts, want_grad, n_sdf, *params):
         pts = pts.detach().contiguous().float()
         M = pts.shape[0]
-        act = torch.empty(n_sdf - 1, M, 256, device=pts.device)
+        act = core.sdf_saved_buffer(M, want_grad)
         sdf, _, grad = core.sdf_forward(pts, want_grad=want_grad, save_act=act)
         ctx.core, ctx.cfg = core, (want_grad, n_sdf)
+        ctx.fused = core.fused_sdf and want_grad
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(pts, act, *params)
         if not want_grad:
@@ -136,7 +144,10 @@ class _SdfPointsFn(Function):
         W, b = list(saved[2:2 + n_sdf]), list(saved[2 + n_sdf:2 + 2 * n_sdf])
         dW, db = _zeros_like_all([W, b])
         if g_sdf is not None or (want_grad and g_grad is not None):
-            ctx.core.sdf_backward(W, pts.shape[0], act, dW, db, pts=pts, g_sdf=g_sdf, g_grad=g_grad if want_grad else None)
+            if ctx.fused:
+                ctx.core.fused_backward(pts.shape[0], act, dW, db, pts=pts, g_sdf=g_sdf, g_grad=g_grad)
+            else:
+                ctx.core.sdf_backward(W, pts.shape[0], act, dW, db, pts=pts, g_sdf=g_sdf, g_grad=g_grad if want_grad else None)
         return (None,) * 4 + tuple(dW + db)
 
 

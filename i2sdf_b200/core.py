@@ -77,6 +77,9 @@ class RenderCore:
         tcbits = self.lib.i2sdf_uses_tensor_cores(h)
         self.uses_tensor_cores = bool(tcbits & 1)
         self.uses_tensor_cores_main = bool(tcbits & 2)
+        # what the training forwards save: plane slots + fused tensor-core backward, or fp32 pre-activations + layer-wise backward
+        self.fused_main = bool(self.lib.i2sdf_saved_format(h, 0))
+        self.fused_sdf = bool(self.lib.i2sdf_saved_format(h, 1))
         self._ws = None
         self._ws_rays = -1
         self._packed_refs = None
@@ -162,6 +165,12 @@ class RenderCore:
         check(self.lib.i2sdf_rays(self.h, _ptr(uv), _ptr(pose), _ptr(intr), B, P, _ptr(o), _ptr(d), _ptr(dn), self._stream()), "i2sdf_rays")
         return o, d, dn
 
+    def sdf_saved_buffer(self, M: int, want_grad: bool) -> torch.Tensor:
+        """Buffer for sdf_forward(save_act=...): plane slots when the tensor-core chain serves the call, else fp32 [L-1,M,256]."""
+        if self.fused_sdf and want_grad:
+            return torch.empty(self.lib.i2sdf_sdf_saved_bytes(self.h, M), dtype=torch.uint8, device=self.device)
+        return torch.empty(self.desc.n_sdf_layers - 1, M, 256, device=self.device)
+
     def sdf_forward(self, pts, want_feat=False, want_grad=False, save_act=None):
         pts = _f32(pts.detach(), self.device)
         M = pts.shape[0]
@@ -240,11 +249,13 @@ class RenderCore:
         o, d, z = _f32(o, dev), _f32(d, dev), _f32(z, dev)
         R, N = z.shape[0], z.shape[1] - 1
         M = R * N
-        L = self.desc.n_sdf_layers
-        out = dict(s_sdf=torch.empty(M, device=dev), s_rgb=torch.empty(M, 3, device=dev), feat=torch.empty(M, 256, device=dev))
-        out["s_grad"] = torch.empty(M, 3, device=dev) if want_grad else None
+        fused = save and self.fused_main and not want_light       # plane slots: features stay inside the saved state
+        out = dict(s_sdf=torch.empty(M, device=dev), s_rgb=torch.empty(M, 3, device=dev))
+        out["feat"] = None if fused else torch.empty(M, 256, device=dev)
+        out["s_grad"] = torch.empty(M, 3, device=dev) if (want_grad or fused) else None
         out["s_light"] = torch.empty(M, device=dev) if want_light else None
-        out["act"] = torch.empty(L - 1, M, 256, device=dev) if save else None
+        out["act"] = torch.empty(self.lib.i2sdf_saved_bytes(self.h, R, N), dtype=torch.uint8, device=dev) if save else None
+        out["fused"] = fused
         ws = self.workspace(R)
         check(self.lib.i2sdf_points_forward(self.h, _ptr(o), _ptr(d), _ptr(z), R, N, _ptr(out["s_sdf"]), _ptr(out["s_grad"]),
                                             _ptr(out["s_rgb"]), _ptr(out["s_light"]), _ptr(out["feat"]), _ptr(out["act"]),
@@ -317,6 +328,26 @@ class RenderCore:
                                           _ptr(g_grad), self._ptr_array(dWs), self._ptr_array(dbs), _ptr(bws), bws.numel(), self._stream()),
               "i2sdf_sdf_backward")
         self._keep = (g_sdf, g_grad)
+
+    def fused_backward(self, M, saved, dW_sdf, db_sdf, pts=None, rays=None, s_rgb=None, g_sdf=None, g_grad=None, g_rgb=None,
+                       dW_col=None, db_col=None):
+        """Tensor-core backward on plane slots (i2sdf_fused_backward).  rays = (o, d, z [R,zstride], ns)."""
+        dev = self.device
+        bws = self.backward_workspace(M)
+        f = lambda t: None if t is None else _f32(t, dev)        # noqa: E731
+        g_sdf, g_grad, g_rgb = f(g_sdf), f(g_grad), f(g_rgb)
+        if rays is not None:
+            o, d, z, ns = rays
+            po, pd, pz, zs, pp = _ptr(o), _ptr(d), _ptr(z), z.shape[1], _ptr(None)
+        else:
+            po = pd = pz = _ptr(None)
+            zs, ns, pp = 0, 1, _ptr(pts)
+        null = C.POINTER(C.c_void_p)()
+        check(self.lib.i2sdf_fused_backward(self.h, pp, po, pd, pz, zs, ns, M, _ptr(saved), _ptr(s_rgb), _ptr(g_sdf), _ptr(g_grad), _ptr(g_rgb),
+                                            self._ptr_array(dW_sdf), self._ptr_array(db_sdf),
+                                            self._ptr_array(dW_col) if dW_col else null, self._ptr_array(db_col) if db_col else null,
+                                            _ptr(bws), bws.numel(), self._stream()), "i2sdf_fused_backward")
+        self._keep = (g_sdf, g_grad, g_rgb)
 
     def render(self, o, d, dnorm, z, beta_param, want_normal=True, want_light=False, per_sample=False, save=None):
         """Main pass + compositing.  z [R,N+1].  Returns dict of per-ray tensors (+ per-sample ones if asked)."""

@@ -19,6 +19,8 @@
 // correct version and is deliberately un-fused — DESIGN.md lists fusing it onto tcgen05 as the next step.)
 #include <stdlib.h>
 #include "common.cuh"
+#include "tc_bwd.cuh"
+#include "wgrad_planes.cuh"
 
 namespace i2sdf {
 
@@ -674,6 +676,86 @@ int launch_composite_backward(const i2sdf_handle* h, const float* z, const float
     C.o_sdf = o_sdf; C.o_rgb = o_rgb; C.o_grad = o_grad; C.o_lmask = o_lmask; C.o_beta = o_beta; C.R = R; C.N = N;
     bwd::composite_bwd_kernel<<<(int)((R + 3) / 4), 128, 0, st>>>(C);
     I2SDF_CUDA_CHECK(cudaGetLastError());
+    return I2SDF_OK;
+}
+
+// ================================================================================================
+// Fused training backward on plane slots (tensor-core path): one chain kernel (mlp_tc_bwd.cu) for every per-point
+// product, one weight-gradient launch for all layers (wgrad_planes.cu), one weighted column-sum launch for the rank-1
+// pieces (sdf row of the last SDF layer, rgb head), and two tiny reductions.
+// saved: forward state written by the tensor-core main pass in save mode (planes::Layout); ws: backward workspace.
+// dW / db (SDF stack) and dWc / dbc (radiance stack; null without g_rgb) are accumulated into.
+// ================================================================================================
+size_t fused_backward_ws_bytes(const i2sdf_handle* h, long long M, bool color) {
+    planes::Layout SL = planes::make_layout(M, h->net.L - 1, h->net.Lc, color, nullptr, nullptr);
+    return SL.bwd_total() + ((size_t)M * 4 + 64) * sizeof(float);
+}
+
+int fused_backward(const i2sdf_handle* h, const bwd::PointSrc& src, long long M, void* saved, const float* s_rgb, const float* g_sdf,
+                   const float* g_grad, const float* g_rgb, float* const* dW, float* const* db, float* const* dWc, float* const* dbc, void* ws,
+                   cudaStream_t st) {
+    using namespace bwd;
+    if (M <= 0) return I2SDF_OK;
+    const NetDev& n = h->net;
+    const int L = n.L, NL = L - 1, Lc = n.Lc;
+    const bool color = g_rgb != nullptr;
+    planes::Layout SL = planes::make_layout(M, NL, Lc, color, saved, ws);
+    float* D = reinterpret_cast<float*>((uint8_t*)ws + SL.bwd_total());          // [M][4] rgb pre-sigmoid adjoints
+    int rc;
+    BwdParams p{};
+    p.pts = src.pts; p.ray_o = src.o; p.ray_d = src.d; p.zarr = src.z; p.zstride = src.zstride; p.ns = src.ns; p.M = M;
+    p.g_sdf = g_sdf; p.g_grad = g_grad; p.g_rgb = g_rgb; p.s_rgb = s_rgb; p.with_color = color ? 1 : 0;
+    p.sl = SL; p.net = n;
+    if ((rc = tc_bwd_launch(h, p, st))) return rc;
+
+    // ---- weight (+ bias) gradients: every dense product with the point index as reduction dimension
+    WgArgs a{};
+    a.ntiles = planes::ntiles(M);
+    auto job = [&](float* dst, int ld, int rows, int cols) { a.jobs[a.njobs] = WgJob{dst, ld, rows, cols}; return a.njobs++; };
+    auto term = [&](int j, size_t Poff, bool Pws, size_t Xoff, bool Xws, int xchunks, float* colsum, int ncs) {
+        a.terms[a.nterms++] = WgTerm{(Pws ? SL.wbase : SL.base) + Poff, (Xws ? SL.wbase : SL.base) + Xoff, j, xchunks, colsum, ncs};
+    };
+    for (int l = NL - 1; l >= 1; --l) {
+        const int j = job(dW[l], h->lay_in[l], h->lay_out[l], h->lay_in[l]);
+        term(j, SL.P(l), true, SL.H(l - 1), false, planes::BIG_CHUNKS, db[l], h->lay_out[l]);
+        if (g_grad) term(j, SL.Q(l), false, SL.HD(l - 1), true, planes::BIG_CHUNKS, nullptr, 0);
+    }
+    {
+        const int j = job(dW[0], h->lay_in[0], h->lay_out[0], h->lay_in[0]);
+        term(j, SL.P(0), true, SL.E(), false, planes::SMALL_CHUNKS, db[0], h->lay_out[0]);
+        if (g_grad) term(j, SL.Q(0), false, SL.ED(), true, planes::SMALL_CHUNKS, nullptr, 0);
+    }
+    if (color) {
+        int j = job(dW[L - 1] + h->lay_in[L - 1], h->lay_in[L - 1], 256, 256);            // feature rows 1..256 of the last SDF layer
+        term(j, SL.FB(), true, SL.H(NL - 1), false, planes::BIG_CHUNKS, db[L - 1] + 1, 256);
+        for (int l = Lc - 2; l >= 1; --l) {
+            j = job(dWc[l], 256, 256, 256);
+            term(j, SL.PC(l), true, SL.C(l - 1), false, planes::BIG_CHUNKS, dbc[l], 256);
+        }
+        const int kin = h->lay_in[L];                                                   // ed + 256, reference column order [PE(dir) | feat]
+        j = job(dWc[0] + n.ed, kin, 256, 256);
+        term(j, SL.PC(0), true, SL.CF(), false, planes::BIG_CHUNKS, dbc[0], 256);
+        j = job(dWc[0], kin, 256, n.ed);
+        term(j, SL.PC(0), true, SL.DV(), false, planes::DV_CHUNKS, nullptr, 0);
+    }
+    if ((rc = wgrad_planes_launch(h, a, st))) return rc;
+
+    // ---- rank-1 pieces
+    CsArgs c{};
+    c.ntiles = a.ntiles; c.M = M;
+    if (g_sdf) c.jobs[c.njobs++] = CsJob{SL.base + SL.H(NL - 1), g_sdf, 1, dW[L - 1], 256};            // dW_last[0,:] += sum sbar h~
+    if (g_grad) c.jobs[c.njobs++] = CsJob{SL.wbase + SL.HD(NL - 1), nullptr, 0, dW[L - 1], 256};        // q_last = e_sdf: += sum hdot~
+    if (color) {
+        sigmoid_adjoint3_kernel<<<blocks(M), 256, 0, st>>>(M, s_rgb, g_rgb, D);
+        I2SDF_CUDA_CHECK(cudaGetLastError());
+        for (int k = 0; k < 3; ++k) c.jobs[c.njobs++] = CsJob{SL.base + SL.C(Lc - 2), D + k, 4, dWc[Lc - 1] + (size_t)k * 256, 256};
+        if ((rc = colsum(st, M, 3, D, 4, nullptr, dbc[Lc - 1]))) return rc;
+    }
+    if ((rc = planes_colsum_launch(h, c, st))) return rc;
+    if (g_sdf) {
+        sum_kernel<<<64, 256, 0, st>>>(M, g_sdf, db[L - 1]);
+        I2SDF_CUDA_CHECK(cudaGetLastError());
+    }
     return I2SDF_OK;
 }
 

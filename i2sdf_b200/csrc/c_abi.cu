@@ -31,6 +31,9 @@ int launch_composite(const i2sdf_handle*, const float*, const float*, const floa
                      const float*, long long, int, float*, float*, float*, float*, float*, float*, cudaStream_t);
 // declared in backward.cu
 namespace bwd { struct PointSrc { const float* pts; const float* o; const float* d; const float* z; int zstride; int ns; }; }
+size_t fused_backward_ws_bytes(const i2sdf_handle*, long long, bool);
+int fused_backward(const i2sdf_handle*, const bwd::PointSrc&, long long, void*, const float*, const float*, const float*, const float*,
+                   float* const*, float* const*, float* const*, float* const*, void*, cudaStream_t);
 size_t sdf_backward_ws_floats(const i2sdf_handle*, long long);
 size_t color_backward_ws_floats(const i2sdf_handle*, long long);
 size_t light_backward_ws_floats(const i2sdf_handle*, long long);
@@ -211,6 +214,7 @@ int i2sdf_create(const i2sdf_desc* d, int device, i2sdf_handle** out) {
     h->tc = nullptr;
     h->prof = new Prof();
     h->tcmain = nullptr;
+    { const char* fe = getenv("I2SDF_FUSED_BWD"); h->fused = !(fe && fe[0] == '0'); }
     if (h->use_tc) {
         int rc = tc_create(h);
         if (rc != I2SDF_OK) { cudaFree(h->pool); free(h); return rc; }
@@ -312,21 +316,34 @@ int i2sdf_rays(i2sdf_handle* h, const float* uv, const float* pose, const float*
 }
 
 static int run_mlp(const i2sdf_handle* h, const MlpParams& p, cudaStream_t st) {
-    const bool sdf_only = !p.out_feat && !p.out_grad && !p.want_color && !p.want_light && !p.save_act;
+    const bool sdf_only = !p.out_feat && !p.out_grad && !p.want_color && !p.want_light && !p.save_act && !p.sl.base;
     ProfScope ps(h, sdf_only ? 0 : 1, st);
     if (h->use_tc && sdf_only) return tc_launch_sdf(h, p, st);
     // eval main pass (sdf + grad_x + rgb per sample, nothing saved) -> tensor-core kernel
     // (training: pre-activations + features are saved for the backward instead of the per-CTA scratch)
     if (h->tcmain && tcmain_has_full(h->tcmain) && p.out_sdf && p.out_grad && p.out_rgb && p.want_color && !p.want_light &&
-        (p.scratch || p.save_act) && ((p.save_act != nullptr) == (p.out_feat != nullptr)) && (p.ray_d || p.pts))
+        (p.scratch || p.sl.base) && !p.save_act && (p.sl.base || !p.out_feat) && (p.ray_d || p.pts))
         return tcmain_launch(h, h->tcmain, p, st);
     // sdf + features only (ImplicitNetwork.forward: mesh extraction, plots): F layers + feature layer; needs no scratch
-    if (h->tcmain && p.out_sdf && p.out_feat && !p.out_grad && !p.want_color && !p.want_light && !p.save_act && (p.ray_d || p.pts))
+    if (h->tcmain && p.out_sdf && p.out_feat && !p.out_grad && !p.want_color && !p.want_light && !p.save_act && !p.sl.base && (p.ray_d || p.pts))
         return tcmain_launch(h, h->tcmain, p, st);
     // sdf + grad_x only (eikonal points / ImplicitNetwork.gradient): F layers then the reverse sweep, no radiance stack
-    if (h->tcmain && p.out_sdf && p.out_grad && !p.want_color && !p.want_light && !p.out_feat && (p.scratch || p.save_act) && (p.ray_d || p.pts))
+    if (h->tcmain && p.out_sdf && p.out_grad && !p.want_color && !p.want_light && !p.out_feat && (p.scratch || p.sl.base) && !p.save_act && (p.ray_d || p.pts))
         return tcmain_launch(h, h->tcmain, p, st);
+    if (p.sl.base) { set_error("run_mlp: plane-slot save requested for a pass the tensor-core kernel does not cover"); return I2SDF_E_INVALID; }
     return launch_mlp_simt(h, p, st);
+}
+
+// format of the state a forward saves for the backward: 1 = plane slots (tensor-core chain kernels + fused backward),
+// 0 = fp32 pre-activations [L-1][M][256] (fp32 kernels + the layer-by-layer backward).  kind 0: main pass, 1: SDF points
+static bool planes_main(const i2sdf_handle* h) { return h->fused && h->tcmain && tcmain_has_full(h->tcmain); }
+static bool planes_sdf(const i2sdf_handle* h) { return h->fused && h->tcmain != nullptr; }
+int i2sdf_saved_format(const i2sdf_handle* h, int kind) { return h ? ((kind == 0 ? planes_main(h) : planes_sdf(h)) ? 1 : 0) : 0; }
+
+size_t i2sdf_sdf_saved_bytes(const i2sdf_handle* h, int64_t M) {
+    if (!h || M < 0) return 0;
+    if (planes_sdf(h)) return planes::make_layout(M, h->net.L - 1, h->net.Lc, false, nullptr, nullptr).saved_total();
+    return (size_t)(h->net.L - 1) * (size_t)M * 256 * sizeof(float);
 }
 
 int i2sdf_sdf_forward(i2sdf_handle* h, const float* pts, int64_t M, float* out_sdf, float* out_feat, float* out_grad,
@@ -336,7 +353,9 @@ int i2sdf_sdf_forward(i2sdf_handle* h, const float* pts, int64_t M, float* out_s
     if (M < 0 || !pts || !out_sdf) { set_error("null argument"); return I2SDF_E_INVALID; }
     MlpParams p{};
     p.pts = pts; p.M = M; p.ns = 1; p.round_idx = -1; p.beta_min = h->smp.beta_min;
-    p.out_sdf = out_sdf; p.out_feat = out_feat; p.out_grad = out_grad; p.save_act = save_act;
+    p.out_sdf = out_sdf; p.out_feat = out_feat; p.out_grad = out_grad;
+    if (save_act && planes_sdf(h) && out_grad && !out_feat) p.sl = planes::make_layout(M, h->net.L - 1, h->net.Lc, false, save_act, nullptr);
+    else p.save_act = save_act;
     if (out_grad && !save_act) {
         if (!workspace || workspace_bytes < ws_scratch_floats(h) * sizeof(float)) { set_error("sdf_forward: workspace too small"); return I2SDF_E_WORKSPACE; }
         p.scratch = (float*)workspace;
@@ -408,7 +427,9 @@ size_t i2sdf_backward_workspace_bytes(const i2sdf_handle* h, int64_t M) {
     size_t a = sdf_backward_ws_floats(h, M), b = color_backward_ws_floats(h, M), c = light_backward_ws_floats(h, M);
     size_t m = a > b ? a : b;
     m = m > c ? m : c;
-    return (m + 64) * sizeof(float);
+    m = (m + 64) * sizeof(float);
+    if (h->tcmain) { const size_t f = fused_backward_ws_bytes(h, M, planes_main(h)) + 256; m = m > f ? m : f; }
+    return m;
 }
 
 int i2sdf_points_forward(i2sdf_handle* h, const float* o, const float* d, const float* z, int64_t R, int N, float* s_sdf, float* s_grad,
@@ -419,7 +440,9 @@ int i2sdf_points_forward(i2sdf_handle* h, const float* o, const float* d, const 
     MlpParams p{};
     p.ray_o = o; p.ray_d = d; p.zarr = z; p.zstride = N + 1; p.ns = N; p.M = (long long)R * N; p.round_idx = -1; p.beta_min = h->smp.beta_min;
     p.out_sdf = s_sdf; p.out_grad = s_grad; p.out_rgb = s_rgb; p.out_light = s_light; p.out_feat = s_feat;
-    p.want_color = s_rgb != nullptr; p.want_light = s_light != nullptr; p.save_act = save_act;
+    p.want_color = s_rgb != nullptr; p.want_light = s_light != nullptr;
+    if (save_act && planes_main(h) && !s_light && s_rgb && s_grad) p.sl = planes::make_layout(p.M, h->net.L - 1, h->net.Lc, true, save_act, nullptr);
+    else p.save_act = save_act;
     if (s_grad && !save_act) {
         if (!workspace || workspace_bytes < ws_scratch_floats(h) * sizeof(float)) { set_error("points_forward: workspace too small"); return I2SDF_E_WORKSPACE; }
         p.scratch = (float*)workspace;
@@ -504,7 +527,20 @@ int i2sdf_profile_read(i2sdf_handle* h, float ms[4], int64_t launches[4]) {
 
 size_t i2sdf_saved_bytes(const i2sdf_handle* h, int64_t R, int N) {
     if (!h) return 0;
+    if (planes_main(h)) return planes::make_layout((long long)R * N, h->net.L - 1, h->net.Lc, true, nullptr, nullptr).saved_total();
     return (size_t)(h->net.L - 1) * (size_t)R * N * 256 * sizeof(float);
+}
+
+int i2sdf_fused_backward(i2sdf_handle* h, const float* pts, const float* o, const float* d, const float* z, int zstride, int ns, int64_t M,
+                         void* saved, const float* s_rgb, const float* g_sdf, const float* g_grad, const float* g_rgb, float* const* dW_sdf,
+                         float* const* db_sdf, float* const* dW_col, float* const* db_col, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h || !saved || !dW_sdf || !db_sdf || !workspace || (!pts && (!o || !d || !z))) { set_error("fused_backward: null argument"); return I2SDF_E_INVALID; }
+    if (g_rgb && (!s_rgb || !dW_col || !db_col)) { set_error("fused_backward: g_rgb needs s_rgb, dW_col, db_col"); return I2SDF_E_INVALID; }
+    if (!(g_rgb ? planes_main(h) : planes_sdf(h))) { set_error("fused_backward: this handle saves fp32 pre-activations (use i2sdf_sdf_backward / i2sdf_color_backward)"); return I2SDF_E_INVALID; }
+    if (workspace_bytes < i2sdf_backward_workspace_bytes(h, M)) { set_error("fused_backward: workspace too small"); return I2SDF_E_WORKSPACE; }
+    bwd::PointSrc S{pts, o, d, z, zstride, ns > 0 ? ns : 1};
+    ProfScope ps(h, 1, (cudaStream_t)stream, 6);
+    return fused_backward(h, S, M, saved, s_rgb, g_sdf, g_grad, g_rgb, dW_sdf, db_sdf, dW_col, db_col, workspace, (cudaStream_t)stream);
 }
 
 int i2sdf_render_forward(i2sdf_handle* h, const float* o, const float* d, const float* dnorm, const float* z, int64_t R, int N,
@@ -531,7 +567,9 @@ int i2sdf_render_forward(i2sdf_handle* h, const float* o, const float* d, const 
     p.beta_min = h->smp.beta_min;
     p.out_sdf = s_sdf; p.out_grad = s_grad; p.out_rgb = s_rgb; p.out_light = s_light;
     p.want_color = s_rgb != nullptr; p.want_light = s_light != nullptr;
-    p.save_act = (float*)save; p.scratch = scratch;
+    if (save && planes_main(h) && !s_light && s_rgb && s_grad) p.sl = planes::make_layout(p.M, h->net.L - 1, h->net.Lc, true, save, nullptr);
+    else p.save_act = (float*)save;
+    p.scratch = scratch;
     p.net = h->net;
     int rc = run_mlp(h, p, st);
     if (rc) return rc;

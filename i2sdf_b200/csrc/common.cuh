@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include "../../include/i2sdf_b200.h"
+#include "planes.cuh"
 
 namespace i2sdf {
 
@@ -64,6 +65,7 @@ struct i2sdf_handle {
     void* tc;                // opaque tcgen05 packed state (see mlp_tc.cu)
     void* prof;              // measurement hook state (c_abi.cu)
     void* tcmain;            // tcgen05 main-pass state (mlp_tc_main.cu), null if unavailable for this network
+    bool fused;              // training state travels as plane slots + fused backward (env I2SDF_FUSED_BWD=0 -> fp32 layer-wise)
 };
 
 namespace i2sdf {
@@ -102,6 +104,7 @@ struct MlpParams {
     float* out_light;
     float* save_act;          // [L-1][M][256] pre-activations (training) or null
     float* scratch;           // per-CTA [(L-1)][TM][256] when grad wanted without save_act
+    planes::Layout sl;        // tensor-core main pass in training: the saved state is plane slots (sl.base != null)
     int want_color;
     int want_light;
     NetDev net;

@@ -22,79 +22,14 @@
 // :134-140) and RenderingNetwork.forward mlp.py:208-229; Embedder embedder.py:28-38.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tc_chain.cuh"
+#include "tc_bwd.cuh"
 
 namespace i2sdf {
 namespace tc3 {
 
 using namespace tc;
-
-constexpr int TM = 128;
-constexpr int NSTAGE = 4;
-constexpr int STAGE_MAX = 16384;
-constexpr int A_CHUNKS = 36;                         // 288 columns
-constexpr int A_PART_BYTES = A_CHUNKS * TM * 16;     // 73728
-constexpr int N_EPI_WARPS = 16;
-constexpr int NTHREADS = (2 + N_EPI_WARPS) * 32;
-constexpr int MAX_OPS = 40;
-constexpr int N_READY = 9;
-constexpr uint32_t LBO_A = TM * 16, SBO = 128;
-constexpr int PART_FLOATS = 4 * 7 * TM;              // [sub][sdf, rgb x3, grad x3][row]
-constexpr size_t kSmemBytes = 1024 + 2 * (size_t)A_PART_BYTES + NSTAGE * STAGE_MAX + PART_FLOATS * 4 + 256;
-
-enum { EK_SDF_HIDDEN = 0, EK_SDF_LAST, EK_FEAT, EK_COL_HIDDEN, EK_COL_LAST, EK_REV, EK_GRAD, EK_SDF_LAST_REV };
-
-struct Op {
-    int w_off;          // byte offset into wpack
-    short ksteps;
-    short n;            // MMA N (256 or 48)
-    short kind;         // epilogue kind applied to this op's accumulator
-    short layer;        // layer index within its stack
-};
-struct OpTable {
-    const uint8_t* wpack;
-    int nops;
-    Op ops[MAX_OPS];
-};
-
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32) : "memory"); }
-
-// 16 consecutive columns (k chunks kc0, kc0+1) of one row of the next A operand, split hi / lo
-__device__ __forceinline__ void store_a16(uint8_t* A_hi, uint8_t* A_lo, int row, int kc0, const float (&hv)[16]) {
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        uint32_t h[4], lo[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) split_bf16x2(hv[s * 8 + 2 * i], hv[s * 8 + 2 * i + 1], h[i], lo[i]);
-        const uint32_t off = seg_off<TM>(row, kc0 + s);
-        *reinterpret_cast<uint4*>(A_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(A_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    }
-}
-__device__ __forceinline__ void publish_chunk(uint64_t* bar, int lane) {
-    fence_proxy_async();          // generic-proxy smem writes -> async proxy (tensor core operand reads)
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar);
-}
-
-// d embed_i / d x_c(i) and the coordinate c(i) it belongs to
-__device__ __forceinline__ float embed_jac(const float (&x)[3], int i, int mx, int& coord) {
-    if (i < 3) { coord = i; return 1.f; }
-    const int qq = i - 3, k = qq / 6, cc = qq % 3;
-    coord = cc;
-    if (k >= mx) return 0.f;
-    const float f = (float)(1 << k);
-    float s, c;
-    sincos_cw(__fmul_rn(x[cc], f), s, c);
-    return ((qq % 6) < 3) ? f * c : -f * s;
-}
-
-// softplus_100'(a) = sigmoid(100 a), from a stored pre-activation
-__device__ __forceinline__ float dsoftplus_fast(float a) {
-    const float e = ex2_approx(-fabsf(a) * 144.26950408889634f);
-    const float rr = rcp_approx(1.0f + e);
-    return (a >= 0.f) ? rr : e * rr;
-}
+using namespace chain;
 
 __device__ __forceinline__ bool round_active(const MlpParams& P) {
     if (P.round_idx <= 0) return true;
@@ -104,7 +39,7 @@ __device__ __forceinline__ bool round_active(const MlpParams& P) {
     return true;
 }
 
-template <bool FULL>
+template <bool FULL, bool SAVE>
 // 18 warps -> one scheduler hosts 5 of them: 16 K regs / 5 warps caps the kernel at 96 registers per thread
 __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, const OpTable T) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -141,58 +76,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ================= weight producer =================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int op = 0; op < T.nops; ++op) {
-                    const uint32_t sb = (uint32_t)T.ops[op].n * 64u;
-                    const uint8_t* src = T.wpack + T.ops[op].w_off;
-                    for (int ks = 0; ks < T.ops[op].ksteps; ++ks) {
-                        mbar_wait(&empty[stage], phase ^ 1);
-                        mbar_arrive_expect_tx(&full[stage], sb);
-                        bulk_g2s(ring + stage * STAGE_MAX, src + (size_t)ks * sb, sb, &full[stage]);
-                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-                    }
-                }
-            }
-        }
+        if (lane == 0) chain_producer(T, ntiles, ring, full, empty);
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t a_hi_s = smem_u32(A_hi), a_lo_s = smem_u32(A_lo), ring_s = smem_u32(ring);
-            uint32_t stage = 0, phase = 0, aphase = 0, g = 0;      // g: global op counter -> TMEM buffer g & 1
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int op = 0; op < T.nops; ++op, ++g) {
-                    const int n = T.ops[op].n;
-                    const uint32_t idesc = instr_desc_bf16(TM, n);
-                    const uint32_t lbo_b = (uint32_t)n * 16u, lo_off = (uint32_t)n * 32u;
-                    const uint32_t d_tmem = tmem_base + (g & 1u) * 256u;
-                    const int nks = T.ops[op].ksteps;
-                    for (int ks = 0; ks < nks; ++ks) {
-                        if ((ks & 1) == 0) {
-                            const int c = ks >> 1;
-                            mbar_wait(&a_ready[c], (aphase >> c) & 1u);
-                            aphase ^= (1u << c);
-                        }
-                        mbar_wait(&full[stage], phase);
-                        tc_fence_after();
-                        const uint32_t a_off = (uint32_t)ks * 2u * LBO_A;
-                        const uint32_t b_s = ring_s + stage * STAGE_MAX;
-                        const uint64_t da_hi = smem_desc(a_hi_s + a_off, LBO_A, SBO);
-                        const uint64_t da_lo = smem_desc(a_lo_s + a_off, LBO_A, SBO);
-                        const uint64_t db_hi = smem_desc(b_s, lbo_b, SBO);
-                        const uint64_t db_lo = smem_desc(b_s + lo_off, lbo_b, SBO);
-                        mma_bf16_ss(d_tmem, da_hi, db_hi, idesc, ks > 0 ? 1u : 0u);
-                        mma_bf16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
-                        mma_bf16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
-                        mma_commit(&empty[stage]);
-                        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-                    }
-                    mma_commit(&d_full[g & 1u]);
-                }
-            }
-        }
+        if (lane == 0) chain_mma(T, ntiles, tmem_base, A_hi, A_lo, ring, full, empty, a_ready, d_full);
     } else {
         // ================= epilogue warps =================
         const int q = warp & 3;
@@ -201,9 +87,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const int nsplit = 256 - net.ex;
         const float RS2 = 0.70710678118654752f;
-        // FULL: softplus'(a_l) per layer round-trips through a per-CTA scratch [l][row][256]; in training (save_act) the
-        // PRE-ACTIVATIONS a_l are written per point [l][m][256] for the backward and softplus' is recomputed from them
-        const bool save = FULL && (P.save_act != nullptr);
+        // FULL: softplus'(a_l) per layer round-trips through a per-CTA scratch [l][row][256]; in training (plane slots, P.sl)
+        // every A operand is ALSO stored per point (h~_l, q_l, features, radiance activations, encodings) for the backward
+        // chain and the weight gradients, and softplus' is recomputed from the stored h~_l
+        constexpr bool save = FULL && SAVE;       // separate instantiation: the eval kernels carry none of the slot code
+        const planes::Layout& SL = P.sl;
         uint32_t dphase = 0, g = 0;
         // point (and view direction) of this thread's row in a tile
         auto load_point = [&](long long tile, float (&x)[3], float (&dv)[3]) {
@@ -222,7 +110,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
             }
         };
         // prologue: A_0 = embedding, 48 columns: sub s writes columns 16 s .. 16 s + 15 (sub 3: nothing)
-        auto prologue = [&](const float (&x)[3]) {
+        auto prologue = [&](const float (&x)[3], long long tile) {
             if (sub < 3) {
                 float hv[16];
 #pragma unroll
@@ -230,12 +118,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                     const int i = sub * 16 + j;
                     hv[j] = (i < net.ex) ? embed_col(x, i, net.mx) : 0.f;
                 }
-                store_a16(A_hi, A_lo, row, sub * 2, hv);
+                uint8_t* g = save ? SL.base + SL.E() + planes::seg(tile * TM + row, sub * 2, planes::SMALL_CHUNKS) : nullptr;
+                store_a16(A_hi, A_lo, row, sub * 2, hv, g, (uint32_t)planes::SMALL_PLANE);
             }
             publish_chunk(&a_ready[sub >> 1], lane);
         };
         float x[3], dv[3];
-        if ((long long)blockIdx.x < ntiles) { load_point(blockIdx.x, x, dv); prologue(x); }
+        if ((long long)blockIdx.x < ntiles) { load_point(blockIdx.x, x, dv); prologue(x, blockIdx.x); }
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const long long m = tile * TM + row;
             const bool valid = m < P.M;
@@ -244,8 +133,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
             float* sig_base = nullptr;
             size_t sig_lstride = 0;
             if (FULL) {
-                if (save) { sig_base = P.save_act + (size_t)(valid ? m : 0) * 256; sig_lstride = (size_t)P.M * 256; }
-                else if (P.scratch) { sig_base = P.scratch + (size_t)blockIdx.x * (size_t)NL * TM * 256 + (size_t)row * 256; sig_lstride = (size_t)TM * 256; }
+                if (!save && P.scratch) { sig_base = P.scratch + (size_t)blockIdx.x * (size_t)NL * TM * 256 + (size_t)row * 256; sig_lstride = (size_t)TM * 256; }
             }   // sig_base stays null for the sdf + features table (no reverse sweep, nothing to keep)
 
             float head = 0.f, rgbp[3] = {0.f, 0.f, 0.f}, gacc[3] = {0.f, 0.f, 0.f};
@@ -260,7 +148,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                     // 1 MB): pull this thread's four 64-byte segments back into L2 one op ahead of their use
                     const int nk = T.ops[op + 1].kind, nl = T.ops[op + 1].layer;
                     const int src_l = (nk == EK_REV) ? nl - 1 : ((nk == EK_COL_LAST) ? NL - 1 : -1);
-                    if (src_l >= 0) {
+                    if (src_l >= 0 && sig_base) {
                         const float* pb = sig_base + (size_t)src_l * sig_lstride + (sub >> 1) * 32 + (sub & 1) * 16;
 #pragma unroll
                         for (int it = 0; it < 4; ++it) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + it * 64));
@@ -270,7 +158,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                     // the A operand is free (this tile's last MMAs are done): start the NEXT tile's first layer now, so its
                     // tensor work overlaps this tile's last epilogue
                     load_point(next_tile, xn, dvn);
-                    prologue(xn);
+                    prologue(xn, next_tile);
                 }
 #pragma unroll 1
                 for (int it = 0; it < 4; ++it) {
@@ -279,8 +167,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                     if (FULL && kind == EK_GRAD && col0 >= 48) break;
                     // global operands of this item (bias, or the softplus' row of the reverse sweep) are requested BEFORE the
                     // TMEM load so their latency overlaps it (the tcgen05.wait::ld below is a compiler barrier)
-                    float4 pre[4];
-                    {
+                    uint4 pre[4];
+                    if (FULL && save && (kind == EK_REV || kind == EK_COL_LAST)) {
+                        load_slot16(SL.base + SL.H(kind == EK_REV ? l - 1 : NL - 1) + planes::seg(m, col0 >> 3, planes::BIG_CHUNKS), pre);
+                    } else {
                         const float* psrc;
                         if (kind == EK_SDF_HIDDEN || kind == EK_SDF_LAST || kind == EK_SDF_LAST_REV) psrc = net.sdf_b[l] + col0;
                         else if (FULL && kind == EK_FEAT) psrc = net.sdf_b[net.L - 1] + col0;
@@ -289,7 +179,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                         else if (FULL && kind == EK_REV) psrc = sig_base + (size_t)(l - 1) * sig_lstride + col0;
                         else psrc = net.sdf_head;
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) pre[j4] = *reinterpret_cast<const float4*>(psrc + j4 * 4);
+                        for (int j4 = 0; j4 < 4; ++j4) pre[j4] = *reinterpret_cast<const uint4*>(psrc + j4 * 4);
                     }
                     uint32_t v[16];
                     tmem_ld16(tmem_base + lane_base + b * 256u + (uint32_t)col0, v);
@@ -298,8 +188,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                     if (kind == EK_SDF_HIDDEN || kind == EK_SDF_LAST || kind == EK_SDF_LAST_REV) {
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
-                            const float4 bb = pre[j4];
-                            const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+                            const float bv[4] = {__uint_as_float(pre[j4].x), __uint_as_float(pre[j4].y), __uint_as_float(pre[j4].z), __uint_as_float(pre[j4].w)};
                             float so[4];
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
@@ -309,15 +198,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                                 if (FULL) {
                                     const float rr = rcp_approx(1.0f + e);
                                     const float sgm = (a >= 0.f) ? rr : e * rr;                     // softplus'(a) = sigmoid(100 a)
-                                    so[u] = save ? a : sgm;
-                                    if (kind == EK_SDF_LAST_REV) {                                  // sdf + grad only: head, then straight
-                                        head = fmaf(hv[j4 * 4 + u], __ldg(net.sdf_head + col0 + j4 * 4 + u), head);   // into the reverse sweep
-                                        hv[j4 * 4 + u] = __ldg(net.sdf_head + col0 + j4 * 4 + u) * sgm;
-                                    }
+                                    so[u] = sgm;
+                                    if (kind == EK_SDF_LAST_REV) v[j4 * 4 + u] = __float_as_uint(sgm);   // the accumulator is consumed: keep softplus' there
                                 }
                             }
-                            if (FULL && sig_base && (!save || valid))
+                            if (FULL && sig_base)
                                 *reinterpret_cast<float4*>(sig_base + (size_t)l * sig_lstride + col0 + j4 * 4) = make_float4(so[0], so[1], so[2], so[3]);
+                        }
+                        if (FULL && kind == EK_SDF_LAST_REV) {
+                            // sdf + grad only: head, h_{NL-1} to its slot, then straight into the reverse sweep: q = w_sdf * softplus'
+                            if (save) store_a16(A_hi, A_lo, row, col0 >> 3, hv, SL.base + SL.H(l) + planes::seg(m, col0 >> 3, planes::BIG_CHUNKS),
+                                                (uint32_t)planes::BIG_PLANE, true, false);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float w = __ldg(net.sdf_head + col0 + j);
+                                head = fmaf(hv[j], w, head);
+                                hv[j] = w * __uint_as_float(v[j]);
+                            }
                         }
                         if (kind == EK_SDF_LAST) {
 #pragma unroll
@@ -340,7 +237,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                         const float* __restrict__ bias = (kind == EK_FEAT ? net.sdf_b[net.L - 1] : net.col_b[l]) + col0;
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
-                            const float4 bb = (kind == EK_COL_LAST) ? __ldg(reinterpret_cast<const float4*>(bias) + j4) : pre[j4];
+                            const float4 bb = (kind == EK_COL_LAST) ? __ldg(reinterpret_cast<const float4*>(bias) + j4)
+                                                                    : make_float4(__uint_as_float(pre[j4].x), __uint_as_float(pre[j4].y), __uint_as_float(pre[j4].z), __uint_as_float(pre[j4].w));
                             hv[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + bb.x;
                             hv[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + bb.y;
                             hv[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + bb.z;
@@ -369,22 +267,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                                 rgbp[2] = fmaf(hh[0], w2.x, fmaf(hh[1], w2.y, fmaf(hh[2], w2.z, fmaf(hh[3], w2.w, rgbp[2]))));
                             }
                             // reverse prologue: adjoint of a_{NL-1} = w_sdf * softplus'(a_{NL-1})
+                            if (save) {
+                                store_a16(A_hi, A_lo, row, col0 >> 3, hv, SL.base + SL.C(l) + planes::seg(m, col0 >> 3, planes::BIG_CHUNKS),
+                                          (uint32_t)planes::BIG_PLANE, true, false);          // last radiance activation: slot only
+                                slot16_values(pre, hv);                                       // h_{NL-1}
 #pragma unroll
-                            for (int j4 = 0; j4 < 4; ++j4) {
-                                const float4 w = __ldg(reinterpret_cast<const float4*>(net.sdf_head + col0) + j4);
-                                float4 s = pre[j4];
-                                if (save) { s.x = dsoftplus_fast(s.x); s.y = dsoftplus_fast(s.y); s.z = dsoftplus_fast(s.z); s.w = dsoftplus_fast(s.w); }
-                                hv[j4 * 4 + 0] = w.x * s.x; hv[j4 * 4 + 1] = w.y * s.y; hv[j4 * 4 + 2] = w.z * s.z; hv[j4 * 4 + 3] = w.w * s.w;
+                                for (int j = 0; j < 16; ++j) hv[j] = __ldg(net.sdf_head + col0 + j) * dsoftplus_from_h(hv[j]);
+                            } else {
+#pragma unroll
+                                for (int j4 = 0; j4 < 4; ++j4) {
+                                    const float4 w = __ldg(reinterpret_cast<const float4*>(net.sdf_head + col0) + j4);
+                                    hv[j4 * 4 + 0] = w.x * __uint_as_float(pre[j4].x); hv[j4 * 4 + 1] = w.y * __uint_as_float(pre[j4].y);
+                                    hv[j4 * 4 + 2] = w.z * __uint_as_float(pre[j4].z); hv[j4 * 4 + 3] = w.w * __uint_as_float(pre[j4].w);
+                                }
                             }
                         }
                     } else if (FULL && kind == EK_REV) {
                         // accumulator = adjoint of the input of SDF layer l ; next A = (that) * softplus'(a_{l-1})
                         const bool is_skip = (l == net.skip);
+                        if (save) {        // softplus'(a_{l-1}) from the stored h~_{l-1} (a skip concat stored it scaled by 1/sqrt2)
+                            slot16_values(pre, hv);
+                            const float hs = is_skip ? 144.26950408889634f * 1.41421356237309505f : 144.26950408889634f;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) hv[j] = 1.0f - ex2_approx(-hs * hv[j]);
+                        }
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
-                            float4 s = pre[j4];
-                            if (save) { s.x = dsoftplus_fast(s.x); s.y = dsoftplus_fast(s.y); s.z = dsoftplus_fast(s.z); s.w = dsoftplus_fast(s.w); }
-                            const float sv[4] = {s.x, s.y, s.z, s.w};
+                            const float sv[4] = {save ? hv[j4 * 4] : __uint_as_float(pre[j4].x), save ? hv[j4 * 4 + 1] : __uint_as_float(pre[j4].y),
+                                                 save ? hv[j4 * 4 + 2] : __uint_as_float(pre[j4].z), save ? hv[j4 * 4 + 3] : __uint_as_float(pre[j4].w)};
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 float rv = __uint_as_float(v[j4 * 4 + u]);
@@ -400,7 +310,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                                         rv = 0.f;
                                     }
                                 }
-                                hv[j4 * 4 + u] = rv * sv[u];
+                                // (columns of the skip concat's embedding part hold PE values in the h~ slot: softplus' is meaningless there)
+                                hv[j4 * 4 + u] = (rv != 0.f) ? rv * sv[u] : 0.f;
                             }
                         }
                     } else if (FULL) {   // EK_GRAD: accumulator columns 0..47 = adjoint of the embedding
@@ -418,7 +329,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                         }
                         break;
                     }
-                    store_a16(A_hi, A_lo, row, col0 >> 3, hv);
+                    {
+                        uint8_t* g = nullptr;
+                        bool keep = true;
+                        if (FULL && save) {
+                            size_t so;
+                            if (kind == EK_SDF_HIDDEN || kind == EK_SDF_LAST) so = SL.H(l);
+                            else if (kind == EK_FEAT) so = SL.CF();
+                            else if (kind == EK_COL_HIDDEN) so = SL.C(l);
+                            else if (kind == EK_REV) { so = SL.Q(l - 1); keep = valid; }
+                            else { so = SL.Q(NL - 1); keep = valid; }          // EK_COL_LAST / EK_SDF_LAST_REV: q_{NL-1}
+                            g = SL.base + so + planes::seg(m, col0 >> 3, planes::BIG_CHUNKS);
+                        }
+                        store_a16(A_hi, A_lo, row, col0 >> 3, hv, g, (uint32_t)planes::BIG_PLANE, keep);
+                    }
                     publish_chunk(&a_ready[c], lane);
                 }
                 if (FULL && kind == EK_FEAT && sub < 2 && op < T.nops - 1) {
@@ -429,7 +353,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                         const int i = sub * 16 + j;
                         hv[j] = (i < net.ed) ? embed_col(dv, i, net.md) : 0.f;
                     }
-                    store_a16(A_hi, A_lo, row, 32 + sub * 2, hv);
+                    uint8_t* g = save ? SL.base + SL.DV() + planes::seg(m, sub * 2, planes::DV_CHUNKS) : nullptr;
+                    store_a16(A_hi, A_lo, row, 32 + sub * 2, hv, g, (uint32_t)(planes::DV_CHUNKS * planes::SUB_CHUNK));
                     publish_chunk(&a_ready[8], lane);
                 }
             }
@@ -508,6 +433,8 @@ struct State {
     OpTable full;             // nops == 0 if the full main pass is unavailable for this network
     OpTable sg;               // SDF + grad_x only (eikonal points): F_0..F_{NL-1}, R_{NL-1}..R_0
     OpTable sf;               // SDF + features (ImplicitNetwork.forward: meshing / plots): F_0..F_{NL-1}, G
+    OpTable bwd_full;         // training backward chain (mlp_tc_bwd.cu): T_0..T_{NL-1}, CR.., CR_0, PF, P_{NL-1}..P_1
+    OpTable bwd_sdf;          // same without the radiance stack (eikonal points): T.., PF, P..
     int src_layer[MAX_OPS];   // packing recipe per op of the full table
     int mode[MAX_OPS], row_off[MAX_OPS], feat_first[MAX_OPS];
     int n_pack;               // number of ops to pack
@@ -563,8 +490,24 @@ int tc_create(i2sdf_handle* h) {
     s->sf.nops = 0;
     for (int l = 0; l < NL; ++l) s->sf.ops[s->sf.nops++] = T.ops[s->blk_fwd_sdf[l]];
     s->sf.ops[s->sf.nops++] = T.ops[s->blk_fwd_feat];
-    cudaError_t e = cudaFuncSetAttribute(tc_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    // backward chains reuse the forward / reverse blocks: tangent = forward SDF blocks, adjoints = W^T blocks
+    for (int variant = 0; variant < 2; ++variant) {
+        OpTable& B = variant == 0 ? s->bwd_full : s->bwd_sdf;
+        B.wpack = s->wpack;
+        B.nops = 0;
+        auto push = [&](int idx, int kind, int layer) { B.ops[B.nops] = T.ops[idx]; B.ops[B.nops].kind = (short)kind; B.ops[B.nops].layer = (short)layer; ++B.nops; };
+        for (int l = 0; l < NL; ++l) push(s->blk_fwd_sdf[l], tcb::BK_TAN, l);
+        if (variant == 0) {
+            for (int l = Lc - 2; l >= 1; --l) push(s->blk_rev_col[l], tcb::BK_COL_REV, l);
+            push(s->blk_rev_col[0], tcb::BK_FEAT_ADJ, 0);
+        }
+        push(s->blk_rev_feat, tcb::BK_P, NL - 1);
+        for (int l = NL - 1; l >= 1; --l) push(s->blk_rev_sdf[l], tcb::BK_P, l - 1);
+        if (variant == 0 && !want_full) B.nops = 0;
+    }
+    cudaError_t e = cudaFuncSetAttribute(tc_mlp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_mlp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_mlp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) { cudaFree(s->wpack); delete s; set_error("tc_create: smem attribute: %s", cudaGetErrorString(e)); return I2SDF_E_CUDA; }
     h->tc = s;
     h->tcmain = (void*)s;     // full main pass only if s->full.nops > 0 (tcmain_has_full)
@@ -600,6 +543,12 @@ static inline int tc_grid(const i2sdf_handle* h, long long M) {
     return (int)(ntiles < (long long)h->num_sms ? ntiles : (long long)h->num_sms);
 }
 
+const chain::OpTable* tc_bwd_table(const i2sdf_handle* h, bool with_color) {
+    const tc3::State* s = (const tc3::State*)h->tc;
+    if (!s) return nullptr;
+    return with_color ? &s->bwd_full : &s->bwd_sdf;
+}
+
 TcBlock tc_block(const i2sdf_handle* h, int role, int layer) {
     using namespace tc3;
     TcBlock b{nullptr, 0, 0};
@@ -624,7 +573,7 @@ int tc_launch_sdf(const i2sdf_handle* h, const MlpParams& p, cudaStream_t st) {
     using namespace tc3;
     if (p.M <= 0) return I2SDF_OK;
     const State* s = (const State*)h->tc;
-    tc_mlp_kernel<false><<<tc_grid(h, p.M), NTHREADS, kSmemBytes, st>>>(p, s->sdf);
+    tc_mlp_kernel<false, false><<<tc_grid(h, p.M), NTHREADS, kSmemBytes, st>>>(p, s->sdf);
     I2SDF_CUDA_CHECK(cudaGetLastError());
     return I2SDF_OK;
 }
@@ -639,7 +588,8 @@ int tcmain_launch(const i2sdf_handle* h, void* state, const MlpParams& p, cudaSt
     if (p.M <= 0) return I2SDF_OK;
     const State* s = (const State*)state;
     const OpTable& tab = p.want_color ? s->full : (p.out_grad ? s->sg : s->sf);
-    tc_mlp_kernel<true><<<tc_grid(h, p.M), NTHREADS, kSmemBytes, st>>>(p, tab);
+    if (p.sl.base) tc_mlp_kernel<true, true><<<tc_grid(h, p.M), NTHREADS, kSmemBytes, st>>>(p, tab);
+    else tc_mlp_kernel<true, false><<<tc_grid(h, p.M), NTHREADS, kSmemBytes, st>>>(p, tab);
     I2SDF_CUDA_CHECK(cudaGetLastError());
     return I2SDF_OK;
 }

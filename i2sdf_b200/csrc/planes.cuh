@@ -40,48 +40,42 @@ __host__ __device__ inline long long ntiles(long long M) { return (M + TM - 1) /
 __host__ __device__ inline size_t big_slot_bytes(long long M) { return (size_t)ntiles(M) * BIG_TILE; }
 __host__ __device__ inline size_t small_slot_bytes(long long M) { return (size_t)ntiles(M) * SMALL_TILE; }
 
-// ---- slot directory of one saved forward state (byte offsets from the base of the buffer) ----------------------
-// forward (written by tc3::tc_mlp_kernel<true> in save mode):
-//   H[l]  l = 0..NL-1 : input of SDF layer l+1  = h~_l  (skip concat and 1/sqrt2 applied)
-//   Q[l]  l = 0..NL-1 : adjoint of a_l in the reverse sweep = softplus'(a_l) * (W_{l+1}^T q_{l+1})       (rows >= M zero)
+// ---- slot directory (byte offsets) ---------------------------------------------------------------------------------
+// saved forward state (written by tc3::tc_mlp_kernel<true> in save mode), NL = SDF hidden layers, Lc = radiance layers:
+//   H(l)  l = 0..NL-1 : input of SDF layer l+1  = h~_l  (skip concat and 1/sqrt2 applied)
+//   Q(l)  l = 0..NL-1 : adjoint of a_l in the reverse sweep = softplus'(a_l) * (W_{l+1}^T q_{l+1})       (rows >= M zero)
 //   E                 : PE(x), 48 columns (input of SDF layer 0)
-//   CF, C[0..Lc-2]    : radiance stack: features (input of layer 0), post-ReLU hidden activations
-//   DV                : PE(view dir), 48 columns
+//   CF, C(0..Lc-2)    : radiance stack: features (input of layer 0), post-ReLU hidden activations
+//   DV                : PE(view dir), 32 columns
 // backward workspace (written by tcb::tc_bwd_kernel):
-//   HD[l] : tangent h~dot_l ; P[l] : adjoint p_l ; ED : tangent of PE(x) ; FB : adjoint of the features ;
-//   PC[l] : adjoint of the radiance pre-activations
-struct SavedDir {
-    size_t H[12], Q[12], E, CF, C[12], DV, total;
+//   HD(l) : tangent h~dot_l ; P(l) : adjoint p_l ; ED : tangent of PE(x) ; FB : adjoint of the features ;
+//   PC(l) : adjoint of the radiance pre-activations
+constexpr int DV_CHUNKS = 4;
+struct Layout {
+    uint8_t* base;      // saved forward state (null: nothing is saved)
+    uint8_t* wbase;     // backward workspace
+    size_t big, small, dvb;
+    int NL, Lc, color;
+    __host__ __device__ size_t H(int l) const { return (size_t)l * big; }
+    __host__ __device__ size_t Q(int l) const { return (size_t)(NL + l) * big; }
+    __host__ __device__ size_t E() const { return (size_t)2 * NL * big; }
+    __host__ __device__ size_t CF() const { return E() + small; }
+    __host__ __device__ size_t C(int l) const { return CF() + (size_t)(1 + l) * big; }
+    __host__ __device__ size_t DV() const { return CF() + (size_t)Lc * big; }
+    __host__ __device__ size_t saved_total() const { return color ? DV() + dvb : E() + small; }
+    __host__ __device__ size_t HD(int l) const { return (size_t)l * big; }
+    __host__ __device__ size_t P(int l) const { return (size_t)(NL + l) * big; }
+    __host__ __device__ size_t ED() const { return (size_t)2 * NL * big; }
+    __host__ __device__ size_t FB() const { return ED() + small; }
+    __host__ __device__ size_t PC(int l) const { return FB() + (size_t)(1 + l) * big; }
+    __host__ __device__ size_t bwd_total() const { return FB() + (size_t)(color ? Lc : 1) * big; }
 };
-struct BwdDir {
-    size_t HD[12], P[12], ED, FB, PC[12], total;
-};
-inline SavedDir saved_dir(long long M, int NL, int Lc, bool with_color) {
-    SavedDir d{};
-    size_t off = 0;
-    const size_t big = big_slot_bytes(M), small = small_slot_bytes(M);
-    for (int l = 0; l < NL; ++l) { d.H[l] = off; off += big; }
-    for (int l = 0; l < NL; ++l) { d.Q[l] = off; off += big; }
-    d.E = off; off += small;
-    if (with_color) {
-        d.CF = off; off += big;
-        for (int l = 0; l < Lc - 1; ++l) { d.C[l] = off; off += big; }
-        d.DV = off; off += small;
-    }
-    d.total = off;
-    return d;
-}
-inline BwdDir bwd_dir(long long M, int NL, int Lc, bool with_color) {
-    BwdDir d{};
-    size_t off = 0;
-    const size_t big = big_slot_bytes(M), small = small_slot_bytes(M);
-    for (int l = 0; l < NL; ++l) { d.HD[l] = off; off += big; }
-    for (int l = 0; l < NL; ++l) { d.P[l] = off; off += big; }
-    d.ED = off; off += small;
-    d.FB = off; off += big;
-    if (with_color) for (int l = 0; l < Lc - 1; ++l) { d.PC[l] = off; off += big; }
-    d.total = off;
-    return d;
+inline Layout make_layout(long long M, int NL, int Lc, bool color, void* base, void* wbase) {
+    Layout L{};
+    L.base = (uint8_t*)base; L.wbase = (uint8_t*)wbase;
+    L.big = big_slot_bytes(M); L.small = small_slot_bytes(M); L.dvb = (size_t)ntiles(M) * 4 * 2 * DV_CHUNKS * SUB_CHUNK;
+    L.NL = NL; L.Lc = Lc; L.color = color ? 1 : 0;
+    return L;
 }
 
 }  // namespace planes

@@ -1,0 +1,36 @@
+// Backward chain kernel (mlp_tc_bwd.cu): parameters, op kinds, host entry points.
+#pragma once
+#include "common.cuh"
+
+namespace i2sdf {
+
+namespace chain { struct OpTable; }
+
+namespace tcb {
+// epilogue kinds of the backward op tables (built in tc_create, mlp_tc3.cu)
+enum { BK_TAN = 0, BK_COL_REV, BK_FEAT_ADJ, BK_P };
+}
+
+struct BwdParams {
+    // point source (as MlpParams): explicit pts, or rays: point m = (ray m / ns, sample m % ns) -> o + z * d
+    const float* pts;
+    const float* ray_o;
+    const float* ray_d;
+    const float* zarr;
+    int zstride;
+    int ns;
+    long long M;
+    // upstream gradients per point (null = 0)
+    const float* g_sdf;    // [M]
+    const float* g_grad;   // [M][3]   upstream of grad_x sdf
+    const float* g_rgb;    // [M][3]   (with_color)
+    const float* s_rgb;    // [M][3]   forward rgb (sigmoid output), for its derivative
+    int with_color;
+    planes::Layout sl;     // saved forward slots (sl.base) + backward workspace slots (sl.wbase)
+    NetDev net;
+};
+
+const chain::OpTable* tc_bwd_table(const i2sdf_handle* h, bool with_color);
+int tc_bwd_launch(const i2sdf_handle* h, const BwdParams& p, cudaStream_t st);
+
+}  // namespace i2sdf

@@ -1,0 +1,161 @@
+// Shared skeleton of the tensor-core "chain" kernels (forward mlp_tc3.cu, backward mlp_tc_bwd.cu): a resident tile of 128
+// points walks through a table of dense ops; warp 0 streams the packed weight blocks of each op through a 4-stage SMEM
+// ring, warp 1 issues 3 tcgen05.mma per k step (A_hi W_hi + A_lo W_hi + A_hi W_lo) into one of two TMEM accumulators, 16
+// epilogue warps turn accumulator g into the A operand of op g+1 in 16-column work items and publish 32-column chunks.
+#pragma once
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace i2sdf {
+namespace chain {
+
+using namespace tc;
+
+constexpr int TM = 128;
+constexpr int NSTAGE = 4;
+constexpr int STAGE_MAX = 16384;
+constexpr int A_CHUNKS = 36;                         // 288 columns
+constexpr int A_PART_BYTES = A_CHUNKS * TM * 16;     // 73728
+constexpr int N_EPI_WARPS = 16;
+constexpr int NTHREADS = (2 + N_EPI_WARPS) * 32;
+constexpr int MAX_OPS = 40;
+constexpr int N_READY = 9;
+constexpr uint32_t LBO_A = TM * 16, SBO = 128;
+constexpr int PART_FLOATS = 4 * 7 * TM;              // [sub][sdf, rgb x3, grad x3][row]
+constexpr size_t kSmemBytes = 1024 + 2 * (size_t)A_PART_BYTES + NSTAGE * STAGE_MAX + PART_FLOATS * 4 + 256;
+
+enum { EK_SDF_HIDDEN = 0, EK_SDF_LAST, EK_FEAT, EK_COL_HIDDEN, EK_COL_LAST, EK_REV, EK_GRAD, EK_SDF_LAST_REV };
+
+struct Op {
+    int w_off;          // byte offset into wpack
+    short ksteps;
+    short n;            // MMA N (256 or 48)
+    short kind;         // epilogue kind applied to this op's accumulator
+    short layer;        // layer index within its stack
+};
+struct OpTable {
+    const uint8_t* wpack;
+    int nops;
+    Op ops[MAX_OPS];
+};
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32) : "memory"); }
+
+// 16 consecutive columns (k chunks kc0, kc0+1) of one row of the next A operand, split hi / lo.
+// g (optional): HI segment of chunk kc0 of this thread's point in a plane slot (planes.cuh), g_lo = byte distance to the LO
+// plane: the same split values are stored there (zeros if !keep: adjoint slots of rows beyond M).
+__device__ __forceinline__ void store_a16(uint8_t* A_hi, uint8_t* A_lo, int row, int kc0, const float (&hv)[16], uint8_t* g = nullptr,
+                                          uint32_t g_lo = 0, bool keep = true, bool to_smem = true) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        uint32_t h[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_bf16x2(hv[s * 8 + 2 * i], hv[s * 8 + 2 * i + 1], h[i], lo[i]);
+        if (to_smem) {
+            const uint32_t off = seg_off<TM>(row, kc0 + s);
+            *reinterpret_cast<uint4*>(A_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(A_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        if (g) {
+            uint8_t* gs = g + s * planes::SUB_CHUNK;
+            *reinterpret_cast<uint4*>(gs) = keep ? make_uint4(h[0], h[1], h[2], h[3]) : make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(gs + g_lo) = keep ? make_uint4(lo[0], lo[1], lo[2], lo[3]) : make_uint4(0, 0, 0, 0);
+        }
+    }
+}
+// 16 columns of a 256-column slot back as fp32: seg = HI segment of the first chunk
+__device__ __forceinline__ void load_slot16(const uint8_t* seg, uint4 (&raw)[4]) {
+    raw[0] = *reinterpret_cast<const uint4*>(seg);
+    raw[1] = *reinterpret_cast<const uint4*>(seg + planes::SUB_CHUNK);
+    raw[2] = *reinterpret_cast<const uint4*>(seg + planes::BIG_PLANE);
+    raw[3] = *reinterpret_cast<const uint4*>(seg + planes::BIG_PLANE + planes::SUB_CHUNK);
+}
+__device__ __forceinline__ void slot16_values(const uint4 (&raw)[4], float (&out)[16]) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const uint32_t hw[4] = {raw[s].x, raw[s].y, raw[s].z, raw[s].w}, lw[4] = {raw[2 + s].x, raw[2 + s].y, raw[2 + s].z, raw[2 + s].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            out[s * 8 + 2 * i] = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
+            out[s * 8 + 2 * i + 1] = __uint_as_float(hw[i] & 0xffff0000u) + __uint_as_float(lw[i] & 0xffff0000u);
+        }
+    }
+}
+// softplus_100'(a) = 1 - exp(-100 softplus_100(a)), from a stored activation h = softplus_100(a)
+__device__ __forceinline__ float dsoftplus_from_h(float h) { return 1.0f - ex2_approx(-144.26950408889634f * h); }
+__device__ __forceinline__ void publish_chunk(uint64_t* bar, int lane) {
+    fence_proxy_async();          // generic-proxy smem writes -> async proxy (tensor core operand reads)
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
+
+// d embed_i / d x_c(i) and the coordinate c(i) it belongs to
+__device__ __forceinline__ float embed_jac(const float (&x)[3], int i, int mx, int& coord) {
+    if (i < 3) { coord = i; return 1.f; }
+    const int qq = i - 3, k = qq / 6, cc = qq % 3;
+    coord = cc;
+    if (k >= mx) return 0.f;
+    const float f = (float)(1 << k);
+    float s, c;
+    sincos_cw(__fmul_rn(x[cc], f), s, c);
+    return ((qq % 6) < 3) ? f * c : -f * s;
+}
+
+
+// ---- warp 0, lane 0: weight producer --------------------------------------------------------------------------------
+__device__ __forceinline__ void chain_producer(const OpTable& T, long long ntiles, uint8_t* ring, uint64_t* full, uint64_t* empty) {
+    uint32_t stage = 0, phase = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int op = 0; op < T.nops; ++op) {
+            const uint32_t sb = (uint32_t)T.ops[op].n * 64u;
+            const uint8_t* src = T.wpack + T.ops[op].w_off;
+            for (int ks = 0; ks < T.ops[op].ksteps; ++ks) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                mbar_arrive_expect_tx(&full[stage], sb);
+                bulk_g2s(ring + stage * STAGE_MAX, src + (size_t)ks * sb, sb, &full[stage]);
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+        }
+    }
+}
+
+// ---- warp 1, lane 0: MMA issuer (waits per 32-column chunk of the A operand, commits per op) ---------------------------
+__device__ __forceinline__ void chain_mma(const OpTable& T, long long ntiles, uint32_t tmem_base, uint8_t* A_hi, uint8_t* A_lo, uint8_t* ring,
+                                          uint64_t* full, uint64_t* empty, uint64_t* a_ready, uint64_t* d_full) {
+    const uint32_t a_hi_s = smem_u32(A_hi), a_lo_s = smem_u32(A_lo), ring_s = smem_u32(ring);
+    uint32_t stage = 0, phase = 0, aphase = 0, g = 0;      // g: global op counter -> TMEM buffer g & 1
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int op = 0; op < T.nops; ++op, ++g) {
+            const int n = T.ops[op].n;
+            const uint32_t idesc = instr_desc_bf16(TM, n);
+            const uint32_t lbo_b = (uint32_t)n * 16u, lo_off = (uint32_t)n * 32u;
+            const uint32_t d_tmem = tmem_base + (g & 1u) * 256u;
+            const int nks = T.ops[op].ksteps;
+            for (int ks = 0; ks < nks; ++ks) {
+                if ((ks & 1) == 0) {
+                    const int c = ks >> 1;
+                    mbar_wait(&a_ready[c], (aphase >> c) & 1u);
+                    aphase ^= (1u << c);
+                }
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t a_off = (uint32_t)ks * 2u * LBO_A;
+                const uint32_t b_s = ring_s + stage * STAGE_MAX;
+                const uint64_t da_hi = smem_desc(a_hi_s + a_off, LBO_A, SBO);
+                const uint64_t da_lo = smem_desc(a_lo_s + a_off, LBO_A, SBO);
+                const uint64_t db_hi = smem_desc(b_s, lbo_b, SBO);
+                const uint64_t db_lo = smem_desc(b_s + lo_off, lbo_b, SBO);
+                mma_bf16_ss(d_tmem, da_hi, db_hi, idesc, ks > 0 ? 1u : 0u);
+                mma_bf16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
+                mma_bf16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
+                mma_commit(&empty[stage]);
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+            mma_commit(&d_full[g & 1u]);
+        }
+    }
+}
+
+}  // namespace chain
+}  // namespace i2sdf

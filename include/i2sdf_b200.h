@@ -212,6 +212,25 @@ int i2sdf_sdf_backward(i2sdf_handle* h, const float* const* W, const float* pts,
 int i2sdf_profile_enable(i2sdf_handle* h, int enable);
 int i2sdf_profile_read(i2sdf_handle* h, float ms[4], int64_t launches[4]);
 
+/* What a forward in training mode saves for the backward.  format 1 = plane slots (tensor-core chain kernels; consumed
+ * by i2sdf_fused_backward), 0 = fp32 pre-activations [L-1][M][256] (fp32 kernels; consumed by i2sdf_sdf_backward /
+ * i2sdf_color_backward).  kind 0: main pass (i2sdf_points_forward / i2sdf_render_forward, size i2sdf_saved_bytes),
+ * kind 1: stand-alone SDF points (i2sdf_sdf_forward with out_grad, size i2sdf_sdf_saved_bytes). */
+int i2sdf_saved_format(const i2sdf_handle* h, int kind);
+size_t i2sdf_sdf_saved_bytes(const i2sdf_handle* h, int64_t M);
+
+/* Fused backward of the per-point networks on plane slots: the tangent pass of the SDF stack along g_grad, the
+ * reverse passes of the radiance and SDF stacks, all weight and bias gradients — what loss.backward() runs through
+ * ImplicitNetwork (mlp.py:84-143, incl. the second-order graph) and RenderingNetwork (mlp.py:208-229) in the reference.
+ * Points as in i2sdf_sdf_backward.  saved: the buffer the forward filled (format 1).  g_sdf [M], g_grad [M,3],
+ * g_rgb [M,3] upstream (NULL = 0; g_rgb NULL: SDF stack only, e.g. eikonal points); s_rgb [M,3] forward rgb.
+ * dW_sdf / db_sdf / dW_col / db_col: per-layer gradient buffers in API order, ACCUMULATED into.
+ * workspace >= i2sdf_backward_workspace_bytes(h, M). */
+int i2sdf_fused_backward(i2sdf_handle* h, const float* pts, const float* o, const float* d, const float* z, int zstride,
+                         int ns, int64_t M, void* saved, const float* s_rgb, const float* g_sdf, const float* g_grad,
+                         const float* g_rgb, float* const* dW_sdf, float* const* db_sdf, float* const* dW_col,
+                         float* const* db_col, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Plane slots: the HBM format of the fused training path (bf16 hi + lo planes per 128-point tile in the tensor
  * cores' SMEM layout, i2sdf_b200/csrc/planes.cuh).  pack / unpack convert from / to plain fp32 [M][ld] arrays
  * (columns = 256 or 48); planes_wgrad is the weight-gradient kernel on its own:

@@ -413,3 +413,113 @@ def test_planes_roundtrip_and_wgrad(cases):
         dWE = core.planes_wgrad([sP0], [sE], M, 256, 39, x_columns=48)
         scaleE = r(P0).abs().T @ E.double().abs()
         assert ((dWE.double() - refE).abs() / scaleE).max() < 3e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused training path: forward-saved slots and the chain backward against plain torch autograd on the same weights
+# ---------------------------------------------------------------------------------------------------------------
+def _torch_stacks(m, x, dirs):
+    """fp64 torch restatement of the two stacks with the model's effective weights (mlp.py:84-105, :208-229).
+    Returns sdf, feat, grad_x (create_graph), rgb and the hidden activations h~_l (inputs of SDF layers 1..)."""
+    Ws, bs = m.effective_weights()
+    n_sdf = m.implicit_network.num_layers - 1
+    W = [w.detach().double().requires_grad_(True) for w in Ws]
+    b = [t.detach().double().requires_grad_(True) for t in bs]
+    x = x.double().requires_grad_(True)
+    mx, md = m.implicit_network.multires, m.rendering_network.multires
+
+    def pe(v, L):
+        out = [v]
+        for k in range(L):
+            out += [torch.sin(v * 2.0 ** k), torch.cos(v * 2.0 ** k)]
+        return torch.cat(out, -1)
+    e = pe(x, mx)
+    h, hs = e, []
+    skip = m.implicit_network.skip_in[0] if m.implicit_network.skip_in else -1
+    for l in range(n_sdf):
+        if l == skip:
+            h = torch.cat([h, e], -1) / 2 ** 0.5
+            hs[-1] = h
+        a = h @ W[l].T + b[l]
+        if l < n_sdf - 1:
+            h = torch.nn.functional.softplus(a, beta=100)
+            hs.append(h)
+    sdf, feat = a[:, 0], a[:, 1:]
+    grad = torch.autograd.grad(sdf.sum(), x, create_graph=True)[0]
+    c = torch.cat([pe(dirs.double(), md), feat], -1)
+    for l in range(n_sdf, len(W)):
+        c = c @ W[l].T + b[l]
+        if l < len(W) - 1:
+            c = torch.relu(c)
+    return dict(sdf=sdf, feat=feat, grad=grad, rgb=torch.sigmoid(c), hs=hs, W=W, b=b)
+
+
+def test_forward_saved_slots_and_fused_backward_vs_torch(cases):
+    from i2sdf_b200.autograd import _PointsFn
+    c = cases["eval_synthetic_soft"]
+    m = _model(c, training=True)
+    core = m._ready_core()
+    if not core.fused_main:
+        pytest.skip("fused tensor-core training path not active")
+    g = torch.Generator().manual_seed(3)
+    R, N = 37, 9                                   # M = 333: 2 full tiles + a ragged one
+    o = ((torch.rand(R, 3, generator=g) - 0.5) * 1.0).cuda()
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=1).cuda()
+    z = torch.sort(torch.rand(R, N + 1, generator=g) * 1.5, dim=1)[0].cuda()
+    M = R * N
+    x = (o[:, None, :] + z[:, :N, None] * d[:, None, :]).reshape(M, 3)
+    dirs = d[:, None, :].expand(R, N, 3).reshape(M, 3)
+    ref = _torch_stacks(m, x, dirs)
+    Ws, bs = m.effective_weights()
+    n_sdf, n_col = m.implicit_network.num_layers - 1, m.rendering_network.num_layers - 1
+    params = [w.detach().contiguous().requires_grad_(True) for w in Ws] + [t.detach().clone().requires_grad_(True) for t in bs]
+    P = params[:n_sdf] + params[n_sdf + n_col:2 * n_sdf + n_col] + params[n_sdf:n_sdf + n_col] + params[2 * n_sdf + n_col:]
+    s_sdf, s_grad, s_rgb, _ = _PointsFn.apply(core, o, d, z, True, n_sdf, n_col, 0, *P)
+    assert relerr(s_sdf, ref["sdf"].float()) < TOL and relerr(s_rgb, ref["rgb"].float()) < TOL and relerr(s_grad, ref["grad"].float()) < 3e-4
+    # saved H slots = inputs of SDF layers 1.. ; slot l lives at l * slot_bytes
+    saved = s_sdf.grad_fn.saved_tensors[3]
+    big = core.lib.i2sdf_planes_slot_bytes(M, 256)
+    for l, h_ref in enumerate(ref["hs"]):
+        mine = core.planes_unpack(saved[l * big:(l + 1) * big], M)
+        assert relerr(mine, h_ref.float()) < 1e-4, (l, relerr(mine, h_ref.float()))
+    # backward: random upstreams on all three outputs -> every weight / bias gradient, first and second order
+    us, ug, ur = (torch.randn(M, generator=g).cuda(), torch.randn(M, 3, generator=g).cuda() * 0.1, torch.randn(M, 3, generator=g).cuda())
+    (s_sdf * us).sum().add((s_grad * ug).sum()).add((s_rgb * ur).sum()).backward()
+    lref = (ref["sdf"] * us.double()).sum() + (ref["grad"] * ug.double()).sum() + (ref["rgb"] * ur.double()).sum()
+    gref = torch.autograd.grad(lref, ref["W"] + ref["b"])
+    nW = len(ref["W"])
+    mine = params[:nW] + params[nW:]
+    worst = 0.0
+    for i, (p, gr) in enumerate(zip(mine, gref)):
+        assert p.grad is not None, i
+        e = float((p.grad.double() - gr).norm() / gr.norm().clamp(min=1e-30))
+        worst = max(worst, e)
+        assert e < 2e-3, (i, "W" if i < nW else "b", e)
+    print(f"fused backward vs torch fp64 autograd: worst relative L2 gradient error {worst:.2e}")
+
+
+def test_fused_sdf_points_backward_vs_torch(cases):
+    """Eikonal-style points: sdf + grad_x only, second order through the fused chain without the radiance stack."""
+    from i2sdf_b200.autograd import _SdfPointsFn
+    c = cases["eval_synthetic_soft"]
+    m = _model(c, training=True)
+    core = m._ready_core()
+    if not core.fused_sdf:
+        pytest.skip("fused tensor-core training path not active")
+    g = torch.Generator().manual_seed(4)
+    M = 300
+    x = ((torch.rand(M, 3, generator=g) - 0.5) * 2.0).cuda()
+    ref = _torch_stacks(m, x, torch.zeros(M, 3).cuda() + 0.5)
+    Ws, bs = m.effective_weights()
+    n_sdf = m.implicit_network.num_layers - 1
+    W = [w.detach().contiguous().requires_grad_(True) for w in Ws[:n_sdf]]
+    b = [t.detach().clone().requires_grad_(True) for t in bs[:n_sdf]]
+    sdf, grad = _SdfPointsFn.apply(core, x, True, n_sdf, *W, *b)
+    assert relerr(sdf, ref["sdf"].float()) < TOL and relerr(grad, ref["grad"].float()) < 3e-4
+    us, ug = torch.randn(M, generator=g).cuda(), torch.randn(M, 3, generator=g).cuda()
+    ((sdf * us).sum() + (grad * ug).sum()).backward()
+    lref = (ref["sdf"] * us.double()).sum() + (ref["grad"] * ug.double()).sum()
+    gref = torch.autograd.grad(lref, ref["W"][:n_sdf] + ref["b"][:n_sdf])
+    for i, (p, gr) in enumerate(zip(W + b, gref)):
+        e = float((p.grad.double() - gr).norm() / gr.norm().clamp(min=1e-30))
+        assert e < 2e-3, (i, e)
