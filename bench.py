@@ -359,7 +359,8 @@ def gpu_arm(args, rank, world, local_rank):
         workload = ("C2: training step on a 1024-ray batch, config/synthetic.yml networks and loss weights "
                     "(rgb L1 + eikonal + depth + normal/angular; steps < 50k: no bubble/smooth terms): forward "
                     "(error-bounded sampler 5x128 sdf-evals/ray, main pass on 97 samples/ray with saved activations, 3R eikonal "
-                    "points) + I2SDFLoss + backward incl. second-order terms + Adam(eps=1e-15) step + weight re-pack"
+                    "points) + I2SDFLoss + backward incl. second-order terms (fused tensor-core chain + one weight-gradient launch) "
+                    "+ Adam(eps=1e-15) step + weight re-pack"
                     + (" + one flat NCCL gradient all-reduce" if world > 1 else ""))
     else:
         workload = ("C2/C3 batch shape: 1024-ray forward render, config/synthetic.yml networks (8x256 SDF + 4x256 radiance), "
@@ -374,7 +375,8 @@ def gpu_arm(args, rank, world, local_rank):
                    "rays_per_gpu": R, "global_rays": world * R, "samples_per_ray_composited": N_COMPOSITED,
                    "sdf_evals_per_ray": 5 * 128 + N_COMPOSITED,
                    "parallelism": f"ray-sharded x{world}, " + ("one flat gradient all-reduce per step" if train else "no collective (inference)"),
-                   "tensor_cores": {"sampler_sdf": core.uses_tensor_cores, "main_pass": core.uses_tensor_cores_main and not train},
+                   "tensor_cores": {"sampler_sdf": core.uses_tensor_cores, "main_pass": core.uses_tensor_cores_main,
+                                    "backward": bool(train and core.fused_main)},
                    "l2": "flushed between timed iterations (256 MB write)", "timing": "CUDA events per step, max over ranks"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
@@ -388,6 +390,22 @@ def gpu_arm(args, rank, world, local_rank):
                      "note": "achieved counts ALGORITHMIC flops (1 MAC = 2 flop); the kernel issues 3 bf16 MMAs per MAC, so 1/3 of the bf16 peak is this precision scheme's ceiling"},
         "clocks": clocks,
     }
+    if train and core.fused_main and prof["weight_grads"]["launches"] > 0:
+        # the two other heavy kernels of the training step, both bounded by HBM: algorithmic bytes = plane slots read / written
+        tile = lambda m: (m + 127) // 128                                                     # noqa: E731
+        big = lambda m: tile(m) * 131072                                                      # noqa: E731
+        m_main, m_eik = R * N_COMPOSITED, 3 * R
+        wg_bytes = (39 * big(m_main) + tile(m_main) * (2 * 24576 + 16384)) + (30 * big(m_eik) + tile(m_eik) * 2 * 24576)
+        bw_bytes = 53.5 * big(m_main) + 48 * big(m_eik)
+        hbm = pk["hbm_gbs"]
+        more = []
+        for name, key, nbytes, what in (("wgrad_planes_kernel", "weight_grads", wg_bytes, "every (P, X) slot pair read once; dW written by atomics (negligible)"),
+                                        ("tc_bwd_kernel", "backward_chain", bw_bytes, "H/Q/C slots read, HD re-read, HD/P/PC/FB slots written")):
+            t_ms = prof[key]["ms"] / K
+            more.append({"kernel": name, "bound": "hbm", "achieved": nbytes / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0, "peak": hbm, "unit": "GB/s",
+                         "frac": (nbytes / (t_ms * 1e-3) / 1e9 / hbm) if t_ms > 0 else None, "bytes_per_step": nbytes, "ms_per_step": t_ms,
+                         "launches_per_step": prof[key]["launches"] / K, "traffic_model": what})
+        line["roofline_more"] = more
     if train and ms_render > 0:
         line["render"] = {"value": world * R * N_COMPOSITED * K / (ms_render * 1e-3), "unit": UNIT, "ms_per_step": ms_render / K,
                           "workload": "eval forward render of the same 1024-ray batch (no backward, no collective), device-resident inputs"}

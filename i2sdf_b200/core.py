@@ -113,10 +113,10 @@ class RenderCore:
         check(self.lib.i2sdf_profile_enable(self.h, int(enable)), "i2sdf_profile_enable")
 
     def profile_read(self):
-        ms = (C.c_float * 4)()
-        n = (C.c_int64 * 4)()
-        check(self.lib.i2sdf_profile_read(self.h, ms, n), "i2sdf_profile_read")
-        kinds = ("sampler_sdf", "main_mlp", "sampler_rays", "misc")
+        ms = (C.c_float * 6)()
+        n = (C.c_int64 * 6)()
+        check(self.lib.i2sdf_profile_read_n(self.h, 6, ms, n), "i2sdf_profile_read_n")
+        kinds = ("sampler_sdf", "main_mlp", "sampler_rays", "misc", "backward_chain", "weight_grads")
         return {k: dict(ms=float(ms[i]), launches=int(n[i])) for i, k in enumerate(kinds)}
 
     # ---- plane slots (HBM format of the fused training path; see csrc/planes.cuh)

@@ -693,7 +693,8 @@ size_t fused_backward_ws_bytes(const i2sdf_handle* h, long long M, bool color) {
 
 int fused_backward(const i2sdf_handle* h, const bwd::PointSrc& src, long long M, void* saved, const float* s_rgb, const float* g_sdf,
                    const float* g_grad, const float* g_rgb, float* const* dW, float* const* db, float* const* dWc, float* const* dbc, void* ws,
-                   cudaStream_t st) {
+                   int phases, cudaStream_t st) {
+    // phases (bit mask, for per-phase timing by the caller): 1 = chain kernel, 2 = weight gradients, 4 = rank-1 pieces
     using namespace bwd;
     if (M <= 0) return I2SDF_OK;
     const NetDev& n = h->net;
@@ -706,7 +707,8 @@ int fused_backward(const i2sdf_handle* h, const bwd::PointSrc& src, long long M,
     p.pts = src.pts; p.ray_o = src.o; p.ray_d = src.d; p.zarr = src.z; p.zstride = src.zstride; p.ns = src.ns; p.M = M;
     p.g_sdf = g_sdf; p.g_grad = g_grad; p.g_rgb = g_rgb; p.s_rgb = s_rgb; p.with_color = color ? 1 : 0;
     p.sl = SL; p.net = n;
-    if ((rc = tc_bwd_launch(h, p, st))) return rc;
+    if ((phases & 1) && (rc = tc_bwd_launch(h, p, st))) return rc;
+    if (!(phases & 6)) return I2SDF_OK;
 
     // ---- weight (+ bias) gradients: every dense product with the point index as reduction dimension
     WgArgs a{};
@@ -738,7 +740,8 @@ int fused_backward(const i2sdf_handle* h, const bwd::PointSrc& src, long long M,
         j = job(dWc[0], kin, 256, n.ed);
         term(j, SL.PC(0), true, SL.DV(), false, planes::DV_CHUNKS, nullptr, 0);
     }
-    if ((rc = wgrad_planes_launch(h, a, st))) return rc;
+    if ((phases & 2) && (rc = wgrad_planes_launch(h, a, st))) return rc;
+    if (!(phases & 4)) return I2SDF_OK;
 
     // ---- rank-1 pieces
     CsArgs c{};

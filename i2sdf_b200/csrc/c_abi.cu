@@ -33,7 +33,7 @@ int launch_composite(const i2sdf_handle*, const float*, const float*, const floa
 namespace bwd { struct PointSrc { const float* pts; const float* o; const float* d; const float* z; int zstride; int ns; }; }
 size_t fused_backward_ws_bytes(const i2sdf_handle*, long long, bool);
 int fused_backward(const i2sdf_handle*, const bwd::PointSrc&, long long, void*, const float*, const float*, const float*, const float*,
-                   float* const*, float* const*, float* const*, float* const*, void*, cudaStream_t);
+                   float* const*, float* const*, float* const*, float* const*, void*, int, cudaStream_t);
 size_t sdf_backward_ws_floats(const i2sdf_handle*, long long);
 size_t color_backward_ws_floats(const i2sdf_handle*, long long);
 size_t light_backward_ws_floats(const i2sdf_handle*, long long);
@@ -103,11 +103,12 @@ static int run_pack(const PackJob& J, cudaStream_t st) {
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // ---- measurement hook ---------------------------------------------------------------------------
+constexpr int kProfKinds = 8;
 struct Prof {
     bool on = false;
-    std::vector<cudaEvent_t> ev[4];     // start/stop pairs
-    size_t used[4] = {0, 0, 0, 0};
-    long long launches[4] = {0, 0, 0, 0};
+    std::vector<cudaEvent_t> ev[kProfKinds];     // start/stop pairs
+    size_t used[kProfKinds] = {};
+    long long launches[kProfKinds] = {};
 };
 struct ProfScope {
     Prof* p; int kind; cudaStream_t st; int nlaunch;
@@ -508,15 +509,17 @@ int i2sdf_profile_enable(i2sdf_handle* h, int enable) {
     if (!h) { set_error("null handle"); return I2SDF_E_INVALID; }
     Prof* p = (Prof*)h->prof;
     p->on = enable != 0;
-    if (enable) for (int k = 0; k < 4; ++k) { p->used[k] = 0; p->launches[k] = 0; }
+    if (enable) for (int k = 0; k < kProfKinds; ++k) { p->used[k] = 0; p->launches[k] = 0; }
     return I2SDF_OK;
 }
 
-int i2sdf_profile_read(i2sdf_handle* h, float ms[4], int64_t launches[4]) {
-    if (!h || !ms || !launches) { set_error("null argument"); return I2SDF_E_INVALID; }
+int i2sdf_profile_read(i2sdf_handle* h, float ms[4], int64_t launches[4]) { return i2sdf_profile_read_n(h, 4, ms, launches); }
+
+int i2sdf_profile_read_n(i2sdf_handle* h, int n, float* ms, int64_t* launches) {
+    if (!h || !ms || !launches || n < 1 || n > kProfKinds) { set_error("profile_read: bad argument"); return I2SDF_E_INVALID; }
     Prof* p = (Prof*)h->prof;
     I2SDF_CUDA_CHECK(cudaDeviceSynchronize());
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < n; ++k) {
         float tot = 0.f;
         for (size_t i = 0; i + 1 < p->used[k]; i += 2) { float t = 0.f; cudaEventElapsedTime(&t, p->ev[k][i], p->ev[k][i + 1]); tot += t; }
         ms[k] = tot;
@@ -539,8 +542,12 @@ int i2sdf_fused_backward(i2sdf_handle* h, const float* pts, const float* o, cons
     if (!(g_rgb ? planes_main(h) : planes_sdf(h))) { set_error("fused_backward: this handle saves fp32 pre-activations (use i2sdf_sdf_backward / i2sdf_color_backward)"); return I2SDF_E_INVALID; }
     if (workspace_bytes < i2sdf_backward_workspace_bytes(h, M)) { set_error("fused_backward: workspace too small"); return I2SDF_E_WORKSPACE; }
     bwd::PointSrc S{pts, o, d, z, zstride, ns > 0 ? ns : 1};
-    ProfScope ps(h, 1, (cudaStream_t)stream, 6);
-    return fused_backward(h, S, M, saved, s_rgb, g_sdf, g_grad, g_rgb, dW_sdf, db_sdf, dW_col, db_col, workspace, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    { ProfScope ps(h, 4, st, 1); if ((rc = fused_backward(h, S, M, saved, s_rgb, g_sdf, g_grad, g_rgb, dW_sdf, db_sdf, dW_col, db_col, workspace, 1, st))) return rc; }
+    { ProfScope ps(h, 5, st, 1); if ((rc = fused_backward(h, S, M, saved, s_rgb, g_sdf, g_grad, g_rgb, dW_sdf, db_sdf, dW_col, db_col, workspace, 2, st))) return rc; }
+    { ProfScope ps(h, 3, st, g_rgb ? 4 : 2); if ((rc = fused_backward(h, S, M, saved, s_rgb, g_sdf, g_grad, g_rgb, dW_sdf, db_sdf, dW_col, db_col, workspace, 4, st))) return rc; }
+    return I2SDF_OK;
 }
 
 int i2sdf_render_forward(i2sdf_handle* h, const float* o, const float* d, const float* dnorm, const float* z, int64_t R, int N,

@@ -211,6 +211,8 @@ int i2sdf_sdf_backward(i2sdf_handle* h, const float* const* W, const float* pts,
  * i2sdf_profile_read synchronises the device and returns summed event durations (ms) and launch counts. */
 int i2sdf_profile_enable(i2sdf_handle* h, int enable);
 int i2sdf_profile_read(i2sdf_handle* h, float ms[4], int64_t launches[4]);
+/* same with n <= 8 classes: 4 = backward chain kernel (fused training path), 5 = weight-gradient kernel. */
+int i2sdf_profile_read_n(i2sdf_handle* h, int n, float* ms, int64_t* launches);
 
 /* What a forward in training mode saves for the backward.  format 1 = plane slots (tensor-core chain kernels; consumed
  * by i2sdf_fused_backward), 0 = fp32 pre-activations [L-1][M][256] (fp32 kernels; consumed by i2sdf_sdf_backward /
