@@ -351,10 +351,17 @@ class I2SDFLoss(nn.Module):
         if self.bubble_weight > 0 and self.max_bubble_iter is not None and self.smooth_iter < self.max_bubble_iter:
             self.smooth_iter = self.max_bubble_iter
 
+    # Masked means are evaluated as sum(mask * x) / sum(mask): same value as the reference's x[mask].mean()
+    # (model/network/__init__.py:320-329) — NaN for an empty mask included — but without the boolean-index gather, whose
+    # nonzero() forces a device->host sync in the middle of every training step.
     @staticmethod
-    def _masked_normal_l1(normal, normal_gt, mask):
-        m = mask.flatten()
-        return torch.abs(1 - torch.sum(normal[m] * normal_gt.reshape(-1, 3)[m], dim=-1)).mean()
+    def _masked_mean(x, mask):
+        m = mask.flatten().bool()
+        return torch.where(m, x, torch.zeros((), dtype=x.dtype, device=x.device)).sum() / m.sum()
+
+    @classmethod
+    def _masked_normal_l1(cls, normal, normal_gt, mask):
+        return cls._masked_mean(torch.abs(1 - torch.sum(normal * normal_gt.reshape(-1, 3), dim=-1)), mask)
 
     def get_rgb_loss(self, rgb_values, rgb_gt):
         return self.rgb_loss(rgb_values, rgb_gt.reshape(-1, 3))
@@ -366,20 +373,18 @@ class I2SDFLoss(nn.Module):
         return F.binary_cross_entropy(mask_pred.clip(1e-3, 1.0 - 1e-3), mask_gt)
 
     def get_depth_loss(self, depth, depth_gt, depth_mask):
-        m = depth_mask.flatten()
-        return F.mse_loss(depth[m], depth_gt.flatten()[m])
+        return self._masked_mean((depth.flatten() - depth_gt.flatten()) ** 2, depth_mask)
 
     def get_normal_l1_loss(self, normal, normal_gt, normal_mask):
         return self._masked_normal_l1(normal, normal_gt, normal_mask)
 
     def get_normal_angular_loss(self, normal, normal_gt, normal_mask):
-        m = normal_mask.flatten()
-        dot = torch.sum(normal[m] * normal_gt.reshape(-1, 3)[m], dim=-1)
-        return (torch.acos(torch.clamp(dot, -1.0 + 1e-6, 1.0 - 1e-6)) / math.tau).clamp_max(0.5).abs().mean()
+        dot = torch.sum(normal * normal_gt.reshape(-1, 3), dim=-1)
+        return self._masked_mean((torch.acos(torch.clamp(dot, -1.0 + 1e-6, 1.0 - 1e-6)) / math.tau).clamp_max(0.5).abs(), normal_mask)
 
     def forward(self, model_outputs, ground_truth, current_step):
         dev = model_outputs["rgb_values"].device
-        zero = lambda: torch.tensor(0.0, device=dev).float()      # noqa: E731
+        zero = lambda: torch.zeros((), device=dev)                # noqa: E731   (a fill kernel: no host->device copy, no sync)
         terms = {"rgb_loss": self.get_rgb_loss(model_outputs["rgb_values"], ground_truth["rgb"])}
         terms["eikonal_loss"] = self.get_eikonal_loss(model_outputs["grad_theta"]) if "grad_theta" in model_outputs else zero()
         smooth_on = self.smooth_iter is None or current_step > self.smooth_iter
