@@ -50,14 +50,16 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], group: Optional[di
     ps = [p for p in params if p.grad is not None]
     if not ps:
         return 0
-    flat = torch.cat([p.grad.reshape(-1) for p in ps])
+    grads = [p.grad for p in ps]
+    flat = torch.cat([g.reshape(-1) for g in grads])                       # one kernel
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        if average:
-            flat /= dist.get_world_size(group)
-    off = 0
-    for p in ps:
-        n = p.grad.numel()
-        p.grad.copy_(flat[off:off + n].view_as(p.grad))
-        off += n
+        world = dist.get_world_size(group)
+        if average and dist.get_backend(group) == "nccl":
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)       # the division happens inside NCCL
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+            if average:
+                flat /= world
+    views = [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in grads]), grads)]
+    torch._foreach_copy_(grads, views)                                     # un-flatten in a couple of multi-tensor kernels
     return flat.numel()
