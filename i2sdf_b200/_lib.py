@@ -48,7 +48,9 @@ SYMBOLS = {
     "i2sdf_profile_read_n": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     "i2sdf_saved_format": (C.c_int, [_P, C.c_int]),
     "i2sdf_sdf_saved_bytes": (C.c_size_t, [_P, C.c_int64]),
-    "i2sdf_fused_backward": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(_P), C.POINTER(_P),
+    "i2sdf_points_forward_ex": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int, _P, C.c_int64] + [_P] * 6 + [_P, C.c_size_t, _P]),
+    "i2sdf_saved_bytes_points": (C.c_size_t, [_P, C.c_int64]),
+    "i2sdf_fused_backward": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(_P), C.POINTER(_P),
                                        C.POINTER(_P), C.POINTER(_P), _P, C.c_size_t, _P]),
     "i2sdf_planes_slot_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
     "i2sdf_planes_pack": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, _P, _P]),

@@ -42,41 +42,60 @@ def _split_params(params, n_sdf, n_col, n_light):
 
 
 class _PointsFn(Function):
-    """(o, d, z) -> per-sample sdf, grad_x sdf, rgb, light-mask.  Differentiable w.r.t. the effective weights."""
+    """(o, d, z) -> per-sample sdf, grad_x sdf, rgb, light-mask.  Differentiable w.r.t. the effective weights.
+    extra_pts [E,3] (or None; fused tensor-core path only): explicit points evaluated in the SAME launches, appended
+    after the R*N ray samples; their grad_x sdf is returned as a fifth output (eikonal / smoothness points)."""
 
     @staticmethod
-    def forward(ctx, core, o, d, z, want_grad, n_sdf, n_col, n_light, *params):
-        out = core.points_forward(o, d, z, want_grad, n_light > 0, save=True)
+    def forward(ctx, core, o, d, z, extra_pts, want_grad, n_sdf, n_col, n_light, *params):
+        out = core.points_forward(o, d, z, want_grad, n_light > 0, save=True, extra_pts=extra_pts)
         ctx.core, ctx.cfg = core, (want_grad, n_sdf, n_col, n_light)
         ctx.fused = out["fused"]
         ctx.set_materialize_grads(False)
+        E = 0 if extra_pts is None else extra_pts.shape[0]
+        M = z.shape[0] * (z.shape[1] - 1)
         keep = [o, d, z, out["act"], out["feat"] if out["feat"] is not None else o.new_empty(0), out["s_rgb"]]
         keep.append(out["s_light"] if out["s_light"] is not None else o.new_empty(0))
+        keep.append(extra_pts.detach() if E else o.new_empty(0))
         ctx.save_for_backward(*keep, *params)
-        s_grad = out["s_grad"] if want_grad else o.new_empty(0)
+        s_grad = out["s_grad"][:M] if want_grad else o.new_empty(0)
         s_light = out["s_light"] if n_light > 0 else o.new_empty(0)
+        x_grad = out["s_grad"][M:] if E else o.new_empty(0)
         if not want_grad:
             ctx.mark_non_differentiable(s_grad)
         if n_light == 0:
             ctx.mark_non_differentiable(s_light)
-        return out["s_sdf"], s_grad, out["s_rgb"], s_light
+        if not E:
+            ctx.mark_non_differentiable(x_grad)
+        return out["s_sdf"][:M], s_grad, out["s_rgb"][:M], s_light, x_grad
 
     @staticmethod
-    def backward(ctx, g_sdf, g_grad, g_rgb, g_light):
+    def backward(ctx, g_sdf, g_grad, g_rgb, g_light, g_xgrad):
         core = ctx.core
         want_grad, n_sdf, n_col, n_light = ctx.cfg
         saved = ctx.saved_tensors
-        o, d, z, act, feat, s_rgb, s_light = saved[:7]
-        W_sdf, b_sdf, W_col, b_col, W_l, b_l = _split_params(saved[7:], n_sdf, n_col, n_light)
+        o, d, z, act, feat, s_rgb, s_light, extra_pts = saved[:8]
+        W_sdf, b_sdf, W_col, b_col, W_l, b_l = _split_params(saved[8:], n_sdf, n_col, n_light)
         R, N = z.shape[0], z.shape[1] - 1
         M = R * N
+        E = extra_pts.shape[0]
         dW_sdf, db_sdf, dW_col, db_col, dW_l, db_l = _zeros_like_all([W_sdf, b_sdf, W_col, b_col, W_l, b_l])
         if ctx.fused:
             # plane slots: one chain kernel + one weight-gradient launch cover both stacks, first and second order
-            if g_sdf is not None or g_rgb is not None or (want_grad and g_grad is not None):
-                core.fused_backward(M, act, dW_sdf, db_sdf, rays=(o, d, z, N), s_rgb=s_rgb, g_sdf=g_sdf,
-                                    g_grad=g_grad if want_grad else None, g_rgb=g_rgb, dW_col=dW_col, db_col=db_col)
-            return (None,) * 8 + tuple(dW_sdf + db_sdf + dW_col + db_col + dW_l + db_l)
+            if not want_grad:
+                g_grad = None
+            if g_sdf is not None or g_rgb is not None or g_grad is not None or (E and g_xgrad is not None):
+                if E:       # upstreams of the appended points: only grad_x sdf carries one
+                    if g_sdf is not None:
+                        g_sdf = torch.cat([g_sdf, g_sdf.new_zeros(E)])
+                    if g_rgb is not None:
+                        g_rgb = torch.cat([g_rgb, g_rgb.new_zeros(E, 3)])
+                    if g_grad is not None or g_xgrad is not None:
+                        g_grad = torch.cat([g_grad if g_grad is not None else o.new_zeros(M, 3),
+                                            g_xgrad if g_xgrad is not None else o.new_zeros(E, 3)])
+                core.fused_backward(M + E, act, dW_sdf, db_sdf, rays=(o, d, z, N), pts=extra_pts if E else None, s_rgb=s_rgb, g_sdf=g_sdf,
+                                    g_grad=g_grad, g_rgb=g_rgb, dW_col=dW_col, db_col=db_col)
+            return (None,) * 9 + tuple(dW_sdf + db_sdf + dW_col + db_col + dW_l + db_l)
         g_feat_ptr, ld = None, 256
         if g_rgb is not None:
             g_x = core.color_backward(W_col, b_col, d, N, feat, s_rgb, g_rgb, dW_col, db_col)
@@ -89,7 +108,7 @@ class _PointsFn(Function):
                               g_grad=g_grad if want_grad else None)
         if g_rgb is not None:
             del g_x
-        return (None,) * 8 + tuple(dW_sdf + db_sdf + dW_col + db_col + dW_l + db_l)
+        return (None,) * 9 + tuple(dW_sdf + db_sdf + dW_col + db_col + dW_l + db_l)
 
 
 class _CompositeFn(Function):
@@ -185,7 +204,18 @@ def forward_train(model, core, input, predict_only=False):
     want_grad = bool(model.use_normal)                  # returns_grad (network/__init__.py:109) in training
     params = [w.contiguous() for w in W_sdf] + list(b_sdf) + [w.contiguous() for w in W_col] + list(b_col) + \
              [w.contiguous() for w in W_l] + list(b_l)
-    s_sdf, s_grad, s_rgb, s_light = _PointsFn.apply(core, o, d, z, want_grad, n_sdf, n_col, n_light, *params)
+    # ---- eikonal / smoothness points (network/__init__.py:175-193).  Drawn here, before the main pass: on the fused
+    # tensor-core path they are appended to the main-pass launches (same RNG calls in the same order as the reference:
+    # nothing random happens in between)
+    pts = None
+    if not predict_only:
+        bsph = model.scene_bounding_sphere
+        eik_u = ov["eik_uniform"].to(dev) if "eik_uniform" in ov else torch.empty(R, 3, device=dev).uniform_(-bsph, bsph)
+        near = o + z_eik[:, None] * d
+        nbr_u = ov["nbr_uniform"].to(dev) if "nbr_uniform" in ov else torch.empty_like(near).uniform_(-0.005, 0.005)
+        pts = torch.cat([eik_u, near, near + nbr_u], 0)
+    ride = pts is not None and core.fused_main and n_light == 0
+    s_sdf, s_grad, s_rgb, s_light, x_grad = _PointsFn.apply(core, o, d, z, pts if ride else None, want_grad, n_sdf, n_col, n_light, *params)
     rgb, depth, wsum, normal, light = _CompositeFn.apply(core, z, dnorm, beta, s_sdf, s_rgb, s_grad, s_light,
                                                          want_grad and not predict_only, n_light > 0)
     res = {"rgb_values": rgb, "depth_values": depth, "weight_sum": wsum[:, None]}
@@ -193,14 +223,11 @@ def forward_train(model, core, input, predict_only=False):
         res["light_mask"] = light[:, None]
     if predict_only:
         return res
-    # ---- eikonal / smoothness points (network/__init__.py:175-193)
-    bsph = model.scene_bounding_sphere
-    eik_u = ov["eik_uniform"].to(dev) if "eik_uniform" in ov else torch.empty(R, 3, device=dev).uniform_(-bsph, bsph)
-    near = o + z_eik[:, None] * d
-    nbr_u = ov["nbr_uniform"].to(dev) if "nbr_uniform" in ov else torch.empty_like(near).uniform_(-0.005, 0.005)
-    pts = torch.cat([eik_u, near, near + nbr_u], 0)
     sdf_params = [w.contiguous() for w in W_sdf] + list(b_sdf)
-    _, g = _SdfPointsFn.apply(core, pts, True, n_sdf, *sdf_params)
+    if ride:
+        g = x_grad
+    else:
+        _, g = _SdfPointsFn.apply(core, pts, True, n_sdf, *sdf_params)
     res["grad_theta"] = g[:2 * R]
     nrm = F.normalize(g[R:], dim=1, eps=1e-6)
     res["diff_norm"] = torch.norm(nrm[:R] - nrm[R:], dim=1)

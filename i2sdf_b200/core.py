@@ -244,22 +244,29 @@ class RenderCore:
     def _ptr_array(tensors):
         return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 
-    def points_forward(self, o, d, z, want_grad, want_light, save=True):
+    def points_forward(self, o, d, z, want_grad, want_light, save=True, extra_pts=None):
+        """Main-pass chain on the R*N ray samples (+ optional explicit points appended: fused tensor-core path only)."""
         dev = self.device
         o, d, z = _f32(o, dev), _f32(d, dev), _f32(z, dev)
         R, N = z.shape[0], z.shape[1] - 1
-        M = R * N
+        E = 0 if extra_pts is None else extra_pts.shape[0]
+        if E:
+            extra_pts = _f32(extra_pts.detach(), dev)
+        M = R * N + E
         fused = save and self.fused_main and not want_light       # plane slots: features stay inside the saved state
         out = dict(s_sdf=torch.empty(M, device=dev), s_rgb=torch.empty(M, 3, device=dev))
         out["feat"] = None if fused else torch.empty(M, 256, device=dev)
         out["s_grad"] = torch.empty(M, 3, device=dev) if (want_grad or fused) else None
         out["s_light"] = torch.empty(M, device=dev) if want_light else None
-        out["act"] = torch.empty(self.lib.i2sdf_saved_bytes(self.h, R, N), dtype=torch.uint8, device=dev) if save else None
+        out["act"] = torch.empty(self.lib.i2sdf_saved_bytes_points(self.h, M), dtype=torch.uint8, device=dev) if save else None
         out["fused"] = fused
+        if E and not fused:
+            raise _lib.I2SDFError("points_forward: appended points need the fused tensor-core path")
         ws = self.workspace(R)
-        check(self.lib.i2sdf_points_forward(self.h, _ptr(o), _ptr(d), _ptr(z), R, N, _ptr(out["s_sdf"]), _ptr(out["s_grad"]),
-                                            _ptr(out["s_rgb"]), _ptr(out["s_light"]), _ptr(out["feat"]), _ptr(out["act"]),
-                                            _ptr(ws), self._ws_bytes, self._stream()), "i2sdf_points_forward")
+        check(self.lib.i2sdf_points_forward_ex(self.h, _ptr(o), _ptr(d), _ptr(z), R, N, _ptr(extra_pts), E, _ptr(out["s_sdf"]),
+                                               _ptr(out["s_grad"]), _ptr(out["s_rgb"]), _ptr(out["s_light"]), _ptr(out["feat"]),
+                                               _ptr(out["act"]), _ptr(ws), self._ws_bytes, self._stream()), "i2sdf_points_forward_ex")
+        self._keep_fwd = extra_pts
         return out
 
     def composite_forward(self, z, dnorm, beta_param, s_sdf, s_rgb, s_grad, s_light):
@@ -331,19 +338,22 @@ class RenderCore:
 
     def fused_backward(self, M, saved, dW_sdf, db_sdf, pts=None, rays=None, s_rgb=None, g_sdf=None, g_grad=None, g_rgb=None,
                        dW_col=None, db_col=None):
-        """Tensor-core backward on plane slots (i2sdf_fused_backward).  rays = (o, d, z [R,zstride], ns)."""
+        """Tensor-core backward on plane slots (i2sdf_fused_backward).  rays = (o, d, z [R,zstride], ns); with rays AND pts
+        the first R*ns points are ray samples and pts are the points appended after them."""
         dev = self.device
         bws = self.backward_workspace(M)
         f = lambda t: None if t is None else _f32(t, dev)        # noqa: E731
         g_sdf, g_grad, g_rgb = f(g_sdf), f(g_grad), f(g_rgb)
+        m_rays = 0
         if rays is not None:
             o, d, z, ns = rays
-            po, pd, pz, zs, pp = _ptr(o), _ptr(d), _ptr(z), z.shape[1], _ptr(None)
+            po, pd, pz, zs, pp = _ptr(o), _ptr(d), _ptr(z), z.shape[1], _ptr(pts)
+            m_rays = z.shape[0] * ns
         else:
             po = pd = pz = _ptr(None)
             zs, ns, pp = 0, 1, _ptr(pts)
         null = C.POINTER(C.c_void_p)()
-        check(self.lib.i2sdf_fused_backward(self.h, pp, po, pd, pz, zs, ns, M, _ptr(saved), _ptr(s_rgb), _ptr(g_sdf), _ptr(g_grad), _ptr(g_rgb),
+        check(self.lib.i2sdf_fused_backward(self.h, pp, po, pd, pz, zs, ns, M, m_rays, _ptr(saved), _ptr(s_rgb), _ptr(g_sdf), _ptr(g_grad), _ptr(g_rgb),
                                             self._ptr_array(dW_sdf), self._ptr_array(db_sdf),
                                             self._ptr_array(dW_col) if dW_col else null, self._ptr_array(db_col) if db_col else null,
                                             _ptr(bws), bws.numel(), self._stream()), "i2sdf_fused_backward")

@@ -693,7 +693,7 @@ size_t fused_backward_ws_bytes(const i2sdf_handle* h, long long M, bool color) {
 
 int fused_backward(const i2sdf_handle* h, const bwd::PointSrc& src, long long M, void* saved, const float* s_rgb, const float* g_sdf,
                    const float* g_grad, const float* g_rgb, float* const* dW, float* const* db, float* const* dWc, float* const* dbc, void* ws,
-                   int phases, cudaStream_t st) {
+                   int phases, long long m_rays, cudaStream_t st) {
     // phases (bit mask, for per-phase timing by the caller): 1 = chain kernel, 2 = weight gradients, 4 = rank-1 pieces
     using namespace bwd;
     if (M <= 0) return I2SDF_OK;
@@ -705,6 +705,7 @@ int fused_backward(const i2sdf_handle* h, const bwd::PointSrc& src, long long M,
     int rc;
     BwdParams p{};
     p.pts = src.pts; p.ray_o = src.o; p.ray_d = src.d; p.zarr = src.z; p.zstride = src.zstride; p.ns = src.ns; p.M = M;
+    p.m_rays = (src.pts && src.o) ? m_rays : 0;
     p.g_sdf = g_sdf; p.g_grad = g_grad; p.g_rgb = g_rgb; p.s_rgb = s_rgb; p.with_color = color ? 1 : 0;
     p.sl = SL; p.net = n;
     if ((phases & 1) && (rc = tc_bwd_launch(h, p, st))) return rc;

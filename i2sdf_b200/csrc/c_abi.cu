@@ -33,7 +33,7 @@ int launch_composite(const i2sdf_handle*, const float*, const float*, const floa
 namespace bwd { struct PointSrc { const float* pts; const float* o; const float* d; const float* z; int zstride; int ns; }; }
 size_t fused_backward_ws_bytes(const i2sdf_handle*, long long, bool);
 int fused_backward(const i2sdf_handle*, const bwd::PointSrc&, long long, void*, const float*, const float*, const float*, const float*,
-                   float* const*, float* const*, float* const*, float* const*, void*, int, cudaStream_t);
+                   float* const*, float* const*, float* const*, float* const*, void*, int, long long, cudaStream_t);
 size_t sdf_backward_ws_floats(const i2sdf_handle*, long long);
 size_t color_backward_ws_floats(const i2sdf_handle*, long long);
 size_t light_backward_ws_floats(const i2sdf_handle*, long long);
@@ -435,11 +435,21 @@ size_t i2sdf_backward_workspace_bytes(const i2sdf_handle* h, int64_t M) {
 
 int i2sdf_points_forward(i2sdf_handle* h, const float* o, const float* d, const float* z, int64_t R, int N, float* s_sdf, float* s_grad,
                          float* s_rgb, float* s_light, float* s_feat, float* save_act, void* workspace, size_t workspace_bytes, void* stream) {
+    return i2sdf_points_forward_ex(h, o, d, z, R, N, nullptr, 0, s_sdf, s_grad, s_rgb, s_light, s_feat, save_act, workspace, workspace_bytes, stream);
+}
+
+int i2sdf_points_forward_ex(i2sdf_handle* h, const float* o, const float* d, const float* z, int64_t R, int N, const float* extra_pts,
+                            int64_t n_extra, float* s_sdf, float* s_grad, float* s_rgb, float* s_light, float* s_feat, float* save_act,
+                            void* workspace, size_t workspace_bytes, void* stream) {
     if (!h || !o || !d || !z || !s_sdf) { set_error("null argument"); return I2SDF_E_INVALID; }
+    if (n_extra < 0 || (n_extra > 0 && (!extra_pts || !planes_main(h) || s_light || !s_rgb || !s_grad))) {
+        set_error("points_forward_ex: extra points need the tensor-core main pass (no light head) with s_rgb and s_grad"); return I2SDF_E_INVALID;
+    }
     if (N < 1 || N > 128) { set_error("points_forward: N=%d unsupported", N); return I2SDF_E_INVALID; }
     if (s_light && h->net.Ll == 0) { set_error("points_forward: no light head"); return I2SDF_E_INVALID; }
     MlpParams p{};
-    p.ray_o = o; p.ray_d = d; p.zarr = z; p.zstride = N + 1; p.ns = N; p.M = (long long)R * N; p.round_idx = -1; p.beta_min = h->smp.beta_min;
+    p.ray_o = o; p.ray_d = d; p.zarr = z; p.zstride = N + 1; p.ns = N; p.M = (long long)R * N + n_extra; p.round_idx = -1; p.beta_min = h->smp.beta_min;
+    if (n_extra > 0) { p.pts = extra_pts; p.m_rays = (long long)R * N; }     // appended explicit points (eikonal / smoothness) ride the same launch
     p.out_sdf = s_sdf; p.out_grad = s_grad; p.out_rgb = s_rgb; p.out_light = s_light; p.out_feat = s_feat;
     p.want_color = s_rgb != nullptr; p.want_light = s_light != nullptr;
     if (save_act && planes_main(h) && !s_light && s_rgb && s_grad) p.sl = planes::make_layout(p.M, h->net.L - 1, h->net.Lc, true, save_act, nullptr);
@@ -528,25 +538,28 @@ int i2sdf_profile_read_n(i2sdf_handle* h, int n, float* ms, int64_t* launches) {
     return I2SDF_OK;
 }
 
-size_t i2sdf_saved_bytes(const i2sdf_handle* h, int64_t R, int N) {
-    if (!h) return 0;
-    if (planes_main(h)) return planes::make_layout((long long)R * N, h->net.L - 1, h->net.Lc, true, nullptr, nullptr).saved_total();
-    return (size_t)(h->net.L - 1) * (size_t)R * N * 256 * sizeof(float);
+size_t i2sdf_saved_bytes(const i2sdf_handle* h, int64_t R, int N) { return i2sdf_saved_bytes_points(h, R * N); }
+
+size_t i2sdf_saved_bytes_points(const i2sdf_handle* h, int64_t M) {
+    if (!h || M < 0) return 0;
+    if (planes_main(h)) return planes::make_layout(M, h->net.L - 1, h->net.Lc, true, nullptr, nullptr).saved_total();
+    return (size_t)(h->net.L - 1) * (size_t)M * 256 * sizeof(float);
 }
 
 int i2sdf_fused_backward(i2sdf_handle* h, const float* pts, const float* o, const float* d, const float* z, int zstride, int ns, int64_t M,
-                         void* saved, const float* s_rgb, const float* g_sdf, const float* g_grad, const float* g_rgb, float* const* dW_sdf,
+                         int64_t m_rays, void* saved, const float* s_rgb, const float* g_sdf, const float* g_grad, const float* g_rgb, float* const* dW_sdf,
                          float* const* db_sdf, float* const* dW_col, float* const* db_col, void* workspace, size_t workspace_bytes, void* stream) {
     if (!h || !saved || !dW_sdf || !db_sdf || !workspace || (!pts && (!o || !d || !z))) { set_error("fused_backward: null argument"); return I2SDF_E_INVALID; }
+    if (pts && o && (m_rays < 0 || m_rays > M)) { set_error("fused_backward: m_rays out of range"); return I2SDF_E_INVALID; }
     if (g_rgb && (!s_rgb || !dW_col || !db_col)) { set_error("fused_backward: g_rgb needs s_rgb, dW_col, db_col"); return I2SDF_E_INVALID; }
     if (!(g_rgb ? planes_main(h) : planes_sdf(h))) { set_error("fused_backward: this handle saves fp32 pre-activations (use i2sdf_sdf_backward / i2sdf_color_backward)"); return I2SDF_E_INVALID; }
     if (workspace_bytes < i2sdf_backward_workspace_bytes(h, M)) { set_error("fused_backward: workspace too small"); return I2SDF_E_WORKSPACE; }
     bwd::PointSrc S{pts, o, d, z, zstride, ns > 0 ? ns : 1};
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    { ProfScope ps(h, 4, st, 1); if ((rc = fused_backward(h, S, M, saved, s_rgb, g_sdf, g_grad, g_rgb, dW_sdf, db_sdf, dW_col, db_col, workspace, 1, st))) return rc; }
-    { ProfScope ps(h, 5, st, 1); if ((rc = fused_backward(h, S, M, saved, s_rgb, g_sdf, g_grad, g_rgb, dW_sdf, db_sdf, dW_col, db_col, workspace, 2, st))) return rc; }
-    { ProfScope ps(h, 3, st, g_rgb ? 4 : 2); if ((rc = fused_backward(h, S, M, saved, s_rgb, g_sdf, g_grad, g_rgb, dW_sdf, db_sdf, dW_col, db_col, workspace, 4, st))) return rc; }
+    { ProfScope ps(h, 4, st, 1); if ((rc = fused_backward(h, S, M, saved, s_rgb, g_sdf, g_grad, g_rgb, dW_sdf, db_sdf, dW_col, db_col, workspace, 1, m_rays, st))) return rc; }
+    { ProfScope ps(h, 5, st, 1); if ((rc = fused_backward(h, S, M, saved, s_rgb, g_sdf, g_grad, g_rgb, dW_sdf, db_sdf, dW_col, db_col, workspace, 2, m_rays, st))) return rc; }
+    { ProfScope ps(h, 3, st, g_rgb ? 4 : 2); if ((rc = fused_backward(h, S, M, saved, s_rgb, g_sdf, g_grad, g_rgb, dW_sdf, db_sdf, dW_col, db_col, workspace, 4, m_rays, st))) return rc; }
     return I2SDF_OK;
 }
 

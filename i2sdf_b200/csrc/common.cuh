@@ -91,6 +91,7 @@ struct MlpParams {
     int zstride;
     int ns;
     long long M;
+    long long m_rays;         // with BOTH sources given: points m < m_rays come from the rays, m >= m_rays from pts[m - m_rays]
     // predication for sampler rounds: run only if round_idx < 0 or all beta_max[j] > beta0 for j < round_idx
     const float* beta_max;    // device [max_iters]
     const float* beta_param;  // device scalar (raw density.beta)

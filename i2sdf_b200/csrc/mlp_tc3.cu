@@ -99,8 +99,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
             x[0] = x[1] = x[2] = 0.f; dv[0] = 0.f; dv[1] = 0.f; dv[2] = 1.f;
             if (m < P.M) {
                 const long long r = m / P.ns;
-                if (P.ray_d) { dv[0] = P.ray_d[r * 3]; dv[1] = P.ray_d[r * 3 + 1]; dv[2] = P.ray_d[r * 3 + 2]; }
-                if (P.pts) { x[0] = P.pts[m * 3]; x[1] = P.pts[m * 3 + 1]; x[2] = P.pts[m * 3 + 2]; }
+                const bool from_pts = P.pts && m >= P.m_rays;
+                const float* pp = P.pts + (m - P.m_rays) * 3;
+                if (P.ray_d && !from_pts) { dv[0] = P.ray_d[r * 3]; dv[1] = P.ray_d[r * 3 + 1]; dv[2] = P.ray_d[r * 3 + 2]; }
+                if (from_pts) { x[0] = pp[0]; x[1] = pp[1]; x[2] = pp[2]; }
                 else {
                     const int j = (int)(m - r * P.ns);
                     const float t = P.zarr[r * P.zstride + j];

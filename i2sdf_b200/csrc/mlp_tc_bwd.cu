@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const BwdParams P, 
             const long long m = tile * TM + row;
             x[0] = x[1] = x[2] = 0.f; gb[0] = gb[1] = gb[2] = 0.f;
             if (m < P.M) {
-                if (P.pts) { x[0] = P.pts[m * 3]; x[1] = P.pts[m * 3 + 1]; x[2] = P.pts[m * 3 + 2]; }
+                if (P.pts && m >= P.m_rays) { const float* pp = P.pts + (m - P.m_rays) * 3; x[0] = pp[0]; x[1] = pp[1]; x[2] = pp[2]; }
                 else {
                     const long long r = m / P.ns;
                     const int j = (int)(m - r * P.ns);

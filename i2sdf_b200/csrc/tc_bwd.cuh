@@ -20,6 +20,7 @@ struct BwdParams {
     int zstride;
     int ns;
     long long M;
+    long long m_rays;      // as MlpParams: both sources given -> first m_rays points from the rays, the rest from pts
     // upstream gradients per point (null = 0)
     const float* g_sdf;    // [M]
     const float* g_grad;   // [M][3]   upstream of grad_x sdf

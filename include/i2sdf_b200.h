@@ -171,6 +171,15 @@ int i2sdf_points_forward(i2sdf_handle* h, const float* o, const float* d, const 
                          float* s_sdf, float* s_grad, float* s_rgb, float* s_light, float* s_feat, float* save_act,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same with n_extra explicit points [n_extra,3] appended after the R*N ray samples (the eikonal / smoothness points of
+ * model/network/__init__.py:175-193 ride the main-pass launch): every per-sample output has R*N + n_extra rows, the
+ * saved state is sized by i2sdf_saved_bytes_points(h, R*N + n_extra).  Tensor-core main pass only. */
+int i2sdf_points_forward_ex(i2sdf_handle* h, const float* o, const float* d, const float* z, int64_t R, int N,
+                            const float* extra_pts, int64_t n_extra, float* s_sdf, float* s_grad, float* s_rgb,
+                            float* s_light, float* s_feat, float* save_act, void* workspace, size_t workspace_bytes,
+                            void* stream);
+size_t i2sdf_saved_bytes_points(const i2sdf_handle* h, int64_t M);
+
 /* Compositing only (model/network/__init__.py:118-125,169,204-219,223-240) on per-sample inputs. */
 int i2sdf_composite_forward(i2sdf_handle* h, const float* z, const float* dnorm, const float* s_sdf, const float* s_rgb,
                             const float* s_grad, const float* s_light, const float* beta_param, int64_t R, int N,
@@ -224,12 +233,13 @@ size_t i2sdf_sdf_saved_bytes(const i2sdf_handle* h, int64_t M);
 /* Fused backward of the per-point networks on plane slots: the tangent pass of the SDF stack along g_grad, the
  * reverse passes of the radiance and SDF stacks, all weight and bias gradients — what loss.backward() runs through
  * ImplicitNetwork (mlp.py:84-143, incl. the second-order graph) and RenderingNetwork (mlp.py:208-229) in the reference.
- * Points as in i2sdf_sdf_backward.  saved: the buffer the forward filled (format 1).  g_sdf [M], g_grad [M,3],
+ * Points as in i2sdf_sdf_backward; with BOTH pts and rays given the first m_rays points are ray samples and the rest
+ * explicit (the layout i2sdf_points_forward_ex produced).  saved: the buffer the forward filled (format 1).  g_sdf [M], g_grad [M,3],
  * g_rgb [M,3] upstream (NULL = 0; g_rgb NULL: SDF stack only, e.g. eikonal points); s_rgb [M,3] forward rgb.
  * dW_sdf / db_sdf / dW_col / db_col: per-layer gradient buffers in API order, ACCUMULATED into.
  * workspace >= i2sdf_backward_workspace_bytes(h, M). */
 int i2sdf_fused_backward(i2sdf_handle* h, const float* pts, const float* o, const float* d, const float* z, int zstride,
-                         int ns, int64_t M, void* saved, const float* s_rgb, const float* g_sdf, const float* g_grad,
+                         int ns, int64_t M, int64_t m_rays, void* saved, const float* s_rgb, const float* g_sdf, const float* g_grad,
                          const float* g_rgb, float* const* dW_sdf, float* const* db_sdf, float* const* dW_col,
                          float* const* db_col, void* workspace, size_t workspace_bytes, void* stream);
 

@@ -467,25 +467,31 @@ def test_forward_saved_slots_and_fused_backward_vs_torch(cases):
     d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=1).cuda()
     z = torch.sort(torch.rand(R, N + 1, generator=g) * 1.5, dim=1)[0].cuda()
     M = R * N
-    x = (o[:, None, :] + z[:, :N, None] * d[:, None, :]).reshape(M, 3)
-    dirs = d[:, None, :].expand(R, N, 3).reshape(M, 3)
+    E = 100                                        # explicit points riding the same launches (eikonal / smoothness points)
+    xe = ((torch.rand(E, 3, generator=g) - 0.5) * 2.0).cuda()
+    x = torch.cat([(o[:, None, :] + z[:, :N, None] * d[:, None, :]).reshape(M, 3), xe])
+    dirs = torch.cat([d[:, None, :].expand(R, N, 3).reshape(M, 3), torch.tensor([[0.0, 0.0, 1.0]]).cuda().expand(E, 3)])
     ref = _torch_stacks(m, x, dirs)
     Ws, bs = m.effective_weights()
     n_sdf, n_col = m.implicit_network.num_layers - 1, m.rendering_network.num_layers - 1
     params = [w.detach().contiguous().requires_grad_(True) for w in Ws] + [t.detach().clone().requires_grad_(True) for t in bs]
     P = params[:n_sdf] + params[n_sdf + n_col:2 * n_sdf + n_col] + params[n_sdf:n_sdf + n_col] + params[2 * n_sdf + n_col:]
-    s_sdf, s_grad, s_rgb, _ = _PointsFn.apply(core, o, d, z, True, n_sdf, n_col, 0, *P)
-    assert relerr(s_sdf, ref["sdf"].float()) < TOL and relerr(s_rgb, ref["rgb"].float()) < TOL and relerr(s_grad, ref["grad"].float()) < 3e-4
+    s_sdf, s_grad, s_rgb, _, x_grad = _PointsFn.apply(core, o, d, z, xe, True, n_sdf, n_col, 0, *P)
+    assert s_sdf.shape == (M,) and s_grad.shape == (M, 3) and s_rgb.shape == (M, 3) and x_grad.shape == (E, 3)
+    assert relerr(s_sdf, ref["sdf"][:M].float()) < TOL and relerr(s_rgb, ref["rgb"][:M].float()) < TOL
+    assert relerr(s_grad, ref["grad"][:M].float()) < 3e-4 and relerr(x_grad, ref["grad"][M:].float()) < 3e-4
     # saved H slots = inputs of SDF layers 1.. ; slot l lives at l * slot_bytes
     saved = s_sdf.grad_fn.saved_tensors[3]
-    big = core.lib.i2sdf_planes_slot_bytes(M, 256)
+    big = core.lib.i2sdf_planes_slot_bytes(M + E, 256)
     for l, h_ref in enumerate(ref["hs"]):
-        mine = core.planes_unpack(saved[l * big:(l + 1) * big], M)
+        mine = core.planes_unpack(saved[l * big:(l + 1) * big], M + E)
         assert relerr(mine, h_ref.float()) < 1e-4, (l, relerr(mine, h_ref.float()))
     # backward: random upstreams on all three outputs -> every weight / bias gradient, first and second order
     us, ug, ur = (torch.randn(M, generator=g).cuda(), torch.randn(M, 3, generator=g).cuda() * 0.1, torch.randn(M, 3, generator=g).cuda())
-    (s_sdf * us).sum().add((s_grad * ug).sum()).add((s_rgb * ur).sum()).backward()
-    lref = (ref["sdf"] * us.double()).sum() + (ref["grad"] * ug.double()).sum() + (ref["rgb"] * ur.double()).sum()
+    ux = torch.randn(E, 3, generator=g).cuda() * 0.3
+    (s_sdf * us).sum().add((s_grad * ug).sum()).add((s_rgb * ur).sum()).add((x_grad * ux).sum()).backward()
+    lref = ((ref["sdf"][:M] * us.double()).sum() + (ref["grad"][:M] * ug.double()).sum() + (ref["rgb"][:M] * ur.double()).sum()
+            + (ref["grad"][M:] * ux.double()).sum())
     gref = torch.autograd.grad(lref, ref["W"] + ref["b"])
     nW = len(ref["W"])
     mine = params[:nW] + params[nW:]
@@ -494,7 +500,10 @@ def test_forward_saved_slots_and_fused_backward_vs_torch(cases):
         assert p.grad is not None, i
         e = float((p.grad.double() - gr).norm() / gr.norm().clamp(min=1e-30))
         worst = max(worst, e)
-        assert e < 2e-3, (i, "W" if i < nW else "b", e)
+        # radiance stack (i >= n_sdf within W / b): a few ReLU masks flip under the 1e-5 feature error of the tensor-core forward,
+        # each flip moves the gradient by one point's contribution (same bound as the reference-fixture training tests)
+        col = (i % nW) >= n_sdf
+        assert e < (5e-3 if col else 2e-3), (i, "W" if i < nW else "b", e)
     print(f"fused backward vs torch fp64 autograd: worst relative L2 gradient error {worst:.2e}")
 
 
