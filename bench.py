@@ -34,8 +34,11 @@ sys.path.insert(0, ROOT)
 METRIC = "full-path ray-samples/sec through SDF+render MLPs"
 UNIT = "ray-samples/s"
 N_COMPOSITED = 97               # N_samples + 2 + N_samples_extra - 1  (model/network/__init__.py:99-100)
-FLOP_PER_SDF_EVAL = 918016      # algorithmic FLOP of one sampler sdf evaluation
-FLOP_PER_RAY_SAMPLE = 2506752   # SDF fwd + grad_x sweep + radiance, per composited sample
+# algorithmic FLOP (2 x MAC, dense layers only) per unit: one sampler sdf evaluation (sdf row of the last
+# layer only); one composited ray-sample = SDF fwd + grad_x sweep + radiance (+ light head)
+FLOPS = {"synthetic": dict(sdf_eval=918016, ray_sample=2506752),
+         "synthetic_light_mask": dict(sdf_eval=2 * (393472 - 65536), ray_sample=1917184)}
+FLOP_PER_SDF_EVAL = FLOPS["synthetic"]["sdf_eval"]
 
 
 def parse():
@@ -45,6 +48,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=1024)
+    ap.add_argument("--config", default="synthetic", choices=["synthetic", "synthetic_light_mask"],
+                    help="synthetic (default, BASELINE.json configs[1]/[2]) or synthetic_light_mask (configs[3]: 6x256 SDF, 3x256 "
+                         "radiance, light-mask head, light_mask_weight 0.5)")
     ap.add_argument("--cpu-rays", type=int, default=128, help="rays per step of the CPU arms (bounded sample)")
     ap.add_argument("--mode", default="train", choices=["render", "train"],
                     help="train (default, BASELINE.json configs[1]): full training step on a 1024-ray batch (forward + I2SDFLoss + "
@@ -53,11 +59,11 @@ def parse():
     return ap.parse_args()
 
 
-def build_params(beta=0.01):
+def build_params(beta=0.01, name="synthetic"):
     """W-sharp: reference geometric init (seed 0) with density.beta = 0.01."""
     from i2sdf_b200 import configs
     from i2sdf_b200.network import I2SDFNetwork
-    conf = configs.model_conf("synthetic")
+    conf = configs.model_conf(name)
     torch.manual_seed(0)
     import contextlib
     import io
@@ -171,26 +177,37 @@ def peaks():
     return dict(bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, hbm_gbs=6650.0, source="B200_PROFILING.md fallback (of fallback)")
 
 
-def make_train_gt(R, seed):
+def make_train_gt(R, seed, light=False):
     g = torch.Generator().manual_seed(seed)
-    return {
+    gt = {
         "rgb": torch.rand(R, 3, generator=g),
         "depth": torch.rand(R, generator=g) * 2 + 0.5,
         "depth_mask": torch.ones(R, dtype=torch.bool),
         "normal": torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1),
         "normal_mask": torch.ones(R, dtype=torch.bool),
     }
+    if light:
+        gt["light_mask"] = (torch.rand(R, 1, generator=g) > 0.9).float()
+    return gt
 
 
-def cpu_train_arm(conf, model, rays, steps, warmup):
+def loss_weights(name):
+    from i2sdf_b200 import configs
+    src = configs.LOSS_SYNTHETIC_LIGHT_MASK if name == "synthetic_light_mask" else configs.LOSS_SYNTHETIC
+    keys = ("eikonal_weight", "smooth_weight", "depth_weight", "normal_weight", "bubble_weight", "light_mask_weight")
+    return src, {k: v for k, v in src.items() if k in keys}
+
+
+def cpu_train_arm(conf, model, rays, steps, warmup, name="synthetic"):
     """Reference training step (forward + I2SDFLoss + backward incl. double backward) on the CPU: oracle port."""
     from i2sdf_b200 import configs
     from oracle import i2sdf_oracle as orc
     spec = orc.spec_from_model_conf(conf, use_normal=True)
     P0 = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     inp = orc.synthetic_rays(rays, seed=1, train_layout=True)
-    gt = make_train_gt(rays, 7)
-    lw = {k: v for k, v in configs.LOSS_SYNTHETIC.items() if k in ("eikonal_weight", "smooth_weight", "depth_weight", "normal_weight", "bubble_weight")}
+    light = name == "synthetic_light_mask"
+    gt = make_train_gt(rays, 7, light)
+    lw = loss_weights(name)[1]
 
     def tape(n_final_guess=None):
         R = rays
@@ -214,7 +231,7 @@ def cpu_train_arm(conf, model, rays, steps, warmup):
               "extra_perm": lambda n: torch.randperm(n)[:spec.n_samples_extra], "eik_idx": torch.randint(98, (R,)),
               "eik_uniform": torch.empty(R, 3).uniform_(-3, 3), "nbr_uniform": torch.empty(R, 3).uniform_(-0.005, 0.005)}
         out = orc.render(spec, P, probe_inp, training=True, tape=tp)
-        orc.recon_loss(out, make_train_gt(R, 3), smooth_active=False, **lw).backward()
+        orc.recon_loss(out, make_train_gt(R, 3, light), smooth_active=False, **lw).backward()
 
     pick_cpu_threads(probe)
     times = []
@@ -240,7 +257,9 @@ def gpu_arm(args, rank, world, local_rank):
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
     train = args.mode == "train"
-    conf, model = build_params()
+    conf, model = build_params(name=args.config)
+    light = args.config == "synthetic_light_mask"
+    flops = FLOPS[args.config]
     if train:
         model.use_normal = True          # trainer sets it from loss.normal_weight (model/trainer/recon.py:34-35)
     cpu_snapshot = {k: v.detach().clone() for k, v in model.state_dict().items()} if rank == 0 else None
@@ -250,14 +269,14 @@ def gpu_arm(args, rank, world, local_rank):
     R = args.rays
     # rank-specific rays: the global batch is world * R rays sharded across ranks
     inp_host = {k: v.pin_memory() for k, v in orc.synthetic_rays(R, seed=1 + rank, train_layout=train).items()}
-    gt_host = {k: v.pin_memory() for k, v in make_train_gt(R, 7 + rank).items()} if train else {}
+    gt_host = {k: v.pin_memory() for k, v in make_train_gt(R, 7 + rank, light).items()} if train else {}
     inp_dev = {k: v.to(dev) for k, v in inp_host.items()}
     gt_dev = {k: v.to(dev) for k, v in gt_host.items()}
     core = model_gpu._ready_core()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
     out_host = {}
     if train:
-        loss_fn = I2SDFLoss(**configs.LOSS_SYNTHETIC)
+        loss_fn = I2SDFLoss(**loss_weights(args.config)[0])
         # Adam(lr, eps=1e-15) as model/trainer/recon.py:201-207; fused=True is the same update as one multi-tensor kernel
         opt = torch.optim.Adam(model_gpu.parameters(), lr=5.0e-4, eps=1e-15, fused=True)
         loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
@@ -346,12 +365,12 @@ def gpu_arm(args, rank, world, local_rank):
     sdf_launches = max(sdf["launches"], 1)
     pts_per_launch = R * 128
     per_launch_ms = sdf["ms"] / sdf_launches
-    achieved = pts_per_launch * FLOP_PER_SDF_EVAL / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
+    achieved = pts_per_launch * flops["sdf_eval"] / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
     peak = pk["bf16_tflops_sustained"] if core.uses_tensor_cores else 72.0
     launches = sum(v["launches"] for v in prof.values())
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_tc_sdf_traffic.json")
-    if core.uses_tensor_cores and os.path.exists(tpath) and R == 1024:
+    if core.uses_tensor_cores and os.path.exists(tpath) and R == 1024 and not light:
         traffic = json.load(open(tpath))["dram_bytes_per_launch"]      # from the committed ncu --set full capture
     h2d = sum(v.numel() * v.element_size() for v in list(inp_host.values()) + list(gt_host.values()))
     d2h = 4 if train else sum(v.numel() * v.element_size() for v in out_host.values())
@@ -365,12 +384,16 @@ def gpu_arm(args, rank, world, local_rank):
     else:
         workload = ("C2/C3 batch shape: 1024-ray forward render, config/synthetic.yml networks (8x256 SDF + 4x256 radiance), "
                     "eval layout: sampler 5 rounds = 640 sdf-evals/ray + 97 composited samples/ray")
+    if light:
+        workload = workload.replace("C2: training step", "C4: training step").replace("C2/C3 batch shape", "C4 batch shape") \
+            .replace("config/synthetic.yml networks (8x256 SDF + 4x256 radiance)", "config/synthetic_light_mask.yml networks (6x256 SDF + 3x256 radiance + light-mask head)") \
+            .replace("config/synthetic.yml networks and loss weights", "config/synthetic_light_mask.yml networks (6x256 SDF, 3x256 radiance, light-mask head) and loss weights (+ light-mask BCE 0.5)")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_res / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (bf16 hi/lo split products on tcgen05, fp32 accumulate)" if core.uses_tensor_cores else "f32",
         "data": "synthetic",
-        "config": {"workload": workload, "mode": args.mode,
+        "config": {"workload": workload, "mode": args.mode, "network_config": args.config,
                    "weights": "W-sharp: reference geometric init (seed 0), density.beta=0.01 so all 5 sampler rounds run",
                    "rays_per_gpu": R, "global_rays": world * R, "samples_per_ray_composited": N_COMPOSITED,
                    "sdf_evals_per_ray": 5 * 128 + N_COMPOSITED,
@@ -385,12 +408,12 @@ def gpu_arm(args, rank, world, local_rank):
         "roofline": {"bound": "tensor", "kernel": "sdf_tc_kernel (sampler SDF evaluations)" if core.uses_tensor_cores else "mlp_tile_kernel",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                      "traffic": traffic, "traffic_unit": "bytes of DRAM traffic per launch (ncu --set full, profiles/r01_tc_sdf_traffic.json)",
-                     "flop_per_launch": pts_per_launch * FLOP_PER_SDF_EVAL, "ms_per_launch": per_launch_ms,
+                     "flop_per_launch": pts_per_launch * flops["sdf_eval"], "ms_per_launch": per_launch_ms,
                      "peak_source": pk["source"] + (", sustained bf16 (kernel timed inside a step)" if core.uses_tensor_cores else "; fp32 FMA peak 148 SM x 128 FMA x 2 x 1.9 GHz"),
                      "note": "achieved counts ALGORITHMIC flops (1 MAC = 2 flop); the kernel issues 3 bf16 MMAs per MAC, so 1/3 of the bf16 peak is this precision scheme's ceiling"},
         "clocks": clocks,
     }
-    if train and core.fused_main and prof["weight_grads"]["launches"] > 0:
+    if train and core.fused_main and prof["weight_grads"]["launches"] > 0 and not light:
         # the two other heavy kernels of the training step, both bounded by HBM: algorithmic bytes = plane slots read / written
         tile = lambda m: (m + 127) // 128                                                     # noqa: E731
         big = lambda m: tile(m) * 131072                                                      # noqa: E731
@@ -411,7 +434,7 @@ def gpu_arm(args, rank, world, local_rank):
                           "workload": "eval forward render of the same 1024-ray batch (no backward, no collective), device-resident inputs"}
     model_c = type("S", (), {"state_dict": lambda self: cpu_snapshot})()
     if train:
-        cb = cpu_train_arm(conf, model_c, max(args.cpu_rays // 4, 16), steps=1, warmup=1)
+        cb = cpu_train_arm(conf, model_c, max(args.cpu_rays // 4, 16), steps=1, warmup=1, name=args.config)
     else:
         cb = cpu_arm(conf, model_c, args.cpu_rays, steps=2, warmup=1)
     line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port", "sample": cb["sample"]}
@@ -426,9 +449,9 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        conf, model = build_params()
+        conf, model = build_params(name=args.config)
         if args.mode == "train":
-            cb = cpu_train_arm(conf, model, max(args.cpu_rays // 4, 16), steps=args.steps, warmup=args.warmup)
+            cb = cpu_train_arm(conf, model, max(args.cpu_rays // 4, 16), steps=args.steps, warmup=args.warmup, name=args.config)
         else:
             cb = cpu_arm(conf, model, args.cpu_rays, steps=args.steps, warmup=args.warmup)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,

@@ -95,6 +95,9 @@ class _PointsFn(Function):
                                             g_xgrad if g_xgrad is not None else o.new_zeros(E, 3)])
                 core.fused_backward(M + E, act, dW_sdf, db_sdf, rays=(o, d, z, N), pts=extra_pts if E else None, s_rgb=s_rgb, g_sdf=g_sdf,
                                     g_grad=g_grad, g_rgb=g_rgb, dW_col=dW_col, db_col=db_col)
+            if n_light > 0 and g_light is not None:
+                # the head's own parameters only: its input features are detached (network/__init__.py:165)
+                core.light_backward(W_l, b_l, feat[:M], s_light, g_light, dW_l, db_l)
             return (None,) * 9 + tuple(dW_sdf + db_sdf + dW_col + db_col + dW_l + db_l)
         g_feat_ptr, ld = None, 256
         if g_rgb is not None:
@@ -214,7 +217,7 @@ def forward_train(model, core, input, predict_only=False):
         near = o + z_eik[:, None] * d
         nbr_u = ov["nbr_uniform"].to(dev) if "nbr_uniform" in ov else torch.empty_like(near).uniform_(-0.005, 0.005)
         pts = torch.cat([eik_u, near, near + nbr_u], 0)
-    ride = pts is not None and core.fused_main and n_light == 0
+    ride = pts is not None and core.fused_main
     s_sdf, s_grad, s_rgb, s_light, x_grad = _PointsFn.apply(core, o, d, z, pts if ride else None, want_grad, n_sdf, n_col, n_light, *params)
     rgb, depth, wsum, normal, light = _CompositeFn.apply(core, z, dnorm, beta, s_sdf, s_rgb, s_grad, s_light,
                                                          want_grad and not predict_only, n_light > 0)

@@ -113,10 +113,10 @@ class RenderCore:
         check(self.lib.i2sdf_profile_enable(self.h, int(enable)), "i2sdf_profile_enable")
 
     def profile_read(self):
-        ms = (C.c_float * 6)()
-        n = (C.c_int64 * 6)()
-        check(self.lib.i2sdf_profile_read_n(self.h, 6, ms, n), "i2sdf_profile_read_n")
-        kinds = ("sampler_sdf", "main_mlp", "sampler_rays", "misc", "backward_chain", "weight_grads")
+        ms = (C.c_float * 7)()
+        n = (C.c_int64 * 7)()
+        check(self.lib.i2sdf_profile_read_n(self.h, 7, ms, n), "i2sdf_profile_read_n")
+        kinds = ("sampler_sdf", "main_mlp", "sampler_rays", "misc", "backward_chain", "weight_grads", "light_head")
         return {k: dict(ms=float(ms[i]), launches=int(n[i])) for i, k in enumerate(kinds)}
 
     # ---- plane slots (HBM format of the fused training path; see csrc/planes.cuh)
@@ -253,11 +253,12 @@ class RenderCore:
         if E:
             extra_pts = _f32(extra_pts.detach(), dev)
         M = R * N + E
-        fused = save and self.fused_main and not want_light       # plane slots: features stay inside the saved state
+        fused = save and self.fused_main                          # plane slots: features stay inside the saved state
         out = dict(s_sdf=torch.empty(M, device=dev), s_rgb=torch.empty(M, 3, device=dev))
-        out["feat"] = None if fused else torch.empty(M, 256, device=dev)
+        # (with a light head the features are ALSO written as fp32: the head is a second pass over them, forward and backward)
+        out["feat"] = None if (fused and not want_light) else torch.empty(M, 256, device=dev)
         out["s_grad"] = torch.empty(M, 3, device=dev) if (want_grad or fused) else None
-        out["s_light"] = torch.empty(M, device=dev) if want_light else None
+        out["s_light"] = torch.empty(R * N, device=dev) if want_light else None
         out["act"] = torch.empty(self.lib.i2sdf_saved_bytes_points(self.h, M), dtype=torch.uint8, device=dev) if save else None
         out["fused"] = fused
         if E and not fused:

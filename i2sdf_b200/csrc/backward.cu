@@ -27,7 +27,7 @@ namespace i2sdf {
 // tensor-core GEMMs (tc_gemm.cu)
 size_t tc_wgrad_ws_floats(const i2sdf_handle* h);
 int tc_gemm_pw(const i2sdf_handle* h, cudaStream_t st, long long M, const float* A, int lda, int kvalid, const TcBlock& blk, float* C, int ldc,
-               int ncols, const float* bias, int relu);
+               int ncols, const float* bias, int relu);      // relu: bit 0 = ReLU on the output, bit 1 = ReLU on the input
 int tc_gemm_wgrad(const i2sdf_handle* h, cudaStream_t st, long long M, const float* P0, int ldp0, const float* X0, int ldx0, const float* P1,
                   int ldp1, const float* X1, int ldx1, int n1, int n2, float* dW, int ldw, float* ws);
 int tc_gemm_pw_ex(const i2sdf_handle* h, cudaStream_t st, long long M, const float* A, int lda, int kvalid, const TcBlock& blk, float* C, int ldc,
@@ -517,7 +517,9 @@ __global__ void light_mid_kernel(long long M, int lh, const float* __restrict__ 
 }
 }  // namespace bwd
 
-size_t light_backward_ws_floats(const i2sdf_handle* h, long long M) { return (size_t)M * 256 + (size_t)2 * M * h->net.lh + (size_t)M + 64; }
+size_t light_backward_ws_floats(const i2sdf_handle* h, long long M) {
+    return (size_t)M * 256 + (size_t)2 * M * h->net.lh + (size_t)M + 64 + (h->use_tc ? tc_wgrad_ws_floats(h) : 0);
+}
 
 int light_backward(const i2sdf_handle* h, long long M, const float* const* W, const float* const* b, const float* feat, const float* lm,
                    const float* glm, float* const* dW, float* const* db, float* ws, cudaStream_t st) {
@@ -528,17 +530,65 @@ int light_backward(const i2sdf_handle* h, long long M, const float* const* W, co
     float* A = LF + (size_t)M * 256;             // [M][lh]
     float* Hs = A + (size_t)M * lh;              // [M][lh]
     float* d1 = Hs + (size_t)M * lh;             // [M]
+    float* WGP = d1 + (size_t)M + 16;            // tensor-core weight-gradient partials
+    const TcBlock blk = h->use_tc ? tc_block(h, TCB_FWD_LIGHT, 0) : TcBlock{nullptr, 0, 0};
+    const bool tc = blk.ptr != nullptr;
     int rc;
     relu_copy_kernel<<<blocks((long long)M * 256), 256, 0, st>>>((long long)M * 256, feat, LF);
     I2SDF_CUDA_CHECK(cudaGetLastError());
-    if ((rc = gemm_nt(st, (int)M, lh, 256, LF, 256, W[0], 256, A, lh))) return rc;
+    if (tc) rc = tc_gemm_pw(h, st, M, LF, 256, 256, blk, A, lh, lh, nullptr, 0);       // recompute the hidden pre-activations (bias added below)
+    else rc = gemm_nt(st, (int)M, lh, 256, LF, 256, W[0], 256, A, lh);
+    if (rc) return rc;
     light_mid_kernel<<<blocks((long long)M * lh), 256, 0, st>>>(M, lh, b[0], W[1], lm, glm, A, Hs, d1);
     I2SDF_CUDA_CHECK(cudaGetLastError());
     if ((rc = colsum(st, M, lh, Hs, lh, d1, dW[1]))) return rc;          // dW1[0,:] += sum delta * h
     sum_kernel<<<64, 256, 0, st>>>(M, d1, db[1]);
     I2SDF_CUDA_CHECK(cudaGetLastError());
-    if ((rc = gemm_tn_acc(st, lh, 256, M, A, lh, LF, 256, dW[0], 256, h->num_sms))) return rc;
+    if (tc) rc = tc_gemm_wgrad(h, st, M, A, lh, LF, 256, nullptr, 0, nullptr, 0, lh, 256, dW[0], 256, WGP);
+    else rc = gemm_tn_acc(st, lh, 256, M, A, lh, LF, 256, dW[0], 256, h->num_sms);
+    if (rc) return rc;
     if ((rc = colsum(st, M, lh, A, lh, nullptr, db[0]))) return rc;
+    return I2SDF_OK;
+}
+
+// ================================================================================================
+// light-mask head forward behind the tensor-core main pass (model/network/__init__.py:162-170):
+//   lmask = sigmoid(w1 . softplus_100(W0 relu(feat) + b0) + b1)
+// The main-pass chain kernel has no room for a second 256-wide A operand (relu(feat) next to feat), so the head runs as
+// its own HBM-bound pass over the features that kernel writes: one tcgen05 GEMM (ReLU fused into the operand staging)
+// + one warp-per-point epilogue kernel.  32 896 of the path's ~1.0 M MACs per point.
+// ================================================================================================
+namespace bwd {
+// A [M][lh] = W0 relu(feat) + b0  ->  out[m] = sigmoid(w1 . softplus(A[m]) + b1);  head = [w1 (lh) | b1];  lh <= 128, lh % 4 == 0
+__global__ void __launch_bounds__(256) light_out_kernel(long long M, int lh, const float* __restrict__ A, const float* __restrict__ head,
+                                                        float* __restrict__ out) {
+    const long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (m >= M) return;
+    float acc = 0.f;
+    if (lane * 4 < lh) {
+        const float4 a = *reinterpret_cast<const float4*>(A + (size_t)m * lh + lane * 4);
+        const float4 w = __ldg(reinterpret_cast<const float4*>(head) + lane);
+        acc = fmaf(sp100(a.x), w.x, fmaf(sp100(a.y), w.y, fmaf(sp100(a.z), w.z, sp100(a.w) * w.w)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[m] = __fdiv_rn(1.0f, 1.0f + expf(-(acc + __ldg(head + lh))));
+}
+}  // namespace bwd
+
+size_t light_forward_ws_floats(const i2sdf_handle* h, long long M) { return (size_t)M * h->net.lh + 64; }
+
+int light_forward(const i2sdf_handle* h, long long M, const float* feat, float* out_light, float* ws, cudaStream_t st) {
+    using namespace bwd;
+    if (M <= 0) return I2SDF_OK;
+    const NetDev& n = h->net;
+    const TcBlock blk = h->use_tc ? tc_block(h, TCB_FWD_LIGHT, 0) : TcBlock{nullptr, 0, 0};
+    if (!blk.ptr || n.lh > 128 || (n.lh & 3)) { set_error("light_forward: tensor-core light block unavailable"); return I2SDF_E_INVALID; }
+    int rc;
+    if ((rc = tc_gemm_pw(h, st, M, feat, 256, 256, blk, ws, n.lh, n.lh, n.light_b0, /*relu: input*/ 2))) return rc;
+    light_out_kernel<<<blocks(M * 32), 256, 0, st>>>(M, n.lh, ws, n.light_head, out_light);
+    I2SDF_CUDA_CHECK(cudaGetLastError());
     return I2SDF_OK;
 }
 

@@ -43,6 +43,8 @@ int color_backward(const i2sdf_handle*, long long, int, const float*, const floa
                    const float*, float* const*, float* const*, float*, float**, int*, cudaStream_t);
 int light_backward(const i2sdf_handle*, long long, const float* const*, const float* const*, const float*, const float*, const float*,
                    float* const*, float* const*, float*, cudaStream_t);
+size_t light_forward_ws_floats(const i2sdf_handle*, long long);
+int light_forward(const i2sdf_handle*, long long, const float*, float*, float*, cudaStream_t);
 int launch_composite_backward(const i2sdf_handle*, const float*, const float*, const float*, const float*, const float*, const float*,
                               const float*, long long, int, const float*, const float*, const float*, const float*, const float*, float*,
                               float*, float*, float*, float*, cudaStream_t);
@@ -303,10 +305,32 @@ int i2sdf_pack_weights(i2sdf_handle* h, const float* const* W, const float* cons
 static size_t ws_sampler_floats(const i2sdf_handle* h, int64_t R) { return (sampler_ws_floats(h, R) + 63) / 64 * 64; }
 static size_t ws_scratch_floats(const i2sdf_handle* h) { return (mlp_simt_scratch_floats(h) + 63) / 64 * 64; }
 
+// Light-mask head behind the tensor-core main pass: the head is its own pass over the features the main pass writes
+// (light_forward, backward.cu).  Workspace region = [ hidden pre-activations: rows x lh | features: rows x 256 ] for one
+// chunk of at most kLightChunkRays rays (eval renders of more rays walk the chunks; training passes its own feature buffer).
+constexpr int64_t kLightChunkRays = 4096;
+static bool light_tc(const i2sdf_handle* h);
+static int64_t light_chunk_rays(int64_t R) { return R < kLightChunkRays ? R : kLightChunkRays; }
+static size_t ws_light_hidden_floats(const i2sdf_handle* h, int64_t R) { return (light_forward_ws_floats(h, light_chunk_rays(R) * 128) + 63) / 64 * 64; }
+static size_t ws_light_floats(const i2sdf_handle* h, int64_t R) {
+    if (!light_tc(h)) return 0;
+    return ws_light_hidden_floats(h, R) + (size_t)light_chunk_rays(R) * 128 * 256;
+}
+
 size_t i2sdf_workspace_bytes(const i2sdf_handle* h, int64_t R, int training) {
     (void)training;
     if (!h || R < 0) return 0;
-    return (ws_sampler_floats(h, R) + ws_scratch_floats(h) + (size_t)R * 128 * 8 + 64) * sizeof(float);
+    return (ws_sampler_floats(h, R) + ws_scratch_floats(h) + (size_t)R * 128 * 8 + 64 + ws_light_floats(h, R)) * sizeof(float);
+}
+// light head over rows [0, M) of feat, in chunks that fit the workspace's hidden buffer
+static int run_light(const i2sdf_handle* h, long long M, const float* feat, float* s_light, float* hidden, long long hidden_rows, cudaStream_t st) {
+    ProfScope ps(h, 6, st, 2);
+    for (long long m0 = 0; m0 < M; m0 += hidden_rows) {
+        const long long mc = (M - m0 < hidden_rows) ? M - m0 : hidden_rows;
+        int rc = light_forward(h, mc, feat + (size_t)m0 * 256, s_light + m0, hidden, st);
+        if (rc) return rc;
+    }
+    return I2SDF_OK;
 }
 
 int i2sdf_rays(i2sdf_handle* h, const float* uv, const float* pose, const float* intr, int B, int P, float* o, float* d,
@@ -322,8 +346,9 @@ static int run_mlp(const i2sdf_handle* h, const MlpParams& p, cudaStream_t st) {
     if (h->use_tc && sdf_only) return tc_launch_sdf(h, p, st);
     // eval main pass (sdf + grad_x + rgb per sample, nothing saved) -> tensor-core kernel
     // (training: pre-activations + features are saved for the backward instead of the per-CTA scratch)
+    // (a light head rides behind it as its own pass over p.out_feat: the callers clear want_light, see run_light)
     if (h->tcmain && tcmain_has_full(h->tcmain) && p.out_sdf && p.out_grad && p.out_rgb && p.want_color && !p.want_light &&
-        (p.scratch || p.sl.base) && !p.save_act && (p.sl.base || !p.out_feat) && (p.ray_d || p.pts))
+        (p.scratch || p.sl.base) && !p.save_act && (p.ray_d || p.pts))
         return tcmain_launch(h, h->tcmain, p, st);
     // sdf + features only (ImplicitNetwork.forward: mesh extraction, plots): F layers + feature layer; needs no scratch
     if (h->tcmain && p.out_sdf && p.out_feat && !p.out_grad && !p.want_color && !p.want_light && !p.save_act && !p.sl.base && (p.ray_d || p.pts))
@@ -339,6 +364,7 @@ static int run_mlp(const i2sdf_handle* h, const MlpParams& p, cudaStream_t st) {
 // 0 = fp32 pre-activations [L-1][M][256] (fp32 kernels + the layer-by-layer backward).  kind 0: main pass, 1: SDF points
 static bool planes_main(const i2sdf_handle* h) { return h->fused && h->tcmain && tcmain_has_full(h->tcmain); }
 static bool planes_sdf(const i2sdf_handle* h) { return h->fused && h->tcmain != nullptr; }
+static bool light_tc(const i2sdf_handle* h) { return h->net.Ll == 2 && h->use_tc && h->tcmain && tcmain_has_full(h->tcmain); }
 int i2sdf_saved_format(const i2sdf_handle* h, int kind) { return h ? ((kind == 0 ? planes_main(h) : planes_sdf(h)) ? 1 : 0) : 0; }
 
 size_t i2sdf_sdf_saved_bytes(const i2sdf_handle* h, int64_t M) {
@@ -442,24 +468,32 @@ int i2sdf_points_forward_ex(i2sdf_handle* h, const float* o, const float* d, con
                             int64_t n_extra, float* s_sdf, float* s_grad, float* s_rgb, float* s_light, float* s_feat, float* save_act,
                             void* workspace, size_t workspace_bytes, void* stream) {
     if (!h || !o || !d || !z || !s_sdf) { set_error("null argument"); return I2SDF_E_INVALID; }
-    if (n_extra < 0 || (n_extra > 0 && (!extra_pts || !planes_main(h) || s_light || !s_rgb || !s_grad))) {
-        set_error("points_forward_ex: extra points need the tensor-core main pass (no light head) with s_rgb and s_grad"); return I2SDF_E_INVALID;
+    if (n_extra < 0 || (n_extra > 0 && (!extra_pts || !planes_main(h) || !s_rgb || !s_grad))) {
+        set_error("points_forward_ex: extra points need the tensor-core main pass with s_rgb and s_grad"); return I2SDF_E_INVALID;
     }
     if (N < 1 || N > 128) { set_error("points_forward: N=%d unsupported", N); return I2SDF_E_INVALID; }
     if (s_light && h->net.Ll == 0) { set_error("points_forward: no light head"); return I2SDF_E_INVALID; }
     MlpParams p{};
     p.ray_o = o; p.ray_d = d; p.zarr = z; p.zstride = N + 1; p.ns = N; p.M = (long long)R * N + n_extra; p.round_idx = -1; p.beta_min = h->smp.beta_min;
     if (n_extra > 0) { p.pts = extra_pts; p.m_rays = (long long)R * N; }     // appended explicit points (eikonal / smoothness) ride the same launch
-    p.out_sdf = s_sdf; p.out_grad = s_grad; p.out_rgb = s_rgb; p.out_light = s_light; p.out_feat = s_feat;
-    p.want_color = s_rgb != nullptr; p.want_light = s_light != nullptr;
-    if (save_act && planes_main(h) && !s_light && s_rgb && s_grad) p.sl = planes::make_layout(p.M, h->net.L - 1, h->net.Lc, true, save_act, nullptr);
+    // tensor-core main pass + light head: the head is a second pass over the features (s_feat, rows of the R*N ray samples)
+    const bool ltc = s_light && light_tc(h) && s_rgb && s_grad && (!save_act || planes_main(h));
+    if (ltc && (!s_feat || !workspace || workspace_bytes < i2sdf_workspace_bytes(h, R, 0))) {
+        set_error("points_forward: the light head on the tensor-core path needs s_feat and the full workspace"); return I2SDF_E_WORKSPACE;
+    }
+    p.out_sdf = s_sdf; p.out_grad = s_grad; p.out_rgb = s_rgb; p.out_light = ltc ? nullptr : s_light; p.out_feat = s_feat;
+    p.want_color = s_rgb != nullptr; p.want_light = (s_light != nullptr) && !ltc;
+    if (save_act && planes_main(h) && (!s_light || ltc) && s_rgb && s_grad) p.sl = planes::make_layout(p.M, h->net.L - 1, h->net.Lc, true, save_act, nullptr);
     else p.save_act = save_act;
     if (s_grad && !save_act) {
         if (!workspace || workspace_bytes < ws_scratch_floats(h) * sizeof(float)) { set_error("points_forward: workspace too small"); return I2SDF_E_WORKSPACE; }
         p.scratch = (float*)workspace;
     }
     p.net = h->net;
-    return run_mlp(h, p, (cudaStream_t)stream);
+    int rc = run_mlp(h, p, (cudaStream_t)stream);
+    if (rc || !ltc) return rc;
+    float* hidden = (float*)workspace + ws_sampler_floats(h, R) + ws_scratch_floats(h) + (size_t)R * 128 * 8 + 64;
+    return run_light(h, (long long)R * N, s_feat, s_light, hidden, light_chunk_rays(R) * 128, (cudaStream_t)stream);
 }
 
 int i2sdf_composite_forward(i2sdf_handle* h, const float* z, const float* dnorm, const float* s_sdf, const float* s_rgb, const float* s_grad,
@@ -501,7 +535,7 @@ int i2sdf_light_backward(i2sdf_handle* h, const float* const* W, const float* co
     if (!h || !W || !b || !feat || !s_light || !g_light || !dW || !db || !workspace) { set_error("null argument"); return I2SDF_E_INVALID; }
     if (h->net.Ll != 2) { set_error("light_backward: network has no light head"); return I2SDF_E_INVALID; }
     if (workspace_bytes < i2sdf_backward_workspace_bytes(h, M)) { set_error("light_backward: workspace too small"); return I2SDF_E_WORKSPACE; }
-    ProfScope ps(h, 1, (cudaStream_t)stream, 8);
+    ProfScope ps(h, 6, (cudaStream_t)stream, 8);
     return light_backward(h, M, W, b, feat, s_light, g_light, dW, db, (float*)workspace, (cudaStream_t)stream);
 }
 
@@ -582,16 +616,29 @@ int i2sdf_render_forward(i2sdf_handle* h, const float* o, const float* d, const 
     if (!s_rgb && rgb) s_rgb = tmp + (size_t)R * 128 * 4;
     if (!s_light && light) s_light = tmp + (size_t)R * 128 * 7;
     (void)RN;
-    MlpParams p{};
-    p.ray_o = o; p.ray_d = d; p.zarr = z; p.zstride = N + 1; p.ns = N; p.M = (long long)R * N; p.round_idx = -1;
-    p.beta_min = h->smp.beta_min;
-    p.out_sdf = s_sdf; p.out_grad = s_grad; p.out_rgb = s_rgb; p.out_light = s_light;
-    p.want_color = s_rgb != nullptr; p.want_light = s_light != nullptr;
-    if (save && planes_main(h) && !s_light && s_rgb && s_grad) p.sl = planes::make_layout(p.M, h->net.L - 1, h->net.Lc, true, save, nullptr);
-    else p.save_act = (float*)save;
-    p.scratch = scratch;
-    p.net = h->net;
-    int rc = run_mlp(h, p, st);
+    // tensor-core main pass + light head: walk the rays in chunks; each chunk's features go to the workspace and the head
+    // (light_forward) turns them into the per-sample light mask
+    const bool ltc = s_light && light_tc(h) && s_rgb && s_grad && (!save || planes_main(h));
+    const int64_t CH = ltc ? light_chunk_rays(R) : R;
+    if (ltc && save && R > CH) { set_error("render_forward: saving state with a light head is limited to %lld rays per call", (long long)CH); return I2SDF_E_INVALID; }
+    float* lhidden = tmp + (size_t)R * 128 * 8 + 64;
+    float* lfeat = lhidden + ws_light_hidden_floats(h, R);
+    int rc = I2SDF_OK;
+    for (int64_t r0 = 0; r0 < R && rc == I2SDF_OK; r0 += (CH > 0 ? CH : 1)) {
+        const int64_t rc_rays = (R - r0 < CH) ? R - r0 : CH;
+        MlpParams p{};
+        p.ray_o = o + r0 * 3; p.ray_d = d + r0 * 3; p.zarr = z + r0 * (N + 1); p.zstride = N + 1; p.ns = N; p.M = (long long)rc_rays * N; p.round_idx = -1;
+        p.beta_min = h->smp.beta_min;
+        p.out_sdf = s_sdf + r0 * N; p.out_grad = s_grad ? s_grad + r0 * N * 3 : nullptr; p.out_rgb = s_rgb ? s_rgb + r0 * N * 3 : nullptr;
+        p.out_light = ltc ? nullptr : s_light; p.out_feat = ltc ? lfeat : nullptr;
+        p.want_color = s_rgb != nullptr; p.want_light = (s_light != nullptr) && !ltc;
+        if (save && planes_main(h) && (!s_light || ltc) && s_rgb && s_grad) p.sl = planes::make_layout(p.M, h->net.L - 1, h->net.Lc, true, save, nullptr);
+        else p.save_act = (float*)save;
+        p.scratch = scratch;
+        p.net = h->net;
+        rc = run_mlp(h, p, st);
+        if (rc == I2SDF_OK && ltc) rc = run_light(h, p.M, lfeat, s_light + r0 * N, lhidden, CH * 128, st);
+    }
     if (rc) return rc;
     ProfScope ps(h, 3, st);
     return launch_composite(h, z, dnorm, s_sdf, s_rgb, s_grad, s_light, beta_param, R, N, rgb, depth, weight_sum, normal, light, s_w, st);

@@ -115,7 +115,7 @@ int launch_mlp_simt(const i2sdf_handle* h, const MlpParams& p, cudaStream_t stre
 size_t mlp_simt_scratch_floats(const i2sdf_handle* h);
 
 // ---- tensor-core weight blocks (mlp_tc3.cu) used by the backward GEMMs (tc_gemm.cu) -----------------
-enum { TCB_FWD_SDF = 0, TCB_FWD_FEAT, TCB_FWD_COL, TCB_REV_SDF, TCB_REV_FEAT, TCB_REV_COL };
+enum { TCB_FWD_SDF = 0, TCB_FWD_FEAT, TCB_FWD_COL, TCB_REV_SDF, TCB_REV_FEAT, TCB_REV_COL, TCB_FWD_LIGHT };
 struct TcBlock { const uint8_t* ptr; int ksteps; int n; };     // bf16 hi/lo k-step blocks of n*64 bytes
 TcBlock tc_block(const i2sdf_handle* h, int role, int layer);
 

@@ -442,6 +442,7 @@ struct State {
     int n_pack;               // number of ops to pack
     // weight blocks by role, for the backward GEMMs (tc_gemm.cu): index into full.ops, -1 = absent
     int blk_fwd_sdf[kMaxLayers], blk_fwd_feat, blk_fwd_col[kMaxLayers], blk_rev_sdf[kMaxLayers], blk_rev_feat, blk_rev_col[kMaxLayers];
+    int blk_fwd_light;        // light head layer 0 (N = light_hidden), consumed by tc_gemm_pw (the head runs as its own small pass)
 };
 
 }  // namespace tc3
@@ -451,7 +452,8 @@ int tc_create(i2sdf_handle* h) {
     State* s = new State();
     const NetDev& n = h->net;
     const int L = n.L, NL = L - 1, Lc = n.Lc;
-    const bool want_full = (n.Ll == 0) && !(getenv("I2SDF_SIMT_MAIN") && getenv("I2SDF_SIMT_MAIN")[0] == '1');
+    // (the light-mask head is not an op of the chain: it reads the features the main pass writes, see light_forward in backward.cu)
+    const bool want_full = !(getenv("I2SDF_SIMT_MAIN") && getenv("I2SDF_SIMT_MAIN")[0] == '1');
     OpTable& T = s->full;
     int nops = 0;
     size_t off = 0;
@@ -463,7 +465,7 @@ int tc_create(i2sdf_handle* h) {
         ++nops;
     };
     for (int i = 0; i < kMaxLayers; ++i) s->blk_fwd_sdf[i] = s->blk_fwd_col[i] = s->blk_rev_sdf[i] = s->blk_rev_col[i] = -1;
-    s->blk_fwd_feat = s->blk_rev_feat = -1;
+    s->blk_fwd_feat = s->blk_rev_feat = s->blk_fwd_light = -1;
     for (int l = 0; l < NL; ++l) { s->blk_fwd_sdf[l] = nops; add(l == 0 ? 3 : 16, 256, l == NL - 1 ? EK_SDF_LAST : EK_SDF_HIDDEN, l, l, 0, 0, 0); }
     s->blk_fwd_feat = nops;
     add(16, 256, EK_FEAT, L - 1, L - 1, 0, 1, 0);
@@ -477,6 +479,7 @@ int tc_create(i2sdf_handle* h) {
     for (int l = Lc - 2; l >= 1; --l) { s->blk_rev_col[l] = nops; add(16, 256, -1, l, L + l, 1, 0, 0); }
     s->blk_rev_col[0] = nops;
     add(16, 256, -1, 0, L, 1, 0, n.ed);                                          // feature columns of radiance layer 0
+    if (n.Ll == 2) { s->blk_fwd_light = nops; add(16, n.lh, -1, 0, L + Lc, 0, 0, 0); }   // light layer 0: [lh out][256 in]
     s->n_pack = nops;
     T.nops = want_full ? n_kernel_ops : 0;
     if (cudaMalloc(&s->wpack, off) != cudaSuccess) { delete s; set_error("tc_create: cudaMalloc failed"); return I2SDF_E_CUDA; }
@@ -564,6 +567,7 @@ TcBlock tc_block(const i2sdf_handle* h, int role, int layer) {
         case TCB_REV_SDF: idx = s->blk_rev_sdf[layer]; break;
         case TCB_REV_FEAT: idx = s->blk_rev_feat; break;
         case TCB_REV_COL: idx = s->blk_rev_col[layer]; break;
+        case TCB_FWD_LIGHT: idx = s->blk_fwd_light; break;
     }
     if (idx < 0) return b;
     const Op& o = s->full.ops[idx];

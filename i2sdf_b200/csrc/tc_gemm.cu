@@ -40,6 +40,7 @@ struct PWArgs {
     // optional fused input transform (tangent forward):  A'[m][k] = softplus'(A[m][k]) * A2[m][k]
     //   (+ skip concat: k >= nsplit -> E2[m][k - nsplit]; everything / sqrt2)
     const float* A2; int lda2; int is_skip; int nsplit; const float* E2;
+    int in_relu;                               // A'[m][k] = max(A[m][k], 0)  (light head: relu(features))
 };
 
 // fast softplus_100 and its derivative (same approximations as the forward tensor-core kernels)
@@ -174,6 +175,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_pw_kernel(const PWArgs G) {
                 } else {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) hv[j] = (rowok && col0 + j < G.kvalid) ? arow[col0 + j] : 0.f;
+                }
+                if (G.in_relu) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) hv[j] = fmaxf(hv[j], 0.f);
                 }
                 if (G.A2) {          // fused: softplus'(a) * adot  (+ skip concat)
                     const float* a2 = G.A2 + (size_t)(rowok ? m : 0) * G.lda2 + col0;
@@ -454,6 +459,7 @@ int tc_gemm_pw_ex(const i2sdf_handle* h, cudaStream_t st, long long M, const flo
     G.A = A; G.lda = lda; G.kvalid = kvalid; G.M = M; G.B = blk.ptr; G.ksteps = blk.ksteps; G.n = blk.n; G.C = C; G.ldc = ldc; G.ncols = ncols;
     G.bias = bias; G.relu = relu;
     G.A2 = A2; G.lda2 = lda2; G.is_skip = is_skip; G.nsplit = nsplit; G.E2 = E2;
+    G.in_relu = (relu & 2) ? 1 : 0; G.relu = relu & 1;       // relu bit 0: ReLU on the output, bit 1: ReLU on the input
     long long ntiles = (M + TM - 1) / TM;
     int grid = (int)(ntiles < (long long)h->num_sms ? ntiles : (long long)h->num_sms);
     gemm_pw_kernel<<<grid, NTHREADS, kSmemPW, st>>>(G);

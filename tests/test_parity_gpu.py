@@ -532,3 +532,34 @@ def test_fused_sdf_points_backward_vs_torch(cases):
     for i, (p, gr) in enumerate(zip(W + b, gref)):
         e = float((p.grad.double() - gr).norm() / gr.norm().clamp(min=1e-30))
         assert e < 2e-3, (i, e)
+
+
+def test_light_head_chunked_render_is_consistent(cases):
+    """Light-mask config on the tensor-core main pass: the head runs as its own pass over the features of <= 4096-ray chunks
+    (i2sdf_render_forward); a render that spans two chunks must equal the renders of its parts."""
+    c = cases["eval_light_sharp"]
+    m = _model(c)
+    core = m._ready_core()
+    assert core.uses_tensor_cores_main, "the light-mask config must run its main pass on the tensor cores"
+    R, cut = 4096 + 200, 4096
+    inp = orc.synthetic_rays(R, seed=9)
+    o, d, dn = (t.cuda() for t in orc.flatten_rays(inp["uv"], inp["pose"], inp["intrinsics"]))
+    g = torch.Generator().manual_seed(11)
+    z = torch.sort(torch.rand(R, core.n_out, generator=g) * 6.0, dim=1).values
+    z[:, -1] = 6.0
+    z = z.cuda()
+    beta = m.density.beta.detach()
+    whole = core.render(o, d, dn, z, beta, want_normal=True, want_light=True, per_sample=True)
+    tail = core.render(o[cut:].contiguous(), d[cut:].contiguous(), dn[cut:].contiguous(), z[cut:].contiguous(), beta,
+                       want_normal=True, want_light=True, per_sample=True)
+    head = core.render(o[:300].contiguous(), d[:300].contiguous(), dn[:300].contiguous(), z[:300].contiguous(), beta,
+                       want_normal=True, want_light=True, per_sample=True)
+    N = core.n_out - 1
+    for k in ("s_sdf", "s_light", "s_rgb"):
+        w = whole[k].reshape(R, N, -1)
+        assert torch.equal(w[cut:], tail[k].reshape(R - cut, N, -1)), k
+        assert relerr(w[:300], head[k].reshape(300, N, -1)) < 1e-6, k
+    for k in ("rgb", "light", "depth"):
+        assert torch.equal(whole[k][cut:], tail[k]), k
+    assert 0.0 < float(whole["s_light"].min()) and float(whole["s_light"].max()) < 1.0       # per-sample sigmoid outputs
+    assert 0.0 <= float(whole["light"].min()) and float(whole["light"].max()) < 1.0 + 1e-5   # composited with weights summing to <= 1
