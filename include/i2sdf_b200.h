@@ -173,7 +173,9 @@ int i2sdf_points_forward(i2sdf_handle* h, const float* o, const float* d, const 
 
 /* Same with n_extra explicit points [n_extra,3] appended after the R*N ray samples (the eikonal / smoothness points of
  * model/network/__init__.py:175-193 ride the main-pass launch): every per-sample output has R*N + n_extra rows, the
- * saved state is sized by i2sdf_saved_bytes_points(h, R*N + n_extra).  Tensor-core main pass only. */
+ * saved state is sized by i2sdf_saved_bytes_points(h, R*N + n_extra).  Tensor-core main pass only.
+ * Networks with a light-mask head: s_light keeps R*N rows (the head is evaluated on the ray samples only, as its own pass
+ * over s_feat, which is then REQUIRED together with workspace >= i2sdf_workspace_bytes(h, R, 0)). */
 int i2sdf_points_forward_ex(i2sdf_handle* h, const float* o, const float* d, const float* z, int64_t R, int N,
                             const float* extra_pts, int64_t n_extra, float* s_sdf, float* s_grad, float* s_rgb,
                             float* s_light, float* s_feat, float* save_act, void* workspace, size_t workspace_bytes,
@@ -220,7 +222,8 @@ int i2sdf_sdf_backward(i2sdf_handle* h, const float* const* W, const float* pts,
  * i2sdf_profile_read synchronises the device and returns summed event durations (ms) and launch counts. */
 int i2sdf_profile_enable(i2sdf_handle* h, int enable);
 int i2sdf_profile_read(i2sdf_handle* h, float ms[4], int64_t launches[4]);
-/* same with n <= 8 classes: 4 = backward chain kernel (fused training path), 5 = weight-gradient kernel. */
+/* same with n <= 8 classes: 4 = backward chain kernel (fused training path), 5 = weight-gradient kernel,
+ * 6 = light-mask head (forward pass over the features + its backward). */
 int i2sdf_profile_read_n(i2sdf_handle* h, int n, float* ms, int64_t* launches);
 
 /* What a forward in training mode saves for the backward.  format 1 = plane slots (tensor-core chain kernels; consumed
