@@ -32,6 +32,7 @@ SYMBOLS = {
     "i2sdf_sdf_forward": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "i2sdf_sampler_rounds": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P, C.c_size_t, _P]),
     "i2sdf_sampler_finalize": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "i2sdf_sampler_finalize_candidates": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "i2sdf_sampler_info": (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_size_t, _P]),
     "i2sdf_sampler_round_debug": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, _P, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     "i2sdf_render_forward": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int, _P] + [_P] * 10 + [_P, C.c_size_t, _P, C.c_size_t, _P]),

@@ -189,6 +189,11 @@ def sdf_with_grad(model, x):
 def forward_train(model, core, input, predict_only=False):
     """I2SDFNetwork.forward with self.training == True (model/network/__init__.py:80-209)."""
     ov = getattr(model, "_tape_override", None) or {}
+    # effective weights W = g v/|v| (mlp.py:71-72) once per step: differentiable inputs of the Functions below, and the source
+    # of the packed device copies every kernel of this step reads (two launches)
+    Ws, bs = model.effective_weights()
+    core.pack(Ws, bs)
+    model._packed_key = model._param_key()
     o, d, dnorm = core.rays(input["uv"], input["pose"], input["intrinsics"])
     R, dev = o.shape[0], o.device
     beta = model.density.beta
@@ -196,8 +201,7 @@ def forward_train(model, core, input, predict_only=False):
         z, z_eik = ov["z_all"].to(dev).contiguous(), ov["z_eik"].to(dev).reshape(-1).contiguous()
     else:
         tape = {k: ov[k] for k in ("jitter", "u_final", "extra_perm", "eik_idx") if k in ov} or model._draw_sampler_tape(R, dev)
-        z, z_eik = core.sample(o, d, beta.detach(), tape)
-    Ws, bs = model.effective_weights()
+        z, z_eik = core.sample(o, d, beta.detach(), tape, defer_sync=True)      # resolved below, behind the main pass
     n_sdf = model.implicit_network.num_layers - 1
     n_col = model.rendering_network.num_layers - 1
     n_light = (model.light_network.num_layers - 1) if model.use_light else 0
@@ -224,6 +228,9 @@ def forward_train(model, core, input, predict_only=False):
     res = {"rgb_values": rgb, "depth_values": depth, "weight_sum": wsum[:, None]}
     if n_light > 0:
         res["light_mask"] = light[:, None]
+    # the sampler's round count is read back only now: the main pass is queued behind it, so the device stays busy while the
+    # host waits, then replays the reference's one CPU-generator draw (randperm(n), ray_sampler.py:223)
+    core.sampler_resolve()
     if predict_only:
         return res
     sdf_params = [w.contiguous() for w in W_sdf] + list(b_sdf)

@@ -184,9 +184,16 @@ class RenderCore:
                                          _ptr(ws), self._ws_bytes, self._stream()), "i2sdf_sdf_forward")
         return sdf, feat, grad
 
-    def sample(self, o, d, beta_param, tape: Optional[Dict[str, torch.Tensor]] = None, want_info=False):
+    def sample(self, o, d, beta_param, tape: Optional[Dict[str, torch.Tensor]] = None, want_info=False, defer_sync=False):
         """ErrorBoundSampler.get_z_vals.  tape (training): jitter [R,128], u_final [R,64] fp32;
-        extra_perm: callable n -> LongTensor[32] (drawn after one 8-byte D2H of n) or int tensor; eik_idx [R]."""
+        extra_perm: callable n -> LongTensor[32] (drawn after one 8-byte D2H of n) or int tensor; eik_idx [R].
+
+        defer_sync (training step): the reference draws randperm(n)[:32] on the CPU generator AFTER it knows n = 128 * rounds
+        (ray_sampler.py:223), which costs a device->host round trip in the middle of the step.  Instead every candidate
+        (n = 128 .. 128 * max_iters) is drawn from the SAME generator state, the device picks the row that applies, and
+        sampler_resolve() - called by the caller once it has queued enough work behind the sampler - reads n back and
+        replays the one draw that happened, so the host generator ends in exactly the reference's state."""
+        self.sampler_resolve()
         o, d = _f32(o, self.device), _f32(d, self.device)
         R = o.shape[0]
         tape = tape or {}
@@ -198,6 +205,29 @@ class RenderCore:
                                             _ptr(ws), self._ws_bytes, st), "i2sdf_sampler_rounds")
         info = torch.zeros(2, dtype=torch.int32, device=self.device)
         extra = None
+        if defer_sync and callable(tape.get("extra_perm")):
+            ep = tape["extra_perm"]
+            state = torch.get_rng_state()
+            cands = []
+            for k in range(self.desc.max_total_iters):
+                torch.set_rng_state(state)
+                cands.append(ep(self.desc.n_samples_eval * (k + 1)).to(torch.int32))
+            torch.set_rng_state(state)
+            table = torch.stack(cands).contiguous().to(self.device)
+            eik = tape["eik_idx"].to(device=self.device, dtype=torch.int32).contiguous() if "eik_idx" in tape else None
+            if callable(tape.get("eik_idx_fn")):
+                eik = tape["eik_idx_fn"]().to(device=self.device, dtype=torch.int32).contiguous()
+            z = torch.empty(R, self.n_out, device=self.device)
+            z_eik = torch.empty(R, device=self.device) if eik is not None else None
+            check(self.lib.i2sdf_sampler_finalize_candidates(self.h, R, _ptr(beta_param), _ptr(table), _ptr(eik), _ptr(z), _ptr(z_eik),
+                                                             _ptr(info), _ptr(ws), self._ws_bytes, st), "i2sdf_sampler_finalize_candidates")
+            if getattr(self, "_info_host", None) is None:
+                self._info_host = torch.zeros(2, dtype=torch.int32).pin_memory()
+            self._info_host.copy_(info, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._pending = (state, ep, ev)
+            return (z, z_eik, info) if want_info else (z, z_eik)
         if "extra_perm" in tape:
             ep = tape["extra_perm"]
             if callable(ep):
@@ -214,6 +244,17 @@ class RenderCore:
         if want_info:
             return z, z_eik, info
         return z, z_eik
+
+    def sampler_resolve(self):
+        """Second half of sample(defer_sync=True): wait for the round count and replay the host generator draw that applied."""
+        pend = getattr(self, "_pending", None)
+        if pend is None:
+            return
+        self._pending = None
+        state, ep, ev = pend
+        ev.synchronize()
+        torch.set_rng_state(state)
+        ep(int(self._info_host[1]))
 
     def sampler_round_debug(self, z, sdf, beta_param, beta_in, upsample: bool, u_tape=None):
         dev = self.device

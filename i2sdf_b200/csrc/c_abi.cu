@@ -23,7 +23,7 @@ size_t sampler_ws_floats(const i2sdf_handle*, long long);
 SamplerWs carve_sampler_ws(const i2sdf_handle*, long long, float*);
 int launch_sampler_init(const i2sdf_handle*, const SamplerWs&, long long, const float*, float, cudaStream_t);
 int launch_sampler_round(const i2sdf_handle*, const SamplerWs&, long long, int, int, const float*, const float*, cudaStream_t);
-int launch_sampler_finalize(const i2sdf_handle*, const SamplerWs&, long long, const float*, const int*, const int*, float*,
+int launch_sampler_finalize(const i2sdf_handle*, const SamplerWs&, long long, const float*, const int*, int, const int*, float*,
                             float*, int*, cudaStream_t);
 int launch_sampler_round_debug(const i2sdf_handle*, const float*, const float*, long long, int, const float*, const float*, int,
                                const float*, float*, float*, int*, float*, float*, int*, cudaStream_t);
@@ -74,30 +74,41 @@ struct PackJob {
     int ed;
 };
 
-__global__ void pack_kernel(PackJob J) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long n = (long long)J.rows * J.ld;
-    if (i >= n) return;
-    int k = (int)(i / J.ld), f = (int)(i % J.ld);
-    float v = 0.f;
-    if (J.mode == PACK_T) {
-        int col = -1;
-        if (J.feat_first > 0) {
-            if (k < J.feat_first) col = J.ed + k;
-            else if (k - J.feat_first < J.ed) col = k - J.feat_first;
-        } else if (k < J.in) col = k;
-        if (col >= 0 && col < J.in && f < J.nvalid) v = J.src[(size_t)(f + J.row_off) * J.in + col];
-    } else if (J.mode == PACK_R) {
-        if (k < J.out && f < J.in) v = J.src[(size_t)k * J.in + f];
-    } else {
-        if (f < J.nvalid) v = J.src[J.row_off + f];
+// All jobs of one i2sdf_pack_weights call run as ONE launch (grid.y = job): the training step re-packs after every
+// optimizer step, so the ~45 small jobs must not cost ~45 launches.
+constexpr int kMaxPackJobs = 3 * kMaxLayers + 2 + 2 * kMaxLayers + 2 + 4;
+struct PackBatch { int n; PackJob jobs[kMaxPackJobs]; };
+
+__global__ void pack_batch_kernel(const PackBatch B) {
+    const PackJob& J = B.jobs[blockIdx.y];
+    const long long n = (long long)J.rows * J.ld;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int k = (int)(i / J.ld), f = (int)(i % J.ld);
+        float v = 0.f;
+        if (J.mode == PACK_T) {
+            int col = -1;
+            if (J.feat_first > 0) {
+                if (k < J.feat_first) col = J.ed + k;
+                else if (k - J.feat_first < J.ed) col = k - J.feat_first;
+            } else if (k < J.in) col = k;
+            if (col >= 0 && col < J.in && f < J.nvalid) v = J.src[(size_t)(f + J.row_off) * J.in + col];
+        } else if (J.mode == PACK_R) {
+            if (k < J.out && f < J.in) v = J.src[(size_t)k * J.in + f];
+        } else {
+            if (f < J.nvalid) v = J.src[J.row_off + f];
+        }
+        J.dst[i] = v;
     }
-    J.dst[i] = v;
 }
 
-static int run_pack(const PackJob& J, cudaStream_t st) {
-    long long n = (long long)J.rows * J.ld;
-    pack_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(J);
+static int run_pack(PackBatch& B, const PackJob& J) {
+    if (B.n >= kMaxPackJobs) { set_error("pack: too many jobs"); return I2SDF_E_INVALID; }
+    B.jobs[B.n++] = J;
+    return I2SDF_OK;
+}
+static int flush_pack(const PackBatch& B, cudaStream_t st) {
+    if (B.n == 0) return I2SDF_OK;
+    pack_batch_kernel<<<dim3(64, B.n), 256, 0, st>>>(B);
     I2SDF_CUDA_CHECK(cudaGetLastError());
     return I2SDF_OK;
 }
@@ -246,25 +257,26 @@ int i2sdf_pack_weights(i2sdf_handle* h, const float* const* W, const float* cons
     cudaStream_t st = (cudaStream_t)stream;
     const NetDev& n = h->net;
     int li = 0, rc;
-    ProfScope ps(h, 3, st, 3 * h->n_layers);
+    ProfScope ps(h, 3, st, 2);
+    PackBatch PB{};
     for (int l = 0; l < n.L; ++l, ++li) {
         const int outd = h->lay_out[li], in = h->lay_in[li];
         const bool last = (l == n.L - 1);
         PackJob J{};
         J.mode = PACK_T; J.dst = (float*)n.sdf_wt[l]; J.rows = n.sdf_kpad[l]; J.ld = 256; J.src = W[li]; J.out = outd; J.in = in;
         J.row_off = last ? 1 : 0; J.nvalid = last ? 256 : outd;
-        if ((rc = run_pack(J, st))) return rc;
+        if ((rc = run_pack(PB, J))) return rc;
         PackJob R{};
         R.mode = PACK_R; R.dst = (float*)n.sdf_wr[l]; R.rows = 256; R.ld = (l == 0) ? 64 : 256; R.src = W[li]; R.out = last ? 1 : outd; R.in = in;
-        if ((rc = run_pack(R, st))) return rc;
+        if ((rc = run_pack(PB, R))) return rc;
         PackJob V{};
         V.mode = PACK_V; V.dst = (float*)n.sdf_b[l]; V.rows = 1; V.ld = 256; V.src = b[li]; V.row_off = last ? 1 : 0; V.nvalid = last ? 256 : outd;
-        if ((rc = run_pack(V, st))) return rc;
+        if ((rc = run_pack(PB, V))) return rc;
         if (last) {
             PackJob H{}; H.mode = PACK_V; H.dst = (float*)n.sdf_head; H.rows = 1; H.ld = 256; H.src = W[li]; H.row_off = 0; H.nvalid = 256;
-            if ((rc = run_pack(H, st))) return rc;
+            if ((rc = run_pack(PB, H))) return rc;
             PackJob HB{}; HB.mode = PACK_V; HB.dst = (float*)n.sdf_head + 256; HB.rows = 1; HB.ld = 1; HB.src = b[li]; HB.row_off = 0; HB.nvalid = 1;
-            if ((rc = run_pack(HB, st))) return rc;
+            if ((rc = run_pack(PB, HB))) return rc;
         }
     }
     for (int l = 0; l < n.Lc; ++l, ++li) {
@@ -273,29 +285,30 @@ int i2sdf_pack_weights(i2sdf_handle* h, const float* const* W, const float* cons
             PackJob J{};
             J.mode = PACK_T; J.dst = (float*)n.col_wt[l]; J.rows = n.col_kpad[l]; J.ld = 256; J.src = W[li]; J.out = outd; J.in = in; J.nvalid = outd;
             if (l == 0) { J.feat_first = 256; J.ed = n.ed; }
-            if ((rc = run_pack(J, st))) return rc;
+            if ((rc = run_pack(PB, J))) return rc;
             PackJob V{}; V.mode = PACK_V; V.dst = (float*)n.col_b[l]; V.rows = 1; V.ld = 256; V.src = b[li]; V.nvalid = outd;
-            if ((rc = run_pack(V, st))) return rc;
+            if ((rc = run_pack(PB, V))) return rc;
         } else {
             PackJob H{}; H.mode = PACK_V; H.dst = (float*)n.col_head; H.rows = 1; H.ld = 768; H.src = W[li]; H.nvalid = 768;
-            if ((rc = run_pack(H, st))) return rc;
+            if ((rc = run_pack(PB, H))) return rc;
             PackJob HB{}; HB.mode = PACK_V; HB.dst = (float*)n.col_head + 768; HB.rows = 1; HB.ld = 3; HB.src = b[li]; HB.nvalid = 3;
-            if ((rc = run_pack(HB, st))) return rc;
+            if ((rc = run_pack(PB, HB))) return rc;
         }
     }
     if (n.Ll == 2) {
         PackJob J{};
         J.mode = PACK_T; J.dst = (float*)n.light_wt0; J.rows = 256; J.ld = 128; J.src = W[li]; J.out = n.lh; J.in = 256; J.nvalid = n.lh;
-        if ((rc = run_pack(J, st))) return rc;
+        if ((rc = run_pack(PB, J))) return rc;
         PackJob V{}; V.mode = PACK_V; V.dst = (float*)n.light_b0; V.rows = 1; V.ld = 128; V.src = b[li]; V.nvalid = n.lh;
-        if ((rc = run_pack(V, st))) return rc;
+        if ((rc = run_pack(PB, V))) return rc;
         ++li;
         PackJob H{}; H.mode = PACK_V; H.dst = (float*)n.light_head; H.rows = 1; H.ld = 128; H.src = W[li]; H.nvalid = n.lh;
-        if ((rc = run_pack(H, st))) return rc;
+        if ((rc = run_pack(PB, H))) return rc;
         PackJob HB{}; HB.mode = PACK_V; HB.dst = (float*)n.light_head + n.lh; HB.rows = 1; HB.ld = 1; HB.src = b[li]; HB.nvalid = 1;
-        if ((rc = run_pack(HB, st))) return rc;
+        if ((rc = run_pack(PB, HB))) return rc;
         ++li;
     }
+    if ((rc = flush_pack(PB, st))) return rc;
     if (h->use_tc && (rc = tc_pack(h, W, b, st))) return rc;
     if (h->tcmain && (rc = tcmain_pack(h, h->tcmain, W, st))) return rc;
     return I2SDF_OK;
@@ -419,7 +432,16 @@ int i2sdf_sampler_finalize(i2sdf_handle* h, int64_t R, const float* beta_param, 
     if (workspace_bytes < i2sdf_workspace_bytes(h, R, 0)) { set_error("sampler: workspace too small"); return I2SDF_E_WORKSPACE; }
     SamplerWs W = carve_sampler_ws(h, R, (float*)workspace);
     ProfScope ps(h, 2, (cudaStream_t)stream);
-    return launch_sampler_finalize(h, W, R, beta_param, extra_idx, eik_idx, out_z, out_z_eik, out_info, (cudaStream_t)stream);
+    return launch_sampler_finalize(h, W, R, beta_param, extra_idx, 0, eik_idx, out_z, out_z_eik, out_info, (cudaStream_t)stream);
+}
+
+int i2sdf_sampler_finalize_candidates(i2sdf_handle* h, int64_t R, const float* beta_param, const int32_t* extra_table, const int32_t* eik_idx,
+                                      float* out_z, float* out_z_eik, int32_t* out_info, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h || !beta_param || !out_z || !workspace || !extra_table) { set_error("null argument"); return I2SDF_E_INVALID; }
+    if (workspace_bytes < i2sdf_workspace_bytes(h, R, 0)) { set_error("sampler: workspace too small"); return I2SDF_E_WORKSPACE; }
+    SamplerWs W = carve_sampler_ws(h, R, (float*)workspace);
+    ProfScope ps(h, 2, (cudaStream_t)stream);
+    return launch_sampler_finalize(h, W, R, beta_param, extra_table, 1, eik_idx, out_z, out_z_eik, out_info, (cudaStream_t)stream);
 }
 
 __global__ void sampler_info_kernel(SamplerDev S, const float* beta_max, const float* beta_param, int* info) {

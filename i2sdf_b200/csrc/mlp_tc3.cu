@@ -400,33 +400,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
 //   mode 0 (forward):  W[(n + row_off) * in + col(k)]   col(k) = k, or for the radiance input layer
 //                      k < feat ? ed + k : k - feat  (our A operand is [feat | PE(dir)], the reference's [PE(dir) | feat])
 //   mode 1 (reverse):  W[(k + row_off) * in + n + col_off]   (B = W^T: n = input index, k = output index)
-__global__ void pack_kernel(uint8_t* __restrict__ dst, const float* __restrict__ W, int outd, int in, int ksteps, int n_rows, int mode,
-                            int row_off, int feat_first, int ed) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int total = ksteps * 2 * n_rows;
-    if (i >= total) return;
-    int n = i % n_rows, chunk = (i / n_rows) % 2, ks = i / (2 * n_rows);
-    uint16_t hi[8], lo[8];
-    for (int e = 0; e < 8; ++e) {
-        int k = ks * 16 + chunk * 8 + e;
-        float w = 0.f;
-        if (mode == 0) {
-            int col = k;
-            if (feat_first > 0) col = (k < feat_first) ? ed + k : ((k - feat_first < ed) ? k - feat_first : -1);
-            if (col >= 0 && col < in && n + row_off < outd) w = W[(size_t)(n + row_off) * in + col];
-        } else {
-            // reverse: feat_first doubles as a column offset (radiance layer 0: only the feature columns are needed)
-            if (k + row_off < outd && n + feat_first < in) w = W[(size_t)(k + row_off) * in + n + feat_first];
+struct TcPackJob { uint8_t* dst; const float* W; int outd, in, ksteps, n_rows, mode, row_off, feat_first, pad; };
+struct TcPackBatch { int n; int ed; TcPackJob jobs[MAX_OPS]; };
+// one launch for all weight blocks (grid.y = block): re-packing follows every optimizer step in training
+__global__ void pack_kernel(const TcPackBatch B) {
+    const TcPackJob& J = B.jobs[blockIdx.y];
+    const int total = J.ksteps * 2 * J.n_rows;
+    const float* __restrict__ W = J.W;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int n_rows = J.n_rows, in = J.in, outd = J.outd, row_off = J.row_off, feat_first = J.feat_first, ed = B.ed;
+        int n = i % n_rows, chunk = (i / n_rows) % 2, ks = i / (2 * n_rows);
+        uint16_t hi[8], lo[8];
+        for (int e = 0; e < 8; ++e) {
+            int k = ks * 16 + chunk * 8 + e;
+            float w = 0.f;
+            if (J.mode == 0) {
+                int col = k;
+                if (feat_first > 0) col = (k < feat_first) ? ed + k : ((k - feat_first < ed) ? k - feat_first : -1);
+                if (col >= 0 && col < in && n + row_off < outd) w = W[(size_t)(n + row_off) * in + col];
+            } else {
+                // reverse: feat_first doubles as a column offset (radiance layer 0: only the feature columns are needed)
+                if (k + row_off < outd && n + feat_first < in) w = W[(size_t)(k + row_off) * in + n + feat_first];
+            }
+            __nv_bfloat16 h = __float2bfloat16_rn(w);
+            __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+            hi[e] = *reinterpret_cast<uint16_t*>(&h);
+            lo[e] = *reinterpret_cast<uint16_t*>(&l);
         }
-        __nv_bfloat16 h = __float2bfloat16_rn(w);
-        __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
-        hi[e] = *reinterpret_cast<uint16_t*>(&h);
-        lo[e] = *reinterpret_cast<uint16_t*>(&l);
+        const size_t sb = (size_t)n_rows * 64;
+        uint8_t* base = J.dst + (size_t)ks * sb + (size_t)chunk * n_rows * 16 + (size_t)n * 16;
+        *reinterpret_cast<uint4*>(base) = *reinterpret_cast<uint4*>(hi);
+        *reinterpret_cast<uint4*>(base + sb / 2) = *reinterpret_cast<uint4*>(lo);
     }
-    const size_t sb = (size_t)n_rows * 64;
-    uint8_t* base = dst + (size_t)ks * sb + (size_t)chunk * n_rows * 16 + (size_t)n * 16;
-    *reinterpret_cast<uint4*>(base) = *reinterpret_cast<uint4*>(hi);
-    *reinterpret_cast<uint4*>(base + sb / 2) = *reinterpret_cast<uint4*>(lo);
 }
 
 struct State {
@@ -532,13 +537,14 @@ int tc_pack(i2sdf_handle* h, const float* const* W, const float* const* b, cudaS
     using namespace tc3;
     (void)b;   // biases / heads reuse the fp32 arrays packed for the fp32 path
     State* s = (State*)h->tc;
+    TcPackBatch B{};
+    B.n = s->n_pack; B.ed = h->net.ed;
     for (int op = 0; op < s->n_pack; ++op) {
         const Op& o = s->full.ops[op];
         const int li = s->src_layer[op];
-        const int total = o.ksteps * 2 * o.n;
-        pack_kernel<<<(total + 255) / 256, 256, 0, st>>>(s->wpack + o.w_off, W[li], h->lay_out[li], h->lay_in[li], o.ksteps, o.n, s->mode[op],
-                                                         s->row_off[op], s->feat_first[op], h->net.ed);
+        B.jobs[op] = TcPackJob{s->wpack + o.w_off, W[li], h->lay_out[li], h->lay_in[li], o.ksteps, o.n, s->mode[op], s->row_off[op], s->feat_first[op], 0};
     }
+    pack_kernel<<<dim3(36, B.n), 256, 0, st>>>(B);
     I2SDF_CUDA_CHECK(cudaGetLastError());
     return I2SDF_OK;
 }

@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(kRayThreads) sampler_resample_kernel(SamplerDe
 // final sample set   (ray_sampler.py:215-234)
 // ------------------------------------------------------------------------------------------------
 __global__ void sampler_finalize_kernel(SamplerDev S, SamplerWs W, long long R, const float* __restrict__ beta_param,
-                                        const int* __restrict__ extra_tape, const int* __restrict__ eik_idx,
+                                        const int* __restrict__ extra_tape, int extra_per_round, const int* __restrict__ eik_idx,
                                         float* __restrict__ out_z, float* __restrict__ out_z_eik, int* __restrict__ info) {
     __shared__ float vals[kWarpsPerCta][128];
     __shared__ float sorted[kWarpsPerCta][128];
@@ -440,7 +440,8 @@ __global__ void sampler_finalize_kernel(SamplerDev S, SamplerWs W, long long R, 
     const int total = ns + 2 + ne;
     const float* zg = W.z[cur] + r * W.zmax;
     const float* smp = W.samples + r * S.n_eval;
-    const int* eidx = extra_tape ? extra_tape : (S.extra_idx + klast * ne);
+    // extra_tape: one index set, or (extra_per_round) one candidate set per possible round count [max_iters][ne]
+    const int* eidx = extra_tape ? extra_tape + (extra_per_round ? klast * ne : 0) : (S.extra_idx + klast * ne);
     for (int i = lane; i < total; i += 32) {
         float v;
         if (i < ns) v = smp[i];
@@ -620,8 +621,8 @@ int launch_sampler_round(const i2sdf_handle* h, const SamplerWs& W, long long R,
 }
 
 int launch_sampler_finalize(const i2sdf_handle* h, const SamplerWs& W, long long R, const float* beta_param,
-                            const int* extra_tape, const int* eik_idx, float* out_z, float* out_z_eik, int* info, cudaStream_t st) {
-    sampler_finalize_kernel<<<ray_grid(R), kWarpsPerCta * 32, 0, st>>>(h->smp, W, R, beta_param, extra_tape, eik_idx, out_z, out_z_eik, info);
+                            const int* extra_tape, int extra_per_round, const int* eik_idx, float* out_z, float* out_z_eik, int* info, cudaStream_t st) {
+    sampler_finalize_kernel<<<ray_grid(R), kWarpsPerCta * 32, 0, st>>>(h->smp, W, R, beta_param, extra_tape, extra_per_round, eik_idx, out_z, out_z_eik, info);
     I2SDF_CUDA_CHECK(cudaGetLastError());
     return I2SDF_OK;
 }

@@ -21,6 +21,24 @@ from ._lib import I2SDFError
 from .core import RenderCore
 
 
+# Packed device copies of the weights must follow every parameter update.  Tensor version counters catch most in-place
+# writes (load_state_dict, foreach/for-loop optimizers) but NOT the fused optimizers (torch._fused_adam_ leaves _version
+# unchanged), so (a) a training-mode forward always re-packs from the effective weights it computes anyway, and (b) any
+# optimizer step anywhere bumps this epoch, which is part of the key an eval-mode forward checks.
+_OPT_EPOCH = [0]
+
+
+def _bump_opt_epoch(*_args, **_kwargs):
+    _OPT_EPOCH[0] += 1
+
+
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_post_hook
+    _reg_post_hook(_bump_opt_epoch)
+except Exception:                                   # very old torch: training forwards still re-pack every step
+    pass
+
+
 def _get(conf, key, default=None):
     if isinstance(conf, dict):
         return conf.get(key, default)
@@ -271,18 +289,22 @@ class I2SDFNetwork(nn.Module):
             s.append(self.light_network)
         return s
 
-    def _ready_core(self) -> RenderCore:
-        """The RenderCore on the parameters' device with up-to-date packed weights."""
+    def _param_key(self):
+        return (_OPT_EPOCH[0],) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _ready_core(self, defer_pack=False) -> RenderCore:
+        """The RenderCore on the parameters' device with up-to-date packed weights (defer_pack: the caller packs itself)."""
         dev = self.density.beta.device
         if dev.type != "cuda":
             raise I2SDFError("I2SDFNetwork (i2sdf_b200) needs its parameters on a CUDA device; there is no CPU path")
         if self._core_obj is None or self._core_obj.device != dev:
             self._core_obj = RenderCore(self._model_conf, dev)
             self._packed_key = None
-        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
-        if key != self._packed_key:
-            self.pack_weights()
-            self._packed_key = key
+        if not defer_pack:
+            key = self._param_key()
+            if key != self._packed_key:
+                self.pack_weights()
+                self._packed_key = key
         return self._core_obj
 
     def effective_weights(self):
@@ -312,11 +334,11 @@ class I2SDFNetwork(nn.Module):
 
     # ------------------------------------------------------------------ forward
     def forward(self, input, predict_only=False):
-        core = self._ready_core()
         if self.training:
             from .autograd import forward_train
-            return forward_train(self, core, input, predict_only)
-        return self._forward_nograd(core, input, predict_only)
+            # forward_train packs the effective weights it builds for autograd (every step: the optimizer moved them)
+            return forward_train(self, self._ready_core(defer_pack=True), input, predict_only)
+        return self._forward_nograd(self._ready_core(), input, predict_only)
 
     @torch.no_grad()
     def _forward_nograd(self, core, input, predict_only):

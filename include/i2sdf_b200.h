@@ -128,6 +128,14 @@ int i2sdf_sampler_finalize(i2sdf_handle* h, int64_t R, const float* beta_param, 
                            const int32_t* eik_idx, float* out_z, float* out_z_eik, int32_t* out_info,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same without the host round trip a training caller would otherwise need to learn n before drawing randperm(n)[:32]:
+ * extra_table = device int32[max_total_iters][n_samples_extra], row k = the index set to use if sampling stopped after
+ * k+1 rounds (n = 128 (k+1)); the kernel picks the row on the device.  The caller draws every candidate from the SAME
+ * host generator state and re-draws the one that applied once out_info has been copied back (i2sdf_b200/core.py). */
+int i2sdf_sampler_finalize_candidates(i2sdf_handle* h, int64_t R, const float* beta_param, const int32_t* extra_table,
+                                      const int32_t* eik_idx, float* out_z, float* out_z_eik, int32_t* out_info,
+                                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* Device int32[2] as above WITHOUT finalising: lets a training caller read n (one 8-byte D2H, the only host
  * sync of the path; the reference syncs once per round at ray_sampler.py:151) to draw randperm(n)[:32]. */
 int i2sdf_sampler_info(i2sdf_handle* h, int64_t R, const float* beta_param, int32_t* out_info,

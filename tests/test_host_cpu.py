@@ -88,3 +88,16 @@ def test_pixel_grid_matches_reference_get_uv():
     uv = np.mgrid[0:H, 0:W].astype(np.int32)
     ref = torch.from_numpy(np.flip(uv, axis=0).copy()).float().reshape(2, -1).transpose(1, 0)
     assert torch.equal(pixel_grid((H, W)), ref)
+
+
+def test_any_optimizer_step_invalidates_the_packed_weights_key():
+    """network._OPT_EPOCH is part of the key an eval forward checks before reusing the packed weights; fused optimizers do
+    not bump tensor versions, so the global optimizer post-step hook has to."""
+    import torch
+    from i2sdf_b200 import network
+    lin = torch.nn.Linear(2, 2)
+    opt = torch.optim.SGD(lin.parameters(), lr=0.1)
+    lin(torch.ones(1, 2)).sum().backward()
+    before = network._OPT_EPOCH[0]
+    opt.step()
+    assert network._OPT_EPOCH[0] == before + 1

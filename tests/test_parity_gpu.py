@@ -563,3 +563,55 @@ def test_light_head_chunked_render_is_consistent(cases):
         assert torch.equal(whole[k][cut:], tail[k]), k
     assert 0.0 < float(whole["s_light"].min()) and float(whole["s_light"].max()) < 1.0       # per-sample sigmoid outputs
     assert 0.0 <= float(whole["light"].min()) and float(whole["light"].max()) < 1.0 + 1e-5   # composited with weights summing to <= 1
+
+
+def test_sampler_deferred_randperm_equals_synchronous():
+    """Training sampler without the mid-step host sync: the candidate-table path (sample(defer_sync=True) + sampler_resolve)
+    returns the same z's as the synchronous path and leaves the CPU generator in the same state (ray_sampler.py:223)."""
+    c = Case("train_synthetic")
+    m = _model(c, training=True)
+    core = m._ready_core()
+    o, d, _ = (t.cuda() for t in orc.flatten_rays(c.inputs["uv"], c.inputs["pose"], c.inputs["intrinsics"]))
+    R = o.shape[0]
+    got = []
+    for defer in (False, True):
+        torch.manual_seed(77)
+        tape = m._draw_sampler_tape(R, torch.device("cuda"))
+        z, z_eik, info = core.sample(o, d, m.density.beta.detach(), tape, want_info=True, defer_sync=defer)
+        core.sampler_resolve()
+        got.append((z.clone(), z_eik.clone(), info.clone(), torch.rand(4), torch.rand(4, device="cuda")))
+    for a, b in zip(*got):
+        assert torch.equal(a, b)
+    assert int(got[0][2][1]) == 128 * int(got[0][2][0])
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_packed_weights_follow_the_optimizer(fused):
+    """The kernels read packed copies of the weights: they must follow every optimizer step, also a fused Adam step (which
+    leaves tensor._version untouched).  After two training steps the module must render exactly like a fresh module that
+    loaded its state dict, and the second training forward must already have seen the first update."""
+    from i2sdf_b200.network import I2SDFLoss, I2SDFNetwork
+    c = Case("train_synthetic")
+    m = _model(c, training=True)
+    inp = {k: v.cuda() for k, v in c.inputs.items()}
+    gt = {k: v.cuda() for k, v in c.gt.items()}
+    loss_fn = I2SDFLoss(**c.loss_conf)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-2, eps=1e-15, fused=fused)
+    losses = []
+    for _ in range(2):
+        torch.manual_seed(5)                      # same rays, same sampler randomness: only the weights differ between the steps
+        out = m(inp)
+        loss = loss_fn(out, gt, 0)["loss"]
+        losses.append(loss.item())
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+    assert losses[0] != losses[1], "second forward ran on stale packed weights"
+    m.eval()
+    ev = {k: v.cuda() for k, v in orc.synthetic_rays(256, seed=1).items()}
+    a = m(ev)["rgb_values"].clone()
+    conf = dict(c.model_conf)
+    fresh = I2SDFNetwork(conf)
+    fresh.load_state_dict(m.state_dict())
+    b = fresh.cuda().eval()(ev)["rgb_values"]
+    assert torch.equal(a, b)
