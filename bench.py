@@ -337,7 +337,9 @@ def gpu_arm(args, rank, world, local_rank):
         step_e2e()
     clk = ClockSampler(local_rank)
     clk.start()
+    core.rounds_log.clear()
     ms_res, prof = timed(step_resident, args.steps, profile=True)
+    rounds_seen = sorted(set(core.rounds_log))
     ms_e2e, _ = timed(step_e2e, args.steps)
     clocks = clk.stop()
     ms_render = 0.0
@@ -397,6 +399,7 @@ def gpu_arm(args, rank, world, local_rank):
                    "weights": "W-sharp: reference geometric init (seed 0), density.beta=0.01 so all 5 sampler rounds run",
                    "rays_per_gpu": R, "global_rays": world * R, "samples_per_ray_composited": N_COMPOSITED,
                    "sdf_evals_per_ray": 5 * 128 + N_COMPOSITED,
+                   "sampler_rounds_in_timed_steps": rounds_seen if train else "5 (eval: weights fixed)",
                    "parallelism": f"ray-sharded x{world}, " + ("one flat gradient all-reduce per step" if train else "no collective (inference)"),
                    "tensor_cores": {"sampler_sdf": core.uses_tensor_cores, "main_pass": core.uses_tensor_cores_main,
                                     "backward": bool(train and core.fused_main)},

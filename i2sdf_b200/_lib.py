@@ -17,6 +17,15 @@ class Desc(C.Structure):
         ("extra_idx", C.POINTER(C.c_int32))]
 
 
+class LossArgs(C.Structure):
+    """i2sdf_loss_args (include/i2sdf_b200.h)."""
+    _fields_ = [("R", C.c_int64), ("n_eik", C.c_int64), ("n_bubble", C.c_int64)] + [(n, C.c_void_p) for n in (
+        "rgb", "rgb_gt", "grad_theta", "diff_norm", "weight_sum", "mask_gt", "depth", "depth_gt", "depth_mask", "normal",
+        "normal_gt", "normal_mask", "surface_sdf", "light", "light_gt")] + [(n, C.c_float) for n in (
+        "w_eik", "w_smooth", "w_mask", "w_depth", "w_normal", "w_angular", "w_bubble", "w_light")] + [(n, C.c_void_p) for n in (
+        "terms", "g_rgb", "g_grad_theta", "g_diff_norm", "g_weight_sum", "g_depth", "g_normal", "g_surface_sdf", "g_light")]
+
+
 # every symbol include/i2sdf_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -53,6 +62,7 @@ SYMBOLS = {
     "i2sdf_saved_bytes_points": (C.c_size_t, [_P, C.c_int64]),
     "i2sdf_fused_backward": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(_P), C.POINTER(_P),
                                        C.POINTER(_P), C.POINTER(_P), _P, C.c_size_t, _P]),
+    "i2sdf_loss_forward": (C.c_int, [C.POINTER(LossArgs), _P]),
     "i2sdf_planes_slot_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
     "i2sdf_planes_pack": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, _P, _P]),
     "i2sdf_planes_unpack": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, C.c_int, C.c_int, _P]),

@@ -250,3 +250,92 @@ def forward_train(model, core, input, predict_only=False):
     if model.use_normal:
         res["normal_values"] = normal
     return res
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# I2SDFLoss on CUDA tensors: one launch for every term + the gradient w.r.t. every model output (csrc/loss.cu)
+# ----------------------------------------------------------------------------------------------------------------------
+_LOSS_PRED = ("rgb", "grad_theta", "diff_norm", "weight_sum", "depth", "normal", "surface_sdf", "light")     # differentiable inputs
+_LOSS_AUX = ("rgb_gt", "mask_gt", "depth_gt", "depth_mask", "normal_gt", "normal_mask", "light_gt")
+
+
+class _LossFn(Function):
+    @staticmethod
+    def forward(ctx, weights, aux, *preds):
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        a = _lib.LossArgs()
+        dev = preds[0].device
+        keep = []
+
+        def prep(t, dtype=torch.float32):
+            t = t.detach()
+            if t.dtype != dtype or not t.is_contiguous() or t.device != dev:
+                t = t.to(device=dev, dtype=dtype).contiguous()
+            keep.append(t)
+            return t
+
+        P = {k: (None if t is None else prep(t)) for k, t in zip(_LOSS_PRED, preds)}
+        R = P["rgb"].shape[0]
+        a.R, a.n_eik = R, (0 if P["grad_theta"] is None else P["grad_theta"].shape[0])
+        a.n_bubble = 0 if P["surface_sdf"] is None else P["surface_sdf"].numel()
+        for k in _LOSS_PRED:
+            if P[k] is not None:
+                rows = {"grad_theta": a.n_eik, "surface_sdf": a.n_bubble}.get(k, R)
+                width = 3 if k in ("rgb", "grad_theta", "normal") else 1
+                if P[k].numel() != rows * width:
+                    raise _lib.I2SDFError(f"I2SDFLoss: {k} has {P[k].numel()} elements, expected {rows * width}")
+                setattr(a, k, P[k].data_ptr())
+        need = {"rgb": ("rgb_gt",), "weight_sum": ("mask_gt",), "depth": ("depth_gt", "depth_mask"), "normal": ("normal_gt", "normal_mask"),
+                "light": ("light_gt",)}
+        for k, deps in need.items():
+            if P[k] is None:
+                continue
+            for dname in deps:
+                t = aux.get(dname)
+                if t is None:
+                    raise _lib.I2SDFError(f"I2SDFLoss: ground truth for '{k}' is missing ({dname})")
+                t = prep(t, torch.bool if dname.endswith("_mask") else torch.float32)
+                if t.numel() != R * (3 if dname in ("rgb_gt", "normal_gt") else 1):
+                    raise _lib.I2SDFError(f"I2SDFLoss: {dname} has the wrong size")
+                setattr(a, dname, t.data_ptr())
+        for k, v in weights.items():
+            setattr(a, k, float(v))
+        # one flat buffer: terms[10] (padded to 16) + the gradient of every differentiable input that needs one
+        want = [i for i, k in enumerate(_LOSS_PRED) if P[k] is not None and ctx.needs_input_grad[2 + i]]
+        sizes = [(P[_LOSS_PRED[i]].numel() + 3) // 4 * 4 for i in want]
+        flat = torch.empty(16 + sum(sizes), dtype=torch.float32, device=dev)
+        a.terms = flat.data_ptr()
+        grads, off = [None] * len(_LOSS_PRED), 16
+        for i, n in zip(want, sizes):
+            k = _LOSS_PRED[i]
+            grads[i] = flat[off:off + P[k].numel()].view(preds[i].shape)
+            setattr(a, "g_" + k, grads[i].data_ptr())
+            off += n
+        with torch.cuda.device(dev):
+            _lib.check(lib.i2sdf_loss_forward(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "i2sdf_loss_forward")
+        ctx.grads = grads
+        ctx.flat = flat
+        ctx.set_materialize_grads(False)
+        del keep
+        return flat[:10]
+
+    @staticmethod
+    def backward(ctx, g_terms):
+        out = [None, None] + [None] * len(_LOSS_PRED)
+        if g_terms is None:
+            return tuple(out)
+        live = [g for g in ctx.grads if g is not None]
+        scaled = torch._foreach_mul(live, g_terms[0]) if live else []          # upstream of `loss` (terms[0]); the other terms are logged detached
+        it = iter(scaled)
+        for i, g in enumerate(ctx.grads):
+            if g is not None:
+                out[2 + i] = next(it)
+        return tuple(out)
+
+
+def fused_loss(sel, weights):
+    """sel: dict with the _LOSS_PRED / _LOSS_AUX entries (None = term off) -> terms [10] (terms[0] = loss, differentiable)."""
+    aux = {k: sel.get(k) for k in _LOSS_AUX}
+    return _LossFn.apply(weights, aux, *[sel.get(k) for k in _LOSS_PRED])

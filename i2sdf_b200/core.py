@@ -83,6 +83,7 @@ class RenderCore:
         self._ws = None
         self._ws_rays = -1
         self._packed_refs = None
+        self.rounds_log = []
 
     def close(self):
         if getattr(self, "h", None):
@@ -255,6 +256,8 @@ class RenderCore:
         ev.synchronize()
         torch.set_rng_state(state)
         ep(int(self._info_host[1]))
+        self.rounds_log.append(int(self._info_host[0]))          # sampler rounds of that forward (bench.py reports them)
+        del self.rounds_log[:-256]
 
     def sampler_round_debug(self, z, sdf, beta_param, beta_in, upsample: bool, u_tape=None):
         dev = self.device

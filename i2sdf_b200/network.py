@@ -359,7 +359,7 @@ class I2SDFNetwork(nn.Module):
 
 class I2SDFLoss(nn.Module):
     """Loss of the reconstruction stage; consumes I2SDFNetwork outputs (reference: model/network/__init__.py:289-406).
-    Kept in PyTorch (SURVEY §8(f) ranks fusing it as the next tier)."""
+    On CUDA tensors the whole loss and its backward seed are one kernel (csrc/loss.cu)."""
 
     def __init__(self, eikonal_weight=0.1, smooth_weight=0.0, mask_weight=0.0, depth_weight=0.1, normal_weight=0.05,
                  angular_weight=0.05, bubble_weight=0.0, min_bubble_iter=0, max_bubble_iter=None, smooth_iter=None,
@@ -405,6 +405,39 @@ class I2SDFLoss(nn.Module):
         return self._masked_mean((torch.acos(torch.clamp(dot, -1.0 + 1e-6, 1.0 - 1e-6)) / math.tau).clamp_max(0.5).abs(), normal_mask)
 
     def forward(self, model_outputs, ground_truth, current_step):
+        if model_outputs["rgb_values"].is_cuda:
+            return self._forward_fused(model_outputs, ground_truth, current_step)
+        return self._forward_torch(model_outputs, ground_truth, current_step)
+
+    _TERMS = ("loss", "rgb_loss", "eikonal_loss", "smooth_loss", "mask_loss", "depth_loss", "normal_loss", "angular_loss",
+              "bubble_loss", "light_mask_loss")
+
+    def _forward_fused(self, out, gt, current_step):
+        """CUDA tensors: every term, the total and d loss / d output in ONE launch (csrc/loss.cu, i2sdf_loss_forward); the
+        reference's ~60 small loss / loss-backward kernels per step become 1 + a multi-tensor scale in backward."""
+        from .autograd import fused_loss
+        smooth_on = self.smooth_iter is None or current_step > self.smooth_iter
+        has_n = "normal" in gt and (self.normal_weight > 0 or self.angular_weight > 0)
+        sel = dict(
+            rgb=out["rgb_values"], rgb_gt=gt["rgb"],
+            grad_theta=out.get("grad_theta"),
+            diff_norm=out["diff_norm"] if (smooth_on and self.smooth_weight > 0 and "diff_norm" in out) else None,
+            weight_sum=out["weight_sum"] if ("mask" in gt and self.mask_weight > 0) else None, mask_gt=gt.get("mask"),
+            depth=out["depth_values"] if ("depth" in gt and self.depth_weight > 0) else None, depth_gt=gt.get("depth"), depth_mask=gt.get("depth_mask"),
+            normal=out["normal_values"] if has_n else None, normal_gt=gt.get("normal"), normal_mask=gt.get("normal_mask"),
+            surface_sdf=out["surface_sdf"] if ("surface_sdf" in out and self.bubble_weight > 0) else None,
+            light=out["light_mask"] if ("light_mask" in out and self.light_mask_weight > 0) else None, light_gt=gt.get("light_mask"))
+        w = dict(w_eik=self.eikonal_weight, w_smooth=self.smooth_weight, w_mask=self.mask_weight, w_depth=self.depth_weight,
+                 w_normal=self.normal_weight, w_angular=self.angular_weight, w_bubble=self.bubble_weight, w_light=self.light_mask_weight)
+        terms = fused_loss(sel, w)
+        res = {"loss": terms[0]}
+        det = terms.detach()
+        for i, k in enumerate(self._TERMS[1:], 1):
+            res[k] = det[i]
+        return res
+
+    def _forward_torch(self, model_outputs, ground_truth, current_step):
+        """Plain PyTorch restatement (CPU tensors: host-side tests of the loss module; the CUDA path is _forward_fused)."""
         dev = model_outputs["rgb_values"].device
         zero = lambda: torch.zeros((), device=dev)                # noqa: E731   (a fill kernel: no host->device copy, no sync)
         terms = {"rgb_loss": self.get_rgb_loss(model_outputs["rgb_values"], ground_truth["rgb"])}

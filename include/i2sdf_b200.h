@@ -266,6 +266,44 @@ int i2sdf_planes_unpack(i2sdf_handle* h, const void* slot, int columns, int64_t 
 int i2sdf_planes_wgrad(i2sdf_handle* h, int nterms, const void* const* P, const void* const* X, int x_columns, int64_t M,
                        float* dW, int ld, int rows, int cols, float* colsum, void* stream);
 
+/* ---- loss ---------------------------------------------------------------------------------
+ * Replaces: I2SDFLoss.forward (model/network/__init__.py:338-406) AND the backward autograd runs through it: one launch
+ * computes every term, the weighted total and d loss / d input for every model output that carries gradient.
+ * All pointers are device memory; a NULL prediction pointer switches its term off (the caller applies the reference's
+ * "key present and weight > 0" rules, e.g. diff_norm is passed only once current_step > smooth_iter).  Masks are bytes
+ * (torch.bool).  g_* outputs may be NULL.  No handle: the loss has no network state. */
+typedef struct i2sdf_loss_args {
+    int64_t R;                   /* rays */
+    int64_t n_eik;               /* rows of grad_theta (2R) */
+    int64_t n_bubble;            /* rows of surface_sdf */
+    const float* rgb;            /* [R,3] rgb_values */
+    const float* rgb_gt;         /* [R,3] */
+    const float* grad_theta;     /* [n_eik,3] or NULL */
+    const float* diff_norm;      /* [R] or NULL */
+    const float* weight_sum;     /* [R] or NULL  (mask BCE) */
+    const float* mask_gt;        /* [R] */
+    const float* depth;          /* [R] or NULL */
+    const float* depth_gt;       /* [R] */
+    const uint8_t* depth_mask;   /* [R] */
+    const float* normal;         /* [R,3] normal_values or NULL */
+    const float* normal_gt;      /* [R,3] */
+    const uint8_t* normal_mask;  /* [R] */
+    const float* surface_sdf;    /* [n_bubble] or NULL */
+    const float* light;          /* [R] light_mask or NULL */
+    const float* light_gt;       /* [R] */
+    float w_eik, w_smooth, w_mask, w_depth, w_normal, w_angular, w_bubble, w_light;
+    float* terms;                /* [10]: loss, rgb, eikonal, smooth, mask, depth, normal, angular, bubble, light_mask */
+    float* g_rgb;                /* [R,3] */
+    float* g_grad_theta;         /* [n_eik,3] */
+    float* g_diff_norm;          /* [R] */
+    float* g_weight_sum;         /* [R] */
+    float* g_depth;              /* [R] */
+    float* g_normal;             /* [R,3] */
+    float* g_surface_sdf;        /* [n_bubble] */
+    float* g_light;              /* [R] */
+} i2sdf_loss_args;
+int i2sdf_loss_forward(const i2sdf_loss_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -615,3 +615,42 @@ def test_packed_weights_follow_the_optimizer(fused):
     fresh.load_state_dict(m.state_dict())
     b = fresh.cuda().eval()(ev)["rgb_values"]
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("R,all_terms", [(1024, True), (1600, False), (37, True)])
+def test_fused_loss_matches_the_pytorch_restatement(R, all_terms):
+    """i2sdf_loss_forward (one launch: all terms + d loss / d output) vs I2SDFLoss._forward_torch + autograd on the same CUDA
+    tensors (that restatement is checked against the reference's loss values by the training fixtures)."""
+    from i2sdf_b200.network import I2SDFLoss
+    g = torch.Generator().manual_seed(R)
+    rnd = lambda *s: torch.rand(*s, generator=g)          # noqa: E731
+    out = {"rgb_values": rnd(R, 3), "depth_values": rnd(R) * 3, "weight_sum": rnd(R, 1) * 1.2 - 0.1,
+           "normal_values": torch.nn.functional.normalize(rnd(R, 3) - 0.5, dim=1), "grad_theta": (rnd(2 * R, 3) - 0.5) * 3,
+           "diff_norm": rnd(R)}
+    out["grad_theta"][3] = 0.0                           # |g| = 0: torch's norm backward gives 0 there
+    gt = {"rgb": rnd(R, 1, 3), "depth": rnd(R, 1) * 3, "depth_mask": rnd(R, 1) > 0.3, "normal": torch.nn.functional.normalize(rnd(R, 3) - 0.5, dim=1),
+          "normal_mask": rnd(R) > 0.5}
+    kw = dict(eikonal_weight=0.1, depth_weight=0.1, normal_weight=0.05)
+    if all_terms:
+        out.update(surface_sdf=rnd(77, 1) - 0.5, light_mask=rnd(R, 1))
+        gt.update(mask=(rnd(R, 1) > 0.5).float(), light_mask=(rnd(R, 1) > 0.8).float())
+        kw.update(smooth_weight=0.01, smooth_iter=10, mask_weight=0.2, bubble_weight=0.5, light_mask_weight=0.5)
+    loss_fn = I2SDFLoss(**kw)
+    gt = {k: v.cuda() for k, v in gt.items()}
+    res = {}
+    for mode in ("fused", "torch"):
+        o = {k: v.clone().cuda().requires_grad_(True) for k, v in out.items()}
+        r = loss_fn(o, gt, 100) if mode == "fused" else loss_fn._forward_torch(o, gt, 100)
+        (r["loss"] * 1.7).backward()
+        res[mode] = (r, o)
+    rf, of = res["fused"]
+    rt, ot = res["torch"]
+    for k in rt:
+        a, b = float(rf[k]), float(rt[k])
+        assert abs(a - b) <= 2e-6 * max(abs(b), 1e-3), (k, a, b)
+    for k in ot:
+        if ot[k].grad is None:
+            assert of[k].grad is None or float(of[k].grad.abs().max()) == 0.0, k
+            continue
+        assert of[k].grad is not None, k
+        assert relerr(of[k].grad, ot[k].grad) < 1e-5, (k, relerr(of[k].grad, ot[k].grad))

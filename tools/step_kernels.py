@@ -46,3 +46,14 @@ tot_ours = sum(v[1] for k, v in tab.items() if any(o in k for o in ours))
 print(f"library kernels {tot_ours/N/1e3:.3f} ms/step, everything else (PyTorch ops, memcpy/memset) {(busy-tot_ours)/N/1e3:.3f} ms/step")
 for k, v in sorted(tab.items(), key=lambda kv: -kv[1][1])[:70]:
     print(f"{v[1]/N:9.1f} us  x{v[0]/N:5.1f}  {k}")
+
+# idle time of the stream, by (kernel before the gap -> kernel after the gap)
+gaps = {}
+for a, b in zip(evs[:-1], evs[1:]):
+    g = b.time_range.start - a.time_range.end
+    if g > 2:
+        t = gaps.setdefault((a.name[:48], b.name[:48]), [0, 0.0])
+        t[0] += 1; t[1] += g
+print(f"idle gaps > 2 us: {sum(v[1] for v in gaps.values())/N/1e3:.3f} ms per step")
+for k, v in sorted(gaps.items(), key=lambda kv: -kv[1][1])[:25]:
+    print(f"{v[1]/N:9.1f} us  x{v[0]/N:5.1f}  {k[0]}  ->  {k[1]}")
