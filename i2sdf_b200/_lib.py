@@ -40,6 +40,8 @@ SYMBOLS = {
     "i2sdf_rays": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "i2sdf_sdf_forward": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "i2sdf_sampler_rounds": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P, C.c_size_t, _P]),
+    "i2sdf_sampler_step": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, C.c_int, C.c_int, _P, C.c_size_t, _P]),
+    "i2sdf_sampler_beta_max": (C.c_void_p, [_P, C.c_int64, _P]),
     "i2sdf_sampler_finalize": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "i2sdf_sampler_finalize_candidates": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "i2sdf_sampler_info": (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_size_t, _P]),

@@ -201,7 +201,8 @@ def forward_train(model, core, input, predict_only=False):
         z, z_eik = ov["z_all"].to(dev).contiguous(), ov["z_eik"].to(dev).reshape(-1).contiguous()
     else:
         tape = {k: ov[k] for k in ("jitter", "u_final", "extra_perm", "eik_idx") if k in ov} or model._draw_sampler_tape(R, dev)
-        z, z_eik = core.sample(o, d, beta.detach(), tape, defer_sync=True)      # resolved below, behind the main pass
+        z, z_eik = core.sample(o, d, beta.detach(), tape, defer_sync=True,      # resolved below, behind the main pass
+                                group=getattr(model, "convergence_group", None))
     n_sdf = model.implicit_network.num_layers - 1
     n_col = model.rendering_network.num_layers - 1
     n_light = (model.light_network.num_layers - 1) if model.use_light else 0

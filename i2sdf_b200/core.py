@@ -185,7 +185,7 @@ class RenderCore:
                                          _ptr(ws), self._ws_bytes, self._stream()), "i2sdf_sdf_forward")
         return sdf, feat, grad
 
-    def sample(self, o, d, beta_param, tape: Optional[Dict[str, torch.Tensor]] = None, want_info=False, defer_sync=False):
+    def sample(self, o, d, beta_param, tape: Optional[Dict[str, torch.Tensor]] = None, want_info=False, defer_sync=False, group=None):
         """ErrorBoundSampler.get_z_vals.  tape (training): jitter [R,128], u_final [R,64] fp32;
         extra_perm: callable n -> LongTensor[32] (drawn after one 8-byte D2H of n) or int tensor; eik_idx [R].
 
@@ -193,7 +193,11 @@ class RenderCore:
         (ray_sampler.py:223), which costs a device->host round trip in the middle of the step.  Instead every candidate
         (n = 128 .. 128 * max_iters) is drawn from the SAME generator state, the device picks the row that applies, and
         sampler_resolve() - called by the caller once it has queued enough work behind the sampler - reads n back and
-        replays the one draw that happened, so the host generator ends in exactly the reference's state."""
+        replays the one draw that happened, so the host generator ends in exactly the reference's state.
+
+        group (torch.distributed process group, world > 1): the rays of this call are one shard of a batch; the convergence
+        word of every round is MAX-all-reduced over the group so that all shards run the rounds the whole batch would
+        (the reference's test is batch-global, ray_sampler.py:151)."""
         self.sampler_resolve()
         o, d = _f32(o, self.device), _f32(d, self.device)
         R = o.shape[0]
@@ -202,8 +206,19 @@ class RenderCore:
         jit = _f32(tape["jitter"], self.device) if "jitter" in tape else None
         ufin = _f32(tape["u_final"], self.device) if "u_final" in tape else None
         st = self._stream()
-        check(self.lib.i2sdf_sampler_rounds(self.h, _ptr(o), _ptr(d), R, _ptr(beta_param), _ptr(jit), _ptr(ufin),
-                                            _ptr(ws), self._ws_bytes, st), "i2sdf_sampler_rounds")
+        if group is not None and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1:
+            import torch.distributed as dist
+            args = (self.h, _ptr(o), _ptr(d), R, _ptr(beta_param), _ptr(jit), _ptr(ufin))
+            check(self.lib.i2sdf_sampler_step(*args, 0, 0, _ptr(ws), self._ws_bytes, st), "i2sdf_sampler_step")
+            off = self.lib.i2sdf_sampler_beta_max(self.h, R, _ptr(ws)) - ws.data_ptr()
+            beta_max = ws[off:off + 4 * self.desc.max_total_iters].view(torch.float32)
+            for k in range(self.desc.max_total_iters):
+                check(self.lib.i2sdf_sampler_step(*args, 1, k, _ptr(ws), self._ws_bytes, st), "i2sdf_sampler_step")
+                dist.all_reduce(beta_max[k:k + 1], op=dist.ReduceOp.MAX, group=group)       # 4 bytes, in stream order
+                check(self.lib.i2sdf_sampler_step(*args, 2, k, _ptr(ws), self._ws_bytes, st), "i2sdf_sampler_step")
+        else:
+            check(self.lib.i2sdf_sampler_rounds(self.h, _ptr(o), _ptr(d), R, _ptr(beta_param), _ptr(jit), _ptr(ufin),
+                                                _ptr(ws), self._ws_bytes, st), "i2sdf_sampler_rounds")
         info = torch.zeros(2, dtype=torch.int32, device=self.device)
         extra = None
         if defer_sync and callable(tape.get("extra_perm")):

@@ -797,12 +797,12 @@ int fused_backward(const i2sdf_handle* h, const bwd::PointSrc& src, long long M,
     // ---- rank-1 pieces
     CsArgs c{};
     c.ntiles = a.ntiles; c.M = M;
-    if (g_sdf) c.jobs[c.njobs++] = CsJob{SL.base + SL.H(NL - 1), g_sdf, 1, dW[L - 1], 256};            // dW_last[0,:] += sum sbar h~
-    if (g_grad) c.jobs[c.njobs++] = CsJob{SL.wbase + SL.HD(NL - 1), nullptr, 0, dW[L - 1], 256};        // q_last = e_sdf: += sum hdot~
+    if (g_sdf) c.jobs[c.njobs++] = CsJob{SL.base + SL.H(NL - 1), g_sdf, 1, dW[L - 1], 256, 1, 0};            // dW_last[0,:] += sum sbar h~
+    if (g_grad) c.jobs[c.njobs++] = CsJob{SL.wbase + SL.HD(NL - 1), nullptr, 0, dW[L - 1], 256, 1, 0};        // q_last = e_sdf: += sum hdot~
     if (color) {
         sigmoid_adjoint3_kernel<<<blocks(M), 256, 0, st>>>(M, s_rgb, g_rgb, D);
         I2SDF_CUDA_CHECK(cudaGetLastError());
-        for (int k = 0; k < 3; ++k) c.jobs[c.njobs++] = CsJob{SL.base + SL.C(Lc - 2), D + k, 4, dWc[Lc - 1] + (size_t)k * 256, 256};
+        c.jobs[c.njobs++] = CsJob{SL.base + SL.C(Lc - 2), D, 4, dWc[Lc - 1], 256, 3, 256};      // the three rgb-head rows: one pass over the slot
         if ((rc = colsum(st, M, 3, D, 4, nullptr, dbc[Lc - 1]))) return rc;
     }
     if ((rc = planes_colsum_launch(h, c, st))) return rc;

@@ -426,6 +426,34 @@ int i2sdf_sampler_rounds(i2sdf_handle* h, const float* o, const float* d, int64_
     return I2SDF_OK;
 }
 
+int i2sdf_sampler_step(i2sdf_handle* h, const float* o, const float* d, int64_t R, const float* beta_param, const float* jitter,
+                       const float* u_final, int stage, int k, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h || !o || !d || !beta_param || !workspace) { set_error("null argument"); return I2SDF_E_INVALID; }
+    if (workspace_bytes < i2sdf_workspace_bytes(h, R, 0)) { set_error("sampler: workspace too small"); return I2SDF_E_WORKSPACE; }
+    if (stage < 0 || stage > 2 || (stage > 0 && (k < 0 || k >= h->smp.max_iters))) { set_error("sampler_step: bad stage / round"); return I2SDF_E_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    SamplerWs W = carve_sampler_ws(h, R, (float*)workspace);
+    if (stage == 0) { ProfScope ps(h, 2, st); return launch_sampler_init(h, W, R, jitter, h->desc.lemma2_coeff, st); }
+    if (stage == 1) {
+        MlpParams p{};
+        p.ray_o = o; p.ray_d = d; p.zarr = W.samples; p.zstride = h->smp.n_eval; p.ns = h->smp.n_eval;
+        p.M = (long long)R * h->smp.n_eval; p.out_sdf = W.sdf_new;
+        p.beta_max = W.beta_max; p.beta_param = beta_param; p.beta_min = h->smp.beta_min; p.round_idx = k;
+        p.net = h->net;
+        int rc = run_mlp(h, p, st);
+        if (rc) return rc;
+        ProfScope ps(h, 2, st, 1);
+        return launch_sampler_round(h, W, R, k, 0, beta_param, nullptr, st);
+    }
+    ProfScope ps(h, 2, st, 1);
+    return launch_sampler_round(h, W, R, k, 1, beta_param, u_final, st);
+}
+
+float* i2sdf_sampler_beta_max(i2sdf_handle* h, int64_t R, void* workspace) {
+    if (!h || !workspace) return nullptr;
+    return carve_sampler_ws(h, R, (float*)workspace).beta_max;
+}
+
 int i2sdf_sampler_finalize(i2sdf_handle* h, int64_t R, const float* beta_param, const int32_t* extra_idx, const int32_t* eik_idx,
                            float* out_z, float* out_z_eik, int32_t* out_info, void* workspace, size_t workspace_bytes, void* stream) {
     if (!h || !beta_param || !out_z || !workspace) { set_error("null argument"); return I2SDF_E_INVALID; }

@@ -252,21 +252,29 @@ __global__ void from_planes_kernel(const uint8_t* __restrict__ slot, int chunks,
     }
 }
 
-// out[j] += sum_m w[m * wstride] * X[m][j]   for a 256-column slot (w null: plain column sums); grid = (tile groups, jobs)
+// out[k][j] += sum_m w_k[m] * X[m][j]   for a 256-column slot (w null: plain column sums), up to 3 weight vectors per pass
+// over the slot (the three rows of the rgb head's gradient read the last radiance activation once); grid = (tile groups, jobs)
 __global__ void __launch_bounds__(256) planes_colsum_kernel(const CsArgs A) {
     const CsJob& J = A.jobs[blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nw = J.w ? J.nw : 1;
     const long long t0 = A.ntiles * blockIdx.x / gridDim.x, t1 = A.ntiles * (blockIdx.x + 1) / gridDim.x;
-    float cs[4][8];
+    float cs[3][4][8];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int k = 0; k < 3; ++k)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) cs[a][e] = 0.f;
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) cs[k][a][e] = 0.f;
     for (long long tile = t0; tile < t1; ++tile) {
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
             const long long m = tile * planes::TM + rr * 32 + lane;
-            const float w = J.w ? (m < A.M ? J.w[(size_t)m * J.wstride] : 0.f) : 1.f;
+            float w[3] = {1.f, 0.f, 0.f};
+            if (J.w) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) w[k] = (k < nw && m < A.M) ? J.w[(size_t)m * J.wstride + k] : 0.f;
+            }
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
                 const uint8_t* sp = J.slot + planes::seg(m, warp + 8 * a, planes::BIG_CHUNKS);
@@ -274,21 +282,33 @@ __global__ void __launch_bounds__(256) planes_colsum_kernel(const CsArgs A) {
                 const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    cs[a][2 * i] = fmaf(w, __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16), cs[a][2 * i]);
-                    cs[a][2 * i + 1] = fmaf(w, __uint_as_float(hw[i] & 0xffff0000u) + __uint_as_float(lw[i] & 0xffff0000u), cs[a][2 * i + 1]);
+                    const float x0 = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
+                    const float x1 = __uint_as_float(hw[i] & 0xffff0000u) + __uint_as_float(lw[i] & 0xffff0000u);
+                    cs[0][a][2 * i] = fmaf(w[0], x0, cs[0][a][2 * i]);
+                    cs[0][a][2 * i + 1] = fmaf(w[0], x1, cs[0][a][2 * i + 1]);
+                    if (nw > 1) {
+                        cs[1][a][2 * i] = fmaf(w[1], x0, cs[1][a][2 * i]);
+                        cs[1][a][2 * i + 1] = fmaf(w[1], x1, cs[1][a][2 * i + 1]);
+                        cs[2][a][2 * i] = fmaf(w[2], x0, cs[2][a][2 * i]);
+                        cs[2][a][2 * i + 1] = fmaf(w[2], x1, cs[2][a][2 * i + 1]);
+                    }
                 }
             }
         }
     }
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int k = 0; k < 3; ++k) {
+        if (k >= nw) break;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            float v = cs[a][e];
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            const int col = (warp + 8 * a) * 8 + e;
-            if (lane == 0 && col < J.n) atomicAdd(J.out + col, v);
-        }
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float v = cs[k][a][e];
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                const int col = (warp + 8 * a) * 8 + e;
+                if (lane == 0 && col < J.n) atomicAdd(J.out + (size_t)k * J.ostride + col, v);
+            }
+    }
 }
 
 }  // namespace wgp

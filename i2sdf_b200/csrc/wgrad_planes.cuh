@@ -31,10 +31,12 @@ struct WgArgs {
 
 struct CsJob {
     const uint8_t* slot;   // 256-column slot
-    const float* w;        // optional per-point weight w[m * wstride]
+    const float* w;        // optional per-point weights w_k[m] = w[m * wstride + k]
     int wstride;
-    float* out;            // out[j] += sum_m w_m X[m][j], j < n
+    float* out;            // out[k * ostride + j] += sum_m w_k[m] X[m][j], j < n, k < nw
     int n;
+    int nw;                // weight vectors sharing ONE pass over the slot (1..3; w null: 1 = plain column sums)
+    int ostride;
 };
 struct CsArgs {
     long long ntiles, M;

@@ -44,6 +44,19 @@ def shard_rays(batch: Dict[str, torch.Tensor], rank: int, world: int) -> Dict[st
     return out
 
 
+def use_global_convergence(model, group: Optional[dist.ProcessGroup] = None, enable: bool = True):
+    """Make the error-bounded sampler's convergence test global over all ranks' rays (strict sharding parity).
+
+    The reference stops up-sampling when `beta.max() <= beta0` over the rays of ONE forward call (ray_sampler.py:151), so a
+    shard on its own may stop a round earlier than the full batch would and then draws different z's.  With this switch
+    every round MAX-all-reduces its 4-byte convergence word over `group` (NCCL, in stream order, no host sync): the
+    sharded render then equals the single-GPU render of the whole batch bit for bit (tests/test_multigpu.py)."""
+    if enable and not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("use_global_convergence needs an initialised torch.distributed process group")
+    model.convergence_group = (group if group is not None else dist.group.WORLD) if enable else None
+    return model
+
+
 def allreduce_gradients(params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None,
                         average: bool = True) -> int:
     """One all-reduce of all gradients as a single flat bucket; returns the number of elements reduced."""

