@@ -53,7 +53,7 @@ SYMBOLS = {
     "i2sdf_composite_forward": (C.c_int, [_P] + [_P] * 7 + [C.c_int64, C.c_int] + [_P] * 6 + [_P]),
     "i2sdf_composite_backward": (C.c_int, [_P] + [_P] * 7 + [C.c_int64, C.c_int] + [_P] * 10 + [_P]),
     "i2sdf_color_backward": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), _P, C.c_int, _P, _P, _P, C.c_int64, C.POINTER(_P), C.POINTER(_P), _P, _P, C.c_size_t, _P]),
-    "i2sdf_light_backward": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), _P, _P, _P, C.c_int64, C.POINTER(_P), C.POINTER(_P), _P, C.c_size_t, _P]),
+    "i2sdf_light_backward": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), _P, _P, _P, _P, C.c_int64, C.POINTER(_P), C.POINTER(_P), _P, C.c_size_t, _P]),
     "i2sdf_sdf_backward": (C.c_int, [_P, C.POINTER(_P), _P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, _P, _P, _P, C.c_int, _P, C.POINTER(_P), C.POINTER(_P), _P, C.c_size_t, _P]),
     "i2sdf_profile_enable": (C.c_int, [_P, C.c_int]),
     "i2sdf_profile_read": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),

@@ -97,7 +97,8 @@ class _PointsFn(Function):
                                     g_grad=g_grad, g_rgb=g_rgb, dW_col=dW_col, db_col=db_col)
             if n_light > 0 and g_light is not None:
                 # the head's own parameters only: its input features are detached (network/__init__.py:165)
-                core.light_backward(W_l, b_l, feat[:M], s_light, g_light, dW_l, db_l)
+                hidden = act.data_ptr() + act.numel() - (M + E) * core.desc.light_hidden * 4     # behind the plane slots (i2sdf_b200.h)
+                core.light_backward(W_l, b_l, feat[:M], s_light, g_light, dW_l, db_l, hidden_ptr=hidden)
             return (None,) * 9 + tuple(dW_sdf + db_sdf + dW_col + db_col + dW_l + db_l)
         g_feat_ptr, ld = None, 256
         if g_rgb is not None:

@@ -368,11 +368,12 @@ class RenderCore:
                                             bws.numel(), self._stream()), "i2sdf_color_backward")
         return g_x
 
-    def light_backward(self, Ws, bs, feat, s_light, g_light, dWs, dbs):
+    def light_backward(self, Ws, bs, feat, s_light, g_light, dWs, dbs, hidden_ptr=0):
+        """hidden_ptr: device address of the head's saved hidden pre-activations (fused path), 0 = recompute."""
         M = feat.shape[0]
         bws = self.backward_workspace(M)
         g_light = _f32(g_light, self.device)
-        check(self.lib.i2sdf_light_backward(self.h, self._ptr_array(Ws), self._ptr_array(bs), _ptr(feat), _ptr(s_light), _ptr(g_light), M,
+        check(self.lib.i2sdf_light_backward(self.h, self._ptr_array(Ws), self._ptr_array(bs), _ptr(feat), C.c_void_p(hidden_ptr), _ptr(s_light), _ptr(g_light), M,
                                             self._ptr_array(dWs), self._ptr_array(dbs), _ptr(bws), bws.numel(), self._stream()),
               "i2sdf_light_backward")
 

@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "tc_bwd.cuh"
 #include "wgrad_planes.cuh"
+#include "tc_common.cuh"
 
 namespace i2sdf {
 
@@ -146,6 +147,13 @@ static int gemm_tn_acc(cudaStream_t st, int N1, int N2, long long K, const float
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float sp100(float a) { float t = a * 100.f; return t > 20.f ? a : __fdiv_rn(log1pf(expf(t)), 100.f); }
 __device__ __forceinline__ float dsp100(float a) { float t = a * 100.f; if (t > 20.f) return 1.f; float z = expf(t); return __fdiv_rn(z, z + 1.f); }
+// MUFU versions (ex2 / lg2 / rcp .approx.ftz, as in the tensor-core epilogues): softplus_100 and its derivative from ONE exp
+__device__ __forceinline__ void sp100_fast(float a, float& sp, float& dsp) {
+    const float e = tc::ex2_approx(-fabsf(a) * 144.26950408889634f);          // exp(-|100 a|)
+    sp = fmaf(tc::lg2_approx(1.0f + e), 0.0069314718055994531f, fmaxf(a, 0.0f));
+    const float rr = tc::rcp_approx(1.0f + e);
+    dsp = (a >= 0.f) ? rr : e * rr;
+}
 __device__ __forceinline__ float d2sp100(float a) { float t = a * 100.f; if (t > 20.f) return 0.f; float z = expf(t); float q = z + 1.f; return 100.f * __fdiv_rn(z, q * q); }
 
 struct PointSrc {             // explicit points, or rays: m -> (m / ns, m % ns)
@@ -502,17 +510,21 @@ __global__ void relu_copy_kernel(long long n, const float* __restrict__ X, float
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) Y[i] = fmaxf(X[i], 0.f);
 }
-// A [M][128] pre-activation (bias added here) -> Hs = softplus ; given glm, lm: delta1 [M], D0 [M][128]
+// Ain [M][128] pre-activation (bias b0 added here unless null) -> Hs = softplus ; given glm, lm: delta1 [M], D0 = A [M][128]
+template <bool FAST>
 __global__ void light_mid_kernel(long long M, int lh, const float* __restrict__ b0, const float* __restrict__ w1, const float* __restrict__ lm,
-                                 const float* __restrict__ glm, float* __restrict__ A, float* __restrict__ Hs, float* __restrict__ d1) {
+                                 const float* __restrict__ glm, const float* Ain, float* A, float* __restrict__ Hs, float* __restrict__ d1) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M * lh) return;
     long long m = i / lh; int f = (int)(i % lh);
-    float a = A[i] + b0[f];
+    float a = Ain[i] + (b0 ? b0[f] : 0.f);
     float y = lm[m];
     float delta = glm[m] * y * (1.f - y);
-    Hs[i] = sp100(a);
-    A[i] = delta * w1[f] * dsp100(a);          // adjoint of the hidden pre-activation
+    float sp, dsp;
+    if (FAST) sp100_fast(a, sp, dsp);
+    else { sp = sp100(a); dsp = dsp100(a); }
+    Hs[i] = sp;
+    A[i] = delta * w1[f] * dsp;                // adjoint of the hidden pre-activation
     if (f == 0) d1[m] = delta;
 }
 }  // namespace bwd
@@ -521,8 +533,10 @@ size_t light_backward_ws_floats(const i2sdf_handle* h, long long M) {
     return (size_t)M * 256 + (size_t)2 * M * h->net.lh + (size_t)M + 64 + (h->use_tc ? tc_wgrad_ws_floats(h) : 0);
 }
 
-int light_backward(const i2sdf_handle* h, long long M, const float* const* W, const float* const* b, const float* feat, const float* lm,
-                   const float* glm, float* const* dW, float* const* db, float* ws, cudaStream_t st) {
+// hidden (optional, tensor-core path): the head's hidden pre-activations W0 relu(feat) + b0 [M][lh] as light_forward left
+// them in the saved state; without it they are recomputed
+int light_backward(const i2sdf_handle* h, long long M, const float* const* W, const float* const* b, const float* feat, const float* hidden,
+                   const float* lm, const float* glm, float* const* dW, float* const* db, float* ws, cudaStream_t st) {
     using namespace bwd;
     if (M <= 0) return I2SDF_OK;
     const int lh = h->net.lh;
@@ -534,17 +548,23 @@ int light_backward(const i2sdf_handle* h, long long M, const float* const* W, co
     const TcBlock blk = h->use_tc ? tc_block(h, TCB_FWD_LIGHT, 0) : TcBlock{nullptr, 0, 0};
     const bool tc = blk.ptr != nullptr;
     int rc;
+    // relu(feat) once (100 MB: it stays L2-resident for the weight-gradient pass below, which is why this copy is cheaper than
+    // fusing the ReLU into that pass's HBM-latency-bound operand loader: measured 74 + 70 us vs 213 us)
     relu_copy_kernel<<<blocks((long long)M * 256), 256, 0, st>>>((long long)M * 256, feat, LF);
     I2SDF_CUDA_CHECK(cudaGetLastError());
-    if (tc) rc = tc_gemm_pw(h, st, M, LF, 256, 256, blk, A, lh, lh, nullptr, 0);       // recompute the hidden pre-activations (bias added below)
-    else rc = gemm_nt(st, (int)M, lh, 256, LF, 256, W[0], 256, A, lh);
-    if (rc) return rc;
-    light_mid_kernel<<<blocks((long long)M * lh), 256, 0, st>>>(M, lh, b[0], W[1], lm, glm, A, Hs, d1);
+    if (!tc) {
+        if ((rc = gemm_nt(st, (int)M, lh, 256, LF, 256, W[0], 256, A, lh))) return rc;
+    } else if (!hidden) {
+        if ((rc = tc_gemm_pw(h, st, M, feat, 256, 256, blk, A, lh, lh, nullptr, /*relu: input*/ 2))) return rc;
+    }
+    // hidden already holds the bias; the recomputed products do not
+    if (tc) light_mid_kernel<true><<<blocks((long long)M * lh), 256, 0, st>>>(M, lh, hidden ? nullptr : b[0], W[1], lm, glm, hidden ? hidden : A, A, Hs, d1);
+    else light_mid_kernel<false><<<blocks((long long)M * lh), 256, 0, st>>>(M, lh, b[0], W[1], lm, glm, A, A, Hs, d1);
     I2SDF_CUDA_CHECK(cudaGetLastError());
     if ((rc = colsum(st, M, lh, Hs, lh, d1, dW[1]))) return rc;          // dW1[0,:] += sum delta * h
     sum_kernel<<<64, 256, 0, st>>>(M, d1, db[1]);
     I2SDF_CUDA_CHECK(cudaGetLastError());
-    if (tc) rc = tc_gemm_wgrad(h, st, M, A, lh, LF, 256, nullptr, 0, nullptr, 0, lh, 256, dW[0], 256, WGP);
+    if (tc) rc = tc_gemm_wgrad(h, st, M, A, lh, LF, 256, nullptr, 0, nullptr, 0, lh, 256, dW[0], 256, WGP);      // dW0 += D0^T relu(feat)
     else rc = gemm_tn_acc(st, lh, 256, M, A, lh, LF, 256, dW[0], 256, h->num_sms);
     if (rc) return rc;
     if ((rc = colsum(st, M, lh, A, lh, nullptr, db[0]))) return rc;
@@ -569,7 +589,9 @@ __global__ void __launch_bounds__(256) light_out_kernel(long long M, int lh, con
     if (lane * 4 < lh) {
         const float4 a = *reinterpret_cast<const float4*>(A + (size_t)m * lh + lane * 4);
         const float4 w = __ldg(reinterpret_cast<const float4*>(head) + lane);
-        acc = fmaf(sp100(a.x), w.x, fmaf(sp100(a.y), w.y, fmaf(sp100(a.z), w.z, sp100(a.w) * w.w)));
+        float s0, s1, s2, s3, dd;
+        sp100_fast(a.x, s0, dd); sp100_fast(a.y, s1, dd); sp100_fast(a.z, s2, dd); sp100_fast(a.w, s3, dd);
+        acc = fmaf(s0, w.x, fmaf(s1, w.y, fmaf(s2, w.z, s3 * w.w)));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);

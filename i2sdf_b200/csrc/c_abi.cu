@@ -41,7 +41,7 @@ int sdf_backward(const i2sdf_handle*, const bwd::PointSrc&, long long, const flo
                  const float*, float* const*, float* const*, float*, cudaStream_t);
 int color_backward(const i2sdf_handle*, long long, int, const float*, const float* const*, const float* const*, const float*, const float*,
                    const float*, float* const*, float* const*, float*, float**, int*, cudaStream_t);
-int light_backward(const i2sdf_handle*, long long, const float* const*, const float* const*, const float*, const float*, const float*,
+int light_backward(const i2sdf_handle*, long long, const float* const*, const float* const*, const float*, const float*, const float*, const float*,
                    float* const*, float* const*, float*, cudaStream_t);
 size_t light_forward_ws_floats(const i2sdf_handle*, long long);
 int light_forward(const i2sdf_handle*, long long, const float*, float*, float*, cudaStream_t);
@@ -377,6 +377,7 @@ static int run_mlp(const i2sdf_handle* h, const MlpParams& p, cudaStream_t st) {
 // 0 = fp32 pre-activations [L-1][M][256] (fp32 kernels + the layer-by-layer backward).  kind 0: main pass, 1: SDF points
 static bool planes_main(const i2sdf_handle* h) { return h->fused && h->tcmain && tcmain_has_full(h->tcmain); }
 static bool planes_sdf(const i2sdf_handle* h) { return h->fused && h->tcmain != nullptr; }
+static size_t planes_main_bytes(const i2sdf_handle* h, int64_t M) { return planes::make_layout(M, h->net.L - 1, h->net.Lc, true, nullptr, nullptr).saved_total(); }
 static bool light_tc(const i2sdf_handle* h) { return h->net.Ll == 2 && h->use_tc && h->tcmain && tcmain_has_full(h->tcmain); }
 int i2sdf_saved_format(const i2sdf_handle* h, int kind) { return h ? ((kind == 0 ? planes_main(h) : planes_sdf(h)) ? 1 : 0) : 0; }
 
@@ -542,6 +543,8 @@ int i2sdf_points_forward_ex(i2sdf_handle* h, const float* o, const float* d, con
     p.net = h->net;
     int rc = run_mlp(h, p, (cudaStream_t)stream);
     if (rc || !ltc) return rc;
+    if (p.sl.base)      // training: the hidden pre-activations stay in the saved state for i2sdf_light_backward
+        return run_light(h, (long long)R * N, s_feat, s_light, (float*)((uint8_t*)save_act + planes_main_bytes(h, p.M)), p.M, (cudaStream_t)stream);
     float* hidden = (float*)workspace + ws_sampler_floats(h, R) + ws_scratch_floats(h) + (size_t)R * 128 * 8 + 64;
     return run_light(h, (long long)R * N, s_feat, s_light, hidden, light_chunk_rays(R) * 128, (cudaStream_t)stream);
 }
@@ -580,13 +583,13 @@ int i2sdf_color_backward(i2sdf_handle* h, const float* const* W, const float* co
     return I2SDF_OK;
 }
 
-int i2sdf_light_backward(i2sdf_handle* h, const float* const* W, const float* const* b, const float* feat, const float* s_light,
+int i2sdf_light_backward(i2sdf_handle* h, const float* const* W, const float* const* b, const float* feat, const float* hidden, const float* s_light,
                          const float* g_light, int64_t M, float* const* dW, float* const* db, void* workspace, size_t workspace_bytes, void* stream) {
     if (!h || !W || !b || !feat || !s_light || !g_light || !dW || !db || !workspace) { set_error("null argument"); return I2SDF_E_INVALID; }
     if (h->net.Ll != 2) { set_error("light_backward: network has no light head"); return I2SDF_E_INVALID; }
     if (workspace_bytes < i2sdf_backward_workspace_bytes(h, M)) { set_error("light_backward: workspace too small"); return I2SDF_E_WORKSPACE; }
     ProfScope ps(h, 6, (cudaStream_t)stream, 8);
-    return light_backward(h, M, W, b, feat, s_light, g_light, dW, db, (float*)workspace, (cudaStream_t)stream);
+    return light_backward(h, M, W, b, feat, hidden, s_light, g_light, dW, db, (float*)workspace, (cudaStream_t)stream);
 }
 
 int i2sdf_sdf_backward(i2sdf_handle* h, const float* const* W, const float* pts, const float* o, const float* d, const float* z, int zstride,
@@ -624,9 +627,10 @@ int i2sdf_profile_read_n(i2sdf_handle* h, int n, float* ms, int64_t* launches) {
 
 size_t i2sdf_saved_bytes(const i2sdf_handle* h, int64_t R, int N) { return i2sdf_saved_bytes_points(h, R * N); }
 
+// plane slots of the main pass (+ for networks with a light head: the head's hidden pre-activations [M][lh] fp32 behind them)
 size_t i2sdf_saved_bytes_points(const i2sdf_handle* h, int64_t M) {
     if (!h || M < 0) return 0;
-    if (planes_main(h)) return planes::make_layout(M, h->net.L - 1, h->net.Lc, true, nullptr, nullptr).saved_total();
+    if (planes_main(h)) return planes_main_bytes(h, M) + (light_tc(h) ? (size_t)M * h->net.lh * sizeof(float) : 0);
     return (size_t)(h->net.L - 1) * (size_t)M * 256 * sizeof(float);
 }
 

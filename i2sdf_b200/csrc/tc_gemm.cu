@@ -280,6 +280,7 @@ struct WGArgs {
     // optional fused X transform: X0 := softplus(Aprev) and X1 := softplus'(Aprev) * Adprev  (ld 256), with the skip concat
     // (columns >= nsplit come from E0 / E1 [M][40]; everything / sqrt2).  When Aprev is set X0 / X1 pointers are ignored.
     const float* Aprev; const float* Adprev; int is_skip; int nsplit; const float* E0; const float* E1;
+    int x_relu;                                               // X := max(X, 0) while staging (light head: relu(features))
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_wgrad_kernel(const WGArgs G) {
@@ -358,6 +359,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_wgrad_kernel(const WGArgs G)
                 a[i] = (ok && r < G.n1) ? __ldg(Pp + (size_t)p * ldp + r) : 0.f;
                 if (!G.Aprev) {
                     bv[i] = (ok && r < G.n2) ? __ldg(Xp + (size_t)p * ldx + r) : 0.f;
+                    if (G.x_relu) bv[i] = fmaxf(bv[i], 0.f);
                 } else if (!(ok && r < G.n2)) {
                     bv[i] = 0.f;
                 } else if (G.is_skip && r >= G.nsplit) {
@@ -491,6 +493,7 @@ int tc_gemm_wgrad_ex(const i2sdf_handle* h, cudaStream_t st, long long M, const 
     WGArgs G;
     G.P0 = P0; G.ldp0 = ldp0; G.X0 = X0; G.ldx0 = ldx0; G.P1 = P1; G.ldp1 = ldp1; G.X1 = X1; G.ldx1 = ldx1; G.n1 = n1; G.n2 = n2; G.M = M; G.partial = ws;
     G.Aprev = Aprev; G.Adprev = Adprev; G.is_skip = is_skip; G.nsplit = nsplit; G.E0 = E0; G.E1 = E1;
+    G.x_relu = (is_skip & 2) ? 1 : 0; G.is_skip = is_skip & 1;      // is_skip bit 1 (only without Aprev): ReLU on X
     long long nk16 = (M + 15) / 16;
     int grid = (int)(nk16 < (long long)h->num_sms ? nk16 : (long long)h->num_sms);
     gemm_wgrad_kernel<<<grid, NTHREADS, kSmemWG, st>>>(G);

@@ -222,10 +222,13 @@ int i2sdf_color_backward(i2sdf_handle* h, const float* const* W, const float* co
                          const float* feat, const float* s_rgb, const float* g_rgb, int64_t M, float* const* dW,
                          float* const* db, float* g_x, void* workspace, size_t workspace_bytes, void* stream);
 
-/* Light-mask head backward (model/network/__init__.py:162-168; features detached -> head parameters only). */
+/* Light-mask head backward (model/network/__init__.py:162-168; features detached -> head parameters only).
+ * feat [M,256] fp32 features; hidden: NULL, or (tensor-core path) the head's hidden pre-activations [M,light_hidden] that
+ * i2sdf_points_forward_ex left behind the plane slots of its saved state (at byte offset
+ * i2sdf_saved_bytes_points(h, M_total) - M_total * light_hidden * 4), which saves recomputing them. */
 int i2sdf_light_backward(i2sdf_handle* h, const float* const* W, const float* const* b, const float* feat,
-                         const float* s_light, const float* g_light, int64_t M, float* const* dW, float* const* db,
-                         void* workspace, size_t workspace_bytes, void* stream);
+                         const float* hidden, const float* s_light, const float* g_light, int64_t M, float* const* dW,
+                         float* const* db, void* workspace, size_t workspace_bytes, void* stream);
 
 /* SDF stack backward incl. second order.  Points: pts [M,3], or (pts NULL) rays o,d [M/ns,3] with z [.., zstride].
  * act: pre-activations saved by the forward.  g_sdf [M] / g_feat [M, ld g_feat_ld] / g_grad [M,3] upstream (NULL = 0);
