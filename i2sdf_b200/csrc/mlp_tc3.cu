@@ -4,10 +4,10 @@
 // layer = ksteps x 3 tcgen05.mma):
 //     sdf-only (sampler):   F_0 .. F_{NL-1}                                   -> sdf
 //     full main pass:       F_0 .. F_{NL-1}, G, C_0 .. C_{Lc-2}, R_{NL-1} .. R_1, R_0   -> sdf, rgb, grad_x sdf
-//   F  SDF hidden layers        epilogue: +b, softplus_100 (+skip concat) [full: softplus' -> scratch]
+//   F  SDF hidden layers        epilogue: +b, softplus_100 (+skip concat) [full: h~ also to its slot / the per-CTA scratch]
 //   G  feature rows of last layer           +b ; appends PE(view dir) as k chunk 8
 //   C  radiance hidden layers               +b, ReLU ; last: rgb head (fp32 dots) + reverse prologue w_sdf * softplus'
-//   R  reverse sweep with W^T               (skip split) * softplus'_{l-1} ;  R_0: J(x)^T r -> grad_x sdf
+//   R  reverse sweep with W^T               (skip split) * softplus'_{l-1} = 1 - exp(-100 h_{l-1}) ;  R_0: J(x)^T r -> grad_x sdf
 // Activations never leave the SM: they are the SMEM A operand (bf16 hi + bf16 lo, canonical K-major layout); weights
 // stream from L2 by cp.async.bulk into a 4-stage ring; accumulators are fp32 in TMEM, two buffers ping-ponged by op;
 // every MAC is 3 bf16 products  A_hi W_hi + A_lo W_hi + A_hi W_lo  (error ~2^-16, measured 3e-5 on the outputs).
@@ -87,9 +87,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const int nsplit = 256 - net.ex;
         const float RS2 = 0.70710678118654752f;
-        // FULL: softplus'(a_l) per layer round-trips through a per-CTA scratch [l][row][256]; in training (plane slots, P.sl)
-        // every A operand is ALSO stored per point (h~_l, q_l, features, radiance activations, encodings) for the backward
-        // chain and the weight gradients, and softplus' is recomputed from the stored h~_l
+        // FULL: the reverse sweep rebuilds softplus'(a_l) from h~_l, which round-trips through HBM/L2 as bf16 hi/lo plane
+        // segments (the bytes the SMEM operand gets): a per-CTA scratch in eval; in training (plane slots, P.sl) every A
+        // operand is stored per point (h~_l, q_l, features, radiance activations, encodings) for the backward chain and the
+        // weight gradients
         constexpr bool save = FULL && SAVE;       // separate instantiation: the eval kernels carry none of the slot code
         const planes::Layout& SL = P.sl;
         uint32_t dphase = 0, g = 0;
@@ -132,11 +133,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
             const bool valid = m < P.M;
             const long long next_tile = tile + gridDim.x;
             float xn[3] = {0.f, 0.f, 0.f}, dvn[3] = {0.f, 0.f, 1.f};
-            float* sig_base = nullptr;
-            size_t sig_lstride = 0;
+            // h~_l (the A operands of the SDF stack) are what the reverse sweep rebuilds softplus' from.  Training: the H slots of
+            // the saved state (indexed by point).  Eval: a per-CTA scratch holding ONE tile in the same plane format (indexed by
+            // row), so the same 16-byte hi/lo segments the SMEM operand gets are stored / re-loaded fully coalesced.
+            // hbase stays null for the sdf + features table (no reverse sweep, nothing to keep).
+            uint8_t* hbase = nullptr;
+            size_t hstride = 0;
+            long long hm = 0;
             if (FULL) {
-                if (!save && P.scratch) { sig_base = P.scratch + (size_t)blockIdx.x * (size_t)NL * TM * 256 + (size_t)row * 256; sig_lstride = (size_t)TM * 256; }
-            }   // sig_base stays null for the sdf + features table (no reverse sweep, nothing to keep)
+                if (save) { hbase = SL.base + SL.H(0); hstride = SL.big; hm = m; }
+                else if (P.scratch) { hbase = reinterpret_cast<uint8_t*>(P.scratch) + (size_t)blockIdx.x * (size_t)NL * planes::BIG_TILE; hstride = planes::BIG_TILE; hm = row; }
+            }
 
             float head = 0.f, rgbp[3] = {0.f, 0.f, 0.f}, gacc[3] = {0.f, 0.f, 0.f};
             for (int op = 0; op < T.nops; ++op, ++g) {
@@ -145,17 +152,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                 mbar_wait(&d_full[b], (dphase >> b) & 1u);
                 dphase ^= (1u << b);
                 tc_fence_after();
-                if (FULL && op + 1 < T.nops) {
-                    // the NEXT op's epilogue may read softplus' rows written ~10 ops ago (they can have left L2: 148 CTAs x
-                    // 1 MB): pull this thread's four 64-byte segments back into L2 one op ahead of their use
-                    const int nk = T.ops[op + 1].kind, nl = T.ops[op + 1].layer;
-                    const int src_l = (nk == EK_REV) ? nl - 1 : ((nk == EK_COL_LAST) ? NL - 1 : -1);
-                    if (src_l >= 0 && sig_base) {
-                        const float* pb = sig_base + (size_t)src_l * sig_lstride + (sub >> 1) * 32 + (sub & 1) * 16;
-#pragma unroll
-                        for (int it = 0; it < 4; ++it) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + it * 64));
-                    }
-                }
                 if (op == T.nops - 1 && next_tile < ntiles) {
                     // the A operand is free (this tile's last MMAs are done): start the NEXT tile's first layer now, so its
                     // tensor work overlaps this tile's last epilogue
@@ -170,15 +166,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                     // global operands of this item (bias, or the softplus' row of the reverse sweep) are requested BEFORE the
                     // TMEM load so their latency overlaps it (the tcgen05.wait::ld below is a compiler barrier)
                     uint4 pre[4];
-                    if (FULL && save && (kind == EK_REV || kind == EK_COL_LAST)) {
-                        load_slot16(SL.base + SL.H(kind == EK_REV ? l - 1 : NL - 1) + planes::seg(m, col0 >> 3, planes::BIG_CHUNKS), pre);
+                    if (FULL && (kind == EK_REV || kind == EK_COL_LAST)) {
+                        load_slot16(hbase + (size_t)(kind == EK_REV ? l - 1 : NL - 1) * hstride + planes::seg(hm, col0 >> 3, planes::BIG_CHUNKS), pre);
                     } else {
                         const float* psrc;
                         if (kind == EK_SDF_HIDDEN || kind == EK_SDF_LAST || kind == EK_SDF_LAST_REV) psrc = net.sdf_b[l] + col0;
                         else if (FULL && kind == EK_FEAT) psrc = net.sdf_b[net.L - 1] + col0;
                         else if (FULL && kind == EK_COL_HIDDEN) psrc = net.col_b[l] + col0;
-                        else if (FULL && kind == EK_COL_LAST) psrc = sig_base + (size_t)(NL - 1) * sig_lstride + col0;
-                        else if (FULL && kind == EK_REV) psrc = sig_base + (size_t)(l - 1) * sig_lstride + col0;
                         else psrc = net.sdf_head;
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) pre[j4] = *reinterpret_cast<const uint4*>(psrc + j4 * 4);
@@ -191,21 +185,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
                             const float bv[4] = {__uint_as_float(pre[j4].x), __uint_as_float(pre[j4].y), __uint_as_float(pre[j4].z), __uint_as_float(pre[j4].w)};
-                            float so[4];
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 const float a = __uint_as_float(v[j4 * 4 + u]) + bv[u];
                                 const float e = ex2_approx(-fabsf(a) * 144.26950408889634f);          // exp(-|100 a|)
                                 hv[j4 * 4 + u] = fmaf(lg2_approx(1.0f + e), 0.0069314718055994531f, fmaxf(a, 0.0f));
-                                if (FULL) {
+                                if (FULL && kind == EK_SDF_LAST_REV) {
                                     const float rr = rcp_approx(1.0f + e);
-                                    const float sgm = (a >= 0.f) ? rr : e * rr;                     // softplus'(a) = sigmoid(100 a)
-                                    so[u] = sgm;
-                                    if (kind == EK_SDF_LAST_REV) v[j4 * 4 + u] = __float_as_uint(sgm);   // the accumulator is consumed: keep softplus' there
+                                    v[j4 * 4 + u] = __float_as_uint((a >= 0.f) ? rr : e * rr);      // softplus'(a) = sigmoid(100 a); the accumulator is consumed: keep it there
                                 }
                             }
-                            if (FULL && sig_base)
-                                *reinterpret_cast<float4*>(sig_base + (size_t)l * sig_lstride + col0 + j4 * 4) = make_float4(so[0], so[1], so[2], so[3]);
                         }
                         if (FULL && kind == EK_SDF_LAST_REV) {
                             // sdf + grad only: head, h_{NL-1} to its slot, then straight into the reverse sweep: q = w_sdf * softplus'
@@ -269,25 +258,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                                 rgbp[2] = fmaf(hh[0], w2.x, fmaf(hh[1], w2.y, fmaf(hh[2], w2.z, fmaf(hh[3], w2.w, rgbp[2]))));
                             }
                             // reverse prologue: adjoint of a_{NL-1} = w_sdf * softplus'(a_{NL-1})
-                            if (save) {
+                            if (save)
                                 store_a16(A_hi, A_lo, row, col0 >> 3, hv, SL.base + SL.C(l) + planes::seg(m, col0 >> 3, planes::BIG_CHUNKS),
                                           (uint32_t)planes::BIG_PLANE, true, false);          // last radiance activation: slot only
-                                slot16_values(pre, hv);                                       // h_{NL-1}
+                            slot16_values(pre, hv);                                           // h_{NL-1}
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) hv[j] = __ldg(net.sdf_head + col0 + j) * dsoftplus_from_h(hv[j]);
-                            } else {
-#pragma unroll
-                                for (int j4 = 0; j4 < 4; ++j4) {
-                                    const float4 w = __ldg(reinterpret_cast<const float4*>(net.sdf_head + col0) + j4);
-                                    hv[j4 * 4 + 0] = w.x * __uint_as_float(pre[j4].x); hv[j4 * 4 + 1] = w.y * __uint_as_float(pre[j4].y);
-                                    hv[j4 * 4 + 2] = w.z * __uint_as_float(pre[j4].z); hv[j4 * 4 + 3] = w.w * __uint_as_float(pre[j4].w);
-                                }
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const float4 w = __ldg(reinterpret_cast<const float4*>(net.sdf_head + col0) + j4);
+                                hv[j4 * 4 + 0] = w.x * dsoftplus_from_h(hv[j4 * 4 + 0]); hv[j4 * 4 + 1] = w.y * dsoftplus_from_h(hv[j4 * 4 + 1]);
+                                hv[j4 * 4 + 2] = w.z * dsoftplus_from_h(hv[j4 * 4 + 2]); hv[j4 * 4 + 3] = w.w * dsoftplus_from_h(hv[j4 * 4 + 3]);
                             }
                         }
                     } else if (FULL && kind == EK_REV) {
                         // accumulator = adjoint of the input of SDF layer l ; next A = (that) * softplus'(a_{l-1})
                         const bool is_skip = (l == net.skip);
-                        if (save) {        // softplus'(a_{l-1}) from the stored h~_{l-1} (a skip concat stored it scaled by 1/sqrt2)
+                        {                  // softplus'(a_{l-1}) from the stored h~_{l-1} (a skip concat stored it scaled by 1/sqrt2)
                             slot16_values(pre, hv);
                             const float hs = is_skip ? 144.26950408889634f * 1.41421356237309505f : 144.26950408889634f;
 #pragma unroll
@@ -295,8 +280,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                         }
 #pragma unroll
                         for (int j4 = 0; j4 < 4; ++j4) {
-                            const float sv[4] = {save ? hv[j4 * 4] : __uint_as_float(pre[j4].x), save ? hv[j4 * 4 + 1] : __uint_as_float(pre[j4].y),
-                                                 save ? hv[j4 * 4 + 2] : __uint_as_float(pre[j4].z), save ? hv[j4 * 4 + 3] : __uint_as_float(pre[j4].w)};
+                            const float sv[4] = {hv[j4 * 4], hv[j4 * 4 + 1], hv[j4 * 4 + 2], hv[j4 * 4 + 3]};
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 float rv = __uint_as_float(v[j4 * 4 + u]);
@@ -342,6 +326,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                             else if (kind == EK_REV) { so = SL.Q(l - 1); keep = valid; }
                             else { so = SL.Q(NL - 1); keep = valid; }          // EK_COL_LAST / EK_SDF_LAST_REV: q_{NL-1}
                             g = SL.base + so + planes::seg(m, col0 >> 3, planes::BIG_CHUNKS);
+                        } else if (FULL && hbase && (kind == EK_SDF_HIDDEN || kind == EK_SDF_LAST)) {
+                            g = hbase + (size_t)l * hstride + planes::seg(hm, col0 >> 3, planes::BIG_CHUNKS);      // eval: h~_l to the per-CTA scratch
                         }
                         store_a16(A_hi, A_lo, row, col0 >> 3, hv, g, (uint32_t)planes::BIG_PLANE, keep);
                     }
