@@ -17,6 +17,7 @@
 // Replaces (reference): what torch.autograd runs for loss.backward() through ImplicitNetwork.forward / .gradient
 // (mlp.py:84-143, incl. the create_graph second-order graph) and RenderingNetwork.forward (mlp.py:208-229) — every
 // per-point matrix product except the weight gradients themselves.
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tc_chain.cuh"
@@ -59,6 +60,13 @@ __device__ __forceinline__ void store_a8(uint8_t* A_hi, uint8_t* A_lo, int row, 
     }
 }
 
+__device__ __forceinline__ void pf_l2(const uint8_t* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// the four 16-byte segments (hi / lo planes x two chunks) of a 16-column item
+__device__ __forceinline__ void pf_seg16(const uint8_t* seg) {
+    pf_l2(seg); pf_l2(seg + planes::SUB_CHUNK); pf_l2(seg + planes::BIG_PLANE); pf_l2(seg + planes::BIG_PLANE + planes::SUB_CHUNK);
+}
+
+template <bool PF_NEXT>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const BwdParams P, const OpTable T) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -169,6 +177,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const BwdParams P, 
                     const int col0 = c * 32 + (sub & 1) * 16;          // first of this warp's 16 columns
                     const int kc0 = col0 >> 3;
                     const size_t sg = planes::seg(m, kc0, planes::BIG_CHUNKS);
+                    if (PF_NEXT) {
+                        // this warp's NEXT item (same op, or the first item of the next op) reads 2..6 slot segments per 8 columns
+                        // straight from HBM with nothing else to hide the latency behind: pull them into L2 one item ahead
+                        int pk = kind, pl = l, pit = it + P.pf_dist;
+                        if (pit >= 4) { pit -= 4; if (op + 1 < T.nops) { pk = T.ops[op + 1].kind; pl = T.ops[op + 1].layer; } else pk = -1; }
+                        const size_t psg = planes::seg(m, ((2 * pit + (sub >> 1)) * 32 + (sub & 1) * 16) >> 3, planes::BIG_CHUNKS);
+                        if (pk == BK_P) {
+                            pf_seg16(SL.base + SL.H(pl) + psg); pf_seg16(SL.base + SL.Q(pl) + psg); pf_seg16(SL.wbase + SL.HD(pl) + psg);
+                        } else if (pk == BK_TAN) {
+                            pf_seg16(SL.base + SL.H(pl) + psg);
+                        } else if (pk == BK_COL_REV) {
+                            pf_l2(SL.base + SL.C(pl - 1) + psg); pf_l2(SL.base + SL.C(pl - 1) + psg + planes::SUB_CHUNK);
+                        }
+                    }
                     if (kind == BK_TAN) {
                         // hdot_l = softplus'(a_l) * adot_l   (skip concat: [hdot | J gbar] / sqrt2)
                         const bool feeds_skip = (l + 1 == net.skip);
@@ -302,13 +324,21 @@ int tc_bwd_launch(const i2sdf_handle* h, const BwdParams& p, cudaStream_t st) {
     const chain::OpTable* tab = tc_bwd_table(h, p.with_color != 0);
     if (!tab || tab->nops == 0) { set_error("tc_bwd_launch: no backward op table for this network"); return I2SDF_E_INVALID; }
     static bool attr_done = false;
+    static int pf = 1;
     if (!attr_done) {
-        I2SDF_CUDA_CHECK(cudaFuncSetAttribute(tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain::kSmemBytes));
+        I2SDF_CUDA_CHECK(cudaFuncSetAttribute(tc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain::kSmemBytes));
+        I2SDF_CUDA_CHECK(cudaFuncSetAttribute(tc_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain::kSmemBytes));
+        const char* e = getenv("I2SDF_BWD_PREFETCH");          // items ahead (1..4), 0 = off
+        pf = e ? atoi(e) : 1;
+        if (pf < 0 || pf > 4) pf = 1;
         attr_done = true;
     }
     const long long ntiles = (p.M + chain::TM - 1) / chain::TM;
     const int grid = (int)(ntiles < (long long)h->num_sms ? ntiles : (long long)h->num_sms);
-    tc_bwd_kernel<<<grid, chain::NTHREADS, chain::kSmemBytes, st>>>(p, *tab);
+    BwdParams q = p;
+    q.pf_dist = pf;
+    if (pf) tc_bwd_kernel<true><<<grid, chain::NTHREADS, chain::kSmemBytes, st>>>(q, *tab);
+    else tc_bwd_kernel<false><<<grid, chain::NTHREADS, chain::kSmemBytes, st>>>(q, *tab);
     I2SDF_CUDA_CHECK(cudaGetLastError());
     return I2SDF_OK;
 }

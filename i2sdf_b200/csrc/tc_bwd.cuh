@@ -27,6 +27,7 @@ struct BwdParams {
     const float* g_rgb;    // [M][3]   (with_color)
     const float* s_rgb;    // [M][3]   forward rgb (sigmoid output), for its derivative
     int with_color;
+    int pf_dist;           // slot segments are prefetched into L2 this many 16-column items ahead (set by tc_bwd_launch)
     planes::Layout sl;     // saved forward slots (sl.base) + backward workspace slots (sl.wbase)
     NetDev net;
 };
