@@ -340,6 +340,7 @@ def gpu_arm(args, rank, world, local_rank):
     core.rounds_log.clear()
     ms_res, prof = timed(step_resident, args.steps, profile=True)
     rounds_seen = sorted(set(core.rounds_log))
+    rounds_total = sum(core.rounds_log)
     ms_e2e, _ = timed(step_e2e, args.steps)
     clocks = clk.stop()
     ms_render = 0.0
@@ -364,7 +365,9 @@ def gpu_arm(args, rank, world, local_rank):
     pk = peaks()
     # dominant kernel: sampler SDF evaluations (73 % of the forward path's FLOPs)
     sdf = prof["sampler_sdf"]
-    sdf_launches = max(sdf["launches"], 1)
+    # launches of rounds the device-side convergence word switched off return at once: only ACTIVE launches count (training: the
+    # rounds each timed step really ran, read back by sampler_resolve; eval: the W-sharp weights run all of them)
+    sdf_launches = max(rounds_total if (train and rounds_total > 0) else sdf["launches"], 1)
     pts_per_launch = R * 128
     per_launch_ms = sdf["ms"] / sdf_launches
     achieved = pts_per_launch * flops["sdf_eval"] / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0

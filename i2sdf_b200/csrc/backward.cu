@@ -544,7 +544,7 @@ int light_backward(const i2sdf_handle* h, long long M, const float* const* W, co
     float* A = LF + (size_t)M * 256;             // [M][lh]
     float* Hs = A + (size_t)M * lh;              // [M][lh]
     float* d1 = Hs + (size_t)M * lh;             // [M]
-    float* WGP = d1 + (size_t)M + 16;            // tensor-core weight-gradient partials
+    float* WGP = d1 + (((size_t)M + 3) & ~(size_t)3) + 16;   // tensor-core weight-gradient partials (16-byte aligned: float4 stores)
     const TcBlock blk = h->use_tc ? tc_block(h, TCB_FWD_LIGHT, 0) : TcBlock{nullptr, 0, 0};
     const bool tc = blk.ptr != nullptr;
     int rc;

@@ -654,3 +654,43 @@ def test_fused_loss_matches_the_pytorch_restatement(R, all_terms):
             continue
         assert of[k].grad is not None, k
         assert relerr(of[k].grad, ot[k].grad) < 1e-5, (k, relerr(of[k].grad, ot[k].grad))
+
+
+@pytest.mark.parametrize("R", [1, 5, 130])
+def test_ragged_ray_counts_render_and_train(R):
+    """Ray counts that fill neither a tile nor a warp: eval render against the oracle, and a full training step (finite loss and
+    gradients for every parameter) — the reference accepts any batch size (train_dataset.py:169-209)."""
+    from i2sdf_b200 import configs
+    from i2sdf_b200.network import I2SDFLoss, I2SDFNetwork
+    import contextlib
+    import io
+    conf = configs.model_conf("synthetic_light_mask")
+    conf["use_normal"] = True
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = I2SDFNetwork(conf)
+    with torch.no_grad():
+        m.density.beta.fill_(0.05)
+    m = m.cuda().eval()
+    inp = orc.synthetic_rays(R, seed=R)
+    out = m({k: v.cuda() for k, v in inp.items()})
+    spec = orc.spec_from_model_conf(conf, use_normal=False)
+    P = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        ref = orc.render(spec, P, inp, training=False)
+    for k in ("rgb_values", "depth_values", "weight_sum", "light_mask"):
+        assert out[k].shape == ref[k].shape, k
+        assert relerr(out[k], ref[k]) < 5e-3, (k, relerr(out[k], ref[k]))       # end to end through the sampler (indices may move one bin)
+    m.train()
+    tin = {k: v.cuda() for k, v in orc.synthetic_rays(R, seed=R + 1, train_layout=True).items()}
+    g = torch.Generator().manual_seed(R)
+    gt = {"rgb": torch.rand(R, 3, generator=g).cuda(), "depth": (torch.rand(R, generator=g) + 1).cuda(), "depth_mask": torch.ones(R, dtype=torch.bool).cuda(),
+          "normal": torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=1).cuda(), "normal_mask": torch.ones(R, dtype=torch.bool).cuda(),
+          "light_mask": (torch.rand(R, 1, generator=g) > 0.5).float().cuda()}
+    tout = m(tin)
+    assert tout["grad_theta"].shape == (2 * R, 3) and tout["light_mask"].shape == (R, 1)
+    loss = I2SDFLoss(**configs.LOSS_SYNTHETIC_LIGHT_MASK)(tout, gt, 0)["loss"]
+    loss.backward()
+    assert torch.isfinite(loss)
+    for n, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n

@@ -9,8 +9,13 @@ for r in rows[1:]:
     v = float(r[vi].replace(",", "")); u = r[ui]
     v = v / 1000 if u in ("ns", "nsecond") else v * (1000 if u in ("ms", "msecond") else 1)
     L.append((re.sub(r"\(.*", "", r[ki])[:60], v))
-n = len(L) // nsteps
-L = L[-n:]
+# one full step = the launches between two consecutive sampler_init_kernel launches (a cyclic shift of a step: the tail of one
+# step and the head of the next); falls back to the last 1/nsteps of the list
+marks = [i for i, (k, _) in enumerate(L) if "sampler_init_kernel" in k]
+if len(marks) >= 2:
+    L = L[marks[-2]:marks[-1]]
+else:
+    L = L[-(len(L) // nsteps):]
 agg = collections.defaultdict(lambda: [0, 0.0])
 for k, v in L:
     agg[k][0] += 1; agg[k][1] += v
