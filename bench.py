@@ -399,7 +399,10 @@ def gpu_arm(args, rank, world, local_rank):
         "dtype": "f32 (bf16 hi/lo split products on tcgen05, fp32 accumulate)" if core.uses_tensor_cores else "f32",
         "data": "synthetic",
         "config": {"workload": workload, "mode": args.mode, "network_config": args.config,
-                   "weights": "W-sharp: reference geometric init (seed 0), density.beta=0.01 so all 5 sampler rounds run",
+                   "weights": ("W-sharp at step 0: reference geometric init (seed 0), density.beta=0.01 (all 5 sampler rounds run); training then "
+                               "moves the weights every step (Adam, lr 5e-4) and the packed copies follow, so later steps may converge in fewer "
+                               "rounds: see sampler_rounds_in_timed_steps") if train else
+                              "W-sharp: reference geometric init (seed 0), density.beta=0.01 so all 5 sampler rounds run",
                    "rays_per_gpu": R, "global_rays": world * R, "samples_per_ray_composited": N_COMPOSITED,
                    "sdf_evals_per_ray": 5 * 128 + N_COMPOSITED,
                    "sampler_rounds_in_timed_steps": rounds_seen if train else "5 (eval: weights fixed)",
