@@ -26,6 +26,18 @@ class LossArgs(C.Structure):
         "terms", "g_rgb", "g_grad_theta", "g_diff_norm", "g_weight_sum", "g_depth", "g_normal", "g_surface_sdf", "g_light")]
 
 
+WNORM_MAX_JOBS = 28
+
+
+class WnormJob(C.Structure):
+    """i2sdf_wnorm_job (include/i2sdf_b200.h)."""
+    _fields_ = [(n, C.c_void_p) for n in ("g", "v", "W", "norm", "dW", "dg", "dv")] + [("rows", C.c_int32), ("cols", C.c_int32)]
+
+
+class WnormBatch(C.Structure):
+    _fields_ = [("n", C.c_int32), ("pad_", C.c_int32), ("jobs", WnormJob * WNORM_MAX_JOBS)]
+
+
 # every symbol include/i2sdf_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -65,6 +77,7 @@ SYMBOLS = {
     "i2sdf_fused_backward": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(_P), C.POINTER(_P),
                                        C.POINTER(_P), C.POINTER(_P), _P, C.c_size_t, _P]),
     "i2sdf_loss_forward": (C.c_int, [C.POINTER(LossArgs), _P]),
+    "i2sdf_weight_norm": (C.c_int, [C.POINTER(WnormBatch), C.c_int, _P]),
     "i2sdf_planes_slot_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
     "i2sdf_planes_pack": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, _P, _P]),
     "i2sdf_planes_unpack": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, C.c_int, C.c_int, _P]),

@@ -341,3 +341,75 @@ def fused_loss(sel, weights):
     """sel: dict with the _LOSS_PRED / _LOSS_AUX entries (None = term off) -> terms [10] (terms[0] = loss, differentiable)."""
     aux = {k: sel.get(k) for k in _LOSS_AUX}
     return _LossFn.apply(weights, aux, *[sel.get(k) for k in _LOSS_PRED])
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# weight norm of every layer in one launch per direction (csrc/wnorm.cu)
+# ----------------------------------------------------------------------------------------------------------------------
+class _WeightNormAll(Function):
+    """(g_0, v_0, g_1, v_1, ...) -> (W_0, W_1, ...) with W = g v / ||v||_row  (torch._weight_norm(v, g, 0) per layer)."""
+
+    @staticmethod
+    def _launch(gs, vs, norms, Ws=None, dWs=None, dgs=None, dvs=None):
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        b = _lib.WnormBatch()
+        b.n = len(gs)
+        for i, (g, v, nrm) in enumerate(zip(gs, vs, norms)):
+            j = b.jobs[i]
+            j.g, j.v, j.norm, j.rows, j.cols = g.data_ptr(), v.data_ptr(), nrm.data_ptr(), v.shape[0], v.shape[1]
+            if Ws is not None:
+                j.W = Ws[i].data_ptr()
+            if dWs is not None and dWs[i] is not None:
+                j.dW, j.dg, j.dv = dWs[i].data_ptr(), dgs[i].data_ptr(), dvs[i].data_ptr()
+        dev = vs[0].device
+        with torch.cuda.device(dev):
+            _lib.check(lib.i2sdf_weight_norm(C.byref(b), 0 if Ws is not None else 1, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                       "i2sdf_weight_norm")
+
+    @staticmethod
+    def forward(ctx, *gv):
+        gs = [t.detach().contiguous() for t in gv[0::2]]
+        vs = [t.detach().contiguous() for t in gv[1::2]]
+        dev = vs[0].device
+        rows = [v.shape[0] for v in vs]
+        flat_n = torch.empty(sum((r + 3) // 4 * 4 for r in rows), device=dev)          # all norms in one allocation
+        norms, off = [], 0
+        for r in rows:
+            norms.append(flat_n[off:off + r])
+            off += (r + 3) // 4 * 4
+        Ws = [torch.empty_like(v) for v in vs]
+        _WeightNormAll._launch(gs, vs, norms, Ws=Ws)
+        ctx.save_for_backward(*gs, *vs, flat_n)
+        ctx.rows = rows
+        ctx.set_materialize_grads(False)
+        return tuple(Ws)
+
+    @staticmethod
+    def backward(ctx, *dWs):
+        n = len(ctx.rows)
+        saved = ctx.saved_tensors
+        gs, vs, flat_n = saved[:n], saved[n:2 * n], saved[2 * n]
+        norms, off = [], 0
+        for r in ctx.rows:
+            norms.append(flat_n[off:off + r])
+            off += (r + 3) // 4 * 4
+        dWs = [None if d is None else d.contiguous() for d in dWs]
+        if all(d is None for d in dWs):
+            return (None,) * (2 * n)
+        dgs = [None if d is None else torch.empty_like(g) for d, g in zip(dWs, gs)]
+        dvs = [None if d is None else torch.empty_like(v) for d, v in zip(dWs, vs)]
+        _WeightNormAll._launch(gs, vs, norms, dWs=dWs, dgs=dgs, dvs=dvs)
+        out = []
+        for dg, dv in zip(dgs, dvs):
+            out += [dg, dv]
+        return tuple(out)
+
+
+def weight_norm_all(layers):
+    """Effective weights of weight-normed nn.Linear layers (attributes weight_g [out,1], weight_v [out,in]) on a CUDA device."""
+    args = []
+    for lin in layers:
+        args += [lin.weight_g, lin.weight_v]
+    return list(_WeightNormAll.apply(*args))

@@ -20,6 +20,7 @@
 // Replaces (reference): ImplicitNetwork.get_sdf_vals mlp.py:145-151 as called by the sampler (ray_sampler.py:84-89);
 // model/network/__init__.py:103-116 = ImplicitNetwork.get_outputs mlp.py:123-143 (forward :84-105 + autograd.grad
 // :134-140) and RenderingNetwork.forward mlp.py:208-229; Embedder embedder.py:28-38.
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tc_chain.cuh"
@@ -500,6 +501,14 @@ int tc_create(i2sdf_handle* h) {
         push(s->blk_rev_feat, tcb::BK_P, NL - 1);
         for (int l = NL - 1; l >= 1; --l) push(s->blk_rev_sdf[l], tcb::BK_P, l - 1);
         if (variant == 0 && !want_full) B.nops = 0;
+    }
+    {
+        const char* dm = getenv("I2SDF_DEBUG_MMAS");
+        const int nm = (dm && (dm[0] == '1' || dm[0] == '2')) ? dm[0] - '0' : 3;
+        s->full.mma_per_k = s->sdf.mma_per_k = s->sg.mma_per_k = s->sf.mma_per_k = s->bwd_full.mma_per_k = s->bwd_sdf.mma_per_k = nm;
+        const char* ns = getenv("I2SDF_DEBUG_NOSTREAM");
+        const int nost = (ns && ns[0] == '1') ? 1 : 0;
+        s->full.no_stream = s->sdf.no_stream = s->sg.no_stream = s->sf.no_stream = s->bwd_full.no_stream = s->bwd_sdf.no_stream = nost;
     }
     cudaError_t e = cudaFuncSetAttribute(tc_mlp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_mlp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);

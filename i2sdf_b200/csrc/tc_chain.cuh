@@ -36,6 +36,8 @@ struct Op {
 struct OpTable {
     const uint8_t* wpack;
     int nops;
+    int mma_per_k;      // 3 (hi*hi + lo*hi + hi*lo).  1 / 2 = ablation only (I2SDF_DEBUG_MMAS: wrong numerics, shows how MMA-bound a chain is)
+    int no_stream;      // ablation only (I2SDF_DEBUG_NOSTREAM=1): the producer signals the ring stages without copying the weights
     Op ops[MAX_OPS];
 };
 
@@ -112,8 +114,11 @@ __device__ __forceinline__ void chain_producer(const OpTable& T, long long ntile
             const uint8_t* src = T.wpack + T.ops[op].w_off;
             for (int ks = 0; ks < T.ops[op].ksteps; ++ks) {
                 mbar_wait(&empty[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&full[stage], sb);
-                bulk_g2s(ring + stage * STAGE_MAX, src + (size_t)ks * sb, sb, &full[stage]);
+                if (T.no_stream) { mbar_arrive(&full[stage]); }
+                else {
+                    mbar_arrive_expect_tx(&full[stage], sb);
+                    bulk_g2s(ring + stage * STAGE_MAX, src + (size_t)ks * sb, sb, &full[stage]);
+                }
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
         }
@@ -147,8 +152,8 @@ __device__ __forceinline__ void chain_mma(const OpTable& T, long long ntiles, ui
                 const uint64_t db_hi = smem_desc(b_s, lbo_b, SBO);
                 const uint64_t db_lo = smem_desc(b_s + lo_off, lbo_b, SBO);
                 mma_bf16_ss(d_tmem, da_hi, db_hi, idesc, ks > 0 ? 1u : 0u);
-                mma_bf16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
-                mma_bf16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
+                if (T.mma_per_k > 1) mma_bf16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
+                if (T.mma_per_k > 2) mma_bf16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
                 mma_commit(&empty[stage]);
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }

@@ -311,12 +311,14 @@ class I2SDFNetwork(nn.Module):
         return self._core_obj
 
     def effective_weights(self):
-        Ws, bs = [], []
-        for st in self._stacks():
-            w, b = st.effective()
-            Ws += w
-            bs += b
-        return Ws, bs
+        """W = g v / ||v|| of every layer (mlp.py:71-72) + biases, SDF stack first, then radiance, then light.  On CUDA with
+        all layers weight-normed (the shipped configs) this is ONE launch (and one for its backward), csrc/wnorm.cu."""
+        layers = [l for st in self._stacks() for l in st.layers()]
+        bs = [l.bias for l in layers]
+        if len(layers) <= 28 and all(hasattr(l, "weight_g") for l in layers) and layers[0].weight_v.is_cuda:
+            from .autograd import weight_norm_all
+            return weight_norm_all(layers), bs
+        return [_effective_weight(l) for l in layers], bs
 
     @torch.no_grad()
     def pack_weights(self):

@@ -318,6 +318,29 @@ typedef struct i2sdf_loss_args {
 } i2sdf_loss_args;
 int i2sdf_loss_forward(const i2sdf_loss_args* args, void* stream);
 
+/* ---- weight norm --------------------------------------------------------------------------
+ * Replaces: the nn.utils.weight_norm pre-forward hook and its autograd backward for EVERY layer of the model
+ * (mlp.py:71-72, 200-201; torch._weight_norm with dim = 0), one launch per direction.
+ * forward (backward = 0): W = g * v / ||v||_row, norm[r] = ||v[r,:]|| (kept for the backward).
+ * backward (backward = 1): given dW: dg, dv (written, not accumulated); a job with dW == NULL is skipped. */
+#define I2SDF_WNORM_MAX_JOBS 28
+typedef struct i2sdf_wnorm_job {
+    const float* g;       /* [rows]      weight_g */
+    const float* v;       /* [rows,cols] weight_v */
+    float* W;             /* [rows,cols] out (forward) */
+    float* norm;          /* [rows]      out (forward) / in (backward) */
+    const float* dW;      /* [rows,cols] in (backward) or NULL */
+    float* dg;            /* [rows]      out (backward) */
+    float* dv;            /* [rows,cols] out (backward) */
+    int32_t rows, cols;
+} i2sdf_wnorm_job;
+typedef struct i2sdf_wnorm_batch {
+    int32_t n;
+    int32_t pad_;
+    i2sdf_wnorm_job jobs[I2SDF_WNORM_MAX_JOBS];
+} i2sdf_wnorm_batch;
+int i2sdf_weight_norm(const i2sdf_wnorm_batch* batch, int backward, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

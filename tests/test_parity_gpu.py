@@ -694,3 +694,27 @@ def test_ragged_ray_counts_render_and_train(R):
     assert torch.isfinite(loss)
     for n, p in m.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), n
+
+
+def test_batched_weight_norm_matches_torch():
+    """csrc/wnorm.cu (all layers, one launch per direction) vs torch._weight_norm + autograd on the same parameters (a16)."""
+    c = Case("train_light")
+    m = _model(c, training=True)
+    Ws, bs = m.effective_weights()
+    layers = [l for st in m._stacks() for l in st.layers()]
+    assert len(Ws) == len(layers) == 13
+    g = torch.Generator().manual_seed(3)
+    ups = [torch.randn(w.shape, generator=g).cuda() if i != 4 else None for i, w in enumerate(Ws)]      # layer 4 gets no gradient
+    sum((w * u).sum() for w, u in zip(Ws, ups) if u is not None).backward()
+    mine = [(l.weight_g.grad, l.weight_v.grad) for l in layers]
+    for l in layers:
+        l.weight_g.grad = l.weight_v.grad = None
+    ref = [torch._weight_norm(l.weight_v, l.weight_g, 0) for l in layers]
+    sum((w * u).sum() for w, u in zip(ref, ups) if u is not None).backward()
+    for i, (l, w, r) in enumerate(zip(layers, Ws, ref)):
+        assert relerr(w, r) < 1e-6, i
+        if ups[i] is None:
+            assert mine[i][0] is None and mine[i][1] is None
+            continue
+        assert relerr(mine[i][0], l.weight_g.grad) < 1e-5, i
+        assert relerr(mine[i][1], l.weight_v.grad) < 1e-5, i
