@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
     if (warp == 0) {
         if (lane == 0) chain_producer(T, ntiles, ring, full, empty);
     } else if (warp == 1) {
-        if (lane == 0) chain_mma(T, ntiles, tmem_base, A_hi, A_lo, ring, full, empty, a_ready, d_full);
+        chain_mma(T, ntiles, tmem_base, A_hi, A_lo, ring, full, empty, a_ready, d_full, FULL ? nullptr : reinterpret_cast<long long*>(P.scratch));
     } else {
         // ================= epilogue warps =================
         const int q = warp & 3;
@@ -150,9 +150,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
             for (int op = 0; op < T.nops; ++op, ++g) {
                 const uint32_t b = g & 1u;
                 const int kind = T.ops[op].kind, l = T.ops[op].layer;
+                // development probe (I2SDF_DEBUG_TIMELINE, sdf-only kernel): clock64 stamps of CTA 0's second tile per (op, warp):
+                // [0] starts waiting for the accumulator, [1] accumulator complete, [2] last item published
+                long long* tlw = (!FULL && P.scratch && lane == 0 && blockIdx.x == 0 && tile == (long long)gridDim.x)
+                                     ? reinterpret_cast<long long*>(P.scratch) + (op * 20 + (warp - 2)) * 4 : nullptr;
+                if (tlw) tlw[0] = clock64();
                 mbar_wait(&d_full[b], (dphase >> b) & 1u);
                 dphase ^= (1u << b);
                 tc_fence_after();
+                if (tlw) tlw[1] = clock64();
                 if (op == T.nops - 1 && next_tile < ntiles) {
                     // the A operand is free (this tile's last MMAs are done): start the NEXT tile's first layer now, so its
                     // tensor work overlaps this tile's last epilogue
@@ -334,6 +340,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                     }
                     publish_chunk(&a_ready[c], lane);
                 }
+                if (tlw) tlw[2] = clock64();
                 if (FULL && kind == EK_FEAT && sub < 2 && op < T.nops - 1) {
                     // k chunk 8 (columns 256..287) = positional encoding of the view direction, zero padded
                     float hv[16];

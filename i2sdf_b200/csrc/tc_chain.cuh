@@ -125,39 +125,71 @@ __device__ __forceinline__ void chain_producer(const OpTable& T, long long ntile
     }
 }
 
-// ---- warp 1, lane 0: MMA issuer (waits per 32-column chunk of the A operand, commits per op) ---------------------------
+// ---- warp 1: MMA issuer (waits per 32-column chunk of the A operand, commits per op) ----------------------------------------
+// Executed by ALL 32 lanes of the warp in converged control flow; one elected lane issues.  Under `if (lane == 0)` the
+// compiler cannot prove the descriptors / TMEM addresses warp-uniform and wraps every UTCHMMA / UTCBAR in an
+// ELECT + R2UR.BROADCAST + BRA.U.ANY "waterfall": the single issuing thread then needs ~550 clocks per k step (measured
+// with tools/timeline.py) - more than the three MMAs take to execute (384) - and the MMA chain, not the epilogue, paced every
+// op.  Converged + elect.sync, with the descriptors advanced by one 64-bit add per k step, keeps the issue loop short.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// tl (optional, development probe I2SDF_DEBUG_TIMELINE): clock64 stamps of CTA 0's second tile, tl[(op * 20 + 16) * 4 + {0,1,2}] =
+// first chunk ready / last chunk ready / last commit issued; tl[1024 + ks * 5 + {0..4}] = per-k-step stamps of op 2
 __device__ __forceinline__ void chain_mma(const OpTable& T, long long ntiles, uint32_t tmem_base, uint8_t* A_hi, uint8_t* A_lo, uint8_t* ring,
-                                          uint64_t* full, uint64_t* empty, uint64_t* a_ready, uint64_t* d_full) {
+                                          uint64_t* full, uint64_t* empty, uint64_t* a_ready, uint64_t* d_full, long long* tl = nullptr) {
     const uint32_t a_hi_s = smem_u32(A_hi), a_lo_s = smem_u32(A_lo), ring_s = smem_u32(ring);
+    const uint64_t dA_hi0 = smem_desc(a_hi_s, LBO_A, SBO), dA_lo0 = smem_desc(a_lo_s, LBO_A, SBO);
+    const bool lane0 = (threadIdx.x & 31) == 0;
     uint32_t stage = 0, phase = 0, aphase = 0, g = 0;      // g: global op counter -> TMEM buffer g & 1
+    // (polling the next step's barriers before issuing this step's MMAs, to hide the ~60-90 clocks of a try_wait, was measured:
+    // slower, 488 vs 462 clocks per k step)
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int op = 0; op < T.nops; ++op, ++g) {
             const int n = T.ops[op].n;
             const uint32_t idesc = instr_desc_bf16(TM, n);
             const uint32_t lbo_b = (uint32_t)n * 16u, lo_off = (uint32_t)n * 32u;
+            const uint64_t dB0 = smem_desc(ring_s, lbo_b, SBO);          // stage 0, hi part; stage / lo part = address-field adds
             const uint32_t d_tmem = tmem_base + (g & 1u) * 256u;
             const int nks = T.ops[op].ksteps;
+            const bool rec = tl && lane0 && blockIdx.x == 0 && tile == (long long)gridDim.x;
             for (int ks = 0; ks < nks; ++ks) {
+                const bool rk = rec && op == 2;
+                if (rk) tl[1024 + ks * 5 + 0] = clock64();
                 if ((ks & 1) == 0) {
                     const int c = ks >> 1;
                     mbar_wait(&a_ready[c], (aphase >> c) & 1u);
                     aphase ^= (1u << c);
+                    if (rec && ks == 0) tl[(op * 20 + 16) * 4 + 0] = clock64();
+                    if (rec && ks + 2 >= nks) tl[(op * 20 + 16) * 4 + 1] = clock64();
                 }
+                if (rk) tl[1024 + ks * 5 + 1] = clock64();
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
-                const uint32_t a_off = (uint32_t)ks * 2u * LBO_A;
-                const uint32_t b_s = ring_s + stage * STAGE_MAX;
-                const uint64_t da_hi = smem_desc(a_hi_s + a_off, LBO_A, SBO);
-                const uint64_t da_lo = smem_desc(a_lo_s + a_off, LBO_A, SBO);
-                const uint64_t db_hi = smem_desc(b_s, lbo_b, SBO);
-                const uint64_t db_lo = smem_desc(b_s + lo_off, lbo_b, SBO);
-                mma_bf16_ss(d_tmem, da_hi, db_hi, idesc, ks > 0 ? 1u : 0u);
-                if (T.mma_per_k > 1) mma_bf16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
-                if (T.mma_per_k > 2) mma_bf16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
-                mma_commit(&empty[stage]);
+                if (rk) tl[1024 + ks * 5 + 2] = clock64();
+                const uint64_t da_hi = dA_hi0 + (uint64_t)(((uint32_t)ks * 2u * LBO_A) >> 4);
+                const uint64_t da_lo = dA_lo0 + (uint64_t)(((uint32_t)ks * 2u * LBO_A) >> 4);
+                const uint64_t db_hi = dB0 + (uint64_t)((stage * (uint32_t)STAGE_MAX) >> 4);
+                const uint64_t db_lo = db_hi + (uint64_t)(lo_off >> 4);
+                if (elect_one_sync()) {
+                    mma_bf16_ss(d_tmem, da_hi, db_hi, idesc, ks > 0 ? 1u : 0u);
+                    if (T.mma_per_k > 1) mma_bf16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
+                    if (T.mma_per_k > 2) mma_bf16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
+                    mma_commit(&empty[stage]);
+                }
+                __syncwarp();
+                if (rk) tl[1024 + ks * 5 + 4] = clock64();
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
-            mma_commit(&d_full[g & 1u]);
+            if (elect_one_sync()) mma_commit(&d_full[g & 1u]);
+            __syncwarp();
+            if (rec) tl[(op * 20 + 16) * 4 + 2] = clock64();
         }
     }
 }
