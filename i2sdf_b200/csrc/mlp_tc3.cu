@@ -389,6 +389,154 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+// ---- sdf-only chain with 8-column work items (the sampler's kernel) ---------------------------------------------------------
+// Same chain as tc_mlp_kernel<false>, but an epilogue work item is 32 rows x 8 columns: in every iteration all 16 epilogue warps
+// work on ONE 32-column chunk (4 lane quarters x 4 column groups), so the first chunk of the next A operand - and with it the MMA
+// chain of the next layer, which paces the op (tools/timeline.py) - is ready after 1/8 instead of 1/4 of the epilogue.
+__global__ void __launch_bounds__(NTHREADS, 1) tc_sdf8_kernel(const MlpParams P, const OpTable T) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* A_hi = smem;
+    uint8_t* A_lo = smem + A_PART_BYTES;
+    uint8_t* ring = smem + 2 * A_PART_BYTES;
+    float* part = reinterpret_cast<float*>(ring + NSTAGE * STAGE_MAX);      // [4][7][TM]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(part + PART_FLOATS);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + NSTAGE;
+    uint64_t* a_ready = bars + 2 * NSTAGE;       // [N_READY], 16 arrivals each (every epilogue warp contributes to every chunk)
+    uint64_t* d_full = a_ready + N_READY;        // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 2);
+
+    if (!round_active(P)) return;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const NetDev& net = P.net;
+    const int NL = net.L - 1;
+    const long long ntiles = (P.M + TM - 1) / TM;
+
+    if (tid == 0) {
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < N_READY; ++i) mbar_init(&a_ready[i], N_EPI_WARPS);
+        mbar_init(&d_full[0], 1);
+        mbar_init(&d_full[1], 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) chain_producer(T, ntiles, ring, full, empty);
+    } else if (warp == 1) {
+        chain_mma(T, ntiles, tmem_base, A_hi, A_lo, ring, full, empty, a_ready, d_full);
+    } else {
+        const int q = warp & 3;
+        const int sub = (warp - 2) >> 2;                     // column group: columns 8 sub .. 8 sub + 7 of every 32-column chunk
+        const int row = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const int nsplit = 256 - net.ex;
+        const float RS2 = 0.70710678118654752f;
+        uint32_t dphase = 0, g = 0;
+        auto load_point = [&](long long tile, float (&x)[3]) {
+            const long long m = tile * TM + row;
+            x[0] = x[1] = x[2] = 0.f;
+            if (m < P.M) {
+                if (P.pts && m >= P.m_rays) { const float* pp = P.pts + (m - P.m_rays) * 3; x[0] = pp[0]; x[1] = pp[1]; x[2] = pp[2]; }
+                else {
+                    const long long r = m / P.ns;
+                    const int j = (int)(m - r * P.ns);
+                    const float t = P.zarr[r * P.zstride + j];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(P.ray_o[r * 3 + c], __fmul_rn(t, P.ray_d[r * 3 + c]));
+                }
+            }
+        };
+        // A_0 = embedding, 48 columns = k chunks 0..5: group sub writes chunk sub, groups 0 and 1 also chunks 4 and 5
+        auto prologue = [&](const float (&x)[3]) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int kc = sub + 4 * h;
+                if (kc < 6) {
+                    float hv[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { const int i = kc * 8 + j; hv[j] = (i < net.ex) ? embed_col(x, i, net.mx) : 0.f; }
+                    store_a8(A_hi, A_lo, row, kc, hv, nullptr, true, true);
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&a_ready[0]); mbar_arrive(&a_ready[1]); }
+        };
+        float x[3];
+        if ((long long)blockIdx.x < ntiles) { load_point(blockIdx.x, x); prologue(x); }
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const long long m = tile * TM + row;
+            const long long next_tile = tile + gridDim.x;
+            float xn[3] = {0.f, 0.f, 0.f};
+            float head = 0.f;
+            for (int op = 0; op < T.nops; ++op, ++g) {
+                const uint32_t b = g & 1u;
+                const int l = T.ops[op].layer;
+                const bool last = (T.ops[op].kind == EK_SDF_LAST);
+                mbar_wait(&d_full[b], (dphase >> b) & 1u);
+                dphase ^= (1u << b);
+                tc_fence_after();
+                if (op == T.nops - 1 && next_tile < ntiles) {      // the A operand is free: start the next tile's first layer now
+                    load_point(next_tile, xn);
+                    prologue(xn);
+                }
+                const float* __restrict__ bias = net.sdf_b[l] + sub * 8;
+                const bool feeds_skip = (l + 1 == net.skip);
+#pragma unroll 2
+                for (int it = 0; it < 8; ++it) {
+                    const int col0 = it * 32 + sub * 8;
+                    const float4 b0 = *reinterpret_cast<const float4*>(bias + it * 32), b1 = *reinterpret_cast<const float4*>(bias + it * 32 + 4);
+                    uint32_t v[8];
+                    tmem_ld8(tmem_base + lane_base + b * 256u + (uint32_t)col0, v);
+                    tmem_ld_wait();
+                    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                    float hv[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float a = __uint_as_float(v[j]) + bv[j];
+                        const float e = ex2_approx(-fabsf(a) * 144.26950408889634f);          // exp(-|100 a|)
+                        hv[j] = fmaf(lg2_approx(1.0f + e), 0.0069314718055994531f, fmaxf(a, 0.0f));
+                    }
+                    if (last) {
+                        const float4 w0 = __ldg(reinterpret_cast<const float4*>(net.sdf_head + col0)), w1 = __ldg(reinterpret_cast<const float4*>(net.sdf_head + col0 + 4));
+                        head = fmaf(hv[0], w0.x, fmaf(hv[1], w0.y, fmaf(hv[2], w0.z, fmaf(hv[3], w0.w, head))));
+                        head = fmaf(hv[4], w1.x, fmaf(hv[5], w1.y, fmaf(hv[6], w1.z, fmaf(hv[7], w1.w, head))));
+                        continue;
+                    }
+                    if (feeds_skip) {                          // cat([h, embed]) / sqrt(2)   (mlp.py:94-95)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int f = col0 + j;
+                            hv[j] = ((f >= nsplit) ? embed_col(x, f - nsplit, net.mx) : hv[j]) * RS2;
+                        }
+                    }
+                    store_a8(A_hi, A_lo, row, col0 >> 3, hv, nullptr, true, true);
+                    publish_chunk(&a_ready[it], lane);
+                }
+            }
+            // ---- combine the 4 column-group partials of every row
+            part[(size_t)sub * 7 * TM + row] = head;
+            epi_bar_sync();
+            if (sub == 0 && m < P.M)
+                P.out_sdf[m] = (part[row] + part[7 * TM + row]) + (part[14 * TM + row] + part[21 * TM + row]) + __ldg(net.sdf_head + 256);
+            epi_bar_sync();
+#pragma unroll
+            for (int c = 0; c < 3; ++c) x[c] = xn[c];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
 // ---- weight packing -------------------------------------------------------------------------------------
 // dst block per k step: [part hi|lo][chunk 0|1][n rows][8 bf16].  Element (n, k):
 //   mode 0 (forward):  W[(n + row_off) * in + col(k)]   col(k) = k, or for the radiance input layer
@@ -518,6 +666,7 @@ int tc_create(i2sdf_handle* h) {
         s->full.no_stream = s->sdf.no_stream = s->sg.no_stream = s->sf.no_stream = s->bwd_full.no_stream = s->bwd_sdf.no_stream = nost;
     }
     cudaError_t e = cudaFuncSetAttribute(tc_mlp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_sdf8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_mlp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_mlp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) { cudaFree(s->wpack); delete s; set_error("tc_create: smem attribute: %s", cudaGetErrorString(e)); return I2SDF_E_CUDA; }
@@ -587,7 +736,10 @@ int tc_launch_sdf(const i2sdf_handle* h, const MlpParams& p, cudaStream_t st) {
     using namespace tc3;
     if (p.M <= 0) return I2SDF_OK;
     const State* s = (const State*)h->tc;
-    tc_mlp_kernel<false, false><<<tc_grid(h, p.M), NTHREADS, kSmemBytes, st>>>(p, s->sdf);
+    static int wide = -1;                                  // I2SDF_SDF16=1: the 16-column-item variant (A/B runs, timeline probe)
+    if (wide < 0) { const char* e = getenv("I2SDF_SDF16"); wide = (e && e[0] == '1') || getenv("I2SDF_DEBUG_TIMELINE") ? 1 : 0; }
+    if (wide) tc_mlp_kernel<false, false><<<tc_grid(h, p.M), NTHREADS, kSmemBytes, st>>>(p, s->sdf);
+    else tc_sdf8_kernel<<<tc_grid(h, p.M), NTHREADS, kSmemBytes, st>>>(p, s->sdf);
     I2SDF_CUDA_CHECK(cudaGetLastError());
     return I2SDF_OK;
 }

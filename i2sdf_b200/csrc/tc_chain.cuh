@@ -65,6 +65,28 @@ __device__ __forceinline__ void store_a16(uint8_t* A_hi, uint8_t* A_lo, int row,
         }
     }
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+// one chunk (8 columns) of a row of the next A operand and / or of a slot
+__device__ __forceinline__ void store_a8(uint8_t* A_hi, uint8_t* A_lo, int row, int kc, const float (&hv)[8], uint8_t* g, bool keep, bool to_smem) {
+    uint32_t h[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_bf16x2(hv[2 * i], hv[2 * i + 1], h[i], lo[i]);
+    if (to_smem) {
+        const uint32_t off = seg_off<TM>(row, kc);
+        *reinterpret_cast<uint4*>(A_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(A_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    if (g) {
+        *reinterpret_cast<uint4*>(g) = keep ? make_uint4(h[0], h[1], h[2], h[3]) : make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(g + planes::BIG_PLANE) = keep ? make_uint4(lo[0], lo[1], lo[2], lo[3]) : make_uint4(0, 0, 0, 0);
+    }
+}
+
 // 16 columns of a 256-column slot back as fp32: seg = HI segment of the first chunk
 __device__ __forceinline__ void load_slot16(const uint8_t* seg, uint4 (&raw)[4]) {
     raw[0] = *reinterpret_cast<const uint4*>(seg);
