@@ -374,7 +374,7 @@ def gpu_arm(args, rank, world, local_rank):
     peak = pk["bf16_tflops_sustained"] if core.uses_tensor_cores else 72.0
     launches = sum(v["launches"] for v in prof.values())
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_tc_sdf_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01c_tc_sdf_traffic.json")
     if core.uses_tensor_cores and os.path.exists(tpath) and R == 1024 and not light:
         traffic = json.load(open(tpath))["dram_bytes_per_launch"]      # from the committed ncu --set full capture
     h2d = sum(v.numel() * v.element_size() for v in list(inp_host.values()) + list(gt_host.values()))
@@ -414,9 +414,9 @@ def gpu_arm(args, rank, world, local_rank):
         "gpu_launches": launches,
         "kernel_ms_per_step": {k: v["ms"] / K for k, v in prof.items()},
         "kernel_launches_per_step": {k: v["launches"] / K for k, v in prof.items()},
-        "roofline": {"bound": "tensor", "kernel": "sdf_tc_kernel (sampler SDF evaluations)" if core.uses_tensor_cores else "mlp_tile_kernel",
+        "roofline": {"bound": "tensor", "kernel": "tc_sdf8_kernel (sampler SDF evaluations)" if core.uses_tensor_cores else "mlp_tile_kernel",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                     "traffic": traffic, "traffic_unit": "bytes of DRAM traffic per launch (ncu --set full, profiles/r01_tc_sdf_traffic.json)",
+                     "traffic": traffic, "traffic_unit": "bytes of DRAM traffic per launch (ncu --set full, profiles/r01c_tc_sdf_traffic.json)",
                      "flop_per_launch": pts_per_launch * flops["sdf_eval"], "ms_per_launch": per_launch_ms,
                      "peak_source": pk["source"] + (", sustained bf16 (kernel timed inside a step)" if core.uses_tensor_cores else "; fp32 FMA peak 148 SM x 128 FMA x 2 x 1.9 GHz"),
                      "note": "achieved counts ALGORITHMIC flops (1 MAC = 2 flop); the kernel issues 3 bf16 MMAs per MAC, so 1/3 of the bf16 peak is this precision scheme's ceiling"},
