@@ -277,8 +277,13 @@ def gpu_arm(args, rank, world, local_rank):
     out_host = {}
     if train:
         loss_fn = I2SDFLoss(**loss_weights(args.config)[0])
-        # Adam(lr, eps=1e-15) as model/trainer/recon.py:201-207; fused=True is the same update as one multi-tensor kernel
-        opt = torch.optim.Adam(model_gpu.parameters(), lr=5.0e-4, eps=1e-15, fused=True)
+        # Adam(lr, eps=1e-15) as model/trainer/recon.py:201-207; i2sdf_b200.optim.Adam is the same update rule and state layout as
+        # torch.optim.Adam in ONE launch for all 44 parameter tensors (I2SDF_TORCH_ADAM=1: torch's fused Adam, 4 launches)
+        if os.environ.get("I2SDF_TORCH_ADAM") == "1":
+            opt = torch.optim.Adam(model_gpu.parameters(), lr=5.0e-4, eps=1e-15, fused=True)
+        else:
+            from i2sdf_b200.optim import Adam
+            opt = Adam(model_gpu.parameters(), lr=5.0e-4, eps=1e-15)
         loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
 
     def train_step(inp, gt):
@@ -384,7 +389,7 @@ def gpu_arm(args, rank, world, local_rank):
                     "(rgb L1 + eikonal + depth + normal/angular; steps < 50k: no bubble/smooth terms): forward "
                     "(error-bounded sampler 5x128 sdf-evals/ray, main pass on 97 samples/ray with saved activations, 3R eikonal "
                     "points) + I2SDFLoss + backward incl. second-order terms (fused tensor-core chain + one weight-gradient launch) "
-                    "+ Adam(eps=1e-15) step + weight re-pack"
+                    "+ Adam(eps=1e-15) step (one launch) + weight re-pack"
                     + (" + one flat NCCL gradient all-reduce" if world > 1 else ""))
     else:
         workload = ("C2/C3 batch shape: 1024-ray forward render, config/synthetic.yml networks (8x256 SDF + 4x256 radiance), "

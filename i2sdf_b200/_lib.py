@@ -38,6 +38,19 @@ class WnormBatch(C.Structure):
     _fields_ = [("n", C.c_int32), ("pad_", C.c_int32), ("jobs", WnormJob * WNORM_MAX_JOBS)]
 
 
+ADAM_MAX_JOBS = 64
+
+
+class AdamJob(C.Structure):
+    """i2sdf_adam_job (include/i2sdf_b200.h)."""
+    _fields_ = [(n, C.c_void_p) for n in ("param", "grad", "exp_avg", "exp_avg_sq")] + [("numel", C.c_int64)]
+
+
+class AdamBatch(C.Structure):
+    _fields_ = [("n", C.c_int32)] + [(n, C.c_float) for n in ("beta1", "beta2", "eps", "step_size", "bias_correction2_sqrt",
+                                                                "one_minus_beta1", "one_minus_beta2")] + [("jobs", AdamJob * ADAM_MAX_JOBS)]
+
+
 # every symbol include/i2sdf_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -78,6 +91,7 @@ SYMBOLS = {
                                        C.POINTER(_P), C.POINTER(_P), _P, C.c_size_t, _P]),
     "i2sdf_loss_forward": (C.c_int, [C.POINTER(LossArgs), _P]),
     "i2sdf_weight_norm": (C.c_int, [C.POINTER(WnormBatch), C.c_int, _P]),
+    "i2sdf_adam_step": (C.c_int, [C.POINTER(AdamBatch), _P]),
     "i2sdf_planes_slot_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
     "i2sdf_planes_pack": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, _P, _P]),
     "i2sdf_planes_unpack": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, C.c_int, C.c_int, _P]),

@@ -16,6 +16,7 @@ $NVCC $COMMON -fmad=false -Xptxas -v -c "$HERE/sampler.cu" -o "$HERE/build/sampl
 $NVCC $COMMON -Xptxas -v -c "$HERE/backward.cu" -o "$HERE/build/backward.o" 2> "$HERE/build/backward.ptxas.txt"
 $NVCC $COMMON -Xptxas -v -c "$HERE/loss.cu" -o "$HERE/build/loss.o" 2> "$HERE/build/loss.ptxas.txt"
 $NVCC $COMMON -Xptxas -v -c "$HERE/wnorm.cu" -o "$HERE/build/wnorm.o" 2> "$HERE/build/wnorm.ptxas.txt"
+$NVCC $COMMON -Xptxas -v -c "$HERE/adam.cu" -o "$HERE/build/adam.o" 2> "$HERE/build/adam.ptxas.txt"
 $NVCC $COMMON -c "$HERE/c_abi.cu" -o "$HERE/build/c_abi.o"
-$NVCC -shared $ARCH -o "$OUT/libi2sdf_b200.so" "$HERE/build/mlp_simt.o" "$HERE/build/mlp_tc3.o" "$HERE/build/mlp_tc_bwd.o" "$HERE/build/tc_gemm.o" "$HERE/build/wgrad_planes.o" "$HERE/build/sampler.o" "$HERE/build/backward.o" "$HERE/build/loss.o" "$HERE/build/wnorm.o" "$HERE/build/c_abi.o" -lcudart
+$NVCC -shared $ARCH -o "$OUT/libi2sdf_b200.so" "$HERE/build/mlp_simt.o" "$HERE/build/mlp_tc3.o" "$HERE/build/mlp_tc_bwd.o" "$HERE/build/tc_gemm.o" "$HERE/build/wgrad_planes.o" "$HERE/build/sampler.o" "$HERE/build/backward.o" "$HERE/build/loss.o" "$HERE/build/wnorm.o" "$HERE/build/adam.o" "$HERE/build/c_abi.o" -lcudart
 echo "built $OUT/libi2sdf_b200.so"

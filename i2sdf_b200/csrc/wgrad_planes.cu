@@ -333,6 +333,7 @@ int wgrad_planes_launch(const i2sdf_handle* h, const WgArgs& args, cudaStream_t 
 
 int planes_colsum_launch(const i2sdf_handle* h, const CsArgs& args, cudaStream_t st) {
     if (args.njobs <= 0 || args.ntiles <= 0) return I2SDF_OK;
+    // (2 CTAs per SM are resident at this register count; a 4x larger grid was measured slower: 150 vs 111 us)
     int gx = (2 * h->num_sms + args.njobs - 1) / args.njobs;
     if ((long long)gx > args.ntiles) gx = (int)args.ntiles;
     wgp::planes_colsum_kernel<<<dim3(gx, args.njobs), 256, 0, st>>>(args);

@@ -1,0 +1,69 @@
+"""Adam for the reconstruction trainer as ONE kernel launch per step.
+
+    opt = i2sdf_b200.optim.Adam(model.get_param_groups(lr), eps=1e-15)        # instead of torch.optim.Adam(...)
+    sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma)                # unchanged (reads / writes param_groups[i]['lr'])
+
+Reference: model/trainer/recon.py:201-207 builds torch.optim.Adam(self.model.get_param_groups(lr), eps=1e-15) +
+ExponentialLR.  Same update rule, same state layout (`step`, `exp_avg`, `exp_avg_sq`: state dicts interchange with
+torch.optim.Adam), no weight decay / amsgrad / maximize (the reference uses none).  CUDA fp32 parameters only: like the rest of
+the package there is no CPU path.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+
+
+class Adam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=False, maximize=False):
+        if weight_decay != 0.0 or amsgrad or maximize:
+            raise _lib.I2SDFError("i2sdf_b200.optim.Adam: weight_decay / amsgrad / maximize are not supported (the reference uses none)")
+        if lr < 0.0 or eps < 0.0 or not (0.0 <= betas[0] < 1.0) or not (0.0 <= betas[1] < 1.0):
+            raise ValueError("invalid Adam hyper-parameters")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=0.0, amsgrad=False, maximize=False))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = _lib.load()
+        for group in self.param_groups:
+            ps = [p for p in group["params"] if p.grad is not None]
+            if not ps:
+                continue
+            beta1, beta2 = group["betas"]
+            steps = set()
+            for p in ps:
+                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous() or p.grad.is_sparse:
+                    raise _lib.I2SDFError("i2sdf_b200.optim.Adam needs contiguous fp32 CUDA parameters with dense gradients")
+                st = self.state[p]
+                if len(st) == 0:
+                    st["step"] = torch.tensor(0.0, dtype=torch.float32)          # host scalar, as torch.optim.Adam keeps it
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["step"] += 1
+                steps.add(float(st["step"]))
+            if len(steps) != 1:
+                raise _lib.I2SDFError("i2sdf_b200.optim.Adam: the parameters of one group must share their step count")
+            t = steps.pop()
+            dev = ps[0].device
+            grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in ps]
+            with torch.cuda.device(dev):
+                stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+                for lo in range(0, len(ps), _lib.ADAM_MAX_JOBS):
+                    b = _lib.AdamBatch()
+                    chunk = ps[lo:lo + _lib.ADAM_MAX_JOBS]
+                    b.n, b.beta1, b.beta2, b.eps = len(chunk), beta1, beta2, group["eps"]
+                    b.one_minus_beta1, b.one_minus_beta2 = 1.0 - beta1, 1.0 - beta2
+                    b.step_size = group["lr"] / (1.0 - beta1 ** t)
+                    b.bias_correction2_sqrt = math.sqrt(1.0 - beta2 ** t)
+                    for i, p in enumerate(chunk):
+                        st, j = self.state[p], b.jobs[i]
+                        j.param, j.grad, j.numel = p.data_ptr(), grads[lo + i].data_ptr(), p.numel()
+                        j.exp_avg, j.exp_avg_sq = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
+                    _lib.check(lib.i2sdf_adam_step(C.byref(b), stream), "i2sdf_adam_step")
+        return loss

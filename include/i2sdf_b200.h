@@ -341,6 +341,26 @@ typedef struct i2sdf_wnorm_batch {
 } i2sdf_wnorm_batch;
 int i2sdf_weight_norm(const i2sdf_wnorm_batch* batch, int backward, void* stream);
 
+/* ---- optimizer --------------------------------------------------------------------------
+ * Replaces: torch.optim.Adam(...).step() of the reconstruction trainer (model/trainer/recon.py:201-207) for every
+ * parameter tensor in one launch.  The host passes the step's scalars: step_size = lr / (1 - beta1^t),
+ * bias_correction2_sqrt = sqrt(1 - beta2^t).  No weight decay / amsgrad (the reference uses neither). */
+#define I2SDF_ADAM_MAX_JOBS 64
+typedef struct i2sdf_adam_job {
+    float* param;           /* [numel] updated in place */
+    const float* grad;      /* [numel] */
+    float* exp_avg;         /* [numel] */
+    float* exp_avg_sq;      /* [numel] */
+    int64_t numel;
+} i2sdf_adam_job;
+typedef struct i2sdf_adam_batch {
+    int32_t n;
+    float beta1, beta2, eps, step_size, bias_correction2_sqrt;
+    float one_minus_beta1, one_minus_beta2;   /* 1 - beta formed in double by the host (1 - 0.999f != (float)0.001) */
+    i2sdf_adam_job jobs[I2SDF_ADAM_MAX_JOBS];
+} i2sdf_adam_batch;
+int i2sdf_adam_step(const i2sdf_adam_batch* batch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
