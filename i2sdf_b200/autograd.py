@@ -194,7 +194,7 @@ def forward_train(model, core, input, predict_only=False):
     # of the packed device copies every kernel of this step reads (two launches)
     Ws, bs = model.effective_weights()
     core.pack(Ws, bs)
-    model._packed_key = model._param_key()
+    model._packed_key = None        # an eval-mode forward after this one re-checks (and re-packs: the optimizer will have stepped)
     o, d, dnorm = core.rays(input["uv"], input["pose"], input["intrinsics"])
     R, dev = o.shape[0], o.device
     beta = model.density.beta

@@ -229,7 +229,13 @@ class RenderCore:
                 torch.set_rng_state(state)
                 cands.append(ep(self.desc.n_samples_eval * (k + 1)).to(torch.int32))
             torch.set_rng_state(state)
-            table = torch.stack(cands).contiguous().to(self.device)
+            # staged through a persistent PINNED buffer: a pageable host->device copy is synchronous - the host would block
+            # here until the device has run everything queued so far (the sampler rounds), which is the very wait this path removes
+            if getattr(self, "_cand_host", None) is None:
+                self._cand_host = torch.zeros(self.desc.max_total_iters, self.desc.n_samples_extra, dtype=torch.int32).pin_memory()
+            torch.stack(cands, out=self._cand_host)
+            table = torch.empty(self._cand_host.shape, dtype=torch.int32, device=self.device)
+            table.copy_(self._cand_host, non_blocking=True)
             eik = tape["eik_idx"].to(device=self.device, dtype=torch.int32).contiguous() if "eik_idx" in tape else None
             if callable(tape.get("eik_idx_fn")):
                 eik = tape["eik_idx_fn"]().to(device=self.device, dtype=torch.int32).contiguous()

@@ -23,6 +23,7 @@ class Adam(torch.optim.Optimizer):
         if lr < 0.0 or eps < 0.0 or not (0.0 <= betas[0] < 1.0) or not (0.0 <= betas[1] < 1.0):
             raise ValueError("invalid Adam hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=0.0, amsgrad=False, maximize=False))
+        self._fresh_steps = {}
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -31,22 +32,32 @@ class Adam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         lib = _lib.load()
+        if not hasattr(self, "_fresh_steps"):
+            self._fresh_steps = {}
         for group in self.param_groups:
             ps = [p for p in group["params"] if p.grad is not None]
             if not ps:
                 continue
             beta1, beta2 = group["betas"]
-            steps = set()
+            # the step counters are host tensors (torch.optim.Adam's state layout); parameters created together share ONE
+            # tensor object so that a step costs one host increment, not one per parameter
+            steps, seen = set(), set()
             for p in ps:
                 if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous() or p.grad.is_sparse:
                     raise _lib.I2SDFError("i2sdf_b200.optim.Adam needs contiguous fp32 CUDA parameters with dense gradients")
                 st = self.state[p]
                 if len(st) == 0:
-                    st["step"] = torch.tensor(0.0, dtype=torch.float32)          # host scalar, as torch.optim.Adam keeps it
+                    shared = self._fresh_steps.get(id(group))
+                    if shared is None or float(shared) != 0.0:          # (a counter that already advanced is not handed to new parameters)
+                        shared = self._fresh_steps[id(group)] = torch.tensor(0.0, dtype=torch.float32)
+                    st["step"] = shared
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                st["step"] += 1
-                steps.add(float(st["step"]))
+                sp = st["step"]
+                if id(sp) not in seen:
+                    seen.add(id(sp))
+                    sp += 1
+                    steps.add(float(sp))
             if len(steps) != 1:
                 raise _lib.I2SDFError("i2sdf_b200.optim.Adam: the parameters of one group must share their step count")
             t = steps.pop()

@@ -15,7 +15,8 @@ R = 1024
 inp = {k: v.cuda() for k, v in orc.synthetic_rays(R, seed=1, train_layout=True).items()}
 gt = {k: v.cuda() for k, v in bench.make_train_gt(R, 7).items()}
 loss_fn = I2SDFLoss(**configs.LOSS_SYNTHETIC)
-opt = torch.optim.Adam(m.parameters(), lr=5e-4, eps=1e-15, fused=True)
+from i2sdf_b200.optim import Adam
+opt = Adam(m.parameters(), lr=5e-4, eps=1e-15)
 def step():
     out = m(inp)
     loss = loss_fn(out, gt, 0)["loss"]
