@@ -153,15 +153,6 @@ __device__ __forceinline__ void chain_producer(const OpTable& T, long long ntile
 // ELECT + R2UR.BROADCAST + BRA.U.ANY "waterfall": the single issuing thread then needs ~550 clocks per k step (measured
 // with tools/timeline.py) - more than the three MMAs take to execute (384) - and the MMA chain, not the epilogue, paced every
 // op.  Converged + elect.sync, with the descriptors advanced by one 64-bit add per k step, keeps the issue loop short.
-__device__ __forceinline__ bool elect_one_sync() {
-    uint32_t pred = 0;
-    asm volatile(
-        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
-        "elect.sync rx|px, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, px;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
 // tl (optional, development probe I2SDF_DEBUG_TIMELINE): clock64 stamps of CTA 0's second tile, tl[(op * 20 + 16) * 4 + {0,1,2}] =
 // first chunk ready / last chunk ready / last commit issued; tl[1024 + ks * 5 + {0..4}] = per-k-step stamps of op 2
 __device__ __forceinline__ void chain_mma(const OpTable& T, long long ntiles, uint32_t tmem_base, uint8_t* A_hi, uint8_t* A_lo, uint8_t* ring,

@@ -119,10 +119,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_pw_kernel(const PWArgs G) {
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        // all 32 lanes in converged control flow, one elected lane issues (see chain_mma in tc_chain.cuh for why)
+        {
             const uint32_t a_hi_s = smem_u32(A_hi), a_lo_s = smem_u32(A_lo), ring_s = smem_u32(ring);
             const uint32_t idesc = instr_desc_bf16(TM, G.n);
             const uint32_t lbo_b = (uint32_t)G.n * 16u, lo_off = (uint32_t)G.n * 32u;
+            const uint64_t dA_hi0 = smem_desc(a_hi_s, LBO_A, SBO), dA_lo0 = smem_desc(a_lo_s, LBO_A, SBO), dB0 = smem_desc(ring_s, lbo_b, SBO);
             uint32_t stage = 0, phase = 0, aphase = 0, t = 0;
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++t) {
                 const uint32_t d_tmem = tmem_base + (t & 1u) * 256u;
@@ -138,19 +140,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_pw_kernel(const PWArgs G) {
                     }
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_off = (uint32_t)ks * 2u * LBO_A;
-                    const uint32_t b_s = ring_s + stage * STAGE_MAX;
-                    const uint64_t da_hi = smem_desc(a_hi_s + a_off, LBO_A, SBO);
-                    const uint64_t da_lo = smem_desc(a_lo_s + a_off, LBO_A, SBO);
-                    const uint64_t db_hi = smem_desc(b_s, lbo_b, SBO);
-                    const uint64_t db_lo = smem_desc(b_s + lo_off, lbo_b, SBO);
-                    mma_bf16_ss(d_tmem, da_hi, db_hi, idesc, ks > 0 ? 1u : 0u);
-                    mma_bf16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
-                    mma_bf16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
-                    mma_commit(&empty[stage]);
+                    const uint64_t da_hi = dA_hi0 + (uint64_t)(((uint32_t)ks * 2u * LBO_A) >> 4);
+                    const uint64_t da_lo = dA_lo0 + (uint64_t)(((uint32_t)ks * 2u * LBO_A) >> 4);
+                    const uint64_t db_hi = dB0 + (uint64_t)((stage * (uint32_t)STAGE_MAX) >> 4);
+                    const uint64_t db_lo = db_hi + (uint64_t)(lo_off >> 4);
+                    if (elect_one_sync()) {
+                        mma_bf16_ss(d_tmem, da_hi, db_hi, idesc, ks > 0 ? 1u : 0u);
+                        mma_bf16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
+                        mma_bf16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
+                        mma_commit(&empty[stage]);
+                    }
+                    __syncwarp();
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
-                mma_commit(&d_full[t & 1u]);
+                if (elect_one_sync()) mma_commit(&d_full[t & 1u]);
+                __syncwarp();
             }
         }
     } else {
@@ -315,7 +319,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_wgrad_kernel(const WGArgs G)
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 1) {
-        if (lane == 0) {
+        // all 32 lanes converged, one elected lane issues (see chain_mma in tc_chain.cuh)
+        {
             const uint32_t ring_s = smem_u32(ring);
             const uint32_t idesc = instr_desc_bf16(TM, n2pad);
             const uint32_t lbo = 256u * 16u;
@@ -326,18 +331,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_wgrad_kernel(const WGArgs G)
                 const uint32_t base = ring_s + stage * WG_STAGE_BYTES;
                 const uint64_t db_hi = smem_desc(base + 16384, lbo, SBO);
                 const uint64_t db_lo = smem_desc(base + 24576, lbo, SBO);
-                for (int mt = 0; mt < mt_count; ++mt) {
-                    const uint32_t d_tmem = tmem_base + (uint32_t)mt * 256u;
-                    const uint64_t da_hi = smem_desc(base + (uint32_t)mt * 2048u, lbo, SBO);
-                    const uint64_t da_lo = smem_desc(base + 8192 + (uint32_t)mt * 2048u, lbo, SBO);
-                    mma_bf16_ss(d_tmem, da_hi, db_hi, idesc, st > 0 ? 1u : 0u);
-                    mma_bf16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
-                    mma_bf16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
+                if (elect_one_sync()) {
+                    for (int mt = 0; mt < mt_count; ++mt) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)mt * 256u;
+                        const uint64_t da_hi = smem_desc(base + (uint32_t)mt * 2048u, lbo, SBO);
+                        const uint64_t da_lo = smem_desc(base + 8192 + (uint32_t)mt * 2048u, lbo, SBO);
+                        mma_bf16_ss(d_tmem, da_hi, db_hi, idesc, st > 0 ? 1u : 0u);
+                        mma_bf16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
+                        mma_bf16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
+                    }
+                    mma_commit(&empty[stage]);
                 }
-                mma_commit(&empty[stage]);
+                __syncwarp();
                 if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
             }
-            mma_commit(d_full);
+            if (elect_one_sync()) mma_commit(d_full);
+            __syncwarp();
         }
     } else if (warp >= 2) {
         // ---- loaders: thread e = (kc, r): feature row r (0..255), k chunk kc (8 points) of the A (P) and B (X) operands
