@@ -101,3 +101,50 @@ def test_any_optimizer_step_invalidates_the_packed_weights_key():
     before = network._OPT_EPOCH[0]
     opt.step()
     assert network._OPT_EPOCH[0] == before + 1
+
+
+def test_loss_restatement_matches_the_oracle_loss_on_cpu():
+    """I2SDFLoss._forward_torch (the CPU-tensor path; the CUDA kernel is checked against it on the GPU) vs the oracle's
+    recon_loss, which the training fixtures pin on the reference's loss values (model/network/__init__.py:338-406)."""
+    import torch
+    from i2sdf_b200.network import I2SDFLoss
+    from oracle import i2sdf_oracle as orc
+    g = torch.Generator().manual_seed(0)
+    R = 50
+    out = {"rgb_values": torch.rand(R, 3, generator=g), "depth_values": torch.rand(R, generator=g) * 3, "weight_sum": torch.rand(R, 1, generator=g),
+           "normal_values": torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=1), "grad_theta": torch.randn(2 * R, 3, generator=g),
+           "diff_norm": torch.rand(R, generator=g), "surface_sdf": torch.randn(9, 1, generator=g), "light_mask": torch.rand(R, 1, generator=g)}
+    gt = {"rgb": torch.rand(R, 3, generator=g), "depth": torch.rand(R, generator=g) * 3, "depth_mask": torch.rand(R, generator=g) > 0.3,
+          "normal": torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=1), "normal_mask": torch.rand(R, generator=g) > 0.4,
+          "mask": (torch.rand(R, 1, generator=g) > 0.5).float(), "light_mask": (torch.rand(R, 1, generator=g) > 0.7).float()}
+    kw = dict(eikonal_weight=0.1, smooth_weight=0.01, depth_weight=0.1, normal_weight=0.05, bubble_weight=0.5, light_mask_weight=0.5,
+              mask_weight=0.2)
+    mine = I2SDFLoss(smooth_iter=10, **kw)(out, gt, 100)
+    ref = orc.recon_loss(out, gt, angular_weight=0.05, smooth_active=True, **kw)
+    assert abs(float(mine["loss"]) - float(ref)) < 1e-6 * abs(float(ref))
+    assert set(mine) == {"loss", "rgb_loss", "eikonal_loss", "smooth_loss", "mask_loss", "depth_loss", "normal_loss", "angular_loss",
+                         "bubble_loss", "light_mask_loss"}
+    assert float(mine["angular_loss"]) == float(mine["normal_loss"])         # the reference's "angular" term IS the L1 normal loss (:368-371)
+    early = I2SDFLoss(smooth_iter=1000, **kw)(out, gt, 100)
+    assert float(early["smooth_loss"]) == 0.0                                # smoothness term only after smooth_iter (:347-351)
+
+
+def test_opt_in_helpers_fail_loudly_off_the_gpu():
+    """No CPU paths: the one-launch Adam rejects CPU parameters and unsupported options; the global-convergence switch needs
+    an initialised process group."""
+    import pytest
+    import torch
+    from i2sdf_b200 import _lib
+    from i2sdf_b200.optim import Adam
+    from i2sdf_b200.parallel import use_global_convergence
+    lin = torch.nn.Linear(3, 2)
+    opt = Adam(lin.parameters(), lr=1e-3, eps=1e-15)
+    lin(torch.ones(1, 3)).sum().backward()
+    with pytest.raises(_lib.I2SDFError):
+        opt.step()
+    with pytest.raises(_lib.I2SDFError):
+        Adam(lin.parameters(), weight_decay=0.1)
+    with pytest.raises(RuntimeError):
+        use_global_convergence(lin)
+    sd = opt.state_dict()
+    assert set(sd) == {"state", "param_groups"} and sd["param_groups"][0]["eps"] == 1e-15
