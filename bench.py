@@ -222,11 +222,11 @@ def cpu_train_arm(conf, model, rays, steps, warmup, name="synthetic"):
         loss = orc.recon_loss(out, gt, smooth_active=False, **lw)
         loss.backward()
 
-    probe_inp = orc.synthetic_rays(8, seed=2, train_layout=True)
+    probe_inp = orc.synthetic_rays(32, seed=2, train_layout=True)
 
     def probe():
         P = {k: v.clone().requires_grad_(True) for k, v in P0.items()}
-        R = 8
+        R = 32
         tp = {"jitter": torch.rand(R, spec.n_samples_eval), "u_final": torch.rand(R, spec.n_samples),
               "extra_perm": lambda n: torch.randperm(n)[:spec.n_samples_extra], "eik_idx": torch.randint(98, (R,)),
               "eik_uniform": torch.empty(R, 3).uniform_(-3, 3), "nbr_uniform": torch.empty(R, 3).uniform_(-0.005, 0.005)}
@@ -448,7 +448,7 @@ def gpu_arm(args, rank, world, local_rank):
                           "workload": "eval forward render of the same 1024-ray batch (no backward, no collective), device-resident inputs"}
     model_c = type("S", (), {"state_dict": lambda self: cpu_snapshot})()
     if train:
-        cb = cpu_train_arm(conf, model_c, max(args.cpu_rays // 4, 16), steps=1, warmup=1, name=args.config)
+        cb = cpu_train_arm(conf, model_c, args.cpu_rays, steps=2, warmup=1, name=args.config)
     else:
         cb = cpu_arm(conf, model_c, args.cpu_rays, steps=2, warmup=1)
     line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port", "sample": cb["sample"]}
@@ -465,7 +465,7 @@ def main():
             return
         conf, model = build_params(name=args.config)
         if args.mode == "train":
-            cb = cpu_train_arm(conf, model, max(args.cpu_rays // 4, 16), steps=args.steps, warmup=args.warmup, name=args.config)
+            cb = cpu_train_arm(conf, model, args.cpu_rays, steps=args.steps, warmup=args.warmup, name=args.config)
         else:
             cb = cpu_arm(conf, model, args.cpu_rays, steps=args.steps, warmup=args.warmup)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
