@@ -23,7 +23,7 @@ class LossArgs(C.Structure):
         "rgb", "rgb_gt", "grad_theta", "diff_norm", "weight_sum", "mask_gt", "depth", "depth_gt", "depth_mask", "normal",
         "normal_gt", "normal_mask", "surface_sdf", "light", "light_gt")] + [(n, C.c_float) for n in (
         "w_eik", "w_smooth", "w_mask", "w_depth", "w_normal", "w_angular", "w_bubble", "w_light")] + [(n, C.c_void_p) for n in (
-        "terms", "g_rgb", "g_grad_theta", "g_diff_norm", "g_weight_sum", "g_depth", "g_normal", "g_surface_sdf", "g_light")]
+        "terms", "g_rgb", "g_grad_theta", "g_diff_norm", "g_weight_sum", "g_depth", "g_normal", "g_surface_sdf", "g_light", "denom")]
 
 
 WNORM_MAX_JOBS = 28

@@ -304,6 +304,11 @@ class _LossFn(Function):
                 setattr(a, dname, t.data_ptr())
         for k, v in weights.items():
             setattr(a, k, float(v))
+        if aux.get("denom") is not None:            # sharded batch: divisors of the means (I2SDFLoss._shard_denominators)
+            den = prep(aux["denom"])
+            if den.numel() != 5:
+                raise _lib.I2SDFError("I2SDFLoss: denom must hold 5 divisors (rays, eikonal rows, bubble points, depth count, normal count)")
+            a.denom = den.data_ptr()
         # one flat buffer: terms[10] (padded to 16) + the gradient of every differentiable input that needs one
         want = [i for i, k in enumerate(_LOSS_PRED) if P[k] is not None and ctx.needs_input_grad[2 + i]]
         sizes = [(P[_LOSS_PRED[i]].numel() + 3) // 4 * 4 for i in want]
@@ -339,7 +344,7 @@ class _LossFn(Function):
 
 def fused_loss(sel, weights):
     """sel: dict with the _LOSS_PRED / _LOSS_AUX entries (None = term off) -> terms [10] (terms[0] = loss, differentiable)."""
-    aux = {k: sel.get(k) for k in _LOSS_AUX}
+    aux = {k: sel.get(k) for k in _LOSS_AUX + ("denom",)}
     return _LossFn.apply(weights, aux, *[sel.get(k) for k in _LOSS_PRED])
 
 

@@ -75,16 +75,21 @@ __global__ void __launch_bounds__(NT, 1) loss_kernel(const i2sdf_loss_args a) {
         tot[tid] = v;
     }
     __syncthreads();
-    const double n_depth = tot[A_DEPTH_N], n_normal = tot[A_NORMAL_N];
+    // divisors of the means: this call's own counts, or (sharded batches) the caller's share of the global counts
+    const double n_ray = a.denom ? (double)a.denom[I2SDF_LOSS_DENOM_RAYS] : (double)R;
+    const double n_eik = a.denom ? (double)a.denom[I2SDF_LOSS_DENOM_EIK] : (double)a.n_eik;
+    const double n_bub = a.denom ? (double)a.denom[I2SDF_LOSS_DENOM_BUBBLE] : (double)a.n_bubble;
+    const double n_depth = a.denom ? (double)a.denom[I2SDF_LOSS_DENOM_DEPTH] : tot[A_DEPTH_N];
+    const double n_normal = a.denom ? (double)a.denom[I2SDF_LOSS_DENOM_NORMAL] : tot[A_NORMAL_N];
     if (tid == 0) {
-        const float t_rgb = (float)(tot[A_RGB] / (3.0 * (double)R));
-        const float t_eik = a.grad_theta ? (float)(tot[A_EIK] / (double)a.n_eik) : 0.f;
-        const float t_smooth = a.diff_norm ? (float)(tot[A_SMOOTH] / (double)R) : 0.f;
-        const float t_mask = a.weight_sum ? (float)(tot[A_MASK] / (double)R) : 0.f;
+        const float t_rgb = (float)(tot[A_RGB] / (3.0 * n_ray));
+        const float t_eik = a.grad_theta ? (float)(tot[A_EIK] / n_eik) : 0.f;
+        const float t_smooth = a.diff_norm ? (float)(tot[A_SMOOTH] / n_ray) : 0.f;
+        const float t_mask = a.weight_sum ? (float)(tot[A_MASK] / n_ray) : 0.f;
         const float t_depth = a.depth ? (float)(tot[A_DEPTH] / n_depth) : 0.f;
         const float t_normal = a.normal ? (float)(tot[A_NORMAL] / n_normal) : 0.f;
-        const float t_bubble = a.surface_sdf ? (float)(tot[A_BUBBLE] / (double)a.n_bubble) : 0.f;
-        const float t_light = a.light ? (float)(tot[A_LIGHT] / (double)R) : 0.f;
+        const float t_bubble = a.surface_sdf ? (float)(tot[A_BUBBLE] / n_bub) : 0.f;
+        const float t_light = a.light ? (float)(tot[A_LIGHT] / n_ray) : 0.f;
         const float t_n = (a.w_normal > 0.f) ? t_normal : 0.f, t_a = (a.w_angular > 0.f) ? t_normal : 0.f;
         // same association order as the reference's sum (:383-391)
         float loss = t_rgb;
@@ -94,8 +99,8 @@ __global__ void __launch_bounds__(NT, 1) loss_kernel(const i2sdf_loss_args a) {
         a.terms[6] = t_n; a.terms[7] = t_a; a.terms[8] = t_bubble; a.terms[9] = t_light;
     }
     // ---- phase 2: gradients
-    const float k_rgb = (float)(1.0 / (3.0 * (double)R));
-    const float k_ray = (float)(1.0 / (double)R);
+    const float k_rgb = (float)(1.0 / (3.0 * n_ray));
+    const float k_ray = (float)(1.0 / n_ray);
     const float k_depth = (float)((double)a.w_depth * 2.0 / n_depth);
     const float k_normal = (float)((double)(a.w_normal + a.w_angular) / n_normal);
     for (long long r = tid; r < R; r += NT) {
@@ -119,7 +124,7 @@ __global__ void __launch_bounds__(NT, 1) loss_kernel(const i2sdf_loss_args a) {
         if (a.g_light) { float d; bce(a.light[r], a.light_gt[r], &d); a.g_light[r] = a.w_light * d * k_ray; }
     }
     if (a.g_grad_theta) {
-        const float k_eik = (float)(2.0 * (double)a.w_eik / (double)a.n_eik);
+        const float k_eik = (float)(2.0 * (double)a.w_eik / n_eik);
         for (long long i = tid; i < a.n_eik; i += NT) {
             const float x = a.grad_theta[i * 3], y = a.grad_theta[i * 3 + 1], z = a.grad_theta[i * 3 + 2];
             const float nrm = sqrtf(x * x + y * y + z * z);
@@ -128,7 +133,7 @@ __global__ void __launch_bounds__(NT, 1) loss_kernel(const i2sdf_loss_args a) {
         }
     }
     if (a.g_surface_sdf) {
-        const float k_b = (float)((double)a.w_bubble / (double)a.n_bubble);
+        const float k_b = (float)((double)a.w_bubble / n_bub);
         for (long long i = tid; i < a.n_bubble; i += NT) a.g_surface_sdf[i] = sgn(a.surface_sdf[i]) * k_b;
     }
 }

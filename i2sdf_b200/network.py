@@ -375,6 +375,8 @@ class I2SDFLoss(nn.Module):
         self.bubble_weight, self.light_mask_weight = bubble_weight, light_mask_weight
         self.min_bubble_iter, self.max_bubble_iter, self.smooth_iter = min_bubble_iter, max_bubble_iter, smooth_iter
         self.rgb_loss = F.l1_loss
+        # rays sharded over ranks: divide by the GLOBAL counts (parallel.use_global_loss_means); None = this call's own counts
+        self.means_group = None
         if self.bubble_weight > 0 and self.max_bubble_iter is not None and self.smooth_iter < self.max_bubble_iter:
             self.smooth_iter = self.max_bubble_iter
 
@@ -414,6 +416,28 @@ class I2SDFLoss(nn.Module):
             return self._forward_fused(model_outputs, ground_truth, current_step)
         return self._forward_torch(model_outputs, ground_truth, current_step)
 
+    def _shard_denominators(self, n_rays, n_eik, n_bubble, depth_mask, normal_mask, dev):
+        """Divisors of the means when the batch is sharded over the ranks of `means_group` (SURVEY.md §8(e) caveat 2): the
+        reference's means run over the whole batch (model/network/__init__.py:308-329), so every rank divides its sums by
+        (global count) / world — the average over ranks of the returned losses, and of the parameter gradients that
+        `parallel.allreduce_gradients` averages, is then the single-GPU loss / gradient of the whole batch even when the shards
+        are ragged or their mask counts differ.  One 40-byte SUM all-reduce in stream order; no host sync.  Returns float32 [5]
+        in the I2SDF_LOSS_DENOM_* order (rays, eikonal rows, bubble points, depth-mask count, normal-mask count) or None."""
+        import torch.distributed as dist
+        g = self.means_group
+        if g is None or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(g) == 1:
+            return None
+        cnt = torch.zeros(5, dtype=torch.float64, device=dev)
+        cnt[0].fill_(float(n_rays))
+        cnt[1].fill_(float(n_eik))
+        cnt[2].fill_(float(n_bubble))
+        if depth_mask is not None:
+            cnt[3].copy_(depth_mask.to(dev).sum())
+        if normal_mask is not None:
+            cnt[4].copy_(normal_mask.to(dev).sum())
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=g)
+        return (cnt / dist.get_world_size(g)).float()
+
     _TERMS = ("loss", "rgb_loss", "eikonal_loss", "smooth_loss", "mask_loss", "depth_loss", "normal_loss", "angular_loss",
               "bubble_loss", "light_mask_loss")
 
@@ -434,6 +458,11 @@ class I2SDFLoss(nn.Module):
             light=out["light_mask"] if ("light_mask" in out and self.light_mask_weight > 0) else None, light_gt=gt.get("light_mask"))
         w = dict(w_eik=self.eikonal_weight, w_smooth=self.smooth_weight, w_mask=self.mask_weight, w_depth=self.depth_weight,
                  w_normal=self.normal_weight, w_angular=self.angular_weight, w_bubble=self.bubble_weight, w_light=self.light_mask_weight)
+        sel["denom"] = self._shard_denominators(
+            sel["rgb"].shape[0], 0 if sel["grad_theta"] is None else sel["grad_theta"].shape[0],
+            0 if sel["surface_sdf"] is None else sel["surface_sdf"].numel(),
+            sel["depth_mask"] if sel["depth"] is not None else None, sel["normal_mask"] if sel["normal"] is not None else None,
+            sel["rgb"].device)
         terms = fused_loss(sel, w)
         res = {"loss": terms[0]}
         det = terms.detach()
@@ -445,6 +474,15 @@ class I2SDFLoss(nn.Module):
         """Plain PyTorch restatement (CPU tensors: host-side tests of the loss module; the CUDA path is _forward_fused)."""
         dev = model_outputs["rgb_values"].device
         zero = lambda: torch.zeros((), device=dev)                # noqa: E731   (a fill kernel: no host->device copy, no sync)
+        if self.means_group is not None:
+            has_d = "depth" in ground_truth and self.depth_weight > 0
+            has_nn = "normal" in ground_truth and (self.normal_weight > 0 or self.angular_weight > 0)
+            den = self._shard_denominators(
+                model_outputs["rgb_values"].shape[0], model_outputs["grad_theta"].shape[0] if "grad_theta" in model_outputs else 0,
+                model_outputs["surface_sdf"].numel() if ("surface_sdf" in model_outputs and self.bubble_weight > 0) else 0,
+                ground_truth["depth_mask"] if has_d else None, ground_truth["normal_mask"] if has_nn else None, dev)
+            if den is not None:
+                return self._forward_torch_sharded(model_outputs, ground_truth, current_step, den)
         terms = {"rgb_loss": self.get_rgb_loss(model_outputs["rgb_values"], ground_truth["rgb"])}
         terms["eikonal_loss"] = self.get_eikonal_loss(model_outputs["grad_theta"]) if "grad_theta" in model_outputs else zero()
         smooth_on = self.smooth_iter is None or current_step > self.smooth_iter
@@ -467,3 +505,41 @@ class I2SDFLoss(nn.Module):
         out = {"loss": loss}
         out.update(terms)
         return out
+
+    def _forward_torch_sharded(self, out, gt, current_step, den):
+        """_forward_torch with every mean written as (this shard's sum) / den[...] (see _shard_denominators)."""
+        dev = out["rgb_values"].device
+        zero = lambda: torch.zeros((), device=dev)                # noqa: E731
+        n_ray, n_eik, n_bub, n_depth, n_normal = den[0], den[1], den[2], den[3], den[4]
+
+        def msum(x, mask):
+            return torch.where(mask.flatten().bool(), x, torch.zeros((), dtype=x.dtype, device=dev)).sum()
+
+        def bce_sum(p, t):
+            return F.binary_cross_entropy(p.clip(1e-3, 1.0 - 1e-3), t, reduction="sum")
+
+        def normal_l1():
+            return msum(torch.abs(1 - torch.sum(out["normal_values"] * gt["normal"].reshape(-1, 3), dim=-1)), gt["normal_mask"]) / n_normal
+
+        terms = {"rgb_loss": (out["rgb_values"] - gt["rgb"].reshape(-1, 3)).abs().sum() / (3 * n_ray)}
+        terms["eikonal_loss"] = ((out["grad_theta"].norm(2, dim=1) - 1) ** 2).sum() / n_eik if "grad_theta" in out else zero()
+        smooth_on = self.smooth_iter is None or current_step > self.smooth_iter
+        terms["smooth_loss"] = out["diff_norm"].sum() / n_ray if (smooth_on and self.smooth_weight > 0 and "diff_norm" in out) else zero()
+        terms["mask_loss"] = bce_sum(out["weight_sum"], gt["mask"]) / n_ray if ("mask" in gt and self.mask_weight > 0) else zero()
+        terms["depth_loss"] = (msum((out["depth_values"].flatten() - gt["depth"].flatten()) ** 2, gt["depth_mask"]) / n_depth
+                               if ("depth" in gt and self.depth_weight > 0) else zero())
+        has_n = "normal" in gt
+        terms["normal_loss"] = normal_l1() if (has_n and self.normal_weight > 0) else zero()
+        terms["angular_loss"] = normal_l1() if (has_n and self.angular_weight > 0) else zero()
+        terms["bubble_loss"] = out["surface_sdf"].abs().sum() / n_bub if ("surface_sdf" in out and self.bubble_weight > 0) else zero()
+        terms["light_mask_loss"] = (bce_sum(out["light_mask"].reshape(-1, 1), gt["light_mask"].reshape(-1, 1)) / n_ray
+                                    if ("light_mask" in out and self.light_mask_weight > 0) else zero())
+        weights = {"eikonal_loss": self.eikonal_weight, "smooth_loss": self.smooth_weight, "mask_loss": self.mask_weight,
+                   "depth_loss": self.depth_weight, "normal_loss": self.normal_weight, "angular_loss": self.angular_weight,
+                   "bubble_loss": self.bubble_weight, "light_mask_loss": self.light_mask_weight}
+        loss = terms["rgb_loss"]
+        for k, w in weights.items():
+            loss = loss + w * terms[k]
+        res = {"loss": loss}
+        res.update(terms)
+        return res

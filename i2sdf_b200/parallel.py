@@ -11,7 +11,8 @@ ordinary parameter gradients, so DDP's bucket hooks fire as usual.)
 
 Parity caveats of sharding, all inherited from the reference's batch-global semantics: the
 sampler's convergence test is global over the rays of ONE forward call (ray_sampler.py:151), so a shard may stop
-up-sampling one round earlier than the full batch would; masked-mean losses average per shard.
+up-sampling one round earlier than the full batch would (`use_global_convergence` restores the batch-global test);
+masked-mean losses average per shard (`use_global_loss_means` restores the batch-global means).
 """
 from typing import Dict, Iterable, Optional
 
@@ -55,6 +56,20 @@ def use_global_convergence(model, group: Optional[dist.ProcessGroup] = None, ena
         raise RuntimeError("use_global_convergence needs an initialised torch.distributed process group")
     model.convergence_group = (group if group is not None else dist.group.WORLD) if enable else None
     return model
+
+
+def use_global_loss_means(loss_fn, group: Optional[dist.ProcessGroup] = None, enable: bool = True):
+    """Make I2SDFLoss divide by the counts of the WHOLE batch (strict sharding parity of the loss and its gradients).
+
+    The reference's loss terms are means over all rays of the batch, two of them over masked subsets
+    (model/network/__init__.py:320-329).  A mean of per-shard means equals the batch mean only if every shard has the same
+    count — false for the depth / normal masks in general and for ragged shards.  With this switch every rank divides its
+    sums by (global count) / world (one 40-byte SUM all-reduce per step, in stream order): averaging the ranks' losses, and
+    the gradients as `allreduce_gradients(average=True)` does, then gives exactly the single-GPU values."""
+    if enable and not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("use_global_loss_means needs an initialised torch.distributed process group")
+    loss_fn.means_group = (group if group is not None else dist.group.WORLD) if enable else None
+    return loss_fn
 
 
 def allreduce_gradients(params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None,

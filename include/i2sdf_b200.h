@@ -285,7 +285,17 @@ int i2sdf_planes_wgrad(i2sdf_handle* h, int nterms, const void* const* P, const 
  * computes every term, the weighted total and d loss / d input for every model output that carries gradient.
  * All pointers are device memory; a NULL prediction pointer switches its term off (the caller applies the reference's
  * "key present and weight > 0" rules, e.g. diff_norm is passed only once current_step > smooth_iter).  Masks are bytes
- * (torch.bool).  g_* outputs may be NULL.  No handle: the loss has no network state. */
+ * (torch.bool).  g_* outputs may be NULL.  No handle: the loss has no network state.
+ * denom (optional): rays sharded over several GPUs (SURVEY.md §8(e) caveat 2).  The reference's means run over the WHOLE
+ * batch; a shard's own masked means differ from them as soon as the shards' mask counts differ.  With denom != NULL the
+ * kernel divides this shard's sums by the five given divisors instead of its local counts; the caller passes
+ * (global count) / (number of shards), so that the plain average over the shards of the returned loss - and of the
+ * parameter gradients, which the gradient all-reduce averages anyway - is the single-GPU loss / gradient of the whole batch. */
+#define I2SDF_LOSS_DENOM_RAYS 0    /* divisor of the per-ray means: rgb (x3), smooth, mask BCE, light BCE */
+#define I2SDF_LOSS_DENOM_EIK 1     /* eikonal rows */
+#define I2SDF_LOSS_DENOM_BUBBLE 2  /* bubble points */
+#define I2SDF_LOSS_DENOM_DEPTH 3   /* rays with depth_mask */
+#define I2SDF_LOSS_DENOM_NORMAL 4  /* rays with normal_mask */
 typedef struct i2sdf_loss_args {
     int64_t R;                   /* rays */
     int64_t n_eik;               /* rows of grad_theta (2R) */
@@ -315,6 +325,7 @@ typedef struct i2sdf_loss_args {
     float* g_normal;             /* [R,3] */
     float* g_surface_sdf;        /* [n_bubble] */
     float* g_light;              /* [R] */
+    const float* denom;          /* [5] device, I2SDF_LOSS_DENOM_* order, or NULL = this call's own counts */
 } i2sdf_loss_args;
 int i2sdf_loss_forward(const i2sdf_loss_args* args, void* stream);
 

@@ -148,3 +148,33 @@ def test_opt_in_helpers_fail_loudly_off_the_gpu():
         use_global_convergence(lin)
     sd = opt.state_dict()
     assert set(sd) == {"state", "param_groups"} and sd["param_groups"][0]["eps"] == 1e-15
+
+
+def test_ctypes_structs_match_the_header_field_by_field(tmp_path):
+    """Every struct of include/i2sdf_b200.h against its ctypes mirror in i2sdf_b200/_lib.py: a C probe compiled with gcc prints
+    sizeof and the offset of every field; the binding must agree (a silent mismatch would hand the kernels shifted pointers)."""
+    import ctypes
+    import subprocess
+    from i2sdf_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pairs = {"i2sdf_desc": _lib.Desc, "i2sdf_loss_args": _lib.LossArgs, "i2sdf_wnorm_job": _lib.WnormJob, "i2sdf_wnorm_batch": _lib.WnormBatch,
+             "i2sdf_adam_job": _lib.AdamJob, "i2sdf_adam_batch": _lib.AdamBatch}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "i2sdf_b200.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'printf("{cname} . %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['return 0; }']
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    seen = 0
+    for ln in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines():
+        cname, fname, val = ln.split()
+        cls = pairs[cname]
+        want = ctypes.sizeof(cls) if fname == "." else getattr(cls, fname).offset
+        assert int(val) == want, (cname, fname, int(val), want)
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in pairs.values())
+    assert _lib.WNORM_MAX_JOBS == 28 and _lib.ADAM_MAX_JOBS == 64          # I2SDF_WNORM_MAX_JOBS / I2SDF_ADAM_MAX_JOBS

@@ -74,3 +74,72 @@ def test_shard_bounds_cover_everything_once():
     eval_batch = {"uv": torch.zeros(1, 10, 2), "pose": torch.zeros(1, 4, 4), "intrinsics": torch.zeros(1, 4, 4)}
     a, b = shard_rays(eval_batch, 0, 2), shard_rays(eval_batch, 1, 2)
     assert a["uv"].shape == (1, 5, 2) and b["uv"].shape == (1, 5, 2) and a["pose"].shape == (1, 4, 4)
+
+
+# ---- batch-global loss means over ragged shards (SURVEY.md §8(e) caveat 2) ---------------------------------------------------
+def _loss_case(R, seed):
+    g = torch.Generator().manual_seed(seed)
+    out = {"rgb_values": torch.rand(R, 3, generator=g), "depth_values": torch.rand(R, generator=g) * 3,
+           "weight_sum": torch.rand(R, 1, generator=g), "grad_theta": torch.randn(2 * R, 3, generator=g),
+           "diff_norm": torch.rand(R, generator=g), "normal_values": torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1),
+           "surface_sdf": torch.randn(4, 1, generator=g) * 0.1, "light_mask": torch.rand(R, 1, generator=g)}
+    gt = {"rgb": torch.rand(R, 3, generator=g), "depth": torch.rand(R, generator=g) * 3, "depth_mask": torch.rand(R, generator=g) > 0.4,
+          "normal": torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1), "normal_mask": torch.rand(R, generator=g) > 0.6,
+          "mask": (torch.rand(R, 1, generator=g) > 0.5).float(), "light_mask": (torch.rand(R, 1, generator=g) > 0.5).float()}
+    gt["depth_mask"][0] = True
+    gt["normal_mask"][0] = True
+    return out, gt
+
+
+_LOSS_KW = dict(eikonal_weight=0.1, smooth_weight=0.01, mask_weight=0.2, depth_weight=0.1, normal_weight=0.05, angular_weight=0.05,
+                bubble_weight=0.5, light_mask_weight=0.5)
+_SHARDS = (11, 6)            # ragged on purpose: the per-ray means need the global ray count too
+
+
+def _loss_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from i2sdf_b200.network import I2SDFLoss
+    from i2sdf_b200.parallel import use_global_loss_means
+    out, gt = _loss_case(_SHARDS[rank], 100 + rank)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in out.items()}
+    fn = use_global_loss_means(I2SDFLoss(**_LOSS_KW))
+    res = fn(leaves, gt, 10)
+    res["loss"].backward()
+    q.put((rank, float(res["loss"]), {k: float(v) for k, v in res.items()}, {k: v.grad.clone() for k, v in leaves.items()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_global_loss_means_equal_the_single_process_loss():
+    from i2sdf_b200.network import I2SDFLoss
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_loss_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=180) for _ in range(world)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # the whole batch in one process, the reference's formulas
+    cases = [_loss_case(_SHARDS[r], 100 + r) for r in range(world)]
+    out = {k: torch.cat([c[0][k] for c in cases]).clone().requires_grad_(True) for k in cases[0][0]}
+    gt = {k: torch.cat([c[1][k] for c in cases]) for k in cases[0][1]}
+    fn = I2SDFLoss(**_LOSS_KW)
+    whole = fn(out, gt, 10)
+    whole["loss"].backward()
+    assert abs(sum(r[1] for r in res) / world - float(whole["loss"])) < 1e-6 * abs(float(whole["loss"]))
+    for k in ("rgb_loss", "eikonal_loss", "smooth_loss", "mask_loss", "depth_loss", "normal_loss", "bubble_loss", "light_mask_loss"):
+        assert abs(sum(r[2][k] for r in res) / world - float(whole[k])) < 2e-6 * max(abs(float(whole[k])), 1e-3), k
+    # gradient of a shard's outputs, averaged as the gradient all-reduce averages parameter gradients, = its slice of the whole
+    # batch's gradient
+    for k in out:
+        got = torch.cat([r[3][k] for r in res]) / world
+        assert torch.allclose(got, out[k].grad, rtol=1e-5, atol=1e-8), k
+    # without the switch the per-shard means differ (this is what the test guards against)
+    plain = [I2SDFLoss(**_LOSS_KW)(c[0], c[1], 10) for c in cases]
+    assert abs(sum(float(p["depth_loss"]) for p in plain) / world - float(whole["depth_loss"])) > 1e-4

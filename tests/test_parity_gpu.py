@@ -656,6 +656,41 @@ def test_fused_loss_matches_the_pytorch_restatement(R, all_terms):
         assert relerr(of[k].grad, ot[k].grad) < 1e-5, (k, relerr(of[k].grad, ot[k].grad))
 
 
+def test_fused_loss_with_shard_denominators():
+    """Sharded batches (SURVEY.md §8(e) caveat 2): the kernel divides by the caller's divisors (global count / world) instead of its own
+    counts.  Same check as above with explicit divisors against I2SDFLoss._forward_torch_sharded (whose 2-rank gloo test shows
+    that these divisors reproduce the single-process loss and gradients)."""
+    from i2sdf_b200.network import I2SDFLoss
+    R = 130
+    g = torch.Generator().manual_seed(9)
+    rnd = lambda *s: torch.rand(*s, generator=g)          # noqa: E731
+    out = {"rgb_values": rnd(R, 3), "depth_values": rnd(R) * 3, "weight_sum": rnd(R, 1), "normal_values": torch.nn.functional.normalize(rnd(R, 3) - 0.5, dim=1),
+           "grad_theta": (rnd(2 * R, 3) - 0.5) * 3, "diff_norm": rnd(R), "surface_sdf": rnd(77, 1) - 0.5, "light_mask": rnd(R, 1)}
+    gt = {"rgb": rnd(R, 1, 3), "depth": rnd(R, 1) * 3, "depth_mask": rnd(R, 1) > 0.3, "normal": torch.nn.functional.normalize(rnd(R, 3) - 0.5, dim=1),
+          "normal_mask": rnd(R) > 0.5, "mask": (rnd(R, 1) > 0.5).float(), "light_mask": (rnd(R, 1) > 0.8).float()}
+    gt = {k: v.cuda() for k, v in gt.items()}
+    loss_fn = I2SDFLoss(eikonal_weight=0.1, depth_weight=0.1, normal_weight=0.05, smooth_weight=0.01, smooth_iter=10, mask_weight=0.2,
+                        bubble_weight=0.5, light_mask_weight=0.5)
+    den = torch.tensor([150.5, 240.0, 60.5, 101.5, 71.0], device="cuda")          # rays, eikonal rows, bubble points, depth count, normal count
+    loss_fn._shard_denominators = lambda *a: den
+    res = {}
+    for mode in ("fused", "torch"):
+        o = {k: v.clone().cuda().requires_grad_(True) for k, v in out.items()}
+        r = loss_fn(o, gt, 100) if mode == "fused" else loss_fn._forward_torch_sharded(o, gt, 100, den)
+        (r["loss"] * 0.6).backward()
+        res[mode] = (r, o)
+    (rf, of), (rt, ot) = res["fused"], res["torch"]
+    for k in rt:
+        a, b = float(rf[k]), float(rt[k])
+        assert abs(a - b) <= 2e-6 * max(abs(b), 1e-3), (k, a, b)
+    for k in ot:
+        assert of[k].grad is not None, k
+        assert relerr(of[k].grad, ot[k].grad) < 1e-5, (k, relerr(of[k].grad, ot[k].grad))
+    # and the divisors matter: the plain call (own counts) gives another value
+    plain = I2SDFLoss(eikonal_weight=0.1, depth_weight=0.1)({k: v.cuda() for k, v in out.items()}, gt, 100)
+    assert abs(float(plain["depth_loss"]) - float(rf["depth_loss"])) > 1e-4
+
+
 @pytest.mark.parametrize("R", [1, 5, 130])
 def test_ragged_ray_counts_render_and_train(R):
     """Ray counts that fill neither a tile nor a warp: eval render against the oracle, and a full training step (finite loss and
