@@ -80,15 +80,33 @@ class RayFeed:
             gt["normal_mask"] = self.normal_masks[img, pix]
         return indices, img, sample, gt
 
-    def batches(self, batch_size: int, shuffle: bool = True, drop_last: bool = False,
-                generator: Optional[torch.Generator] = None) -> Iterator[Tuple[torch.Tensor, torch.Tensor, dict, dict]]:
-        """One epoch: every pixel of every image exactly once (DataLoader(shuffle=True) semantics)."""
+    def batches(self, batch_size: int, shuffle: bool = True, drop_last: bool = False, generator: Optional[torch.Generator] = None,
+                group=None) -> Iterator[Tuple[torch.Tensor, torch.Tensor, dict, dict]]:
+        """One epoch: every pixel of every image exactly once (DataLoader(shuffle=True) semantics).
+
+        group (a torch.distributed process group, rays sharded over its ranks): `batch_size` stays the GLOBAL batch of the
+        reference's trainer; every rank walks the same shuffled epoch — the permutation's seed is drawn on rank 0 and broadcast
+        (8 bytes per epoch) — and yields its contiguous share of each global batch (parallel.shard_bounds), so the ranks'
+        batches are disjoint, cover the global batch, and the union over an epoch is every pixel exactly once."""
         n = len(self)
+        rank, world = 0, 1
+        if group is not None:
+            import torch.distributed as dist
+            from .parallel import shard_bounds
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+            if shuffle:
+                seed = torch.randint(0, 2 ** 62, (1,), generator=generator if (generator is None or generator.device.type == "cpu") else None)
+                seed = seed.to(self.device)
+                dist.broadcast(seed, src=dist.get_global_rank(group, 0), group=group)
+                generator = torch.Generator(device=self.device).manual_seed(int(seed.item()))
         order = torch.randperm(n, device=self.device, generator=generator) if shuffle else torch.arange(n, device=self.device)
         for lo in range(0, n, batch_size):
             idx = order[lo:lo + batch_size]
             if drop_last and idx.numel() < batch_size:
                 return
+            if world > 1:
+                a, b = shard_bounds(idx.numel(), rank, world)
+                idx = idx[a:b]
             yield self.gather(idx)
 
     def random_batch(self, batch_size: int, generator: Optional[torch.Generator] = None):
@@ -111,8 +129,31 @@ class BubblePDF:
         self.pdf_prune, self.pdf_max, self.uniform = pdf_prune, pdf_max, uniform
 
     @torch.no_grad()
-    def update_pdf(self, value: torch.Tensor, idx: torch.Tensor) -> None:
-        """pdf[point of pixel idx] = clamp / prune(value)   (recon.py:142-152); pixels without a point are skipped."""
+    def update_pdf(self, value: torch.Tensor, idx: torch.Tensor, group=None) -> None:
+        """pdf[point of pixel idx] = clamp / prune(value)   (recon.py:142-152); pixels without a point are skipped.
+
+        group: rays sharded over the ranks of a process group (SURVEY.md §8(e) caveat 4).  The reference's PDF is one buffer
+        updated with the errors of the WHOLE batch; a rank on its own would only see its shard.  With `group` the (value, idx)
+        pairs of all ranks are all-gathered (ragged shards padded) and applied in rank order, so every rank holds the PDF the
+        single-process trainer would hold."""
+        if group is not None:
+            import torch.distributed as dist
+            world = dist.get_world_size(group)
+            if world > 1:
+                dev = self.pdf.device
+                value, idx = value.to(dev).reshape(-1).float(), idx.to(dev).reshape(-1).long()
+                n = torch.tensor([value.numel()], device=dev, dtype=torch.long)
+                sizes = [torch.zeros_like(n) for _ in range(world)]
+                dist.all_gather(sizes, n, group=group)
+                sizes = [int(t.item()) for t in sizes]
+                cap = max(sizes)
+                pv, pi = value.new_zeros(cap), idx.new_full((cap,), -1)
+                pv[:value.numel()], pi[:idx.numel()] = value, idx
+                gv, gi = [torch.empty_like(pv) for _ in range(world)], [torch.empty_like(pi) for _ in range(world)]
+                dist.all_gather(gv, pv, group=group)
+                dist.all_gather(gi, pi, group=group)
+                value = torch.cat([t[:k] for t, k in zip(gv, sizes)])
+                idx = torch.cat([t[:k] for t, k in zip(gi, sizes)])
         value = value.to(self.pdf.device).clone()
         if self.pdf_max is not None:
             value = value.clamp(max=self.pdf_max)

@@ -45,6 +45,24 @@ def shard_rays(batch: Dict[str, torch.Tensor], rank: int, world: int) -> Dict[st
     return out
 
 
+def seed_rank(seed: int, rank: int, device: Optional[torch.device] = None) -> int:
+    """Per-rank RNG streams for the training-mode draws of a sharded step (SURVEY.md §8(e) caveat 3).
+
+    The reference seeds ONE process (`pl.seed_everything(args.seed)`, main_recon.py:63) and then draws, per step, the sampler's
+    jitter / inverse-CDF uniforms (ray_sampler.py:39,190: device generator), the extra-sample permutation (:223: CPU generator),
+    the eikonal pick (:233) and the eikonal / neighbour points (network/__init__.py:178,186).  Ranks that shared that seed would
+    draw the SAME jitter and eikonal points for different rays; every rank therefore gets its own stream, a fixed function of
+    (seed, rank): rank 0 keeps the reference's seed, so a 1-GPU run reproduces the unsharded run draw for draw.  Seeds the CPU
+    generator and `device`'s generator (default: the current CUDA device if there is one); returns the seed used."""
+    s = int(seed) + 0x9E3779B1 * int(rank)          # distinct, reproducible, rank 0 == seed
+    s &= (1 << 63) - 1
+    torch.manual_seed(s)                             # CPU generator (+ all CUDA generators, as torch.manual_seed does)
+    if device is not None and torch.device(device).type == "cuda":
+        with torch.cuda.device(device):
+            torch.cuda.manual_seed(s)
+    return s
+
+
 def use_global_convergence(model, group: Optional[dist.ProcessGroup] = None, enable: bool = True):
     """Make the error-bounded sampler's convergence test global over all ranks' rays (strict sharding parity).
 

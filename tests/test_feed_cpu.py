@@ -1,5 +1,6 @@
 """Host logic of the device-resident ray feed (i2sdf_b200/feed.py) against a literal restatement of the reference's per-pixel
 dataset items + collate (dataset/train_dataset.py:169-209) and of its bubble PDF (model/trainer/recon.py:142-168)."""
+import numpy as np
 import torch
 
 from i2sdf_b200.feed import BubblePDF, RayFeed
@@ -94,3 +95,65 @@ def test_bubble_pdf_update_and_sampling():
     assert all(any(torch.equal(p, cloud[j]) for j in picked) for p in pts)
     uni = BubblePDF(cloud, links, uniform=True)
     assert uni.sample_bubble(5).shape == (5, 3)
+
+
+# ---- rays sharded over ranks (gloo, world_size 2): disjoint shares of the same shuffled epoch, one PDF ------------------------
+def _shard_worker(rank, world, port, q):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    t, hw = _tables()
+    feed = RayFeed(**t)
+    torch.manual_seed(1234 + rank)                       # ranks do NOT share a seed: the epoch's permutation comes from rank 0
+    got = [(b[0].numpy().copy(), b[3]["rgb"].numpy().copy()) for b in feed.batches(7, group=dist.group.WORLD)]      # numpy: pickled by value
+    # bubble PDF: every rank reports the errors of its own (ragged) shard
+    links = torch.arange(3 * hw) % 11
+    links[::5] = -1
+    pdf = BubblePDF(torch.rand(11, 3, generator=torch.Generator().manual_seed(0)), links, pdf_prune=0.1, pdf_max=0.8)
+    g = torch.Generator().manual_seed(50 + rank)
+    n = 9 if rank == 0 else 4
+    val, idx = torch.rand(n, generator=g), torch.randint(3 * hw, (n,), generator=g)
+    pdf.update_pdf(val, idx, group=dist.group.WORLD)
+    q.put((rank, got, pdf.pdf.numpy().copy(), val.numpy().copy(), idx.numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_epoch_and_all_gathered_pdf_updates():
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shard_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=180) for _ in range(world)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    t, hw = _tables()
+    n = 3 * hw
+    as_t = lambda pairs: [(torch.from_numpy(i), torch.from_numpy(c)) for i, c in pairs]          # noqa: E731
+    b0, b1 = as_t(res[0][1]), as_t(res[1][1])
+    assert len(b0) == len(b1) == -(-n // 7)
+    seen = []
+    for k, ((i0, rgb0), (i1, rgb1)) in enumerate(zip(b0, b1)):
+        size = min(7, n - 7 * k)
+        assert i0.numel() == -(-size // 2) and i1.numel() == size // 2            # shard_bounds: rank 0 takes the odd one
+        assert torch.equal(rgb0, t["rgb_images"].reshape(-1, 3)[i0])
+        seen += i0.tolist() + i1.tolist()
+    assert sorted(seen) == list(range(n))                                         # the epoch covers every pixel exactly once
+    assert seen != list(range(n))                                                 # ... shuffled
+    # PDF: both ranks hold what one process would hold after the updates of the whole batch, applied in rank order
+    links = torch.arange(n) % 11
+    links[::5] = -1
+    ref = BubblePDF(torch.rand(11, 3, generator=torch.Generator().manual_seed(0)), links, pdf_prune=0.1, pdf_max=0.8)
+    ref.update_pdf(torch.from_numpy(np.concatenate([res[0][3], res[1][3]])), torch.from_numpy(np.concatenate([res[0][4], res[1][4]])))
+    assert np.array_equal(res[0][2], ref.pdf.numpy()) and np.array_equal(res[1][2], ref.pdf.numpy()) and float(ref.pdf.sum()) > 0

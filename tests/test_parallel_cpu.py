@@ -107,7 +107,7 @@ def _loss_worker(rank, world, port, q):
     fn = use_global_loss_means(I2SDFLoss(**_LOSS_KW))
     res = fn(leaves, gt, 10)
     res["loss"].backward()
-    q.put((rank, float(res["loss"]), {k: float(v) for k, v in res.items()}, {k: v.grad.clone() for k, v in leaves.items()}))
+    q.put((rank, float(res["loss"]), {k: float(v) for k, v in res.items()}, {k: v.grad.numpy().copy() for k, v in leaves.items()}))      # numpy: pickled by value
     dist.barrier()
     dist.destroy_process_group()
 
@@ -138,8 +138,22 @@ def test_global_loss_means_equal_the_single_process_loss():
     # gradient of a shard's outputs, averaged as the gradient all-reduce averages parameter gradients, = its slice of the whole
     # batch's gradient
     for k in out:
-        got = torch.cat([r[3][k] for r in res]) / world
+        got = torch.cat([torch.from_numpy(r[3][k]) for r in res]) / world
         assert torch.allclose(got, out[k].grad, rtol=1e-5, atol=1e-8), k
     # without the switch the per-shard means differ (this is what the test guards against)
     plain = [I2SDFLoss(**_LOSS_KW)(c[0], c[1], 10) for c in cases]
     assert abs(sum(float(p["depth_loss"]) for p in plain) / world - float(whole["depth_loss"])) > 1e-4
+
+
+def test_seed_rank_streams():
+    from i2sdf_b200.parallel import seed_rank
+    assert seed_rank(42, 0) == 42                       # rank 0 keeps the reference's seed: same draws as the unsharded run
+    a = torch.rand(4)
+    torch.manual_seed(42)
+    assert torch.equal(a, torch.rand(4))
+    seeds = {seed_rank(42, r) for r in range(8)}
+    assert len(seeds) == 8
+    seed_rank(42, 3)
+    b = torch.rand(4)
+    seed_rank(42, 3)
+    assert torch.equal(b, torch.rand(4)) and not torch.equal(a, b)
