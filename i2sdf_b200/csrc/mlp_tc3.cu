@@ -44,7 +44,7 @@ template <bool FULL, bool SAVE>
 // 18 warps -> one scheduler hosts 5 of them: 16 K regs / 5 warps caps the kernel at 96 registers per thread
 __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, const OpTable T) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_align1024(smem_raw);
     uint8_t* A_hi = smem;
     uint8_t* A_lo = smem + A_PART_BYTES;
     uint8_t* ring = smem + 2 * A_PART_BYTES;
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
 // chain of the next layer, which paces the op (tools/timeline.py) - is ready after 1/8 instead of 1/4 of the epilogue.
 __global__ void __launch_bounds__(NTHREADS, 1) tc_sdf8_kernel(const MlpParams P, const OpTable T) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_align1024(smem_raw);
     uint8_t* A_hi = smem;
     uint8_t* A_lo = smem + A_PART_BYTES;
     uint8_t* ring = smem + 2 * A_PART_BYTES;

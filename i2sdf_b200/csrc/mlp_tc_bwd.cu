@@ -47,7 +47,7 @@ __device__ __forceinline__ void pf_seg16(const uint8_t* seg) {
 template <bool PF_NEXT>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const BwdParams P, const OpTable T) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_align1024(smem_raw);
     uint8_t* A_hi = smem;
     uint8_t* A_lo = smem + A_PART_BYTES;
     uint8_t* ring = smem + 2 * A_PART_BYTES;

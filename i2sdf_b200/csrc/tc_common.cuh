@@ -15,6 +15,11 @@ namespace i2sdf {
 namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// First 1024-byte aligned address of the dynamic shared memory, derived by pointer arithmetic on the `extern __shared__` array
+// so that the compiler still knows every pointer built from it is shared memory.  (Rounding the pointer through uintptr_t
+// makes it generic: the operand stores of the epilogues then compile to ST.E.128 with 64-bit address arithmetic and a
+// per-item S2UR SR_CgaCtaId / SR_SWINHI window rebuild instead of STS.128 - seen in the SASS of every chain kernel.)
+__device__ __forceinline__ uint8_t* smem_align1024(uint8_t* raw) { return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u); }
 
 // ---- mbarrier ------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -74,7 +74,7 @@ __device__ __forceinline__ void publish(uint64_t* bar, int lane) {
 
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_pw_kernel(const PWArgs G) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_align1024(smem_raw);
     uint8_t* A_hi = smem;
     uint8_t* A_lo = smem + A_PART_BYTES;
     uint8_t* ring = smem + 2 * A_PART_BYTES;
@@ -289,7 +289,7 @@ struct WGArgs {
 
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_wgrad_kernel(const WGArgs G) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_align1024(smem_raw);
     uint8_t* ring = smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + WG_STAGES * WG_STAGE_BYTES);
     uint64_t* full = bars;                   // [WG_STAGES] 16 arrivals (loader warps)

@@ -40,7 +40,7 @@ __device__ __forceinline__ bool flush_after(const WgArgs& A, long long u, long l
 
 __global__ void __launch_bounds__(NTHREADS, 1) wgrad_planes_kernel(const WgArgs A) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_align1024(smem_raw);
     uint8_t* ring = smem;
     float* xpose = reinterpret_cast<float*>(ring + NSTAGE * STAGE_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(xpose + N_FLUSH_WARPS * XPOSE_FLOATS);
