@@ -243,7 +243,54 @@ def train_case(case, conf_name, weights_name, beta, R, perturb, seed, n_cloud=24
     return P
 
 
+def uniform_case(case, conf_name, weights_name, beta, R, perturb, seed, n_uniform=64):
+    """BASELINE.json configs[0] (C1): the reference forward with its OWN `UniformSampler(scene_bounding_sphere, near, 64)`
+    (model/network/ray_sampler.py:15-43) in place of the error-bounded sampler, eval mode: z = linspace(0, 6, 64), 63
+    composited points per ray.  I2SDFNetwork.forward expects (z_vals, z_samples_eik) from its sampler (network/__init__.py:96),
+    UniformSampler returns z_vals only, so the stand-in pairs it with z[:, :1] (unused in eval mode)."""
+    import importlib
+    net, conf, m = build_ref(conf_name, False, beta, perturb)
+    m.eval()
+    P = params_of(m)
+    rs = importlib.import_module("model.network.ray_sampler")
+    uni = rs.UniformSampler(conf.model.scene_bounding_sphere, conf.model.ray_sampler.near, n_uniform)
+
+    class _Pair:
+        def get_z_vals(self, ray_dirs, cam_loc, model):
+            z = uni.get_z_vals(ray_dirs, cam_loc, model)
+            return z, z[:, :1]
+
+    m.ray_sampler = _Pair()
+    spec = orc.spec_from_model_conf(configs.model_conf(conf_name), use_normal=False)
+    inp = orc.synthetic_rays(R, seed=seed)
+    store = {}
+    hook_intermediates(m, store)
+    ref_out = {k: v.detach() for k, v in m({k: v.clone() for k, v in inp.items()}).items()}
+    z = store["z_all"]
+    assert z.shape == (R, n_uniform) and torch.equal(z[0], torch.linspace(0., 1., n_uniform) * spec.far)
+    with torch.no_grad():
+        o_out = orc.render(spec, P, inp, training=False, z_override=z)
+    for k in ref_out:
+        e = relerr(o_out[k], ref_out[k])
+        print(f"   [{case}] {k:14s} oracle-vs-reference rel err {e:.2e}")
+        assert e < 2e-5, (k, e)
+    arrays = {}
+    arrays.update(np_dict(inp, "in_"))
+    arrays.update(np_dict(ref_out, "ref_"))
+    arrays.update(np_dict({"z_all": z, "sdf": store["sdf"], "grad": store["grad"]}, "ref_mid_"))
+    arrays["meta_conf"] = np.asarray(conf_name)
+    arrays["meta_weights"] = np.asarray(weights_name)
+    arrays["meta_beta"] = np.asarray(beta, dtype=np.float32)
+    np.savez_compressed(os.path.join(HERE, f"{case}.npz"), **arrays)
+    return P
+
+
 if __name__ == "__main__":
+    if "--only-uniform" in sys.argv:          # adds the C1 fixture without rewriting the others (same weights: asserted)
+        Pu = uniform_case("eval_uniform_c1", "synthetic", "synthetic", beta=0.05, R=48, perturb=0.06, seed=6)
+        w = np.load(os.path.join(HERE, "weights_synthetic.npz"))
+        assert all(np.array_equal(w[k], Pu[k].numpy()) for k in w.files)
+        sys.exit(0)
     P = eval_case("eval_synthetic_sharp", "synthetic", "synthetic", beta=0.01, R=48, perturb=0.06, seed=1)
     Pw = {k: v for k, v in P.items() if k != "density.beta"}
     save_weights("synthetic", Pw)
@@ -256,4 +303,6 @@ if __name__ == "__main__":
     save_weights("light", Pl)
     P5 = train_case("train_light", "synthetic_light_mask", "light", beta=0.05, R=32, perturb=0.06, seed=5)
     assert all(torch.equal(P5[k], Pl[k]) for k in Pl)
+    Pu = uniform_case("eval_uniform_c1", "synthetic", "synthetic", beta=0.05, R=48, perturb=0.06, seed=6)
+    assert all(torch.equal(Pu[k], Pw[k]) for k in Pw)
     print("golden fixtures written to", HERE)

@@ -58,11 +58,16 @@ def test_oracle_train_matches_reference(name):
 
 
 def test_uniform_sampler_config_c1():
-    """BASELINE config 1: 64 uniform samples on [0, 6] -> 63 composited points/ray (plumbing case)."""
-    c = Case("eval_synthetic_soft")
+    """BASELINE config 1 (the reference's own CPU-runnable case): 64 uniform samples on [0, 6] -> 63 composited points/ray.
+    Fixture: the unmodified reference with its own UniformSampler swapped in (tests/golden/make_golden.py: uniform_case)."""
+    c = Case("eval_uniform_c1")
     R = c.inputs["uv"].shape[1]
-    z = torch.linspace(0, 1, 64)[None].repeat(R, 1) * c.spec.far
+    z = c.mid["z_all"]
+    assert z.shape == (R, 64) and torch.equal(z, (torch.linspace(0, 1, 64) * c.spec.far)[None].repeat(R, 1))
     with torch.no_grad():
         out = orc.render(c.spec, c.params, c.inputs, training=False, z_override=z)
-    assert out["rgb_values"].shape == (R, 3) and torch.isfinite(out["rgb_values"]).all()
-    assert (out["weight_sum"] <= 1 + 1e-5).all()
+    assert set(out) == set(c.ref)
+    for k, v in c.ref.items():
+        assert out[k].shape == v.shape, k
+        assert relerr(out[k], v) < 2e-6, k
+    assert (out["weight_sum"] <= 1 + 1e-5).all() and float(out["weight_sum"].max()) > 0.5     # the rays do hit the surface
