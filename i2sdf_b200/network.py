@@ -364,7 +364,7 @@ class I2SDFNetwork(nn.Module):
 
 class I2SDFLoss(nn.Module):
     """Loss of the reconstruction stage; consumes I2SDFNetwork outputs (reference: model/network/__init__.py:289-406).
-    On CUDA tensors the whole loss and its backward seed are one kernel (csrc/loss.cu)."""
+    The whole loss and its backward seed are one kernel (csrc/loss.cu); CPU tensors are rejected."""
 
     def __init__(self, eikonal_weight=0.1, smooth_weight=0.0, mask_weight=0.0, depth_weight=0.1, normal_weight=0.05,
                  angular_weight=0.05, bubble_weight=0.0, min_bubble_iter=0, max_bubble_iter=None, smooth_iter=None,
@@ -412,9 +412,13 @@ class I2SDFLoss(nn.Module):
         return self._masked_mean((torch.acos(torch.clamp(dot, -1.0 + 1e-6, 1.0 - 1e-6)) / math.tau).clamp_max(0.5).abs(), normal_mask)
 
     def forward(self, model_outputs, ground_truth, current_step):
-        if model_outputs["rgb_values"].is_cuda:
-            return self._forward_fused(model_outputs, ground_truth, current_step)
-        return self._forward_torch(model_outputs, ground_truth, current_step)
+        if not model_outputs["rgb_values"].is_cuda:
+            # no CPU path in the product: I2SDFNetwork only produces CUDA tensors.  (_forward_torch below is the PyTorch
+            # restatement the tests check the kernel against; it is not reachable from here.)
+            from ._lib import I2SDFError
+            raise I2SDFError("I2SDFLoss runs on CUDA tensors only (csrc/loss.cu, no CPU fallback); got model outputs on "
+                             f"{model_outputs['rgb_values'].device}")
+        return self._forward_fused(model_outputs, ground_truth, current_step)
 
     def _shard_denominators(self, n_rays, n_eik, n_bubble, depth_mask, normal_mask, dev):
         """Divisors of the means when the batch is sharded over the ranks of `means_group` (SURVEY.md §8(e) caveat 2): the
@@ -471,7 +475,8 @@ class I2SDFLoss(nn.Module):
         return res
 
     def _forward_torch(self, model_outputs, ground_truth, current_step):
-        """Plain PyTorch restatement (CPU tensors: host-side tests of the loss module; the CUDA path is _forward_fused)."""
+        """Plain PyTorch restatement of the reference's loss (model/network/__init__.py:338-406).  CHECKER ONLY: the tests compare
+        the CUDA kernel with it (and it with the oracle's loss, which the fixtures pin on the reference); forward() never calls it."""
         dev = model_outputs["rgb_values"].device
         zero = lambda: torch.zeros((), device=dev)                # noqa: E731   (a fill kernel: no host->device copy, no sync)
         if self.means_group is not None:

@@ -104,7 +104,7 @@ def test_any_optimizer_step_invalidates_the_packed_weights_key():
 
 
 def test_loss_restatement_matches_the_oracle_loss_on_cpu():
-    """I2SDFLoss._forward_torch (the CPU-tensor path; the CUDA kernel is checked against it on the GPU) vs the oracle's
+    """I2SDFLoss._forward_torch (the PyTorch restatement the CUDA kernel is checked against on the GPU) vs the oracle's
     recon_loss, which the training fixtures pin on the reference's loss values (model/network/__init__.py:338-406)."""
     import torch
     from i2sdf_b200.network import I2SDFLoss
@@ -119,13 +119,15 @@ def test_loss_restatement_matches_the_oracle_loss_on_cpu():
           "mask": (torch.rand(R, 1, generator=g) > 0.5).float(), "light_mask": (torch.rand(R, 1, generator=g) > 0.7).float()}
     kw = dict(eikonal_weight=0.1, smooth_weight=0.01, depth_weight=0.1, normal_weight=0.05, bubble_weight=0.5, light_mask_weight=0.5,
               mask_weight=0.2)
-    mine = I2SDFLoss(smooth_iter=10, **kw)(out, gt, 100)
+    mine = I2SDFLoss(smooth_iter=10, **kw)._forward_torch(out, gt, 100)
     ref = orc.recon_loss(out, gt, angular_weight=0.05, smooth_active=True, **kw)
     assert abs(float(mine["loss"]) - float(ref)) < 1e-6 * abs(float(ref))
     assert set(mine) == {"loss", "rgb_loss", "eikonal_loss", "smooth_loss", "mask_loss", "depth_loss", "normal_loss", "angular_loss",
                          "bubble_loss", "light_mask_loss"}
     assert float(mine["angular_loss"]) == float(mine["normal_loss"])         # the reference's "angular" term IS the L1 normal loss (:368-371)
-    early = I2SDFLoss(smooth_iter=1000, **kw)(out, gt, 100)
+    early = I2SDFLoss(smooth_iter=1000, **kw)._forward_torch(out, gt, 100)
+    with pytest.raises(_lib.I2SDFError):                                    # the module itself has no CPU path
+        I2SDFLoss(**kw)(out, gt, 100)
     assert float(early["smooth_loss"]) == 0.0                                # smoothness term only after smooth_iter (:347-351)
 
 

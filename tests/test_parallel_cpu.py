@@ -105,7 +105,7 @@ def _loss_worker(rank, world, port, q):
     out, gt = _loss_case(_SHARDS[rank], 100 + rank)
     leaves = {k: v.clone().requires_grad_(True) for k, v in out.items()}
     fn = use_global_loss_means(I2SDFLoss(**_LOSS_KW))
-    res = fn(leaves, gt, 10)
+    res = fn._forward_torch(leaves, gt, 10)          # the PyTorch restatement (the CUDA kernel takes the same divisors: GPU test)
     res["loss"].backward()
     q.put((rank, float(res["loss"]), {k: float(v) for k, v in res.items()}, {k: v.grad.numpy().copy() for k, v in leaves.items()}))      # numpy: pickled by value
     dist.barrier()
@@ -130,7 +130,7 @@ def test_global_loss_means_equal_the_single_process_loss():
     out = {k: torch.cat([c[0][k] for c in cases]).clone().requires_grad_(True) for k in cases[0][0]}
     gt = {k: torch.cat([c[1][k] for c in cases]) for k in cases[0][1]}
     fn = I2SDFLoss(**_LOSS_KW)
-    whole = fn(out, gt, 10)
+    whole = fn._forward_torch(out, gt, 10)
     whole["loss"].backward()
     assert abs(sum(r[1] for r in res) / world - float(whole["loss"])) < 1e-6 * abs(float(whole["loss"]))
     for k in ("rgb_loss", "eikonal_loss", "smooth_loss", "mask_loss", "depth_loss", "normal_loss", "bubble_loss", "light_mask_loss"):
@@ -141,7 +141,7 @@ def test_global_loss_means_equal_the_single_process_loss():
         got = torch.cat([torch.from_numpy(r[3][k]) for r in res]) / world
         assert torch.allclose(got, out[k].grad, rtol=1e-5, atol=1e-8), k
     # without the switch the per-shard means differ (this is what the test guards against)
-    plain = [I2SDFLoss(**_LOSS_KW)(c[0], c[1], 10) for c in cases]
+    plain = [I2SDFLoss(**_LOSS_KW)._forward_torch(c[0], c[1], 10) for c in cases]
     assert abs(sum(float(p["depth_loss"]) for p in plain) / world - float(whole["depth_loss"])) > 1e-4
 
 
