@@ -180,3 +180,23 @@ def test_ctypes_structs_match_the_header_field_by_field(tmp_path):
         seen += 1
     assert seen == sum(len(c._fields_) + 1 for c in pairs.values())
     assert _lib.WNORM_MAX_JOBS == 28 and _lib.ADAM_MAX_JOBS == 64          # I2SDF_WNORM_MAX_JOBS / I2SDF_ADAM_MAX_JOBS
+
+
+def test_c_abi_from_plain_c(tmp_path):
+    """The boundary is a C ABI: tests/cabi/probe.c (C11, libdl only, no torch, no CUDA headers) binds the library the way a
+    foreign-function stub would, checks argument validation, and creates a handle — which must fail LOUDLY (I2SDF_E_NOGPU and a
+    message, no crash, no fallback) on a host without a B200 and succeed on one."""
+    import subprocess
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cabi", "probe.c"),
+                    "-o", str(exe), "-ldl"], check=True)
+    r = subprocess.run([str(exe), _lib.LIB_PATH], check=True, capture_output=True, text=True, timeout=120)
+    lines = {ln.split()[0]: ln for ln in r.stdout.splitlines()}
+    assert lines["abi"].split()[1] == lines["abi"].split()[3] == str(_lib.ABI_VERSION)
+    assert lines["slot256"].split()[1] == str(_lib.load().i2sdf_planes_slot_bytes(1000, 256))
+    assert " rc -1 " in lines["create_bad"] and "handle null" in lines["create_bad"] and "256" in lines["create_bad"]
+    assert " rc -1 " in lines["loss_null"] and "required" in lines["loss_null"]
+    if torch.cuda.is_available():
+        assert " rc 0 " in lines["create_ok"] and lines["destroy"].endswith("rc 0")
+    else:
+        assert " rc -3 " in lines["create_nogpu"] and "handle null" in lines["create_nogpu"]  # I2SDF_E_NOGPU
