@@ -285,7 +285,46 @@ def uniform_case(case, conf_name, weights_name, beta, R, perturb, seed, n_unifor
     return P
 
 
+LOSS_ALL_KW = dict(eikonal_weight=0.1, smooth_weight=0.01, mask_weight=0.2, depth_weight=0.1, normal_weight=0.05, angular_weight=0.05,
+                   bubble_weight=0.5, light_mask_weight=0.5, smooth_iter=10)
+
+
+def loss_case(case="loss_all_terms", R=57, seed=11):
+    """The reference's I2SDFLoss (model/network/__init__.py:289-406) with EVERY term switched on (the training fixtures only
+    exercise the terms of the shipped yamls) on random model outputs: all ten returned values at two steps (before / after
+    smooth_iter) and d loss / d output from the reference's autograd.  Includes the edges the CUDA kernel special-cases:
+    |grad_theta| = 0, weight_sum / light_mask outside the BCE clip range."""
+    net, _ = ref_shim.load()
+    g = torch.Generator().manual_seed(seed)
+    rnd = lambda *s: torch.rand(*s, generator=g)          # noqa: E731
+    out = {"rgb_values": rnd(R, 3), "depth_values": rnd(R) * 3, "weight_sum": rnd(R, 1) * 1.2 - 0.1,
+           "normal_values": torch.nn.functional.normalize(rnd(R, 3) - 0.5, dim=1), "grad_theta": (rnd(2 * R, 3) - 0.5) * 3,
+           "diff_norm": rnd(R), "surface_sdf": rnd(23, 1) - 0.5, "light_mask": rnd(R, 1) * 1.2 - 0.1}
+    out["grad_theta"][3] = 0.0
+    gt = {"rgb": rnd(R, 1, 3), "depth": rnd(R, 1) * 3, "depth_mask": rnd(R, 1) > 0.3,
+          "normal": torch.nn.functional.normalize(rnd(R, 3) - 0.5, dim=1), "normal_mask": rnd(R) > 0.5,
+          "mask": (rnd(R, 1) > 0.5).float(), "light_mask": (rnd(R, 1) > 0.8).float()}
+    fn = net.I2SDFLoss(**LOSS_ALL_KW)
+    arrays = {}
+    arrays.update(np_dict(out, "out_"))
+    arrays.update(np_dict(gt, "gt_"))
+    for step in (5, 100):
+        leaves = {k: v.clone().requires_grad_(True) for k, v in out.items()}
+        res = fn(leaves, gt, step)
+        res["loss"].backward()
+        arrays.update(np_dict({k: v.detach() for k, v in res.items()}, f"ref{step}_"))
+        arrays.update(np_dict({k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}, f"refgrad{step}_"))
+        o_loss = orc.recon_loss(out, gt, smooth_active=step > LOSS_ALL_KW["smooth_iter"],
+                                **{k: v for k, v in LOSS_ALL_KW.items() if k != "smooth_iter"})
+        print(f"   [{case}] step {step}: reference loss {res['loss'].item():.7f} oracle {o_loss.item():.7f}")
+        assert abs(o_loss.item() - res["loss"].item()) < 1e-6 * abs(res["loss"].item())
+    np.savez_compressed(os.path.join(HERE, f"{case}.npz"), **arrays)
+
+
 if __name__ == "__main__":
+    if "--only-loss" in sys.argv:             # adds the all-terms loss fixture without rewriting the others
+        loss_case()
+        sys.exit(0)
     if "--only-uniform" in sys.argv:          # adds the C1 fixture without rewriting the others (same weights: asserted)
         Pu = uniform_case("eval_uniform_c1", "synthetic", "synthetic", beta=0.05, R=48, perturb=0.06, seed=6)
         w = np.load(os.path.join(HERE, "weights_synthetic.npz"))
@@ -305,4 +344,5 @@ if __name__ == "__main__":
     assert all(torch.equal(P5[k], Pl[k]) for k in Pl)
     Pu = uniform_case("eval_uniform_c1", "synthetic", "synthetic", beta=0.05, R=48, perturb=0.06, seed=6)
     assert all(torch.equal(Pu[k], Pw[k]) for k in Pw)
+    loss_case()
     print("golden fixtures written to", HERE)
