@@ -102,3 +102,16 @@ def test_loss_all_terms_matches_reference():
         for k, g in refgrad.items():
             got = leaves[k].grad if leaves[k].grad is not None else torch.zeros_like(leaves[k])
             assert relerr(got, g) < 1e-5 or float(g.abs().max()) == 0.0 == float(got.abs().max()), (step, k)
+
+
+@pytest.mark.parametrize("name", ["eval_synthetic_soft", "eval_light_sharp"])
+def test_oracle_predict_only_returns_the_early_dict(name):
+    """forward(input, predict_only=True) returns before the normals / training extras (network/__init__.py:156-173): rgb, depth,
+    weight_sum (+ light_mask) only, same values as the full call."""
+    c = Case(name)
+    with torch.no_grad():
+        out = orc.render(c.spec, c.params, c.inputs, training=False, predict_only=True)
+    want = {"rgb_values", "depth_values", "weight_sum"} | ({"light_mask"} if c.spec.light_dims else set())
+    assert set(out) == want
+    for k in want:
+        assert relerr(out[k], c.ref[k]) < 2e-5, k
