@@ -200,3 +200,32 @@ def test_c_abi_from_plain_c(tmp_path):
         assert " rc 0 " in lines["create_ok"] and lines["destroy"].endswith("rc 0")
     else:
         assert " rc -3 " in lines["create_nogpu"] and "handle null" in lines["create_nogpu"]  # I2SDF_E_NOGPU
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under i2sdf_b200/ may import it (statically: every import statement of every
+    module; dynamically: importing the whole package in a fresh interpreter leaves no `oracle*` module loaded), and the C sources
+    do not mention it either."""
+    import ast
+    import subprocess
+    import sys
+    pkg = os.path.join(ROOT, "i2sdf_b200")
+    mods = [f for f in os.listdir(pkg) if f.endswith(".py")]
+    assert len(mods) >= 8
+    for f in mods:
+        tree = ast.parse(open(os.path.join(pkg, f)).read())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            assert not any(n == "oracle" or n.startswith("oracle.") for n in names), (f, names)
+    code = ("import sys, importlib; sys.path.insert(0, %r);\n"
+            "[importlib.import_module('i2sdf_b200.' + m) for m in %r];\n"
+            "bad = [m for m in sys.modules if m == 'oracle' or m.startswith('oracle.')]; print('LOADED', bad)") % (ROOT, [m[:-3] for m in mods if m != "__init__.py"])
+    r = subprocess.run([sys.executable, "-c", code], check=True, capture_output=True, text=True, timeout=300)
+    assert "LOADED []" in r.stdout, r.stdout
+    for f in os.listdir(os.path.join(pkg, "csrc")):
+        if f.endswith((".cu", ".cuh")):
+            assert "oracle" not in open(os.path.join(pkg, "csrc", f)).read().lower(), f
