@@ -15,3 +15,5 @@ done
 echo "=================== kernel times (tools/quick_bench.py): 8-column items (default) and 16-column items"
 timeout 120 python tools/quick_bench.py 2>/dev/null | head -3
 I2SDF_SDF16=1 timeout 120 python tools/quick_bench.py 2>/dev/null | head -3
+echo "=================== stand-alone k-step probe (tools/probe_kstep.cu): MMA pace / epilogue pace per traffic source"
+bash tools/build_probe.sh >/dev/null 2>&1 && timeout 120 ./tools/probe_kstep
