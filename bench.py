@@ -96,6 +96,12 @@ def pick_cpu_threads(run_once):
     return best
 
 
+# The CPU arms time the oracle PORT (the reference tree does not exist on the GPU box).  Port vs the unmodified reference, same inputs,
+# same 8 threads, measured in the build container where both run: eval render 0.98x, training step 0.76x the
+# reference's speed (the port's explicit reverse sweep makes a longer double-backward graph than autograd.grad(create_graph=True)).
+PORT_VS_REFERENCE = {"render": 0.98, "train": 0.76}
+
+
 def cpu_arm(conf, model, rays, steps, warmup):
     from oracle import i2sdf_oracle as orc
     spec = orc.spec_from_model_conf(conf, use_normal=False)
@@ -117,7 +123,8 @@ def cpu_arm(conf, model, rays, steps, warmup):
                 cores=torch.get_num_threads(),
                 sample=f"{rays} of the 1024 rays per step (same weights, same ray distribution), eval forward, "
                        f"{len(times)} steps after {warmup} warm-up, torch CPU fp32, best of 8/16/32/64/all host threads "
-                       f"(picked {torch.get_num_threads()} of {os.cpu_count()})")
+                       f"(picked {torch.get_num_threads()} of {os.cpu_count()}); oracle port = {PORT_VS_REFERENCE['render']}x the unmodified "
+                       f"reference's speed where both run (build container)")
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -245,7 +252,8 @@ def cpu_train_arm(conf, model, rays, steps, warmup, name="synthetic"):
     return dict(value=rays * N_COMPOSITED * len(times) / total, ms_per_step=1e3 * total / len(times), cores=torch.get_num_threads(),
                 sample=f"{rays} of the 1024 rays per step, full training step (forward + loss + backward; no optimizer), "
                        f"{len(times)} steps after {warmup} warm-up, torch CPU fp32, best of 8/16/32/64/all host threads "
-                       f"(picked {torch.get_num_threads()} of {os.cpu_count()})")
+                       f"(picked {torch.get_num_threads()} of {os.cpu_count()}); oracle port = {PORT_VS_REFERENCE['train']}x the unmodified "
+                       f"reference's speed where both run (build container)")
 
 
 def gpu_arm(args, rank, world, local_rank):
