@@ -776,3 +776,29 @@ def test_one_launch_adam_matches_torch_adam():
     ob.load_state_dict(oa.state_dict())              # same keys / shapes
     for pa, pb in zip(ma.parameters(), mb.parameters()):
         assert torch.equal(oa.state[pa]["exp_avg_sq"], ob.state[pb]["exp_avg_sq"])
+
+
+def test_full_size_batch_properties(cases):
+    """BASELINE.json's batch (1024 rays, W-sharp weights: all sampler rounds run) through the size-independent properties of the path:
+    98 sorted samples per ray inside [near, far], compositing weights that sum to at most 1, colours inside the sigmoid's range,
+    non-negative depths bounded by far, and a second call that reproduces the first bit for bit."""
+    c = cases["eval_synthetic_sharp"]
+    m = _model(c)
+    core = m._ready_core()
+    R = 1024
+    inp = {k: v.cuda() for k, v in orc.synthetic_rays(R, seed=1).items()}
+    o, d, _ = core.rays(inp["uv"], inp["pose"], inp["intrinsics"])
+    z = core.sample(o, d, m.density.beta.detach())[0]
+    assert z.shape == (R, 98) and bool(torch.isfinite(z).all())
+    assert bool((z[:, 1:] >= z[:, :-1]).all())                                   # sorted (ray_sampler.py:226-230)
+    assert float(z.min()) >= 0.0 and float(z.max()) <= c.spec.far + 1e-6
+    out = m(inp)
+    assert out["rgb_values"].shape == (R, 3) and out["depth_values"].shape == (R,) and out["weight_sum"].shape == (R, 1)
+    for k in ("rgb_values", "depth_values", "weight_sum"):
+        assert bool(torch.isfinite(out[k]).all()), k
+    assert float(out["weight_sum"].min()) >= -1e-6 and float(out["weight_sum"].max()) <= 1.0 + 1e-4
+    assert float(out["rgb_values"].min()) >= 0.0 and float(out["rgb_values"].max()) <= 1.0 + 1e-4
+    assert float(out["depth_values"].min()) >= 0.0 and float(out["depth_values"].max()) <= c.spec.far + 1e-3
+    assert float(out["weight_sum"].max()) > 0.9                                  # the batch does see the surface
+    again = m(inp)
+    assert all(torch.equal(again[k], out[k]) for k in ("rgb_values", "depth_values", "weight_sum"))
