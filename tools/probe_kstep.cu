@@ -30,6 +30,8 @@ struct Args {
     const uint8_t* w;     // 16 blocks of 16 KB (one layer's worth of packed weights; contents irrelevant)
     long long* out;       // [grid][4]: issue clocks, issue + drain clocks, epilogue clocks, -
     int nops, nmma, stream, epi;
+    int issue;            // 0: the product's loop; 1: unrolled over the 4 ring stages (compile-time stage / descriptor offsets), no tcgen05 fence after the
+                          //    weight barrier (the weights arrive through the async proxy; the fence is only needed behind the a_ready waits)
 };
 
 __device__ __forceinline__ void tmem_ld8p(uint32_t taddr, uint32_t (&v)[8]) {
@@ -89,23 +91,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) probe(const Args a) {
         const uint32_t lo_off = 256u * 32u;
         uint32_t stage = 0, phase = 0;
         const long long t0 = clock64();
-        for (int op = 0; op < a.nops; ++op) {
-            const uint32_t d_tmem = tmem_base + (uint32_t)(op & 1) * 256u;
-            for (int ks = 0; ks < 16; ++ks) {
-                mbar_wait(&full[stage], phase);
-                tc_fence_after();
-                const uint64_t da_hi = dA_hi0 + (uint64_t)(((uint32_t)ks * 2u * LBO_A) >> 4);
-                const uint64_t da_lo = dA_lo0 + (uint64_t)(((uint32_t)ks * 2u * LBO_A) >> 4);
-                const uint64_t db_hi = dB0 + (uint64_t)((stage * (uint32_t)STAGE) >> 4);
-                const uint64_t db_lo = db_hi + (uint64_t)(lo_off >> 4);
-                if (elect_one_sync()) {
-                    mma_bf16_ss(d_tmem, da_hi, db_hi, idesc, ks > 0 ? 1u : 0u);
-                    if (a.nmma > 1) mma_bf16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
-                    if (a.nmma > 2) mma_bf16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
-                    mma_commit(&empty[stage]);
+        if (a.issue == 0) {
+            for (int op = 0; op < a.nops; ++op) {
+                const uint32_t d_tmem = tmem_base + (uint32_t)(op & 1) * 256u;
+                for (int ks = 0; ks < 16; ++ks) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da_hi = dA_hi0 + (uint64_t)(((uint32_t)ks * 2u * LBO_A) >> 4);
+                    const uint64_t da_lo = dA_lo0 + (uint64_t)(((uint32_t)ks * 2u * LBO_A) >> 4);
+                    const uint64_t db_hi = dB0 + (uint64_t)((stage * (uint32_t)STAGE) >> 4);
+                    const uint64_t db_lo = db_hi + (uint64_t)(lo_off >> 4);
+                    if (elect_one_sync()) {
+                        mma_bf16_ss(d_tmem, da_hi, db_hi, idesc, ks > 0 ? 1u : 0u);
+                        if (a.nmma > 1) mma_bf16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
+                        if (a.nmma > 2) mma_bf16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
+                        mma_commit(&empty[stage]);
+                    }
+                    __syncwarp();
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+        } else {
+            // 16 k steps = 4 passes over the 4-stage ring: the stage (barrier addresses, B descriptors) is a compile-time constant and
+            // the A descriptors advance by a constant per k step
+            for (int op = 0; op < a.nops; ++op) {
+                const uint32_t d_tmem = tmem_base + (uint32_t)(op & 1) * 256u;
+                uint64_t da_hi = dA_hi0, da_lo = dA_lo0;
+#pragma unroll 1
+                for (int pass = 0; pass < 4; ++pass) {
+#pragma unroll
+                    for (int st = 0; st < NSTAGE; ++st) {
+                        mbar_wait(&full[st], phase);
+                        const uint64_t db_hi = dB0 + (uint64_t)(((uint32_t)st * (uint32_t)STAGE) >> 4);
+                        const uint64_t db_lo = db_hi + (uint64_t)(lo_off >> 4);
+                        if (elect_one_sync()) {
+                            mma_bf16_ss(d_tmem, da_hi, db_hi, idesc, (pass | st) ? 1u : 0u);
+                            if (a.nmma > 1) mma_bf16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
+                            if (a.nmma > 2) mma_bf16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
+                            mma_commit(&empty[st]);
+                        }
+                        __syncwarp();
+                        da_hi += (uint64_t)((2u * LBO_A) >> 4);
+                        da_lo += (uint64_t)((2u * LBO_A) >> 4);
+                    }
+                    phase ^= 1;
+                }
             }
         }
         const long long t1 = clock64();
@@ -170,11 +200,12 @@ int main(int argc, char** argv) {
     CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
     std::vector<long long> h(4 * grid);
     printf("grid %d CTAs, %d ops x 16 k steps per CTA; clocks per k step (median over CTAs)\n", grid, nops);
-    printf("nmma stream epi |  issue loop   issue+drain   epilogue per op\n");
+    printf("issue nmma stream epi |  issue loop   issue+drain   epilogue per op\n");
+    for (int issue = 0; issue < 2; ++issue)
     for (int epi = 0; epi < 3; ++epi)
         for (int stream = 0; stream < 2; ++stream)
             for (int nmma = 1; nmma <= 3; ++nmma) {
-                Args a{w, out, nops, nmma, stream, epi};
+                Args a{w, out, nops, nmma, stream, epi, issue};
                 for (int rep = 0; rep < 2; ++rep) {            // second launch is the measurement (weights L2-resident)
                     CK(cudaMemset(out, 0, sizeof(long long) * 4 * grid));
                     probe<<<grid, NTHREADS, kSmem>>>(a);
@@ -186,7 +217,7 @@ int main(int argc, char** argv) {
                 for (int b = 0; b < grid; ++b) { c0.push_back(h[b * 4]); c1.push_back(h[b * 4 + 1]); c2.push_back(h[b * 4 + 2]); }
                 auto med = [](std::vector<long long>& v) { std::sort(v.begin(), v.end()); return (double)v[v.size() / 2]; };
                 const double ks = (double)nops * 16.0;
-                printf("  %d     %d     %d  |  %9.1f   %9.1f   %12.1f\n", nmma, stream, epi, med(c0) / ks, med(c1) / ks, med(c2) / (double)nops);
+                printf("  %d     %d     %d     %d  |  %9.1f   %9.1f   %12.1f\n", issue, nmma, stream, epi, med(c0) / ks, med(c1) / ks, med(c2) / (double)nops);
             }
     cudaFree(w);
     cudaFree(out);
