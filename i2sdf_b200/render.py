@@ -24,8 +24,14 @@ def pixel_grid(img_res: Sequence[int], device=None) -> torch.Tensor:
 
 @torch.no_grad()
 def render_image(model, pose: torch.Tensor, intrinsics: torch.Tensor, img_res: Sequence[int], split_n_pixels: int = 65536,
-                 predict_only: bool = False) -> Dict[str, torch.Tensor]:
-    """Render one full view.  pose, intrinsics: [4,4] (or [1,4,4]).  Returns {key: [H*W, C]} like merge_output."""
+                 predict_only: bool = False, group=None, assemble: bool = True) -> Dict[str, torch.Tensor]:
+    """Render one full view.  pose, intrinsics: [4,4] (or [1,4,4]).  Returns {key: [H*W, C]} like merge_output.
+
+    group (torch.distributed process group): the view's chunks are dealt to the ranks round-robin — chunk i of the single-GPU
+    loop goes to rank i % world, so every chunk is the SAME set of rays as without sharding and (the sampler's convergence test
+    being global per forward call, ray_sampler.py:151) renders to the same bits.  No collective on the data path (SURVEY.md
+    §8(e): inference has none); with `assemble` the ranks' disjoint pieces are summed into the full image on every rank by one
+    all-reduce per output key at the end, otherwise each rank returns its own chunks and zeros elsewhere."""
     if model.training:
         raise RuntimeError("render_image is an inference driver: call model.eval() first")
     dev = model.density.beta.device
@@ -33,6 +39,8 @@ def render_image(model, pose: torch.Tensor, intrinsics: torch.Tensor, img_res: S
     total = uv.shape[0]
     pose = pose.reshape(1, 4, 4).to(dev).float()
     intrinsics = intrinsics.reshape(1, 4, 4).to(dev).float()
+    if group is not None:
+        return _render_image_sharded(model, uv, pose, intrinsics, split_n_pixels, predict_only, group, assemble)
     out: Dict[str, torch.Tensor] = {}
     for lo in range(0, total, split_n_pixels):
         hi = min(lo + split_n_pixels, total)
@@ -42,4 +50,30 @@ def render_image(model, pose: torch.Tensor, intrinsics: torch.Tensor, img_res: S
             if k not in out:
                 out[k] = torch.empty(total, v2.shape[1], device=dev, dtype=v2.dtype)
             out[k][lo:hi] = v2
+    return out
+
+
+def _render_image_sharded(model, uv, pose, intrinsics, split_n_pixels, predict_only, group, assemble):
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev, total = uv.device, uv.shape[0]
+    out: Dict[str, torch.Tensor] = {}
+    for i, lo in enumerate(range(0, total, split_n_pixels)):
+        if i % world != rank:
+            continue
+        hi = min(lo + split_n_pixels, total)
+        res = model({"uv": uv[None, lo:hi], "pose": pose, "intrinsics": intrinsics}, predict_only=predict_only)
+        for k, v in res.items():
+            v2 = v.reshape(hi - lo, -1)
+            if k not in out:
+                out[k] = torch.zeros(total, v2.shape[1], device=dev, dtype=v2.dtype)
+            out[k][lo:hi] = v2
+    if assemble and world > 1:
+        # a rank with no chunk (more ranks than chunks) learns keys / widths / dtypes from rank 0, which always owns chunk 0
+        meta = [[(k, v.shape[1], str(v.dtype).replace("torch.", "")) for k, v in sorted(out.items())] if rank == 0 else None]
+        dist.broadcast_object_list(meta, src=dist.get_global_rank(group, 0), group=group)
+        for k, width, dt in meta[0]:
+            if k not in out:
+                out[k] = torch.zeros(total, width, device=dev, dtype=getattr(torch, dt))
+            dist.all_reduce(out[k], op=dist.ReduceOp.SUM, group=group)       # disjoint pieces + zeros: the sum is exact
     return out

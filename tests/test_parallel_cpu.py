@@ -157,3 +157,74 @@ def test_seed_rank_streams():
     b = torch.rand(4)
     seed_rank(42, 3)
     assert torch.equal(b, torch.rand(4)) and not torch.equal(a, b)
+
+
+# ---- sharded whole-image render (inference: chunks dealt to ranks, no data-path collective) -------------------------------------
+class _FakeEvalModel:
+    """Stands in for I2SDFNetwork(eval) on the CPU: per-ray outputs that depend on the ray AND on the whole chunk (like the
+    sampler's batch-global convergence test), so a different chunking would change the result."""
+    training = False
+
+    class density:                      # noqa: N801  (attribute path model.density.beta.device)
+        beta = torch.zeros(())
+
+    def __call__(self, inp, predict_only=False):
+        uv = inp["uv"][0]
+        chunk_stat = uv.sum() * 1e-3
+        rgb = torch.stack([uv[:, 0], uv[:, 1], uv[:, 0] * 0 + chunk_stat], -1) + float(inp["pose"][0, 0, 3])
+        out = {"rgb_values": rgb, "depth_values": uv[:, 0] + uv[:, 1], "weight_sum": (uv[:, :1] > 2).float()}
+        if not predict_only:
+            out["normal_map"] = rgb * 0.5
+        return out
+
+
+def _render_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from i2sdf_b200.render import render_image
+    pose = torch.eye(4)
+    pose[0, 3] = 0.25
+    res = {}
+    for name, res_hw, split in (("five_chunks", (7, 9), 13), ("one_chunk", (3, 4), 100)):
+        full = render_image(_FakeEvalModel(), pose, torch.eye(4), res_hw, split_n_pixels=split, group=dist.group.WORLD)
+        own = render_image(_FakeEvalModel(), pose, torch.eye(4), res_hw, split_n_pixels=split, group=dist.group.WORLD, assemble=False)
+        res[name] = ({k: v.numpy().copy() for k, v in full.items()}, {k: v.numpy().copy() for k, v in own.items()})
+    q.put((rank, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_render_image_equals_the_single_process_image():
+    import numpy as np
+    from i2sdf_b200.render import render_image
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_render_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    pose = torch.eye(4)
+    pose[0, 3] = 0.25
+    for name, res_hw, split in (("five_chunks", (7, 9), 13), ("one_chunk", (3, 4), 100)):
+        single = render_image(_FakeEvalModel(), pose, torch.eye(4), res_hw, split_n_pixels=split)
+        for rank in range(world):
+            full, own = res[rank][name]
+            assert set(full) == set(single)
+            for k, v in single.items():
+                assert np.array_equal(full[k], v.numpy()), (name, rank, k)          # every rank holds the single-process image, bit for bit
+        # without assembly: the ranks' pieces are disjoint and together cover the image
+        total = res_hw[0] * res_hw[1]
+        owner = np.arange(total) // split % world
+        for k, v in single.items():
+            for rank in range(world):
+                own = res[rank][name][1]
+                if k in own:
+                    assert np.array_equal(own[k][owner == rank], v.numpy()[owner == rank]) and not own[k][owner != rank].any()
+                else:
+                    assert not (owner == rank).any()
