@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const BwdParams P, 
                     const float jac = (i < net.ex) ? embed_jac(x, i, net.mx, coord) : 0.f;
                     hv[j] = jac * (coord == 0 ? gb[0] : (coord == 1 ? gb[1] : gb[2]));
                 }
-                store_a16(A_hi, A_lo, row, sub * 2, hv, SL.wbase + SL.ED() + planes::seg(tile * TM + row, sub * 2, planes::SMALL_CHUNKS),
+                store_a16<false>(A_hi, A_lo, row, sub * 2, hv, SL.wbase + SL.ED() + planes::seg(tile * TM + row, sub * 2, planes::SMALL_CHUNKS),
                           (uint32_t)planes::SMALL_PLANE);
             }
             publish_chunk(&a_ready[sub >> 1], lane);
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const BwdParams P, 
                             hv[j] = t;
                         }
                         const bool more = (l < NL - 1);
-                        store_a16(A_hi, A_lo, row, kc0, hv, SL.wbase + SL.HD(l) + sg, (uint32_t)planes::BIG_PLANE, true, more);
+                        store_a16<false>(A_hi, A_lo, row, kc0, hv, SL.wbase + SL.HD(l) + sg, (uint32_t)planes::BIG_PLANE, true, more);
                         if (!more) {
                             // the tangent pass is over and its last MMAs are done: build the A operand of the reverse pass
                             if (color) {
@@ -210,11 +210,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const BwdParams P, 
                                     const float u = fmaf(delta[0], __ldg(wh + j), fmaf(delta[1], __ldg(wh + 256 + j), delta[2] * __ldg(wh + 512 + j)));
                                     hv[j] = cv > 0.f ? u : 0.f;
                                 }
-                                store_a16(A_hi, A_lo, row, kc0, hv, SL.wbase + SL.PC(net.Lc - 2) + sg, (uint32_t)planes::BIG_PLANE, valid);
+                                store_a16<false>(A_hi, A_lo, row, kc0, hv, SL.wbase + SL.PC(net.Lc - 2) + sg, (uint32_t)planes::BIG_PLANE, valid);
                             } else {
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) hv[j] = 0.f;     // no radiance stack: fbar = 0
-                                store_a16(A_hi, A_lo, row, kc0, hv);
+                                store_a16<false>(A_hi, A_lo, row, kc0, hv);
                             }
                         }
                         publish_chunk(&a_ready[c], lane);
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const BwdParams P, 
                             const float cv = (j & 1) ? __uint_as_float(cw[j >> 1] & 0xffff0000u) : __uint_as_float(cw[j >> 1] << 16);
                             hv[j] = cv > 0.f ? __uint_as_float(v[j]) : 0.f;
                         }
-                        store_a16(A_hi, A_lo, row, kc0, hv, SL.wbase + SL.PC(l - 1) + sg, (uint32_t)planes::BIG_PLANE, valid);
+                        store_a16<false>(A_hi, A_lo, row, kc0, hv, SL.wbase + SL.PC(l - 1) + sg, (uint32_t)planes::BIG_PLANE, valid);
                         publish_chunk(&a_ready[c], lane);
                     } else if (kind == BK_FEAT_ADJ) {
                         // accumulator = adjoint of the features
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const BwdParams P, 
                         float hv[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) hv[j] = __uint_as_float(v[j]);
-                        store_a16(A_hi, A_lo, row, kc0, hv, SL.wbase + SL.FB() + sg, (uint32_t)planes::BIG_PLANE, valid);
+                        store_a16<false>(A_hi, A_lo, row, kc0, hv, SL.wbase + SL.FB() + sg, (uint32_t)planes::BIG_PLANE, valid);
                         publish_chunk(&a_ready[c], lane);
                     } else {
                         // BK_P: accumulator = W_{l+1}^T p_{l+1} ; produce p_l (l = op.layer), 8 columns at a time
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const BwdParams P, 
                                 if (feeds_skip && f >= nsplit) p = 0.f;
                                 pv[j] = p;
                             }
-                            store_a8(A_hi, A_lo, row, kc0 + s, pv, SL.wbase + SL.P(l) + sg8, valid, !last_op);
+                            store_a8<false>(A_hi, A_lo, row, kc0 + s, pv, SL.wbase + SL.P(l) + sg8, valid, !last_op);
                         }
                         if (!last_op) publish_chunk(&a_ready[c], lane);
                     }

@@ -8,6 +8,7 @@
 //   One MMA (K=16) consumes two k chunks: its descriptor starts at chunk 2*kstep.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -110,6 +111,11 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 __host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// same with A/B = fp16 (a_format = b_format = 0).  The two 16-bit formats cannot be mixed in one instruction: A bf16 x B fp16 raises
+// "illegal instruction" on the B200 (tools/probe_fmt.cu), although the descriptor has independent format fields.
+__host__ __device__ constexpr uint32_t instr_desc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
 __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -139,6 +145,30 @@ __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, u
     hi = *reinterpret_cast<uint32_t*>(&h);
     lo = *reinterpret_cast<uint32_t*>(&l);
 }
+
+// split fp32 into fp16 hi + fp16 lo (11 + 11 mantissa bits; the low half of a small value is an fp16 subnormal, absolute error
+// <= 2^-25): with 3 products and fp32 accumulation in TMEM a K = 256 layer is as accurate as an fp32 FMA chain (measured on the
+// B200, tools/probe_fmt.cu: max error 1.1e-6 of max|D| against 7.0e-7 for the FMA chain and 5.9e-6 for the bf16 split).
+// satfinite: a value beyond fp16's range (|x| > 65504) saturates instead of turning the whole tile into NaNs.
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    uint32_t h, l;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(x1 - hf.y), "f"(x0 - hf.x));
+    hi = h;
+    lo = l;
+}
+// value pair of one 32-bit word of a hi plane + the same word of the lo plane
+__device__ __forceinline__ float2 join_f16x2(uint32_t hi, uint32_t lo) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hi)), b = __half22float2(*reinterpret_cast<const __half2*>(&lo));
+    return make_float2(a.x + b.x, a.y + b.y);
+}
+__device__ __forceinline__ float2 join_bf16x2(uint32_t hi, uint32_t lo) {
+    return make_float2(__uint_as_float(hi << 16) + __uint_as_float(lo << 16), __uint_as_float(hi & 0xffff0000u) + __uint_as_float(lo & 0xffff0000u));
+}
+// The fp16 weight blocks hold W * kWScale (a power of two: exact), so that the low halves of typical weights (|W| ~ 0.05) are
+// normal fp16 numbers; the accumulator is multiplied by kWInv in the epilogue (folded into the bias add: one FFMA).
+constexpr float kWScale = 256.0f, kWInv = 1.0f / 256.0f;
 
 // softplus_100 in the overflow-free form max(a,0) + log1p(exp(-|100 a|))/100; equals nn.Softplus(beta=100,
 // threshold=20) to < 3e-11 absolute (the thresholded branch differs from the exact value by log1p(e^-20)/100).
