@@ -401,8 +401,8 @@ int i2sdf_sdf_forward(i2sdf_handle* h, const float* pts, int64_t M, float* out_s
         if (!workspace || workspace_bytes < ws_scratch_floats(h) * sizeof(float)) { set_error("sdf_forward: workspace too small"); return I2SDF_E_WORKSPACE; }
         p.scratch = (float*)workspace;
     }
-    // development probe: the sdf-only tensor-core kernel stamps its hand-offs into the first 16 KB of the workspace
-    if (!out_grad && !out_feat && !save_act && workspace && workspace_bytes >= 16384 && getenv("I2SDF_DEBUG_TIMELINE")) p.scratch = (float*)workspace;
+    // development probe: the sdf-only tensor-core kernel stamps its hand-offs into the first 64 KB of the workspace
+    if (!out_grad && !out_feat && !save_act && workspace && workspace_bytes >= 65536 && getenv("I2SDF_DEBUG_TIMELINE")) p.scratch = (float*)workspace;
     p.net = h->net;
     return run_mlp(h, p, (cudaStream_t)stream);
 }

@@ -383,17 +383,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
 }
 
 // ---- sdf-only chain with 8-column work items (the sampler's kernel) ---------------------------------------------------------
-// Same chain as tc_mlp_kernel<false>, but an epilogue work item is 32 rows x 8 columns: in every iteration all 16 epilogue warps
+// Same chain as the full kernel's F ops, but an epilogue work item is 32 rows x 8 columns: in every iteration all 16 epilogue warps
 // work on ONE 32-column chunk (4 lane quarters x 4 column groups), so the first chunk of the next A operand - and with it the MMA
-// chain of the next layer, which paces the op (tools/timeline.py) - is ready after 1/8 instead of 1/4 of the epilogue.
+// chain of the next layer - is ready after 1/8 of the epilogue.
+// Own shared-memory layout (K <= 256: 32 operand chunks): A_hi | A_lo | weight ring | PE stash | biases | partial heads | barriers.
+//   * PE stash [39][128] fp32: the positional encoding of the tile's points, written once by the tile's prologue and read by the
+//     layer that feeds the skip concat.  Round 2's timeline (tools/timeline.py) showed that op taking 14.8 k clocks against 8.4 k
+//     for the others: the concat re-evaluated a Cody-Waite sincos per element (if-converted, so for ALL 256 columns).
+//   * biases of all hidden layers, copied once per launch: LDS broadcast instead of two LDG.128 per item on the critical path
+//     between "accumulator complete" and "first chunk published".
+constexpr int S8_A_PART = 32 * TM * 16;                          // 65536
+constexpr int S8_PE_FLOATS = 40 * TM;                            // [ex <= 39][128]
+constexpr int S8_BIAS_FLOATS = (kMaxLayers - 1) * 256;
+constexpr size_t kSmemSdf8 = 1024 + 2 * (size_t)S8_A_PART + NSTAGE * STAGE_MAX + (S8_PE_FLOATS + S8_BIAS_FLOATS + 4 * TM) * 4 + 256;
+static_assert(kSmemSdf8 <= 232448, "sdf8 shared memory");
+
+// TL: development probe (I2SDF_DEBUG_TIMELINE=1, tools/timeline.py) - clock64 stamps of CTA 0's second tile into P.scratch:
+// epilogue warp w, op: tl[(op * 16 + w) * 4 + {0 waits for the accumulator, 1 sees it, 2 first chunk published, 3 last chunk published}]
+template <bool TL>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_sdf8_kernel(const MlpParams P, const OpTable T) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_align1024(smem_raw);
     uint8_t* A_hi = smem;
-    uint8_t* A_lo = smem + A_PART_BYTES;
-    uint8_t* ring = smem + 2 * A_PART_BYTES;
-    float* part = reinterpret_cast<float*>(ring + NSTAGE * STAGE_MAX);      // [4][7][TM]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(part + PART_FLOATS);
+    uint8_t* A_lo = smem + S8_A_PART;
+    uint8_t* ring = smem + 2 * S8_A_PART;
+    float* pe = reinterpret_cast<float*>(ring + NSTAGE * STAGE_MAX);        // [40][TM]
+    float* sbias = pe + S8_PE_FLOATS;                                        // [NL][256]
+    float* part = sbias + S8_BIAS_FLOATS;                                    // [4][TM]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(part + 4 * TM);
     uint64_t* full = bars;
     uint64_t* empty = bars + NSTAGE;
     uint64_t* a_ready = bars + 2 * NSTAGE;       // [N_READY], 16 arrivals each (every epilogue warp contributes to every chunk)
@@ -414,6 +431,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sdf8_kernel(const MlpParams P,
         mbar_init(&d_full[1], 1);
         fence_mbar_init();
     }
+    for (int i = tid; i < NL * 256; i += NTHREADS) sbias[i] = net.sdf_b[i >> 8][i & 255];
     if (warp == 1) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
@@ -423,7 +441,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sdf8_kernel(const MlpParams P,
     if (warp == 0) {
         if (lane == 0) chain_producer(T, ntiles, ring, full, empty);
     } else if (warp == 1) {
-        chain_mma(T, ntiles, tmem_base, A_hi, A_lo, ring, full, empty, a_ready, d_full);
+        chain_mma<TL>(T, ntiles, tmem_base, A_hi, A_lo, ring, full, empty, a_ready, d_full, reinterpret_cast<long long*>(P.scratch));
     } else {
         const int q = warp & 3;
         const int sub = (warp - 2) >> 2;                     // column group: columns 8 sub .. 8 sub + 7 of every 32-column chunk
@@ -431,6 +449,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sdf8_kernel(const MlpParams P,
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const int nsplit = 256 - net.ex;
         const float RS2 = 0.70710678118654752f;
+        const float acc_scale = T.acc_scale;
         uint32_t dphase = 0, g = 0;
         auto load_point = [&](long long tile, float (&x)[3]) {
             const long long m = tile * TM + row;
@@ -446,7 +465,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sdf8_kernel(const MlpParams P,
                 }
             }
         };
-        // A_0 = embedding, 48 columns = k chunks 0..5: group sub writes chunk sub, groups 0 and 1 also chunks 4 and 5
+        // A_0 = embedding, 48 columns = k chunks 0..5: group sub writes chunk sub, groups 0 and 1 also chunks 4 and 5; every value
+        // also goes to the PE stash (the previous tile's skip layer is long done when this runs inside its last op)
         auto prologue = [&](const float (&x)[3]) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -454,7 +474,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sdf8_kernel(const MlpParams P,
                 if (kc < 6) {
                     float hv[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) { const int i = kc * 8 + j; hv[j] = (i < net.ex) ? embed_col(x, i, net.mx) : 0.f; }
+                    for (int j = 0; j < 8; ++j) {
+                        const int i = kc * 8 + j;
+                        hv[j] = (i < net.ex) ? embed_col(x, i, net.mx) : 0.f;
+                        if (i < 40) pe[i * TM + row] = hv[j];
+                    }
                     store_a8<true>(A_hi, A_lo, row, kc, hv, nullptr, true, true);
                 }
             }
@@ -468,20 +492,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sdf8_kernel(const MlpParams P,
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const long long m = tile * TM + row;
             const long long next_tile = tile + gridDim.x;
-            float xn[3] = {0.f, 0.f, 0.f};
             float head = 0.f;
             for (int op = 0; op < T.nops; ++op, ++g) {
                 const uint32_t b = g & 1u;
                 const int l = T.ops[op].layer;
                 const bool last = (T.ops[op].kind == EK_SDF_LAST);
+                const float* __restrict__ bias = sbias + l * 256 + sub * 8;
+                long long* tlw = (TL && P.scratch && lane == 0 && blockIdx.x == 0 && tile == (long long)gridDim.x)
+                                     ? reinterpret_cast<long long*>(P.scratch) + (op * 16 + (warp - 2)) * 4 : nullptr;
+                if (TL && tlw) tlw[0] = clock64();
                 mbar_wait(&d_full[b], (dphase >> b) & 1u);
                 dphase ^= (1u << b);
                 tc_fence_after();
-                if (op == T.nops - 1 && next_tile < ntiles) {      // the A operand is free: start the next tile's first layer now
-                    load_point(next_tile, xn);
-                    prologue(xn);
-                }
-                const float* __restrict__ bias = net.sdf_b[l] + sub * 8;
+                if (TL && tlw) tlw[1] = clock64();
                 // one work item = 32 rows x 8 columns; three specialisations of the item loop so that the common one carries neither the
                 // head dot (last layer) nor the skip concat (mode: 0 hidden layer, 1 hidden layer feeding the skip concat, 2 last)
                 auto items = [&](auto mode_c) {
@@ -489,15 +512,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sdf8_kernel(const MlpParams P,
 #pragma unroll 2
                     for (int it = 0; it < 8; ++it) {
                         const int col0 = it * 32 + sub * 8;
-                        const float4 b0 = *reinterpret_cast<const float4*>(bias + it * 32), b1 = *reinterpret_cast<const float4*>(bias + it * 32 + 4);
                         uint32_t v[8];
                         tmem_ld8(tmem_base + lane_base + b * 256u + (uint32_t)col0, v);
+                        const float4 b0 = *reinterpret_cast<const float4*>(bias + it * 32), b1 = *reinterpret_cast<const float4*>(bias + it * 32 + 4);
                         tmem_ld_wait();
                         const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                         float hv[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float a = fmaf(__uint_as_float(v[j]), T.acc_scale, bv[j]);
+                            const float a = fmaf(__uint_as_float(v[j]), acc_scale, bv[j]);
                             const float e = ex2_approx(-fabsf(a) * 144.26950408889634f);          // exp(-|100 a|)
                             hv[j] = fmaf(lg2_approx(1.0f + e), 0.0069314718055994531f, fmaxf(a, 0.0f));
                         }
@@ -508,28 +531,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sdf8_kernel(const MlpParams P,
                             continue;
                         }
                         if (MODE == 1) {                           // cat([h, embed]) / sqrt(2)   (mlp.py:94-95)
+                            if (col0 + 8 > nsplit) {               // warp-uniform: only the items that reach into the embedding part
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const int f = col0 + j;
-                                hv[j] = ((f >= nsplit) ? embed_col(x, f - nsplit, net.mx) : hv[j]) * RS2;
+                                for (int j = 0; j < 8; ++j) {
+                                    const int f = col0 + j;
+                                    if (f >= nsplit) hv[j] = pe[(f - nsplit) * TM + row];
+                                }
                             }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) hv[j] *= RS2;
                         }
                         store_a8<true>(A_hi, A_lo, row, col0 >> 3, hv, nullptr, true, true);
                         publish_chunk(&a_ready[it], lane);
+                        if (TL && tlw && it == 0) tlw[2] = clock64();
                     }
+                    if (TL && tlw) tlw[3] = clock64();
                 };
-                if (last) items(std::integral_constant<int, 2>{});
-                else if (l + 1 == net.skip) items(std::integral_constant<int, 1>{});
+                if (last) {
+                    if (next_tile < ntiles) {      // the A operand is free (this tile's last MMAs are done): start the next tile's first layer now
+                        load_point(next_tile, x);
+                        prologue(x);
+                    }
+                    items(std::integral_constant<int, 2>{});
+                } else if (l + 1 == net.skip) items(std::integral_constant<int, 1>{});
                 else items(std::integral_constant<int, 0>{});
             }
             // ---- combine the 4 column-group partials of every row
-            part[(size_t)sub * 7 * TM + row] = head;
+            part[sub * TM + row] = head;
             epi_bar_sync();
             if (sub == 0 && m < P.M)
-                P.out_sdf[m] = (part[row] + part[7 * TM + row]) + (part[14 * TM + row] + part[21 * TM + row]) + __ldg(net.sdf_head + 256);
+                P.out_sdf[m] = (part[row] + part[TM + row]) + (part[2 * TM + row] + part[3 * TM + row]) + __ldg(net.sdf_head + 256);
             epi_bar_sync();
-#pragma unroll
-            for (int c = 0; c < 3; ++c) x[c] = xn[c];
         }
     }
     tc_fence_before();
@@ -684,7 +716,8 @@ int tc_create(i2sdf_handle* h) {
         for (int l = NL - 1; l >= 1; --l) push(s->blk_rev_sdf[l], tcb::BK_P, l - 1);
         if (variant == 0 && !want_full) B.nops = 0;
     }
-    cudaError_t e = cudaFuncSetAttribute(tc_sdf8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(tc_sdf8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSdf8);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_sdf8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSdf8);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_mlp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_mlp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) { cudaFree(s->wpack); delete s; set_error("tc_create: smem attribute: %s", cudaGetErrorString(e)); return I2SDF_E_CUDA; }
@@ -754,7 +787,10 @@ int tc_launch_sdf(const i2sdf_handle* h, const MlpParams& p, cudaStream_t st) {
     using namespace tc3;
     if (p.M <= 0) return I2SDF_OK;
     const State* s = (const State*)h->tc;
-    tc_sdf8_kernel<<<tc_grid(h, p.M), NTHREADS, kSmemBytes, st>>>(p, s->sdf);
+    static int tl = -1;
+    if (tl < 0) tl = getenv("I2SDF_DEBUG_TIMELINE") ? 1 : 0;
+    if (tl && p.scratch) tc_sdf8_kernel<true><<<tc_grid(h, p.M), NTHREADS, kSmemSdf8, st>>>(p, s->sdf);
+    else tc_sdf8_kernel<false><<<tc_grid(h, p.M), NTHREADS, kSmemSdf8, st>>>(p, s->sdf);
     I2SDF_CUDA_CHECK(cudaGetLastError());
     return I2SDF_OK;
 }

@@ -181,8 +181,11 @@ __device__ __forceinline__ void chain_producer(const OpTable& T, long long ntile
 // stages (barrier addresses and B descriptors become constants, the A descriptors advance by a constant) and without the
 // tcgen05 fence behind the weight barrier (the weights arrive through the async proxy; only the a_ready waits order generic-proxy
 // stores of the epilogue warps) it paces at the tensor pipe's 384.
+// TL (development probe, tools/timeline.py): clock64 stamps of CTA 0's second tile: tl[2048 + op * 32 + ks] = k step issued,
+// tl[4096 + op * 32 + ks] = A chunk of an even k step seen, tl[6144 + op] = accumulator committed.
+template <bool TL = false>
 __device__ __forceinline__ void chain_mma(const OpTable& T, long long ntiles, uint32_t tmem_base, uint8_t* A_hi, uint8_t* A_lo, uint8_t* ring,
-                                          uint64_t* full, uint64_t* empty, uint64_t* a_ready, uint64_t* d_full) {
+                                          uint64_t* full, uint64_t* empty, uint64_t* a_ready, uint64_t* d_full, long long* tl = nullptr) {
     const uint32_t a_hi_s = smem_u32(A_hi), a_lo_s = smem_u32(A_lo), ring_s = smem_u32(ring);
     const uint64_t dA_hi0 = smem_desc(a_hi_s, LBO_A, SBO), dA_lo0 = smem_desc(a_lo_s, LBO_A, SBO);
     constexpr uint64_t kStepA = (uint64_t)((2u * LBO_A) >> 4);
@@ -196,6 +199,7 @@ __device__ __forceinline__ void chain_mma(const OpTable& T, long long ntiles, ui
             const uint32_t d_tmem = tmem_base + (g & 1u) * 256u;
             const int nks = T.ops[op].ksteps;
             uint64_t da_hi = dA_hi0, da_lo = dA_lo0;
+            const bool rec = TL && tl && blockIdx.x == 0 && tile == (long long)gridDim.x && (threadIdx.x & 31) == 0;
 #pragma unroll 1
             for (int ks0 = 0; ks0 < nks; ks0 += NSTAGE) {
 #pragma unroll
@@ -207,6 +211,7 @@ __device__ __forceinline__ void chain_mma(const OpTable& T, long long ntiles, ui
                         mbar_wait(&a_ready[c], (aphase >> c) & 1u);
                         aphase ^= (1u << c);
                         tc_fence_after();
+                        if (TL && rec) tl[4096 + op * 32 + ks] = clock64();
                     }
                     mbar_wait(&full[st], phase);
                     const uint64_t db_hi = dB0 + (uint64_t)(((uint32_t)st * (uint32_t)STAGE_MAX) >> 4);
@@ -220,6 +225,7 @@ __device__ __forceinline__ void chain_mma(const OpTable& T, long long ntiles, ui
                         mma_commit(&empty[st]);
                     }
                     __syncwarp();
+                    if (TL && rec) tl[2048 + op * 32 + ks] = clock64();
                     da_hi += kStepA;
                     da_lo += kStepA;
                 }
@@ -227,6 +233,7 @@ __device__ __forceinline__ void chain_mma(const OpTable& T, long long ntiles, ui
             }
             if (elect_one_sync()) mma_commit(&d_full[g & 1u]);
             __syncwarp();
+            if (TL && rec) tl[6144 + op] = clock64();
         }
     }
 }

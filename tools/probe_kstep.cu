@@ -30,6 +30,8 @@ struct Args {
     const uint8_t* w;     // 16 blocks of 16 KB (one layer's worth of packed weights; contents irrelevant)
     long long* out;       // [grid][4]: issue clocks, issue + drain clocks, epilogue clocks, -
     int nops, nmma, stream, epi;
+    int half;             // 1 (with issue = 1): N = 128 MMAs, one ring stage = TWO k steps of one N half (6 MMAs = 384 tensor clocks per stage) - the
+                          //    N-split schedule (half A of an op completes T/2 before half B, hiding the first-chunk latency of the next op)
     int issue;            // 0: the product's loop; 1: unrolled over the 4 ring stages (compile-time stage / descriptor offsets), no tcgen05 fence after the
                           //    weight barrier (the weights arrive through the async proxy; the fence is only needed behind the a_ready waits)
 };
@@ -124,6 +126,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) probe(const Args a) {
                         mbar_wait(&full[st], phase);
                         const uint64_t db_hi = dB0 + (uint64_t)(((uint32_t)st * (uint32_t)STAGE) >> 4);
                         const uint64_t db_lo = db_hi + (uint64_t)(lo_off >> 4);
+                        if (a.half) {
+                            // stage = [k step a: hi 4 KB | lo 4 KB][k step b: hi | lo], N = 128: LBO 2048
+                            const uint32_t id128 = instr_desc_bf16(TM, 128);
+                            const uint64_t b0h = smem_desc(ring_s + (uint32_t)st * STAGE, 128u * 16u, SBO), b0l = b0h + (4096u >> 4), b1h = b0h + (8192u >> 4), b1l = b0h + (12288u >> 4);
+                            const uint64_t da_hi2 = da_hi + (uint64_t)((2u * LBO_A) >> 4), da_lo2 = da_lo + (uint64_t)((2u * LBO_A) >> 4);
+                            if (elect_one_sync()) {
+                                mma_bf16_ss(d_tmem, da_hi, b0h, id128, (pass | st) ? 1u : 0u);
+                                mma_bf16_ss(d_tmem, da_lo, b0h, id128, 1u);
+                                mma_bf16_ss(d_tmem, da_hi, b0l, id128, 1u);
+                                mma_bf16_ss(d_tmem, da_hi2, b1h, id128, 1u);
+                                mma_bf16_ss(d_tmem, da_lo2, b1h, id128, 1u);
+                                mma_bf16_ss(d_tmem, da_hi2, b1l, id128, 1u);
+                                mma_commit(&empty[st]);
+                            }
+                            __syncwarp();
+                            da_hi += (uint64_t)((2u * LBO_A) >> 4);        // (stays inside the 36-chunk operand: 4 passes x 4 stages x 1 chunk pair + 1)
+                            da_lo += (uint64_t)((2u * LBO_A) >> 4);
+                            continue;
+                        }
                         if (elect_one_sync()) {
                             mma_bf16_ss(d_tmem, da_hi, db_hi, idesc, (pass | st) ? 1u : 0u);
                             if (a.nmma > 1) mma_bf16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
@@ -205,7 +226,7 @@ int main(int argc, char** argv) {
     for (int epi = 0; epi < 3; ++epi)
         for (int stream = 0; stream < 2; ++stream)
             for (int nmma = 1; nmma <= 3; ++nmma) {
-                Args a{w, out, nops, nmma, stream, epi, issue};
+                Args a{w, out, nops, nmma, stream, epi, 0, issue};
                 for (int rep = 0; rep < 2; ++rep) {            // second launch is the measurement (weights L2-resident)
                     CK(cudaMemset(out, 0, sizeof(long long) * 4 * grid));
                     probe<<<grid, NTHREADS, kSmem>>>(a);
@@ -219,6 +240,23 @@ int main(int argc, char** argv) {
                 const double ks = (double)nops * 16.0;
                 printf("  %d     %d     %d     %d  |  %9.1f   %9.1f   %12.1f\n", issue, nmma, stream, epi, med(c0) / ks, med(c1) / ks, med(c2) / (double)nops);
             }
+    printf("N-split schedule: N = 128 MMAs, 6 per ring stage (= 2 k steps, 384 tensor clocks): clocks per STAGE\n");
+    for (int epi = 0; epi < 3; ++epi)
+        for (int stream = 0; stream < 2; ++stream) {
+            Args a{w, out, nops, 3, stream, epi, 1, 1};
+            for (int rep = 0; rep < 2; ++rep) {
+                CK(cudaMemset(out, 0, sizeof(long long) * 4 * grid));
+                probe<<<grid, NTHREADS, kSmem>>>(a);
+                CK(cudaGetLastError());
+                CK(cudaDeviceSynchronize());
+            }
+            CK(cudaMemcpy(h.data(), out, sizeof(long long) * 4 * grid, cudaMemcpyDeviceToHost));
+            std::vector<long long> c0, c1, c2;
+            for (int b = 0; b < grid; ++b) { c0.push_back(h[b * 4]); c1.push_back(h[b * 4 + 1]); c2.push_back(h[b * 4 + 2]); }
+            auto med = [](std::vector<long long>& v) { std::sort(v.begin(), v.end()); return (double)v[v.size() / 2]; };
+            const double ks = (double)nops * 16.0;
+            printf("  half  stream %d  epi %d  |  %9.1f   %9.1f   %12.1f\n", stream, epi, med(c0) / ks, med(c1) / ks, med(c2) / (double)nops);
+        }
     cudaFree(w);
     cudaFree(out);
     return 0;
