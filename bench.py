@@ -10,13 +10,26 @@ samples/ray -> compositing -> 3R eikonal points) + I2SDFLoss + backward incl. th
 0.01 so all five sampler rounds run).  value = full-path ray-samples/s = rays * 97 / step time, whole job (all ranks).
 `--mode render` times the eval forward render of the same batch instead (also reported as `render` in train mode).
 
-N > 1 (torchrun, one rank per GPU): rays shard across ranks, every rank processes its own 1024-ray batch (weak
-scaling); training all-reduces the flat 3.2 MB gradient once per step over NCCL, inference has no collective;
-time = max over ranks of the device time of the K steps.
+N > 1 (torchrun, one rank per GPU): rays shard across ranks.  The headline `value` is WEAK scaling (every rank processes
+its own 1024-ray batch); the same line carries `strong_scaling` (ONE 1024-ray batch split over the ranks,
+1024 / N rays per GPU).  Training all-reduces the flat 3.2 MB gradient once per step over NCCL (parallel.GradBucket: the
+gradients live in one persistent buffer, no flatten / un-flatten), inference has no collective; time = max over ranks of
+the device time of the K steps.
 
 --impl reference: the reference's CPU implementation of the same path.  The reference is Python/PyTorch and cannot
 travel to the GPU box, so this arm times the oracle port (oracle/i2sdf_oracle.py, pinned bit-for-bit against the
-reference on the golden fixtures) on the host cores, one bounded sample of the workload per step.
+reference on the golden fixtures) on the host cores: the SAME config as the GPU arm (1024 rays per step, same weights, rays and
+targets, training step incl. the Adam update).
+
+Algorithmic FLOP model (flop_model below; 2 x MAC of the dense layers only, PE / activations / compositing excluded), synthetic.yml:
+  sdf-eval (sampler)      918 016   = 2 x (39x256 + 256x256x2 + 256x217 + 256x256x4 + 256)           sdf row of the last layer only
+  ray-sample forward    2 506 752   = 2 x (524 544 SDF incl. 256 feature rows + 459 008 grad_x reverse sweep + 269 824 radiance)
+  eikonal point forward 1 836 032   = 2 x (459 008 + 459 008)                                        sdf + grad_x, no features / radiance
+  ray-sample backward   4 991 488   = 2 x (2 x 269 824 radiance dX + dW, 458 752 tangent pass, 65 536 feature adjoint,
+                                           448 768 adjoint chain, 2 x 458 752 + 65 536 weight gradients)   first + second order
+  eikonal point backward 3 650 560  = 2 x (458 752 + 256 + 448 768 + 2 x 458 752)
+  training step  = rounds x 128 R x sdf-eval + 97 R x (fwd + bwd) + 3 R x (eik fwd + eik bwd)   = 1.364 TFLOP at R = 1024, 5 rounds
+  eval render    = rounds x 128 R x sdf-eval + 97 R x ray-sample forward                          = 0.851 TFLOP at R = 1024, 5 rounds
 """
 import argparse
 import json
@@ -36,9 +49,39 @@ UNIT = "ray-samples/s"
 N_COMPOSITED = 97               # N_samples + 2 + N_samples_extra - 1  (model/network/__init__.py:99-100)
 # algorithmic FLOP (2 x MAC, dense layers only) per unit: one sampler sdf evaluation (sdf row of the last
 # layer only); one composited ray-sample = SDF fwd + grad_x sweep + radiance (+ light head)
-FLOPS = {"synthetic": dict(sdf_eval=918016, ray_sample=2506752),
-         "synthetic_light_mask": dict(sdf_eval=2 * (393472 - 65536), ray_sample=1917184)}
-FLOP_PER_SDF_EVAL = FLOPS["synthetic"]["sdf_eval"]
+
+
+def flop_model(conf):
+    """Algorithmic FLOPs (2 x MAC, dense layers only) per unit of work, from the network dims of a model conf (see the module doc)."""
+    imp, ren = conf["implicit_network"], conf["rendering_network"]
+    ex, ed = 3 + 6 * imp["multires"], 3 + 6 * ren["multires"]
+    dims = [ex] + list(imp["dims"])
+    skip = list(imp.get("skip_in", ()))
+    hid = 0                                     # MACs of the SDF hidden layers (a layer feeding a skip concat is ex narrower)
+    for l in range(len(dims) - 1):
+        out = dims[l + 1] - (ex if (l + 1) in skip else 0)
+        hid += dims[l] * out
+    feat = conf["feature_vector_size"]
+    sdf_fwd_full = hid + dims[-1] * (1 + feat)              # as the reference executes it (257 output rows)
+    sdf_row = hid + dims[-1]                                # sdf row only = the grad_x reverse sweep's MACs too
+    cdims = [ed + feat] + list(ren["dims"]) + [3]
+    col = sum(a * b for a, b in zip(cdims[:-1], cdims[1:]))
+    light = conf.get("light_network")
+    lmac = 0
+    if light:
+        ld = [feat] + list(light["dims"]) + [1]              # an ImplicitNetwork with dims [256, 128, 1] (network/__init__.py:29-32)
+        lmac = sum(a * b for a, b in zip(ld[:-1], ld[1:]))
+    adj = hid - dims[0] * (dims[1] - (ex if 1 in skip else 0))          # adjoint chain stops in front of layer 0
+    return dict(sdf_eval=2 * sdf_row, ray_sample=2 * (sdf_fwd_full + sdf_row + col + lmac), eik_fwd=2 * (sdf_row + sdf_row),
+                ray_sample_bwd=2 * (2 * col + hid + feat * dims[-1] + adj + 2 * hid + feat * dims[-1] + 2 * lmac),
+                eik_bwd=2 * (hid + dims[-1] + adj + 2 * hid))
+
+
+def step_flops(fm, R, rounds, train):
+    f = rounds * 128 * R * fm["sdf_eval"] + N_COMPOSITED * R * fm["ray_sample"]
+    if train:
+        f += N_COMPOSITED * R * fm["ray_sample_bwd"] + 3 * R * (fm["eik_fwd"] + fm["eik_bwd"])
+    return f
 
 
 def parse():
@@ -51,7 +94,9 @@ def parse():
     ap.add_argument("--config", default="synthetic", choices=["synthetic", "synthetic_light_mask"],
                     help="synthetic (default, BASELINE.json configs[1]/[2]) or synthetic_light_mask (configs[3]: 6x256 SDF, 3x256 "
                          "radiance, light-mask head, light_mask_weight 0.5)")
-    ap.add_argument("--cpu-rays", type=int, default=128, help="rays per step of the CPU arms (bounded sample)")
+    ap.add_argument("--cpu-rays", type=int, default=0, help="rays per step of the CPU arms (0 = --rays: the same config as the GPU arm)")
+    ap.add_argument("--bubble", type=int, default=0, help="training variant of steps 50k-150k (config/synthetic.yml:22-23): N bubble points per "
+                                                          "step through the SDF (bubble_weight 0.5) and the smoothness term switched on")
     ap.add_argument("--mode", default="train", choices=["render", "train"],
                     help="train (default, BASELINE.json configs[1]): full training step on a 1024-ray batch (forward + I2SDFLoss + "
                          "backward incl. second order + gradient all-reduce + Adam + weight re-pack); "
@@ -102,14 +147,15 @@ def pick_cpu_threads(run_once):
 PORT_VS_REFERENCE = {"render": "1.0-1.1", "train": "1.0-1.1"}
 
 
-def cpu_arm(conf, model, rays, steps, warmup):
+def cpu_arm(conf, model, rays, steps, warmup, full_rays=1024):
+    from i2sdf_b200.synthetic import synthetic_rays
     from oracle import i2sdf_oracle as orc
     spec = orc.spec_from_model_conf(conf, use_normal=False)
     P = {k: v.detach().cpu() for k, v in model.state_dict().items()}
-    probe = orc.synthetic_rays(16, seed=2)
+    probe = synthetic_rays(16, seed=2)
     with torch.no_grad():
         pick_cpu_threads(lambda: orc.render(spec, P, probe, training=False))
-    inp = orc.synthetic_rays(rays, seed=1)
+    inp = synthetic_rays(rays, seed=1)
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
@@ -121,7 +167,8 @@ def cpu_arm(conf, model, rays, steps, warmup):
     total = sum(times)
     return dict(value=rays * N_COMPOSITED * len(times) / total, ms_per_step=1e3 * total / len(times),
                 cores=torch.get_num_threads(),
-                sample=f"{rays} of the 1024 rays per step (same weights, same ray distribution), eval forward, "
+                same_config=(rays == full_rays),
+                sample=f"{rays} of the {full_rays} rays per step (same weights, same rays), eval forward, "
                        f"{len(times)} steps after {warmup} warm-up, torch CPU fp32, best of 8/16/32/64/all host threads "
                        f"(picked {torch.get_num_threads()} of {os.cpu_count()}); oracle port = {PORT_VS_REFERENCE['render']}x the unmodified "
                        f"reference's speed where both run (build container)")
@@ -185,17 +232,8 @@ def peaks():
 
 
 def make_train_gt(R, seed, light=False):
-    g = torch.Generator().manual_seed(seed)
-    gt = {
-        "rgb": torch.rand(R, 3, generator=g),
-        "depth": torch.rand(R, generator=g) * 2 + 0.5,
-        "depth_mask": torch.ones(R, dtype=torch.bool),
-        "normal": torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1),
-        "normal_mask": torch.ones(R, dtype=torch.bool),
-    }
-    if light:
-        gt["light_mask"] = (torch.rand(R, 1, generator=g) > 0.9).float()
-    return gt
+    from i2sdf_b200.synthetic import make_train_gt as mk
+    return mk(R, seed, light)
 
 
 def loss_weights(name):
@@ -205,13 +243,13 @@ def loss_weights(name):
     return src, {k: v for k, v in src.items() if k in keys}
 
 
-def cpu_train_arm(conf, model, rays, steps, warmup, name="synthetic"):
-    """Reference training step (forward + I2SDFLoss + backward incl. double backward) on the CPU: oracle port."""
-    from i2sdf_b200 import configs
+def cpu_train_arm(conf, model, rays, steps, warmup, name="synthetic", full_rays=1024):
+    """Reference training step (forward + I2SDFLoss + backward incl. double backward + Adam) on the CPU: oracle port."""
+    from i2sdf_b200.synthetic import synthetic_rays
     from oracle import i2sdf_oracle as orc
     spec = orc.spec_from_model_conf(conf, use_normal=True)
     P0 = {k: v.detach().cpu() for k, v in model.state_dict().items()}
-    inp = orc.synthetic_rays(rays, seed=1, train_layout=True)
+    inp = synthetic_rays(rays, seed=1, train_layout=True)
     light = name == "synthetic_light_mask"
     gt = make_train_gt(rays, 7, light)
     lw = loss_weights(name)[1]
@@ -223,13 +261,18 @@ def cpu_train_arm(conf, model, rays, steps, warmup, name="synthetic"):
                 "eik_uniform": torch.empty(R, 3).uniform_(-spec.bounding_sphere, spec.bounding_sphere),
                 "nbr_uniform": torch.empty(R, 3).uniform_(-0.005, 0.005)}
 
-    def one():
-        P = {k: v.clone().requires_grad_(True) for k, v in P0.items()}
-        out = orc.render(spec, P, inp, training=True, tape=tape())
-        loss = orc.recon_loss(out, gt, smooth_active=False, **lw)
-        loss.backward()
+    # the parameters persist and move with Adam(eps=1e-15) (model/trainer/recon.py:201-207), as on the GPU arm
+    Pt = {k: v.clone().requires_grad_(True) for k, v in P0.items()}
+    opt = torch.optim.Adam(list(Pt.values()), lr=5.0e-4, eps=1e-15)
 
-    probe_inp = orc.synthetic_rays(32, seed=2, train_layout=True)
+    def one():
+        out = orc.render(spec, Pt, inp, training=True, tape=tape())
+        loss = orc.recon_loss(out, gt, smooth_active=False, **lw)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+
+    probe_inp = synthetic_rays(32, seed=2, train_layout=True)
 
     def probe():
         P = {k: v.clone().requires_grad_(True) for k, v in P0.items()}
@@ -250,7 +293,8 @@ def cpu_train_arm(conf, model, rays, steps, warmup, name="synthetic"):
             times.append(dt)
     total = sum(times)
     return dict(value=rays * N_COMPOSITED * len(times) / total, ms_per_step=1e3 * total / len(times), cores=torch.get_num_threads(),
-                sample=f"{rays} of the 1024 rays per step, full training step (forward + loss + backward; no optimizer), "
+                same_config=(rays == full_rays),
+                sample=f"{rays} of the {full_rays} rays per step, full training step (forward + loss + backward incl. second order + Adam), "
                        f"{len(times)} steps after {warmup} warm-up, torch CPU fp32, best of 8/16/32/64/all host threads "
                        f"(picked {torch.get_num_threads()} of {os.cpu_count()}); oracle port = {PORT_VS_REFERENCE['train']}x the unmodified "
                        f"reference's speed where both run (build container)")
@@ -258,33 +302,29 @@ def cpu_train_arm(conf, model, rays, steps, warmup, name="synthetic"):
 
 def gpu_arm(args, rank, world, local_rank):
     import torch.distributed as dist
-    from oracle import i2sdf_oracle as orc
-    from i2sdf_b200 import configs
     from i2sdf_b200.network import I2SDFLoss
-    from i2sdf_b200.parallel import allreduce_gradients
+    from i2sdf_b200.parallel import GradBucket
+    from i2sdf_b200.synthetic import bubble_points, synthetic_rays
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
     train = args.mode == "train"
     conf, model = build_params(name=args.config)
     light = args.config == "synthetic_light_mask"
-    flops = FLOPS[args.config]
+    fm = flop_model(conf)
     if train:
         model.use_normal = True          # trainer sets it from loss.normal_weight (model/trainer/recon.py:34-35)
     cpu_snapshot = {k: v.detach().clone() for k, v in model.state_dict().items()} if rank == 0 else None
     model_gpu = model.to(dev)
     model_gpu.train(train)
     init_state = {k: v.detach().clone() for k, v in model_gpu.state_dict().items()}
-    R = args.rays
-    # rank-specific rays: the global batch is world * R rays sharded across ranks
-    inp_host = {k: v.pin_memory() for k, v in orc.synthetic_rays(R, seed=1 + rank, train_layout=train).items()}
-    gt_host = {k: v.pin_memory() for k, v in make_train_gt(R, 7 + rank, light).items()} if train else {}
-    inp_dev = {k: v.to(dev) for k, v in inp_host.items()}
-    gt_dev = {k: v.to(dev) for k, v in gt_host.items()}
     core = model_gpu._ready_core()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
-    out_host = {}
     if train:
-        loss_fn = I2SDFLoss(**loss_weights(args.config)[0])
+        lw = dict(loss_weights(args.config)[0])
+        if args.bubble > 0:              # steps 50k-150k of config/synthetic.yml: bubble loss on, smoothness on
+            lw.update(bubble_weight=0.5, smooth_weight=lw.get("smooth_weight") or 0.01, smooth_iter=0, min_bubble_iter=0, max_bubble_iter=None)
+        loss_fn = I2SDFLoss(**lw)
+        loss_step = 10 ** 6 if args.bubble > 0 else 0
         # Adam(lr, eps=1e-15) as model/trainer/recon.py:201-207; i2sdf_b200.optim.Adam is the same update rule and state layout as
         # torch.optim.Adam in ONE launch for all 44 parameter tensors (I2SDF_TORCH_ADAM=1: torch's fused Adam, 4 launches)
         if os.environ.get("I2SDF_TORCH_ADAM") == "1":
@@ -292,106 +332,146 @@ def gpu_arm(args, rank, world, local_rank):
         else:
             from i2sdf_b200.optim import Adam
             opt = Adam(model_gpu.parameters(), lr=5.0e-4, eps=1e-15)
+        bucket = GradBucket(model_gpu.parameters())     # every .grad is a view of ONE flat buffer: all-reduced in place, read by Adam
         loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
-
-    def train_step(inp, gt):
-        out = model_gpu(inp)
-        loss = loss_fn(out, gt, 0)["loss"]
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        if world > 1:
-            allreduce_gradients(model_gpu.parameters())
-        opt.step()
-        return loss
-
-    def step_resident():
-        if train:
-            return train_step(inp_dev, gt_dev)
-        return model_gpu(inp_dev)
-
-    def step_e2e():
-        d = {k: v.to(dev, non_blocking=True) for k, v in inp_host.items()}
-        if train:
-            g = {k: v.to(dev, non_blocking=True) for k, v in gt_host.items()}
-            loss = train_step(d, g)
-            loss_host.copy_(loss.detach(), non_blocking=True)
-            return loss
-        out = model_gpu(d)
-        for k, v in out.items():
-            if k not in out_host:
-                out_host[k] = torch.empty(v.shape, dtype=v.dtype).pin_memory()
-            out_host[k].copy_(v, non_blocking=True)
-        return out
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, profile=False):
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        barrier()
-        if profile:
-            core.profile(True)
-        for a, b in ev:
-            flush.zero_()                      # L2 flush between timed iterations (outside the event pair)
-            a.record()
-            fn()
-            b.record()
-        barrier()
-        prof = core.profile_read() if profile else None
-        if profile:
-            core.profile(False)
-        ms = sum(a.elapsed_time(b) for a, b in ev)
-        return ms, prof
+    def measure(R, first_ray, global_rays):
+        """K timed steps on this rank's R rays [first_ray, first_ray + R) of a global batch: device-resident and end-to-end."""
+        # the global batch is generated identically on every rank, each rank keeps its shard
+        full = synthetic_rays(global_rays, seed=1, train_layout=train)
+        gt_full = make_train_gt(global_rays, 7, light) if train else {}
+        sl = slice(first_ray, first_ray + R)
+        if train:
+            inp_host = {k: v[sl].contiguous().pin_memory() for k, v in full.items()}
+        else:
+            inp_host = {"uv": full["uv"][:, sl].contiguous().pin_memory(), "pose": full["pose"].pin_memory(), "intrinsics": full["intrinsics"].pin_memory()}
+        gt_host = {k: v[sl].contiguous().pin_memory() for k, v in gt_full.items()}
+        if train and args.bubble > 0:
+            inp_host["pointcloud"] = bubble_points(args.bubble, seed=11 + rank).pin_memory()
+        inp_dev = {k: v.to(dev) for k, v in inp_host.items()}
+        gt_dev = {k: v.to(dev) for k, v in gt_host.items()}
+        out_host = {}
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-        step_e2e()
+        def train_step(inp, gt):
+            out = model_gpu(inp)
+            loss = loss_fn(out, gt, loss_step)["loss"]
+            bucket.zero()
+            loss.backward()
+            bucket.allreduce()               # gathers every .grad into the flat buffer; all-reduces it when world > 1
+            opt.step()
+            return loss
+
+        def step_resident():
+            return train_step(inp_dev, gt_dev) if train else model_gpu(inp_dev)
+
+        def step_e2e():
+            d = {k: v.to(dev, non_blocking=True) for k, v in inp_host.items()}
+            if train:
+                g = {k: v.to(dev, non_blocking=True) for k, v in gt_host.items()}
+                loss = train_step(d, g)
+                loss_host.copy_(loss.detach(), non_blocking=True)
+                return loss
+            out = model_gpu(d)
+            for k, v in out.items():
+                if k not in out_host:
+                    out_host[k] = torch.empty(v.shape, dtype=v.dtype).pin_memory()
+                out_host[k].copy_(v, non_blocking=True)
+            return out
+
+        def timed(fn, steps, profile=False):
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            barrier()
+            if profile:
+                core.profile(True)
+            for a, b in ev:
+                flush.zero_()                      # L2 flush between timed iterations (outside the event pair)
+                a.record()
+                fn()
+                b.record()
+            barrier()
+            prof = core.profile_read() if profile else None
+            if profile:
+                core.profile(False)
+            return sum(a.elapsed_time(b) for a, b in ev), prof
+
+        model_gpu.load_state_dict(init_state)          # every measurement starts from the W-sharp weights
+        if train:
+            opt.state.clear()
+        for _ in range(max(args.warmup, 3)):
+            step_resident()
+            step_e2e()
+        core.rounds_log.clear()
+        ms_res, prof = timed(step_resident, args.steps, profile=True)
+        rounds = list(core.rounds_log)
+        ms_e2e, _ = timed(step_e2e, args.steps)
+        h2d = sum(v.numel() * v.element_size() for v in list(inp_host.values()) + list(gt_host.values()))
+        d2h = 4 if train else sum(v.numel() * v.element_size() for v in out_host.values())
+        return dict(ms_res=ms_res, ms_e2e=ms_e2e, prof=prof, rounds=rounds, h2d=h2d, d2h=d2h)
+
+    def reduce_max(*vals):
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    R = args.rays
     clk = ClockSampler(local_rank)
     clk.start()
-    core.rounds_log.clear()
-    ms_res, prof = timed(step_resident, args.steps, profile=True)
-    rounds_seen = sorted(set(core.rounds_log))
-    rounds_total = sum(core.rounds_log)
-    ms_e2e, _ = timed(step_e2e, args.steps)
+    weak = measure(R, rank * R, world * R)              # weak scaling: R rays per rank, a global batch of world * R
     clocks = clk.stop()
+    strong = None
+    if world > 1:                                       # strong scaling (SURVEY.md C5): ONE R-ray batch split over the ranks
+        from i2sdf_b200.parallel import shard_bounds
+        lo, hi = shard_bounds(R, rank, world)
+        strong = measure(hi - lo, lo, R)
     ms_render = 0.0
     if train:       # also report the forward-render throughput of the same networks (inference: no collective)
         model_gpu.load_state_dict(init_state)          # back to the W-sharp weights (Adam steps changed beta / the surface)
         model_gpu.eval()
-        inp_eval = {k: v.to(dev) for k, v in orc.synthetic_rays(R, seed=1 + rank).items()}
+        inp_eval = {k: v.to(dev) for k, v in synthetic_rays(R, seed=1 + rank).items()}
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         with torch.no_grad():
             for _ in range(3):
                 model_gpu(inp_eval)
-            ms_render, _ = timed(lambda: model_gpu(inp_eval), args.steps)
+            barrier()
+            for a, b in ev:
+                flush.zero_()
+                a.record()
+                model_gpu(inp_eval)
+                b.record()
+            barrier()
+        ms_render = sum(a.elapsed_time(b) for a, b in ev)
         model_gpu.train(True)
-    t = torch.tensor([ms_res, ms_e2e, ms_render], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_res, ms_e2e, ms_render = float(t[0]), float(t[1]), float(t[2])
+    vals = reduce_max(weak["ms_res"], weak["ms_e2e"], ms_render, strong["ms_res"] if strong else 0.0, strong["ms_e2e"] if strong else 0.0)
+    ms_res, ms_e2e, ms_render, ms_strong, ms_strong_e2e = vals
     if rank != 0:
-        return None
+        return None, None
     K = args.steps
+    prof = weak["prof"]
     value = world * R * N_COMPOSITED * K / (ms_res * 1e-3)
     e2e_value = world * R * N_COMPOSITED * K / (ms_e2e * 1e-3)
     pk = peaks()
-    # dominant kernel: sampler SDF evaluations (73 % of the forward path's FLOPs)
+    rounds_seen = sorted(set(weak["rounds"]))
+    rounds_total = sum(weak["rounds"])
+    # dominant kernel: sampler SDF evaluations (44 % of a training step's FLOPs, 71 % of a render's)
     sdf = prof["sampler_sdf"]
     # launches of rounds the device-side convergence word switched off return at once: only ACTIVE launches count (training: the
     # rounds each timed step really ran, read back by sampler_resolve; eval: the W-sharp weights run all of them)
     sdf_launches = max(rounds_total if (train and rounds_total > 0) else sdf["launches"], 1)
     pts_per_launch = R * 128
     per_launch_ms = sdf["ms"] / sdf_launches
-    achieved = pts_per_launch * flops["sdf_eval"] / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
+    achieved = pts_per_launch * fm["sdf_eval"] / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
     peak = pk["bf16_tflops_sustained"] if core.uses_tensor_cores else 72.0
     launches = sum(v["launches"] for v in prof.values())
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01c_tc_sdf_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_tc_sdf_traffic.json")
     if core.uses_tensor_cores and os.path.exists(tpath) and R == 1024 and not light:
         traffic = json.load(open(tpath))["dram_bytes_per_launch"]      # from the committed ncu --set full capture
-    h2d = sum(v.numel() * v.element_size() for v in list(inp_host.values()) + list(gt_host.values()))
-    d2h = 4 if train else sum(v.numel() * v.element_size() for v in out_host.values())
     if train:
         workload = ("C2: training step on a 1024-ray batch, config/synthetic.yml networks and loss weights "
                     "(rgb L1 + eikonal + depth + normal/angular; steps < 50k: no bubble/smooth terms): forward "
@@ -399,6 +479,8 @@ def gpu_arm(args, rank, world, local_rank):
                     "points) + I2SDFLoss + backward incl. second-order terms (fused tensor-core chain + one weight-gradient launch) "
                     "+ Adam(eps=1e-15) step (one launch) + weight re-pack"
                     + (" + one flat NCCL gradient all-reduce" if world > 1 else ""))
+        if args.bubble > 0:
+            workload = workload.replace("steps < 50k: no bubble/smooth terms", f"steps 50k-150k: + bubble loss on {args.bubble} surface points + smoothness term")
     else:
         workload = ("C2/C3 batch shape: 1024-ray forward render, config/synthetic.yml networks (8x256 SDF + 4x256 radiance), "
                     "eval layout: sampler 5 rounds = 640 sdf-evals/ray + 97 composited samples/ray")
@@ -406,10 +488,12 @@ def gpu_arm(args, rank, world, local_rank):
         workload = workload.replace("C2: training step", "C4: training step").replace("C2/C3 batch shape", "C4 batch shape") \
             .replace("config/synthetic.yml networks (8x256 SDF + 4x256 radiance)", "config/synthetic_light_mask.yml networks (6x256 SDF + 3x256 radiance + light-mask head)") \
             .replace("config/synthetic.yml networks and loss weights", "config/synthetic_light_mask.yml networks (6x256 SDF, 3x256 radiance, light-mask head) and loss weights (+ light-mask BCE 0.5)")
+    mean_rounds = (rounds_total / len(weak["rounds"])) if (train and weak["rounds"]) else 5.0
+    fstep = step_flops(fm, R, mean_rounds, train)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_res / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 (bf16 hi/lo split products on tcgen05, fp32 accumulate)" if core.uses_tensor_cores else "f32",
+        "dtype": "f32 (fp16 hi/lo split products on tcgen05, fp32 accumulate in TMEM; backward chain: bf16 hi/lo)" if core.uses_tensor_cores else "f32",
         "data": "synthetic",
         "config": {"workload": workload, "mode": args.mode, "network_config": args.config,
                    "weights": ("W-sharp at step 0: reference geometric init (seed 0), density.beta=0.01 (all 5 sampler rounds run); training then "
@@ -419,22 +503,40 @@ def gpu_arm(args, rank, world, local_rank):
                    "rays_per_gpu": R, "global_rays": world * R, "samples_per_ray_composited": N_COMPOSITED,
                    "sdf_evals_per_ray": 5 * 128 + N_COMPOSITED,
                    "sampler_rounds_in_timed_steps": rounds_seen if train else "5 (eval: weights fixed)",
-                   "parallelism": f"ray-sharded x{world}, " + ("one flat gradient all-reduce per step" if train else "no collective (inference)"),
+                   "parallelism": f"ray-sharded x{world}, " + ("one flat gradient all-reduce per step (persistent bucket, in place)" if train else "no collective (inference)"),
                    "tensor_cores": {"sampler_sdf": core.uses_tensor_cores, "main_pass": core.uses_tensor_cores_main,
                                     "backward": bool(train and core.fused_main)},
                    "l2": "flushed between timed iterations (256 MB write)", "timing": "CUDA events per step, max over ranks"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": weak["h2d"], "d2h_bytes_per_step": weak["d2h"]},
         "gpu_launches": launches,
         "kernel_ms_per_step": {k: v["ms"] / K for k, v in prof.items()},
         "kernel_launches_per_step": {k: v["launches"] / K for k, v in prof.items()},
         "roofline": {"bound": "tensor", "kernel": "tc_sdf8_kernel (sampler SDF evaluations)" if core.uses_tensor_cores else "mlp_tile_kernel",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                     "traffic": traffic, "traffic_unit": "bytes of DRAM traffic per launch (ncu --set full, profiles/r01c_tc_sdf_traffic.json)",
-                     "flop_per_launch": pts_per_launch * flops["sdf_eval"], "ms_per_launch": per_launch_ms,
+                     "traffic": traffic, "traffic_unit": "bytes of DRAM traffic per launch (ncu --set full, profiles/r02_tc_sdf_traffic.json)",
+                     "flop_per_launch": pts_per_launch * fm["sdf_eval"], "ms_per_launch": per_launch_ms,
                      "peak_source": pk["source"] + (", sustained bf16 (kernel timed inside a step)" if core.uses_tensor_cores else "; fp32 FMA peak 148 SM x 128 FMA x 2 x 1.9 GHz"),
-                     "note": "achieved counts ALGORITHMIC flops (1 MAC = 2 flop); the kernel issues 3 bf16 MMAs per MAC, so 1/3 of the bf16 peak is this precision scheme's ceiling"},
+                     "note": "achieved counts ALGORITHMIC flops (1 MAC = 2 flop); the kernel issues 3 fp16 MMAs per MAC (hi*hi + lo*hi + hi*lo), so 1/3 of the 16-bit "
+                             "dense peak is this precision scheme's ceiling"},
+        # whole-step roofline: the step's algorithmic FLOPs by the formula in this file's doc string / flop_model()
+        "roofline_step": {"bound": "tensor", "flop_per_step_per_gpu": fstep, "achieved": fstep / (ms_res / K * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                          "frac": fstep / (ms_res / K * 1e-3) / 1e12 / peak if peak else None, "flop_model": fm, "mean_sampler_rounds": mean_rounds,
+                          "formula": ("rounds*128*R*sdf_eval + 97*R*(ray_sample + ray_sample_bwd) + 3*R*(eik_fwd + eik_bwd)" if train
+                                      else "rounds*128*R*sdf_eval + 97*R*ray_sample")},
         "clocks": clocks,
     }
+    if strong is not None:
+        sv = R * N_COMPOSITED * K / (ms_strong * 1e-3)
+        line["strong_scaling"] = {
+            "value": sv, "unit": UNIT, "ms_per_step": ms_strong / K, "global_rays": R, "rays_per_gpu": R / world,
+            "e2e": {"value": R * N_COMPOSITED * K / (ms_strong_e2e * 1e-3), "ms_per_step": ms_strong_e2e / K},
+            "workload": "SURVEY.md C5: ONE 1024-ray batch split over the ranks (same weights / rays / targets as N = 1), plain sharding "
+                        "(per-shard sampler convergence and loss means; the strict-parity switches add 5 + 1 tiny all-reduces per step)",
+            "kernel_ms_per_step": {k: v["ms"] / K for k, v in strong["prof"].items()},
+            "limiter": "at 1024 / N rays per GPU a launch covers N x fewer 128-point tiles than the GPU has SMs (128 rays x 128 points = 128 tiles on "
+                       "148 SMs), so every kernel runs ONE partial wave whatever N is: step time is bounded below by the step's ~60 dependent launches "
+                       "and single-tile chain latencies, not by throughput",
+        }
     if train and core.fused_main and prof["weight_grads"]["launches"] > 0 and not light:
         # the two other heavy kernels of the training step, both bounded by HBM: algorithmic bytes = plane slots read / written
         tile = lambda m: (m + 127) // 128                                                     # noqa: E731
@@ -452,14 +554,24 @@ def gpu_arm(args, rank, world, local_rank):
                          "launches_per_step": prof[key]["launches"] / K, "traffic_model": what})
         line["roofline_more"] = more
     if train and ms_render > 0:
+        fr = step_flops(fm, R, 5.0, False)
         line["render"] = {"value": world * R * N_COMPOSITED * K / (ms_render * 1e-3), "unit": UNIT, "ms_per_step": ms_render / K,
-                          "workload": "eval forward render of the same 1024-ray batch (no backward, no collective), device-resident inputs"}
+                          "workload": "eval forward render of the same 1024-ray batch (no backward, no collective), device-resident inputs",
+                          "roofline_step": {"flop_per_step_per_gpu": fr, "achieved": fr / (ms_render / K * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                                            "frac": fr / (ms_render / K * 1e-3) / 1e12 / peak if peak else None}}
+    return line, (conf, cpu_snapshot)
+
+
+def add_cpu_baseline(line, args, conf, cpu_snapshot):
+    """Rank 0, after the process group is gone (so the other ranks are not spinning in a barrier next to it)."""
     model_c = type("S", (), {"state_dict": lambda self: cpu_snapshot})()
-    if train:
-        cb = cpu_train_arm(conf, model_c, args.cpu_rays, steps=2, warmup=1, name=args.config)
+    rays = args.cpu_rays or args.rays
+    if args.mode == "train":
+        cb = cpu_train_arm(conf, model_c, rays, steps=2, warmup=1, name=args.config, full_rays=args.rays)
     else:
-        cb = cpu_arm(conf, model_c, args.cpu_rays, steps=2, warmup=1)
-    line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port", "sample": cb["sample"]}
+        cb = cpu_arm(conf, model_c, rays, steps=2, warmup=1, full_rays=args.rays)
+    line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port", "sample": cb["sample"],
+                            "same_config": cb["same_config"], "ms_per_step": cb["ms_per_step"]}
     return line
 
 
@@ -472,16 +584,19 @@ def main():
         if rank != 0:
             return
         conf, model = build_params(name=args.config)
+        rays = args.cpu_rays or args.rays
         if args.mode == "train":
-            cb = cpu_train_arm(conf, model, args.cpu_rays, steps=args.steps, warmup=args.warmup, name=args.config)
+            cb = cpu_train_arm(conf, model, rays, steps=args.steps, warmup=args.warmup, name=args.config, full_rays=args.rays)
         else:
-            cb = cpu_arm(conf, model, args.cpu_rays, steps=args.steps, warmup=args.warmup)
+            cb = cpu_arm(conf, model, rays, steps=args.steps, warmup=args.warmup, full_rays=args.rays)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"same as --impl ours --mode {args.mode} (1024-ray batch, synthetic.yml, W-sharp); each step is a "
-                                       "bounded sample of the batch on the host CPU (see cpu_baseline.sample)", "mode": args.mode},
-                "cpu_baseline": {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port", "sample": cb["sample"]},
+                "config": {"workload": f"same as --impl ours --mode {args.mode}: {rays}-ray batch, {args.config}.yml networks, W-sharp weights, same rays / targets"
+                                       + (", training step incl. the Adam update" if args.mode == "train" else "") + ", on the host CPU (oracle port of the "
+                                       "reference's PyTorch path; one process: the reference has no multi-device path, so the CPU arm does not scale with --gpus)",
+                           "mode": args.mode, "same_config": cb["same_config"]},
+                "cpu_baseline": {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port", "sample": cb["sample"], "same_config": cb["same_config"]},
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -494,14 +609,16 @@ def main():
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-    line = gpu_arm(args, rank, world, local_rank)
-    if rank == 0:
-        sys.stdout.flush()
-        print(json.dumps(line), flush=True)
+    line, cpu = gpu_arm(args, rank, world, local_rank)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0:
+        # the CPU baseline runs with the GPUs idle and the other ranks gone
+        line = add_cpu_baseline(line, args, *cpu)
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

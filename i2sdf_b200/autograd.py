@@ -14,6 +14,14 @@ import torch.nn.functional as F
 from torch.autograd import Function
 
 
+# parameter -> persistent gradient view (parallel.GradBucket): the weight-norm backward writes dg / dv straight into these
+import weakref
+
+
+def register_grad_view(param, view):
+    param._i2sdf_grad_view = view         # an attribute of the Parameter object (tensors do not hash / compare as dictionary keys)
+
+
 def _zeros_like_all(groups):
     """Zero-initialised gradient buffers for several lists of tensors, carved from ONE flat allocation (one fill kernel)."""
     flat_n = sum(t.numel() for g in groups for t in g)
@@ -388,6 +396,8 @@ class _WeightNormAll(Function):
         _WeightNormAll._launch(gs, vs, norms, Ws=Ws)
         ctx.save_for_backward(*gs, *vs, flat_n)
         ctx.rows = rows
+        # [g_0, v_0, g_1, v_1, ...]: (parameter, its persistent gradient view) where a GradBucket registered one
+        ctx.grad_views = [(weakref.ref(t), getattr(t, "_i2sdf_grad_view", None)) for t in gv]
         ctx.set_materialize_grads(False)
         return tuple(Ws)
 
@@ -403,8 +413,18 @@ class _WeightNormAll(Function):
         dWs = [None if d is None else d.contiguous() for d in dWs]
         if all(d is None for d in dWs):
             return (None,) * (2 * n)
-        dgs = [None if d is None else torch.empty_like(g) for d, g in zip(dWs, gs)]
-        dvs = [None if d is None else torch.empty_like(v) for d, v in zip(dWs, vs)]
+        gvw = ctx.grad_views
+
+        def out_like(t, i):
+            # straight into the bucket view - but only while the parameter has no .grad: autograd would otherwise ADD this result to
+            # a .grad that already is the same memory (zero_grad(set_to_none=False)) and double it
+            if gvw is not None and gvw[i][1] is not None:
+                prm, w = gvw[i][0](), gvw[i][1]
+                if prm is not None and prm.grad is None and w.shape == t.shape and w.device == t.device:
+                    return w
+            return torch.empty_like(t)
+        dgs = [None if d is None else out_like(g, 2 * i) for i, (d, g) in enumerate(zip(dWs, gs))]
+        dvs = [None if d is None else out_like(v, 2 * i + 1) for i, (d, v) in enumerate(zip(dWs, vs))]
         _WeightNormAll._launch(gs, vs, norms, dWs=dWs, dgs=dgs, dvs=dvs)
         out = []
         for dg, dv in zip(dgs, dvs):

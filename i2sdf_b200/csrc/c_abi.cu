@@ -691,6 +691,9 @@ int i2sdf_render_forward(i2sdf_handle* h, const float* o, const float* d, const 
         if (save && planes_main(h) && (!s_light || ltc) && s_rgb && s_grad) p.sl = planes::make_layout(p.M, h->net.L - 1, h->net.Lc, true, save, nullptr);
         else p.save_act = (float*)save;
         p.scratch = scratch;
+        // development probe: the tensor-core main pass stamps its hand-offs into the first 64 KB of the workspace (the sampler's state,
+        // dead by now)
+        if (!save && getenv("I2SDF_DEBUG_TIMELINE")) p.tl = workspace;
         p.net = h->net;
         rc = run_mlp(h, p, st);
         if (rc == I2SDF_OK && ltc) rc = run_light(h, p.M, lfeat, s_light + r0 * N, lhidden, CH * 128, st);

@@ -105,6 +105,7 @@ struct MlpParams {
     float* out_light;
     float* save_act;          // [L-1][M][256] pre-activations (training) or null
     float* scratch;           // per-CTA [(L-1)][TM][256] when grad wanted without save_act
+    void* tl;                 // development probe (I2SDF_DEBUG_TIMELINE): 64 KB of clock64 stamps, tensor-core main pass only
     planes::Layout sl;        // tensor-core main pass in training: the saved state is plane slots (sl.base != null)
     int want_color;
     int want_light;

@@ -43,21 +43,40 @@ __device__ __forceinline__ bool round_active(const MlpParams& P) {
     return true;
 }
 
-template <bool FULL, bool SAVE>
+// ---- full chain (main pass, eikonal points, sdf + features) ---------------------------------------------------------------------
+// Work items are 32 rows x 8 columns as in the sampler's kernel below: in every iteration all 16 epilogue warps work on ONE 32-column
+// chunk, so the next op's MMA chain starts after 1/8 of an epilogue (round 1 used 16-column items, 8 warps per chunk: the main pass
+// ran at ~16 k clocks per op against ~8.4 k for the sampler's kernel).  Each epilogue kind has its own specialisation of the item loop.
+// Shared memory: A_hi | A_lo (36 chunks each) | weight ring | parameters | barriers.
+//   * parameters: every bias and both heads, copied once per launch, read as LDS broadcasts (ncu, round 2: with LDG the first FFMA of
+//     an item carried 17 % of all stall samples - the bias load missed L1 behind the scratch traffic);
+//   * the skip concat and the Jacobians of the reverse sweep re-evaluate sincos, but only in the items that reach into the embedding
+//     columns (warp-uniform branch; round 1's if-converted form evaluated it for all 256 columns);
+//   * the per-row partial sums (head, rgb, grad_x: [4 column groups][7][128]) alias operand chunks 32..35 (PE(view dir), consumed by
+//     C_0 long before the tile ends).
+enum { K_F = 0, K_FSKIP, K_FLAST, K_FLASTREV, K_G, K_C, K_CLAST, K_REV, K_REVSKIP, K_GRAD };
+constexpr int M8_PARAM_FLOATS = 36 * TM;            // 4608: (NL + 1 + Lc - 1) x 256 biases + sdf head (257 -> 260) + rgb head (771 -> 772)
+constexpr size_t kSmemMain = 128 + 2 * (size_t)A_PART_BYTES + NSTAGE * STAGE_MAX + M8_PARAM_FLOATS * 4 + 256;
+static_assert(kSmemMain <= 232448, "main pass shared memory");
+
+// TL: development probe (I2SDF_DEBUG_TIMELINE=1, tools/timeline.py main): clock64 stamps of CTA 0's second tile into P.tl
+template <bool SAVE, bool TL = false>
 // 18 warps -> one scheduler hosts 5 of them: 16 K regs / 5 warps caps the kernel at 96 registers per thread
-__global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, const OpTable T) {
+__global__ void __launch_bounds__(NTHREADS, 1) tc_main8_kernel(const MlpParams P, const OpTable T) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = smem_align1024(smem_raw);
+    uint8_t* smem = smem_align128(smem_raw);
     uint8_t* A_hi = smem;
     uint8_t* A_lo = smem + A_PART_BYTES;
     uint8_t* ring = smem + 2 * A_PART_BYTES;
-    float* part = reinterpret_cast<float*>(ring + NSTAGE * STAGE_MAX);      // [4][7][TM]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(part + PART_FLOATS);
+    float* sprm = reinterpret_cast<float*>(ring + NSTAGE * STAGE_MAX);      // [sdf_b NL x 256 | feat_b 256 | col_b (Lc-1) x 256 | sdf_head 260 | col_head 772]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sprm + M8_PARAM_FLOATS);
     uint64_t* full = bars;
     uint64_t* empty = bars + NSTAGE;
-    uint64_t* a_ready = bars + 2 * NSTAGE;       // [N_READY], 8 arrivals each
+    uint64_t* a_ready = bars + 2 * NSTAGE;       // [N_READY], 16 arrivals each
     uint64_t* d_full = a_ready + N_READY;        // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 2);
+    float* part01 = reinterpret_cast<float*>(A_hi + 32 * TM * 16);          // [2][7][TM]
+    float* part23 = reinterpret_cast<float*>(A_lo + 32 * TM * 16);          // [2][7][TM]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const NetDev& net = P.net;
@@ -66,11 +85,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
 
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < N_READY; ++i) mbar_init(&a_ready[i], 8);
+        for (int i = 0; i < N_READY; ++i) mbar_init(&a_ready[i], N_EPI_WARPS);
         mbar_init(&d_full[0], 1);
         mbar_init(&d_full[1], 1);
         fence_mbar_init();
     }
+    const int Lc1 = net.Lc - 1;
+    float* s_sdf_b = sprm;
+    float* s_feat_b = sprm + NL * 256;
+    float* s_col_b = s_feat_b + 256;
+    float* s_sdf_head = s_col_b + Lc1 * 256;
+    float* s_col_head = s_sdf_head + 260;
+    for (int i = tid; i < NL * 256; i += NTHREADS) s_sdf_b[i] = net.sdf_b[i >> 8][i & 255];
+    for (int i = tid; i < 256; i += NTHREADS) s_feat_b[i] = net.sdf_b[net.L - 1][i];
+    for (int i = tid; i < Lc1 * 256; i += NTHREADS) s_col_b[i] = net.col_b[i >> 8][i & 255];
+    for (int i = tid; i < 257; i += NTHREADS) s_sdf_head[i] = net.sdf_head[i];
+    for (int i = tid; i < 771; i += NTHREADS) s_col_head[i] = net.col_head[i];
     if (warp == 1) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
@@ -80,24 +110,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
     if (warp == 0) {
         if (lane == 0) chain_producer(T, ntiles, ring, full, empty);
     } else if (warp == 1) {
-        chain_mma(T, ntiles, tmem_base, A_hi, A_lo, ring, full, empty, a_ready, d_full);
+        chain_mma<TL>(T, ntiles, tmem_base, A_hi, A_lo, ring, full, empty, a_ready, d_full, reinterpret_cast<long long*>(P.tl));
     } else {
         // ================= epilogue warps =================
         const int q = warp & 3;
-        const int sub = (warp - 2) >> 2;
+        const int sub = (warp - 2) >> 2;                     // column group: columns 8 sub .. 8 sub + 7 of every 32-column chunk
         const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const int nsplit = 256 - net.ex;
-        const float RS2 = 0.70710678118654752f;
-        // FULL: the reverse sweep rebuilds softplus'(a_l) from h~_l, which round-trips through HBM/L2 as hi/lo plane segments:
-        // a per-CTA scratch in eval (fp16 halves: the bytes the SMEM operand gets); in training (plane slots, P.sl) every A
-        // operand is stored per point (h~_l, q_l, features, radiance activations, encodings) as bf16 halves for the backward
-        // chain and the weight gradients
-        constexpr bool save = FULL && SAVE;       // separate instantiation: the eval kernels carry none of the slot code
+        const float RS2 = 0.70710678118654752f, C1 = 144.26950408889634f, C2 = 0.0069314718055994531f;
+        const float acc_scale = T.acc_scale;
+        // The reverse sweep rebuilds softplus'(a_l) from h~_l, which round-trips through HBM/L2 as hi/lo plane segments: a per-CTA
+        // scratch in eval (fp16 halves: the bytes the SMEM operand gets); in training (plane slots, P.sl) every A operand is stored
+        // per point (h~_l, q_l, features, radiance activations, encodings) as bf16 halves for the backward chain and the weight
+        // gradients.
+        constexpr bool save = SAVE;               // separate instantiation: the eval kernel carries none of the slot code
         const planes::Layout& SL = P.sl;
         uint32_t dphase = 0, g = 0;
+        float x[3], dv[3];
         // point (and view direction) of this thread's row in a tile
-        auto load_point = [&](long long tile, float (&x)[3], float (&dv)[3]) {
+        auto load_point = [&](long long tile) {
             const long long m = tile * TM + row;
             x[0] = x[1] = x[2] = 0.f; dv[0] = 0.f; dv[1] = 0.f; dv[2] = 1.f;
             if (m < P.M) {
@@ -114,267 +146,290 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_mlp_kernel(const MlpParams P, 
                 }
             }
         };
-        // prologue: A_0 = embedding, 48 columns: sub s writes columns 16 s .. 16 s + 15 (sub 3: nothing)
-        auto prologue = [&](const float (&x)[3], long long tile) {
-            if (sub < 3) {
-                float hv[16];
+        // prologue: A_0 = embedding, 48 columns = k chunks 0..5: group sub writes chunk sub, groups 0 and 1 also chunks 4 and 5
+        auto prologue = [&](long long tile) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int i = sub * 16 + j;
-                    hv[j] = (i < net.ex) ? embed_col(x, i, net.mx) : 0.f;
+            for (int h = 0; h < 2; ++h) {
+                const int kc = sub + 4 * h;
+                if (kc < 6) {
+                    float hv[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int i = kc * 8 + j;
+                        hv[j] = (i < net.ex) ? embed_col(x, i, net.mx) : 0.f;
+                    }
+                    uint8_t* gs = save ? SL.base + SL.E() + planes::seg(tile * TM + row, kc, planes::SMALL_CHUNKS) : nullptr;
+                    store_a8<true, !save>(A_hi, A_lo, row, kc, hv, gs, true, true, (uint32_t)planes::SMALL_PLANE);
                 }
-                uint8_t* g = save ? SL.base + SL.E() + planes::seg(tile * TM + row, sub * 2, planes::SMALL_CHUNKS) : nullptr;
-                store_a16<true, !save>(A_hi, A_lo, row, sub * 2, hv, g, (uint32_t)planes::SMALL_PLANE);
             }
-            publish_chunk(&a_ready[sub >> 1], lane);
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&a_ready[0]); mbar_arrive(&a_ready[1]); }
         };
-        float x[3], dv[3];
-        if ((long long)blockIdx.x < ntiles) { load_point(blockIdx.x, x, dv); prologue(x, blockIdx.x); }
+        if ((long long)blockIdx.x < ntiles) { load_point(blockIdx.x); prologue(blockIdx.x); }
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const long long m = tile * TM + row;
             const bool valid = m < P.M;
             const long long next_tile = tile + gridDim.x;
-            float xn[3] = {0.f, 0.f, 0.f}, dvn[3] = {0.f, 0.f, 1.f};
-            // h~_l (the A operands of the SDF stack) are what the reverse sweep rebuilds softplus' from.  Training: the H slots of
-            // the saved state (indexed by point).  Eval: a per-CTA scratch holding ONE tile in the same plane format (indexed by
-            // row), so the same 16-byte hi/lo segments the SMEM operand gets are stored / re-loaded fully coalesced.
-            // hbase stays null for the sdf + features table (no reverse sweep, nothing to keep).
+            // h~_l storage the reverse sweep reads back: training = H slots (by point), eval = per-CTA scratch holding ONE tile (by row);
+            // null for the sdf + features table (no reverse sweep)
             uint8_t* hbase = nullptr;
             size_t hstride = 0;
             long long hm = 0;
-            if (FULL) {
-                if (save) { hbase = SL.base + SL.H(0); hstride = SL.big; hm = m; }
-                else if (P.scratch) { hbase = reinterpret_cast<uint8_t*>(P.scratch) + (size_t)blockIdx.x * (size_t)NL * planes::BIG_TILE; hstride = planes::BIG_TILE; hm = row; }
-            }
+            if (save) { hbase = SL.base + SL.H(0); hstride = SL.big; hm = m; }
+            else if (P.scratch) { hbase = reinterpret_cast<uint8_t*>(P.scratch) + (size_t)blockIdx.x * (size_t)NL * planes::BIG_TILE; hstride = planes::BIG_TILE; hm = row; }
 
             float head = 0.f, rgbp[3] = {0.f, 0.f, 0.f}, gacc[3] = {0.f, 0.f, 0.f};
             for (int op = 0; op < T.nops; ++op, ++g) {
                 const uint32_t b = g & 1u;
                 const int kind = T.ops[op].kind, l = T.ops[op].layer;
+                const bool last_op = (op == T.nops - 1);
+                long long* tlw = (TL && P.tl && lane == 0 && blockIdx.x == 0 && tile == (long long)gridDim.x)
+                                     ? reinterpret_cast<long long*>(P.tl) + (op * 16 + (warp - 2)) * 4 : nullptr;
+                if (TL && tlw) tlw[0] = clock64();
                 mbar_wait(&d_full[b], (dphase >> b) & 1u);
                 dphase ^= (1u << b);
                 tc_fence_after();
-                if (op == T.nops - 1 && next_tile < ntiles) {
-                    // the A operand is free (this tile's last MMAs are done): start the NEXT tile's first layer now, so its
-                    // tensor work overlaps this tile's last epilogue
-                    load_point(next_tile, xn, dvn);
-                    prologue(xn, next_tile);
-                }
-#pragma unroll 1
-                for (int it = 0; it < 4; ++it) {
-                    const int c = 2 * it + (sub >> 1);                 // 32-column chunk
-                    const int col0 = c * 32 + (sub & 1) * 16;          // first of this warp's 16 columns
-                    if (FULL && kind == EK_GRAD && col0 >= 48) break;
-                    // global operands of this item (bias, or the softplus' row of the reverse sweep) are requested BEFORE the
-                    // TMEM load so their latency overlaps it (the tcgen05.wait::ld below is a compiler barrier)
-                    uint4 pre[4];
-                    if (FULL && (kind == EK_REV || kind == EK_COL_LAST)) {
-                        load_slot16(hbase + (size_t)(kind == EK_REV ? l - 1 : NL - 1) * hstride + planes::seg(hm, col0 >> 3, planes::BIG_CHUNKS), pre);
-                    } else {
-                        const float* psrc;
-                        if (kind == EK_SDF_HIDDEN || kind == EK_SDF_LAST || kind == EK_SDF_LAST_REV) psrc = net.sdf_b[l] + col0;
-                        else if (FULL && kind == EK_FEAT) psrc = net.sdf_b[net.L - 1] + col0;
-                        else if (FULL && kind == EK_COL_HIDDEN) psrc = net.col_b[l] + col0;
-                        else psrc = net.sdf_head;
+                if (TL && tlw) tlw[1] = clock64();
+                const uint32_t acc_addr = tmem_base + lane_base + b * 256u;
+                if (hbase && !last_op) {
+                    // the next op's stored h~ (written up to 20 ops ago, possibly evicted to HBM): pull this thread's 16 segments into L2 now
+                    const int nk = T.ops[op + 1].kind, nl = T.ops[op + 1].layer;
+                    if (nk == EK_REV || nk == EK_COL_LAST) {
+                        const uint8_t* ns = hbase + (size_t)(nk == EK_COL_LAST ? NL - 1 : nl - 1) * hstride + planes::seg(hm, sub, planes::BIG_CHUNKS);
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) pre[j4] = *reinterpret_cast<const uint4*>(psrc + j4 * 4);
+                        for (int it = 0; it < 8; ++it) { pf_l2(ns + (size_t)it * 4 * planes::SUB_CHUNK); pf_l2(ns + (size_t)it * 4 * planes::SUB_CHUNK + planes::BIG_PLANE); }
                     }
-                    uint32_t v[16];
-                    tmem_ld16(tmem_base + lane_base + b * 256u + (uint32_t)col0, v);
-                    tmem_ld_wait();
-                    float hv[16];
-                    if (kind == EK_SDF_HIDDEN || kind == EK_SDF_LAST || kind == EK_SDF_LAST_REV) {
+                }
+
+                auto items = [&](auto kind_c) {
+                    constexpr int K = decltype(kind_c)::value;
+                    constexpr bool is_f = (K == K_F || K == K_FSKIP || K == K_FLAST || K == K_FLASTREV);
+                    constexpr bool has_bias = is_f || K == K_G || K == K_C || K == K_CLAST;
+                    constexpr bool loads_h = (K == K_CLAST || K == K_REV || K == K_REVSKIP);
+                    const float* __restrict__ bias = nullptr;
+                    if (is_f) bias = s_sdf_b + l * 256;
+                    else if (K == K_G) bias = s_feat_b;
+                    else if (K == K_C || K == K_CLAST) bias = s_col_b + l * 256;
+                    const uint8_t* hsrc = nullptr;             // stored h~ the item needs: h_{NL-1} (reverse prologue) / h~_{l-1}
+                    if (loads_h) hsrc = hbase + (size_t)(K == K_CLAST ? NL - 1 : l - 1) * hstride;
+                    const float hs = (K == K_REVSKIP) ? C1 * 1.41421356237309505f : C1;
+                    // stored h~ segments travel one item ahead in registers (they come from L2 / HBM: the scratch of 148 CTAs exceeds L2)
+                    uint4 ph = make_uint4(0, 0, 0, 0), pl = ph;
+                    if (loads_h) {
+                        const uint8_t* ps = hsrc + planes::seg(hm, sub, planes::BIG_CHUNKS);
+                        ph = ldg_cs(ps);
+                        pl = ldg_cs(ps + planes::BIG_PLANE);
+                    }
+#pragma unroll 2
+                    for (int it = 0; it < (K == K_GRAD ? 2 : 8); ++it) {
+                        const int col0 = it * 32 + sub * 8, kc = it * 4 + sub;
+                        if (K == K_GRAD && col0 >= 48) break;
+                        uint32_t v[8];
+                        tmem_ld8(acc_addr + (uint32_t)col0, v);
+                        uint4 nph = ph, npl = pl;
+                        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                        if (loads_h && it < 7) {
+                            const uint8_t* ps = hsrc + planes::seg(hm, kc + 4, planes::BIG_CHUNKS);
+                            nph = ldg_cs(ps);
+                            npl = ldg_cs(ps + planes::BIG_PLANE);
+                        }
+                        if (has_bias) { b0 = *reinterpret_cast<const float4*>(bias + col0); b1 = *reinterpret_cast<const float4*>(bias + col0 + 4); }
+                        tmem_ld_wait();
+                        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                        float hv[8];
+                        uint32_t ch[4], cl[4];                 // K_CLAST in training: the split last radiance activation, stored behind the publish
+                        uint8_t* gs = nullptr;                 // slot / scratch segment this item stores to
+                        bool keep = true;
+                        if (is_f) {
+                            float sp[8];
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            const float bv[4] = {__uint_as_float(pre[j4].x), __uint_as_float(pre[j4].y), __uint_as_float(pre[j4].z), __uint_as_float(pre[j4].w)};
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const float a = fmaf(__uint_as_float(v[j4 * 4 + u]), T.acc_scale, bv[u]);
-                                const float e = ex2_approx(-fabsf(a) * 144.26950408889634f);          // exp(-|100 a|)
-                                hv[j4 * 4 + u] = fmaf(lg2_approx(1.0f + e), 0.0069314718055994531f, fmaxf(a, 0.0f));
-                                if (FULL && kind == EK_SDF_LAST_REV) {
+                            for (int j = 0; j < 8; ++j) {
+                                const float a = fmaf(__uint_as_float(v[j]), acc_scale, bv[j]);
+                                const float e = ex2_approx(-fabsf(a) * C1);          // exp(-|100 a|)
+                                hv[j] = fmaf(lg2_approx(1.0f + e), C2, fmaxf(a, 0.0f));
+                                if (K == K_FLASTREV) {
                                     const float rr = rcp_approx(1.0f + e);
-                                    v[j4 * 4 + u] = __float_as_uint((a >= 0.f) ? rr : e * rr);      // softplus'(a) = sigmoid(100 a); the accumulator is consumed: keep it there
+                                    sp[j] = (a >= 0.f) ? rr : e * rr;                 // softplus'(a) = sigmoid(100 a)
                                 }
                             }
-                        }
-                        if (FULL && kind == EK_SDF_LAST_REV) {
-                            // sdf + grad only: head, h_{NL-1} to its slot, then straight into the reverse sweep: q = w_sdf * softplus'
-                            if (save) store_a16<true, false>(A_hi, A_lo, row, col0 >> 3, hv, SL.base + SL.H(l) + planes::seg(m, col0 >> 3, planes::BIG_CHUNKS),
-                                                             (uint32_t)planes::BIG_PLANE, true, false);
+                            if (K == K_FSKIP) {                // cat([h, embed]) / sqrt(2)   (mlp.py:94-95)
+                                if (col0 + 8 > nsplit) {       // warp-uniform: only the items that reach into the embedding part
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const float w = __ldg(net.sdf_head + col0 + j);
-                                head = fmaf(hv[j], w, head);
-                                hv[j] = w * __uint_as_float(v[j]);
+                                    for (int j = 0; j < 8; ++j) {
+                                        const int f = col0 + j;
+                                        if (f >= nsplit) hv[j] = embed_col(x, f - nsplit, net.mx);
+                                    }
+                                }
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) hv[j] *= RS2;
                             }
-                        }
-                        if (kind == EK_SDF_LAST) {
+                            if (K == K_FLAST || K == K_FLASTREV) {
+                                const float4 w0 = *reinterpret_cast<const float4*>(s_sdf_head + col0), w1 = *reinterpret_cast<const float4*>(s_sdf_head + col0 + 4);
+                                const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                            for (int j4 = 0; j4 < 4; ++j4) {
-                                const float4 w = __ldg(reinterpret_cast<const float4*>(net.sdf_head + col0) + j4);
-                                head = fmaf(hv[j4 * 4 + 0], w.x, head);
-                                head = fmaf(hv[j4 * 4 + 1], w.y, head);
-                                head = fmaf(hv[j4 * 4 + 2], w.z, head);
-                                head = fmaf(hv[j4 * 4 + 3], w.w, head);
+                                for (int j = 0; j < 8; ++j) head = fmaf(hv[j], w[j], head);
+                                if (K == K_FLASTREV) {
+                                    // sdf + grad only: h_{NL-1} to its slot, then straight into the reverse sweep: q = w_sdf * softplus'
+                                    if (save) store_a8<true, false>(A_hi, A_lo, row, kc, hv, SL.base + SL.H(l) + planes::seg(m, kc, planes::BIG_CHUNKS), true, false);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) hv[j] = w[j] * sp[j];
+                                }
                             }
-                            if (!FULL) continue;                       // sdf-only: nothing follows the last hidden layer
-                        } else if (l + 1 == net.skip) {                // cat([h, embed]) / sqrt(2)   (mlp.py:94-95)
+                            if (K == K_FLASTREV) { if (save) { gs = SL.base + SL.Q(NL - 1) + planes::seg(m, kc, planes::BIG_CHUNKS); keep = valid; } }
+                            else if (save) gs = SL.base + SL.H(l) + planes::seg(m, kc, planes::BIG_CHUNKS);
+                            else if (hbase) gs = hbase + (size_t)l * hstride + planes::seg(hm, kc, planes::BIG_CHUNKS);
+                        } else if (K == K_G) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const int f = col0 + j;
-                                hv[j] = ((f >= nsplit) ? embed_col(x, f - nsplit, net.mx) : hv[j]) * RS2;
+                            for (int j = 0; j < 8; ++j) hv[j] = fmaf(__uint_as_float(v[j]), acc_scale, bv[j]);
+                            if (last_op) {                     // sdf + features only: nothing follows
+                                if (P.out_feat && valid) {
+                                    float4* o4 = reinterpret_cast<float4*>(P.out_feat + (size_t)m * 256 + col0);
+                                    o4[0] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                                    o4[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
+                                }
+                                continue;
                             }
-                        }
-                    } else if (FULL && (kind == EK_FEAT || kind == EK_COL_HIDDEN || kind == EK_COL_LAST)) {
-                        const float* __restrict__ bias = (kind == EK_FEAT ? net.sdf_b[net.L - 1] : net.col_b[l]) + col0;
+                            if (save) gs = SL.base + SL.CF() + planes::seg(m, kc, planes::BIG_CHUNKS);
+                        } else if (K == K_C || K == K_CLAST) {
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            const float4 bb = (kind == EK_COL_LAST) ? __ldg(reinterpret_cast<const float4*>(bias) + j4)
-                                                                    : make_float4(__uint_as_float(pre[j4].x), __uint_as_float(pre[j4].y), __uint_as_float(pre[j4].z), __uint_as_float(pre[j4].w));
-                            hv[j4 * 4 + 0] = fmaf(__uint_as_float(v[j4 * 4 + 0]), T.acc_scale, bb.x);
-                            hv[j4 * 4 + 1] = fmaf(__uint_as_float(v[j4 * 4 + 1]), T.acc_scale, bb.y);
-                            hv[j4 * 4 + 2] = fmaf(__uint_as_float(v[j4 * 4 + 2]), T.acc_scale, bb.z);
-                            hv[j4 * 4 + 3] = fmaf(__uint_as_float(v[j4 * 4 + 3]), T.acc_scale, bb.w);
-                        }
-                        if (kind != EK_FEAT) {
+                            for (int j = 0; j < 8; ++j) hv[j] = fmaxf(fmaf(__uint_as_float(v[j]), acc_scale, bv[j]), 0.f);
+                            if (K == K_C) { if (save) gs = SL.base + SL.C(l) + planes::seg(m, kc, planes::BIG_CHUNKS); }
+                            else {
+                                const float* __restrict__ wh = s_col_head + col0;
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) hv[j] = fmaxf(hv[j], 0.f);
-                        } else if (P.out_feat && valid) {
+                                for (int c = 0; c < 3; ++c) {
+                                    const float4 w0 = *reinterpret_cast<const float4*>(wh + c * 256), w1 = *reinterpret_cast<const float4*>(wh + c * 256 + 4);
+                                    rgbp[c] = fmaf(hv[0], w0.x, fmaf(hv[1], w0.y, fmaf(hv[2], w0.z, fmaf(hv[3], w0.w, rgbp[c]))));
+                                    rgbp[c] = fmaf(hv[4], w1.x, fmaf(hv[5], w1.y, fmaf(hv[6], w1.z, fmaf(hv[7], w1.w, rgbp[c]))));
+                                }
+                                // last radiance activation: slot only (stored behind the publish below); then the reverse prologue: adjoint of
+                                // a_{NL-1} = w_sdf * softplus'(a_{NL-1})
+                                if (save) {
 #pragma unroll
-                            for (int j4 = 0; j4 < 4; ++j4)
-                                *reinterpret_cast<float4*>(P.out_feat + (size_t)m * 256 + col0 + j4 * 4) =
-                                    make_float4(hv[j4 * 4], hv[j4 * 4 + 1], hv[j4 * 4 + 2], hv[j4 * 4 + 3]);
-                        }
-                        if (kind == EK_FEAT && op == T.nops - 1) continue;     // sdf + features only: nothing follows
-                        if (kind == EK_COL_LAST) {
-                            const float* __restrict__ wh = net.col_head + col0;
+                                    for (int i = 0; i < 4; ++i) split_bf16x2(hv[2 * i], hv[2 * i + 1], ch[i], cl[i]);
+                                }
+                                seg8_values<!save>(ph, pl, hv);                       // h_{NL-1}
+                                const float4 w0 = *reinterpret_cast<const float4*>(s_sdf_head + col0), w1 = *reinterpret_cast<const float4*>(s_sdf_head + col0 + 4);
+                                const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                            for (int j4 = 0; j4 < 4; ++j4) {
-                                const float4 w0 = __ldg(reinterpret_cast<const float4*>(wh) + j4);
-                                const float4 w1 = __ldg(reinterpret_cast<const float4*>(wh + 256) + j4);
-                                const float4 w2 = __ldg(reinterpret_cast<const float4*>(wh + 512) + j4);
-                                const float* hh = hv + j4 * 4;
-                                rgbp[0] = fmaf(hh[0], w0.x, fmaf(hh[1], w0.y, fmaf(hh[2], w0.z, fmaf(hh[3], w0.w, rgbp[0]))));
-                                rgbp[1] = fmaf(hh[0], w1.x, fmaf(hh[1], w1.y, fmaf(hh[2], w1.z, fmaf(hh[3], w1.w, rgbp[1]))));
-                                rgbp[2] = fmaf(hh[0], w2.x, fmaf(hh[1], w2.y, fmaf(hh[2], w2.z, fmaf(hh[3], w2.w, rgbp[2]))));
+                                for (int j = 0; j < 8; ++j) hv[j] = w[j] * (1.0f - ex2_approx(-C1 * hv[j]));
+                                if (save) { gs = SL.base + SL.Q(NL - 1) + planes::seg(m, kc, planes::BIG_CHUNKS); keep = valid; }
                             }
-                            // reverse prologue: adjoint of a_{NL-1} = w_sdf * softplus'(a_{NL-1})
-                            if (save)
-                                store_a16<true, false>(A_hi, A_lo, row, col0 >> 3, hv, SL.base + SL.C(l) + planes::seg(m, col0 >> 3, planes::BIG_CHUNKS),
-                                                       (uint32_t)planes::BIG_PLANE, true, false);          // last radiance activation: slot only
-                            slot16_values<!save>(pre, hv);                                    // h_{NL-1}
+                        } else if (K == K_REV || K == K_REVSKIP) {
+                            // accumulator = adjoint of the input of SDF layer l ; next A = (that) * softplus'(a_{l-1}), softplus' from the
+                            // stored h~_{l-1} (a skip concat stored it scaled by 1/sqrt2; its embedding part goes to grad_x through J(x)^T)
+                            float sv[8];
+                            seg8_values<!save>(ph, pl, sv);
 #pragma unroll
-                            for (int j4 = 0; j4 < 4; ++j4) {
-                                const float4 w = __ldg(reinterpret_cast<const float4*>(net.sdf_head + col0) + j4);
-                                hv[j4 * 4 + 0] = w.x * dsoftplus_from_h(hv[j4 * 4 + 0]); hv[j4 * 4 + 1] = w.y * dsoftplus_from_h(hv[j4 * 4 + 1]);
-                                hv[j4 * 4 + 2] = w.z * dsoftplus_from_h(hv[j4 * 4 + 2]); hv[j4 * 4 + 3] = w.w * dsoftplus_from_h(hv[j4 * 4 + 3]);
+                            for (int j = 0; j < 8; ++j) {
+                                const float rv = __uint_as_float(v[j]) * (K == K_REVSKIP ? RS2 * acc_scale : acc_scale);
+                                hv[j] = (rv != 0.f) ? rv * (1.0f - ex2_approx(-hs * sv[j])) : 0.f;
                             }
-                        }
-                    } else if (FULL && kind == EK_REV) {
-                        // accumulator = adjoint of the input of SDF layer l ; next A = (that) * softplus'(a_{l-1})
-                        const bool is_skip = (l == net.skip);
-                        {                  // softplus'(a_{l-1}) from the stored h~_{l-1} (a skip concat stored it scaled by 1/sqrt2)
-                            slot16_values<!save>(pre, hv);
-                            const float hs = is_skip ? 144.26950408889634f * 1.41421356237309505f : 144.26950408889634f;
+                            if (K == K_REVSKIP && col0 + 8 > nsplit) {     // warp-uniform: the items that reach into the embedding part
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) hv[j] = 1.0f - ex2_approx(-hs * hv[j]);
-                        }
-#pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            const float sv[4] = {hv[j4 * 4], hv[j4 * 4 + 1], hv[j4 * 4 + 2], hv[j4 * 4 + 3]};
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                float rv = __uint_as_float(v[j4 * 4 + u]) * (is_skip ? RS2 * T.acc_scale : T.acc_scale);
-                                if (is_skip) {
-                                    const int f = col0 + j4 * 4 + u;
+                                for (int j = 0; j < 8; ++j) {
+                                    const int f = col0 + j;
                                     if (f >= nsplit) {
                                         int coord;
                                         const float jac = embed_jac(x, f - nsplit, net.mx, coord);
+                                        const float rv = __uint_as_float(v[j]) * (RS2 * acc_scale);
                                         gacc[0] += (coord == 0) ? jac * rv : 0.f;
                                         gacc[1] += (coord == 1) ? jac * rv : 0.f;
                                         gacc[2] += (coord == 2) ? jac * rv : 0.f;
-                                        rv = 0.f;
+                                        hv[j] = 0.f;
                                     }
                                 }
-                                // (columns of the skip concat's embedding part hold PE values in the h~ slot: softplus' is meaningless there)
-                                hv[j4 * 4 + u] = (rv != 0.f) ? rv * sv[u] : 0.f;
                             }
-                        }
-                    } else if (FULL) {   // EK_GRAD: accumulator columns 0..47 = adjoint of the embedding
+                            if (save) { gs = SL.base + SL.Q(l - 1) + planes::seg(m, kc, planes::BIG_CHUNKS); keep = valid; }
+                        } else {                               // K_GRAD: accumulator columns 0..47 = adjoint of the embedding
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int i = col0 + j;
-                            if (i < net.ex) {
-                                int coord;
-                                const float jac = embed_jac(x, i, net.mx, coord);
-                                const float rv = __uint_as_float(v[j]) * T.acc_scale;
-                                gacc[0] += (coord == 0) ? jac * rv : 0.f;
-                                gacc[1] += (coord == 1) ? jac * rv : 0.f;
-                                gacc[2] += (coord == 2) ? jac * rv : 0.f;
+                            for (int j = 0; j < 8; ++j) {
+                                const int i = col0 + j;
+                                if (i < net.ex) {
+                                    int coord;
+                                    const float jac = embed_jac(x, i, net.mx, coord);
+                                    const float rv = __uint_as_float(v[j]) * acc_scale;
+                                    gacc[0] += (coord == 0) ? jac * rv : 0.f;
+                                    gacc[1] += (coord == 1) ? jac * rv : 0.f;
+                                    gacc[2] += (coord == 2) ? jac * rv : 0.f;
+                                }
+                            }
+                            continue;
+                        }
+                        {
+                            // SMEM operand first, published at once; the slot / scratch copy leaves behind the fence
+                            uint32_t hh[4], ll[4];
+                            sts_a8<true>(A_hi, A_lo, row, kc, hv, hh, ll);
+                            publish_chunk(&a_ready[it], lane);
+                            if (gs) stg_a8<!save>(gs, (uint32_t)planes::BIG_PLANE, keep, hv, hh, ll);
+                            if (K == K_CLAST && save) {
+                                uint8_t* cs = SL.base + SL.C(l) + planes::seg(m, kc, planes::BIG_CHUNKS);
+                                *reinterpret_cast<uint4*>(cs) = make_uint4(ch[0], ch[1], ch[2], ch[3]);
+                                *reinterpret_cast<uint4*>(cs + planes::BIG_PLANE) = make_uint4(cl[0], cl[1], cl[2], cl[3]);
+                            }
+                            if (K == K_G && P.out_feat && valid) {
+                                float4* o4 = reinterpret_cast<float4*>(P.out_feat + (size_t)m * 256 + col0);
+                                o4[0] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                                o4[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
                             }
                         }
-                        break;
+                        ph = nph; pl = npl;
+                        if (TL && tlw && it == 0) tlw[2] = clock64();
                     }
-                    {
-                        uint8_t* g = nullptr;
-                        bool keep = true;
-                        if (FULL && save) {
-                            size_t so;
-                            if (kind == EK_SDF_HIDDEN || kind == EK_SDF_LAST) so = SL.H(l);
-                            else if (kind == EK_FEAT) so = SL.CF();
-                            else if (kind == EK_COL_HIDDEN) so = SL.C(l);
-                            else if (kind == EK_REV) { so = SL.Q(l - 1); keep = valid; }
-                            else { so = SL.Q(NL - 1); keep = valid; }          // EK_COL_LAST / EK_SDF_LAST_REV: q_{NL-1}
-                            g = SL.base + so + planes::seg(m, col0 >> 3, planes::BIG_CHUNKS);
-                        } else if (FULL && hbase && (kind == EK_SDF_HIDDEN || kind == EK_SDF_LAST)) {
-                            g = hbase + (size_t)l * hstride + planes::seg(hm, col0 >> 3, planes::BIG_CHUNKS);      // eval: h~_l to the per-CTA scratch
-                        }
-                        store_a16<true, !save>(A_hi, A_lo, row, col0 >> 3, hv, g, (uint32_t)planes::BIG_PLANE, keep);
-                    }
-                    publish_chunk(&a_ready[c], lane);
+                    if (TL && tlw) tlw[3] = clock64();
+                };
+                // the A operand is free once the tile's last MMAs are done: start the NEXT tile's first layer inside the last epilogue
+                // (behind the items when they still need this tile's point: the Jacobians of the last reverse op)
+                const bool start_next = last_op && next_tile < ntiles;
+                if (start_next && kind != EK_GRAD) { load_point(next_tile); prologue(next_tile); }
+                switch (kind) {
+                    case EK_SDF_HIDDEN: if (l + 1 == net.skip) items(std::integral_constant<int, K_FSKIP>{}); else items(std::integral_constant<int, K_F>{}); break;
+                    case EK_SDF_LAST: items(std::integral_constant<int, K_FLAST>{}); break;
+                    case EK_SDF_LAST_REV: items(std::integral_constant<int, K_FLASTREV>{}); break;
+                    case EK_FEAT: items(std::integral_constant<int, K_G>{}); break;
+                    case EK_COL_HIDDEN: items(std::integral_constant<int, K_C>{}); break;
+                    case EK_COL_LAST: items(std::integral_constant<int, K_CLAST>{}); break;
+                    case EK_REV: if (l == net.skip) items(std::integral_constant<int, K_REVSKIP>{}); else items(std::integral_constant<int, K_REV>{}); break;
+                    default: items(std::integral_constant<int, K_GRAD>{}); break;
                 }
-                if (FULL && kind == EK_FEAT && sub < 2 && op < T.nops - 1) {
-                    // k chunk 8 (columns 256..287) = positional encoding of the view direction, zero padded
-                    float hv[16];
+                if (kind == EK_FEAT && !last_op) {
+                    // k chunk 8 (columns 256..287) = positional encoding of the view direction, zero padded: group sub writes 8 columns
+                    float hv[8];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int i = sub * 16 + j;
+                    for (int j = 0; j < 8; ++j) {
+                        const int i = sub * 8 + j;
                         hv[j] = (i < net.ed) ? embed_col(dv, i, net.md) : 0.f;
                     }
-                    uint8_t* g = save ? SL.base + SL.DV() + planes::seg(m, sub * 2, planes::DV_CHUNKS) : nullptr;
-                    store_a16<true, !save>(A_hi, A_lo, row, 32 + sub * 2, hv, g, (uint32_t)(planes::DV_CHUNKS * planes::SUB_CHUNK));
+                    uint8_t* gs = save ? SL.base + SL.DV() + planes::seg(m, sub, planes::DV_CHUNKS) : nullptr;
+                    store_a8<true, !save>(A_hi, A_lo, row, 32 + sub, hv, gs, true, true, (uint32_t)(planes::DV_CHUNKS * planes::SUB_CHUNK));
                     publish_chunk(&a_ready[8], lane);
                 }
+                if (start_next && kind == EK_GRAD) { load_point(next_tile); prologue(next_tile); }
             }
-            // ---- combine the 4 column-partials of every row and write the per-sample results
-            float* pp = part + (size_t)sub * 7 * TM;
+            // ---- combine the 4 column-group partials of every row and write the per-sample results
+            float* pp = (sub < 2 ? part01 : part23) + (size_t)(sub & 1) * 7 * TM;
             pp[row] = head;
-            if (FULL) {
-                pp[TM + row] = rgbp[0]; pp[2 * TM + row] = rgbp[1]; pp[3 * TM + row] = rgbp[2];
-                pp[4 * TM + row] = gacc[0]; pp[5 * TM + row] = gacc[1]; pp[6 * TM + row] = gacc[2];
-            }
+            pp[TM + row] = rgbp[0]; pp[2 * TM + row] = rgbp[1]; pp[3 * TM + row] = rgbp[2];
+            pp[4 * TM + row] = gacc[0]; pp[5 * TM + row] = gacc[1]; pp[6 * TM + row] = gacc[2];
             epi_bar_sync();
             if (sub == 0 && m < P.M) {
                 float acc[7];
 #pragma unroll
-                for (int k = 0; k < (FULL ? 7 : 1); ++k)
-                    acc[k] = (part[k * TM + row] + part[(7 + k) * TM + row]) + (part[(14 + k) * TM + row] + part[(21 + k) * TM + row]);
-                P.out_sdf[m] = acc[0] + __ldg(net.sdf_head + 256);
-                if (FULL) {
+                for (int k = 0; k < 7; ++k)
+                    acc[k] = (part01[k * TM + row] + part01[(7 + k) * TM + row]) + (part23[k * TM + row] + part23[(7 + k) * TM + row]);
+                P.out_sdf[m] = acc[0] + s_sdf_head[256];
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        if (P.out_rgb) {
-                            const float s = acc[1 + c] + __ldg(net.col_head + 768 + c);
-                            P.out_rgb[m * 3 + c] = __fdiv_rn(1.0f, 1.0f + expf(-s));
-                        }
-                        if (P.out_grad) P.out_grad[m * 3 + c] = acc[4 + c];
+                for (int c = 0; c < 3; ++c) {
+                    if (P.out_rgb) {
+                        const float s = acc[1 + c] + s_col_head[768 + c];
+                        P.out_rgb[m * 3 + c] = __fdiv_rn(1.0f, 1.0f + expf(-s));
                     }
+                    if (P.out_grad) P.out_grad[m * 3 + c] = acc[4 + c];
                 }
             }
             epi_bar_sync();     // part[] free for the next tile
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { x[c] = xn[c]; dv[c] = dvn[c]; }
         }
     }
     tc_fence_before();
@@ -651,7 +706,8 @@ int tc_create(i2sdf_handle* h) {
     const NetDev& n = h->net;
     const int L = n.L, NL = L - 1, Lc = n.Lc;
     // (the light-mask head is not an op of the chain: it reads the features the main pass writes, see light_forward in backward.cu)
-    const bool want_full = !(getenv("I2SDF_SIMT_MAIN") && getenv("I2SDF_SIMT_MAIN")[0] == '1');
+    // (the full chain keeps every bias and both heads in shared memory: (NL + Lc) x 256 + 1032 floats must fit M8_PARAM_FLOATS)
+    const bool want_full = !(getenv("I2SDF_SIMT_MAIN") && getenv("I2SDF_SIMT_MAIN")[0] == '1') && ((NL + Lc) * 256 + 1032 <= M8_PARAM_FLOATS);
     OpTable& T = s->full;
     int nops = 0;
     size_t off = 0;
@@ -718,8 +774,9 @@ int tc_create(i2sdf_handle* h) {
     }
     cudaError_t e = cudaFuncSetAttribute(tc_sdf8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSdf8);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_sdf8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSdf8);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_mlp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_mlp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_main8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMain);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_main8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMain);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_main8_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMain);
     if (e != cudaSuccess) { cudaFree(s->wpack); delete s; set_error("tc_create: smem attribute: %s", cudaGetErrorString(e)); return I2SDF_E_CUDA; }
     h->tc = s;
     h->tcmain = (void*)s;     // full main pass only if s->full.nops > 0 (tcmain_has_full)
@@ -805,8 +862,9 @@ int tcmain_launch(const i2sdf_handle* h, void* state, const MlpParams& p, cudaSt
     if (p.M <= 0) return I2SDF_OK;
     const State* s = (const State*)state;
     const OpTable& tab = p.want_color ? s->full : (p.out_grad ? s->sg : s->sf);
-    if (p.sl.base) tc_mlp_kernel<true, true><<<tc_grid(h, p.M), NTHREADS, kSmemBytes, st>>>(p, tab);
-    else tc_mlp_kernel<true, false><<<tc_grid(h, p.M), NTHREADS, kSmemBytes, st>>>(p, tab);
+    if (p.sl.base) tc_main8_kernel<true><<<tc_grid(h, p.M), NTHREADS, kSmemMain, st>>>(p, tab);
+    else if (p.tl) tc_main8_kernel<false, true><<<tc_grid(h, p.M), NTHREADS, kSmemMain, st>>>(p, tab);
+    else tc_main8_kernel<false><<<tc_grid(h, p.M), NTHREADS, kSmemMain, st>>>(p, tab);
     I2SDF_CUDA_CHECK(cudaGetLastError());
     return I2SDF_OK;
 }

@@ -29,16 +29,6 @@ namespace tcb {
 using namespace tc;
 using namespace chain;
 
-// 8 columns (one chunk) of a slot: hi / lo segments -> fp32
-__device__ __forceinline__ void seg8_values(const uint4& hi, const uint4& lo, float (&out)[8]) {
-    const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        out[2 * i] = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
-        out[2 * i + 1] = __uint_as_float(hw[i] & 0xffff0000u) + __uint_as_float(lw[i] & 0xffff0000u);
-    }
-}
-__device__ __forceinline__ void pf_l2(const uint8_t* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // the four 16-byte segments (hi / lo planes x two chunks) of a 16-column item
 __device__ __forceinline__ void pf_seg16(const uint8_t* seg) {
     pf_l2(seg); pf_l2(seg + planes::SUB_CHUNK); pf_l2(seg + planes::BIG_PLANE); pf_l2(seg + planes::BIG_PLANE + planes::SUB_CHUNK);
@@ -118,10 +108,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const BwdParams P, 
                     const float jac = (i < net.ex) ? embed_jac(x, i, net.mx, coord) : 0.f;
                     hv[j] = jac * (coord == 0 ? gb[0] : (coord == 1 ? gb[1] : gb[2]));
                 }
+                store_a16<false>(A_hi, A_lo, row, sub * 2, hv);
+                publish_chunk(&a_ready[sub >> 1], lane);
+                // slot copies leave BEHIND the publish: a fence.proxy.async behind a global store waits for that store (MEMBAR.ALL.CTA)
                 store_a16<false>(A_hi, A_lo, row, sub * 2, hv, SL.wbase + SL.ED() + planes::seg(tile * TM + row, sub * 2, planes::SMALL_CHUNKS),
-                          (uint32_t)planes::SMALL_PLANE);
+                                 (uint32_t)planes::SMALL_PLANE, true, false);
+            } else {
+                publish_chunk(&a_ready[sub >> 1], lane);
             }
-            publish_chunk(&a_ready[sub >> 1], lane);
         };
         float x[3], gb[3];
         if ((long long)blockIdx.x < ntiles) { load_point(blockIdx.x, x, gb); prologue(x, gb, blockIdx.x); }
@@ -195,7 +189,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const BwdParams P, 
                             hv[j] = t;
                         }
                         const bool more = (l < NL - 1);
-                        store_a16<false>(A_hi, A_lo, row, kc0, hv, SL.wbase + SL.HD(l) + sg, (uint32_t)planes::BIG_PLANE, true, more);
+                        if (more) {
+                            store_a16<false>(A_hi, A_lo, row, kc0, hv);
+                            publish_chunk(&a_ready[c], lane);
+                        }
+                        store_a16<false>(A_hi, A_lo, row, kc0, hv, SL.wbase + SL.HD(l) + sg, (uint32_t)planes::BIG_PLANE, true, false);
                         if (!more) {
                             // the tangent pass is over and its last MMAs are done: build the A operand of the reverse pass
                             if (color) {
@@ -210,14 +208,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const BwdParams P, 
                                     const float u = fmaf(delta[0], __ldg(wh + j), fmaf(delta[1], __ldg(wh + 256 + j), delta[2] * __ldg(wh + 512 + j)));
                                     hv[j] = cv > 0.f ? u : 0.f;
                                 }
-                                store_a16<false>(A_hi, A_lo, row, kc0, hv, SL.wbase + SL.PC(net.Lc - 2) + sg, (uint32_t)planes::BIG_PLANE, valid);
+                                store_a16<false>(A_hi, A_lo, row, kc0, hv);
+                                publish_chunk(&a_ready[c], lane);
+                                store_a16<false>(A_hi, A_lo, row, kc0, hv, SL.wbase + SL.PC(net.Lc - 2) + sg, (uint32_t)planes::BIG_PLANE, valid, false);
                             } else {
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) hv[j] = 0.f;     // no radiance stack: fbar = 0
                                 store_a16<false>(A_hi, A_lo, row, kc0, hv);
+                                publish_chunk(&a_ready[c], lane);
                             }
                         }
-                        publish_chunk(&a_ready[c], lane);
                     } else if (kind == BK_COL_REV) {
                         // accumulator = W_l^T pc_l ; pc_{l-1} = that * [c_{l-1} > 0]
                         const uint8_t* cs = SL.base + SL.C(l - 1) + sg;
@@ -232,8 +232,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const BwdParams P, 
                             const float cv = (j & 1) ? __uint_as_float(cw[j >> 1] & 0xffff0000u) : __uint_as_float(cw[j >> 1] << 16);
                             hv[j] = cv > 0.f ? __uint_as_float(v[j]) : 0.f;
                         }
-                        store_a16<false>(A_hi, A_lo, row, kc0, hv, SL.wbase + SL.PC(l - 1) + sg, (uint32_t)planes::BIG_PLANE, valid);
+                        store_a16<false>(A_hi, A_lo, row, kc0, hv);
                         publish_chunk(&a_ready[c], lane);
+                        store_a16<false>(A_hi, A_lo, row, kc0, hv, SL.wbase + SL.PC(l - 1) + sg, (uint32_t)planes::BIG_PLANE, valid, false);
                     } else if (kind == BK_FEAT_ADJ) {
                         // accumulator = adjoint of the features
                         uint32_t v[16];
@@ -242,14 +243,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const BwdParams P, 
                         float hv[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) hv[j] = __uint_as_float(v[j]);
-                        store_a16<false>(A_hi, A_lo, row, kc0, hv, SL.wbase + SL.FB() + sg, (uint32_t)planes::BIG_PLANE, valid);
+                        store_a16<false>(A_hi, A_lo, row, kc0, hv);
                         publish_chunk(&a_ready[c], lane);
+                        store_a16<false>(A_hi, A_lo, row, kc0, hv, SL.wbase + SL.FB() + sg, (uint32_t)planes::BIG_PLANE, valid, false);
                     } else {
                         // BK_P: accumulator = W_{l+1}^T p_{l+1} ; produce p_l (l = op.layer), 8 columns at a time
                         const bool feeds_skip = (l + 1 == net.skip);
                         const bool top = (l == NL - 1);
                         const float hs = feeds_skip ? 144.26950408889634f * S2 : 144.26950408889634f;
-#pragma unroll 1
+                        float pv16[16];
+#pragma unroll
                         for (int s = 0; s < 2; ++s) {
                             const size_t sg8 = sg + (size_t)s * planes::SUB_CHUNK;
                             const uint8_t* ph = SL.base + SL.H(l) + sg8;
@@ -279,9 +282,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const BwdParams P, 
                                 if (feeds_skip && f >= nsplit) p = 0.f;
                                 pv[j] = p;
                             }
-                            store_a8<false>(A_hi, A_lo, row, kc0 + s, pv, SL.wbase + SL.P(l) + sg8, valid, !last_op);
+                            if (!last_op) store_a8<false>(A_hi, A_lo, row, kc0 + s, pv, nullptr, true, true);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) pv16[s * 8 + j] = pv[j];
                         }
                         if (!last_op) publish_chunk(&a_ready[c], lane);
+                        store_a16<false>(A_hi, A_lo, row, kc0, pv16, SL.wbase + SL.P(l) + sg, (uint32_t)planes::BIG_PLANE, valid, false);
                     }
                 }
             }

@@ -85,9 +85,11 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                  : "r"(taddr)
                  : "memory");
 }
-// one chunk (8 columns) of a row of the next A operand and / or of a slot (slot format = operand format)
-template <bool F16S>
-__device__ __forceinline__ void store_a8(uint8_t* A_hi, uint8_t* A_lo, int row, int kc, const float (&hv)[8], uint8_t* g, bool keep, bool to_smem) {
+// one chunk (8 columns) of a row of the next A operand and / or of a slot; g = HI segment, g_lo = byte distance to the LO plane
+// (SLOT_SAME as in store_a16)
+template <bool F16S, bool SLOT_SAME = true>
+__device__ __forceinline__ void store_a8(uint8_t* A_hi, uint8_t* A_lo, int row, int kc, const float (&hv)[8], uint8_t* g, bool keep, bool to_smem,
+                                         uint32_t g_lo = (uint32_t)planes::BIG_PLANE) {
     uint32_t h[4], lo[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) split2<F16S>(hv[2 * i], hv[2 * i + 1], h[i], lo[i]);
@@ -97,8 +99,46 @@ __device__ __forceinline__ void store_a8(uint8_t* A_hi, uint8_t* A_lo, int row, 
         *reinterpret_cast<uint4*>(A_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
     if (g) {
+        if (!SLOT_SAME) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_bf16x2(hv[2 * i], hv[2 * i + 1], h[i], lo[i]);
+        }
         *reinterpret_cast<uint4*>(g) = keep ? make_uint4(h[0], h[1], h[2], h[3]) : make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(g + planes::BIG_PLANE) = keep ? make_uint4(lo[0], lo[1], lo[2], lo[3]) : make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(g + g_lo) = keep ? make_uint4(lo[0], lo[1], lo[2], lo[3]) : make_uint4(0, 0, 0, 0);
+    }
+}
+// the same in two steps, for epilogues that publish the SMEM operand BEFORE they store the slot copy (a fence.proxy.async behind a
+// global store compiles to MEMBAR.ALL.CTA and waits for that store: measured on the main pass, F ops 10-12 k clocks per epilogue with
+// the slot / scratch store in front of the fence against 6 k for ops without one)
+template <bool F16S>
+__device__ __forceinline__ void sts_a8(uint8_t* A_hi, uint8_t* A_lo, int row, int kc, const float (&hv)[8], uint32_t (&h)[4], uint32_t (&lo)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split2<F16S>(hv[2 * i], hv[2 * i + 1], h[i], lo[i]);
+    const uint32_t off = seg_off<TM>(row, kc);
+    *reinterpret_cast<uint4*>(A_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(A_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+template <bool SLOT_SAME>
+__device__ __forceinline__ void stg_a8(uint8_t* g, uint32_t g_lo, bool keep, const float (&hv)[8], uint32_t (&h)[4], uint32_t (&lo)[4]) {
+    if (!SLOT_SAME) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_bf16x2(hv[2 * i], hv[2 * i + 1], h[i], lo[i]);
+    }
+    // streaming stores: the eval scratch is read back once by the same CTA, the training slots once by the backward kernels, and
+    // neither should push the weight blocks out of L2
+    stg_cs(g, keep ? make_uint4(h[0], h[1], h[2], h[3]) : make_uint4(0, 0, 0, 0));
+    stg_cs(g + g_lo, keep ? make_uint4(lo[0], lo[1], lo[2], lo[3]) : make_uint4(0, 0, 0, 0));
+}
+__device__ __forceinline__ void pf_l2(const uint8_t* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// 8 columns (one chunk) of a slot: hi / lo segments -> fp32
+template <bool F16 = false>
+__device__ __forceinline__ void seg8_values(const uint4& hi, const uint4& lo, float (&out)[8]) {
+    const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 v = F16 ? join_f16x2(hw[i], lw[i]) : join_bf16x2(hw[i], lw[i]);
+        out[2 * i] = v.x;
+        out[2 * i + 1] = v.y;
     }
 }
 
@@ -149,6 +189,7 @@ __device__ __forceinline__ float embed_jac(const float (&x)[3], int i, int mx, i
 // is signalled without a copy), so an op always starts at stage 0 and the MMA issuer's loop over the stages can be unrolled.
 __device__ __forceinline__ void chain_producer(const OpTable& T, long long ntiles, uint8_t* ring, uint64_t* full, uint64_t* empty) {
     uint32_t phase = 0;
+    const uint64_t pol = l2_policy_evict_last();
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int op = 0; op < T.nops; ++op) {
             const uint32_t sb = (uint32_t)T.ops[op].n * 64u;
@@ -161,7 +202,7 @@ __device__ __forceinline__ void chain_producer(const OpTable& T, long long ntile
                     mbar_wait(&empty[st], phase ^ 1);
                     if (ks < nks) {
                         mbar_arrive_expect_tx(&full[st], sb);
-                        bulk_g2s(ring + st * STAGE_MAX, src + (size_t)ks * sb, sb, &full[st]);
+                        bulk_g2s_hint(ring + st * STAGE_MAX, src + (size_t)ks * sb, sb, &full[st], pol);
                     } else {
                         mbar_arrive(&full[st]);
                     }

@@ -21,6 +21,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // makes it generic: the operand stores of the epilogues then compile to ST.E.128 with 64-bit address arithmetic and a
 // per-item S2UR SR_CgaCtaId / SR_SWINHI window rebuild instead of STS.128 - seen in the SASS of every chain kernel.)
 __device__ __forceinline__ uint8_t* smem_align1024(uint8_t* raw) { return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u); }
+// (the operand layouts used here are un-swizzled: descriptors and bulk copies need 16-byte alignment only)
+__device__ __forceinline__ uint8_t* smem_align128(uint8_t* raw) { return raw + ((128u - (smem_u32(raw) & 127u)) & 127u); }
 
 // ---- mbarrier ------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -65,6 +67,27 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+// the same with an L2 eviction-priority hint (createpolicy): the 3-6 MB of packed weights are re-read by every CTA for every tile and
+// must survive the streaming scratch / slot traffic of the chain kernels in L2
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
+}
+// streaming (evict-first) 16-byte global accesses for data that is written once and read once (per-CTA scratch)
+__device__ __forceinline__ void stg_cs(void* p, const uint4& v) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ldg_cs(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
 }
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -280,7 +280,8 @@ class I2SDFNetwork(nn.Module):
         self._tape_override = None       # test hook: dict of RNG tapes / reference z's (see autograd.forward_train)
         # rays of one batch sharded over several GPUs: a torch.distributed group here makes the sampler's convergence test
         # batch-global again (parallel.use_global_convergence); None = per-call test, as a single-GPU reference run has it
-        self.convergence_group = None
+        self.convergence_group = None          # training forwards: batch-global sampler convergence over this group (parallel.use_global_convergence)
+        self.convergence_group_eval = None     # eval forwards: explicit opt-in only (rank-0-only validation must not enter a collective)
 
     def get_param_groups(self, lr):
         return [{"params": self.parameters(), "lr": lr}]
@@ -350,7 +351,7 @@ class I2SDFNetwork(nn.Module):
         o, d, dnorm = core.rays(input["uv"], input["pose"], input["intrinsics"])
         R = o.shape[0]
         beta = self.density.beta.detach()
-        z, z_eik = core.sample(o, d, beta, None, group=self.convergence_group)
+        z, z_eik = core.sample(o, d, beta, None, group=self.convergence_group_eval)
         # grad_x is always evaluated (the reference's returns_grad is True in eval, network/__init__.py:109); this also
         # keeps predict_only calls on the same kernels, hence bit-identical to the full call
         out = core.render(o, d, dnorm, z, beta, want_normal=True, want_light=self.use_light)

@@ -41,7 +41,7 @@ class Adam(torch.optim.Optimizer):
             beta1, beta2 = group["betas"]
             # the step counters are host tensors (torch.optim.Adam's state layout); parameters created together share ONE
             # tensor object so that a step costs one host increment, not one per parameter
-            steps, seen = set(), set()
+            seen = set()
             for p in ps:
                 if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous() or p.grad.is_sparse:
                     raise _lib.I2SDFError("i2sdf_b200.optim.Adam needs contiguous fp32 CUDA parameters with dense gradients")
@@ -57,24 +57,35 @@ class Adam(torch.optim.Optimizer):
                 if id(sp) not in seen:
                     seen.add(id(sp))
                     sp += 1
-                    steps.add(float(sp))
-            if len(steps) != 1:
-                raise _lib.I2SDFError("i2sdf_b200.optim.Adam: the parameters of one group must share their step count")
-            t = steps.pop()
+            # one launch per distinct step count: normally ONE for the whole group; a parameter that got its first gradient later
+            # than the others (a loss term switched on mid-training) runs on its own count, as in torch.optim.Adam
+            by_step = {}
+            for p in ps:
+                by_step.setdefault(float(self.state[p]["step"]), []).append(p)
             dev = ps[0].device
-            grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in ps]
             with torch.cuda.device(dev):
                 stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-                for lo in range(0, len(ps), _lib.ADAM_MAX_JOBS):
-                    b = _lib.AdamBatch()
-                    chunk = ps[lo:lo + _lib.ADAM_MAX_JOBS]
-                    b.n, b.beta1, b.beta2, b.eps = len(chunk), beta1, beta2, group["eps"]
-                    b.one_minus_beta1, b.one_minus_beta2 = 1.0 - beta1, 1.0 - beta2
-                    b.step_size = group["lr"] / (1.0 - beta1 ** t)
-                    b.bias_correction2_sqrt = math.sqrt(1.0 - beta2 ** t)
-                    for i, p in enumerate(chunk):
-                        st, j = self.state[p], b.jobs[i]
-                        j.param, j.grad, j.numel = p.data_ptr(), grads[lo + i].data_ptr(), p.numel()
-                        j.exp_avg, j.exp_avg_sq = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
-                    _lib.check(lib.i2sdf_adam_step(C.byref(b), stream), "i2sdf_adam_step")
+                for t, plist in by_step.items():
+                    grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in plist]
+                    for lo in range(0, len(plist), _lib.ADAM_MAX_JOBS):
+                        b = _lib.AdamBatch()
+                        chunk = plist[lo:lo + _lib.ADAM_MAX_JOBS]
+                        b.n, b.beta1, b.beta2, b.eps = len(chunk), beta1, beta2, group["eps"]
+                        b.one_minus_beta1, b.one_minus_beta2 = 1.0 - beta1, 1.0 - beta2
+                        b.step_size = group["lr"] / (1.0 - beta1 ** t)
+                        b.bias_correction2_sqrt = math.sqrt(1.0 - beta2 ** t)
+                        for i, p in enumerate(chunk):
+                            st, j = self.state[p], b.jobs[i]
+                            j.param, j.grad, j.numel = p.data_ptr(), grads[lo + i].data_ptr(), p.numel()
+                            j.exp_avg, j.exp_avg_sq = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
+                        _lib.check(lib.i2sdf_adam_step(C.byref(b), stream), "i2sdf_adam_step")
+                    del grads
         return loss
+
+    def state_dict(self):
+        """torch.optim.Adam's layout with ONE step tensor PER PARAMETER: inside this optimizer the parameters of a group share a
+        step tensor object (one host increment per step); saved as is, `torch.save` would keep that aliasing and a
+        torch.optim.Adam loading the checkpoint would then advance the shared counter once per parameter."""
+        sd = super().state_dict()
+        sd["state"] = {k: ({**v, "step": v["step"].clone()} if "step" in v else dict(v)) for k, v in sd["state"].items()}
+        return sd

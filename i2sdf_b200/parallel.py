@@ -63,16 +63,23 @@ def seed_rank(seed: int, rank: int, device: Optional[torch.device] = None) -> in
     return s
 
 
-def use_global_convergence(model, group: Optional[dist.ProcessGroup] = None, enable: bool = True):
+def use_global_convergence(model, group: Optional[dist.ProcessGroup] = None, enable: bool = True, eval_forwards: bool = False):
     """Make the error-bounded sampler's convergence test global over all ranks' rays (strict sharding parity).
 
     The reference stops up-sampling when `beta.max() <= beta0` over the rays of ONE forward call (ray_sampler.py:151), so a
     shard on its own may stop a round earlier than the full batch would and then draws different z's.  With this switch
     every round MAX-all-reduces its 4-byte convergence word over `group` (NCCL, in stream order, no host sync): the
-    sharded render then equals the single-GPU render of the whole batch bit for bit (tests/test_multigpu.py)."""
+    sharded step / render then equals the single-GPU one of the whole batch bit for bit (tests/test_multigpu.py).
+
+    Training forwards only, unless `eval_forwards` is set: an eval-mode forward that enters a collective deadlocks as soon
+    as the ranks do not ALL call it the same number of times - rank-0-only validation / plotting, or `render_image(group=)`
+    dealing an odd number of chunks.  With `eval_forwards=True` every rank must issue the same eval forwards (e.g. one
+    sharded batch rendered by all ranks together); `render_image(group=)` switches it off around its own chunk loop."""
     if enable and not (dist.is_available() and dist.is_initialized()):
         raise RuntimeError("use_global_convergence needs an initialised torch.distributed process group")
-    model.convergence_group = (group if group is not None else dist.group.WORLD) if enable else None
+    g = (group if group is not None else dist.group.WORLD) if enable else None
+    model.convergence_group = g
+    model.convergence_group_eval = g if eval_forwards else None
     return model
 
 
@@ -90,22 +97,96 @@ def use_global_loss_means(loss_fn, group: Optional[dist.ProcessGroup] = None, en
     return loss_fn
 
 
+class GradBucket:
+    """ONE persistent flat gradient buffer for all parameters: the all-reduce runs on it directly, the optimizer reads it.
+
+    Round 1 flattened with `torch.cat` before and un-flattened with `_foreach_copy_` after every all-reduce (two extra passes
+    over 3.2 MB + their launches, SCALE_r01: +0.28 ms per step at 8 GPUs against ~0.03 ms of wire time).  Here every
+    parameter's `.grad` IS a view of the flat buffer: the weight-norm backward (the last kernel of `loss.backward()`, which
+    produces 99.5 % of the gradient bytes) writes dg / dv straight into its views (`autograd._WeightNormAll`), the few
+    tensors autograd produced elsewhere (biases, density.beta) are copied in by one multi-tensor kernel, parameters without
+    a gradient contribute zeros - so the flat size is identical on every rank whatever terms a shard happened to have.
+
+        bucket = GradBucket(model.parameters())
+        loss.backward(); bucket.allreduce(group); opt.step(); bucket.zero()          # zero() instead of opt.zero_grad()
+    """
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("GradBucket: no parameters")
+        ref = self.params[0]
+        offs, n = [], 0
+        for p in self.params:
+            if p.dtype != ref.dtype or p.device != ref.device:
+                raise ValueError("GradBucket: parameters must share dtype and device")
+            offs.append(n)
+            n += (p.numel() + 3) // 4 * 4                   # 16-byte aligned views
+        self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device)
+        self.views = [self.flat[o:o + p.numel()].view(p.shape) for o, p in zip(offs, self.params)]
+        from . import autograd as _ag
+        for p, v in zip(self.params, self.views):
+            _ag.register_grad_view(p, v)
+
+    def gather(self) -> int:
+        """After backward: make every parameter's .grad the bucket view (copying what was produced elsewhere, zeroing what has
+        no gradient).  Returns the number of tensors that had to be copied."""
+        src, dst, zero = [], [], []
+        for p, v in zip(self.params, self.views):
+            g = p.grad
+            if g is None:
+                zero.append(v)
+            elif g.data_ptr() != v.data_ptr() or g.stride() != v.stride():
+                src.append(g)
+                dst.append(v)
+            p.grad = v
+        if zero:
+            torch._foreach_zero_(zero)
+        if src:
+            torch._foreach_copy_(dst, src)
+        return len(src)
+
+    def allreduce(self, group: Optional[dist.ProcessGroup] = None, average: bool = True) -> int:
+        self.gather()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            if average and dist.get_backend(group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)       # the division happens inside NCCL
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+                if average:
+                    self.flat /= dist.get_world_size(group)
+        return self.flat.numel()
+
+    def zero(self):
+        """Replacement for optimizer.zero_grad(set_to_none=True): the next backward writes fresh values into the views."""
+        for p in self.params:
+            p.grad = None
+
+
 def allreduce_gradients(params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None,
                         average: bool = True) -> int:
-    """One all-reduce of all gradients as a single flat bucket; returns the number of elements reduced."""
-    ps = [p for p in params if p.grad is not None]
+    """One all-reduce of all gradients as a single flat bucket; returns the number of elements reduced.
+
+    Stateless variant (flatten / un-flatten every call); `GradBucket` is the persistent one.  Parameters without a gradient
+    contribute ZEROS (and receive the reduced value): the flat buffer has the same size on every rank even when a term was
+    absent on one shard - dropping them per rank, as round 1 did, made NCCL hang or mis-assign silently."""
+    ps = [p for p in params if p.requires_grad]
     if not ps:
         return 0
-    grads = [p.grad for p in ps]
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    if world == 1:
+        return sum(p.numel() for p in ps if p.grad is not None)
+    grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in ps]
     flat = torch.cat([g.reshape(-1) for g in grads])                       # one kernel
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        world = dist.get_world_size(group)
-        if average and dist.get_backend(group) == "nccl":
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)       # the division happens inside NCCL
-        else:
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-            if average:
-                flat /= world
+    if average and dist.get_backend(group) == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)           # the division happens inside NCCL
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            flat /= world
     views = [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in grads]), grads)]
     torch._foreach_copy_(grads, views)                                     # un-flatten in a couple of multi-tensor kernels
+    for p, g in zip(ps, grads):
+        if p.grad is None:
+            p.grad = g
     return flat.numel()

@@ -58,16 +58,24 @@ def _render_image_sharded(model, uv, pose, intrinsics, split_n_pixels, predict_o
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     dev, total = uv.device, uv.shape[0]
     out: Dict[str, torch.Tensor] = {}
-    for i, lo in enumerate(range(0, total, split_n_pixels)):
-        if i % world != rank:
-            continue
-        hi = min(lo + split_n_pixels, total)
-        res = model({"uv": uv[None, lo:hi], "pose": pose, "intrinsics": intrinsics}, predict_only=predict_only)
-        for k, v in res.items():
-            v2 = v.reshape(hi - lo, -1)
-            if k not in out:
-                out[k] = torch.zeros(total, v2.shape[1], device=dev, dtype=v2.dtype)
-            out[k][lo:hi] = v2
+    # The ranks render DIFFERENT chunks, possibly different numbers of them: a sampler that MAX-all-reduces its convergence word
+    # (parallel.use_global_convergence(eval_forwards=True)) would deadlock on an odd chunk count and, with equal counts, couple the
+    # convergence of unrelated chunks.  Each chunk is its own forward call, as in the single-GPU loop: switch the collective off here.
+    saved_group = getattr(model, "convergence_group_eval", None)
+    model.convergence_group_eval = None
+    try:
+        for i, lo in enumerate(range(0, total, split_n_pixels)):
+            if i % world != rank:
+                continue
+            hi = min(lo + split_n_pixels, total)
+            res = model({"uv": uv[None, lo:hi], "pose": pose, "intrinsics": intrinsics}, predict_only=predict_only)
+            for k, v in res.items():
+                v2 = v.reshape(hi - lo, -1)
+                if k not in out:
+                    out[k] = torch.zeros(total, v2.shape[1], device=dev, dtype=v2.dtype)
+                out[k][lo:hi] = v2
+    finally:
+        model.convergence_group_eval = saved_group
     if assemble and world > 1:
         # a rank with no chunk (more ranks than chunks) learns keys / widths / dtypes from rank 0, which always owns chunk 0
         meta = [[(k, v.shape[1], str(v.dtype).replace("torch.", "")) for k, v in sorted(out.items())] if rank == 0 else None]

@@ -59,7 +59,7 @@ def _worker(rank, world, port, q):
     inp = _rays(R)
     mine = {k: v.to(dev) for k, v in shard_rays(inp, rank, world).items()}
     out_local = {k: v.clone() for k, v in m(mine).items()}                       # per-shard convergence test
-    use_global_convergence(m)
+    use_global_convergence(m, eval_forwards=True)
     out_global = {k: v.clone() for k, v in m(mine).items()}                      # batch-global convergence test
     use_global_convergence(m, enable=False)
     res = {}

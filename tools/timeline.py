@@ -14,12 +14,26 @@ from i2sdf_b200.network import I2SDFNetwork  # noqa: E402
 torch.manual_seed(0)
 m = I2SDFNetwork(configs.model_conf("synthetic")).cuda().eval()
 core = m._ready_core()
-pts = (torch.rand(131072, 3, device="cuda") - 0.5) * 3
-for _ in range(3):
-    core.sdf_forward(pts)
+MAIN = len(sys.argv) > 1 and sys.argv[1] == "main"
+if MAIN:        # the full main pass (21 ops for synthetic.yml): usage  python tools/timeline.py main
+    R = 1024
+    g = torch.Generator().manual_seed(1)
+    o = torch.zeros(R, 3, device="cuda")
+    o[:, 2] = -1.5
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=1).cuda()
+    z = torch.sort(torch.rand(R, 98, generator=g) * 6.0, dim=1).values.cuda()
+    with torch.no_grad():
+        m.density.beta.fill_(0.01)
+    for _ in range(3):
+        core.render(o, d, torch.ones(R, device="cuda"), z, m.density.beta.detach())
+    NOPS = 21
+else:
+    pts = (torch.rand(131072, 3, device="cuda") - 0.5) * 3
+    for _ in range(3):
+        core.sdf_forward(pts)
+    NOPS = 8
 torch.cuda.synchronize()
 raw = core._ws[:65536].view(torch.int64).cpu()
-NOPS = 8
 ep = raw[:NOPS * 16 * 4].reshape(NOPS, 16, 4)
 issue = raw[2048:2048 + NOPS * 32].reshape(NOPS, 32)
 seen = raw[4096:4096 + NOPS * 32].reshape(NOPS, 32)
@@ -38,7 +52,7 @@ for op in range(NOPS):
         line += f" || {int(seen[op + 1, 0]) - base:6d} | {int(issue[op + 1, 0]) - base:6d} {int(issue[op + 1, n - 1]) - base:6d} | {int(commit[op + 1]) - base:6d}"
     print(line)
     prev = base
-for op in (2, 5):
+for op in ((2, 5, 10, 14, 17) if MAIN else (2, 5)):
     b0 = int(ep[op - 1, :, 1].min())
     print(f"MMA warp, op {op}: per k step, clocks since the previous op's accumulator completed: A chunk seen (even steps) / issued; step length")
     last = None
