@@ -97,10 +97,13 @@ def parse():
     ap.add_argument("--cpu-rays", type=int, default=0, help="rays per step of the CPU arms (0 = --rays: the same config as the GPU arm)")
     ap.add_argument("--bubble", type=int, default=0, help="training variant of steps 50k-150k (config/synthetic.yml:22-23): N bubble points per "
                                                           "step through the SDF (bubble_weight 0.5) and the smoothness term switched on")
-    ap.add_argument("--mode", default="train", choices=["render", "train"],
+    ap.add_argument("--grid-res", type=int, default=256, help="--mode grid: resolution of the uniform SDF grid (reference meshes use 100 .. 512)")
+    ap.add_argument("--mode", default="train", choices=["render", "train", "grid"],
                     help="train (default, BASELINE.json configs[1]): full training step on a 1024-ray batch (forward + I2SDFLoss + "
                          "backward incl. second order + gradient all-reduce + Adam + weight re-pack); "
-                         "render: eval forward render of a 1024-ray batch (configs[2] batch shape)")
+                         "render: eval forward render of a 1024-ray batch (configs[2] batch shape); "
+                         "grid: SDF of a uniform grid for mesh extraction (SURVEY.md §8(f)-3), reported in points/s - a secondary line, "
+                         "not the BASELINE metric")
     return ap.parse_args()
 
 
@@ -562,6 +565,68 @@ def gpu_arm(args, rank, world, local_rank):
     return line, (conf, cpu_snapshot)
 
 
+def grid_arm(args, local_rank):
+    """SDF of a res^3 uniform grid on [-2, 2]^3 through i2sdf_sdf_grid (points generated on the device, sdf-only chain)."""
+    from i2sdf_b200.grid import grid_axes_uniform, grid_points, sdf_grid
+    from oracle import i2sdf_oracle as orc
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    conf, model = build_params(name=args.config)
+    fm = flop_model(conf)
+    m = model.to(dev).eval()
+    x, y, z = grid_axes_uniform(args.grid_res)
+    n = len(x) * len(y) * len(z)
+    for _ in range(max(args.warmup, 3)):
+        sdf_grid(m, x, y, z)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    clk = ClockSampler(local_rank)
+    clk.start()
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        out = sdf_grid(m, x, y, z)
+        b.record()
+    torch.cuda.synchronize()
+    clocks = clk.stop()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    # end to end: axes from the host, the volume back to the host (what marching cubes consumes)
+    host = torch.empty(n, dtype=torch.float32).pin_memory()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        host.copy_(sdf_grid(m, x, y, z), non_blocking=True)
+    torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+    pk = peaks()
+    # CPU baseline: the reference's loop over a bounded sample of the grid (first 2^18 points), implicit_network(p)[:, 0] incl. the 256 discarded features
+    spec = orc.spec_from_model_conf(conf, use_normal=False)
+    P = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    layers = orc.layer_params(P, "implicit_network", spec.n_sdf_layers)
+    pts = grid_points(x[:64], y[:64], z[:64])
+    with torch.no_grad():
+        pick_cpu_threads(lambda: orc.sdf_mlp(spec, layers, pts[:4096]))
+        t0 = time.perf_counter()
+        ref = orc.sdf_mlp(spec, layers, pts)[0][:, 0]
+        dt = time.perf_counter() - t0
+    chk = sdf_grid(m, x[:64], y[:64], z[:64]).cpu()
+    err = float((chk - ref).abs().max() / ref.abs().max())
+    ach = n * fm["sdf_eval"] / (ms * 1e-3) / 1e12
+    return {"metric": "SDF grid evaluation for mesh extraction (secondary line; the BASELINE metric is --mode train)", "value": n / (ms * 1e-3), "unit": "points/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (fp16 hi/lo split products on tcgen05, fp32 accumulate in TMEM)", "data": "synthetic",
+            "config": {"workload": f"sdf of a {args.grid_res}^3 uniform grid on [-2, 2]^3 (utils/plots.py:440-451 point order), points generated on the device, "
+                                   f"{args.config}.yml SDF network, W-sharp weights", "grid_points": n, "l2": "flushed between timed iterations"},
+            "e2e": {"value": n / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": 3 * 4 * args.grid_res, "d2h_bytes_per_step": 4 * n},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "tensor", "kernel": "tc_sdf8_kernel (grid point source)", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "flop_per_point": fm["sdf_eval"]},
+            "clocks": clocks, "parity": {"max_abs_err_over_max_abs_sdf_vs_oracle_on_64^3": err},
+            "cpu_baseline": {"value": pts.shape[0] / dt, "unit": "points/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"first 64^3 = {pts.shape[0]} grid points through the oracle's ImplicitNetwork.forward (257 outputs, 256 discarded, as "
+                                       "model/eval/recon.py:51 does), torch CPU fp32"}}
+
+
 def add_cpu_baseline(line, args, conf, cpu_snapshot):
     """Rank 0, after the process group is gone (so the other ranks are not spinning in a barrier next to it)."""
     model_c = type("S", (), {"state_dict": lambda self: cpu_snapshot})()
@@ -609,6 +674,10 @@ def main():
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    if args.mode == "grid":
+        if rank == 0:
+            print(json.dumps(grid_arm(args, local_rank)), flush=True)
+        return
     line, cpu = gpu_arm(args, rank, world, local_rank)
     if world > 1:
         import torch.distributed as dist

@@ -64,6 +64,7 @@ SYMBOLS = {
     "i2sdf_workspace_bytes": (C.c_size_t, [_P, C.c_int64, C.c_int]),
     "i2sdf_rays": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "i2sdf_sdf_forward": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "i2sdf_sdf_grid": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "i2sdf_sampler_rounds": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P, C.c_size_t, _P]),
     "i2sdf_sampler_step": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "i2sdf_sampler_beta_max": (C.c_void_p, [_P, C.c_int64, _P]),

@@ -185,6 +185,18 @@ class RenderCore:
                                          _ptr(ws), self._ws_bytes, self._stream()), "i2sdf_sdf_forward")
         return sdf, feat, grad
 
+    def sdf_grid(self, gx, gy, gz, affine=None):
+        """sdf of the regular grid meshgrid(gx, gy, gz) (numpy 'xy' order, utils/plots.py:445-446), points generated on the device."""
+        gx, gy, gz = (_f32(torch.as_tensor(a), self.device) for a in (gx, gy, gz))
+        aff = None if affine is None else _f32(torch.as_tensor(affine).reshape(12), self.device)
+        n = gx.numel() * gy.numel() * gz.numel()
+        out = torch.empty(n, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.i2sdf_sdf_grid(self.h, _ptr(gx), _ptr(gy), _ptr(gz), gx.numel(), gy.numel(), gz.numel(), _ptr(aff), _ptr(out), self._stream()),
+                  "i2sdf_sdf_grid")
+        self._keep_grid = (gx, gy, gz, aff)
+        return out
+
     def sample(self, o, d, beta_param, tape: Optional[Dict[str, torch.Tensor]] = None, want_info=False, defer_sync=False, group=None):
         """ErrorBoundSampler.get_z_vals.  tape (training): jitter [R,128], u_final [R,64] fp32;
         extra_perm: callable n -> LongTensor[32] (drawn after one 8-byte D2H of n) or int tensor; eik_idx [R].

@@ -407,6 +407,19 @@ int i2sdf_sdf_forward(i2sdf_handle* h, const float* pts, int64_t M, float* out_s
     return run_mlp(h, p, (cudaStream_t)stream);
 }
 
+int i2sdf_sdf_grid(i2sdf_handle* h, const float* gx, const float* gy, const float* gz, int nx, int ny, int nz, const float* affine,
+                   float* out_sdf, void* stream) {
+    if (!h || !gx || !gy || !gz || !out_sdf) { set_error("null argument"); return I2SDF_E_INVALID; }
+    if (nx < 1 || ny < 1 || nz < 1) { set_error("sdf_grid: empty grid"); return I2SDF_E_INVALID; }
+    if (!h->use_tc) { set_error("sdf_grid: the tensor-core sdf kernel is not available for this handle"); return I2SDF_E_INVALID; }
+    MlpParams p{};
+    p.gx = gx; p.gy = gy; p.gz = gz; p.nx = nx; p.ny = ny; p.nz = nz; p.grid_affine = affine;
+    p.M = (long long)nx * ny * nz; p.ns = 1; p.round_idx = -1; p.beta_min = h->smp.beta_min;
+    p.out_sdf = out_sdf;
+    p.net = h->net;
+    return run_mlp(h, p, (cudaStream_t)stream);
+}
+
 int i2sdf_sampler_rounds(i2sdf_handle* h, const float* o, const float* d, int64_t R, const float* beta_param,
                          const float* jitter, const float* u_final, void* workspace, size_t workspace_bytes, void* stream) {
     if (!h || !o || !d || !beta_param || !workspace) { set_error("null argument"); return I2SDF_E_INVALID; }

@@ -92,6 +92,12 @@ struct MlpParams {
     int ns;
     long long M;
     long long m_rays;         // with BOTH sources given: points m < m_rays come from the rays, m >= m_rays from pts[m - m_rays]
+    // third source (sdf-only kernel): a regular grid generated on the device, numpy.meshgrid(x, y, z) order as utils/plots.py:440-451:
+    // point m = (j, i, k) = (m / (nx nz), (m / nz) % nx, m % nz) -> (gx[i], gy[j], gz[k]), then p' = A p + t if grid_affine (12 floats:
+    // row-major 3x3 A, then t)
+    const float* gx; const float* gy; const float* gz;
+    int nx, ny, nz;
+    const float* grid_affine;
     // predication for sampler rounds: run only if round_idx < 0 or all beta_max[j] > beta0 for j < round_idx
     const float* beta_max;    // device [max_iters]
     const float* beta_param;  // device scalar (raw density.beta)

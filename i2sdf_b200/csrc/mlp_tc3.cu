@@ -510,7 +510,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_sdf8_kernel(const MlpParams P,
             const long long m = tile * TM + row;
             x[0] = x[1] = x[2] = 0.f;
             if (m < P.M) {
-                if (P.pts && m >= P.m_rays) { const float* pp = P.pts + (m - P.m_rays) * 3; x[0] = pp[0]; x[1] = pp[1]; x[2] = pp[2]; }
+                if (P.gx) {                       // regular grid, generated here (utils/plots.py:440-451 order; model/eval/recon.py:80-84 affine)
+                    const long long ji = m / P.nz;
+                    const int k = (int)(m - ji * P.nz), j = (int)(ji / P.nx), i = (int)(ji - (long long)j * P.nx);
+                    const float px = __ldg(P.gx + i), py = __ldg(P.gy + j), pz = __ldg(P.gz + k);
+                    x[0] = px; x[1] = py; x[2] = pz;
+                    if (P.grid_affine) {
+                        const float* A = P.grid_affine;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            x[c] = __fadd_rn(fmaf(__ldg(A + c * 3 + 2), pz, fmaf(__ldg(A + c * 3 + 1), py, __fmul_rn(__ldg(A + c * 3), px))), __ldg(A + 9 + c));
+                    }
+                } else if (P.pts && m >= P.m_rays) { const float* pp = P.pts + (m - P.m_rays) * 3; x[0] = pp[0]; x[1] = pp[1]; x[2] = pp[2]; }
                 else {
                     const long long r = m / P.ns;
                     const int j = (int)(m - r * P.ns);

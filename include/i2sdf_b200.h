@@ -108,6 +108,15 @@ int i2sdf_rays(i2sdf_handle* h, const float* uv, const float* pose, const float*
 int i2sdf_sdf_forward(i2sdf_handle* h, const float* pts, int64_t M, float* out_sdf, float* out_feat,
                       float* out_grad, float* save_act, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Replaces: the SDF evaluation of a regular grid for mesh extraction / validation plots - `implicit_network(pnts)[:, 0]` over
+ * `get_grid_uniform` / `get_grid` points (model/eval/recon.py:46-56, 87-90; utils/plots.py:188-225, 440-489).
+ * The points are generated on the device from the three axis arrays in numpy.meshgrid(x, y, z) order - point m = (j, i, k) =
+ * (m / (nx nz), (m / nz) % nx, m % nz) -> (gx[i], gy[j], gz[k]) - optionally mapped p' = A p + t (affine: 12 device floats, row-major
+ * 3x3 then t: the PCA-aligned grid of eval/recon.py:80-84), and go through the sdf-only tensor-core chain: no point array is read, no
+ * feature is computed or written (the reference evaluates and discards 256 of them per point).  out_sdf [nx*ny*nz]. */
+int i2sdf_sdf_grid(i2sdf_handle* h, const float* gx, const float* gy, const float* gz, int nx, int ny, int nz, const float* affine,
+                   float* out_sdf, void* stream);
+
 /* Replaces: ErrorBoundSampler.get_z_vals rounds (ray_sampler.py:67-212): uniform init (+ stratified jitter),
  * up to max_total_iters rounds of {SDF of new samples, d*, beta line search, opacity-bound pdf, inverse CDF,
  * merge}.  No host synchronisation: the batch-global convergence test (ray_sampler.py:151) is evaluated on

@@ -92,3 +92,83 @@ def test_sharded_render_with_global_convergence_equals_single_gpu():
         assert p.exitcode == 0
     assert tag == "eval" and ok_global, "sharded render with the global convergence word differs from the single-GPU render"
     print(f"per-shard convergence test happened to equal the single-GPU render: {same_local} (may legitimately differ)")
+
+
+# ---- training: sharded step (global convergence word + global loss means + one flat all-reduce) == the whole batch on one GPU ----------
+def _train_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    from i2sdf_b200 import configs
+    from i2sdf_b200.network import I2SDFLoss
+    from i2sdf_b200.parallel import GradBucket, shard_bounds, shard_rays, use_global_convergence, use_global_loss_means
+    from i2sdf_b200.synthetic import make_train_gt, synthetic_rays
+    dev = torch.device(f"cuda:{rank}")
+    R = 384                                   # 192 rays per rank: ragged against the 128-point tiles
+    g = torch.Generator().manual_seed(11)
+    inp = synthetic_rays(R, seed=4, train_layout=True)
+    gt = make_train_gt(R, 5)
+    gt["depth_mask"] = torch.rand(R, generator=g) > 0.4          # masked means with different counts per shard
+    gt["normal_mask"] = torch.rand(R, generator=g) > 0.3
+    tape = {"jitter": torch.rand(R, 128, generator=g), "u_final": torch.rand(R, 64, generator=g), "extra_perm": torch.randperm(128, generator=g)[:32],
+            "eik_idx": torch.randint(98, (R,), generator=g), "eik_uniform": (torch.rand(R, 3, generator=g) - 0.5) * 6,
+            "nbr_uniform": (torch.rand(R, 3, generator=g) - 0.5) * 0.01}
+
+    def run(lo, hi, strict):
+        m = _build(0.02)
+        m.use_normal = True
+        m = m.to(dev).train()
+        loss_fn = I2SDFLoss(**configs.LOSS_SYNTHETIC)
+        if strict:
+            use_global_convergence(m)
+            use_global_loss_means(loss_fn)
+        m._tape_override = {k: (v[lo:hi] if (torch.is_tensor(v) and v.shape[0] == R) else v) for k, v in tape.items()}
+        out = m({k: v[lo:hi].to(dev) for k, v in inp.items()})
+        loss = loss_fn(out, {k: v[lo:hi].to(dev) for k, v in gt.items()}, 0)["loss"]
+        bucket = GradBucket(m.parameters())
+        loss.backward()
+        if strict:
+            bucket.allreduce()
+        else:
+            bucket.gather()
+        return loss.detach(), bucket.flat.clone(), [n for n, _ in m.named_parameters()], bucket
+    lo, hi = shard_bounds(R, rank, world)
+    loss_s, flat_s, names, bucket = run(lo, hi, True)
+    t = loss_s.clone()
+    dist.all_reduce(t, op=dist.ReduceOp.AVG)
+    if rank == 0:
+        loss_w, flat_w, _, _ = run(0, R, False)                  # the whole batch on one GPU, no collective
+        e_flat = float((flat_s - flat_w).norm() / flat_w.norm())
+        worst, worst_name = 0.0, ""
+        for name, p, v in zip(names, bucket.params, bucket.views):
+            off = v.data_ptr() - bucket.flat.data_ptr()
+            a = flat_s[off // 4: off // 4 + v.numel()]
+            b = flat_w[off // 4: off // 4 + v.numel()]
+            e = float((a - b).norm() / b.norm().clamp(min=1e-30))
+            if e > worst:
+                worst, worst_name = e, name
+        q.put(("train", float(t), float(loss_w), e_flat, worst, worst_name))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_training_step_equals_whole_batch_gradients():
+    """model/trainer/recon.py:245-254 sees the whole batch in one process; two ranks with the strict-parity switches must produce the same
+    loss and, after ONE all-reduce of the flat gradient bucket, the same gradients (fp32 summation order aside)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    tag, loss_sharded, loss_whole, e_flat, worst, worst_name = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    print(f"sharded training step: loss {loss_sharded:.8f} vs whole batch {loss_whole:.8f}; flat gradient L2 rel err {e_flat:.2e}; worst tensor {worst:.2e} ({worst_name})")
+    assert tag == "train"
+    assert abs(loss_sharded - loss_whole) < 1e-5 * abs(loss_whole)
+    assert e_flat < 1e-4 and worst < 1e-3
