@@ -4,6 +4,9 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libi2sdf_b200.so")
+# test infrastructure: the same ABI with the fp32 SIMT kernel + layer-by-layer backward as a selectable cross-check backend
+# (I2SDF_SIMT=1 / I2SDF_SIMT_MAIN=1 / I2SDF_FUSED_BWD=0 at RenderCore creation); the product library ignores those switches
+CHECK_LIB_PATH = os.path.join(_HERE, "libi2sdf_b200_check.so")
 ABI_VERSION = 1
 
 
@@ -100,33 +103,51 @@ SYMBOLS = {
 }
 
 _lib = None
+_check_lib = None
+
+
+def wants_check_backend() -> bool:
+    return os.environ.get("I2SDF_SIMT") == "1" or os.environ.get("I2SDF_SIMT_MAIN") == "1" or os.environ.get("I2SDF_FUSED_BWD") == "0"
 
 
 class I2SDFError(RuntimeError):
     pass
 
 
-def load():
-    """Load the CUDA library.  Fails loudly: there is no CPU fallback."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+def _open(path):
+    if not os.path.exists(path):
         raise I2SDFError(
-            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(or i2sdf_b200/csrc/build.sh).  i2sdf_b200 has no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)          # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
     if lib.i2sdf_abi_version() != ABI_VERSION:
         raise I2SDFError(f"ABI mismatch: library {lib.i2sdf_abi_version()} vs binding {ABI_VERSION}")
-    _lib = lib
     return lib
+
+
+def load():
+    """Load the CUDA library.  Fails loudly: there is no CPU fallback."""
+    global _lib
+    if _lib is None:
+        _lib = _open(LIB_PATH)
+    return _lib
+
+
+def load_check():
+    """The check build (tests / tools only): product kernels + the fp32 cross-check backend behind the I2SDF_SIMT* switches."""
+    global _check_lib
+    if _check_lib is None:
+        _check_lib = _open(CHECK_LIB_PATH)
+    return _check_lib
 
 
 def check(rc, what=""):
     if rc != 0:
         msg = load().i2sdf_last_error().decode(errors="replace")
+        if not msg and _check_lib is not None:
+            msg = _check_lib.i2sdf_last_error().decode(errors="replace")
         raise I2SDFError(f"{what} failed (code {rc}): {msg}")

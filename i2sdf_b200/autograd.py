@@ -156,10 +156,13 @@ class _SdfPointsFn(Function):
     def forward(ctx, core, pts, want_grad, n_sdf, *params):
         pts = pts.detach().contiguous().float()
         M = pts.shape[0]
-        act = core.sdf_saved_buffer(M, want_grad)
-        sdf, _, grad = core.sdf_forward(pts, want_grad=want_grad, save_act=act)
+        # sdf-only points with a backward (the bubble loss, network/__init__.py:196-201) also ride the tensor-core chain: its sdf + grad_x
+        # table is the one that saves plane slots, the unused grad_x costs a reverse sweep on a few thousand points
+        fused = bool(core.fused_sdf)
+        act = core.sdf_saved_buffer(M, want_grad or fused)
+        sdf, _, grad = core.sdf_forward(pts, want_grad=(want_grad or fused), save_act=act)
         ctx.core, ctx.cfg = core, (want_grad, n_sdf)
-        ctx.fused = core.fused_sdf and want_grad
+        ctx.fused = fused
         ctx.set_materialize_grads(False)
         ctx.save_for_backward(pts, act, *params)
         if not want_grad:
@@ -176,7 +179,7 @@ class _SdfPointsFn(Function):
         dW, db = _zeros_like_all([W, b])
         if g_sdf is not None or (want_grad and g_grad is not None):
             if ctx.fused:
-                ctx.core.fused_backward(pts.shape[0], act, dW, db, pts=pts, g_sdf=g_sdf, g_grad=g_grad)
+                ctx.core.fused_backward(pts.shape[0], act, dW, db, pts=pts, g_sdf=g_sdf, g_grad=g_grad if want_grad else None)
             else:
                 ctx.core.sdf_backward(W, pts.shape[0], act, dW, db, pts=pts, g_sdf=g_sdf, g_grad=g_grad if want_grad else None)
         return (None,) * 4 + tuple(dW + db)

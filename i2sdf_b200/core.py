@@ -26,7 +26,8 @@ class RenderCore:
     def __init__(self, model_conf: dict, device: torch.device):
         if device.type != "cuda":
             raise _lib.I2SDFError("i2sdf_b200 runs on CUDA devices only (no CPU fallback); move the module to a B200")
-        self.lib = _lib.load()
+        # (the cross-check backend lives in its own library: only a process that sets one of the I2SDF_SIMT* switches ever loads it)
+        self.lib = _lib.load_check() if _lib.wants_check_backend() else _lib.load()
         self.device = device
         imp, ren, smp = model_conf["implicit_network"], model_conf["rendering_network"], model_conf["ray_sampler"]
         if ren.get("mode", "nerf") != "nerf":

@@ -20,7 +20,12 @@ $NVCC $COMMON -Xptxas -v -c "$HERE/loss.cu" -o "$HERE/build/loss.o" 2> "$HERE/bu
 $NVCC $COMMON -Xptxas -v -c "$HERE/wnorm.cu" -o "$HERE/build/wnorm.o" 2> "$HERE/build/wnorm.ptxas.txt" &
 $NVCC $COMMON -Xptxas -v -c "$HERE/adam.cu" -o "$HERE/build/adam.o" 2> "$HERE/build/adam.ptxas.txt" &
 $NVCC $COMMON -c "$HERE/c_abi.cu" -o "$HERE/build/c_abi.o" &
+# check build (test infrastructure): the same ABI + the fp32 SIMT kernel / layer-wise backward as a selectable cross-check backend
+$NVCC $COMMON -DI2SDF_CHECK_BUILD -c "$HERE/c_abi.cu" -o "$HERE/build/c_abi_check.o" &
+$NVCC $COMMON -DI2SDF_CHECK_BUILD -c "$HERE/mlp_tc3.cu" -o "$HERE/build/mlp_tc3_check.o" &
 wait
-for f in mlp_simt mlp_tc3 mlp_tc_bwd tc_gemm wgrad_planes sampler backward loss wnorm adam c_abi; do [ -s "$HERE/build/$f.o" ] || { echo "build failed: $f"; cat "$HERE/build/$f.ptxas.txt" 2>/dev/null | grep -i error; exit 1; }; done
-$NVCC -shared $ARCH -o "$OUT/libi2sdf_b200.so" "$HERE/build/mlp_simt.o" "$HERE/build/mlp_tc3.o" "$HERE/build/mlp_tc_bwd.o" "$HERE/build/tc_gemm.o" "$HERE/build/wgrad_planes.o" "$HERE/build/sampler.o" "$HERE/build/backward.o" "$HERE/build/loss.o" "$HERE/build/wnorm.o" "$HERE/build/adam.o" "$HERE/build/c_abi.o" -lcudart
-echo "built $OUT/libi2sdf_b200.so"
+for f in mlp_simt mlp_tc3 mlp_tc_bwd tc_gemm wgrad_planes sampler backward loss wnorm adam c_abi c_abi_check mlp_tc3_check; do [ -s "$HERE/build/$f.o" ] || { echo "build failed: $f"; cat "$HERE/build/$f.ptxas.txt" 2>/dev/null | grep -i error; exit 1; }; done
+# product: no mlp_simt.o
+$NVCC -shared $ARCH -o "$OUT/libi2sdf_b200.so" "$HERE/build/mlp_tc3.o" "$HERE/build/mlp_tc_bwd.o" "$HERE/build/tc_gemm.o" "$HERE/build/wgrad_planes.o" "$HERE/build/sampler.o" "$HERE/build/backward.o" "$HERE/build/loss.o" "$HERE/build/wnorm.o" "$HERE/build/adam.o" "$HERE/build/c_abi.o" -lcudart
+$NVCC -shared $ARCH -o "$OUT/libi2sdf_b200_check.so" "$HERE/build/mlp_simt.o" "$HERE/build/mlp_tc3_check.o" "$HERE/build/mlp_tc_bwd.o" "$HERE/build/tc_gemm.o" "$HERE/build/wgrad_planes.o" "$HERE/build/sampler.o" "$HERE/build/backward.o" "$HERE/build/loss.o" "$HERE/build/wnorm.o" "$HERE/build/adam.o" "$HERE/build/c_abi_check.o" -lcudart
+echo "built $OUT/libi2sdf_b200.so (+ libi2sdf_b200_check.so)"

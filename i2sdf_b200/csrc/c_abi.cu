@@ -223,12 +223,20 @@ int i2sdf_create(const i2sdf_desc* d, int device, i2sdf_handle** out) {
     cudaMemcpy(h->pool + o_ufin, d->u_final, sizeof(float) * d->n_samples, cudaMemcpyHostToDevice);
     cudaMemcpy(h->pool + o_tin, d->t_init, sizeof(float) * d->n_samples_eval, cudaMemcpyHostToDevice);
     cudaMemcpy(h->pool + o_eidx, d->extra_idx, sizeof(int) * mi * ne, cudaMemcpyHostToDevice);
+    // The product library (libi2sdf_b200.so) has ONE backend: the tcgen05 chain kernels and the fused plane-slot backward.  The fp32 SIMT
+    // kernel and the layer-by-layer backward exist only in the CHECK build (libi2sdf_b200_check.so, -DI2SDF_CHECK_BUILD: test
+    // infrastructure, selected there by I2SDF_SIMT=1 / I2SDF_SIMT_MAIN=1 / I2SDF_FUSED_BWD=0) as the exact-fp32 cross-check.
+#ifdef I2SDF_CHECK_BUILD
     const char* env = getenv("I2SDF_SIMT");
     h->use_tc = !(env && env[0] == '1');
+    { const char* fe = getenv("I2SDF_FUSED_BWD"); h->fused = !(fe && fe[0] == '0'); }
+#else
+    h->use_tc = true;
+    h->fused = true;
+#endif
     h->tc = nullptr;
     h->prof = new Prof();
     h->tcmain = nullptr;
-    { const char* fe = getenv("I2SDF_FUSED_BWD"); h->fused = !(fe && fe[0] == '0'); }
     if (h->use_tc) {
         int rc = tc_create(h);
         if (rc != I2SDF_OK) { cudaFree(h->pool); free(h); return rc; }
@@ -316,7 +324,9 @@ int i2sdf_pack_weights(i2sdf_handle* h, const float* const* W, const float* cons
 
 // workspace = [ sampler state | mlp scratch | per-sample temporaries (8 floats x R x 128) ]
 static size_t ws_sampler_floats(const i2sdf_handle* h, int64_t R) { return (sampler_ws_floats(h, R) + 63) / 64 * 64; }
-static size_t ws_scratch_floats(const i2sdf_handle* h) { return (mlp_simt_scratch_floats(h) + 63) / 64 * 64; }
+// per-CTA scratch of the eval main pass: one tile of h~_l per SDF hidden layer in plane format (and the same bytes as the fp32
+// cross-check kernel's [2 CTAs per SM][L-1][64][256] floats)
+static size_t ws_scratch_floats(const i2sdf_handle* h) { return ((size_t)h->num_sms * (size_t)(h->net.L - 1) * (planes::BIG_TILE / sizeof(float)) + 63) / 64 * 64; }
 
 // Light-mask head behind the tensor-core main pass: the head is its own pass over the features the main pass writes
 // (light_forward, backward.cu).  Workspace region = [ hidden pre-activations: rows x lh | features: rows x 256 ] for one
@@ -370,7 +380,13 @@ static int run_mlp(const i2sdf_handle* h, const MlpParams& p, cudaStream_t st) {
     if (h->tcmain && p.out_sdf && p.out_grad && !p.want_color && !p.want_light && !p.out_feat && (p.scratch || p.sl.base) && !p.save_act && (p.ray_d || p.pts))
         return tcmain_launch(h, h->tcmain, p, st);
     if (p.sl.base) { set_error("run_mlp: plane-slot save requested for a pass the tensor-core kernel does not cover"); return I2SDF_E_INVALID; }
+#ifdef I2SDF_CHECK_BUILD
     return launch_mlp_simt(h, p, st);
+#else
+    set_error("this call is not covered by the tensor-core chain kernels (network too deep for the full chain: n_sdf_layers - 1 + n_color_layers > 13, "
+              "or an output combination no reference call site uses); the product library has no second backend");
+    return I2SDF_E_INVALID;
+#endif
 }
 
 // format of the state a forward saves for the backward: 1 = plane slots (tensor-core chain kernels + fused backward),

@@ -718,7 +718,10 @@ int tc_create(i2sdf_handle* h) {
     const int L = n.L, NL = L - 1, Lc = n.Lc;
     // (the light-mask head is not an op of the chain: it reads the features the main pass writes, see light_forward in backward.cu)
     // (the full chain keeps every bias and both heads in shared memory: (NL + Lc) x 256 + 1032 floats must fit M8_PARAM_FLOATS)
-    const bool want_full = !(getenv("I2SDF_SIMT_MAIN") && getenv("I2SDF_SIMT_MAIN")[0] == '1') && ((NL + Lc) * 256 + 1032 <= M8_PARAM_FLOATS);
+    bool want_full = ((NL + Lc) * 256 + 1032 <= M8_PARAM_FLOATS);
+#ifdef I2SDF_CHECK_BUILD
+    if (getenv("I2SDF_SIMT_MAIN") && getenv("I2SDF_SIMT_MAIN")[0] == '1') want_full = false;      // cross-check: main pass on the fp32 kernel
+#endif
     OpTable& T = s->full;
     int nops = 0;
     size_t off = 0;

@@ -229,3 +229,28 @@ def test_product_package_never_imports_the_oracle():
     for f in os.listdir(os.path.join(pkg, "csrc")):
         if f.endswith((".cu", ".cuh")):
             assert "oracle" not in open(os.path.join(pkg, "csrc", f)).read().lower(), f
+
+
+def test_synthetic_inputs_flop_model_and_grid_axes():
+    """The neutral input generator equals the oracle's; the published FLOP model gives SURVEY.md §8(d)'s numbers; the grid axes are the
+    reference's (utils/plots.py:440-489) and the explicit point list has numpy.meshgrid's order."""
+    import numpy as np
+    import bench
+    from i2sdf_b200 import configs
+    from i2sdf_b200.grid import grid_axes_from_points, grid_axes_uniform, grid_points
+    from i2sdf_b200.synthetic import synthetic_rays
+    from oracle import i2sdf_oracle as orc
+    for tl in (False, True):
+        a, b = synthetic_rays(33, seed=4, train_layout=tl), orc.synthetic_rays(33, seed=4, train_layout=tl)
+        assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in a)
+    fm = bench.flop_model(configs.model_conf("synthetic"))
+    assert fm["sdf_eval"] == 918016 and fm["ray_sample"] == 2506752                        # SURVEY.md §8(d)
+    assert bench.flop_model(configs.model_conf("synthetic_light_mask"))["ray_sample"] == 1917184
+    assert abs(bench.step_flops(fm, 1024, 5, False) / 1024 - 830.7e6) < 0.1e6               # 830.7 MFLOP per ray, worst case
+    x, y, z = grid_axes_uniform(5, (-2.0, 2.0))
+    assert np.array_equal(x, np.linspace(-2.0, 2.0, 5)) and x is y and y is z
+    pts = grid_points([0.0, 1.0], [10.0, 20.0, 30.0], [5.0])
+    assert pts.shape == (6, 3) and pts.tolist()[:3] == [[0.0, 10.0, 5.0], [1.0, 10.0, 5.0], [0.0, 20.0, 5.0]]   # (j, i, k): y outer, x, z inner
+    cloud = torch.tensor([[0.0, 0.0, 0.0], [1.0, 2.0, 4.0]])
+    (ax, ay, az), length, sa = grid_axes_from_points(cloud, 11)
+    assert sa == 0 and len(ax) == 11 and abs(length - 1.2) < 1e-6 and abs((ay[1] - ay[0]) - 0.12) < 1e-6 and abs(ay[0] + 0.1) < 1e-6 and az[-1] >= 4.1 - 1e-6

@@ -178,14 +178,32 @@ class _FakeEvalModel:
         return out
 
 
+class _FakeCollectiveEvalModel(_FakeEvalModel):
+    """Stand-in for a model after parallel.use_global_convergence(eval_forwards=True): every eval forward enters a collective, as the
+    real sampler does once per round.  render_image(group=) deals the ranks DIFFERENT numbers of chunks; it must switch that off."""
+
+    def __call__(self, inp, predict_only=False):
+        if self.convergence_group_eval is not None:
+            dist.all_reduce(torch.zeros(1), group=self.convergence_group_eval)       # would deadlock on an odd chunk count
+        return super().__call__(inp, predict_only)
+
+
 def _render_worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dist.init_process_group("gloo", rank=rank, world_size=world, timeout=__import__("datetime").timedelta(seconds=60))
+    from i2sdf_b200.parallel import use_global_convergence
     from i2sdf_b200.render import render_image
     pose = torch.eye(4)
     pose[0, 3] = 0.25
     res = {}
+    # five chunks over two ranks (3 + 2) through a model whose eval forwards would enter a collective: no hang, same image, switch restored
+    fm = use_global_convergence(_FakeCollectiveEvalModel(), eval_forwards=True)
+    guarded = render_image(fm, pose, torch.eye(4), (7, 9), split_n_pixels=13, group=dist.group.WORLD)
+    assert fm.convergence_group_eval is not None and fm.convergence_group is not None
+    use_global_convergence(fm)                                  # default: training forwards only
+    assert fm.convergence_group_eval is None and fm.convergence_group is not None
+    res["guarded"] = ({k: v.numpy().copy() for k, v in guarded.items()}, {})
     for name, res_hw, split in (("five_chunks", (7, 9), 13), ("one_chunk", (3, 4), 100)):
         full = render_image(_FakeEvalModel(), pose, torch.eye(4), res_hw, split_n_pixels=split, group=dist.group.WORLD)
         own = render_image(_FakeEvalModel(), pose, torch.eye(4), res_hw, split_n_pixels=split, group=dist.group.WORLD, assemble=False)
@@ -211,6 +229,10 @@ def test_sharded_render_image_equals_the_single_process_image():
         assert p.exitcode == 0
     pose = torch.eye(4)
     pose[0, 3] = 0.25
+    single = render_image(_FakeEvalModel(), pose, torch.eye(4), (7, 9), split_n_pixels=13)
+    for rank in range(world):                                   # the guarded render (advisor finding r01: eval collective + odd chunk count)
+        for k, v in single.items():
+            assert np.array_equal(res[rank]["guarded"][0][k], v.numpy()), (rank, k)
     for name, res_hw, split in (("five_chunks", (7, 9), 13), ("one_chunk", (3, 4), 100)):
         single = render_image(_FakeEvalModel(), pose, torch.eye(4), res_hw, split_n_pixels=split)
         for rank in range(world):
@@ -228,3 +250,47 @@ def test_sharded_render_image_equals_the_single_process_image():
                     assert np.array_equal(own[k][owner == rank], v.numpy()[owner == rank]) and not own[k][owner != rank].any()
                 else:
                     assert not (owner == rank).any()
+
+
+# ---- persistent flat gradient bucket (parallel.GradBucket) -------------------------------------------------------------------
+def _bucket_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from i2sdf_b200.parallel import GradBucket
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(7)), torch.nn.Parameter(torch.randn(())), torch.nn.Parameter(torch.randn(2, 2))]
+    bucket = GradBucket(ps)
+    n_flat = bucket.flat.numel()
+    ok = True
+    for step in range(2):
+        bucket.zero()
+        assert all(p.grad is None for p in ps)
+        # rank 1 has no gradient for parameter 1 (a loss term absent on its shard); parameter 3 gets none on any rank
+        loss = (ps[0] * (rank + 1.0 + step)).sum() + ps[2] * 3.0
+        if rank == 0:
+            loss = loss + (ps[1] * 2.0).sum()
+        loss.backward()
+        n = bucket.allreduce()
+        ok &= n == n_flat
+        ok &= all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(ps, bucket.views))                 # every .grad IS its bucket view
+        ok &= torch.allclose(ps[0].grad, torch.full((5, 3), 1.5 + step)) and torch.allclose(ps[1].grad, torch.full((7,), 1.0))
+        ok &= torch.allclose(ps[2].grad, torch.tensor(3.0)) and torch.equal(ps[3].grad, torch.zeros(2, 2))
+    q.put((rank, bool(ok), n_flat))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_grad_bucket_allreduces_in_place_with_uneven_none_grads():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res) and res[0][2] == res[1][2] == 16 + 8 + 4 + 4
