@@ -2,6 +2,10 @@
 
 Tolerance (north_star): 1e-4 relative fp32 = max|a-b| / max|b| per tensor; integer outputs exact given identical
 float inputs (sampler stage tests feed the oracle's own z / sdf), end-to-end sampler compared by value.
+
+Round 2: the forward chains multiply fp16 hi/lo operands and compensate the tensor core's round-toward-zero accumulator
+(csrc/mlp_tc3.cu: acc_scale); sdf now carries 2e-7 near the surface (the fp32 CPU oracle itself: 1.75e-7 against float64), so the
+bounds below are the round-2 measurements with head room - 10-100x tighter than round 1's (profiles/parity_r02.json).
 """
 import pytest
 import torch
@@ -47,13 +51,13 @@ def test_sdf_forward_matches_oracle(cases, name):
         ref, gref = orc.sdf_mlp(c.spec, layers, pts, want_grad=True)
     out = m.implicit_network(pts.cuda())                       # sdf + features: tensor-core chain F.., G when enabled
     assert out.shape == (1000, 257)
-    tol = TOL if m._core_obj.uses_tensor_cores else 1e-5
+    tol = 1e-5                                                 # measured ~1e-6 on the tensor-core chain (round 1: 1.2e-5 against a 1e-4 bound)
     assert relerr(out[:, 0], ref[:, 0]) < tol
     assert relerr(out[:, 1:], ref[:, 1:]) < tol
     g2 = m.implicit_network.gradient(pts.cuda())              # sdf + grad_x: tensor-core chain F.., R.. when enabled
-    assert relerr(g2, gref) < (2 * TOL if m._core_obj.uses_tensor_cores else 2e-5), relerr(g2, gref)
+    assert relerr(g2, gref) < 2e-5, relerr(g2, gref)          # measured ~3e-6
     s2 = m.implicit_network.get_sdf_vals(pts.cuda())        # sdf-only evaluations run on the tcgen05 kernel
-    assert s2.shape == (1000, 1) and relerr(s2[:, 0], ref[:, 0]) < (TOL if m._core_obj.uses_tensor_cores else 1e-5)
+    assert s2.shape == (1000, 1) and relerr(s2[:, 0], ref[:, 0]) < tol
 
 
 def test_sdf_forward_ragged_and_empty(cases):
@@ -65,7 +69,7 @@ def test_sdf_forward_ragged_and_empty(cases):
         with torch.no_grad():
             ref = orc.sdf_mlp(c.spec, layers, pts)[0]
         out = m.implicit_network(pts.cuda())
-        assert relerr(out, ref) < (TOL if m._core_obj.uses_tensor_cores else 1e-5)
+        assert relerr(out, ref) < 1e-5
     out = m.implicit_network(torch.zeros(0, 3).cuda())
     assert out.shape == (0, 257)
 
@@ -108,6 +112,22 @@ def test_sampler_rounds_on_identical_inputs(cases, name):
         stats["max_cdf"] = max(stats["max_cdf"], float(cdf_err[good].max()))
         inds = out["inds"].cpu().long()
         same = inds == c.trace[f"round{i}_inds"]
+        # the integer step itself is exact: the kernel's indices ARE searchsorted(right=True) of the kernel's own cdf
+        ns_i = inds.shape[1]
+        u_i = (torch.linspace(0.0, 1.0, ns_i)[None].repeat(inds.shape[0], 1)).contiguous()
+        assert torch.equal(torch.searchsorted(out["cdf"].cpu().contiguous(), u_i, right=True), inds)
+        # ... and on rays that hit the surface every index that differs from the oracle's sits on a bin edge: all cdf entries between the two
+        # indices are within that ray's cdf difference of u (several bins only where zero-mass bins repeat the same cdf value)
+        ref_inds, ref_cdf = c.trace[f"round{i}_inds"], c.trace[f"round{i}_cdf"]
+        good_rows = ok_ray & hit
+        rr, jj = torch.where(~same & good_rows[:, None])
+        if rr.numel():
+            a_idx = torch.minimum(inds[rr, jj], ref_inds[rr, jj])
+            b_idx = torch.maximum(inds[rr, jj], ref_inds[rr, jj]) - 1
+            ray_cdf_err = (out["cdf"].cpu() - ref_cdf).abs().max(-1)[0][rr] + 1e-7
+            assert bool(((u_i[rr, jj] - ref_cdf[rr, a_idx]).abs() <= ray_cdf_err).all()) and bool(((u_i[rr, jj] - ref_cdf[rr, b_idx]).abs() <= ray_cdf_err).all())
+        good, empty = ok_ray & hit, ok_ray & ~hit
+        stats["max_cdf"] = max(stats["max_cdf"], float(cdf_err[good].max()))
         stats["bad_inds"] += int((~same[good]).sum())
         stats["n_inds"] += int(same[good].numel())
         samp_err = (out["samples"].cpu() - c.trace[f"round{i}_samples"]).abs()
@@ -123,7 +143,7 @@ def test_sampler_rounds_on_identical_inputs(cases, name):
             assert torch.equal(torch.sort(cat, -1)[0], zm)
         beta_in = ref_beta
     print(f"{name}: sampler-round stats {stats}")
-    assert stats["bad_beta"] <= max(1, stats["n_beta"] // 50), stats
+    assert stats["bad_beta"] <= 1, stats                       # measured 0 of 96 .. 240
     assert stats["max_cdf"] < 2e-5, stats
     assert stats["bad_inds"] <= max(2, stats["n_inds"] // 100), stats
     assert stats["max_samp"] < 1e-4, stats
@@ -149,10 +169,11 @@ def test_sampler_end_to_end(cases, name):
     close_all = ((zc - ref).abs() < 1e-3).float().mean()
     print(f"{name}: end-to-end sampler: z within 1e-3 of the reference: {close_hit:.4f} of surface-hitting rays, "
           f"{close_all:.4f} of all rays (tensor cores: {core.uses_tensor_cores})")
-    # the sampler is a chain of discrete decisions (bisection, bin search): an sdf perturbed by the tensor-core path's
-    # ~3e-5 moves a few percent of the samples of a few rays; images are unaffected (see the PSNR test below)
-    assert close_hit > 0.94, close_hit
-    assert close_all > 0.85, close_all
+    # the sampler is a chain of discrete decisions (bisection, bin search) that amplifies last-bit differences: measured 0.9997 / 1.0 /
+    # 0.9689 of the surface-hitting rays' samples within 1e-3 (round 1, sdf error 1e-5: 0.94); rays that miss the surface have a
+    # noise-dominated up-sampling pdf (see above) and carry no weight
+    assert close_hit > 0.96, close_hit
+    assert close_all > 0.9, close_all
 
 
 @pytest.mark.parametrize("name", EVAL_CASES)
@@ -210,12 +231,16 @@ def test_forward_eval_end_to_end(cases, name):
     assert set(out) == set(c.ref)
     for k, v in c.ref.items():
         assert out[k].shape == v.shape, k
-    # end to end the sampler's z may differ in a few bins (see above) -> compare as images: PSNR(new, reference)
+    # end to end through the sampler, north_star's bar on the fixtures: measured rgb 4.3e-6 / 1.2e-6 / 4.2e-5, weight_sum alike, depth
+    # 3e-6 / 2e-6 / 2.4e-4 (light fixture: one ray whose sample set differs; the fp32 cross-check kernel gives 1.7e-5 there), PSNR 109-135 dB
     mse = ((out["rgb_values"].cpu() - c.ref["rgb_values"]) ** 2).mean()
     psnr = -10.0 * torch.log10(mse.clamp(min=1e-20))
-    print(f"{name}: PSNR(new render, reference render) = {psnr:.1f} dB; rgb rel err {relerr(out['rgb_values'], c.ref['rgb_values']):.2e}")
-    assert psnr > 60.0, psnr
-    assert relerr(out["depth_values"], c.ref["depth_values"]) < 5e-3
+    print(f"{name}: PSNR(new render, reference render) = {psnr:.1f} dB; rgb rel err {relerr(out['rgb_values'], c.ref['rgb_values']):.2e} "
+          f"depth {relerr(out['depth_values'], c.ref['depth_values']):.2e} weight_sum {relerr(out['weight_sum'], c.ref['weight_sum']):.2e}")
+    assert psnr > 100.0, psnr
+    assert relerr(out["rgb_values"], c.ref["rgb_values"]) < TOL
+    assert relerr(out["weight_sum"], c.ref["weight_sum"]) < TOL
+    assert relerr(out["depth_values"], c.ref["depth_values"]) < 5e-4
     out2 = m({k: v.cuda() for k, v in c.inputs.items()}, predict_only=True)
     assert "normal_map" not in out2 and torch.equal(out2["rgb_values"], out["rgb_values"])   # same kernels, deterministic
     out3 = m({k: v.cuda() for k, v in c.inputs.items()})
@@ -317,8 +342,9 @@ def test_training_step_on_reference_z(name):
         if e_max > worst_max:
             worst_max, worst_name = e_max, k
         worst_l2 = max(worst_l2, e_l2)
-        assert e_l2 < (5e-3 if tcm else 2e-3), (k, e_l2)
-        assert e_max < (2e-2 if tcm else 2e-3), (k, e_max)
+        # measured (tensor-core forward, fused backward): worst L2 2.0e-4 / 3.6e-5, worst max-norm 9.6e-4 / 9.4e-5 (round 1: 3.5e-3 / 7e-3)
+        assert e_l2 < 1e-3, (k, e_l2)
+        assert e_max < 5e-3, (k, e_max)
     print(f"{name}: param-grad errors: worst max-norm {worst_max:.2e} ({worst_name}), worst L2 {worst_l2:.2e} (tensor-core forward: {tcm})")
 
 
@@ -478,8 +504,8 @@ def test_forward_saved_slots_and_fused_backward_vs_torch(cases):
     P = params[:n_sdf] + params[n_sdf + n_col:2 * n_sdf + n_col] + params[n_sdf:n_sdf + n_col] + params[2 * n_sdf + n_col:]
     s_sdf, s_grad, s_rgb, _, x_grad = _PointsFn.apply(core, o, d, z, xe, True, n_sdf, n_col, 0, *P)
     assert s_sdf.shape == (M,) and s_grad.shape == (M, 3) and s_rgb.shape == (M, 3) and x_grad.shape == (E, 3)
-    assert relerr(s_sdf, ref["sdf"][:M].float()) < TOL and relerr(s_rgb, ref["rgb"][:M].float()) < TOL
-    assert relerr(s_grad, ref["grad"][:M].float()) < 3e-4 and relerr(x_grad, ref["grad"][M:].float()) < 3e-4
+    assert relerr(s_sdf, ref["sdf"][:M].float()) < 1e-5 and relerr(s_rgb, ref["rgb"][:M].float()) < 1e-5
+    assert relerr(s_grad, ref["grad"][:M].float()) < 3e-5 and relerr(x_grad, ref["grad"][M:].float()) < 3e-5
     # saved H slots = inputs of SDF layers 1.. ; slot l lives at l * slot_bytes
     saved = s_sdf.grad_fn.saved_tensors[3]
     big = core.lib.i2sdf_planes_slot_bytes(M + E, 256)
@@ -502,8 +528,7 @@ def test_forward_saved_slots_and_fused_backward_vs_torch(cases):
         worst = max(worst, e)
         # radiance stack (i >= n_sdf within W / b): a few ReLU masks flip under the 1e-5 feature error of the tensor-core forward,
         # each flip moves the gradient by one point's contribution (same bound as the reference-fixture training tests)
-        col = (i % nW) >= n_sdf
-        assert e < (5e-3 if col else 2e-3), (i, "W" if i < nW else "b", e)
+        assert e < 2e-4, (i, "W" if i < nW else "b", e)           # measured worst 1.2e-5 (round 1: 1.1e-3)
     print(f"fused backward vs torch fp64 autograd: worst relative L2 gradient error {worst:.2e}")
 
 
@@ -715,7 +740,7 @@ def test_ragged_ray_counts_render_and_train(R):
         ref = orc.render(spec, P, inp, training=False)
     for k in ("rgb_values", "depth_values", "weight_sum", "light_mask"):
         assert out[k].shape == ref[k].shape, k
-        assert relerr(out[k], ref[k]) < 5e-3, (k, relerr(out[k], ref[k]))       # end to end through the sampler (indices may move one bin)
+        assert relerr(out[k], ref[k]) < 2e-3, (k, relerr(out[k], ref[k]))       # end to end through the sampler (a flipped sample set on one of <= 130 rays)
     m.train()
     tin = {k: v.cuda() for k, v in orc.synthetic_rays(R, seed=R + 1, train_layout=True).items()}
     g = torch.Generator().manual_seed(R)
