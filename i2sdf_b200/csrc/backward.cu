@@ -788,7 +788,10 @@ int fused_backward(const i2sdf_handle* h, const bwd::PointSrc& src, long long M,
     a.ntiles = planes::ntiles(M);
     auto job = [&](float* dst, int ld, int rows, int cols) { a.jobs[a.njobs] = WgJob{dst, ld, rows, cols}; return a.njobs++; };
     auto term = [&](int j, size_t Poff, bool Pws, size_t Xoff, bool Xws, int xchunks, float* colsum, int ncs) {
-        a.terms[a.nterms++] = WgTerm{(Pws ? SL.wbase : SL.base) + Poff, (Xws ? SL.wbase : SL.base) + Xoff, j, xchunks, colsum, ncs};
+        // P operands in the workspace are adjoint slots (P, PC, FB: HI plane only); X operands in the workspace are tangent slots (HD, ED)
+        const int pp = Pws ? planes::kPlanesAdj : 2;
+        const int xp = (Xws && xchunks == planes::BIG_CHUNKS) ? planes::kPlanesHD : 2;
+        a.terms[a.nterms++] = WgTerm{(Pws ? SL.wbase : SL.base) + Poff, (Xws ? SL.wbase : SL.base) + Xoff, j, xchunks, colsum, ncs, pp, xp};
     };
     for (int l = NL - 1; l >= 1; --l) {
         const int j = job(dW[l], h->lay_in[l], h->lay_out[l], h->lay_in[l]);
@@ -819,12 +822,12 @@ int fused_backward(const i2sdf_handle* h, const bwd::PointSrc& src, long long M,
     // ---- rank-1 pieces
     CsArgs c{};
     c.ntiles = a.ntiles; c.M = M;
-    if (g_sdf) c.jobs[c.njobs++] = CsJob{SL.base + SL.H(NL - 1), g_sdf, 1, dW[L - 1], 256, 1, 0};            // dW_last[0,:] += sum sbar h~
-    if (g_grad) c.jobs[c.njobs++] = CsJob{SL.wbase + SL.HD(NL - 1), nullptr, 0, dW[L - 1], 256, 1, 0};        // q_last = e_sdf: += sum hdot~
+    if (g_sdf) c.jobs[c.njobs++] = CsJob{SL.base + SL.H(NL - 1), g_sdf, 1, dW[L - 1], 256, 1, 0, 2};            // dW_last[0,:] += sum sbar h~
+    if (g_grad) c.jobs[c.njobs++] = CsJob{SL.wbase + SL.HD(NL - 1), nullptr, 0, dW[L - 1], 256, 1, 0, planes::kPlanesHD};        // q_last = e_sdf: += sum hdot~
     if (color) {
         sigmoid_adjoint3_kernel<<<blocks(M), 256, 0, st>>>(M, s_rgb, g_rgb, D);
         I2SDF_CUDA_CHECK(cudaGetLastError());
-        c.jobs[c.njobs++] = CsJob{SL.base + SL.C(Lc - 2), D, 4, dWc[Lc - 1], 256, 3, 256};      // the three rgb-head rows: one pass over the slot
+        c.jobs[c.njobs++] = CsJob{SL.base + SL.C(Lc - 2), D, 4, dWc[Lc - 1], 256, 3, 256, 2};      // the three rgb-head rows: one pass over the slot
         if ((rc = colsum(st, M, 3, D, 4, nullptr, dbc[Lc - 1]))) return rc;
     }
     if ((rc = planes_colsum_launch(h, c, st))) return rc;

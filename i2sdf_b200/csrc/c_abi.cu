@@ -756,7 +756,7 @@ int i2sdf_planes_wgrad(i2sdf_handle* h, int nterms, const void* const* P, const 
     WgArgs a{};
     a.ntiles = planes::ntiles(M); a.nterms = nterms; a.njobs = 1;
     a.jobs[0] = WgJob{dW, ld, rows, cols};
-    for (int t = 0; t < nterms; ++t) a.terms[t] = WgTerm{(const uint8_t*)P[t], (const uint8_t*)X[t], 0, planes_chunks(x_columns), t == 0 ? colsum : nullptr, rows};
+    for (int t = 0; t < nterms; ++t) a.terms[t] = WgTerm{(const uint8_t*)P[t], (const uint8_t*)X[t], 0, planes_chunks(x_columns), t == 0 ? colsum : nullptr, rows, 2, 2};
     return wgrad_planes_launch(h, a, (cudaStream_t)stream);
 }
 

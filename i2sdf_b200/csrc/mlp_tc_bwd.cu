@@ -18,6 +18,7 @@
 // (mlp.py:84-143, incl. the create_graph second-order graph) and RenderingNetwork.forward (mlp.py:208-229) — every
 // per-point matrix product except the weight gradients themselves.
 #include <stdlib.h>
+#include <type_traits>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tc_chain.cuh"
@@ -29,22 +30,29 @@ namespace tcb {
 using namespace tc;
 using namespace chain;
 
-// the four 16-byte segments (hi / lo planes x two chunks) of a 16-column item
-__device__ __forceinline__ void pf_seg16(const uint8_t* seg) {
-    pf_l2(seg); pf_l2(seg + planes::SUB_CHUNK); pf_l2(seg + planes::BIG_PLANE); pf_l2(seg + planes::BIG_PLANE + planes::SUB_CHUNK);
-}
+// Work items are 32 rows x 8 columns (round 2): in every iteration all 16 epilogue warps work on ONE 32-column chunk, so the next op's
+// MMA chain starts after 1/8 of an epilogue; the slot segments an op reads (H / Q / HD / C: written up to 20 ops - or a whole kernel -
+// earlier, i.e. in HBM) are pulled into L2 one OP ahead and requested in front of the item's TMEM load; the slot copies of an item leave
+// behind its publish.  Round 1 (16-column items, 8 warps per chunk, prefetch one item ahead) ran at ~24 k clocks per op against ~8 k
+// for the sampler's kernel: every item waited for its own HBM round trips.
+// Shared memory: A_hi | A_lo (32 chunks each: K <= 256) | weight ring | heads (sdf head 257, rgb head 771 floats) | barriers.
+constexpr int B8_A_PART = 32 * TM * 16;
+constexpr int B8_PARAM_FLOATS = 260 + 772;
+constexpr size_t kSmemBwd8 = 128 + 2 * (size_t)B8_A_PART + NSTAGE * STAGE_MAX + B8_PARAM_FLOATS * 4 + 256;
+enum { KB_TAN = 0, KB_TAN_SKIP, KB_TAN_LAST, KB_COL_REV, KB_FEAT_ADJ, KB_P, KB_P_SKIP, KB_P_TOP };
 
-template <bool PF_NEXT>
-__global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const BwdParams P, const OpTable T) {
+__global__ void __launch_bounds__(NTHREADS, 1) tc_bwd8_kernel(const BwdParams P, const OpTable T) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = smem_align1024(smem_raw);
+    uint8_t* smem = smem_align128(smem_raw);
     uint8_t* A_hi = smem;
-    uint8_t* A_lo = smem + A_PART_BYTES;
-    uint8_t* ring = smem + 2 * A_PART_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + NSTAGE * STAGE_MAX + PART_FLOATS * 4);
+    uint8_t* A_lo = smem + B8_A_PART;
+    uint8_t* ring = smem + 2 * B8_A_PART;
+    float* s_sdf_head = reinterpret_cast<float*>(ring + NSTAGE * STAGE_MAX);
+    float* s_col_head = s_sdf_head + 260;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_sdf_head + B8_PARAM_FLOATS);
     uint64_t* full = bars;
     uint64_t* empty = bars + NSTAGE;
-    uint64_t* a_ready = bars + 2 * NSTAGE;       // [N_READY], 8 arrivals each
+    uint64_t* a_ready = bars + 2 * NSTAGE;       // [N_READY], 16 arrivals each
     uint64_t* d_full = a_ready + N_READY;        // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 2);
 
@@ -55,11 +63,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const BwdParams P, 
 
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < N_READY; ++i) mbar_init(&a_ready[i], 8);
+        for (int i = 0; i < N_READY; ++i) mbar_init(&a_ready[i], N_EPI_WARPS);
         mbar_init(&d_full[0], 1);
         mbar_init(&d_full[1], 1);
         fence_mbar_init();
     }
+    for (int i = tid; i < 257; i += NTHREADS) s_sdf_head[i] = net.sdf_head[i];
+    for (int i = tid; i < 771; i += NTHREADS) s_col_head[i] = net.col_head[i];
     if (warp == 1) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
@@ -73,16 +83,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const BwdParams P, 
     } else {
         // ================= epilogue warps =================
         const int q = warp & 3;
-        const int sub = (warp - 2) >> 2;
+        const int sub = (warp - 2) >> 2;                     // column group: columns 8 sub .. 8 sub + 7 of every 32-column chunk
         const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const int nsplit = 256 - net.ex;
-        const float RS2 = 0.70710678118654752f, S2 = 1.41421356237309505f;
+        const float RS2 = 0.70710678118654752f, S2 = 1.41421356237309505f, C1 = 144.26950408889634f;
         const planes::Layout& SL = P.sl;
         const bool color = P.with_color != 0;
         uint32_t dphase = 0, g = 0;
+        float x[3], gb[3];
         // point of this thread's row and the upstream of grad_x sdf there
-        auto load_point = [&](long long tile, float (&x)[3], float (&gb)[3]) {
+        auto load_point = [&](long long tile) {
             const long long m = tile * TM + row;
             x[0] = x[1] = x[2] = 0.f; gb[0] = gb[1] = gb[2] = 0.f;
             if (m < P.M) {
@@ -97,33 +108,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const BwdParams P, 
                 if (P.g_grad) { gb[0] = P.g_grad[m * 3]; gb[1] = P.g_grad[m * 3 + 1]; gb[2] = P.g_grad[m * 3 + 2]; }
             }
         };
-        // prologue: A_0 = tangent of the embedding, J(x) gbar, 48 columns (sub s: columns 16 s ..), also slot ED
-        auto prologue = [&](const float (&x)[3], const float (&gb)[3], long long tile) {
-            if (sub < 3) {
-                float hv[16];
+        auto gb_of = [&](int coord) -> float { return coord == 0 ? gb[0] : (coord == 1 ? gb[1] : gb[2]); };
+        // prologue: A_0 = tangent of the embedding, J(x) gbar, 48 columns = k chunks 0..5 (group sub: chunk sub, groups 0 / 1 also 4 / 5), also slot ED
+        auto prologue = [&](long long tile) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int i = sub * 16 + j;
-                    int coord = 0;
-                    const float jac = (i < net.ex) ? embed_jac(x, i, net.mx, coord) : 0.f;
-                    hv[j] = jac * (coord == 0 ? gb[0] : (coord == 1 ? gb[1] : gb[2]));
+            for (int h = 0; h < 2; ++h) {
+                const int kc = sub + 4 * h;
+                if (kc < 6) {
+                    float hv[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int i = kc * 8 + j;
+                        int coord = 0;
+                        const float jac = (i < net.ex) ? embed_jac(x, i, net.mx, coord) : 0.f;
+                        hv[j] = jac * gb_of(coord);
+                    }
+                    uint32_t hh[4], ll[4];
+                    sts_a8<false>(A_hi, A_lo, row, kc, hv, hh, ll);
+                    stg_a8<true>(SL.wbase + SL.ED() + planes::seg(tile * TM + row, kc, planes::SMALL_CHUNKS), (uint32_t)planes::SMALL_PLANE, true, hv, hh, ll);
                 }
-                store_a16<false>(A_hi, A_lo, row, sub * 2, hv);
-                publish_chunk(&a_ready[sub >> 1], lane);
-                // slot copies leave BEHIND the publish: a fence.proxy.async behind a global store waits for that store (MEMBAR.ALL.CTA)
-                store_a16<false>(A_hi, A_lo, row, sub * 2, hv, SL.wbase + SL.ED() + planes::seg(tile * TM + row, sub * 2, planes::SMALL_CHUNKS),
-                                 (uint32_t)planes::SMALL_PLANE, true, false);
-            } else {
-                publish_chunk(&a_ready[sub >> 1], lane);
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&a_ready[0]); mbar_arrive(&a_ready[1]); }
+        };
+        // L2 prefetch of the 8 segments (one per item) this thread reads from a slot in one op
+        auto pf_slot = [&](const uint8_t* base, long long m, bool both_planes, int slot_planes = 2) {
+            const uint8_t* s0 = base + planes::segp(m, sub, planes::BIG_CHUNKS, slot_planes);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                pf_l2(s0 + (size_t)it * 4 * planes::SUB_CHUNK);
+                if (both_planes) pf_l2(s0 + (size_t)it * 4 * planes::SUB_CHUNK + planes::BIG_PLANE);
             }
         };
-        float x[3], gb[3];
-        if ((long long)blockIdx.x < ntiles) { load_point(blockIdx.x, x, gb); prologue(x, gb, blockIdx.x); }
+        if ((long long)blockIdx.x < ntiles) { load_point(blockIdx.x); prologue(blockIdx.x); }
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const long long m = tile * TM + row;
             const bool valid = m < P.M;
             const long long next_tile = tile + gridDim.x;
-            float xn[3] = {0.f, 0.f, 0.f}, gbn[3] = {0.f, 0.f, 0.f};
             // per-point upstream scalars
             const float sbar = (valid && P.g_sdf) ? P.g_sdf[m] : 0.f;
             float delta[3] = {0.f, 0.f, 0.f};
@@ -131,168 +154,179 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd_kernel(const BwdParams P, 
 #pragma unroll
                 for (int c = 0; c < 3; ++c) { const float y = P.s_rgb[m * 3 + c]; delta[c] = P.g_rgb[m * 3 + c] * y * (1.f - y); }
             }
+            if (tile == (long long)blockIdx.x) pf_slot(SL.base + SL.H(0), m, true);       // first op of the first tile
             for (int op = 0; op < T.nops; ++op, ++g) {
                 const uint32_t b = g & 1u;
                 const int kind = T.ops[op].kind, l = T.ops[op].layer;
+                const bool last_op = (op == T.nops - 1);
                 mbar_wait(&d_full[b], (dphase >> b) & 1u);
                 dphase ^= (1u << b);
                 tc_fence_after();
-                const bool last_op = (op == T.nops - 1);
+                const uint32_t acc_addr = tmem_base + lane_base + b * 256u;
+                {   // pull what the NEXT op reads into L2 now (for the last op: the next tile's first op)
+                    const int nk = last_op ? BK_TAN : T.ops[op + 1].kind, nl = last_op ? 0 : T.ops[op + 1].layer;
+                    const long long nm = last_op ? next_tile * TM + row : m;
+                    if (!last_op || next_tile < ntiles) {
+                        if (nk == BK_TAN) {
+                            pf_slot(SL.base + SL.H(nl), nm, true);
+                            if (nl == NL - 1 && color) pf_slot(SL.base + SL.C(net.Lc - 2), nm, false);
+                        } else if (nk == BK_COL_REV) pf_slot(SL.base + SL.C(nl - 1), nm, false);
+                        else if (nk == BK_P) { pf_slot(SL.base + SL.H(nl), nm, true); pf_slot(SL.base + SL.Q(nl), nm, true); pf_slot(SL.wbase + SL.HD(nl), nm, planes::kPlanesHD == 2, planes::kPlanesHD); }
+                    }
+                }
                 if (last_op && next_tile < ntiles) {
                     // the A operand is free (this tile's last MMAs are done): start the next tile's first op now
-                    load_point(next_tile, xn, gbn);
-                    prologue(xn, gbn, next_tile);
+                    load_point(next_tile);
+                    prologue(next_tile);
                 }
+                auto items = [&](auto kind_c) {
+                    constexpr int K = decltype(kind_c)::value;
+                    constexpr bool is_tan = (K == KB_TAN || K == KB_TAN_SKIP || K == KB_TAN_LAST);
+                    constexpr bool is_p = (K == KB_P || K == KB_P_SKIP || K == KB_P_TOP);
+                    const float hs = (K == KB_TAN_SKIP || K == KB_P_SKIP) ? C1 * S2 : C1;
 #pragma unroll 1
-                for (int it = 0; it < 4; ++it) {
-                    const int c = 2 * it + (sub >> 1);                 // 32-column chunk
-                    const int col0 = c * 32 + (sub & 1) * 16;          // first of this warp's 16 columns
-                    const int kc0 = col0 >> 3;
-                    const size_t sg = planes::seg(m, kc0, planes::BIG_CHUNKS);
-                    if (PF_NEXT) {
-                        // this warp's NEXT item (same op, or the first item of the next op) reads 2..6 slot segments per 8 columns
-                        // straight from HBM with nothing else to hide the latency behind: pull them into L2 one item ahead
-                        int pk = kind, pl = l, pit = it + P.pf_dist;
-                        if (pit >= 4) { pit -= 4; if (op + 1 < T.nops) { pk = T.ops[op + 1].kind; pl = T.ops[op + 1].layer; } else pk = -1; }
-                        const size_t psg = planes::seg(m, ((2 * pit + (sub >> 1)) * 32 + (sub & 1) * 16) >> 3, planes::BIG_CHUNKS);
-                        if (pk == BK_P) {
-                            pf_seg16(SL.base + SL.H(pl) + psg); pf_seg16(SL.base + SL.Q(pl) + psg); pf_seg16(SL.wbase + SL.HD(pl) + psg);
-                        } else if (pk == BK_TAN) {
-                            pf_seg16(SL.base + SL.H(pl) + psg);
-                        } else if (pk == BK_COL_REV) {
-                            pf_l2(SL.base + SL.C(pl - 1) + psg); pf_l2(SL.base + SL.C(pl - 1) + psg + planes::SUB_CHUNK);
+                    for (int it = 0; it < 8; ++it) {
+                        const int col0 = it * 32 + sub * 8, kc = it * 4 + sub;
+                        const size_t sg = planes::seg(m, kc, planes::BIG_CHUNKS);
+                        const size_t sg_adj = planes::segp(m, kc, planes::BIG_CHUNKS, planes::kPlanesAdj);      // adjoint slots: HI plane only
+                        const size_t sg_hd = planes::segp(m, kc, planes::BIG_CHUNKS, planes::kPlanesHD);
+                        // slot operands of the item: requested in front of the TMEM load (L2 hits thanks to the op-ahead prefetch)
+                        uint4 h_hi = make_uint4(0, 0, 0, 0), h_lo = h_hi, q_hi = h_hi, q_lo = h_hi, d_hi = h_hi, d_lo = h_hi, c_hi = h_hi;
+                        if (is_tan || is_p) {
+                            const uint8_t* ph = SL.base + SL.H(l) + sg;
+                            h_hi = ldg_cs(ph); h_lo = ldg_cs(ph + planes::BIG_PLANE);
                         }
-                    }
-                    if (kind == BK_TAN) {
-                        // hdot_l = softplus'(a_l) * adot_l   (skip concat: [hdot | J gbar] / sqrt2)
-                        const bool feeds_skip = (l + 1 == net.skip);
-                        uint4 raw[4];
-                        load_slot16(SL.base + SL.H(l) + sg, raw);
-                        uint32_t v[16];
-                        tmem_ld16(tmem_base + lane_base + b * 256u + (uint32_t)col0, v);
+                        if (is_p) {
+                            const uint8_t* pq = SL.base + SL.Q(l) + sg;
+                            const uint8_t* pd = SL.wbase + SL.HD(l) + sg_hd;
+                            q_hi = ldg_cs(pq); q_lo = ldg_cs(pq + planes::BIG_PLANE);
+                            d_hi = ldg_cs(pd);
+                            if (planes::kPlanesHD == 2) d_lo = ldg_cs(pd + planes::BIG_PLANE);
+                        }
+                        if (K == KB_COL_REV) c_hi = ldg_cs(SL.base + SL.C(l - 1) + sg);
+                        if (K == KB_TAN_LAST && color) c_hi = ldg_cs(SL.base + SL.C(net.Lc - 2) + sg);
+                        uint32_t v[8];
+                        tmem_ld8(acc_addr + (uint32_t)col0, v);
                         tmem_ld_wait();
-                        float hv[16];
-                        slot16_values(raw, hv);
-                        const float hs = feeds_skip ? 144.26950408889634f * S2 : 144.26950408889634f;
+                        float hv[8];
+                        uint8_t* gs = nullptr;
+                        bool keep = true, to_smem = true, adj_slot = true;       // adj_slot: gs is an adjoint slot (HI plane only), else a tangent slot
+                        if (is_tan) {
+                            // hdot_l = softplus'(a_l) * adot_l   (skip concat: [hdot | J gbar] / sqrt2)
+                            float hh[8];
+                            seg8_values<false>(h_hi, h_lo, hh);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float t = (1.0f - ex2_approx(-hs * hv[j])) * __uint_as_float(v[j]);
-                            if (feeds_skip) {
-                                const int f = col0 + j;
-                                if (f >= nsplit) {
-                                    int coord;
-                                    const float jac = embed_jac(x, f - nsplit, net.mx, coord);
-                                    t = jac * (coord == 0 ? gb[0] : (coord == 1 ? gb[1] : gb[2]));
+                            for (int j = 0; j < 8; ++j) hv[j] = (1.0f - ex2_approx(-hs * hh[j])) * __uint_as_float(v[j]);
+                            if (K == KB_TAN_SKIP) {
+                                if (col0 + 8 > nsplit) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        const int f = col0 + j;
+                                        if (f >= nsplit) {
+                                            int coord;
+                                            const float jac = embed_jac(x, f - nsplit, net.mx, coord);
+                                            hv[j] = jac * gb_of(coord);
+                                        }
+                                    }
                                 }
-                                t *= RS2;
-                            }
-                            hv[j] = t;
-                        }
-                        const bool more = (l < NL - 1);
-                        if (more) {
-                            store_a16<false>(A_hi, A_lo, row, kc0, hv);
-                            publish_chunk(&a_ready[c], lane);
-                        }
-                        store_a16<false>(A_hi, A_lo, row, kc0, hv, SL.wbase + SL.HD(l) + sg, (uint32_t)planes::BIG_PLANE, true, false);
-                        if (!more) {
-                            // the tangent pass is over and its last MMAs are done: build the A operand of the reverse pass
-                            if (color) {
-                                // pc_{Lc-2} = [c_{Lc-2} > 0] * (W_head^T delta)
-                                const uint8_t* cs = SL.base + SL.C(net.Lc - 2) + sg;
-                                const uint4 c0 = *reinterpret_cast<const uint4*>(cs), c1 = *reinterpret_cast<const uint4*>(cs + planes::SUB_CHUNK);
-                                const uint32_t cw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-                                const float* __restrict__ wh = net.col_head + col0;
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) {
-                                    const float cv = (j & 1) ? __uint_as_float(cw[j >> 1] & 0xffff0000u) : __uint_as_float(cw[j >> 1] << 16);
-                                    const float u = fmaf(delta[0], __ldg(wh + j), fmaf(delta[1], __ldg(wh + 256 + j), delta[2] * __ldg(wh + 512 + j)));
-                                    hv[j] = cv > 0.f ? u : 0.f;
+                                for (int j = 0; j < 8; ++j) hv[j] *= RS2;
+                            }
+                            gs = SL.wbase + SL.HD(l) + sg_hd;
+                            adj_slot = false;
+                            if (K == KB_TAN_LAST) {
+                                // the tangent pass is over and its last MMAs are done: HD(l) to its slot, then build the A operand of the reverse pass
+                                uint32_t th[4], tl[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) split_bf16x2(hv[2 * i], hv[2 * i + 1], th[i], tl[i]);
+                                stg_cs(gs, make_uint4(th[0], th[1], th[2], th[3]));
+                                if (planes::kPlanesHD == 2) stg_cs(gs + planes::BIG_PLANE, make_uint4(tl[0], tl[1], tl[2], tl[3]));
+                                gs = nullptr;
+                                adj_slot = true;
+                                if (color) {
+                                    // pc_{Lc-2} = [c_{Lc-2} > 0] * (W_head^T delta)
+                                    const uint32_t cw[4] = {c_hi.x, c_hi.y, c_hi.z, c_hi.w};
+                                    const float* __restrict__ wh = s_col_head + col0;
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        const float cv = (j & 1) ? __uint_as_float(cw[j >> 1] & 0xffff0000u) : __uint_as_float(cw[j >> 1] << 16);
+                                        const float u = fmaf(delta[0], wh[j], fmaf(delta[1], wh[256 + j], delta[2] * wh[512 + j]));
+                                        hv[j] = cv > 0.f ? u : 0.f;
+                                    }
+                                    gs = SL.wbase + SL.PC(net.Lc - 2) + sg_adj;
+                                    keep = valid;
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) hv[j] = 0.f;     // no radiance stack: fbar = 0
                                 }
-                                store_a16<false>(A_hi, A_lo, row, kc0, hv);
-                                publish_chunk(&a_ready[c], lane);
-                                store_a16<false>(A_hi, A_lo, row, kc0, hv, SL.wbase + SL.PC(net.Lc - 2) + sg, (uint32_t)planes::BIG_PLANE, valid, false);
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) hv[j] = 0.f;     // no radiance stack: fbar = 0
-                                store_a16<false>(A_hi, A_lo, row, kc0, hv);
-                                publish_chunk(&a_ready[c], lane);
                             }
-                        }
-                    } else if (kind == BK_COL_REV) {
-                        // accumulator = W_l^T pc_l ; pc_{l-1} = that * [c_{l-1} > 0]
-                        const uint8_t* cs = SL.base + SL.C(l - 1) + sg;
-                        const uint4 c0 = *reinterpret_cast<const uint4*>(cs), c1 = *reinterpret_cast<const uint4*>(cs + planes::SUB_CHUNK);
-                        const uint32_t cw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-                        uint32_t v[16];
-                        tmem_ld16(tmem_base + lane_base + b * 256u + (uint32_t)col0, v);
-                        tmem_ld_wait();
-                        float hv[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float cv = (j & 1) ? __uint_as_float(cw[j >> 1] & 0xffff0000u) : __uint_as_float(cw[j >> 1] << 16);
-                            hv[j] = cv > 0.f ? __uint_as_float(v[j]) : 0.f;
-                        }
-                        store_a16<false>(A_hi, A_lo, row, kc0, hv);
-                        publish_chunk(&a_ready[c], lane);
-                        store_a16<false>(A_hi, A_lo, row, kc0, hv, SL.wbase + SL.PC(l - 1) + sg, (uint32_t)planes::BIG_PLANE, valid, false);
-                    } else if (kind == BK_FEAT_ADJ) {
-                        // accumulator = adjoint of the features
-                        uint32_t v[16];
-                        tmem_ld16(tmem_base + lane_base + b * 256u + (uint32_t)col0, v);
-                        tmem_ld_wait();
-                        float hv[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) hv[j] = __uint_as_float(v[j]);
-                        store_a16<false>(A_hi, A_lo, row, kc0, hv);
-                        publish_chunk(&a_ready[c], lane);
-                        store_a16<false>(A_hi, A_lo, row, kc0, hv, SL.wbase + SL.FB() + sg, (uint32_t)planes::BIG_PLANE, valid, false);
-                    } else {
-                        // BK_P: accumulator = W_{l+1}^T p_{l+1} ; produce p_l (l = op.layer), 8 columns at a time
-                        const bool feeds_skip = (l + 1 == net.skip);
-                        const bool top = (l == NL - 1);
-                        const float hs = feeds_skip ? 144.26950408889634f * S2 : 144.26950408889634f;
-                        float pv16[16];
-#pragma unroll
-                        for (int s = 0; s < 2; ++s) {
-                            const size_t sg8 = sg + (size_t)s * planes::SUB_CHUNK;
-                            const uint8_t* ph = SL.base + SL.H(l) + sg8;
-                            const uint8_t* pq = SL.base + SL.Q(l) + sg8;
-                            const uint8_t* pd = SL.wbase + SL.HD(l) + sg8;
-                            const uint4 h_hi = *reinterpret_cast<const uint4*>(ph), h_lo = *reinterpret_cast<const uint4*>(ph + planes::BIG_PLANE);
-                            const uint4 q_hi = *reinterpret_cast<const uint4*>(pq), q_lo = *reinterpret_cast<const uint4*>(pq + planes::BIG_PLANE);
-                            const uint4 d_hi = *reinterpret_cast<const uint4*>(pd), d_lo = *reinterpret_cast<const uint4*>(pd + planes::BIG_PLANE);
-                            uint32_t v[8];
-                            tmem_ld8(tmem_base + lane_base + b * 256u + (uint32_t)(col0 + 8 * s), v);
-                            tmem_ld_wait();
-                            float hh[8], qq[8], dd[8], pv[8];
-                            seg8_values(h_hi, h_lo, hh);
-                            seg8_values(q_hi, q_lo, qq);
-                            seg8_values(d_hi, d_lo, dd);
+                        } else if (K == KB_COL_REV) {
+                            // accumulator = W_l^T pc_l ; pc_{l-1} = that * [c_{l-1} > 0]
+                            const uint32_t cw[4] = {c_hi.x, c_hi.y, c_hi.z, c_hi.w};
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                const int f = col0 + 8 * s + j;
+                                const float cv = (j & 1) ? __uint_as_float(cw[j >> 1] & 0xffff0000u) : __uint_as_float(cw[j >> 1] << 16);
+                                hv[j] = cv > 0.f ? __uint_as_float(v[j]) : 0.f;
+                            }
+                            gs = SL.wbase + SL.PC(l - 1) + sg_adj;
+                            keep = valid;
+                        } else if (K == KB_FEAT_ADJ) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) hv[j] = __uint_as_float(v[j]);
+                            gs = SL.wbase + SL.FB() + sg_adj;
+                            keep = valid;
+                        } else {
+                            // BK_P: accumulator = W_{l+1}^T p_{l+1} ; p_l = s'(a_l) u + s''(a_l) adot_l v_l with q_l = s'(a_l) v_l from the forward
+                            float hh[8], qq[8], dd[8];
+                            seg8_values<false>(h_hi, h_lo, hh);
+                            seg8_values<false>(q_hi, q_lo, qq);
+                            seg8_values<false>(d_hi, d_lo, dd);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
                                 const float e = ex2_approx(-hs * hh[j]);          // 1 - softplus'
                                 const float sp = 1.0f - e;
                                 float u = __uint_as_float(v[j]);
-                                if (top) u = fmaf(sbar, __ldg(net.sdf_head + f), u);
+                                if (K == KB_P_TOP) u = fmaf(sbar, s_sdf_head[col0 + j], u);
                                 float hd = dd[j];
-                                if (feeds_skip) { u *= RS2; hd *= S2; }
+                                if (K == KB_P_SKIP) { u *= RS2; hd *= S2; }
                                 const float t2 = sp > 0.f ? 100.f * e * hd * qq[j] * rcp_approx(sp) : 0.f;
                                 float p = fmaf(sp, u, t2);
-                                if (feeds_skip && f >= nsplit) p = 0.f;
-                                pv[j] = p;
+                                if (K == KB_P_SKIP && col0 + j >= nsplit) p = 0.f;
+                                hv[j] = p;
                             }
-                            if (!last_op) store_a8<false>(A_hi, A_lo, row, kc0 + s, pv, nullptr, true, true);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) pv16[s * 8 + j] = pv[j];
+                            gs = SL.wbase + SL.P(l) + sg_adj;
+                            keep = valid;
+                            to_smem = !last_op;
                         }
-                        if (!last_op) publish_chunk(&a_ready[c], lane);
-                        store_a16<false>(A_hi, A_lo, row, kc0, pv16, SL.wbase + SL.P(l) + sg, (uint32_t)planes::BIG_PLANE, valid, false);
+                        uint32_t hh2[4], ll2[4];
+                        if (to_smem) {
+                            sts_a8<false>(A_hi, A_lo, row, kc, hv, hh2, ll2);
+                            publish_chunk(&a_ready[it], lane);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) split_bf16x2(hv[2 * i], hv[2 * i + 1], hh2[i], ll2[i]);
+                        }
+                        if (gs) {
+                            if (adj_slot) stg_a8<true, planes::kPlanesAdj>(gs, (uint32_t)planes::BIG_PLANE, keep, hv, hh2, ll2);
+                            else stg_a8<true, planes::kPlanesHD>(gs, (uint32_t)planes::BIG_PLANE, keep, hv, hh2, ll2);
+                        }
                     }
+                };
+                switch (kind) {
+                    case BK_TAN:
+                        if (l == NL - 1) items(std::integral_constant<int, KB_TAN_LAST>{});
+                        else if (l + 1 == net.skip) items(std::integral_constant<int, KB_TAN_SKIP>{});
+                        else items(std::integral_constant<int, KB_TAN>{});
+                        break;
+                    case BK_COL_REV: items(std::integral_constant<int, KB_COL_REV>{}); break;
+                    case BK_FEAT_ADJ: items(std::integral_constant<int, KB_FEAT_ADJ>{}); break;
+                    default:
+                        if (l == NL - 1) items(std::integral_constant<int, KB_P_TOP>{});
+                        else if (l + 1 == net.skip) items(std::integral_constant<int, KB_P_SKIP>{});
+                        else items(std::integral_constant<int, KB_P>{});
+                        break;
                 }
             }
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { x[c] = xn[c]; gb[c] = gbn[c]; }
         }
     }
     tc_fence_before();
@@ -307,22 +341,17 @@ int tc_bwd_launch(const i2sdf_handle* h, const BwdParams& p, cudaStream_t st) {
     if (p.M <= 0) return I2SDF_OK;
     const chain::OpTable* tab = tc_bwd_table(h, p.with_color != 0);
     if (!tab || tab->nops == 0) { set_error("tc_bwd_launch: no backward op table for this network"); return I2SDF_E_INVALID; }
-    static bool attr_done = false;
-    static int pf = 1;
-    if (!attr_done) {
-        I2SDF_CUDA_CHECK(cudaFuncSetAttribute(tc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain::kSmemBytes));
-        I2SDF_CUDA_CHECK(cudaFuncSetAttribute(tc_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain::kSmemBytes));
-        const char* e = getenv("I2SDF_BWD_PREFETCH");          // items ahead (1..4), 0 = off
-        pf = e ? atoi(e) : 1;
-        if (pf < 0 || pf > 4) pf = 1;
-        attr_done = true;
+    // (per device: cudaFuncSetAttribute is a per-device setting)
+    static bool attr_done[64] = {};
+    int dev = 0;
+    I2SDF_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+        I2SDF_CUDA_CHECK(cudaFuncSetAttribute(tc_bwd8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBwd8));
+        attr_done[dev] = true;
     }
     const long long ntiles = (p.M + chain::TM - 1) / chain::TM;
     const int grid = (int)(ntiles < (long long)h->num_sms ? ntiles : (long long)h->num_sms);
-    BwdParams q = p;
-    q.pf_dist = pf;
-    if (pf) tc_bwd_kernel<true><<<grid, chain::NTHREADS, chain::kSmemBytes, st>>>(q, *tab);
-    else tc_bwd_kernel<false><<<grid, chain::NTHREADS, chain::kSmemBytes, st>>>(q, *tab);
+    tc_bwd8_kernel<<<grid, chain::NTHREADS, kSmemBwd8, st>>>(p, *tab);
     I2SDF_CUDA_CHECK(cudaGetLastError());
     return I2SDF_OK;
 }

@@ -36,6 +36,18 @@ __host__ __device__ inline size_t seg(long long m, int kc, int chunks) {
     return (size_t)(m >> 5) * (size_t)(2 * chunks) * SUB_CHUNK + (size_t)kc * SUB_CHUNK + (size_t)(m & 31) * 16;
 }
 
+// the same for a slot with `nplanes` planes per sub tile (1: HI plane only)
+__host__ __device__ inline size_t segp(long long m, int kc, int chunks, int nplanes) {
+    return (size_t)(m >> 5) * (size_t)(nplanes * chunks) * SUB_CHUNK + (size_t)kc * SUB_CHUNK + (size_t)(m & 31) * 16;
+}
+// Planes per slot kind (1 = HI plane only).  Adjoints (P, PC, FB) are written by the backward chain and read ONLY by the weight-gradient
+// kernel, so their LO plane can be dropped for half the bytes of those streams.  Measured in round 2 (profiles/r02_summary.txt): chain
+// 1.54 -> 1.46 ms, weight gradients 0.68 -> 0.59 ms, training step -3 % - but the parameter-gradient error against the reference grew from
+// 2.0e-4 to 6.7e-4 (L2, 32-ray fixture; 3.6e-5 -> 3.5e-4 on the light config): a 2^-9 rounding per adjoint averages out only over many
+// points.  Rejected: both planes stay.  The plane count is a per-slot-kind constant so that the trade can be re-made in one place.
+constexpr int kPlanesAdj = 2;
+constexpr int kPlanesHD = 2;
+
 __host__ __device__ inline long long ntiles(long long M) { return (M + TM - 1) / TM; }
 __host__ __device__ inline size_t big_slot_bytes(long long M) { return (size_t)ntiles(M) * BIG_TILE; }
 __host__ __device__ inline size_t small_slot_bytes(long long M) { return (size_t)ntiles(M) * SMALL_TILE; }
@@ -55,6 +67,7 @@ struct Layout {
     uint8_t* base;      // saved forward state (null: nothing is saved)
     uint8_t* wbase;     // backward workspace
     size_t big, small, dvb;
+    size_t adj, hd;     // bytes of one adjoint slot (P, PC, FB) / one tangent slot (HD): big * planes / 2
     int NL, Lc, color;
     __host__ __device__ size_t H(int l) const { return (size_t)l * big; }
     __host__ __device__ size_t Q(int l) const { return (size_t)(NL + l) * big; }
@@ -63,17 +76,18 @@ struct Layout {
     __host__ __device__ size_t C(int l) const { return CF() + (size_t)(1 + l) * big; }
     __host__ __device__ size_t DV() const { return CF() + (size_t)Lc * big; }
     __host__ __device__ size_t saved_total() const { return color ? DV() + dvb : E() + small; }
-    __host__ __device__ size_t HD(int l) const { return (size_t)l * big; }
-    __host__ __device__ size_t P(int l) const { return (size_t)(NL + l) * big; }
-    __host__ __device__ size_t ED() const { return (size_t)2 * NL * big; }
+    __host__ __device__ size_t HD(int l) const { return (size_t)l * hd; }
+    __host__ __device__ size_t P(int l) const { return (size_t)NL * hd + (size_t)l * adj; }
+    __host__ __device__ size_t ED() const { return (size_t)NL * hd + (size_t)NL * adj; }
     __host__ __device__ size_t FB() const { return ED() + small; }
-    __host__ __device__ size_t PC(int l) const { return FB() + (size_t)(1 + l) * big; }
-    __host__ __device__ size_t bwd_total() const { return FB() + (size_t)(color ? Lc : 1) * big; }
+    __host__ __device__ size_t PC(int l) const { return FB() + (size_t)(1 + l) * adj; }
+    __host__ __device__ size_t bwd_total() const { return FB() + (size_t)(color ? Lc : 1) * adj; }
 };
 inline Layout make_layout(long long M, int NL, int Lc, bool color, void* base, void* wbase) {
     Layout L{};
     L.base = (uint8_t*)base; L.wbase = (uint8_t*)wbase;
     L.big = big_slot_bytes(M); L.small = small_slot_bytes(M); L.dvb = (size_t)ntiles(M) * 4 * 2 * DV_CHUNKS * SUB_CHUNK;
+    L.adj = L.big * kPlanesAdj / 2; L.hd = L.big * kPlanesHD / 2;
     L.NL = NL; L.Lc = Lc; L.color = color ? 1 : 0;
     return L;
 }

@@ -118,7 +118,7 @@ __device__ __forceinline__ void sts_a8(uint8_t* A_hi, uint8_t* A_lo, int row, in
     *reinterpret_cast<uint4*>(A_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(A_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
-template <bool SLOT_SAME>
+template <bool SLOT_SAME, int NPLANES = 2>
 __device__ __forceinline__ void stg_a8(uint8_t* g, uint32_t g_lo, bool keep, const float (&hv)[8], uint32_t (&h)[4], uint32_t (&lo)[4]) {
     if (!SLOT_SAME) {
 #pragma unroll
@@ -127,7 +127,7 @@ __device__ __forceinline__ void stg_a8(uint8_t* g, uint32_t g_lo, bool keep, con
     // streaming stores: the eval scratch is read back once by the same CTA, the training slots once by the backward kernels, and
     // neither should push the weight blocks out of L2
     stg_cs(g, keep ? make_uint4(h[0], h[1], h[2], h[3]) : make_uint4(0, 0, 0, 0));
-    stg_cs(g + g_lo, keep ? make_uint4(lo[0], lo[1], lo[2], lo[3]) : make_uint4(0, 0, 0, 0));
+    if (NPLANES == 2) stg_cs(g + g_lo, keep ? make_uint4(lo[0], lo[1], lo[2], lo[3]) : make_uint4(0, 0, 0, 0));
 }
 __device__ __forceinline__ void pf_l2(const uint8_t* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // 8 columns (one chunk) of a slot: hi / lo segments -> fp32

@@ -73,17 +73,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_planes_kernel(const WgArgs 
             for (long long u = u0; u < u1; ++u) {
                 const WgTerm& t = A.terms[u / A.ntiles];
                 const long long tile = u % A.ntiles;
-                const uint32_t xsub = (uint32_t)t.xchunks * 2u * (uint32_t)planes::SUB_CHUNK;      // hi + lo of one X sub tile
-                const uint32_t xplane = xsub / 2;
-                const uint8_t* Pb = t.P + (size_t)tile * planes::BIG_TILE;
+                const int pp = t.p_planes == 1 ? 1 : 2, xp = t.x_planes == 1 ? 1 : 2;
+                const uint32_t xplane = (uint32_t)t.xchunks * (uint32_t)planes::SUB_CHUNK;
+                const uint32_t xsub = xplane * (uint32_t)xp;                                       // one X sub tile: hi (+ lo)
+                const uint32_t psub = (uint32_t)planes::BIG_PLANE * (uint32_t)pp;                  // one P sub tile: hi (+ lo)
+                const uint8_t* Pb = t.P + (size_t)tile * 4 * psub;
                 const uint8_t* Xb = t.X + (size_t)tile * 4 * xsub;
                 for (int sub = 0; sub < planes::TM / SUB_ROWS; ++sub) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full[stage], (uint32_t)planes::BIG_SUB + xsub);
+                    mbar_arrive_expect_tx(&full[stage], psub + xsub);
                     uint8_t* dst = ring + stage * STAGE_BYTES;
-                    bulk_g2s(dst, Pb + (size_t)sub * planes::BIG_SUB, (uint32_t)planes::BIG_SUB, &full[stage]);      // P_hi | P_lo
+                    bulk_g2s(dst, Pb + (size_t)sub * psub, psub, &full[stage]);                                      // P_hi (| P_lo)
                     bulk_g2s(dst + 2 * PLANE_STAGE, Xb + (size_t)sub * xsub, xplane, &full[stage]);                  // X_hi
-                    bulk_g2s(dst + 3 * PLANE_STAGE, Xb + (size_t)sub * xsub + xplane, xplane, &full[stage]);         // X_lo
+                    if (xp == 2) bulk_g2s(dst + 3 * PLANE_STAGE, Xb + (size_t)sub * xsub + xplane, xplane, &full[stage]);   // X_lo
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
             }
@@ -99,6 +101,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_planes_kernel(const WgArgs 
             for (long long u = u0; u < u1; ++u) {
                 const WgTerm& t = A.terms[u / A.ntiles];
                 const uint32_t idesc = instr_desc_bf16(128, t.xchunks * 8) | (1u << 15) | (1u << 16);
+                const bool p2 = t.p_planes != 1, x2 = t.x_planes != 1;       // an operand with its HI plane only: its lo product is skipped
                 for (int sub = 0; sub < planes::TM / SUB_ROWS; ++sub) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
@@ -115,8 +118,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_planes_kernel(const WgArgs 
                             const uint64_t a_lo = smem_desc(base + PLANE_STAGE + aoff, lbo, sbo);
                             const uint32_t d = tmem_base + (uint32_t)hf * 256u;
                             mma_bf16_ss(d, a_hi, b_hi, idesc, fresh ? 0u : 1u);
-                            mma_bf16_ss(d, a_lo, b_hi, idesc, 1u);
-                            mma_bf16_ss(d, a_hi, b_lo, idesc, 1u);
+                            if (p2) mma_bf16_ss(d, a_lo, b_hi, idesc, 1u);
+                            if (x2) mma_bf16_ss(d, a_hi, b_lo, idesc, 1u);
                         }
                         fresh = false;
                     }
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) wgrad_planes_kernel(const WgArgs 
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
                         const uint4 hi = *reinterpret_cast<const uint4*>(sp + (fw + 8 * a) * SUB_CHUNK);
-                        const uint4 lo = *reinterpret_cast<const uint4*>(sp + PLANE_STAGE + (fw + 8 * a) * SUB_CHUNK);
+                        const uint4 lo = (t.p_planes != 1) ? *reinterpret_cast<const uint4*>(sp + PLANE_STAGE + (fw + 8 * a) * SUB_CHUNK) : make_uint4(0, 0, 0, 0);
                         const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
@@ -277,8 +280,9 @@ __global__ void __launch_bounds__(256) planes_colsum_kernel(const CsArgs A) {
             }
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
-                const uint8_t* sp = J.slot + planes::seg(m, warp + 8 * a, planes::BIG_CHUNKS);
-                const uint4 hi = *reinterpret_cast<const uint4*>(sp), lo = *reinterpret_cast<const uint4*>(sp + planes::BIG_PLANE);
+                const int np = J.nplanes == 1 ? 1 : 2;
+                const uint8_t* sp = J.slot + planes::segp(m, warp + 8 * a, planes::BIG_CHUNKS, np);
+                const uint4 hi = *reinterpret_cast<const uint4*>(sp), lo = (np == 2) ? *reinterpret_cast<const uint4*>(sp + planes::BIG_PLANE) : make_uint4(0, 0, 0, 0);
                 const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {

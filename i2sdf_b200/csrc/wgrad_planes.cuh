@@ -17,6 +17,7 @@ struct WgTerm {
     int xchunks;           // 32, or 6 for the positional-encoding slots
     float* colsum;         // optional: colsum[j] += sum_m P[m][j]  (bias gradient), j < colsum_n
     int colsum_n;
+    int p_planes, x_planes;   // planes per sub tile of each operand: 2 = hi + lo, 1 = hi only (adjoint slots); 0 is read as 2
 };
 struct WgJob {
     float* dW;             // fp32 [rows][ld], accumulated into
@@ -37,6 +38,7 @@ struct CsJob {
     int n;
     int nw;                // weight vectors sharing ONE pass over the slot (1..3; w null: 1 = plain column sums)
     int ostride;
+    int nplanes;           // planes of the slot (0 is read as 2)
 };
 struct CsArgs {
     long long ntiles, M;
