@@ -42,8 +42,8 @@ def main():
     print(f"sdf_forward (sdf only) M={M}: {t:.3f} ms  {M / t / 1e3:.1f} M pts/s  {M * 918016 / t / 1e9:.1f} TFLOP/s algorithmic")
     Mf = R * 97
     ptsf = pts[:Mf].contiguous()
-    t = timeit(lambda: core.sdf_forward(ptsf, want_feat=True, want_grad=True))
-    print(f"sdf_forward (feat+grad, fp32 kernel) M={Mf}: {t:.3f} ms  {Mf / t / 1e3:.1f} M pts/s")
+    t = timeit(lambda: core.sdf_forward(ptsf, want_grad=True))
+    print(f"sdf_forward (sdf + grad_x, chain F.. R..) M={Mf}: {t:.3f} ms  {Mf / t / 1e3:.1f} M pts/s")
     o, d, dn = core.rays(inp["uv"], inp["pose"], inp["intrinsics"])
     beta = m.density.beta.detach()
     t = timeit(lambda: core.sample(o, d, beta))
