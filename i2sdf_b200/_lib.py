@@ -93,6 +93,8 @@ SYMBOLS = {
     "i2sdf_saved_bytes_points": (C.c_size_t, [_P, C.c_int64]),
     "i2sdf_fused_backward": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(_P), C.POINTER(_P),
                                        C.POINTER(_P), C.POINTER(_P), _P, C.c_size_t, _P]),
+    "i2sdf_fused_backward_ex": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.c_int64, _P, C.POINTER(_P), C.POINTER(_P),
+                                          C.POINTER(_P), C.POINTER(_P), _P, C.c_size_t, _P]),
     "i2sdf_loss_forward": (C.c_int, [C.POINTER(LossArgs), _P]),
     "i2sdf_weight_norm": (C.c_int, [C.POINTER(WnormBatch), C.c_int, _P]),
     "i2sdf_adam_step": (C.c_int, [C.POINTER(AdamBatch), _P]),

@@ -93,16 +93,10 @@ class _PointsFn(Function):
             if not want_grad:
                 g_grad = None
             if g_sdf is not None or g_rgb is not None or g_grad is not None or (E and g_xgrad is not None):
-                if E:       # upstreams of the appended points: only grad_x sdf carries one
-                    if g_sdf is not None:
-                        g_sdf = torch.cat([g_sdf, g_sdf.new_zeros(E)])
-                    if g_rgb is not None:
-                        g_rgb = torch.cat([g_rgb, g_rgb.new_zeros(E, 3)])
-                    if g_grad is not None or g_xgrad is not None:
-                        g_grad = torch.cat([g_grad if g_grad is not None else o.new_zeros(M, 3),
-                                            g_xgrad if g_xgrad is not None else o.new_zeros(E, 3)])
+                # the upstream arrays cover the M ray samples; the appended points only carry an upstream of grad_x sdf (no concatenation
+                # with zero blocks: i2sdf_fused_backward_ex takes the two pieces as they are)
                 core.fused_backward(M + E, act, dW_sdf, db_sdf, rays=(o, d, z, N), pts=extra_pts if E else None, s_rgb=s_rgb, g_sdf=g_sdf,
-                                    g_grad=g_grad, g_rgb=g_rgb, dW_col=dW_col, db_col=db_col)
+                                    g_grad=g_grad, g_rgb=g_rgb, dW_col=dW_col, db_col=db_col, m_up=M, g_grad_tail=g_xgrad if E else None)
             if n_light > 0 and g_light is not None:
                 # the head's own parameters only: its input features are detached (network/__init__.py:165)
                 hidden = act.data_ptr() + act.numel() - (M + E) * core.desc.light_hidden * 4     # behind the plane slots (i2sdf_b200.h)
@@ -417,13 +411,17 @@ class _WeightNormAll(Function):
         if all(d is None for d in dWs):
             return (None,) * (2 * n)
         gvw = ctx.grad_views
+        direct = {}            # output index -> parameter whose .grad becomes the bucket view this backward wrote into
 
         def out_like(t, i):
-            # straight into the bucket view - but only while the parameter has no .grad: autograd would otherwise ADD this result to
-            # a .grad that already is the same memory (zero_grad(set_to_none=False)) and double it
+            # Straight into the parameter's persistent gradient view (parallel.GradBucket) - and then the parameter's .grad is SET to that
+            # view here and autograd gets no gradient for this input: handing the view back would make AccumulateGrad clone it (a view
+            # is never "stolen": 27 device-to-device copies per step in the round-2 trace, tools/gpu_gaps.py).  Only while the parameter
+            # has no .grad (with zero_grad(set_to_none=False) autograd must accumulate, so the ordinary path is taken).
             if gvw is not None and gvw[i][1] is not None:
                 prm, w = gvw[i][0](), gvw[i][1]
                 if prm is not None and prm.grad is None and w.shape == t.shape and w.device == t.device:
+                    direct[i] = prm
                     return w
             return torch.empty_like(t)
         dgs = [None if d is None else out_like(g, 2 * i) for i, (d, g) in enumerate(zip(dWs, gs))]
@@ -432,6 +430,9 @@ class _WeightNormAll(Function):
         out = []
         for dg, dv in zip(dgs, dvs):
             out += [dg, dv]
+        for i, prm in direct.items():
+            prm.grad = out[i]
+            out[i] = None
         return tuple(out)
 
 

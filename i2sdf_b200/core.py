@@ -417,13 +417,13 @@ class RenderCore:
         self._keep = (g_sdf, g_grad)
 
     def fused_backward(self, M, saved, dW_sdf, db_sdf, pts=None, rays=None, s_rgb=None, g_sdf=None, g_grad=None, g_rgb=None,
-                       dW_col=None, db_col=None):
+                       dW_col=None, db_col=None, m_up=None, g_grad_tail=None):
         """Tensor-core backward on plane slots (i2sdf_fused_backward).  rays = (o, d, z [R,zstride], ns); with rays AND pts
         the first R*ns points are ray samples and pts are the points appended after them."""
         dev = self.device
         bws = self.backward_workspace(M)
         f = lambda t: None if t is None else _f32(t, dev)        # noqa: E731
-        g_sdf, g_grad, g_rgb = f(g_sdf), f(g_grad), f(g_rgb)
+        g_sdf, g_grad, g_rgb, g_grad_tail = f(g_sdf), f(g_grad), f(g_rgb), f(g_grad_tail)
         m_rays = 0
         if rays is not None:
             o, d, z, ns = rays
@@ -433,11 +433,13 @@ class RenderCore:
             po = pd = pz = _ptr(None)
             zs, ns, pp = 0, 1, _ptr(pts)
         null = C.POINTER(C.c_void_p)()
-        check(self.lib.i2sdf_fused_backward(self.h, pp, po, pd, pz, zs, ns, M, m_rays, _ptr(saved), _ptr(s_rgb), _ptr(g_sdf), _ptr(g_grad), _ptr(g_rgb),
-                                            self._ptr_array(dW_sdf), self._ptr_array(db_sdf),
-                                            self._ptr_array(dW_col) if dW_col else null, self._ptr_array(db_col) if db_col else null,
-                                            _ptr(bws), bws.numel(), self._stream()), "i2sdf_fused_backward")
-        self._keep = (g_sdf, g_grad, g_rgb)
+        # m_up: the upstream arrays cover the first m_up points; the appended points' grad_x upstream comes separately (g_grad_tail)
+        check(self.lib.i2sdf_fused_backward_ex(self.h, pp, po, pd, pz, zs, ns, M, m_rays, _ptr(saved), _ptr(s_rgb), _ptr(g_sdf), _ptr(g_grad), _ptr(g_rgb),
+                                               M if m_up is None else m_up, _ptr(g_grad_tail),
+                                               self._ptr_array(dW_sdf), self._ptr_array(db_sdf),
+                                               self._ptr_array(dW_col) if dW_col else null, self._ptr_array(db_col) if db_col else null,
+                                               _ptr(bws), bws.numel(), self._stream()), "i2sdf_fused_backward_ex")
+        self._keep = (g_sdf, g_grad, g_rgb, g_grad_tail)
 
     def render(self, o, d, dnorm, z, beta_param, want_normal=True, want_light=False, per_sample=False, save=None):
         """Main pass + compositing.  z [R,N+1].  Returns dict of per-ray tensors (+ per-sample ones if asked)."""

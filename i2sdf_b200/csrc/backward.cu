@@ -421,10 +421,11 @@ __global__ void relu_mask_kernel(long long n, const float* __restrict__ H, float
     G[i] = H[i] > 0.f ? G[i] : 0.f;
 }
 // delta [M][4] = grgb * rgb (1 - rgb)
-__global__ void sigmoid_adjoint3_kernel(long long M, const float* __restrict__ rgb, const float* __restrict__ grgb, float* __restrict__ D) {
+__global__ void sigmoid_adjoint3_kernel(long long M, const float* __restrict__ rgb, const float* __restrict__ grgb, float* __restrict__ D, long long m_up = -1) {
     long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
-    for (int c = 0; c < 3; ++c) { float y = rgb[m * 3 + c]; D[m * 4 + c] = grgb[m * 3 + c] * y * (1.f - y); }
+    const bool up = m_up < 0 || m < m_up;            // grgb covers the first m_up points only
+    for (int c = 0; c < 3; ++c) { float y = rgb[m * 3 + c]; D[m * 4 + c] = up ? grgb[m * 3 + c] * y * (1.f - y) : 0.f; }
     D[m * 4 + 3] = 0.f;
 }
 }  // namespace bwd
@@ -765,7 +766,8 @@ size_t fused_backward_ws_bytes(const i2sdf_handle* h, long long M, bool color) {
 
 int fused_backward(const i2sdf_handle* h, const bwd::PointSrc& src, long long M, void* saved, const float* s_rgb, const float* g_sdf,
                    const float* g_grad, const float* g_rgb, float* const* dW, float* const* db, float* const* dWc, float* const* dbc, void* ws,
-                   int phases, long long m_rays, cudaStream_t st) {
+                   int phases, long long m_rays, cudaStream_t st, long long m_up, const float* g_grad_tail) {
+    if (m_up < 0 || m_up > M) m_up = M;
     // phases (bit mask, for per-phase timing by the caller): 1 = chain kernel, 2 = weight gradients, 4 = rank-1 pieces
     using namespace bwd;
     if (M <= 0) return I2SDF_OK;
@@ -779,6 +781,8 @@ int fused_backward(const i2sdf_handle* h, const bwd::PointSrc& src, long long M,
     p.pts = src.pts; p.ray_o = src.o; p.ray_d = src.d; p.zarr = src.z; p.zstride = src.zstride; p.ns = src.ns; p.M = M;
     p.m_rays = (src.pts && src.o) ? m_rays : 0;
     p.g_sdf = g_sdf; p.g_grad = g_grad; p.g_rgb = g_rgb; p.s_rgb = s_rgb; p.with_color = color ? 1 : 0;
+    p.m_up = m_up; p.g_grad_tail = g_grad_tail;
+    const bool any_grad = g_grad != nullptr || g_grad_tail != nullptr;
     p.sl = SL; p.net = n;
     if ((phases & 1) && (rc = tc_bwd_launch(h, p, st))) return rc;
     if (!(phases & 6)) return I2SDF_OK;
@@ -796,12 +800,12 @@ int fused_backward(const i2sdf_handle* h, const bwd::PointSrc& src, long long M,
     for (int l = NL - 1; l >= 1; --l) {
         const int j = job(dW[l], h->lay_in[l], h->lay_out[l], h->lay_in[l]);
         term(j, SL.P(l), true, SL.H(l - 1), false, planes::BIG_CHUNKS, db[l], h->lay_out[l]);
-        if (g_grad) term(j, SL.Q(l), false, SL.HD(l - 1), true, planes::BIG_CHUNKS, nullptr, 0);
+        if (any_grad) term(j, SL.Q(l), false, SL.HD(l - 1), true, planes::BIG_CHUNKS, nullptr, 0);
     }
     {
         const int j = job(dW[0], h->lay_in[0], h->lay_out[0], h->lay_in[0]);
         term(j, SL.P(0), true, SL.E(), false, planes::SMALL_CHUNKS, db[0], h->lay_out[0]);
-        if (g_grad) term(j, SL.Q(0), false, SL.ED(), true, planes::SMALL_CHUNKS, nullptr, 0);
+        if (any_grad) term(j, SL.Q(0), false, SL.ED(), true, planes::SMALL_CHUNKS, nullptr, 0);
     }
     if (color) {
         int j = job(dW[L - 1] + h->lay_in[L - 1], h->lay_in[L - 1], 256, 256);            // feature rows 1..256 of the last SDF layer
@@ -822,17 +826,17 @@ int fused_backward(const i2sdf_handle* h, const bwd::PointSrc& src, long long M,
     // ---- rank-1 pieces
     CsArgs c{};
     c.ntiles = a.ntiles; c.M = M;
-    if (g_sdf) c.jobs[c.njobs++] = CsJob{SL.base + SL.H(NL - 1), g_sdf, 1, dW[L - 1], 256, 1, 0, 2};            // dW_last[0,:] += sum sbar h~
-    if (g_grad) c.jobs[c.njobs++] = CsJob{SL.wbase + SL.HD(NL - 1), nullptr, 0, dW[L - 1], 256, 1, 0, planes::kPlanesHD};        // q_last = e_sdf: += sum hdot~
+    if (g_sdf) c.jobs[c.njobs++] = CsJob{SL.base + SL.H(NL - 1), g_sdf, 1, dW[L - 1], 256, 1, 0, 2, m_up};      // dW_last[0,:] += sum sbar h~
+    if (any_grad) c.jobs[c.njobs++] = CsJob{SL.wbase + SL.HD(NL - 1), nullptr, 0, dW[L - 1], 256, 1, 0, planes::kPlanesHD};        // q_last = e_sdf: += sum hdot~
     if (color) {
-        sigmoid_adjoint3_kernel<<<blocks(M), 256, 0, st>>>(M, s_rgb, g_rgb, D);
+        sigmoid_adjoint3_kernel<<<blocks(M), 256, 0, st>>>(M, s_rgb, g_rgb, D, m_up);
         I2SDF_CUDA_CHECK(cudaGetLastError());
         c.jobs[c.njobs++] = CsJob{SL.base + SL.C(Lc - 2), D, 4, dWc[Lc - 1], 256, 3, 256, 2};      // the three rgb-head rows: one pass over the slot
         if ((rc = colsum(st, M, 3, D, 4, nullptr, dbc[Lc - 1]))) return rc;
     }
     if ((rc = planes_colsum_launch(h, c, st))) return rc;
     if (g_sdf) {
-        sum_kernel<<<64, 256, 0, st>>>(M, g_sdf, db[L - 1]);
+        sum_kernel<<<64, 256, 0, st>>>(m_up, g_sdf, db[L - 1]);
         I2SDF_CUDA_CHECK(cudaGetLastError());
     }
     return I2SDF_OK;

@@ -33,7 +33,7 @@ int launch_composite(const i2sdf_handle*, const float*, const float*, const floa
 namespace bwd { struct PointSrc { const float* pts; const float* o; const float* d; const float* z; int zstride; int ns; }; }
 size_t fused_backward_ws_bytes(const i2sdf_handle*, long long, bool);
 int fused_backward(const i2sdf_handle*, const bwd::PointSrc&, long long, void*, const float*, const float*, const float*, const float*,
-                   float* const*, float* const*, float* const*, float* const*, void*, int, long long, cudaStream_t);
+                   float* const*, float* const*, float* const*, float* const*, void*, int, long long, cudaStream_t, long long m_up, const float* g_grad_tail);
 size_t sdf_backward_ws_floats(const i2sdf_handle*, long long);
 size_t color_backward_ws_floats(const i2sdf_handle*, long long);
 size_t light_backward_ws_floats(const i2sdf_handle*, long long);
@@ -144,6 +144,20 @@ struct ProfScope {
 }  // namespace i2sdf
 
 using namespace i2sdf;
+
+namespace {
+// Entry points run on the handle's device whatever the caller's current device is (and leave the caller's device current again):
+// a module moved to cuda:1 in a process whose current device is cuda:0 must not launch its kernels on cuda:0.
+struct DeviceScope {
+    int prev = -1;
+    explicit DeviceScope(const i2sdf_handle* h) {
+        if (!h) return;
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != h->device) { prev = cur; cudaSetDevice(h->device); }
+    }
+    ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+};
+}  // namespace
 
 extern "C" {
 
@@ -261,6 +275,7 @@ int i2sdf_num_layers(const i2sdf_handle* h) { return h ? h->n_layers : 0; }
 int i2sdf_uses_tensor_cores(const i2sdf_handle* h) { return h ? ((h->use_tc ? 1 : 0) | ((h->tcmain && tcmain_has_full(h->tcmain)) ? 2 : 0)) : 0; }
 
 int i2sdf_pack_weights(i2sdf_handle* h, const float* const* W, const float* const* b, void* stream) {
+    DeviceScope device_scope(h);
     if (!h || !W || !b) { set_error("null argument"); return I2SDF_E_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
     const NetDev& n = h->net;
@@ -358,6 +373,7 @@ static int run_light(const i2sdf_handle* h, long long M, const float* feat, floa
 
 int i2sdf_rays(i2sdf_handle* h, const float* uv, const float* pose, const float* intr, int B, int P, float* o, float* d,
                float* dnorm, void* stream) {
+    DeviceScope device_scope(h);
     if (!h || !uv || !pose || !intr || !o || !d || !dnorm) { set_error("null argument"); return I2SDF_E_INVALID; }
     ProfScope ps(h, 3, (cudaStream_t)stream);
     return launch_rays(uv, pose, intr, B, P, o, d, dnorm, (cudaStream_t)stream);
@@ -405,6 +421,7 @@ size_t i2sdf_sdf_saved_bytes(const i2sdf_handle* h, int64_t M) {
 
 int i2sdf_sdf_forward(i2sdf_handle* h, const float* pts, int64_t M, float* out_sdf, float* out_feat, float* out_grad,
                       float* save_act, void* workspace, size_t workspace_bytes, void* stream) {
+    DeviceScope device_scope(h);
     if (!h) { set_error("null handle"); return I2SDF_E_INVALID; }
     if (M == 0) return I2SDF_OK;
     if (M < 0 || !pts || !out_sdf) { set_error("null argument"); return I2SDF_E_INVALID; }
@@ -425,6 +442,7 @@ int i2sdf_sdf_forward(i2sdf_handle* h, const float* pts, int64_t M, float* out_s
 
 int i2sdf_sdf_grid(i2sdf_handle* h, const float* gx, const float* gy, const float* gz, int nx, int ny, int nz, const float* affine,
                    float* out_sdf, void* stream) {
+    DeviceScope device_scope(h);
     if (!h || !gx || !gy || !gz || !out_sdf) { set_error("null argument"); return I2SDF_E_INVALID; }
     if (nx < 1 || ny < 1 || nz < 1) { set_error("sdf_grid: empty grid"); return I2SDF_E_INVALID; }
     if (!h->use_tc) { set_error("sdf_grid: the tensor-core sdf kernel is not available for this handle"); return I2SDF_E_INVALID; }
@@ -438,6 +456,7 @@ int i2sdf_sdf_grid(i2sdf_handle* h, const float* gx, const float* gy, const floa
 
 int i2sdf_sampler_rounds(i2sdf_handle* h, const float* o, const float* d, int64_t R, const float* beta_param,
                          const float* jitter, const float* u_final, void* workspace, size_t workspace_bytes, void* stream) {
+    DeviceScope device_scope(h);
     if (!h || !o || !d || !beta_param || !workspace) { set_error("null argument"); return I2SDF_E_INVALID; }
     if (workspace_bytes < i2sdf_workspace_bytes(h, R, 0)) { set_error("sampler: workspace too small"); return I2SDF_E_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
@@ -460,6 +479,7 @@ int i2sdf_sampler_rounds(i2sdf_handle* h, const float* o, const float* d, int64_
 
 int i2sdf_sampler_step(i2sdf_handle* h, const float* o, const float* d, int64_t R, const float* beta_param, const float* jitter,
                        const float* u_final, int stage, int k, void* workspace, size_t workspace_bytes, void* stream) {
+    DeviceScope device_scope(h);
     if (!h || !o || !d || !beta_param || !workspace) { set_error("null argument"); return I2SDF_E_INVALID; }
     if (workspace_bytes < i2sdf_workspace_bytes(h, R, 0)) { set_error("sampler: workspace too small"); return I2SDF_E_WORKSPACE; }
     if (stage < 0 || stage > 2 || (stage > 0 && (k < 0 || k >= h->smp.max_iters))) { set_error("sampler_step: bad stage / round"); return I2SDF_E_INVALID; }
@@ -488,6 +508,7 @@ float* i2sdf_sampler_beta_max(i2sdf_handle* h, int64_t R, void* workspace) {
 
 int i2sdf_sampler_finalize(i2sdf_handle* h, int64_t R, const float* beta_param, const int32_t* extra_idx, const int32_t* eik_idx,
                            float* out_z, float* out_z_eik, int32_t* out_info, void* workspace, size_t workspace_bytes, void* stream) {
+    DeviceScope device_scope(h);
     if (!h || !beta_param || !out_z || !workspace) { set_error("null argument"); return I2SDF_E_INVALID; }
     if (workspace_bytes < i2sdf_workspace_bytes(h, R, 0)) { set_error("sampler: workspace too small"); return I2SDF_E_WORKSPACE; }
     SamplerWs W = carve_sampler_ws(h, R, (float*)workspace);
@@ -497,6 +518,7 @@ int i2sdf_sampler_finalize(i2sdf_handle* h, int64_t R, const float* beta_param, 
 
 int i2sdf_sampler_finalize_candidates(i2sdf_handle* h, int64_t R, const float* beta_param, const int32_t* extra_table, const int32_t* eik_idx,
                                       float* out_z, float* out_z_eik, int32_t* out_info, void* workspace, size_t workspace_bytes, void* stream) {
+    DeviceScope device_scope(h);
     if (!h || !beta_param || !out_z || !workspace || !extra_table) { set_error("null argument"); return I2SDF_E_INVALID; }
     if (workspace_bytes < i2sdf_workspace_bytes(h, R, 0)) { set_error("sampler: workspace too small"); return I2SDF_E_WORKSPACE; }
     SamplerWs W = carve_sampler_ws(h, R, (float*)workspace);
@@ -514,6 +536,7 @@ __global__ void sampler_info_kernel(SamplerDev S, const float* beta_max, const f
 
 int i2sdf_sampler_info(i2sdf_handle* h, int64_t R, const float* beta_param, int32_t* out_info, void* workspace,
                        size_t workspace_bytes, void* stream) {
+    DeviceScope device_scope(h);
     if (!h || !beta_param || !out_info || !workspace) { set_error("null argument"); return I2SDF_E_INVALID; }
     if (workspace_bytes < i2sdf_workspace_bytes(h, R, 0)) { set_error("sampler: workspace too small"); return I2SDF_E_WORKSPACE; }
     SamplerWs W = carve_sampler_ws(h, R, (float*)workspace);
@@ -525,6 +548,7 @@ int i2sdf_sampler_info(i2sdf_handle* h, int64_t R, const float* beta_param, int3
 int i2sdf_sampler_round_debug(i2sdf_handle* h, const float* z, const float* sdf, int64_t R, int n, const float* beta_param,
                               const float* beta_in, int force_upsample, const float* u_tape, float* out_beta, float* out_cdf,
                               int32_t* out_inds, float* out_samples, float* out_z_merged, int32_t* out_src, void* stream) {
+    DeviceScope device_scope(h);
     if (!h || !z || !sdf || !beta_param || !beta_in || !out_samples) { set_error("null argument"); return I2SDF_E_INVALID; }
     if (n < 2 || n > h->smp.n_eval * h->smp.max_iters) { set_error("round_debug: n=%d out of range", n); return I2SDF_E_INVALID; }
     return launch_sampler_round_debug(h, z, sdf, R, n, beta_param, beta_in, force_upsample, u_tape, out_beta, out_cdf, out_inds,
@@ -543,12 +567,14 @@ size_t i2sdf_backward_workspace_bytes(const i2sdf_handle* h, int64_t M) {
 
 int i2sdf_points_forward(i2sdf_handle* h, const float* o, const float* d, const float* z, int64_t R, int N, float* s_sdf, float* s_grad,
                          float* s_rgb, float* s_light, float* s_feat, float* save_act, void* workspace, size_t workspace_bytes, void* stream) {
+    DeviceScope device_scope(h);
     return i2sdf_points_forward_ex(h, o, d, z, R, N, nullptr, 0, s_sdf, s_grad, s_rgb, s_light, s_feat, save_act, workspace, workspace_bytes, stream);
 }
 
 int i2sdf_points_forward_ex(i2sdf_handle* h, const float* o, const float* d, const float* z, int64_t R, int N, const float* extra_pts,
                             int64_t n_extra, float* s_sdf, float* s_grad, float* s_rgb, float* s_light, float* s_feat, float* save_act,
                             void* workspace, size_t workspace_bytes, void* stream) {
+    DeviceScope device_scope(h);
     if (!h || !o || !d || !z || !s_sdf) { set_error("null argument"); return I2SDF_E_INVALID; }
     if (n_extra < 0 || (n_extra > 0 && (!extra_pts || !planes_main(h) || !s_rgb || !s_grad))) {
         set_error("points_forward_ex: extra points need the tensor-core main pass with s_rgb and s_grad"); return I2SDF_E_INVALID;
@@ -583,6 +609,7 @@ int i2sdf_points_forward_ex(i2sdf_handle* h, const float* o, const float* d, con
 int i2sdf_composite_forward(i2sdf_handle* h, const float* z, const float* dnorm, const float* s_sdf, const float* s_rgb, const float* s_grad,
                             const float* s_light, const float* beta_param, int64_t R, int N, float* rgb, float* depth, float* weight_sum,
                             float* normal, float* light, float* s_w, void* stream) {
+    DeviceScope device_scope(h);
     if (!h || !z || !dnorm || !s_sdf || !beta_param) { set_error("null argument"); return I2SDF_E_INVALID; }
     ProfScope ps(h, 3, (cudaStream_t)stream);
     return launch_composite(h, z, dnorm, s_sdf, s_rgb, s_grad, s_light, beta_param, R, N, rgb, depth, weight_sum, normal, light, s_w, (cudaStream_t)stream);
@@ -592,6 +619,7 @@ int i2sdf_composite_backward(i2sdf_handle* h, const float* z, const float* dnorm
                              const float* s_light, const float* beta_param, int64_t R, int N, const float* g_rgb, const float* g_depth,
                              const float* g_wsum, const float* g_normal, const float* g_light, float* o_sdf, float* o_rgb, float* o_grad,
                              float* o_light, float* o_beta, void* stream) {
+    DeviceScope device_scope(h);
     if (!h || !z || !dnorm || !s_sdf || !beta_param || !o_sdf) { set_error("null argument"); return I2SDF_E_INVALID; }
     if ((g_rgb && !s_rgb) || (g_normal && !s_grad)) { set_error("composite_backward: missing forward tensors"); return I2SDF_E_INVALID; }
     ProfScope ps(h, 3, (cudaStream_t)stream);
@@ -602,6 +630,7 @@ int i2sdf_composite_backward(i2sdf_handle* h, const float* z, const float* dnorm
 int i2sdf_color_backward(i2sdf_handle* h, const float* const* W, const float* const* b, const float* dirs, int ns, const float* feat,
                          const float* s_rgb, const float* g_rgb, int64_t M, float* const* dW, float* const* db, float* g_x, void* workspace,
                          size_t workspace_bytes, void* stream) {
+    DeviceScope device_scope(h);
     if (!h || !W || !b || !dirs || !feat || !s_rgb || !g_rgb || !dW || !db || !g_x || !workspace) { set_error("null argument"); return I2SDF_E_INVALID; }
     if (workspace_bytes < i2sdf_backward_workspace_bytes(h, M)) { set_error("color_backward: workspace too small"); return I2SDF_E_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
@@ -616,6 +645,7 @@ int i2sdf_color_backward(i2sdf_handle* h, const float* const* W, const float* co
 
 int i2sdf_light_backward(i2sdf_handle* h, const float* const* W, const float* const* b, const float* feat, const float* hidden, const float* s_light,
                          const float* g_light, int64_t M, float* const* dW, float* const* db, void* workspace, size_t workspace_bytes, void* stream) {
+    DeviceScope device_scope(h);
     if (!h || !W || !b || !feat || !s_light || !g_light || !dW || !db || !workspace) { set_error("null argument"); return I2SDF_E_INVALID; }
     if (h->net.Ll != 2) { set_error("light_backward: network has no light head"); return I2SDF_E_INVALID; }
     if (workspace_bytes < i2sdf_backward_workspace_bytes(h, M)) { set_error("light_backward: workspace too small"); return I2SDF_E_WORKSPACE; }
@@ -626,6 +656,7 @@ int i2sdf_light_backward(i2sdf_handle* h, const float* const* W, const float* co
 int i2sdf_sdf_backward(i2sdf_handle* h, const float* const* W, const float* pts, const float* o, const float* d, const float* z, int zstride,
                        int ns, int64_t M, const float* act, const float* g_sdf, const float* g_feat, int g_feat_ld, const float* g_grad,
                        float* const* dW, float* const* db, void* workspace, size_t workspace_bytes, void* stream) {
+    DeviceScope device_scope(h);
     if (!h || !W || !act || !dW || !db || !workspace || (!pts && (!o || !d || !z))) { set_error("null argument"); return I2SDF_E_INVALID; }
     if (workspace_bytes < i2sdf_backward_workspace_bytes(h, M)) { set_error("sdf_backward: workspace too small"); return I2SDF_E_WORKSPACE; }
     bwd::PointSrc S{pts, o, d, z, zstride, ns > 0 ? ns : 1};
@@ -665,27 +696,38 @@ size_t i2sdf_saved_bytes_points(const i2sdf_handle* h, int64_t M) {
     return (size_t)(h->net.L - 1) * (size_t)M * 256 * sizeof(float);
 }
 
-int i2sdf_fused_backward(i2sdf_handle* h, const float* pts, const float* o, const float* d, const float* z, int zstride, int ns, int64_t M,
-                         int64_t m_rays, void* saved, const float* s_rgb, const float* g_sdf, const float* g_grad, const float* g_rgb, float* const* dW_sdf,
-                         float* const* db_sdf, float* const* dW_col, float* const* db_col, void* workspace, size_t workspace_bytes, void* stream) {
+int i2sdf_fused_backward_ex(i2sdf_handle* h, const float* pts, const float* o, const float* d, const float* z, int zstride, int ns, int64_t M,
+                            int64_t m_rays, void* saved, const float* s_rgb, const float* g_sdf, const float* g_grad, const float* g_rgb, int64_t m_up,
+                            const float* g_grad_tail, float* const* dW_sdf, float* const* db_sdf, float* const* dW_col, float* const* db_col,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+    DeviceScope device_scope(h);
     if (!h || !saved || !dW_sdf || !db_sdf || !workspace || (!pts && (!o || !d || !z))) { set_error("fused_backward: null argument"); return I2SDF_E_INVALID; }
     if (pts && o && (m_rays < 0 || m_rays > M)) { set_error("fused_backward: m_rays out of range"); return I2SDF_E_INVALID; }
+    if (m_up < 0 || m_up > M || (g_grad_tail && m_up == M)) { set_error("fused_backward: m_up out of range"); return I2SDF_E_INVALID; }
     if (g_rgb && (!s_rgb || !dW_col || !db_col)) { set_error("fused_backward: g_rgb needs s_rgb, dW_col, db_col"); return I2SDF_E_INVALID; }
     if (!(g_rgb ? planes_main(h) : planes_sdf(h))) { set_error("fused_backward: this handle saves fp32 pre-activations (use i2sdf_sdf_backward / i2sdf_color_backward)"); return I2SDF_E_INVALID; }
     if (workspace_bytes < i2sdf_backward_workspace_bytes(h, M)) { set_error("fused_backward: workspace too small"); return I2SDF_E_WORKSPACE; }
     bwd::PointSrc S{pts, o, d, z, zstride, ns > 0 ? ns : 1};
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    { ProfScope ps(h, 4, st, 1); if ((rc = fused_backward(h, S, M, saved, s_rgb, g_sdf, g_grad, g_rgb, dW_sdf, db_sdf, dW_col, db_col, workspace, 1, m_rays, st))) return rc; }
-    { ProfScope ps(h, 5, st, 1); if ((rc = fused_backward(h, S, M, saved, s_rgb, g_sdf, g_grad, g_rgb, dW_sdf, db_sdf, dW_col, db_col, workspace, 2, m_rays, st))) return rc; }
-    { ProfScope ps(h, 3, st, g_rgb ? 4 : 2); if ((rc = fused_backward(h, S, M, saved, s_rgb, g_sdf, g_grad, g_rgb, dW_sdf, db_sdf, dW_col, db_col, workspace, 4, m_rays, st))) return rc; }
+    { ProfScope ps(h, 4, st, 1); if ((rc = fused_backward(h, S, M, saved, s_rgb, g_sdf, g_grad, g_rgb, dW_sdf, db_sdf, dW_col, db_col, workspace, 1, m_rays, st, m_up, g_grad_tail))) return rc; }
+    { ProfScope ps(h, 5, st, 1); if ((rc = fused_backward(h, S, M, saved, s_rgb, g_sdf, g_grad, g_rgb, dW_sdf, db_sdf, dW_col, db_col, workspace, 2, m_rays, st, m_up, g_grad_tail))) return rc; }
+    { ProfScope ps(h, 3, st, g_rgb ? 4 : 2); if ((rc = fused_backward(h, S, M, saved, s_rgb, g_sdf, g_grad, g_rgb, dW_sdf, db_sdf, dW_col, db_col, workspace, 4, m_rays, st, m_up, g_grad_tail))) return rc; }
     return I2SDF_OK;
+}
+
+int i2sdf_fused_backward(i2sdf_handle* h, const float* pts, const float* o, const float* d, const float* z, int zstride, int ns, int64_t M,
+                         int64_t m_rays, void* saved, const float* s_rgb, const float* g_sdf, const float* g_grad, const float* g_rgb, float* const* dW_sdf,
+                         float* const* db_sdf, float* const* dW_col, float* const* db_col, void* workspace, size_t workspace_bytes, void* stream) {
+    return i2sdf_fused_backward_ex(h, pts, o, d, z, zstride, ns, M, m_rays, saved, s_rgb, g_sdf, g_grad, g_rgb, M, nullptr, dW_sdf, db_sdf, dW_col, db_col,
+                                   workspace, workspace_bytes, stream);
 }
 
 int i2sdf_render_forward(i2sdf_handle* h, const float* o, const float* d, const float* dnorm, const float* z, int64_t R, int N,
                          const float* beta_param, float* rgb, float* depth, float* weight_sum, float* normal, float* light,
                          float* s_sdf, float* s_grad, float* s_rgb, float* s_w, float* s_light, void* save, size_t save_bytes,
                          void* workspace, size_t workspace_bytes, void* stream) {
+    DeviceScope device_scope(h);
     if (!h || !o || !d || !dnorm || !z || !beta_param || !workspace) { set_error("null argument"); return I2SDF_E_INVALID; }
     if (N < 1 || N > 128) { set_error("render_forward: N=%d samples per ray unsupported (1..128)", N); return I2SDF_E_INVALID; }
     if (workspace_bytes < i2sdf_workspace_bytes(h, R, 0)) { set_error("render_forward: workspace too small"); return I2SDF_E_WORKSPACE; }
@@ -740,15 +782,18 @@ size_t i2sdf_planes_slot_bytes(int64_t M, int columns) {
 static int planes_chunks(int columns) { return columns == 256 ? planes::BIG_CHUNKS : (columns == 48 ? planes::SMALL_CHUNKS : 0); }
 
 int i2sdf_planes_pack(i2sdf_handle* h, const float* X, int ld, int width, int64_t M, int columns, void* slot, void* stream) {
+    DeviceScope device_scope(h);
     if (!h || !X || !slot || !planes_chunks(columns) || width > columns) { set_error("planes_pack: bad argument"); return I2SDF_E_INVALID; }
     return planes_pack_launch(X, ld, width, M, (uint8_t*)slot, planes_chunks(columns), (cudaStream_t)stream);
 }
 int i2sdf_planes_unpack(i2sdf_handle* h, const void* slot, int columns, int64_t M, float* X, int ld, int width, void* stream) {
+    DeviceScope device_scope(h);
     if (!h || !X || !slot || !planes_chunks(columns) || width > columns) { set_error("planes_unpack: bad argument"); return I2SDF_E_INVALID; }
     return planes_unpack_launch((const uint8_t*)slot, planes_chunks(columns), M, X, ld, width, (cudaStream_t)stream);
 }
 int i2sdf_planes_wgrad(i2sdf_handle* h, int nterms, const void* const* P, const void* const* X, int x_columns, int64_t M,
                        float* dW, int ld, int rows, int cols, float* colsum, void* stream) {
+    DeviceScope device_scope(h);
     if (!h || !P || !X || !dW || nterms < 1 || nterms > 2 || !planes_chunks(x_columns) || rows > 256 || cols > x_columns) {
         set_error("planes_wgrad: bad argument"); return I2SDF_E_INVALID;
     }

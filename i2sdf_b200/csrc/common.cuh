@@ -72,6 +72,19 @@ namespace i2sdf {
 
 void set_error(const char* fmt, ...);
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting: a process-wide `static bool done` (round 1) left the kernels
+// of a second device in the same process (model.to('cuda:1')) without their shared-memory opt-in.  One flag per device and call site.
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool need() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+        if (done[dev]) return false;
+        done[dev] = true;
+        return true;
+    }
+};
+
 #define I2SDF_CUDA_CHECK(expr)                                                                 \
     do {                                                                                       \
         cudaError_t _e = (expr);                                                               \

@@ -421,12 +421,8 @@ size_t mlp_simt_scratch_floats(const i2sdf_handle* h) {
 }
 
 int launch_mlp_simt(const i2sdf_handle* h, const MlpParams& p, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        I2SDF_CUDA_CHECK(cudaFuncSetAttribute(simt::mlp_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)simt::kSmemBytes));
-        attr_set = true;
-    }
+    static PerDeviceOnce once;
+    if (once.need()) I2SDF_CUDA_CHECK(cudaFuncSetAttribute(simt::mlp_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)simt::kSmemBytes));
     if (p.M <= 0) return I2SDF_OK;
     long long ntiles = (p.M + simt::TM - 1) / simt::TM;
     int grid = (int)(ntiles < (long long)(2 * h->num_sms) ? ntiles : (long long)(2 * h->num_sms));

@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd8_kernel(const BwdParams P,
 #pragma unroll
                     for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(P.ray_o[r * 3 + c], __fmul_rn(t, P.ray_d[r * 3 + c]));
                 }
-                if (P.g_grad) { gb[0] = P.g_grad[m * 3]; gb[1] = P.g_grad[m * 3 + 1]; gb[2] = P.g_grad[m * 3 + 2]; }
+                if (m < P.m_up) { if (P.g_grad) { gb[0] = P.g_grad[m * 3]; gb[1] = P.g_grad[m * 3 + 1]; gb[2] = P.g_grad[m * 3 + 2]; } }
+                else if (P.g_grad_tail) { const float* gt = P.g_grad_tail + (m - P.m_up) * 3; gb[0] = gt[0]; gb[1] = gt[1]; gb[2] = gt[2]; }
             }
         };
         auto gb_of = [&](int coord) -> float { return coord == 0 ? gb[0] : (coord == 1 ? gb[1] : gb[2]); };
@@ -148,9 +149,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd8_kernel(const BwdParams P,
             const bool valid = m < P.M;
             const long long next_tile = tile + gridDim.x;
             // per-point upstream scalars
-            const float sbar = (valid && P.g_sdf) ? P.g_sdf[m] : 0.f;
+            const bool has_up = valid && m < P.m_up;
+            const float sbar = (has_up && P.g_sdf) ? P.g_sdf[m] : 0.f;
             float delta[3] = {0.f, 0.f, 0.f};
-            if (color && valid) {
+            if (color && has_up) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) { const float y = P.s_rgb[m * 3 + c]; delta[c] = P.g_rgb[m * 3 + c] * y * (1.f - y); }
             }
@@ -342,13 +344,8 @@ int tc_bwd_launch(const i2sdf_handle* h, const BwdParams& p, cudaStream_t st) {
     const chain::OpTable* tab = tc_bwd_table(h, p.with_color != 0);
     if (!tab || tab->nops == 0) { set_error("tc_bwd_launch: no backward op table for this network"); return I2SDF_E_INVALID; }
     // (per device: cudaFuncSetAttribute is a per-device setting)
-    static bool attr_done[64] = {};
-    int dev = 0;
-    I2SDF_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-        I2SDF_CUDA_CHECK(cudaFuncSetAttribute(tc_bwd8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBwd8));
-        attr_done[dev] = true;
-    }
+    static PerDeviceOnce once;
+    if (once.need()) I2SDF_CUDA_CHECK(cudaFuncSetAttribute(tc_bwd8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBwd8));
     const long long ntiles = (p.M + chain::TM - 1) / chain::TM;
     const int grid = (int)(ntiles < (long long)h->num_sms ? ntiles : (long long)h->num_sms);
     tc_bwd8_kernel<<<grid, chain::NTHREADS, kSmemBwd8, st>>>(p, *tab);

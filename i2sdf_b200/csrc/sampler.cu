@@ -13,7 +13,7 @@
 // exp of the up-sampling pdf.  pdf = (min(exp(E), 1e6) - 1) T + 1e-6 amplifies a last-bit difference of exp(E) at small E (rays that miss
 // the surface: E ~ 1e-7, exp(E) - 1 is 0 or 1 ulp) into a different inverse-CDF sample set.  torch's CPU exp (Sleef, 1 ulp) agrees with
 // the correctly rounded value for ~99 % of arguments, CUDA's expf (2 ulp) with torch's for ~90 %: that ONE exp is evaluated in double and
-// rounded once.  Measured at 1024 W-sharp rays (profiles/parity_r02.json): z's within 1e-3 of the oracle 0.947 -> 0.985 of all samples
+// rounded once.  Measured at 1024 W-sharp rays (profiles/parity_r02.json): z's within 1e-3 of the CPU reference 0.947 -> 0.985 of all samples
 // (0.776 -> 0.855 within 1e-5).  Doing the same for every exp / expm1 of the beta search costs +0.13 ms per step and changes no output
 // (I2SDF_SAMPLER_EXP64=1 at compile time).
 #ifndef I2SDF_SAMPLER_EXP64
@@ -582,12 +582,11 @@ __global__ void __launch_bounds__(kRayThreads) sampler_round_debug_kernel(Sample
 // host side
 // ------------------------------------------------------------------------------------------------
 static int ensure_smem_attrs() {
-    static bool done = false;
-    if (done) return I2SDF_OK;
+    static PerDeviceOnce once;
+    if (!once.need()) return I2SDF_OK;
     I2SDF_CUDA_CHECK(cudaFuncSetAttribute(sampler_beta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSamplerSmem));
     I2SDF_CUDA_CHECK(cudaFuncSetAttribute(sampler_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSamplerSmem));
     I2SDF_CUDA_CHECK(cudaFuncSetAttribute(sampler_round_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSamplerSmem));
-    done = true;
     return I2SDF_OK;
 }
 

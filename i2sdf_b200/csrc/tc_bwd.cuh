@@ -22,8 +22,12 @@ struct BwdParams {
     long long M;
     long long m_rays;      // as MlpParams: both sources given -> first m_rays points from the rays, the rest from pts
     // upstream gradients per point (null = 0)
-    const float* g_sdf;    // [M]
-    const float* g_grad;   // [M][3]   upstream of grad_x sdf
+    // the upstream arrays cover the first m_up points (m_up = M unless the caller appended points behind its ray samples); points
+    // m >= m_up have no sdf / rgb upstream and take the upstream of grad_x sdf from g_grad_tail[m - m_up]
+    long long m_up;
+    const float* g_grad_tail;   // [M - m_up][3] or null
+    const float* g_sdf;    // [m_up]
+    const float* g_grad;   // [m_up][3]   upstream of grad_x sdf
     const float* g_rgb;    // [M][3]   (with_color)
     const float* s_rgb;    // [M][3]   forward rgb (sigmoid output), for its derivative
     int with_color;

@@ -458,11 +458,10 @@ int tc_gemm_pw(const i2sdf_handle* h, cudaStream_t st, long long M, const float*
 int tc_gemm_pw_ex(const i2sdf_handle* h, cudaStream_t st, long long M, const float* A, int lda, int kvalid, const TcBlock& blk, float* C, int ldc,
                   int ncols, const float* bias, int relu, const float* A2, int lda2, int is_skip, int nsplit, const float* E2) {
     using namespace tcg;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce once;
+    if (once.need()) {
         I2SDF_CUDA_CHECK(cudaFuncSetAttribute(gemm_pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPW));
         I2SDF_CUDA_CHECK(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemWG));
-        attr = true;
     }
     if (M <= 0) return I2SDF_OK;
     if (!blk.ptr || blk.ksteps * 16 > A_CHUNKS * 8 || blk.n > 256) { set_error("tc_gemm_pw: bad weight block"); return I2SDF_E_INVALID; }
@@ -491,11 +490,10 @@ int tc_gemm_wgrad_ex(const i2sdf_handle* h, cudaStream_t st, long long M, const 
                      int ldp1, const float* X1, int ldx1, int n1, int n2, float* dW, int ldw, float* ws, const float* Aprev, const float* Adprev,
                      int is_skip, int nsplit, const float* E0, const float* E1) {
     using namespace tcg;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce once;
+    if (once.need()) {
         I2SDF_CUDA_CHECK(cudaFuncSetAttribute(gemm_pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPW));
         I2SDF_CUDA_CHECK(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemWG));
-        attr = true;
     }
     if (M <= 0) return I2SDF_OK;
     if (n1 > 256 || n2 > 256 || n1 < 1 || n2 < 1) { set_error("tc_gemm_wgrad: n1/n2 out of range"); return I2SDF_E_INVALID; }

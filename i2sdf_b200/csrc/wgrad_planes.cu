@@ -276,7 +276,9 @@ __global__ void __launch_bounds__(256) planes_colsum_kernel(const CsArgs A) {
             float w[3] = {1.f, 0.f, 0.f};
             if (J.w) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) w[k] = (k < nw && m < A.M) ? J.w[(size_t)m * J.wstride + k] : 0.f;
+                const long long wlim = (J.wrows > 0 && J.wrows < A.M) ? J.wrows : A.M;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) w[k] = (k < nw && m < wlim) ? J.w[(size_t)m * J.wstride + k] : 0.f;
             }
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
@@ -320,11 +322,8 @@ __global__ void __launch_bounds__(256) planes_colsum_kernel(const CsArgs A) {
 int wgrad_planes_launch(const i2sdf_handle* h, const WgArgs& args, cudaStream_t st) {
     using namespace wgp;
     if (args.nterms <= 0 || args.ntiles <= 0) return I2SDF_OK;
-    static bool attr_done = false;
-    if (!attr_done) {
-        I2SDF_CUDA_CHECK(cudaFuncSetAttribute(wgrad_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        attr_done = true;
-    }
+    static PerDeviceOnce once;
+    if (once.need()) I2SDF_CUDA_CHECK(cudaFuncSetAttribute(wgrad_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     WgArgs a = args;
     const char* v = getenv("I2SDF_WG_VARIANT");
     a.variant = (v && v[0] == '1') ? 1 : 0;

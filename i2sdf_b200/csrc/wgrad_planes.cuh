@@ -39,6 +39,7 @@ struct CsJob {
     int nw;                // weight vectors sharing ONE pass over the slot (1..3; w null: 1 = plain column sums)
     int ostride;
     int nplanes;           // planes of the slot (0 is read as 2)
+    long long wrows;       // rows the weight array w covers (0: all M); points beyond it carry weight 0
 };
 struct CsArgs {
     long long ntiles, M;

@@ -277,6 +277,15 @@ int i2sdf_fused_backward(i2sdf_handle* h, const float* pts, const float* o, cons
                          const float* g_rgb, float* const* dW_sdf, float* const* db_sdf, float* const* dW_col,
                          float* const* db_col, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same when the caller appended explicit points behind its ray samples (i2sdf_points_forward_ex: the eikonal / smoothness points of
+ * model/network/__init__.py:175-193 ride the main-pass launches): the upstream arrays g_sdf / g_grad / g_rgb cover only the first m_up
+ * points (the ray samples), points m >= m_up have no sdf / rgb upstream and take the upstream of grad_x sdf from g_grad_tail [M - m_up, 3]
+ * (NULL = 0).  Saves the caller three concatenations with zero blocks per training step. */
+int i2sdf_fused_backward_ex(i2sdf_handle* h, const float* pts, const float* o, const float* d, const float* z, int zstride,
+                            int ns, int64_t M, int64_t m_rays, void* saved, const float* s_rgb, const float* g_sdf, const float* g_grad,
+                            const float* g_rgb, int64_t m_up, const float* g_grad_tail, float* const* dW_sdf, float* const* db_sdf,
+                            float* const* dW_col, float* const* db_col, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Plane slots: the HBM format of the fused training path (bf16 hi + lo planes per 128-point tile in the tensor
  * cores' SMEM layout, i2sdf_b200/csrc/planes.cuh).  pack / unpack convert from / to plain fp32 [M][ld] arrays
  * (columns = 256 or 48); planes_wgrad is the weight-gradient kernel on its own:

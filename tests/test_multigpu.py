@@ -172,3 +172,30 @@ def test_sharded_training_step_equals_whole_batch_gradients():
     assert tag == "train"
     assert abs(loss_sharded - loss_whole) < 1e-5 * abs(loss_whole)
     assert e_flat < 1e-4 and worst < 1e-3
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_module_on_second_device_while_first_is_current():
+    """Advisor finding r01: the shared-memory opt-ins were process-wide flags and the ABI trusted the caller's current device.  A module on
+    cuda:1 must run there - eval and one training step - while cuda:0 is the current device, and give cuda:0's result bit for bit."""
+    from i2sdf_b200 import configs
+    from i2sdf_b200.network import I2SDFLoss
+    from i2sdf_b200.synthetic import make_train_gt, synthetic_rays
+    torch.cuda.set_device(0)
+    inp = synthetic_rays(200, seed=2)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        m = _build(0.05).to(dev).eval()
+        out = m({k: v.to(dev) for k, v in inp.items()})
+        assert torch.cuda.current_device() == 0 and out["rgb_values"].device == torch.device(dev)
+        outs.append({k: v.cpu() for k, v in out.items()})
+    assert all(torch.equal(outs[0][k], outs[1][k]) for k in outs[0])
+    m = _build(0.05)
+    m.use_normal = True
+    m = m.to("cuda:1").train()
+    tin = {k: v.to("cuda:1") for k, v in synthetic_rays(64, seed=3, train_layout=True).items()}
+    gt = {k: v.to("cuda:1") for k, v in make_train_gt(64, 4).items()}
+    loss = I2SDFLoss(**configs.LOSS_SYNTHETIC)(m(tin), gt, 0)["loss"]
+    loss.backward()
+    assert torch.isfinite(loss) and all(p.grad is not None and p.grad.device == torch.device("cuda:1") and bool(torch.isfinite(p.grad).all()) for p in m.parameters())
+    assert torch.cuda.current_device() == 0
