@@ -95,6 +95,10 @@ def parse():
                     help="synthetic (default, BASELINE.json configs[1]/[2]) or synthetic_light_mask (configs[3]: 6x256 SDF, 3x256 "
                          "radiance, light-mask head, light_mask_weight 0.5)")
     ap.add_argument("--cpu-rays", type=int, default=0, help="rays per step of the CPU arms (0 = --rays: the same config as the GPU arm)")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="training: also time the step replayed as ONE CUDA graph (i2sdf_b200.graph.GraphedTrainStep).  auto (default): only for the "
+                         "strong-scaling block of a multi-GPU run (1024 / N rays per GPU: issued from Python that step is host-bound); on: for the weak "
+                         "block as well; off: never.  Where both ran the faster one is the block's value, the other is reported beside it")
     ap.add_argument("--bubble", type=int, default=0, help="training variant of steps 50k-150k (config/synthetic.yml:22-23): N bubble points per "
                                                           "step through the SDF (bubble_weight 0.5) and the smoothness term switched on")
     ap.add_argument("--grid-res", type=int, default=256, help="--mode grid: resolution of the uniform SDF grid (reference meshes use 100 .. 512)")
@@ -343,7 +347,7 @@ def gpu_arm(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def measure(R, first_ray, global_rays):
+    def measure(R, first_ray, global_rays, use_graph=False):
         """K timed steps on this rank's R rays [first_ray, first_ray + R) of a global batch: device-resident and end-to-end."""
         # the global batch is generated identically on every rank, each rank keeps its shard
         full = synthetic_rays(global_rays, seed=1, train_layout=train)
@@ -386,16 +390,20 @@ def gpu_arm(args, rank, world, local_rank):
                 out_host[k].copy_(v, non_blocking=True)
             return out
 
+        host = {}
+
         def timed(fn, steps, profile=False):
             ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
             barrier()
             if profile:
                 core.profile(True)
+            h0 = time.perf_counter()
             for a, b in ev:
                 flush.zero_()                      # L2 flush between timed iterations (outside the event pair)
                 a.record()
                 fn()
                 b.record()
+            host["enqueue_ms"] = (time.perf_counter() - h0) * 1e3 / steps       # host time to ENQUEUE a step (no device wait except the sampler's round count)
             barrier()
             prof = core.profile_read() if profile else None
             if profile:
@@ -410,11 +418,46 @@ def gpu_arm(args, rank, world, local_rank):
             step_e2e()
         core.rounds_log.clear()
         ms_res, prof = timed(step_resident, args.steps, profile=True)
+        host_ms = host.get("enqueue_ms")
         rounds = list(core.rounds_log)
         ms_e2e, _ = timed(step_e2e, args.steps)
         h2d = sum(v.numel() * v.element_size() for v in list(inp_host.values()) + list(gt_host.values()))
         d2h = 4 if train else sum(v.numel() * v.element_size() for v in out_host.values())
-        return dict(ms_res=ms_res, ms_e2e=ms_e2e, prof=prof, rounds=rounds, h2d=h2d, d2h=d2h)
+        ms_ar = None
+        if train and world > 1:          # the gradient all-reduce on its own: the bucket, back to back, device time
+            ar = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+            barrier()
+            for a, b in ar:
+                a.record()
+                dist.all_reduce(bucket.flat, op=dist.ReduceOp.AVG)
+                b.record()
+            barrier()
+            ms_ar = sorted(a.elapsed_time(b) for a, b in ar)[len(ar) // 2]
+        res = dict(ms_res=ms_res, ms_e2e=ms_e2e, prof=prof, rounds=rounds, h2d=h2d, d2h=d2h, host_ms=host_ms, ms_ar=ms_ar, graph=None)
+        if train and use_graph:
+            # the same step as ONE CUDA graph (forward + loss + backward + all-reduce + Adam + re-pack captured once, replayed per step)
+            from i2sdf_b200.graph import GraphedTrainStep
+            gstep = GraphedTrainStep(model_gpu, loss_fn, opt, inp_dev, gt_dev, current_step=loss_step, bucket=bucket, warmup=2)
+
+            def g_resident():
+                return gstep(inp_dev, gt_dev)
+
+            def g_e2e():
+                loss = gstep(inp_host, gt_host)          # pinned host batches: the H2D copies into the graph's static inputs are part of the step
+                loss_host.copy_(loss.detach(), non_blocking=True)
+                return loss
+            for _ in range(max(args.warmup, 3)):
+                g_resident()
+                g_e2e()
+            core.rounds_log.clear()
+            g_ms, _ = timed(g_resident, args.steps)
+            g_host = host.get("enqueue_ms")
+            g_rounds = list(core.rounds_log)
+            g_ms_e2e, _ = timed(g_e2e, args.steps)
+            gstep.finish()
+            res["graph"] = dict(ms_res=g_ms, ms_e2e=g_ms_e2e, host_ms=g_host, rounds=g_rounds)
+            del gstep
+        return res
 
     def reduce_max(*vals):
         t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
@@ -425,13 +468,13 @@ def gpu_arm(args, rank, world, local_rank):
     R = args.rays
     clk = ClockSampler(local_rank)
     clk.start()
-    weak = measure(R, rank * R, world * R)              # weak scaling: R rays per rank, a global batch of world * R
+    weak = measure(R, rank * R, world * R, use_graph=(args.graph == "on"))      # weak scaling: R rays per rank, a global batch of world * R
     clocks = clk.stop()
     strong = None
     if world > 1:                                       # strong scaling: ONE R-ray batch split over the ranks
         from i2sdf_b200.parallel import shard_bounds
         lo, hi = shard_bounds(R, rank, world)
-        strong = measure(hi - lo, lo, R)
+        strong = measure(hi - lo, lo, R, use_graph=(args.graph != "off"))
     ms_render = 0.0
     if train:       # also report the forward-render throughput of the same networks (inference: no collective)
         model_gpu.load_state_dict(init_state)          # back to the W-sharp weights (Adam steps changed beta / the surface)
@@ -452,9 +495,33 @@ def gpu_arm(args, rank, world, local_rank):
         model_gpu.train(True)
     vals = reduce_max(weak["ms_res"], weak["ms_e2e"], ms_render, strong["ms_res"] if strong else 0.0, strong["ms_e2e"] if strong else 0.0)
     ms_res, ms_e2e, ms_render, ms_strong, ms_strong_e2e = vals
+    gw, gs = weak.get("graph"), (strong.get("graph") if strong else None)
+    gvals = reduce_max(gw["ms_res"] if gw else 0.0, gw["ms_e2e"] if gw else 0.0, gs["ms_res"] if gs else 0.0, gs["ms_e2e"] if gs else 0.0)
     if rank != 0:
         return None, None
     K = args.steps
+    # where a block ran both ways (every rank did: the flags are the same everywhere) the faster one is its value, the other is kept beside it
+    step_api = "eager"
+    other = None
+    if gw:
+        e = {"api": "eager", "ms_per_step": ms_res / K, "e2e_ms_per_step": ms_e2e / K, "host_enqueue_ms_per_step": weak["host_ms"]}
+        gr = {"api": "graph", "ms_per_step": gvals[0] / K, "e2e_ms_per_step": gvals[1] / K, "host_enqueue_ms_per_step": gw["host_ms"]}
+        if gvals[0] < ms_res:
+            step_api, other = "graph", e
+            ms_res, ms_e2e = gvals[0], gvals[1]
+            weak = dict(weak, host_ms=gw["host_ms"], rounds=gw["rounds"] or weak["rounds"])
+        else:
+            other = gr
+    strong_api, strong_other = "eager", None
+    if gs:
+        e = {"api": "eager", "ms_per_step": ms_strong / K, "e2e_ms_per_step": ms_strong_e2e / K, "host_enqueue_ms_per_step": strong["host_ms"]}
+        gr = {"api": "graph", "ms_per_step": gvals[2] / K, "e2e_ms_per_step": gvals[3] / K, "host_enqueue_ms_per_step": gs["host_ms"]}
+        if gvals[2] < ms_strong:
+            strong_api, strong_other = "graph", e
+            ms_strong, ms_strong_e2e = gvals[2], gvals[3]
+            strong = dict(strong, host_ms=gs["host_ms"])
+        else:
+            strong_other = gr
     prof = weak["prof"]
     value = world * R * N_COMPOSITED * K / (ms_res * 1e-3)
     e2e_value = world * R * N_COMPOSITED * K / (ms_e2e * 1e-3)
@@ -509,7 +576,10 @@ def gpu_arm(args, rank, world, local_rank):
                    "parallelism": f"ray-sharded x{world}, " + ("one flat gradient all-reduce per step (persistent bucket, in place)" if train else "no collective (inference)"),
                    "tensor_cores": {"sampler_sdf": core.uses_tensor_cores, "main_pass": core.uses_tensor_cores_main,
                                     "backward": bool(train and core.fused_main)},
-                   "l2": "flushed between timed iterations (256 MB write)", "timing": "CUDA events per step, max over ranks"},
+                   "l2": "flushed between timed iterations (256 MB write)", "timing": "CUDA events per step, max over ranks",
+                   "step_api": ("i2sdf_b200.graph.GraphedTrainStep: the whole step captured once as a CUDA graph and replayed (one launch per step); "
+                                "`kernel_ms_per_step` is taken from the eager run (identical kernels)") if step_api == "graph" else
+                               ("I2SDFNetwork.forward (+ I2SDFLoss, backward, GradBucket.allreduce, optim.Adam.step) issued from Python" if train else "I2SDFNetwork.forward (eval)")},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": weak["h2d"], "d2h_bytes_per_step": weak["d2h"]},
         "gpu_launches": launches,
         "kernel_ms_per_step": {k: v["ms"] / K for k, v in prof.items()},
@@ -527,7 +597,14 @@ def gpu_arm(args, rank, world, local_rank):
                           "formula": ("rounds*128*R*sdf_eval + 97*R*(ray_sample + ray_sample_bwd) + 3*R*(eik_fwd + eik_bwd)" if train
                                       else "rounds*128*R*sdf_eval + 97*R*ray_sample")},
         "clocks": clocks,
+        "host_enqueue_ms_per_step": weak["host_ms"],
     }
+    if other:
+        line["other_step_api"] = other
+    if weak["ms_ar"] is not None:
+        line["allreduce"] = {"bytes": int(bucket.flat.numel() * 4), "median_ms_alone": weak["ms_ar"],
+                             "note": "one NCCL AVG all-reduce of the persistent flat gradient bucket, timed back to back outside the step; inside the step the ranks "
+                                     "also wait for the slowest one (the timed value is the max over ranks of every step)"}
     if strong is not None:
         sv = R * N_COMPOSITED * K / (ms_strong * 1e-3)
         line["strong_scaling"] = {
@@ -536,9 +613,12 @@ def gpu_arm(args, rank, world, local_rank):
             "workload": "SURVEY.md C5: ONE 1024-ray batch split over the ranks (same weights / rays / targets as N = 1), plain sharding "
                         "(per-shard sampler convergence and loss means; the strict-parity switches add 5 + 1 tiny all-reduces per step)",
             "kernel_ms_per_step": {k: v["ms"] / K for k, v in strong["prof"].items()},
-            "limiter": "at 1024 / N rays per GPU a launch covers N x fewer 128-point tiles than the GPU has SMs (128 rays x 128 points = 128 tiles on "
-                       "148 SMs), so every kernel runs ONE partial wave whatever N is: step time is bounded below by the step's ~60 dependent launches "
-                       "and single-tile chain latencies, not by throughput",
+            "host_enqueue_ms_per_step": strong["host_ms"],
+            "step_api": strong_api, "other_step_api": strong_other,
+            "limiter": "issued from Python (`eager`) the step is host-bound: the kernels of a 1024 / N-ray shard need sum(kernel_ms_per_step) of device "
+                       "time, Python needs ~2.7 ms to issue the step's ~60 launches; replayed as a CUDA graph the host is out of the step and what remains is "
+                       "launch-to-launch latency of ~60 dependent kernels that each fill at most one partial wave (128 rays x 128 points = 128 tiles on 148 "
+                       "SMs at N = 8) plus the all-reduce",
         }
     if train and core.fused_main and prof["weight_grads"]["launches"] > 0 and not light:
         # the two other heavy kernels of the training step, both bounded by HBM: algorithmic bytes = plane slots read / written

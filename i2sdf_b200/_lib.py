@@ -98,6 +98,7 @@ SYMBOLS = {
     "i2sdf_loss_forward": (C.c_int, [C.POINTER(LossArgs), _P]),
     "i2sdf_weight_norm": (C.c_int, [C.POINTER(WnormBatch), C.c_int, _P]),
     "i2sdf_adam_step": (C.c_int, [C.POINTER(AdamBatch), _P]),
+    "i2sdf_adam_step_dev": (C.c_int, [C.POINTER(AdamBatch), _P, _P]),
     "i2sdf_planes_slot_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
     "i2sdf_planes_pack": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int64, C.c_int, _P, _P]),
     "i2sdf_planes_unpack": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, C.c_int, C.c_int, _P]),

@@ -259,6 +259,11 @@ class RenderCore:
             if getattr(self, "_info_host", None) is None:
                 self._info_host = torch.zeros(2, dtype=torch.int32).pin_memory()
             self._info_host.copy_(info, non_blocking=True)
+            if torch.cuda.is_current_stream_capturing():
+                # CUDA-graph capture (i2sdf_b200/graph.py): the candidate upload and the round-count read-back above are graph nodes on
+                # the two pinned buffers; the host side (drawing the candidates, replaying the generator) is graph_pre_replay / graph_resolve
+                self._graph_ep = ep
+                return (z, z_eik, info) if want_info else (z, z_eik)
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.device))
             self._pending = (state, ep, ev)
@@ -282,6 +287,8 @@ class RenderCore:
 
     def sampler_resolve(self):
         """Second half of sample(defer_sync=True): wait for the round count and replay the host generator draw that applied."""
+        if torch.cuda.is_current_stream_capturing():
+            return
         pend = getattr(self, "_pending", None)
         if pend is None:
             return
@@ -291,6 +298,33 @@ class RenderCore:
         torch.set_rng_state(state)
         ep(int(self._info_host[1]))
         self.rounds_log.append(int(self._info_host[0]))          # sampler rounds of that forward (bench.py reports them)
+        del self.rounds_log[:-256]
+
+    def graph_pre_replay(self):
+        """Host half of a captured training forward, before the replay: draw this step's extra-sample candidates (one per possible
+        round count, all from the same generator state, ray_sampler.py:223) into the pinned table the graph uploads."""
+        ep = getattr(self, "_graph_ep", None)
+        if ep is None:
+            return
+        state = torch.get_rng_state()
+        cands = []
+        for k in range(self.desc.max_total_iters):
+            torch.set_rng_state(state)
+            cands.append(ep(self.desc.n_samples_eval * (k + 1)).to(torch.int32))
+        torch.set_rng_state(state)
+        torch.stack(cands, out=self._cand_host)
+        self._graph_state = state
+
+    def graph_resolve(self):
+        """... and after the replay has finished (the caller synchronised): replay the ONE draw that applied, so that the host generator
+        ends where the reference's would (the round count sits in the pinned info buffer)."""
+        state = getattr(self, "_graph_state", None)
+        if state is None:
+            return
+        self._graph_state = None
+        torch.set_rng_state(state)
+        self._graph_ep(int(self._info_host[1]))
+        self.rounds_log.append(int(self._info_host[0]))
         del self.rounds_log[:-256]
 
     def sampler_round_debug(self, z, sdf, beta_param, beta_in, upsample: bool, u_tape=None):

@@ -9,16 +9,19 @@
 namespace i2sdf {
 namespace adamk {
 
-__global__ void __launch_bounds__(256) adam_kernel(const i2sdf_adam_batch B) {
+// scalars (optional, device): {step_size, bias_correction2_sqrt} of THIS step, read at run time instead of the values baked into the
+// launch - what a CUDA-graph replay needs (the host refreshes them through a captured pinned-memory copy, i2sdf_b200/graph.py)
+__global__ void __launch_bounds__(256) adam_kernel(const i2sdf_adam_batch B, const float* __restrict__ scalars) {
     const i2sdf_adam_job& J = B.jobs[blockIdx.y];
     const float one_m_b1 = B.one_minus_beta1, one_m_b2 = B.one_minus_beta2;      // formed in double on the host, as ATen does
+    const float step_size = scalars ? scalars[0] : B.step_size, bc2 = scalars ? scalars[1] : B.bias_correction2_sqrt;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < J.numel; i += (long long)gridDim.x * blockDim.x) {
         const float g = J.grad[i];
         float m = J.exp_avg[i], v = J.exp_avg_sq[i];
         m = fmaf(one_m_b1, g - m, m);                              // lerp(m, g, 1 - beta1)
         v = B.beta2 * v + one_m_b2 * g * g;
-        const float denom = __fdiv_rn(sqrtf(v), B.bias_correction2_sqrt) + B.eps;
-        J.param[i] = J.param[i] - B.step_size * __fdiv_rn(m, denom);
+        const float denom = __fdiv_rn(sqrtf(v), bc2) + B.eps;
+        J.param[i] = J.param[i] - step_size * __fdiv_rn(m, denom);
         J.exp_avg[i] = m;
         J.exp_avg_sq[i] = v;
     }
@@ -27,7 +30,9 @@ __global__ void __launch_bounds__(256) adam_kernel(const i2sdf_adam_batch B) {
 }  // namespace adamk
 }  // namespace i2sdf
 
-extern "C" int i2sdf_adam_step(const i2sdf_adam_batch* b, void* stream) {
+extern "C" int i2sdf_adam_step_dev(const i2sdf_adam_batch* b, const float* scalars_dev, void* stream);
+extern "C" int i2sdf_adam_step(const i2sdf_adam_batch* b, void* stream) { return i2sdf_adam_step_dev(b, nullptr, stream); }
+extern "C" int i2sdf_adam_step_dev(const i2sdf_adam_batch* b, const float* scalars_dev, void* stream) {
     using namespace i2sdf;
     if (!b || b->n < 1 || b->n > I2SDF_ADAM_MAX_JOBS) { set_error("adam_step: bad job count"); return I2SDF_E_INVALID; }
     long long most = 0;
@@ -38,7 +43,7 @@ extern "C" int i2sdf_adam_step(const i2sdf_adam_batch* b, void* stream) {
     }
     int gx = (int)((most + 1023) / 1024);
     if (gx > 128) gx = 128;
-    adamk::adam_kernel<<<dim3(gx, b->n), 256, 0, (cudaStream_t)stream>>>(*b);
+    adamk::adam_kernel<<<dim3(gx, b->n), 256, 0, (cudaStream_t)stream>>>(*b, scalars_dev);
     I2SDF_CUDA_CHECK(cudaGetLastError());
     return I2SDF_OK;
 }

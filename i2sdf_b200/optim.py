@@ -24,6 +24,8 @@ class Adam(torch.optim.Optimizer):
             raise ValueError("invalid Adam hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=0.0, amsgrad=False, maximize=False))
         self._fresh_steps = {}
+        self._batches = {}
+        self._graph_scalars = {}
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -34,6 +36,10 @@ class Adam(torch.optim.Optimizer):
         lib = _lib.load()
         if not hasattr(self, "_fresh_steps"):
             self._fresh_steps = {}
+        if not hasattr(self, "_batches"):
+            self._batches = {}
+        if not hasattr(self, "_graph_scalars"):
+            self._graph_scalars = {}
         for group in self.param_groups:
             ps = [p for p in group["params"] if p.grad is not None]
             if not ps:
@@ -67,20 +73,61 @@ class Adam(torch.optim.Optimizer):
                 stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
                 for t, plist in by_step.items():
                     grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in plist]
-                    for lo in range(0, len(plist), _lib.ADAM_MAX_JOBS):
-                        b = _lib.AdamBatch()
-                        chunk = plist[lo:lo + _lib.ADAM_MAX_JOBS]
-                        b.n, b.beta1, b.beta2, b.eps = len(chunk), beta1, beta2, group["eps"]
+                    # the job tables (pointers of parameter / gradient / moments) are rebuilt only when a pointer changed: with
+                    # parallel.GradBucket every pointer is stable from step to step and a step costs two float stores per table
+                    key = (id(group), tuple(p.data_ptr() for p in plist), tuple(g.data_ptr() for g in grads),
+                           tuple(self.state[p]["exp_avg"].data_ptr() for p in plist), tuple(self.state[p]["exp_avg_sq"].data_ptr() for p in plist))
+                    cached = self._batches.get(id(group))
+                    if cached is None or cached[0] != key:
+                        batches = []
+                        for lo in range(0, len(plist), _lib.ADAM_MAX_JOBS):
+                            b = _lib.AdamBatch()
+                            chunk = plist[lo:lo + _lib.ADAM_MAX_JOBS]
+                            b.n = len(chunk)
+                            for i, p in enumerate(chunk):
+                                st, j = self.state[p], b.jobs[i]
+                                j.param, j.grad, j.numel = p.data_ptr(), grads[lo + i].data_ptr(), p.numel()
+                                j.exp_avg, j.exp_avg_sq = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
+                            batches.append(b)
+                        cached = (key, batches)
+                        if len(by_step) == 1:
+                            self._batches[id(group)] = cached
+                    capturing = torch.cuda.is_current_stream_capturing()
+                    scal = None
+                    if capturing:
+                        # CUDA-graph capture (i2sdf_b200/graph.py): the step's two scalars come from device memory, refreshed on every replay by
+                        # a captured copy from a pinned host buffer that prepare_replay() fills
+                        gi = self.param_groups.index(group)
+                        if gi not in self._graph_scalars:
+                            self._graph_scalars[gi] = (torch.zeros(2, dtype=torch.float32).pin_memory(), torch.zeros(2, dtype=torch.float32, device=dev), plist[0])
+                        host, scal, _ = self._graph_scalars[gi]
+                        host[0], host[1] = group["lr"] / (1.0 - beta1 ** t), math.sqrt(1.0 - beta2 ** t)
+                        scal.copy_(host, non_blocking=True)
+                    for b in cached[1]:
+                        b.beta1, b.beta2, b.eps = beta1, beta2, group["eps"]
                         b.one_minus_beta1, b.one_minus_beta2 = 1.0 - beta1, 1.0 - beta2
                         b.step_size = group["lr"] / (1.0 - beta1 ** t)
                         b.bias_correction2_sqrt = math.sqrt(1.0 - beta2 ** t)
-                        for i, p in enumerate(chunk):
-                            st, j = self.state[p], b.jobs[i]
-                            j.param, j.grad, j.numel = p.data_ptr(), grads[lo + i].data_ptr(), p.numel()
-                            j.exp_avg, j.exp_avg_sq = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
-                        _lib.check(lib.i2sdf_adam_step(C.byref(b), stream), "i2sdf_adam_step")
+                        if scal is not None:
+                            _lib.check(lib.i2sdf_adam_step_dev(C.byref(b), C.c_void_p(scal.data_ptr()), stream), "i2sdf_adam_step_dev")
+                        else:
+                            _lib.check(lib.i2sdf_adam_step(C.byref(b), stream), "i2sdf_adam_step")
                     del grads
         return loss
+
+    def prepare_replay(self):
+        """Before replaying a CUDA graph that captured step(): advance the step counters and refresh the scalars the captured kernels read."""
+        for gi, (host, _, p0) in self._graph_scalars.items():
+            group = self.param_groups[gi]
+            beta1, beta2 = group["betas"]
+            seen = set()
+            for p in group["params"]:
+                st = self.state.get(p)
+                if st and id(st["step"]) not in seen:
+                    seen.add(id(st["step"]))
+                    st["step"] += 1
+            t = float(self.state[p0]["step"])
+            host[0], host[1] = group["lr"] / (1.0 - beta1 ** t), math.sqrt(1.0 - beta2 ** t)
 
     def state_dict(self):
         """torch.optim.Adam's layout with ONE step tensor PER PARAMETER: inside this optimizer the parameters of a group share a

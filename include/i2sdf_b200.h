@@ -389,6 +389,9 @@ typedef struct i2sdf_adam_batch {
     i2sdf_adam_job jobs[I2SDF_ADAM_MAX_JOBS];
 } i2sdf_adam_batch;
 int i2sdf_adam_step(const i2sdf_adam_batch* batch, void* stream);
+/* The same with the two per-step scalars {step_size, bias_correction2_sqrt} read from device memory at run time (scalars_dev [2];
+ * NULL: the values in the batch): a launch captured into a CUDA graph stays valid from step to step. */
+int i2sdf_adam_step_dev(const i2sdf_adam_batch* batch, const float* scalars_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -205,3 +205,71 @@ def test_ray_feed_and_bubble_pdf_on_the_device():
     assert pts.is_cuda and pts.shape == (16, 3)
     picked = torch.where(bg.sample_count > 0)[0]
     assert picked.numel() == 16 and bool((bg.pdf[picked] > 0).all())
+
+
+def test_graphed_training_step_equals_eager_steps():
+    """i2sdf_b200.graph.GraphedTrainStep: the whole step as one CUDA graph.  With every random draw pinned by a tape the replayed steps
+    must move the parameters exactly as eager steps do (weight-gradient atomics aside), Adam's bias correction must advance per replay,
+    and with free-running randomness the replay must keep training (finite loss, loss going down on a fixed batch)."""
+    from i2sdf_b200 import configs
+    from i2sdf_b200.graph import GraphedTrainStep
+    from i2sdf_b200.network import I2SDFLoss
+    from i2sdf_b200.optim import Adam
+    c = Case("train_synthetic")
+    R = 256
+    inp = {k: v.cuda() for k, v in synthetic_rays(R, seed=5, train_layout=True).items()}
+    gt = {k: v.cuda() for k, v in make_train_gt(R, 9).items()}
+    g = torch.Generator().manual_seed(6)
+    tape = {"jitter": torch.rand(R, 128, generator=g), "u_final": torch.rand(R, 64, generator=g), "extra_perm": torch.randperm(128, generator=g)[:32],
+            "eik_idx": torch.randint(98, (R,), generator=g), "eik_uniform": (torch.rand(R, 3, generator=g) - 0.5) * 6,
+            "nbr_uniform": (torch.rand(R, 3, generator=g) - 0.5) * 0.01}
+    tape = {k: v.cuda() for k, v in tape.items()}              # (a capture cannot copy from pageable host memory)
+
+    def run(graphed, n):
+        m = _model(c, training=True)
+        m._tape_override = dict(tape)
+        loss_fn = I2SDFLoss(**configs.LOSS_SYNTHETIC)
+        opt = Adam(m.parameters(), lr=1e-3, eps=1e-15)
+        losses = []
+        if graphed:
+            step = GraphedTrainStep(m, loss_fn, opt, inp, gt, warmup=1)
+            state0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+            return m, opt, step, state0
+        for _ in range(n):
+            loss = loss_fn(m(inp), gt, 0)["loss"]
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            losses.append(float(loss))
+        return m, losses
+
+    # graphed: construction runs 1 warm-up step (eager) and captures; then 3 replays = 4 updates in total
+    mg, opt_g, step, _ = run(True, 0)
+    lg = [float(step(inp, gt)) for _ in range(3)]
+    step.finish()
+    me, le = run(False, 4)
+    assert all(torch.isfinite(torch.tensor(lg)))
+    for a, b in zip(lg, le[1:]):
+        assert abs(a - b) < 2e-5 * abs(b), (lg, le)
+    # Parameters: Adam(eps=1e-15) moves every entry by ~lr per step whatever the size of its gradient, so entries whose gradient is
+    # rounding noise (the embedding columns the geometric init zeroes) follow the order of the weight-gradient atomics - in two eager
+    # runs as well.  Bounded by what sign flips can do (2 lr per update), and the bulk must agree far better than that.
+    lr, n_up = 1e-3, 4
+    worst, mean = 0.0, 0.0
+    for (n1, p1), (_, p2) in zip(mg.named_parameters(), me.named_parameters()):
+        d = (p1 - p2).abs()
+        worst, mean = max(worst, float(d.max())), max(mean, float(d.mean()))
+    print(f"graphed vs eager after 4 Adam updates: losses {lg} vs {le[1:]}; parameter differences: worst {worst:.2e}, worst tensor mean {mean:.2e} (lr {lr})")
+    assert worst <= 2.0 * lr * n_up * 1.01 and mean < 0.1 * lr * n_up
+    assert float(next(iter(opt_g.state.values()))["step"]) == 4.0
+    # free-running randomness (no tape): keeps training on a fixed batch
+    m2 = _model(c, training=True)
+    loss_fn = I2SDFLoss(**configs.LOSS_SYNTHETIC)
+    opt2 = Adam(m2.parameters(), lr=1e-3, eps=1e-15)
+    torch.manual_seed(3)
+    step2 = GraphedTrainStep(m2, loss_fn, opt2, inp, gt)
+    hist = [float(step2(inp, gt)) for _ in range(12)]
+    step2.finish()
+    assert all(h == h and abs(h) < 1e3 for h in hist) and min(hist[-4:]) < hist[0], hist
+    out = m2.eval()({k: v.cuda() for k, v in synthetic_rays(64, seed=1).items()})        # the packed weights follow the replayed updates
+    assert bool(torch.isfinite(out["rgb_values"]).all())

@@ -3,7 +3,7 @@ import cProfile, pstats, io, os, sys, time, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from i2sdf_b200 import configs
 from i2sdf_b200.network import I2SDFNetwork, I2SDFLoss
-from oracle import i2sdf_oracle as orc
+from i2sdf_b200 import synthetic as orc   # (neutral input generator: perf tools do not touch oracle/)
 import bench
 conf = configs.model_conf("synthetic"); conf["use_normal"] = True
 torch.manual_seed(0)

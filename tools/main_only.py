@@ -3,7 +3,7 @@ import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from i2sdf_b200 import configs
 from i2sdf_b200.network import I2SDFNetwork
-from oracle import i2sdf_oracle as orc
+from i2sdf_b200 import synthetic as orc   # (neutral input generator: perf tools do not touch oracle/)
 torch.manual_seed(0)
 m = I2SDFNetwork(configs.model_conf("synthetic"))
 with torch.no_grad():

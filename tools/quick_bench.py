@@ -8,7 +8,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from i2sdf_b200 import configs          # noqa: E402
 from i2sdf_b200.network import I2SDFNetwork  # noqa: E402
-from oracle import i2sdf_oracle as orc  # noqa: E402
+from i2sdf_b200 import synthetic as orc  # noqa: E402   # (neutral input generator: perf tools do not touch oracle/)
 
 
 def timeit(fn, warm=3, it=10):

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from torch.profiler import profile, ProfilerActivity
 from i2sdf_b200 import configs
 from i2sdf_b200.network import I2SDFNetwork, I2SDFLoss
-from oracle import i2sdf_oracle as orc
+from i2sdf_b200 import synthetic as orc   # (neutral input generator: perf tools do not touch oracle/)
 import bench
 name = os.environ.get("CONFIG", "synthetic")
 conf = configs.model_conf(name); conf["use_normal"] = True
