@@ -470,11 +470,12 @@ int i2sdf_sampler_rounds(i2sdf_handle* h, const float* o, const float* d, int64_
         p.beta_max = W.beta_max; p.beta_param = beta_param; p.beta_min = h->smp.beta_min; p.round_idx = k;
         p.net = h->net;
         if ((rc = run_mlp(h, p, st))) return rc;
-        ProfScope ps(h, 2, st, 2);
+        ProfScope ps(h, 2, st, 1);
         if ((rc = launch_sampler_round(h, W, R, k, 0, beta_param, nullptr, st))) return rc;
-        if ((rc = launch_sampler_round(h, W, R, k, 1, beta_param, u_final, st))) return rc;
     }
-    return I2SDF_OK;
+    // the final samples of whichever round turned out to be the last (decided on the device)
+    ProfScope ps(h, 2, st, 1);
+    return launch_sampler_round(h, W, R, -1, 1, beta_param, u_final, st);
 }
 
 int i2sdf_sampler_step(i2sdf_handle* h, const float* o, const float* d, int64_t R, const float* beta_param, const float* jitter,

@@ -1,5 +1,6 @@
 // Shared declarations of the i2sdf_b200 CUDA core (sm_100a).
 #pragma once
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -47,6 +48,20 @@ struct SamplerDev {
     const int* extra_idx;    // [max_iters][n_extra]
 };
 
+}  // namespace i2sdf
+
+namespace i2sdf {
+// Grid of a persistent tile kernel (one CTA per SM, tiles dealt round-robin): every CTA runs ceil(ntiles / grid) rounds whatever the grid, so
+// the smallest grid with the same number of rounds does the same work in the same number of tile times with fewer SMs contending for
+// HBM / L2 and less power drawn (the B200 is power-capped under these kernels): 800 tiles -> 6 rounds on 134 CTAs instead of 148 with
+// 60 CTAs busy in the last round.  I2SDF_GRID_BALANCE=0 restores min(ntiles, SMs).
+inline int balanced_grid(int num_sms, long long ntiles) {
+    static const bool on = [] { const char* e = getenv("I2SDF_GRID_BALANCE"); return !(e && e[0] == '0'); }();
+    if (ntiles <= (long long)num_sms) return (int)(ntiles > 0 ? ntiles : 1);
+    if (!on) return num_sms;
+    const long long rounds = (ntiles + num_sms - 1) / num_sms;
+    return (int)((ntiles + rounds - 1) / rounds);
+}
 }  // namespace i2sdf
 
 struct i2sdf_handle {

@@ -824,7 +824,7 @@ int tc_pack(i2sdf_handle* h, const float* const* W, const float* const* b, cudaS
 
 static inline int tc_grid(const i2sdf_handle* h, long long M) {
     long long ntiles = (M + tc3::TM - 1) / tc3::TM;
-    return (int)(ntiles < (long long)h->num_sms ? ntiles : (long long)h->num_sms);
+    return balanced_grid(h->num_sms, ntiles);
 }
 
 const chain::OpTable* tc_bwd_table(const i2sdf_handle* h, bool with_color) {

@@ -32,13 +32,16 @@ using namespace chain;
 
 // Work items are 32 rows x 8 columns (round 2): in every iteration all 16 epilogue warps work on ONE 32-column chunk, so the next op's
 // MMA chain starts after 1/8 of an epilogue; the slot segments an op reads (H / Q / HD / C: written up to 20 ops - or a whole kernel -
-// earlier, i.e. in HBM) are pulled into L2 one OP ahead and requested in front of the item's TMEM load; the slot copies of an item leave
-// behind its publish.  Round 1 (16-column items, 8 warps per chunk, prefetch one item ahead) ran at ~24 k clocks per op against ~8 k
-// for the sampler's kernel: every item waited for its own HBM round trips.
+// earlier, i.e. in HBM) are pulled into L2 ONE ITEM ahead (the warp's next item of the same op, or the first item of the next op) and
+// requested in front of the item's TMEM load; the slot copies of an item leave behind its publish.
+// Prefetch distance, measured on the 1024-ray C2 step (profiles/r02y_bwd_prefetch_sweep.txt, I2SDF_BWD_PREFETCH): off 1.55 ms, 1 item
+// 1.355, 2 items 1.37, 3 items 1.41, 4 items 1.43, one whole OP ahead 1.61 ms - an op ahead puts 148 CTAs x 384 KB = 57 MB of P-op
+// operands (plus the dirty adjoint lines) into the 2 x 63 MB L2 at once and evicts them again before use.
 // Shared memory: A_hi | A_lo (32 chunks each: K <= 256) | weight ring | heads (sdf head 257, rgb head 771 floats) | barriers.
 constexpr int B8_A_PART = 32 * TM * 16;
 constexpr int B8_PARAM_FLOATS = 260 + 772;
 constexpr size_t kSmemBwd8 = 128 + 2 * (size_t)B8_A_PART + NSTAGE * STAGE_MAX + B8_PARAM_FLOATS * 4 + 256;
+constexpr int kBwdPrefetchDefault = 1;
 enum { KB_TAN = 0, KB_TAN_SKIP, KB_TAN_LAST, KB_COL_REV, KB_FEAT_ADJ, KB_P, KB_P_SKIP, KB_P_TOP };
 
 __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd8_kernel(const BwdParams P, const OpTable T) {
@@ -143,6 +146,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd8_kernel(const BwdParams P,
                 if (both_planes) pf_l2(s0 + (size_t)it * 4 * planes::SUB_CHUNK + planes::BIG_PLANE);
             }
         };
+        // the same for ONE item (chunk 4 itx + sub) of an op of kind bk (BK_*), layer pl: the item-ahead mode (P.pf_dist = 1..7 items)
+        auto pf_item = [&](int bk, int pl, long long pm, int itx) {
+            const int pkc = itx * 4 + sub;
+            const size_t psg = planes::seg(pm, pkc, planes::BIG_CHUNKS);
+            if (bk == BK_TAN || bk == BK_P) {
+                const uint8_t* ph = SL.base + SL.H(pl) + psg;
+                pf_l2(ph); pf_l2(ph + planes::BIG_PLANE);
+                if (bk == BK_P) {
+                    const uint8_t* pq = SL.base + SL.Q(pl) + psg;
+                    const uint8_t* pd = SL.wbase + SL.HD(pl) + planes::segp(pm, pkc, planes::BIG_CHUNKS, planes::kPlanesHD);
+                    pf_l2(pq); pf_l2(pq + planes::BIG_PLANE);
+                    pf_l2(pd);
+                    if (planes::kPlanesHD == 2) pf_l2(pd + planes::BIG_PLANE);
+                } else if (pl == NL - 1 && color) pf_l2(SL.base + SL.C(net.Lc - 2) + psg);
+            } else if (bk == BK_COL_REV) pf_l2(SL.base + SL.C(pl - 1) + psg);
+        };
+        const int pfd = P.pf_dist;
         if ((long long)blockIdx.x < ntiles) { load_point(blockIdx.x); prologue(blockIdx.x); }
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const long long m = tile * TM + row;
@@ -156,7 +176,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd8_kernel(const BwdParams P,
 #pragma unroll
                 for (int c = 0; c < 3; ++c) { const float y = P.s_rgb[m * 3 + c]; delta[c] = P.g_rgb[m * 3 + c] * y * (1.f - y); }
             }
-            if (tile == (long long)blockIdx.x) pf_slot(SL.base + SL.H(0), m, true);       // first op of the first tile
+            if (tile == (long long)blockIdx.x && pfd >= 8) pf_slot(SL.base + SL.H(0), m, true);       // first op of the first tile
             for (int op = 0; op < T.nops; ++op, ++g) {
                 const uint32_t b = g & 1u;
                 const int kind = T.ops[op].kind, l = T.ops[op].layer;
@@ -165,10 +185,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd8_kernel(const BwdParams P,
                 dphase ^= (1u << b);
                 tc_fence_after();
                 const uint32_t acc_addr = tmem_base + lane_base + b * 256u;
-                {   // pull what the NEXT op reads into L2 now (for the last op: the next tile's first op)
-                    const int nk = last_op ? BK_TAN : T.ops[op + 1].kind, nl = last_op ? 0 : T.ops[op + 1].layer;
-                    const long long nm = last_op ? next_tile * TM + row : m;
-                    if (!last_op || next_tile < ntiles) {
+                // what the NEXT op reads (for the last op: the next tile's first op)
+                const int nk = last_op ? (next_tile < ntiles ? (int)BK_TAN : -1) : T.ops[op + 1].kind, nl = last_op ? 0 : T.ops[op + 1].layer;
+                const long long nm = last_op ? next_tile * TM + row : m;
+                if (pfd >= 8) {   // op-ahead mode: pull all of it into L2 now
+                    if (nk >= 0) {
                         if (nk == BK_TAN) {
                             pf_slot(SL.base + SL.H(nl), nm, true);
                             if (nl == NL - 1 && color) pf_slot(SL.base + SL.C(net.Lc - 2), nm, false);
@@ -192,6 +213,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd8_kernel(const BwdParams P,
                         const size_t sg = planes::seg(m, kc, planes::BIG_CHUNKS);
                         const size_t sg_adj = planes::segp(m, kc, planes::BIG_CHUNKS, planes::kPlanesAdj);      // adjoint slots: HI plane only
                         const size_t sg_hd = planes::segp(m, kc, planes::BIG_CHUNKS, planes::kPlanesHD);
+                        if (pfd > 0 && pfd < 8) {
+                            // item-ahead mode: this warp's item pfd steps on (same op, or the head of the next op) into L2
+                            const int tt = it + pfd;
+                            if (tt < 8) pf_item(is_p ? (int)BK_P : (is_tan ? (int)BK_TAN : (K == KB_COL_REV ? (int)BK_COL_REV : (int)BK_FEAT_ADJ)), l, m, tt);
+                            else if (nk >= 0) pf_item(nk, nl, nm, tt - 8);
+                        }
                         // slot operands of the item: requested in front of the TMEM load (L2 hits thanks to the op-ahead prefetch)
                         uint4 h_hi = make_uint4(0, 0, 0, 0), h_lo = h_hi, q_hi = h_hi, q_lo = h_hi, d_hi = h_hi, d_lo = h_hi, c_hi = h_hi;
                         if (is_tan || is_p) {
@@ -347,8 +374,12 @@ int tc_bwd_launch(const i2sdf_handle* h, const BwdParams& p, cudaStream_t st) {
     static PerDeviceOnce once;
     if (once.need()) I2SDF_CUDA_CHECK(cudaFuncSetAttribute(tc_bwd8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBwd8));
     const long long ntiles = (p.M + chain::TM - 1) / chain::TM;
-    const int grid = (int)(ntiles < (long long)h->num_sms ? ntiles : (long long)h->num_sms);
-    tc_bwd8_kernel<<<grid, chain::NTHREADS, kSmemBwd8, st>>>(p, *tab);
+    const int grid = balanced_grid(h->num_sms, ntiles);
+    // L2 prefetch distance of the slot segments: 1..7 = that many 8-column items ahead, 8 = one whole op ahead, 0 = off
+    static const int pf = [] { const char* e = getenv("I2SDF_BWD_PREFETCH"); const int v = e ? atoi(e) : kBwdPrefetchDefault; return (v < 0 || v > 8) ? kBwdPrefetchDefault : v; }();
+    BwdParams q = p;
+    q.pf_dist = pf;
+    tc_bwd8_kernel<<<grid, chain::NTHREADS, kSmemBwd8, st>>>(q, *tab);
     I2SDF_CUDA_CHECK(cudaGetLastError());
     return I2SDF_OK;
 }

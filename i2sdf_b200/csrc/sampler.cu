@@ -381,10 +381,16 @@ __device__ void merge_sorted(const float* __restrict__ z, int n, const float* __
 }
 
 // ------------------------------------------------------------------------------------------------
-// round k, phase 1: merge sdf, d*, beta search, batch-global max(beta)
+// round k: merge sdf, d*, beta search, batch-global max(beta) - and, in the same launch, this ray's up-sampling for round k + 1.
+// Whether round k + 1 happens is a batch-global decision (max over ALL rays of beta, ray_sampler.py:151) that no CTA can know before
+// the launch ends, but when it does happen every ray is up-sampled with its own beta whatever its own state (:153-176), so the
+// up-sampling is done speculatively here (the ray's z / sdf / d* are already in shared memory); if the batch turns out converged,
+// round k + 1's launches predicate themselves off and the speculative samples / merged z (the OTHER z buffer) are never read.
+// One launch per round instead of two: 12 -> 8 per-ray launches per forward, and d* / the z, sdf reload happen once.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kRayThreads) sampler_beta_kernel(SamplerDev S, SamplerWs W, long long R, int k, const float* __restrict__ beta_param) {
     extern __shared__ __align__(16) float smem[];
+    __shared__ float s_smp[128];
     const long long r = blockIdx.x;
     const float b0 = beta0_of(beta_param, S.beta_min);
     if (!sampler_round_active(W.beta_max, k, b0)) return;
@@ -405,37 +411,44 @@ __global__ void __launch_bounds__(kRayThreads) sampler_beta_kernel(SamplerDev S,
     }
     __syncthreads();
     compute_dstar(A, n);
-    float beta = beta_search(A, n, b0, W.beta[r], S);
+    const float beta = beta_search(A, n, b0, W.beta[r], S);
     if (threadIdx.x == 0) {
         W.beta[r] = beta;
         atomicMax(reinterpret_cast<int*>(W.beta_max + k), __float_as_int(beta));    // beta > 0
     }
+    if (k + 1 >= S.max_iters) return;                                               // :151-153: the last round never up-samples
+    __syncthreads();
+    resample(A, n, beta, true, S, S.u_up, S.n_eval, s_smp, nullptr);
+    float* smp = W.samples + r * S.n_eval;
+    for (int j = threadIdx.x; j < S.n_eval; j += kRayThreads) smp[j] = s_smp[j];
+    merge_sorted(A.z, n, s_smp, S.n_eval, W.z[cur ^ 1] + r * W.zmax, W.src + r * W.zmax);
 }
 
 // ------------------------------------------------------------------------------------------------
-// round k, phase 2: pdf / inverse-CDF / merge
+// after the last round that ran (klast: first round whose batch max(beta) met the bound, or max_iters - 1): the final N_samples from the
+// opacity pdf of that round's samples (ray_sampler.py:178-207 with the final weights).  only_k >= 0: staged API, launched after every
+// round - does nothing unless that round is klast.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRayThreads) sampler_resample_kernel(SamplerDev S, SamplerWs W, long long R, int k,
+__global__ void __launch_bounds__(kRayThreads) sampler_resample_kernel(SamplerDev S, SamplerWs W, long long R, int only_k,
                                                                        const float* __restrict__ beta_param, const float* __restrict__ u_final_tape) {
     extern __shared__ __align__(16) float smem[];
     __shared__ float s_smp[128];
     const long long r = blockIdx.x;
     const float b0 = beta0_of(beta_param, S.beta_min);
-    if (!sampler_round_active(W.beta_max, k, b0)) return;
-    const bool upsample = (W.beta_max[k] > b0) && (k + 1 < S.max_iters);            // :151-153
+    int k = 0;
+    while (k + 1 < S.max_iters && (W.beta_max[k] > b0)) ++k;
+    if (only_k >= 0 && only_k != k) return;
     const int n = S.n_eval * (k + 1), cur = k & 1;
     RayArrays A = carve_ray(smem);
     const float* zg = W.z[cur] + r * W.zmax;
     const float* sg = W.sdf[cur] + r * W.zmax;
     for (int i = threadIdx.x; i < n; i += kRayThreads) { A.z[i] = zg[i]; A.s[i] = sg[i]; }
     __syncthreads();
-    if (upsample) compute_dstar(A, n);
-    const int ns = upsample ? S.n_eval : S.n_samples;
-    const float* u = upsample ? S.u_up : (u_final_tape ? u_final_tape + r * S.n_samples : S.u_final);
-    resample(A, n, W.beta[r], upsample, S, u, ns, s_smp, nullptr);
+    const int ns = S.n_samples;
+    const float* u = u_final_tape ? u_final_tape + r * S.n_samples : S.u_final;
+    resample(A, n, W.beta[r], false, S, u, ns, s_smp, nullptr);
     float* smp = W.samples + r * S.n_eval;
     for (int j = threadIdx.x; j < ns; j += kRayThreads) smp[j] = s_smp[j];
-    if (upsample) merge_sorted(A.z, n, s_smp, ns, W.z[cur ^ 1] + r * W.zmax, W.src + r * W.zmax);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -631,6 +644,8 @@ int launch_sampler_round(const i2sdf_handle* h, const SamplerWs& W, long long R,
     int rc = ensure_smem_attrs();
     if (rc) return rc;
     if (R <= 0) return I2SDF_OK;
+    // phase 0: round k (beta search + speculative up-sampling); phase 1: the final samples, k = -1: after whichever round was the last,
+    // k >= 0: only if round k was the last (staged API: launched behind every round's convergence exchange)
     if (phase == 0) sampler_beta_kernel<<<(int)R, kRayThreads, kSamplerSmem, st>>>(h->smp, W, R, k, beta_param);
     else sampler_resample_kernel<<<(int)R, kRayThreads, kSamplerSmem, st>>>(h->smp, W, R, k, beta_param, u_final_tape);
     I2SDF_CUDA_CHECK(cudaGetLastError());

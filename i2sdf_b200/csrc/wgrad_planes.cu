@@ -257,16 +257,19 @@ __global__ void from_planes_kernel(const uint8_t* __restrict__ slot, int chunks,
 
 // out[k][j] += sum_m w_k[m] * X[m][j]   for a 256-column slot (w null: plain column sums), up to 3 weight vectors per pass
 // over the slot (the three rows of the rgb head's gradient read the last radiance activation once); grid = (tile groups, jobs)
-__global__ void __launch_bounds__(256) planes_colsum_kernel(const CsArgs A) {
+// 16 warps x 2 chunks each (round 2: 8 warps x 4 chunks kept 96 accumulators + 32 x 16 B of loads per thread = 205 registers, one 8-warp CTA
+// per SM and 2.7 TB/s; half the accumulators per thread doubles the warps in flight at the same register file use)
+constexpr int kCsWarps = 16, kCsPer = 2;
+__global__ void __launch_bounds__(kCsWarps * 32) planes_colsum_kernel(const CsArgs A) {
     const CsJob& J = A.jobs[blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nw = J.w ? J.nw : 1;
     const long long t0 = A.ntiles * blockIdx.x / gridDim.x, t1 = A.ntiles * (blockIdx.x + 1) / gridDim.x;
-    float cs[3][4][8];
+    float cs[3][kCsPer][8];
 #pragma unroll
     for (int k = 0; k < 3; ++k)
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < kCsPer; ++a)
 #pragma unroll
             for (int e = 0; e < 8; ++e) cs[k][a][e] = 0.f;
     for (long long tile = t0; tile < t1; ++tile) {
@@ -275,15 +278,14 @@ __global__ void __launch_bounds__(256) planes_colsum_kernel(const CsArgs A) {
             const long long m = tile * planes::TM + rr * 32 + lane;
             float w[3] = {1.f, 0.f, 0.f};
             if (J.w) {
-#pragma unroll
                 const long long wlim = (J.wrows > 0 && J.wrows < A.M) ? J.wrows : A.M;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) w[k] = (k < nw && m < wlim) ? J.w[(size_t)m * J.wstride + k] : 0.f;
             }
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
+            for (int a = 0; a < kCsPer; ++a) {
                 const int np = J.nplanes == 1 ? 1 : 2;
-                const uint8_t* sp = J.slot + planes::segp(m, warp + 8 * a, planes::BIG_CHUNKS, np);
+                const uint8_t* sp = J.slot + planes::segp(m, warp + kCsWarps * a, planes::BIG_CHUNKS, np);
                 const uint4 hi = *reinterpret_cast<const uint4*>(sp), lo = (np == 2) ? *reinterpret_cast<const uint4*>(sp + planes::BIG_PLANE) : make_uint4(0, 0, 0, 0);
                 const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
@@ -306,12 +308,12 @@ __global__ void __launch_bounds__(256) planes_colsum_kernel(const CsArgs A) {
     for (int k = 0; k < 3; ++k) {
         if (k >= nw) break;
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < kCsPer; ++a)
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 float v = cs[k][a][e];
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                const int col = (warp + 8 * a) * 8 + e;
+                const int col = (warp + kCsWarps * a) * 8 + e;
                 if (lane == 0 && col < J.n) atomicAdd(J.out + (size_t)k * J.ostride + col, v);
             }
     }
@@ -336,10 +338,10 @@ int wgrad_planes_launch(const i2sdf_handle* h, const WgArgs& args, cudaStream_t 
 
 int planes_colsum_launch(const i2sdf_handle* h, const CsArgs& args, cudaStream_t st) {
     if (args.njobs <= 0 || args.ntiles <= 0) return I2SDF_OK;
-    // (2 CTAs per SM are resident at this register count; a 4x larger grid was measured slower: 150 vs 111 us)
+    // (one 16-warp CTA per SM; a 4x larger grid was measured slower in round 1: 150 vs 111 us)
     int gx = (2 * h->num_sms + args.njobs - 1) / args.njobs;
     if ((long long)gx > args.ntiles) gx = (int)args.ntiles;
-    wgp::planes_colsum_kernel<<<dim3(gx, args.njobs), 256, 0, st>>>(args);
+    wgp::planes_colsum_kernel<<<dim3(gx, args.njobs), wgp::kCsWarps * 32, 0, st>>>(args);
     I2SDF_CUDA_CHECK(cudaGetLastError());
     return I2SDF_OK;
 }
