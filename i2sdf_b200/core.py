@@ -198,7 +198,8 @@ class RenderCore:
         self._keep_grid = (gx, gy, gz, aff)
         return out
 
-    def sample(self, o, d, beta_param, tape: Optional[Dict[str, torch.Tensor]] = None, want_info=False, defer_sync=False, group=None):
+    def sample(self, o, d, beta_param, tape: Optional[Dict[str, torch.Tensor]] = None, want_info=False, defer_sync=False, group=None,
+               staged=False):
         """ErrorBoundSampler.get_z_vals.  tape (training): jitter [R,128], u_final [R,64] fp32;
         extra_perm: callable n -> LongTensor[32] (drawn after one 8-byte D2H of n) or int tensor; eik_idx [R].
 
@@ -210,7 +211,8 @@ class RenderCore:
 
         group (torch.distributed process group, world > 1): the rays of this call are one shard of a batch; the convergence
         word of every round is MAX-all-reduced over the group so that all shards run the rounds the whole batch would
-        (the reference's test is batch-global, ray_sampler.py:151)."""
+        (the reference's test is batch-global, ray_sampler.py:151).  staged=True walks the same stage-by-stage entry point
+        (i2sdf_sampler_step) without a group: same launches as the sharded path minus the exchange (tests)."""
         self.sampler_resolve()
         o, d = _f32(o, self.device), _f32(d, self.device)
         R = o.shape[0]
@@ -219,7 +221,8 @@ class RenderCore:
         jit = _f32(tape["jitter"], self.device) if "jitter" in tape else None
         ufin = _f32(tape["u_final"], self.device) if "u_final" in tape else None
         st = self._stream()
-        if group is not None and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1:
+        sharded = group is not None and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1
+        if sharded or staged:
             import torch.distributed as dist
             args = (self.h, _ptr(o), _ptr(d), R, _ptr(beta_param), _ptr(jit), _ptr(ufin))
             check(self.lib.i2sdf_sampler_step(*args, 0, 0, _ptr(ws), self._ws_bytes, st), "i2sdf_sampler_step")
@@ -227,7 +230,8 @@ class RenderCore:
             beta_max = ws[off:off + 4 * self.desc.max_total_iters].view(torch.float32)
             for k in range(self.desc.max_total_iters):
                 check(self.lib.i2sdf_sampler_step(*args, 1, k, _ptr(ws), self._ws_bytes, st), "i2sdf_sampler_step")
-                dist.all_reduce(beta_max[k:k + 1], op=dist.ReduceOp.MAX, group=group)       # 4 bytes, in stream order
+                if sharded:
+                    dist.all_reduce(beta_max[k:k + 1], op=dist.ReduceOp.MAX, group=group)   # 4 bytes, in stream order
                 check(self.lib.i2sdf_sampler_step(*args, 2, k, _ptr(ws), self._ws_bytes, st), "i2sdf_sampler_step")
         else:
             check(self.lib.i2sdf_sampler_rounds(self.h, _ptr(o), _ptr(d), R, _ptr(beta_param), _ptr(jit), _ptr(ufin),

@@ -139,6 +139,7 @@ struct MlpParams {
     float* out_light;
     float* save_act;          // [L-1][M][256] pre-activations (training) or null
     float* scratch;           // per-CTA [(L-1)][TM][256] when grad wanted without save_act
+    int pf_op_ahead;          // main pass: pull the next op's stored h~ segments into L2 one op ahead (set by tcmain_launch; I2SDF_MAIN_PREFETCH=0 off)
     void* tl;                 // development probe (I2SDF_DEBUG_TIMELINE): 64 KB of clock64 stamps, tensor-core main pass only
     planes::Layout sl;        // tensor-core main pass in training: the saved state is plane slots (sl.base != null)
     int want_color;

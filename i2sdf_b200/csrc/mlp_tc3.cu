@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_main8_kernel(const MlpParams P
                 tc_fence_after();
                 if (TL && tlw) tlw[1] = clock64();
                 const uint32_t acc_addr = tmem_base + lane_base + b * 256u;
-                if (hbase && !last_op) {
+                if (hbase && !last_op && P.pf_op_ahead) {
                     // the next op's stored h~ (written up to 20 ops ago, possibly evicted to HBM): pull this thread's 16 segments into L2 now
                     const int nk = T.ops[op + 1].kind, nl = T.ops[op + 1].layer;
                     if (nk == EK_REV || nk == EK_COL_LAST) {
@@ -876,9 +876,15 @@ int tcmain_launch(const i2sdf_handle* h, void* state, const MlpParams& p, cudaSt
     if (p.M <= 0) return I2SDF_OK;
     const State* s = (const State*)state;
     const OpTable& tab = p.want_color ? s->full : (p.out_grad ? s->sg : s->sf);
-    if (p.sl.base) tc_main8_kernel<true><<<tc_grid(h, p.M), NTHREADS, kSmemMain, st>>>(p, tab);
-    else if (p.tl) tc_main8_kernel<false, true><<<tc_grid(h, p.M), NTHREADS, kSmemMain, st>>>(p, tab);
-    else tc_main8_kernel<false><<<tc_grid(h, p.M), NTHREADS, kSmemMain, st>>>(p, tab);
+    // op-ahead L2 prefetch of the stored h~ (round 2, first sessions: on) measured against off on the 1024-ray C2 step
+    // (profiles/r02b_main_prefetch.txt): training main pass 1.110 vs 1.024 ms - as in the backward chain, a whole op of 134 CTAs ahead
+    // evicts more than it saves; the one-item-ahead register prefetch of the items loop stays.  I2SDF_MAIN_PREFETCH=1 turns it back on.
+    static const int pf = [] { const char* e = getenv("I2SDF_MAIN_PREFETCH"); return (e && e[0] == '1') ? 1 : 0; }();
+    MlpParams q = p;
+    q.pf_op_ahead = pf;
+    if (p.sl.base) tc_main8_kernel<true><<<tc_grid(h, p.M), NTHREADS, kSmemMain, st>>>(q, tab);
+    else if (p.tl) tc_main8_kernel<false, true><<<tc_grid(h, p.M), NTHREADS, kSmemMain, st>>>(q, tab);
+    else tc_main8_kernel<false><<<tc_grid(h, p.M), NTHREADS, kSmemMain, st>>>(q, tab);
     I2SDF_CUDA_CHECK(cudaGetLastError());
     return I2SDF_OK;
 }

@@ -10,10 +10,14 @@ the package there is no CPU path.
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
 from . import _lib
+
+
+_FAST_OFF = os.environ.get("I2SDF_ADAM_FAST", "1") == "0"        # measurement switch (tools/step_times.py)
 
 
 class Adam(torch.optim.Optimizer):
@@ -26,6 +30,7 @@ class Adam(torch.optim.Optimizer):
         self._fresh_steps = {}
         self._batches = {}
         self._graph_scalars = {}
+        self._plans = {}
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -40,10 +45,21 @@ class Adam(torch.optim.Optimizer):
             self._batches = {}
         if not hasattr(self, "_graph_scalars"):
             self._graph_scalars = {}
+        if not hasattr(self, "_plans"):
+            self._plans = {}
         for group in self.param_groups:
+            if self._fast_step(group, lib):
+                continue
             ps = [p for p in group["params"] if p.grad is not None]
             if not ps:
                 continue
+            if len(ps) < len(group["params"]):
+                # a parameter that sits this step out keeps its own count (torch.optim.Adam's per-parameter `step`): detach it from
+                # the counter object it may share with the parameters that do step
+                for p in group["params"]:
+                    st = self.state.get(p) if p.grad is None else None
+                    if st and "step" in st:
+                        st["step"] = st["step"].clone()
             beta1, beta2 = group["betas"]
             # the step counters are host tensors (torch.optim.Adam's state layout); parameters created together share ONE
             # tensor object so that a step costs one host increment, not one per parameter
@@ -92,6 +108,13 @@ class Adam(torch.optim.Optimizer):
                         cached = (key, batches)
                         if len(by_step) == 1:
                             self._batches[id(group)] = cached
+                    # steady state from the next step on (_fast_step): every parameter of the group has a gradient and one shared counter
+                    if len(by_step) == 1 and len(plist) == len(group["params"]) and not torch.cuda.is_current_stream_capturing():
+                        st0 = self.state[plist[0]]
+                        for p in plist:                  # equal counts (one launch): share ONE counter object again, e.g. after load_state_dict
+                            self.state[p]["step"] = st0["step"]
+                        self._plans[id(group)] = dict(params=list(group["params"]), state0=st0, step=st0["step"], batches=cached[1], dev=dev,
+                                                      jobs=[b.jobs[i] for b in cached[1] for i in range(b.n)])
                     capturing = torch.cuda.is_current_stream_capturing()
                     scal = None
                     if capturing:
@@ -114,6 +137,55 @@ class Adam(torch.optim.Optimizer):
                             _lib.check(lib.i2sdf_adam_step(C.byref(b), stream), "i2sdf_adam_step")
                     del grads
         return loss
+
+    def _fast_step(self, group, lib) -> bool:
+        """Steady-state step of one group: same parameter objects as when the job tables were built, all with dense contiguous gradients,
+        one shared step counter, unchanged optimizer state (load_state_dict / add_param_group / a parameter without a gradient fall back to
+        the general path, which rebuilds the plan).  Host cost: one pass over the parameters to refresh the gradient pointers (autograd
+        allocates new gradient tensors every step unless a parallel.GradBucket pins them) - the general path's per-step dictionary
+        lookups, float() conversions and pointer-key tuples cost 0.5-0.8 ms per step for 44 tensors (tools/host_profile.py), which the
+        GPU spends idle at the step boundary once the rest of the step is as short as it is."""
+        plan = self._plans.get(id(group))
+        if plan is None or _FAST_OFF:
+            return False
+
+        def drop():
+            # back to the general path: the shared job tables carry this path's gradient pointers, so its pointer-keyed cache is stale too
+            self._plans.pop(id(group), None)
+            self._batches.pop(id(group), None)
+            return False
+        if torch.cuda.is_current_stream_capturing():
+            return drop()
+        params, pp = group["params"], plan["params"]
+        if len(params) != len(pp):
+            return drop()
+        st0 = self.state.get(params[0])
+        if st0 is None or st0 is not plan["state0"] or st0.get("step") is not plan["step"]:
+            return drop()
+        keep = []                                    # the gradient tensors stay referenced until the launch is queued
+        for p, q, j in zip(params, pp, plan["jobs"]):
+            g = p.grad
+            if p is not q or g is None or g.is_sparse or not g.is_contiguous() or j.param != p.data_ptr():
+                return drop()
+            gp = g.data_ptr()
+            if j.grad != gp:
+                j.grad = gp
+            keep.append(g)
+        sp = plan["step"]
+        sp += 1
+        t = float(sp)
+        beta1, beta2 = group["betas"]
+        dev = plan["dev"]
+        with torch.cuda.device(dev):
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            for b in plan["batches"]:
+                b.beta1, b.beta2, b.eps = beta1, beta2, group["eps"]
+                b.one_minus_beta1, b.one_minus_beta2 = 1.0 - beta1, 1.0 - beta2
+                b.step_size = group["lr"] / (1.0 - beta1 ** t)
+                b.bias_correction2_sqrt = math.sqrt(1.0 - beta2 ** t)
+                _lib.check(lib.i2sdf_adam_step(C.byref(b), stream), "i2sdf_adam_step")
+        del keep
+        return True
 
     def prepare_replay(self):
         """Before replaying a CUDA graph that captured step(): advance the step counters and refresh the scalars the captured kernels read."""

@@ -131,9 +131,13 @@ int i2sdf_sampler_rounds(i2sdf_handle* h, const float* o, const float* d, int64_
 /* The same rounds one stage at a time, for callers that shard the rays of ONE batch over several GPUs and want the
  * reference's batch-global convergence test (`beta.max() > beta0`, ray_sampler.py:151) instead of a per-shard one:
  *   stage 0: initial z's (jitter);  stage 1, round k: SDF on the round's samples + beta search, leaves max_rays(beta) in
- *   i2sdf_sampler_beta_max(...)[k];  stage 2, round k: up-sample / final draw using that word.
+ *   i2sdf_sampler_beta_max(...)[k], and (k + 1 < max_total_iters) up-samples every ray for round k + 1 in the same launch - the
+ *   reference up-samples all rays or none (ray_sampler.py:151-176), so the draw is done speculatively and round k + 1 predicates
+ *   itself off if the batch turns out converged;  stage 2, round k: the final N_samples draw, only if that word says round k was
+ *   the last one (otherwise the launch returns at once).
  * Between stage 1 and stage 2 the caller MAX-all-reduces beta_max[k] across its ranks (4 bytes, stream-ordered; see
- * i2sdf_b200/core.py::sample(group=...)).  Positive floats: integer and float MAX agree. */
+ * i2sdf_b200/core.py::sample(group=...)).  Positive floats: integer and float MAX agree.  i2sdf_sampler_rounds is the same
+ * sequence with ONE final-draw launch behind the last round. */
 int i2sdf_sampler_step(i2sdf_handle* h, const float* o, const float* d, int64_t R, const float* beta_param,
                        const float* jitter, const float* u_final, int stage, int k,
                        void* workspace, size_t workspace_bytes, void* stream);

@@ -590,6 +590,22 @@ def test_light_head_chunked_render_is_consistent(cases):
     assert 0.0 <= float(whole["light"].min()) and float(whole["light"].max()) < 1.0 + 1e-5   # composited with weights summing to <= 1
 
 
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_sampler_staged_entry_point_equals_one_call(cases, name):
+    """i2sdf_sampler_step (init / round k: sdf + beta search + speculative up-sampling / final samples behind each round's convergence
+    exchange - the entry point the ray-sharded sampler walks) returns bit for bit what i2sdf_sampler_rounds returns, on the fixtures that
+    stop after 2 rounds (the speculative up-sampling of the converged round must stay unused) and after all 5."""
+    c = cases[name]
+    m = _model(c)
+    core = m._ready_core()
+    o, d, _ = (t.cuda() for t in orc.flatten_rays(c.inputs["uv"], c.inputs["pose"], c.inputs["intrinsics"]))
+    beta = m.density.beta.detach()
+    z0, _, i0 = core.sample(o, d, beta, None, want_info=True)
+    z1, _, i1 = core.sample(o, d, beta, None, want_info=True, staged=True)
+    assert torch.equal(i0, i1) and int(i0[0]) == int(c.trace["n_rounds"])
+    assert torch.equal(z0, z1)
+
+
 def test_sampler_deferred_randperm_equals_synchronous():
     """Training sampler without the mid-step host sync: the candidate-table path (sample(defer_sync=True) + sampler_resolve)
     returns the same z's as the synchronous path and leaves the CPU generator in the same state (ray_sampler.py:223)."""
@@ -798,9 +814,31 @@ def test_one_launch_adam_matches_torch_adam():
         oa.step(); ob.step(); sa.step(); sb.step()
     for (n, pa), pb in zip(ma.named_parameters(), mb.parameters()):
         assert relerr(pa, pb) < 2e-6, (n, relerr(pa, pb))
-    ob.load_state_dict(oa.state_dict())              # same keys / shapes
+    import copy
+    ob.load_state_dict(copy.deepcopy(oa.state_dict()))              # same keys / shapes
     for pa, pb in zip(ma.parameters(), mb.parameters()):
         assert torch.equal(oa.state[pa]["exp_avg_sq"], ob.state[pb]["exp_avg_sq"])
+    # the steady-state fast path (job tables reused, gradient pointers refreshed) must notice a replaced optimizer state: load torch's
+    # state dict back (per-parameter step tensors), step both twice more (general path, then fast path again) and compare
+    oa.load_state_dict(copy.deepcopy(ob.state_dict()))      # (load_state_dict keeps references to tensors that need no cast: without the copy the two optimizers would share moments)
+    for _ in range(2):
+        for pa, pb in zip(ma.parameters(), mb.parameters()):
+            gr = torch.randn(pa.shape, generator=g).cuda() * 1e-2
+            pa.grad, pb.grad = gr.clone(), gr.clone()
+        oa.step(); ob.step()
+    for (n, pa), pb in zip(ma.named_parameters(), mb.parameters()):
+        assert relerr(pa, pb) < 2e-6, (n, relerr(pa, pb))
+    sd = oa.state_dict()["state"]
+    assert all(float(v["step"]) == 5.0 for v in sd.values()) and len({id(v["step"]) for v in sd.values()}) == len(sd)
+    # a parameter that loses its gradient drops the group back to the general path (and is skipped, as in torch.optim.Adam)
+    ps = list(ma.parameters())
+    before0, before1 = ps[0].detach().clone(), ps[1].detach().clone()
+    for p in ps:
+        p.grad = torch.full_like(p, 1e-3)
+    ps[0].grad = None
+    oa.step()
+    assert torch.equal(ps[0], before0) and not torch.equal(ps[1], before1)
+    assert float(oa.state[ps[0]]["step"]) == 5.0 and float(oa.state[ps[1]]["step"]) == 6.0
 
 
 def test_full_size_batch_properties(cases):
