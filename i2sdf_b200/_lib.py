@@ -87,6 +87,7 @@ SYMBOLS = {
     "i2sdf_profile_enable": (C.c_int, [_P, C.c_int]),
     "i2sdf_profile_read": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     "i2sdf_profile_read_n": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
+    "i2sdf_debug_bwd_timeline": (C.c_int64, [C.POINTER(C.c_int64), C.c_int64]),
     "i2sdf_saved_format": (C.c_int, [_P, C.c_int]),
     "i2sdf_sdf_saved_bytes": (C.c_size_t, [_P, C.c_int64]),
     "i2sdf_points_forward_ex": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int, _P, C.c_int64] + [_P] * 6 + [_P, C.c_size_t, _P]),

@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "planes.cuh"
 #include "wgrad_planes.cuh"
+#include "tc_bwd.cuh"
 
 namespace i2sdf {
 
@@ -686,6 +687,11 @@ int i2sdf_profile_read_n(i2sdf_handle* h, int n, float* ms, int64_t* launches) {
         launches[k] = p->launches[k];
     }
     return I2SDF_OK;
+}
+
+int64_t i2sdf_debug_bwd_timeline(int64_t* out, int64_t n) {
+    cudaDeviceSynchronize();
+    return (int64_t)tc_bwd_timeline_read((long long*)out, (long long)n);
 }
 
 size_t i2sdf_saved_bytes(const i2sdf_handle* h, int64_t R, int N) { return i2sdf_saved_bytes_points(h, R * N); }

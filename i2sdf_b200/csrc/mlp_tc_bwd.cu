@@ -44,6 +44,12 @@ constexpr size_t kSmemBwd8 = 128 + 2 * (size_t)B8_A_PART + NSTAGE * STAGE_MAX + 
 constexpr int kBwdPrefetchDefault = 1;
 enum { KB_TAN = 0, KB_TAN_SKIP, KB_TAN_LAST, KB_COL_REV, KB_FEAT_ADJ, KB_P, KB_P_SKIP, KB_P_TOP };
 
+// TL: development probe (I2SDF_DEBUG_TIMELINE=1, tools/timeline.py bwd): clock64 stamps of CTA 0's second tile into P.tl - per op and epilogue
+// warp [wait starts, accumulator seen, first item published, last item done] at tl[(op * 16 + warp) * 4], the MMA warp's stamps as in
+// chain_mma, and for epilogue warp 0 every item's [start, TMEM + operands there, values computed, published, slot stores issued] at
+// tl[7168 + (op * 8 + it) * 5]
+__device__ __forceinline__ long long tl_clock() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory"); return t; }
+template <bool TL = false>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd8_kernel(const BwdParams P, const OpTable T) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_align128(smem_raw);
@@ -82,7 +88,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd8_kernel(const BwdParams P,
     if (warp == 0) {
         if (lane == 0) chain_producer(T, ntiles, ring, full, empty);
     } else if (warp == 1) {
-        chain_mma(T, ntiles, tmem_base, A_hi, A_lo, ring, full, empty, a_ready, d_full);
+        chain_mma<TL>(T, ntiles, tmem_base, A_hi, A_lo, ring, full, empty, a_ready, d_full, P.tl);
     } else {
         // ================= epilogue warps =================
         const int q = warp & 3;
@@ -181,13 +187,56 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd8_kernel(const BwdParams P,
                 const uint32_t b = g & 1u;
                 const int kind = T.ops[op].kind, l = T.ops[op].layer;
                 const bool last_op = (op == T.nops - 1);
-                mbar_wait(&d_full[b], (dphase >> b) & 1u);
-                dphase ^= (1u << b);
-                tc_fence_after();
+                long long* tlw = (TL && P.tl && lane == 0 && blockIdx.x == 0 && tile == (long long)gridDim.x) ? P.tl + (op * 16 + (warp - 2)) * 4 : nullptr;
+                long long* tli = (TL && tlw && warp == 2) ? P.tl + 7168 + op * 40 : nullptr;
                 const uint32_t acc_addr = tmem_base + lane_base + b * 256u;
                 // what the NEXT op reads (for the last op: the next tile's first op)
                 const int nk = last_op ? (next_tile < ntiles ? (int)BK_TAN : -1) : T.ops[op + 1].kind, nl = last_op ? 0 : T.ops[op + 1].layer;
                 const long long nm = last_op ? next_tile * TM + row : m;
+                // Slot operands travel ONE ITEM AHEAD in registers (round 2, profiles/r02e_timeline_bwd.txt: with the loads issued at the top of
+                // their own item every item exposed 400-1300 clocks of L2 / HBM latency, all four warps of a scheduler waiting together): item 0's
+                // segments are requested BEFORE the wait for the accumulator (the warp idles there anyway), item it + 1's as soon as item it's
+                // values are computed - the operand registers are dead from there on - i.e. in front of the publish fence and the slot stores,
+                // which cover most of the latency.  Same register peak as before.
+                uint4 h_hi = make_uint4(0, 0, 0, 0), h_lo = h_hi, c_hi = h_hi;
+                auto request = [&](auto kind_c, int it2) {
+                    constexpr int K = decltype(kind_c)::value;
+                    constexpr bool is_tan = (K == KB_TAN || K == KB_TAN_SKIP || K == KB_TAN_LAST);
+                    constexpr bool is_p = (K == KB_P || K == KB_P_SKIP || K == KB_P_TOP);
+                    if (is_p) return;                          // P ops load inside their own item, into item-local registers (see items)
+                    const int kc2 = it2 * 4 + sub;
+                    const size_t sg2 = planes::seg(m, kc2, planes::BIG_CHUNKS);
+                    if (is_tan) {
+                        const uint8_t* ph = SL.base + SL.H(l) + sg2;
+                        h_hi = ldg_cs(ph); h_lo = ldg_cs(ph + planes::BIG_PLANE);
+                    }
+                    if (K == KB_COL_REV) c_hi = ldg_cs(SL.base + SL.C(l - 1) + sg2);
+                    if (K == KB_TAN_LAST && color) c_hi = ldg_cs(SL.base + SL.C(net.Lc - 2) + sg2);
+                };
+                // kind of this op as a compile-time constant for the two templated pieces (request / items)
+                auto dispatch = [&](auto&& fn) {
+                    switch (kind) {
+                        case BK_TAN:
+                            if (l == NL - 1) fn(std::integral_constant<int, KB_TAN_LAST>{});
+                            else if (l + 1 == net.skip) fn(std::integral_constant<int, KB_TAN_SKIP>{});
+                            else fn(std::integral_constant<int, KB_TAN>{});
+                            break;
+                        case BK_COL_REV: fn(std::integral_constant<int, KB_COL_REV>{}); break;
+                        case BK_FEAT_ADJ: fn(std::integral_constant<int, KB_FEAT_ADJ>{}); break;
+                        default:
+                            if (l == NL - 1) fn(std::integral_constant<int, KB_P_TOP>{});
+                            else if (l + 1 == net.skip) fn(std::integral_constant<int, KB_P_SKIP>{});
+                            else fn(std::integral_constant<int, KB_P>{});
+                            break;
+                    }
+                };
+                dispatch([&](auto kind_c) { request(kind_c, 0); });        // (does nothing for P ops)
+                // accumulator of this op complete; then the work that had to wait for it
+                if (TL && tlw) tlw[0] = tl_clock();
+                mbar_wait(&d_full[b], (dphase >> b) & 1u);
+                dphase ^= (1u << b);
+                tc_fence_after();
+                if (TL && tlw) tlw[1] = tl_clock();
                 if (pfd >= 8) {   // op-ahead mode: pull all of it into L2 now
                     if (nk >= 0) {
                         if (nk == BK_TAN) {
@@ -210,33 +259,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd8_kernel(const BwdParams P,
 #pragma unroll 1
                     for (int it = 0; it < 8; ++it) {
                         const int col0 = it * 32 + sub * 8, kc = it * 4 + sub;
-                        const size_t sg = planes::seg(m, kc, planes::BIG_CHUNKS);
                         const size_t sg_adj = planes::segp(m, kc, planes::BIG_CHUNKS, planes::kPlanesAdj);      // adjoint slots: HI plane only
                         const size_t sg_hd = planes::segp(m, kc, planes::BIG_CHUNKS, planes::kPlanesHD);
+                        if (TL && tli) tli[it * 5] = tl_clock();
                         if (pfd > 0 && pfd < 8) {
-                            // item-ahead mode: this warp's item pfd steps on (same op, or the head of the next op) into L2
-                            const int tt = it + pfd;
+                            // L2 prefetch: the item that will be REQUESTED pfd items from now (this warp's item it + 1 + pfd of the same op, or the head of
+                            // the next op)
+                            const int tt = it + pfd + (is_p ? 0 : 1);
                             if (tt < 8) pf_item(is_p ? (int)BK_P : (is_tan ? (int)BK_TAN : (K == KB_COL_REV ? (int)BK_COL_REV : (int)BK_FEAT_ADJ)), l, m, tt);
-                            else if (nk >= 0) pf_item(nk, nl, nm, tt - 8);
+                            else if (nk >= 0 && tt - 8 < 8) pf_item(nk, nl, nm, tt - 8);
                         }
-                        // slot operands of the item: requested in front of the TMEM load (L2 hits thanks to the op-ahead prefetch)
-                        uint4 h_hi = make_uint4(0, 0, 0, 0), h_lo = h_hi, q_hi = h_hi, q_lo = h_hi, d_hi = h_hi, d_lo = h_hi, c_hi = h_hi;
-                        if (is_tan || is_p) {
-                            const uint8_t* ph = SL.base + SL.H(l) + sg;
-                            h_hi = ldg_cs(ph); h_lo = ldg_cs(ph + planes::BIG_PLANE);
-                        }
+                        // P ops: the six segments of THIS item, into item-local registers, in front of the item's own TMEM load (see below)
+                        uint4 p_h_hi = make_uint4(0, 0, 0, 0), p_h_lo = p_h_hi, q_hi = p_h_hi, q_lo = p_h_hi, d_hi = p_h_hi, d_lo = p_h_hi;
                         if (is_p) {
+                            const size_t sg = planes::seg(m, kc, planes::BIG_CHUNKS);
+                            const uint8_t* ph = SL.base + SL.H(l) + sg;
                             const uint8_t* pq = SL.base + SL.Q(l) + sg;
                             const uint8_t* pd = SL.wbase + SL.HD(l) + sg_hd;
+                            p_h_hi = ldg_cs(ph); p_h_lo = ldg_cs(ph + planes::BIG_PLANE);
                             q_hi = ldg_cs(pq); q_lo = ldg_cs(pq + planes::BIG_PLANE);
                             d_hi = ldg_cs(pd);
                             if (planes::kPlanesHD == 2) d_lo = ldg_cs(pd + planes::BIG_PLANE);
                         }
-                        if (K == KB_COL_REV) c_hi = ldg_cs(SL.base + SL.C(l - 1) + sg);
-                        if (K == KB_TAN_LAST && color) c_hi = ldg_cs(SL.base + SL.C(net.Lc - 2) + sg);
                         uint32_t v[8];
                         tmem_ld8(acc_addr + (uint32_t)col0, v);
                         tmem_ld_wait();
+                        if (TL && tli) {
+                            // operands there: a dependent use of every requested segment in front of the stamp
+                            const uint32_t dep = h_hi.x ^ h_lo.x ^ p_h_hi.x ^ p_h_lo.x ^ q_hi.x ^ q_lo.x ^ d_hi.x ^ d_lo.x ^ c_hi.x;
+                            asm volatile("" ::"r"(dep) : "memory");
+                            tli[it * 5 + 1] = tl_clock();
+                        }
                         float hv[8];
                         uint8_t* gs = nullptr;
                         bool keep = true, to_smem = true, adj_slot = true;       // adj_slot: gs is an adjoint slot (HI plane only), else a tangent slot
@@ -307,7 +360,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd8_kernel(const BwdParams P,
                         } else {
                             // BK_P: accumulator = W_{l+1}^T p_{l+1} ; p_l = s'(a_l) u + s''(a_l) adot_l v_l with q_l = s'(a_l) v_l from the forward
                             float hh[8], qq[8], dd[8];
-                            seg8_values<false>(h_hi, h_lo, hh);
+                            seg8_values<false>(p_h_hi, p_h_lo, hh);
                             seg8_values<false>(q_hi, q_lo, qq);
                             seg8_values<false>(d_hi, d_lo, dd);
 #pragma unroll
@@ -328,33 +381,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd8_kernel(const BwdParams P,
                             to_smem = !last_op;
                         }
                         uint32_t hh2[4], ll2[4];
+                        if (TL && tli) { asm volatile("" ::"f"(hv[0]), "f"(hv[7]) : "memory"); tli[it * 5 + 2] = tl_clock(); }
+                        // the operand registers are free: T / CR ops (1-2 segments per item) request the next item's segments here, in front of the
+                        // publish: its fence (MEMBAR.ALL.CTA) also waits for loads in flight, but two L2-resident segments cost it little and their
+                        // latency hides behind the publish + store phase (T ops 17.2 k -> 15.5 k clocks per op, CR ops 14.6 k -> 14.1 k).  P ops (6
+                        // segments = 48 KB per 32-column step per CTA) run at their share of HBM bandwidth: requested one item ahead - in front of the
+                        // publish or behind it - the segments arrive no earlier and only delay the publish and the slot stores (measured: 23 k ->
+                        // 26.5 k / 27.5 k clocks per op, profiles/r02f_ / r02g_timeline_bwd.txt), so P ops request at the top of their own item
+                        if (!is_p && it < 7) request(kind_c, it + 1);
                         if (to_smem) {
                             sts_a8<false>(A_hi, A_lo, row, kc, hv, hh2, ll2);
                             publish_chunk(&a_ready[it], lane);
+                            if (TL && tlw && it == 0) tlw[2] = tl_clock();
                         } else {
 #pragma unroll
                             for (int i = 0; i < 4; ++i) split_bf16x2(hv[2 * i], hv[2 * i + 1], hh2[i], ll2[i]);
                         }
+                        if (TL && tli) tli[it * 5 + 3] = tl_clock();
                         if (gs) {
                             if (adj_slot) stg_a8<true, planes::kPlanesAdj>(gs, (uint32_t)planes::BIG_PLANE, keep, hv, hh2, ll2);
                             else stg_a8<true, planes::kPlanesHD>(gs, (uint32_t)planes::BIG_PLANE, keep, hv, hh2, ll2);
                         }
+                        if (TL && tli) tli[it * 5 + 4] = tl_clock();
                     }
+                    if (TL && tlw) tlw[3] = tl_clock();
                 };
-                switch (kind) {
-                    case BK_TAN:
-                        if (l == NL - 1) items(std::integral_constant<int, KB_TAN_LAST>{});
-                        else if (l + 1 == net.skip) items(std::integral_constant<int, KB_TAN_SKIP>{});
-                        else items(std::integral_constant<int, KB_TAN>{});
-                        break;
-                    case BK_COL_REV: items(std::integral_constant<int, KB_COL_REV>{}); break;
-                    case BK_FEAT_ADJ: items(std::integral_constant<int, KB_FEAT_ADJ>{}); break;
-                    default:
-                        if (l == NL - 1) items(std::integral_constant<int, KB_P_TOP>{});
-                        else if (l + 1 == net.skip) items(std::integral_constant<int, KB_P_SKIP>{});
-                        else items(std::integral_constant<int, KB_P>{});
-                        break;
-                }
+                dispatch(items);
             }
         }
     }
@@ -365,6 +417,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_bwd8_kernel(const BwdParams P,
 
 }  // namespace tcb
 
+static long long* g_bwd_tl = nullptr;       // development probe buffer (I2SDF_DEBUG_TIMELINE)
+
+// copies the probe's stamps to the host (after a synchronize); returns the number of int64 copied, 0 if the probe never ran
+long long tc_bwd_timeline_read(long long* out, long long n) {
+    if (!g_bwd_tl || !out || n <= 0) return 0;
+    if (n > 8192) n = 8192;
+    if (cudaMemcpy(out, g_bwd_tl, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return n;
+}
+
 int tc_bwd_launch(const i2sdf_handle* h, const BwdParams& p, cudaStream_t st) {
     using namespace tcb;
     if (p.M <= 0) return I2SDF_OK;
@@ -372,14 +434,25 @@ int tc_bwd_launch(const i2sdf_handle* h, const BwdParams& p, cudaStream_t st) {
     if (!tab || tab->nops == 0) { set_error("tc_bwd_launch: no backward op table for this network"); return I2SDF_E_INVALID; }
     // (per device: cudaFuncSetAttribute is a per-device setting)
     static PerDeviceOnce once;
-    if (once.need()) I2SDF_CUDA_CHECK(cudaFuncSetAttribute(tc_bwd8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBwd8));
+    if (once.need()) {
+        I2SDF_CUDA_CHECK(cudaFuncSetAttribute(tc_bwd8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBwd8));
+        I2SDF_CUDA_CHECK(cudaFuncSetAttribute(tc_bwd8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBwd8));
+    }
     const long long ntiles = (p.M + chain::TM - 1) / chain::TM;
     const int grid = balanced_grid(h->num_sms, ntiles);
     // L2 prefetch distance of the slot segments: 1..7 = that many 8-column items ahead, 8 = one whole op ahead, 0 = off
     static const int pf = [] { const char* e = getenv("I2SDF_BWD_PREFETCH"); const int v = e ? atoi(e) : kBwdPrefetchDefault; return (v < 0 || v > 8) ? kBwdPrefetchDefault : v; }();
     BwdParams q = p;
     q.pf_dist = pf;
-    tc_bwd8_kernel<<<grid, chain::NTHREADS, kSmemBwd8, st>>>(q, *tab);
+    static const bool tl_on = getenv("I2SDF_DEBUG_TIMELINE") != nullptr;
+    if (tl_on) {
+        if (!g_bwd_tl) { I2SDF_CUDA_CHECK(cudaMalloc(&g_bwd_tl, 65536)); I2SDF_CUDA_CHECK(cudaMemset(g_bwd_tl, 0, 65536)); }
+        q.tl = g_bwd_tl;
+        tc_bwd8_kernel<true><<<grid, chain::NTHREADS, kSmemBwd8, st>>>(q, *tab);
+    } else {
+        q.tl = nullptr;
+        tc_bwd8_kernel<false><<<grid, chain::NTHREADS, kSmemBwd8, st>>>(q, *tab);
+    }
     I2SDF_CUDA_CHECK(cudaGetLastError());
     return I2SDF_OK;
 }

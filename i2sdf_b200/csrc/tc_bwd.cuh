@@ -31,6 +31,7 @@ struct BwdParams {
     const float* g_rgb;    // [M][3]   (with_color)
     const float* s_rgb;    // [M][3]   forward rgb (sigmoid output), for its derivative
     int with_color;
+    long long* tl;         // development probe (I2SDF_DEBUG_TIMELINE, tools/timeline.py bwd): 64 KB of clock64 stamps of CTA 0's second tile
     int pf_dist;           // slot segments are prefetched into L2 this many 16-column items ahead (set by tc_bwd_launch)
     planes::Layout sl;     // saved forward slots (sl.base) + backward workspace slots (sl.wbase)
     NetDev net;
@@ -38,5 +39,6 @@ struct BwdParams {
 
 const chain::OpTable* tc_bwd_table(const i2sdf_handle* h, bool with_color);
 int tc_bwd_launch(const i2sdf_handle* h, const BwdParams& p, cudaStream_t st);
+long long tc_bwd_timeline_read(long long* out, long long n);
 
 }  // namespace i2sdf

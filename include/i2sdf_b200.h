@@ -260,6 +260,10 @@ int i2sdf_profile_read(i2sdf_handle* h, float ms[4], int64_t launches[4]);
 /* same with n <= 8 classes: 4 = backward chain kernel (fused training path), 5 = weight-gradient kernel,
  * 6 = light-mask head (forward pass over the features + its backward). */
 int i2sdf_profile_read_n(i2sdf_handle* h, int n, float* ms, int64_t* launches);
+/* Development probe (no reference counterpart): with I2SDF_DEBUG_TIMELINE set in the environment the backward chain kernel stamps clock64
+ * values of one CTA's second tile into a device buffer (csrc/mlp_tc_bwd.cu: tc_bwd8_kernel<true>); this copies up to n int64 of it to the
+ * host (synchronous) and returns how many were copied, 0 if the probe never ran.  tools/timeline.py bwd prints the table. */
+int64_t i2sdf_debug_bwd_timeline(int64_t* out, int64_t n);
 
 /* What a forward in training mode saves for the backward.  format 1 = plane slots (tensor-core chain kernels; consumed
  * by i2sdf_fused_backward), 0 = fp32 pre-activations [L-1][M][256] (fp32 kernels; consumed by i2sdf_sdf_backward /
