@@ -65,7 +65,8 @@ def test_camera_rays_match_the_oracle(layout):
         e_d = float((d.cpu() - d_ref).abs().max())                          # unit vectors: absolute = relative
         e_n = float(((dn.cpu() - n_ref).abs() / n_ref).max())
         worst = max(worst, e_d, e_n)
-        # the 4-term dot products of the pose multiply are summed in a different order than the CPU bmm: a few ulp
+        # the 4-term dot products of the pose multiply are summed in a different order than the CPU bmm: a few ulp (measured: 0 with one
+        # camera, 4.5e-7 with a camera per ray)
         assert e_d < 2e-6 and e_n < 2e-6, (layout, R, e_d, e_n)
         assert float((d.norm(dim=-1) - 1).abs().max()) < 1e-6
     print(f"rays ({layout} layout): worst |d - d_ref| / dnorm rel err {worst:.2e}")
@@ -126,7 +127,9 @@ def test_training_sampler_on_the_reference_tape(name):
     close_hit = float(((zc - ref).abs() < 1e-3)[hit].float().mean()) if hit.any() else 1.0
     print(f"{name}: training sampler on the reference tape: z within 1e-3 of the reference: {close_hit:.4f} of surface-hitting rays' samples, "
           f"{close_all:.4f} of all; rounds {int(info[0])}")
-    assert close_hit > 0.9 and close_all > 0.85, (close_hit, close_all)
+    # measured: 1.0000 of the surface-hitting rays' samples on both fixtures, 0.9866 / 0.9767 of all (rays that miss the surface have a
+    # noise-dominated up-sampling pdf, see test_sampler_rounds_on_identical_inputs)
+    assert close_hit > 0.97 and close_all > 0.93, (close_hit, close_all)
 
 
 def test_whole_image_driver_at_full_resolution():
@@ -186,7 +189,7 @@ def test_training_mode_predict_only_is_the_early_dict(name):
         assert out[k].shape == c.ref[k].shape, k
         e = relerr(out[k], c.ref[k])
         worst = max(worst, e)
-        assert e < 2e-4, (k, e)                                           # same bound as test_training_step_on_reference_z
+        assert e < 1e-4, (k, e)                                           # measured 3.7e-6 / 2.8e-6
     out["rgb_values"].sum().backward()                                   # still differentiable, as in the reference (no torch.no_grad around it)
     assert m.rendering_network.lin0.weight_v.grad is not None and bool(torch.isfinite(m.rendering_network.lin0.weight_v.grad).all())
     # and through the module's own sampler (fresh device draws): same keys, finite
