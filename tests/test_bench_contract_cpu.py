@@ -33,6 +33,9 @@ def _check_common(d):
 
 
 def test_committed_gpu_bench_lines_keep_the_contract():
+    sys.path.insert(0, ROOT)
+    import bench
+    from i2sdf_b200 import configs
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r02*_bench_train*.json")))
     assert files, "no round-2 bench line under profiles/"
     for f in files:
@@ -53,7 +56,8 @@ def test_committed_gpu_bench_lines_keep_the_contract():
         assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
         # achieved = ALGORITHMIC flops per launch / measured launch time (never the 3x the tensor cores execute)
         assert abs(r["achieved"] - r["flop_per_launch"] / (r["ms_per_launch"] * 1e-3) / 1e12) < 1e-6 * r["achieved"]
-        assert r["flop_per_launch"] == d["config"]["rays_per_gpu"] * 128 * 918016
+        sdf_eval = bench.flop_model(configs.model_conf(d["config"]["network_config"]))["sdf_eval"]      # 918 016 for synthetic.yml
+        assert r["flop_per_launch"] == d["config"]["rays_per_gpu"] * 128 * sdf_eval
         c = d["clocks"]
         assert c["sm_mhz"] > 0 and c["sm_max_mhz"] >= c["sm_mhz"]
         assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(c["reasons"]), f
