@@ -175,3 +175,139 @@ def test_training_forward_ragged_count_with_replayed_rng():
     for k in ref:
         e = float((out[k].detach() - ref[k]).abs().max() / ref[k].abs().max().clamp(min=1e-12))
         assert e < 5e-5, (k, e)
+
+
+import contextlib
+
+
+@contextlib.contextmanager
+def _plot_stubs():
+    """utils/plots.py and the dataset package import plotting / meshing packages that are absent from this image and unused by the
+    functions under test: empty stand-ins for the duration of one test."""
+    import importlib
+    import sys
+    import types
+    made = []
+    for name, attrs in (("plotly", {}), ("plotly.graph_objs", {}), ("plotly.offline", {}), ("plotly.subplots", {"make_subplots": None}),
+                        ("skimage", {}), ("skimage.measure", {}), ("trimesh", {}), ("mcubes", {})):
+        try:
+            importlib.import_module(name)
+        except Exception:
+            mod = types.ModuleType(name)
+            mod.__dict__.update(attrs)
+            sys.modules[name] = mod
+            made.append(name)
+    for name in made:                                    # `from skimage import measure`, `import plotly.graph_objs as go`
+        if "." in name:
+            parent, child = name.rsplit(".", 1)
+            setattr(sys.modules[parent], child, sys.modules[name])
+    try:
+        yield
+    finally:
+        for name in made:
+            sys.modules.pop(name, None)
+        for name in [n for n in sys.modules if n == "utils.plots" or n == "dataset" or n.startswith("dataset.")]:
+            sys.modules.pop(name, None)
+
+
+def test_grid_builders_equal_the_references(monkeypatch):
+    """§8(f)-3 host side: i2sdf_b200.grid's axes / point order == utils/plots.py get_grid_uniform / get_grid (:440-489), run live.
+    plots.py imports plotting / meshing packages that are absent here and calls .cuda() on the point list: the former are stubbed
+    (none is used by the two builders), the latter is made the identity for the duration of the test."""
+    import importlib
+    from i2sdf_b200.grid import grid_axes_from_points, grid_axes_uniform, grid_points
+    ref_shim.load()
+    with _plot_stubs():
+        plots = importlib.import_module("utils.plots")
+        monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+        ref = plots.get_grid_uniform(17, [-1.5, 2.5])
+        x, y, z = grid_axes_uniform(17, (-1.5, 2.5))
+        for a, b in zip((x, y, z), ref["xyz"]):
+            assert np.array_equal(a, b)
+        assert torch.equal(grid_points(x, y, z), ref["grid_points"])
+        g = torch.Generator().manual_seed(2)
+        for scale in ((1.0, 2.0, 3.0), (3.0, 0.7, 2.0), (2.0, 3.0, 0.4)):      # shortest axis 0, 1, 2
+            cloud = (torch.rand(200, 3, generator=g) - 0.5) * torch.tensor(scale)
+            ref = plots.get_grid(cloud, 13)
+            (ax, ay, az), length, sa = grid_axes_from_points(cloud, 13)
+            assert sa == ref["shortest_axis_index"] and length == ref["shortest_axis_length"]
+            for a, b in zip((ax, ay, az), ref["xyz"]):
+                assert np.array_equal(a, b)
+            assert torch.equal(grid_points(ax, ay, az), ref["grid_points"])
+
+
+@pytest.mark.parametrize("conf_name", ["synthetic", "synthetic_light_mask"])
+def test_drop_in_module_constructs_the_references_parameters(conf_name):
+    """Boundary (§8(b)), live: under the same seed i2sdf_b200.network.I2SDFNetwork draws the same numbers in the same order as the
+    reference constructor - every tensor of state_dict() bit-identical, same key order, same parameter order in get_param_groups -
+    and afterwards the global generator stands where the reference's does; the reference's checkpoint loads with strict=True."""
+    from i2sdf_b200 import configs
+    from i2sdf_b200.network import I2SDFNetwork
+    net, _ = ref_shim.load()
+    for seed in (0, 42):
+        conf = ref_shim.load_conf(conf_name + ".yml")
+        conf.model.use_normal = True
+        torch.manual_seed(seed)
+        ref = net.I2SDFNetwork(conf.model)
+        after_ref = torch.rand(4)
+        mc = configs.model_conf(conf_name)
+        mc["use_normal"] = True
+        torch.manual_seed(seed)
+        mine = I2SDFNetwork(mc)
+        after_mine = torch.rand(4)
+        sr, sm = ref.state_dict(), mine.state_dict()
+        assert list(sr.keys()) == list(sm.keys())
+        for k in sr:
+            assert sr[k].shape == sm[k].shape and torch.equal(sr[k], sm[k]), k
+        assert torch.equal(after_ref, after_mine)
+        pr = [p.shape for p in ref.get_param_groups(5e-4)[0]["params"]]
+        pm = [p.shape for p in mine.get_param_groups(5e-4)[0]["params"]]
+        assert pr == pm and mine.get_param_groups(5e-4)[0]["lr"] == 5e-4
+        with torch.no_grad():
+            for p in ref.parameters():
+                p.add_(0.01)
+        res = mine.load_state_dict(ref.state_dict(), strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+        assert mine.use_light == ref.use_light and mine.use_normal == ref.use_normal
+
+
+def test_ray_feed_equals_the_references_dataset_items_and_collate():
+    """§8(f)-4, live: RayFeed.from_dataset(ds).gather(idx) == ds.collate_fn([ds[i] for i in idx]) with the reference's OWN
+    ReconDataset.__getitem__ / collate_fn (dataset/train_dataset.py:169-209).  The constructor reads a scene from disk, so the
+    instance is made without it and given the attributes the constructor fills (:42-167); every combination of use_* flags."""
+    import importlib
+    from i2sdf_b200.feed import RayFeed
+    ref_shim.load()
+    with _plot_stubs():
+        td = importlib.import_module("dataset.train_dataset")
+        ReconDataset = td.ReconDataset
+    g = torch.Generator().manual_seed(4)
+    n_img, h, w = 3, 4, 6
+    hw = h * w
+    uv = np.mgrid[0:h, 0:w].astype(np.int32)                              # as the constructor builds it (:71-74)
+    uv = torch.from_numpy(np.flip(uv, axis=0).copy()).float().reshape(2, -1).transpose(1, 0)
+    for use_mask, use_light, use_depth, use_bubble, use_normal in ((False, False, False, False, False), (True, True, True, False, True),
+                                                                   (False, False, False, True, False), (False, True, True, True, True)):
+        ds = object.__new__(ReconDataset)
+        ds.n_images, ds.total_pixels, ds.uv = n_img, hw, uv
+        ds.use_mask, ds.use_lightmask, ds.use_depth, ds.use_bubble, ds.use_normal = use_mask, use_light, use_depth, use_bubble, use_normal
+        ds.intrinsics_all = torch.rand(n_img, 4, 4, generator=g)            # stacked, as the constructor leaves them (:54-55)
+        ds.pose_all = torch.rand(n_img, 4, 4, generator=g)
+        ds.rgb_images = torch.rand(n_img, hw, 3, generator=g)
+        ds.mask_images = (torch.rand(n_img, hw, 1, generator=g) > 0.5).float()
+        ds.lightmask_images = (torch.rand(n_img, hw, 1, generator=g) > 0.8).float()
+        ds.depth_images = torch.rand(n_img, hw, generator=g) * 6
+        ds.depth_masks = torch.rand(n_img, hw, generator=g) > 0.3
+        ds.normal_images = torch.nn.functional.normalize(torch.randn(n_img, hw, 3, generator=g), dim=-1)
+        ds.normal_masks = torch.rand(n_img, hw, generator=g) > 0.2
+        assert len(ds) == n_img * hw
+        idx = torch.tensor([0, 5, 23, 24, 47, 71, 30, 30])
+        ref = ds.collate_fn([ds[int(i)] for i in idx])
+        feed = RayFeed.from_dataset(ds, "cpu")
+        assert len(feed) == len(ds)
+        got = feed.gather(idx)
+        assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]) and got[0].dtype == ref[0].dtype
+        for a, b in ((got[2], ref[2]), (got[3], ref[3])):
+            assert set(a) == set(b), (set(a), set(b))
+            for k in b:
+                assert a[k].shape == b[k].shape and a[k].dtype == b[k].dtype and torch.equal(a[k], b[k]), k
