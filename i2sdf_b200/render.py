@@ -25,7 +25,9 @@ def pixel_grid(img_res: Sequence[int], device=None) -> torch.Tensor:
 @torch.no_grad()
 def render_image(model, pose: torch.Tensor, intrinsics: torch.Tensor, img_res: Sequence[int], split_n_pixels: int = 65536,
                  predict_only: bool = False, group=None, assemble: bool = True) -> Dict[str, torch.Tensor]:
-    """Render one full view.  pose, intrinsics: [4,4] (or [1,4,4]).  Returns {key: [H*W, C]} like merge_output.
+    """Render one full view.  pose, intrinsics: [4,4] (or [1,4,4]).  Returns {key: [H*W, C]}: merge_output's dict, except that the
+    entries it leaves 1-D (depth_values [H*W], utils/__init__.py:76-78) come back as [H*W, 1] - its callers reshape them to
+    (1, H*W, 1) right away (model/eval/recon.py:181-182).
 
     group (torch.distributed process group): the view's chunks are dealt to the ranks round-robin — chunk i of the single-GPU
     loop goes to rank i % world, so every chunk is the SAME set of rays as without sharding and (the sampler's convergence test

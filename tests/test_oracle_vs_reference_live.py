@@ -311,3 +311,102 @@ def test_ray_feed_equals_the_references_dataset_items_and_collate():
             assert set(a) == set(b), (set(a), set(b))
             for k in b:
                 assert a[k].shape == b[k].shape and a[k].dtype == b[k].dtype and torch.equal(a[k], b[k]), k
+
+
+def test_whole_image_driver_equals_the_references_chunk_loop():
+    """§8(f)-2, live: render_image == PlotDataset.get_uv -> utils.split_input -> model(s) per chunk -> utils.merge_output
+    (dataset/eval_dataset.py:143-147, utils/__init__.py:35-84, model/eval/recon.py:161-179) around the same stand-in model whose
+    outputs depend on the ray and on the whole chunk.  Only difference: merge_output leaves 1-D entries 1-D (see render_image)."""
+    import importlib
+    from i2sdf_b200.render import render_image
+    _, ref_utils = ref_shim.load()
+
+    class Model:
+        training = False
+
+        class density:                      # noqa: N801
+            beta = torch.zeros(())
+
+        def __call__(self, inp, predict_only=False):
+            uv = inp["uv"][0]
+            stat = uv.sum() * 1e-3          # chunk-global, like the sampler's convergence test
+            rgb = torch.stack([uv[:, 0], uv[:, 1], uv[:, 0] * 0 + stat], -1) + inp["pose"][0, 0, 3] + inp["intrinsics"][0, 1, 2]
+            return {"rgb_values": rgb, "depth_values": uv[:, 0] - uv[:, 1], "weight_sum": (uv[:, :1] > 2).float(), "normal_map": rgb * 0.5}
+
+    with _plot_stubs():
+        ed = importlib.import_module("dataset.eval_dataset")
+        PlotDataset = ed.PlotDataset
+    pose, K = torch.eye(4), torch.eye(4)
+    pose[0, 3], K[1, 2] = 0.25, 3.0
+    for (H, W), split in (((7, 9), 13), ((4, 5), 100), ((6, 6), 12)):
+        ds = object.__new__(PlotDataset)
+        ds.img_res = [H, W]
+        model_input = {"uv": ds.get_uv()[None], "pose": pose[None], "intrinsics": K[None]}
+        res = [ref_utils.detach_dict(Model()(s)) for s in ref_utils.split_input(model_input, H * W, n_pixels=split)]
+        ref = ref_utils.merge_output(res, H * W, 1)
+        got = render_image(Model(), pose, K, (H, W), split_n_pixels=split)
+        assert set(got) == set(ref)
+        for k, v in ref.items():
+            assert got[k].shape == (H * W, 1 if v.dim() == 1 else v.shape[1]), k
+            assert torch.equal(got[k].reshape(v.shape), v), k
+
+
+def test_bubble_pdf_equals_the_trainers_methods():
+    """§8(f)-4, live: BubblePDF.update_pdf / sample_bubble == ReconstructionTrainer.update_pdf / sample_bubble
+    (model/trainer/recon.py:142-170) called as plain functions on a stand-in `self` (the Lightning module itself needs packages this
+    image lacks; the two methods only touch self.pdf / sample_count / pdf_max / pdf_prune / uniform_bubble and the dataset's
+    pointcloud / pointlinks).  Same global generator state -> same multinomial / randperm draws, same counts."""
+    import importlib
+    import sys
+    import types
+    from i2sdf_b200.feed import BubblePDF
+    ref_shim.load()
+    made, patched = [], []
+
+    class _Dummy:
+        def __init__(self, *a, **k):
+            pass
+    pl = sys.modules["pytorch_lightning"]
+    if not hasattr(pl, "LightningModule"):
+        pl.LightningModule = torch.nn.Module
+        patched.append("LightningModule")
+    for name, attrs in (("torchmetrics", {}), ("torchmetrics.functional", {"structural_similarity_index_measure": None}),
+                        ("torchmetrics.image", {}), ("torchmetrics.image.lpip", {"LearnedPerceptualImagePatchSimilarity": _Dummy})):
+        try:
+            importlib.import_module(name)
+        except Exception:
+            mod = types.ModuleType(name)
+            mod.__dict__.update(attrs)
+            sys.modules[name] = mod
+            made.append(name)
+    try:
+        with _plot_stubs():
+            Trainer = importlib.import_module("model.trainer.recon").ReconstructionTrainer
+        g = torch.Generator().manual_seed(8)
+        n_pts, n_pix = 50, 200
+        cloud = torch.rand(n_pts, 3, generator=g)
+        links = torch.randint(-1, n_pts, (n_pix,), generator=g)
+        for pdf_max, prune, uniform in ((None, 0.0, False), (0.6, 0.2, False), (None, 0.0, True)):
+            me = types.SimpleNamespace(bubble_activated=True, pdf_max=pdf_max, pdf_prune=prune, uniform_bubble=uniform,
+                                       train_dataset=types.SimpleNamespace(pointcloud=cloud, pointlinks=links),
+                                       pdf=torch.zeros(n_pts), sample_count=torch.zeros(n_pts))
+            mine = BubblePDF(cloud, links, pdf_prune=prune, pdf_max=pdf_max, uniform=uniform)
+            for _ in range(3):
+                idx = torch.randint(0, n_pix, (64,), generator=g)
+                val = torch.rand(64, generator=g)
+                Trainer.update_pdf(me, val.clone(), idx)
+                mine.update_pdf(val.clone(), idx)
+                assert torch.equal(mine.pdf, me.pdf)
+            torch.manual_seed(123)
+            a = Trainer.sample_bubble(me, 16)
+            torch.manual_seed(123)
+            b = mine.sample_bubble(16)
+            assert torch.equal(a, b)
+            assert torch.equal(mine.sample_count.float(), me.sample_count)
+    finally:
+        for name in made:
+            sys.modules.pop(name, None)
+        for name in [n for n in sys.modules if n.startswith("model.trainer")]:
+            sys.modules.pop(name, None)
+        for a in patched:
+            delattr(pl, a)
