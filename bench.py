@@ -764,8 +764,10 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        # the CPU baseline runs with the GPUs idle and the other ranks gone
-        line = add_cpu_baseline(line, args, *cpu)
+        # the CPU baseline runs with the GPUs idle, at N = 1 only (the same host cores at every N: the multi-GPU lines of a scaling run
+        # would just repeat it, ~25 s each)
+        if world == 1:
+            line = add_cpu_baseline(line, args, *cpu)
         sys.stdout.flush()
         print(json.dumps(line), flush=True)
 
