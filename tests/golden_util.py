@@ -59,3 +59,23 @@ def relerr(a, b):
     """max |a-b| / max |b|  — the parity metric used throughout (north_star: 1e-4 relative fp32)."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
+
+
+def general_cameras(B, g):
+    """B cameras with a proper rotation (not the identity of the synthetic batches), a translation, per-camera focal lengths,
+    principal points and a NON-ZERO skew: every term of rend_util.py:143-144 is exercised.  -> pose [B,4,4], intrinsics [B,4,4]."""
+    q = torch.nn.functional.normalize(torch.randn(B, 4, generator=g), dim=-1)
+    w, x, y, z = q.unbind(-1)
+    Rm = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                      2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                      2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1).reshape(B, 3, 3)
+    pose = torch.eye(4).repeat(B, 1, 1)
+    pose[:, :3, :3] = Rm
+    pose[:, :3, 3] = torch.randn(B, 3, generator=g) * 2.0
+    K = torch.eye(4).repeat(B, 1, 1)
+    K[:, 0, 0] = 250.0 + 100.0 * torch.rand(B, generator=g)
+    K[:, 1, 1] = 250.0 + 100.0 * torch.rand(B, generator=g)
+    K[:, 0, 2] = 150.0 + 20.0 * torch.rand(B, generator=g)
+    K[:, 1, 2] = 110.0 + 20.0 * torch.rand(B, generator=g)
+    K[:, 0, 1] = torch.randn(B, generator=g) * 0.5
+    return pose, K

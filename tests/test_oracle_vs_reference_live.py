@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 import torch
 
+from golden_util import general_cameras
 from oracle import i2sdf_oracle as orc
 from oracle import ref_shim
 
@@ -40,24 +41,6 @@ def _ref_model(conf_name, training, beta, seed=0, perturb=0.05):
     return net, m, spec, P
 
 
-def _cameras(B, g):
-    q = torch.nn.functional.normalize(torch.randn(B, 4, generator=g), dim=-1)
-    w, x, y, z = q.unbind(-1)
-    Rm = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
-                      2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
-                      2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1).reshape(B, 3, 3)
-    pose = torch.eye(4).repeat(B, 1, 1)
-    pose[:, :3, :3] = Rm
-    pose[:, :3, 3] = torch.randn(B, 3, generator=g) * 2.0
-    K = torch.eye(4).repeat(B, 1, 1)
-    K[:, 0, 0] = 250.0 + 100.0 * torch.rand(B, generator=g)
-    K[:, 1, 1] = 250.0 + 100.0 * torch.rand(B, generator=g)
-    K[:, 0, 2] = 150.0 + 20.0 * torch.rand(B, generator=g)
-    K[:, 1, 2] = 110.0 + 20.0 * torch.rand(B, generator=g)
-    K[:, 0, 1] = torch.randn(B, generator=g) * 0.5
-    return pose, K
-
-
 def test_rays_with_general_cameras_and_skew_are_the_references_bits():
     """oracle.camera_rays / flatten_rays == rend_util.get_camera_params + the flatten / normalise of I2SDFNetwork.forward
     (utils/rend_util.py:92-147, model/network/__init__.py:86-93), bit for bit, with rotations, per-camera intrinsics and skew."""
@@ -65,7 +48,7 @@ def test_rays_with_general_cameras_and_skew_are_the_references_bits():
     rend_util = ref_utils.rend_util if hasattr(ref_utils, "rend_util") else __import__("utils.rend_util", fromlist=["x"])
     g = torch.Generator().manual_seed(3)
     for B, Pn in ((1, 1), (1, 257), (33, 1), (5, 7)):
-        pose, K = _cameras(B, g)
+        pose, K = general_cameras(B, g)
         uv = torch.rand(B, Pn, 2, generator=g) * torch.tensor([320.0, 240.0])
         dirs_ref, cam_ref = rend_util.get_camera_params(uv, pose, K)
         dirs, cam = orc.camera_rays(uv, pose, K)
@@ -108,7 +91,7 @@ def test_eval_forward_fresh_seeds_and_ragged_counts(conf_name, beta, R, seed):
     net, m, spec, P = _ref_model(conf_name, False, beta, seed=seed)
     inp = orc.synthetic_rays(R, seed=seed)
     g = torch.Generator().manual_seed(seed)
-    pose, K = _cameras(1, g)                            # a rotated camera looking at the sphere from 1.6 away, with skew
+    pose, K = general_cameras(1, g)                            # a rotated camera looking at the sphere from 1.6 away, with skew
     pose[0, :3, 3] = -1.6 * pose[0, :3, 2]
     K[0, 0, 1] = 0.3
     inp = {"uv": inp["uv"], "pose": pose, "intrinsics": K}

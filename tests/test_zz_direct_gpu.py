@@ -6,7 +6,7 @@ Named to sort last: the suite runs with `-x`, and these are the newest tests.  S
 import pytest
 import torch
 
-from golden_util import TRAIN_CASES, Case, relerr
+from golden_util import TRAIN_CASES, Case, general_cameras, relerr
 from oracle import i2sdf_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -23,26 +23,6 @@ def _model(case, training=False):
     return m
 
 
-def _general_cameras(B, g):
-    """B cameras with a proper rotation (not the identity of the synthetic batches), a translation, per-camera focal lengths,
-    principal points and a NON-ZERO skew: every term of rend_util.py:143-144 is exercised."""
-    q = torch.nn.functional.normalize(torch.randn(B, 4, generator=g), dim=-1)
-    w, x, y, z = q.unbind(-1)
-    Rm = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
-                      2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
-                      2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1).reshape(B, 3, 3)
-    pose = torch.eye(4).repeat(B, 1, 1)
-    pose[:, :3, :3] = Rm
-    pose[:, :3, 3] = torch.randn(B, 3, generator=g) * 2.0
-    K = torch.eye(4).repeat(B, 1, 1)
-    K[:, 0, 0] = 250.0 + 100.0 * torch.rand(B, generator=g)
-    K[:, 1, 1] = 250.0 + 100.0 * torch.rand(B, generator=g)
-    K[:, 0, 2] = 150.0 + 20.0 * torch.rand(B, generator=g)
-    K[:, 1, 2] = 110.0 + 20.0 * torch.rand(B, generator=g)
-    K[:, 0, 1] = torch.randn(B, generator=g) * 0.5
-    return pose, K
-
-
 @pytest.mark.parametrize("layout", ["eval", "train"])
 def test_camera_rays_match_the_oracle(layout):
     """Row a1: i2sdf_rays == get_camera_params + lift + the flatten / normalise of I2SDFNetwork.forward
@@ -53,10 +33,10 @@ def test_camera_rays_match_the_oracle(layout):
     worst = 0.0
     for R in (1, 37, 1024, 4099):
         if layout == "eval":             # one camera, P = R pixels (dataset/eval_dataset.py:150-168)
-            pose, K = _general_cameras(1, g)
+            pose, K = general_cameras(1, g)
             uv = (torch.rand(1, R, 2, generator=g) * torch.tensor([320.0, 240.0]))
         else:                            # one camera per ray, P = 1 (dataset/train_dataset.py:169-192)
-            pose, K = _general_cameras(R, g)
+            pose, K = general_cameras(R, g)
             uv = (torch.rand(R, 1, 2, generator=g) * torch.tensor([320.0, 240.0]))
         o_ref, d_ref, n_ref = orc.flatten_rays(uv, pose, K)
         o, d, dn = core.rays(uv.cuda(), pose.cuda(), K.cuda())
