@@ -7,7 +7,9 @@ spatial gradient) of the reference algorithm, each function citing the reference
 
 Pinning: tests/golden/*.npz were produced by tests/golden/make_golden.py, which runs the UNMODIFIED
 reference (imported read-only through oracle/ref_shim.py) and this oracle on identical weights/rays and
-records both; tests/test_oracle_golden.py re-checks the oracle against those reference outputs on every run.
+records both; tests/test_oracle_golden.py re-checks the oracle against those reference outputs on every run, and
+tests/test_oracle_vs_reference_live.py runs the reference LIVE beside the oracle wherever the reference tree exists
+(fresh seeds, ragged ray counts, rotated cameras with skew, stage-wise rays / embeddings / density / error bound).
 The reference itself ships no tests or golden vectors, so "reference outputs generated
 here" is the strongest pin available.
 
